@@ -1,0 +1,19 @@
+// C-ABI housekeeping: version, thread-local last error.
+#include "common.cuh"
+#include <stdarg.h>
+
+static thread_local char g_err[512] = "";
+
+void ysod_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" {
+int ysod_version(void) { return 100; }
+const char* ysod_last_error(void) { return g_err; }
+// Which device architecture the library was compiled for (sm_100a only).
+int ysod_compiled_arch(void) { return 100; }
+}

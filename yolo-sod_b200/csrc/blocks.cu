@@ -1,0 +1,672 @@
+// Memory-bound blocks of the MAFN neck: SE, CBAM (channel + spatial), CoordAtt, SPPF pooling, nearest upsample /
+// slice copy, LayerNorm, Swin window partition / reverse, A2 adaptive pooling + bilinear row upsample.
+//
+// Replaces (reference, ~5-12 ATen kernels each):
+//   SE            ultralytics/nn/modules/smallobj_modules.py:57-92
+//   CBAM_Block    ultralytics/nn/modules/cbam_block.py:8-55
+//   CA_Block      ultralytics/nn/modules/ca_block.py:16-59
+//   SPPF pooling  ultralytics/nn/modules/block.py:178-197  (three chained 5x5/s1 max-pools == 5x5, 9x9, 13x13 windows)
+//   Upsample/Concat  nn.Upsample(nearest,2) + conv.py:323-334 Concat (producers write channel slices instead)
+//   window_partition / window_reverse / LayerNorm   blocks_transformer.py:8-79,98-131
+//   A2_Attn pooling + bilinear  a2_attn.py:44-60
+// All are HBM-bound: NHWC, 8 channels (16 B of bf16) per thread access, fp32 math, warp-shuffle / shared-memory
+// reductions, deterministic two-stage global reductions (no float atomics).
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------
+// global average / max pool, stage 1: partial[n][s][c] over a pixel range
+template <typename T>
+__global__ void gap_partial_kernel(const T* __restrict__ x, int HW, int C, int xcs, int S, float* __restrict__ psum,
+                                   float* __restrict__ pmax) {
+    extern __shared__ float sm[];  // [PL][C] sums, then [PL][C] maxes
+    const int n = blockIdx.y, s = blockIdx.x;
+    const int c8n = C >> 3;
+    const int PL = blockDim.x / c8n;
+    const int cg = threadIdx.x % c8n, pl = threadIdx.x / c8n;
+    const int chunk = (HW + S - 1) / S;
+    const int p0 = s * chunk, p1 = min(HW, p0 + chunk);
+    float su[8], mx[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { su[e] = 0.f; mx[e] = -INFINITY; }
+    if (pl < PL) {
+        for (int p = p0 + pl; p < p1; p += PL) {
+            float v[8];
+            ysod_vec8<T>::load(x + ((size_t)n * HW + p) * xcs + cg * 8, v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { su[e] += v[e]; mx[e] = fmaxf(mx[e], v[e]); }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            sm[pl * C + cg * 8 + e] = su[e];
+            sm[(PL + pl) * C + cg * 8 + e] = mx[e];
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f, m = -INFINITY;
+        for (int q = 0; q < PL; ++q) { a += sm[q * C + c]; m = fmaxf(m, sm[(PL + q) * C + c]); }
+        psum[((size_t)n * S + s) * C + c] = a;
+        if (pmax) pmax[((size_t)n * S + s) * C + c] = m;
+    }
+}
+
+// SE gate: mean -> fc1(+bias) -> ReLU -> fc2(+bias) -> sigmoid. One CTA per image. fp32 as in the reference (:81-91).
+__global__ void se_gate_kernel(const float* __restrict__ psum, int S, int HW, int C, const float* __restrict__ w1,
+                               const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2, int hid,
+                               float* __restrict__ gate) {
+    extern __shared__ float sm[];  // mean[C], h[hid]
+    float* mean = sm;
+    float* h = sm + C;
+    const int n = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f;
+        for (int s = 0; s < S; ++s) a += psum[((size_t)n * S + s) * C + c];
+        mean[c] = a / (float)HW;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int j = warp; j < hid; j += nw) {
+        float a = 0.f;
+        for (int c = lane; c < C; c += 32) a = fmaf(w1[(size_t)j * C + c], mean[c], a);
+        a = ysod_warp_sum(a);
+        if (lane == 0) h[j] = fmaxf(a + b1[j], 0.f);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = b2[c];
+        for (int j = 0; j < hid; ++j) a = fmaf(w2[(size_t)c * hid + j], h[j], a);
+        gate[(size_t)n * C + c] = ysod_sigmoid(a);
+    }
+}
+
+// CBAM channel gate: sigmoid(fc(avg) + fc(max)), fc = conv1x1(no bias) -> ReLU -> conv1x1(no bias) (cbam_block.py:14-23)
+__global__ void cbam_gate_kernel(const float* __restrict__ psum, const float* __restrict__ pmax, int S, int HW, int C,
+                                 const float* __restrict__ w1, const float* __restrict__ w2, int hid, float* __restrict__ gate) {
+    extern __shared__ float sm[];  // avg[C], mx[C], ha[hid], hm[hid]
+    float* avg = sm;
+    float* mx = sm + C;
+    float* ha = sm + 2 * C;
+    float* hm = ha + hid;
+    const int n = blockIdx.x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f, m = -INFINITY;
+        for (int s = 0; s < S; ++s) {
+            a += psum[((size_t)n * S + s) * C + c];
+            m = fmaxf(m, pmax[((size_t)n * S + s) * C + c]);
+        }
+        avg[c] = a / (float)HW;
+        mx[c] = m;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int j = warp; j < hid; j += nw) {
+        float a = 0.f, m = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const float w = w1[(size_t)j * C + c];
+            a = fmaf(w, avg[c], a);
+            m = fmaf(w, mx[c], m);
+        }
+        a = ysod_warp_sum(a);
+        m = ysod_warp_sum(m);
+        if (lane == 0) { ha[j] = fmaxf(a, 0.f); hm[j] = fmaxf(m, 0.f); }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = 0.f, m = 0.f;
+        for (int j = 0; j < hid; ++j) {
+            const float w = w2[(size_t)c * hid + j];
+            a = fmaf(w, ha[j], a);
+            m = fmaf(w, hm[j], m);
+        }
+        gate[(size_t)n * C + c] = ysod_sigmoid(a + m);
+    }
+}
+
+// out = x * gate[n][c]
+template <typename T>
+__global__ void scale_channels_kernel(const T* __restrict__ x, int HW, int C, int xcs, const float* __restrict__ gate,
+                                      T* __restrict__ out, int ocs, long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c8n = C >> 3;
+    const int cg = (int)(idx % c8n);
+    const long long pix = idx / c8n;
+    const int n = (int)(pix / HW);
+    float v[8];
+    ysod_vec8<T>::load(x + (size_t)pix * xcs + cg * 8, v);
+    const float4 g0 = *reinterpret_cast<const float4*>(gate + (size_t)n * C + cg * 8);
+    const float4 g1 = *reinterpret_cast<const float4*>(gate + (size_t)n * C + cg * 8 + 4);
+    v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
+    v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
+    ysod_vec8<T>::store(out + (size_t)pix * ocs + cg * 8, v);
+}
+
+// CBAM spatial statistics of x*gate: stats[pix] = (mean_c, max_c). A group of G lanes (G = min(C/8,32)) per pixel.
+template <typename T>
+__global__ void cbam_stats_kernel(const T* __restrict__ x, int HW, int C, int xcs, const float* __restrict__ gate,
+                                  float2* __restrict__ stats, long long npix) {
+    const int c8n = C >> 3;
+    const int G = c8n < 32 ? c8n : 32;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / G, gl = lane % G;
+    const int ppw = 32 / G;  // pixels per warp
+    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long pix = warp_id * ppw + sub;
+    float su = 0.f, mx = -INFINITY;
+    if (pix < npix) {
+        const int n = (int)(pix / HW);
+        for (int cg = gl; cg < c8n; cg += G) {
+            float v[8];
+            ysod_vec8<T>::load(x + (size_t)pix * xcs + cg * 8, v);
+            const float* g = gate + (size_t)n * C + cg * 8;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float t = v[e] * g[e];
+                su += t;
+                mx = fmaxf(mx, t);
+            }
+        }
+    }
+    for (int o = G >> 1; o > 0; o >>= 1) {
+        su += __shfl_xor_sync(0xffffffffu, su, o);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (pix < npix && gl == 0) stats[pix] = make_float2(su / (float)C, mx);
+}
+
+// CBAM apply: sa = sigmoid(conv7x7([mean,max])) ; out = x * gate * sa. Same lane grouping; taps split across the group.
+template <typename T>
+__global__ void cbam_apply_kernel(const T* __restrict__ x, int H, int W, int C, int xcs, const float* __restrict__ gate,
+                                  const float2* __restrict__ stats, const float* __restrict__ wsp, int ks, T* __restrict__ out,
+                                  int ocs, long long npix) {
+    extern __shared__ float swsp[];  // [2][ks][ks]
+    for (int i = threadIdx.x; i < 2 * ks * ks; i += blockDim.x) swsp[i] = wsp[i];
+    __syncthreads();
+    const int c8n = C >> 3;
+    const int G = c8n < 32 ? c8n : 32;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / G, gl = lane % G;
+    const int ppw = 32 / G;
+    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long pix = warp_id * ppw + sub;
+    const int HW = H * W;
+    float a = 0.f;
+    int n = 0;
+    if (pix < npix) {
+        n = (int)(pix / HW);
+        const int rem = (int)(pix % HW);
+        const int h = rem / W, w = rem % W;
+        const int pad = ks / 2;
+        for (int t = gl; t < ks * ks; t += G) {
+            const int r = t / ks, q = t % ks;
+            const int ih = h + r - pad, iw = w + q - pad;
+            if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+                const float2 st = stats[(size_t)n * HW + ih * W + iw];
+                a = fmaf(swsp[t], st.x, a);
+                a = fmaf(swsp[ks * ks + t], st.y, a);
+            }
+        }
+    }
+    for (int o = G >> 1; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (pix < npix) {
+        const float sa = ysod_sigmoid(a);
+        for (int cg = gl; cg < c8n; cg += G) {
+            float v[8];
+            ysod_vec8<T>::load(x + (size_t)pix * xcs + cg * 8, v);
+            const float* g = gate + (size_t)n * C + cg * 8;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = v[e] * g[e] * sa;
+            ysod_vec8<T>::store(out + (size_t)pix * ocs + cg * 8, v);
+        }
+    }
+}
+
+// CoordAtt strip pools -> pooled[n][H + W][C] fp32: rows [0,H) = mean over w, rows [H,H+W) = mean over h (ca_block.py:42-45)
+template <typename T>
+__global__ void ca_pool_kernel(const T* __restrict__ x, int H, int W, int C, int xcs, float* __restrict__ pooled) {
+    const int n = blockIdx.y;
+    const int row = blockIdx.x;  // 0..H+W-1
+    const int c8n = C >> 3;
+    for (int cg = threadIdx.x; cg < c8n; cg += blockDim.x) {
+        float a[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a[e] = 0.f;
+        if (row < H) {
+            for (int w = 0; w < W; ++w) {
+                float v[8];
+                ysod_vec8<T>::load(x + (((size_t)n * H + row) * W + w) * xcs + cg * 8, v);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a[e] += v[e];
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a[e] /= (float)W;
+        } else {
+            const int w = row - H;
+            for (int h = 0; h < H; ++h) {
+                float v[8];
+                ysod_vec8<T>::load(x + (((size_t)n * H + h) * W + w) * xcs + cg * 8, v);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) a[e] += v[e];
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a[e] /= (float)H;
+        }
+        ysod_vec8<float>::store(pooled + ((size_t)n * (H + W) + row) * C + cg * 8, a);
+    }
+}
+
+// CoordAtt gates: y = hsigmoid(conv1'(pooled)) (BN folded), a = sigmoid(conv_{h|w}(y)) (ca_block.py:47-57)
+__global__ void ca_gate_kernel(const float* __restrict__ pooled, int H, int W, int C, int mip, const float* __restrict__ w1,
+                               const float* __restrict__ b1, const float* __restrict__ wh, const float* __restrict__ bh,
+                               const float* __restrict__ ww, const float* __restrict__ bw, float* __restrict__ att) {
+    extern __shared__ float sm[];  // y[mip]
+    const int n = blockIdx.y, row = blockIdx.x;
+    const float* p = pooled + ((size_t)n * (H + W) + row) * C;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int j = warp; j < mip; j += nw) {
+        float a = 0.f;
+        for (int c = lane; c < C; c += 32) a = fmaf(w1[(size_t)j * C + c], p[c], a);
+        a = ysod_warp_sum(a);
+        if (lane == 0) sm[j] = ysod_act(a + b1[j], YSOD_ACT_HSIGMOID);
+    }
+    __syncthreads();
+    const float* wo = row < H ? wh : ww;
+    const float* bo = row < H ? bh : bw;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float a = bo[c];
+        for (int j = 0; j < mip; ++j) a = fmaf(wo[(size_t)c * mip + j], sm[j], a);
+        att[((size_t)n * (H + W) + row) * C + c] = ysod_sigmoid(a);
+    }
+}
+
+// out = x * a_w[n][w][c] * a_h[n][h][c]  (ca_block.py:57)
+template <typename T>
+__global__ void ca_apply_kernel(const T* __restrict__ x, int H, int W, int C, int xcs, const float* __restrict__ att,
+                                T* __restrict__ out, int ocs, long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c8n = C >> 3;
+    const int cg = (int)(idx % c8n);
+    const long long pix = idx / c8n;
+    const int w = (int)(pix % W);
+    const int h = (int)((pix / W) % H);
+    const int n = (int)(pix / ((long long)W * H));
+    float v[8], ah[8], aw[8];
+    ysod_vec8<T>::load(x + (size_t)pix * xcs + cg * 8, v);
+    ysod_vec8<float>::load(att + ((size_t)n * (H + W) + h) * C + cg * 8, ah);
+    ysod_vec8<float>::load(att + ((size_t)n * (H + W) + H + w) * C + cg * 8, aw);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = v[e] * aw[e] * ah[e];
+    ysod_vec8<T>::store(out + (size_t)pix * ocs + cg * 8, v);
+}
+
+// SPPF: o1 = max 5x5, o2 = max 9x9, o3 = max 13x13 of y0 (== three chained 5x5/s1/p2 max pools)
+template <typename T>
+__global__ void sppf_pool_kernel(const T* __restrict__ y0, int H, int W, int C, int xcs, int k, T* __restrict__ o1,
+                                 T* __restrict__ o2, T* __restrict__ o3, int ocs, long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c8n = C >> 3;
+    const int cg = (int)(idx % c8n);
+    const long long pix = idx / c8n;
+    const int w = (int)(pix % W);
+    const int h = (int)((pix / W) % H);
+    const int n = (int)(pix / ((long long)W * H));
+    const int r1 = k / 2, r2 = 2 * r1, r3 = 3 * r1;
+    float m1[8], m2[8], m3[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) m1[e] = m2[e] = m3[e] = -INFINITY;
+    for (int dh = -r3; dh <= r3; ++dh) {
+        const int ih = h + dh;
+        if (ih < 0 || ih >= H) continue;
+        for (int dw = -r3; dw <= r3; ++dw) {
+            const int iw = w + dw;
+            if (iw < 0 || iw >= W) continue;
+            float v[8];
+            ysod_vec8<T>::load(y0 + (((size_t)n * H + ih) * W + iw) * xcs + cg * 8, v);
+            const int ad = max(abs(dh), abs(dw));
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                m3[e] = fmaxf(m3[e], v[e]);
+                if (ad <= r2) m2[e] = fmaxf(m2[e], v[e]);
+                if (ad <= r1) m1[e] = fmaxf(m1[e], v[e]);
+            }
+        }
+    }
+    ysod_vec8<T>::store(o1 + (size_t)pix * ocs + cg * 8, m1);
+    ysod_vec8<T>::store(o2 + (size_t)pix * ocs + cg * 8, m2);
+    ysod_vec8<T>::store(o3 + (size_t)pix * ocs + cg * 8, m3);
+}
+
+// nearest-neighbour upsample by `scale` (1 = plain slice copy) into a channel slice
+template <typename T>
+__global__ void upsample_copy_kernel(const T* __restrict__ x, int H, int W, int C, int xcs, int scale, T* __restrict__ out,
+                                     int ocs, long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c8n = C >> 3;
+    const int cg = (int)(idx % c8n);
+    const long long pix = idx / c8n;
+    const int Wo = W * scale, Ho = H * scale;
+    const int ow = (int)(pix % Wo);
+    const int oh = (int)((pix / Wo) % Ho);
+    const int n = (int)(pix / ((long long)Wo * Ho));
+    const uint4* src = reinterpret_cast<const uint4*>(x + (((size_t)n * H + oh / scale) * W + ow / scale) * xcs + cg * 8);
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)pix * ocs + cg * 8);
+    if (sizeof(T) == 2) {
+        dst[0] = src[0];
+    } else {
+        dst[0] = src[0];
+        dst[1] = src[1];
+    }
+}
+
+// LayerNorm over the last dim, one warp per row (eps inside sqrt, biased variance, as torch.nn.LayerNorm)
+template <typename T, bool GATHER>
+__global__ void layernorm_kernel(const T* __restrict__ x, long long rows, int C, int ldx, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps, T* __restrict__ out, int ldo,
+                                 // window-partition gather (GATHER): x is NHWC, rows are window tokens
+                                 int H, int W, int wh, int ww, int nWh, int nWw, T* __restrict__ raw_out) {
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const int c8n = C >> 3;
+    const T* src = nullptr;
+    if (GATHER) {
+        const int tpw = wh * ww;
+        const int t = (int)(row % tpw);
+        const long long win = row / tpw;
+        const int wj = (int)(win % nWw);
+        const int wi = (int)((win / nWw) % nWh);
+        const int n = (int)(win / ((long long)nWw * nWh));
+        const int h = wi * wh + t / ww, w = wj * ww + t % ww;
+        if (h < H && w < W) src = x + (((size_t)n * H + h) * W + w) * ldx;  // else: zero-padded token (blocks_transformer.py:31-36)
+    } else {
+        src = x + (size_t)row * ldx;
+    }
+    constexpr int MAXG = 8;  // C <= 2048
+    float v[MAXG][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXG; ++i) {
+        const int cg = lane + 32 * i;
+        if (cg < c8n) {
+            if (src) ysod_vec8<T>::load(src + cg * 8, v[i]);
+            else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[i][e] = 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s += v[i][e];
+        }
+    }
+    s = ysod_warp_sum(s);
+    const float mean = s / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXG; ++i) {
+        const int cg = lane + 32 * i;
+        if (cg < c8n) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { const float d = v[i][e] - mean; q += d * d; }
+        }
+    }
+    q = ysod_warp_sum(q);
+    const float rstd = rsqrtf(q / (float)C + eps);
+#pragma unroll
+    for (int i = 0; i < MAXG; ++i) {
+        const int cg = lane + 32 * i;
+        if (cg < c8n) {
+            if (GATHER && raw_out) ysod_vec8<T>::store(raw_out + (size_t)row * ldo + cg * 8, v[i]);
+            float o[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] = (v[i][e] - mean) * rstd * gamma[cg * 8 + e] + beta[cg * 8 + e];
+            ysod_vec8<T>::store(out + (size_t)row * ldo + cg * 8, o);
+        }
+    }
+}
+
+// window tokens -> NHWC (crop the padding) (blocks_transformer.py:49-79,125-129)
+template <typename T>
+__global__ void window_reverse_kernel(const T* __restrict__ tok, int ldt, int H, int W, int C, int wh, int ww, int nWh, int nWw,
+                                      T* __restrict__ out, int ocs, long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c8n = C >> 3;
+    const int cg = (int)(idx % c8n);
+    const long long pix = idx / c8n;
+    const int w = (int)(pix % W);
+    const int h = (int)((pix / W) % H);
+    const int n = (int)(pix / ((long long)W * H));
+    const long long win = ((long long)n * nWh + h / wh) * nWw + w / ww;
+    const long long row = win * (wh * ww) + (h % wh) * ww + (w % ww);
+    float v[8];
+    ysod_vec8<T>::load(tok + (size_t)row * ldt + cg * 8, v);
+    ysod_vec8<T>::store(out + (size_t)pix * ocs + cg * 8, v);
+}
+
+// adaptive_avg_pool2d over H only: (H, W) -> (OH, W); bin i = [floor(i*H/OH), ceil((i+1)*H/OH))
+template <typename T>
+__global__ void adaptive_pool_rows_kernel(const T* __restrict__ x, int H, int W, int C, int xcs, int OH, T* __restrict__ out,
+                                          int ocs, long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c8n = C >> 3;
+    const int cg = (int)(idx % c8n);
+    const long long pix = idx / c8n;
+    const int w = (int)(pix % W);
+    const int oh = (int)((pix / W) % OH);
+    const int n = (int)(pix / ((long long)W * OH));
+    const int h0 = (oh * H) / OH, h1 = ((oh + 1) * H + OH - 1) / OH;
+    float a[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] = 0.f;
+    for (int h = h0; h < h1; ++h) {
+        float v[8];
+        ysod_vec8<T>::load(x + (((size_t)n * H + h) * W + w) * xcs + cg * 8, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a[e] += v[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] /= (float)(h1 - h0);
+    ysod_vec8<T>::store(out + (size_t)pix * ocs + cg * 8, a);
+}
+
+// bilinear (align_corners=False) upsample over H only: (IH, W) -> (OH, W) (a2_attn.py:60; width scale is 1 = identity)
+template <typename T>
+__global__ void bilinear_rows_kernel(const T* __restrict__ x, int IH, int W, int C, int xcs, int OH, T* __restrict__ out, int ocs,
+                                     long long total) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c8n = C >> 3;
+    const int cg = (int)(idx % c8n);
+    const long long pix = idx / c8n;
+    const int w = (int)(pix % W);
+    const int oh = (int)((pix / W) % OH);
+    const int n = (int)(pix / ((long long)W * OH));
+    const float scale = (float)IH / (float)OH;
+    float src = scale * ((float)oh + 0.5f) - 0.5f;
+    if (src < 0.f) src = 0.f;
+    const int i0 = (int)src;
+    const int i1 = i0 + ((i0 < IH - 1) ? 1 : 0);
+    const float l1 = src - (float)i0, l0 = 1.0f - l1;
+    float a[8], b[8];
+    ysod_vec8<T>::load(x + (((size_t)n * IH + i0) * W + w) * xcs + cg * 8, a);
+    ysod_vec8<T>::load(x + (((size_t)n * IH + i1) * W + w) * xcs + cg * 8, b);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] = l0 * a[e] + l1 * b[e];
+    ysod_vec8<T>::store(out + (size_t)pix * ocs + cg * 8, a);
+}
+
+inline int blocks_for(long long total, int threads) { return ysod_cdiv(total, threads); }
+
+}  // namespace
+
+#define YSOD_DISPATCH(dtype, ...)                                   \
+    do {                                                            \
+        if ((dtype) == YSOD_F32) { using T = float; __VA_ARGS__; }  \
+        else if ((dtype) == YSOD_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+        else { ysod_set_error("bad dtype %d", (int)(dtype)); return YSOD_ERR_INVALID; } \
+    } while (0)
+
+extern "C" {
+
+int ysod_gap_partial(const void* x, int dtype, int N, int HW, int C, int xcs, int S, float* psum, float* pmax, cudaStream_t st) {
+    YSOD_CHECK_ARG(x && psum && C % 8 == 0 && xcs % 8 == 0 && S >= 1, "ysod_gap_partial: bad args");
+    const int c8n = C / 8;
+    YSOD_CHECK_ARG(c8n <= 256, "ysod_gap_partial: C too large");
+    const int PL = 256 / c8n;
+    const size_t smem = (size_t)2 * PL * C * sizeof(float);
+    YSOD_CHECK_ARG(smem <= 48 * 1024, "ysod_gap_partial: smem");
+    dim3 grid(S, N);
+    YSOD_DISPATCH(dtype, (gap_partial_kernel<T><<<grid, 256, smem, st>>>((const T*)x, HW, C, xcs, S, psum, pmax)));
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+int ysod_se_gate(const float* psum, int N, int S, int HW, int C, const float* w1, const float* b1, const float* w2,
+                 const float* b2, int hid, float* gate, cudaStream_t st) {
+    YSOD_CHECK_ARG(psum && w1 && b1 && w2 && b2 && gate, "ysod_se_gate: null pointer");
+    se_gate_kernel<<<N, 256, (C + hid) * sizeof(float), st>>>(psum, S, HW, C, w1, b1, w2, b2, hid, gate);
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+int ysod_cbam_gate(const float* psum, const float* pmax, int N, int S, int HW, int C, const float* w1, const float* w2, int hid,
+                   float* gate, cudaStream_t st) {
+    YSOD_CHECK_ARG(psum && pmax && w1 && w2 && gate, "ysod_cbam_gate: null pointer");
+    cbam_gate_kernel<<<N, 256, (2 * C + 2 * hid) * sizeof(float), st>>>(psum, pmax, S, HW, C, w1, w2, hid, gate);
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+int ysod_scale_channels(const void* x, int dtype, int N, int HW, int C, int xcs, const float* gate, void* out, int ocs,
+                        cudaStream_t st) {
+    YSOD_CHECK_ARG(x && gate && out && C % 8 == 0 && xcs % 8 == 0 && ocs % 8 == 0, "ysod_scale_channels: bad args");
+    const long long total = (long long)N * HW * (C / 8);
+    YSOD_DISPATCH(dtype, (scale_channels_kernel<T><<<blocks_for(total, 256), 256, 0, st>>>((const T*)x, HW, C, xcs, gate, (T*)out, ocs, total)));
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+int ysod_cbam_stats(const void* x, int dtype, int N, int HW, int C, int xcs, const float* gate, float* stats, cudaStream_t st) {
+    YSOD_CHECK_ARG(x && gate && stats && C % 8 == 0 && xcs % 8 == 0, "ysod_cbam_stats: bad args");
+    const int c8n = C / 8;
+    YSOD_CHECK_ARG((c8n & (c8n - 1)) == 0, "ysod_cbam_stats: C/8 must be a power of two");
+    const int G = c8n < 32 ? c8n : 32;
+    const long long npix = (long long)N * HW;
+    const long long warps = (npix + (32 / G) - 1) / (32 / G);
+    YSOD_DISPATCH(dtype, (cbam_stats_kernel<T><<<blocks_for(warps * 32, 256), 256, 0, st>>>((const T*)x, HW, C, xcs, gate, (float2*)stats, npix)));
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+int ysod_cbam_apply(const void* x, int dtype, int N, int H, int W, int C, int xcs, const float* gate, const float* stats,
+                    const float* wsp, int ks, void* out, int ocs, cudaStream_t st) {
+    YSOD_CHECK_ARG(x && gate && stats && wsp && out && C % 8 == 0 && xcs % 8 == 0 && ocs % 8 == 0, "ysod_cbam_apply: bad args");
+    const int c8n = C / 8;
+    YSOD_CHECK_ARG((c8n & (c8n - 1)) == 0, "ysod_cbam_apply: C/8 must be a power of two");
+    const int G = c8n < 32 ? c8n : 32;
+    const long long npix = (long long)N * H * W;
+    const long long warps = (npix + (32 / G) - 1) / (32 / G);
+    YSOD_DISPATCH(dtype, (cbam_apply_kernel<T><<<blocks_for(warps * 32, 256), 256, 2 * ks * ks * sizeof(float), st>>>(
+                             (const T*)x, H, W, C, xcs, gate, (const float2*)stats, wsp, ks, (T*)out, ocs, npix)));
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+int ysod_ca_pool(const void* x, int dtype, int N, int H, int W, int C, int xcs, float* pooled, cudaStream_t st) {
+    YSOD_CHECK_ARG(x && pooled && C % 8 == 0 && xcs % 8 == 0, "ysod_ca_pool: bad args");
+    dim3 grid(H + W, N);
+    const int threads = (C / 8) < 32 ? 32 : ((C / 8 + 31) / 32) * 32;
+    YSOD_DISPATCH(dtype, (ca_pool_kernel<T><<<grid, threads > 256 ? 256 : threads, 0, st>>>((const T*)x, H, W, C, xcs, pooled)));
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+int ysod_ca_gate(const float* pooled, int N, int H, int W, int C, int mip, const float* w1, const float* b1, const float* wh,
+                 const float* bh, const float* ww, const float* bw, float* att, cudaStream_t st) {
+    YSOD_CHECK_ARG(pooled && w1 && b1 && wh && bh && ww && bw && att, "ysod_ca_gate: null pointer");
+    dim3 grid(H + W, N);
+    ca_gate_kernel<<<grid, 128, mip * sizeof(float), st>>>(pooled, H, W, C, mip, w1, b1, wh, bh, ww, bw, att);
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+int ysod_ca_apply(const void* x, int dtype, int N, int H, int W, int C, int xcs, const float* att, void* out, int ocs,
+                  cudaStream_t st) {
+    YSOD_CHECK_ARG(x && att && out && C % 8 == 0 && xcs % 8 == 0 && ocs % 8 == 0, "ysod_ca_apply: bad args");
+    const long long total = (long long)N * H * W * (C / 8);
+    YSOD_DISPATCH(dtype, (ca_apply_kernel<T><<<blocks_for(total, 256), 256, 0, st>>>((const T*)x, H, W, C, xcs, att, (T*)out, ocs, total)));
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+int ysod_sppf_pool(const void* y0, int dtype, int N, int H, int W, int C, int xcs, int k, void* o1, void* o2, void* o3, int ocs,
+                   cudaStream_t st) {
+    YSOD_CHECK_ARG(y0 && o1 && o2 && o3 && C % 8 == 0 && xcs % 8 == 0 && ocs % 8 == 0 && (k & 1), "ysod_sppf_pool: bad args");
+    const long long total = (long long)N * H * W * (C / 8);
+    YSOD_DISPATCH(dtype, (sppf_pool_kernel<T><<<blocks_for(total, 128), 128, 0, st>>>((const T*)y0, H, W, C, xcs, k, (T*)o1, (T*)o2, (T*)o3, ocs, total)));
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+int ysod_upsample_copy(const void* x, int dtype, int N, int H, int W, int C, int xcs, int scale, void* out, int ocs,
+                       cudaStream_t st) {
+    YSOD_CHECK_ARG(x && out && C % 8 == 0 && xcs % 8 == 0 && ocs % 8 == 0 && scale >= 1, "ysod_upsample_copy: bad args");
+    const long long total = (long long)N * H * scale * W * scale * (C / 8);
+    YSOD_DISPATCH(dtype, (upsample_copy_kernel<T><<<blocks_for(total, 256), 256, 0, st>>>((const T*)x, H, W, C, xcs, scale, (T*)out, ocs, total)));
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+int ysod_layernorm(const void* x, int dtype, long long rows, int C, int ldx, const float* gamma, const float* beta, float eps,
+                   void* out, int ldo, cudaStream_t st) {
+    YSOD_CHECK_ARG(x && gamma && beta && out && C % 8 == 0 && C <= 2048 && ldx % 8 == 0 && ldo % 8 == 0, "ysod_layernorm: bad args");
+    YSOD_DISPATCH(dtype, (layernorm_kernel<T, false><<<blocks_for(rows * 32, 256), 256, 0, st>>>(
+                             (const T*)x, rows, C, ldx, gamma, beta, eps, (T*)out, ldo, 0, 0, 1, 1, 1, 1, nullptr)));
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+// x: NHWC view; raw_out / norm_out: [N*nWh*nWw*wh*ww][C] token matrices (row stride ldo)
+int ysod_window_partition_ln(const void* x, int dtype, int N, int H, int W, int C, int xcs, int wh, int ww, int nWh, int nWw,
+                             const float* gamma, const float* beta, float eps, void* raw_out, void* norm_out, int ldo,
+                             cudaStream_t st) {
+    YSOD_CHECK_ARG(x && gamma && beta && norm_out && C % 8 == 0 && C <= 2048 && xcs % 8 == 0 && ldo % 8 == 0, "ysod_window_partition_ln: bad args");
+    const long long rows = (long long)N * nWh * nWw * wh * ww;
+    YSOD_DISPATCH(dtype, (layernorm_kernel<T, true><<<blocks_for(rows * 32, 256), 256, 0, st>>>(
+                             (const T*)x, rows, C, xcs, gamma, beta, eps, (T*)norm_out, ldo, H, W, wh, ww, nWh, nWw, (T*)raw_out)));
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+int ysod_window_reverse(const void* tok, int dtype, int ldt, int N, int H, int W, int C, int wh, int ww, int nWh, int nWw, void* out,
+                        int ocs, cudaStream_t st) {
+    YSOD_CHECK_ARG(tok && out && C % 8 == 0 && ldt % 8 == 0 && ocs % 8 == 0, "ysod_window_reverse: bad args");
+    const long long total = (long long)N * H * W * (C / 8);
+    YSOD_DISPATCH(dtype, (window_reverse_kernel<T><<<blocks_for(total, 256), 256, 0, st>>>((const T*)tok, ldt, H, W, C, wh, ww, nWh, nWw, (T*)out, ocs, total)));
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+int ysod_adaptive_pool_rows(const void* x, int dtype, int N, int H, int W, int C, int xcs, int OH, void* out, int ocs,
+                            cudaStream_t st) {
+    YSOD_CHECK_ARG(x && out && C % 8 == 0 && xcs % 8 == 0 && ocs % 8 == 0 && OH >= 1, "ysod_adaptive_pool_rows: bad args");
+    const long long total = (long long)N * OH * W * (C / 8);
+    YSOD_DISPATCH(dtype, (adaptive_pool_rows_kernel<T><<<blocks_for(total, 256), 256, 0, st>>>((const T*)x, H, W, C, xcs, OH, (T*)out, ocs, total)));
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+int ysod_bilinear_rows(const void* x, int dtype, int N, int IH, int W, int C, int xcs, int OH, void* out, int ocs, cudaStream_t st) {
+    YSOD_CHECK_ARG(x && out && C % 8 == 0 && xcs % 8 == 0 && ocs % 8 == 0 && OH >= 1, "ysod_bilinear_rows: bad args");
+    const long long total = (long long)N * OH * W * (C / 8);
+    YSOD_DISPATCH(dtype, (bilinear_rows_kernel<T><<<blocks_for(total, 256), 256, 0, st>>>((const T*)x, IH, W, C, xcs, OH, (T*)out, ocs, total)));
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+}  // extern "C"

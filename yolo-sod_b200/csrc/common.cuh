@@ -1,0 +1,123 @@
+// Shared device/host helpers for the yolo-sod B200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#define YSOD_OK 0
+#define YSOD_ERR_INVALID 1
+#define YSOD_ERR_CUDA 2
+#define YSOD_ERR_UNSUPPORTED 3
+#define YSOD_ERR_WORKSPACE 4
+
+// thread-local last-error text, exposed through ysod_last_error()
+void ysod_set_error(const char* fmt, ...);
+
+#define YSOD_CHECK_ARG(cond, ...)                 \
+    do {                                          \
+        if (!(cond)) {                            \
+            ysod_set_error(__VA_ARGS__);          \
+            return YSOD_ERR_INVALID;              \
+        }                                         \
+    } while (0)
+
+#define YSOD_CUDA(call)                                                                   \
+    do {                                                                                  \
+        cudaError_t e__ = (call);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            ysod_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return YSOD_ERR_CUDA;                                                         \
+        }                                                                                 \
+    } while (0)
+
+#define YSOD_LAUNCH_CHECK()                                                               \
+    do {                                                                                  \
+        cudaError_t e__ = cudaGetLastError();                                             \
+        if (e__ != cudaSuccess) {                                                         \
+            ysod_set_error("%s:%d launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+            return YSOD_ERR_CUDA;                                                         \
+        }                                                                                 \
+    } while (0)
+
+static inline int ysod_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// dtype codes used across the C ABI
+#define YSOD_F32 0
+#define YSOD_BF16 1
+
+// activation codes for fused epilogues
+#define YSOD_ACT_NONE 0
+#define YSOD_ACT_SILU 1
+#define YSOD_ACT_GELU 2   // exact erf GELU (torch.nn.GELU default)
+#define YSOD_ACT_RELU 3
+#define YSOD_ACT_SIGMOID 4
+#define YSOD_ACT_HSIGMOID 5  // relu6(x+3)/6
+
+#ifdef __CUDACC__
+template <typename T> __device__ __forceinline__ float ysod_ld(const T* p);
+template <> __device__ __forceinline__ float ysod_ld<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ysod_ld<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T> __device__ __forceinline__ void ysod_st(T* p, float v);
+template <> __device__ __forceinline__ void ysod_st<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void ysod_st<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float ysod_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float ysod_act(float x, int act) {
+    switch (act) {
+        case YSOD_ACT_SILU: return x / (1.0f + expf(-x));
+        case YSOD_ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+        case YSOD_ACT_RELU: return fmaxf(x, 0.0f);
+        case YSOD_ACT_SIGMOID: return ysod_sigmoid(x);
+        case YSOD_ACT_HSIGMOID: return fminf(fmaxf(x + 3.0f, 0.0f), 6.0f) * (1.0f / 6.0f);
+        default: return x;
+    }
+}
+
+// 8 consecutive channels (16 B of bf16 / 32 B of fp32) <-> 8 floats
+template <typename T> struct ysod_vec8;
+template <> struct ysod_vec8<__nv_bfloat16> {
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* v) {
+        uint4 r = *reinterpret_cast<const uint4*>(p);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float2 f = __bfloat1622float2(h[i]);
+            v[2 * i] = f.x;
+            v[2 * i + 1] = f.y;
+        }
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* v) {
+        uint4 r;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        *reinterpret_cast<uint4*>(p) = r;
+    }
+};
+template <> struct ysod_vec8<float> {
+    static __device__ __forceinline__ void load(const float* p, float* v) {
+        float4 a = *reinterpret_cast<const float4*>(p);
+        float4 b = *reinterpret_cast<const float4*>(p + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float* v) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+};
+
+__device__ __forceinline__ float ysod_warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float ysod_warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+#endif

@@ -1,0 +1,221 @@
+// CUDA-core convolutions for the shapes that do not belong on the tensor cores, and for the fp32 parity mode.
+//
+// Replaces (reference): ultralytics/nn/modules/conv.py:37-55 Conv / :102 DWConv for
+//   * the Cin=3 stem (K = 27, HBM-bound; also performs the NCHW fp32 -> NHWC conversion of the input image),
+//   * depthwise convs (SwinBlock.dw 3x3 blocks_transformer.py:137, AAttn.pe 5x5 block.py:1291, Detect DWConv head.py:51-52),
+//   * grouped convs of yolov12 (yolov12.yaml:20,22),
+//   * every conv when the model runs in fp32 mode (north_star: rtol 1e-4 mode cannot ride on bf16/tf32 MMA).
+// Layouts: activations NHWC (channel-sliced views allowed), weights [Cout][kh][kw][Cin/groups] for dense/grouped,
+// [kh][kw][C] for depthwise, [Cout][kh][kw][3] fp32 for the stem. Epilogue = +bias -> act -> (+residual).
+#include "common.cuh"
+
+namespace {
+
+template <typename TI, typename TO>
+__global__ void conv_direct_kernel(const TI* __restrict__ x, const TI* __restrict__ w, const float* __restrict__ bias,
+                                   const TI* __restrict__ res, TO* __restrict__ out, int N, int H, int W, int Cin, int xcs,
+                                   int Ho, int Wo, int Cout, int ocs, int rcs, int k, int s, int pad, int groups, int act) {
+    const int cog_n = (Cout + 3) >> 2;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)N * Ho * Wo * cog_n;
+    if (idx >= total) return;
+    const int cog = (int)(idx % cog_n);
+    const long long pix = idx / cog_n;
+    const int ow = (int)(pix % Wo);
+    const int oh = (int)((pix / Wo) % Ho);
+    const int n = (int)(pix / ((long long)Wo * Ho));
+    const int co0 = cog * 4;
+    const int cpg = Cin / groups, opg = Cout / groups;
+    const int g = co0 / opg;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int nco = (Cout - co0) < 4 ? (Cout - co0) : 4;
+    for (int r = 0; r < k; ++r) {
+        const int ih = oh * s + r - pad;
+        if (ih < 0 || ih >= H) continue;
+        for (int q = 0; q < k; ++q) {
+            const int iw = ow * s + q - pad;
+            if (iw < 0 || iw >= W) continue;
+            const TI* xp = x + (((size_t)n * H + ih) * W + iw) * xcs + g * cpg;
+            const TI* wp = w + ((size_t)(co0 * k + r) * k + q) * cpg;
+            const size_t wstride = (size_t)k * k * cpg;
+            if ((cpg & 7) == 0) {
+                for (int c = 0; c < cpg; c += 8) {
+                    float xv[8];
+                    ysod_vec8<TI>::load(xp + c, xv);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (j < nco) {
+                            float wv[8];
+                            ysod_vec8<TI>::load(wp + j * wstride + c, wv);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) acc[j] = fmaf(xv[e], wv[e], acc[j]);
+                        }
+                    }
+                }
+            } else {
+                for (int c = 0; c < cpg; ++c) {
+                    const float xv = ysod_ld<TI>(xp + c);
+                    for (int j = 0; j < nco; ++j) acc[j] = fmaf(xv, ysod_ld<TI>(wp + j * wstride + c), acc[j]);
+                }
+            }
+        }
+    }
+    const size_t opix = (size_t)pix;
+    for (int j = 0; j < nco; ++j) {
+        float v = ysod_act(acc[j] + bias[co0 + j], act);
+        if (res) v += ysod_ld<TI>(res + opix * rcs + co0 + j);
+        ysod_st<TO>(out + opix * ocs + co0 + j, v);
+    }
+}
+
+// depthwise k x k, stride s; thread = (pixel, 8 channels)
+template <typename T>
+__global__ void dwconv_kernel(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
+                              const T* __restrict__ res, T* __restrict__ out, int N, int H, int W, int C, int xcs, int Ho,
+                              int Wo, int ocs, int rcs, int k, int s, int pad, int act) {
+    const int c8n = C >> 3;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)N * Ho * Wo * c8n;
+    if (idx >= total) return;
+    const int c0 = (int)(idx % c8n) * 8;
+    const long long pix = idx / c8n;
+    const int ow = (int)(pix % Wo);
+    const int oh = (int)((pix / Wo) % Ho);
+    const int n = (int)(pix / ((long long)Wo * Ho));
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = bias[c0 + e];
+    for (int r = 0; r < k; ++r) {
+        const int ih = oh * s + r - pad;
+        if (ih < 0 || ih >= H) continue;
+        for (int q = 0; q < k; ++q) {
+            const int iw = ow * s + q - pad;
+            if (iw < 0 || iw >= W) continue;
+            float xv[8], wv[8];
+            ysod_vec8<T>::load(x + (((size_t)n * H + ih) * W + iw) * xcs + c0, xv);
+            ysod_vec8<T>::load(w + (size_t)(r * k + q) * C + c0, wv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] = fmaf(xv[e], wv[e], acc[e]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = ysod_act(acc[e], act);
+    if (res) {
+        float rv[8];
+        ysod_vec8<T>::load(res + (size_t)pix * rcs + c0, rv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += rv[e];
+    }
+    ysod_vec8<T>::store(out + (size_t)pix * ocs + c0, acc);
+}
+
+// stem: NCHW fp32 image -> k x k stride-s conv (Cin = 3) -> NHWC; thread = (pixel, 8 output channels)
+template <typename TO>
+__global__ void stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
+                                 TO* __restrict__ out, int N, int H, int W, int Ho, int Wo, int Cout, int ocs, int k, int s,
+                                 int pad, int act) {
+    extern __shared__ float sw[];  // [Cout][k*k*3] + bias
+    const int wn = Cout * k * k * 3;
+    for (int i = threadIdx.x; i < wn; i += blockDim.x) sw[i] = w[i];
+    for (int i = threadIdx.x; i < Cout; i += blockDim.x) sw[wn + i] = bias[i];
+    __syncthreads();
+    const int c8n = Cout >> 3;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)N * Ho * Wo * c8n;
+    if (idx >= total) return;
+    const int c0 = (int)(idx % c8n) * 8;
+    const long long pix = idx / c8n;
+    const int ow = (int)(pix % Wo);
+    const int oh = (int)((pix / Wo) % Ho);
+    const int n = (int)(pix / ((long long)Wo * Ho));
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = sw[wn + c0 + e];
+    const int kk3 = k * k * 3;
+    for (int r = 0; r < k; ++r) {
+        const int ih = oh * s + r - pad;
+        if (ih < 0 || ih >= H) continue;
+        for (int q = 0; q < k; ++q) {
+            const int iw = ow * s + q - pad;
+            if (iw < 0 || iw >= W) continue;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float xv = __ldg(img + (((size_t)n * 3 + c) * H + ih) * W + iw);
+                const float* wp = sw + (size_t)c0 * kk3 + (r * k + q) * 3 + c;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] = fmaf(xv, wp[e * kk3], acc[e]);
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = ysod_act(acc[e], act);
+    ysod_vec8<TO>::store(out + (size_t)pix * ocs + c0, acc);
+}
+
+}  // namespace
+
+extern "C" {
+
+// Generic dense / grouped conv. dtype = element type of x, w, res; out_dtype may be fp32 for the raw head maps.
+int ysod_conv_direct(const void* x, int dtype, int N, int H, int W, int Cin, int xcs, const void* w, const float* bias,
+                     int Cout, int k, int s, int pad, int groups, void* out, int out_dtype, int ocs, const void* res, int rcs,
+                     int act, cudaStream_t stream) {
+    YSOD_CHECK_ARG(x && w && bias && out, "ysod_conv_direct: null pointer");
+    YSOD_CHECK_ARG(groups >= 1 && Cin % groups == 0 && Cout % groups == 0, "ysod_conv_direct: bad groups %d", groups);
+    YSOD_CHECK_ARG(groups == 1 || (Cout / groups) % 4 == 0, "ysod_conv_direct: Cout/groups must be a multiple of 4");
+    const int Ho = (H + 2 * pad - k) / s + 1, Wo = (W + 2 * pad - k) / s + 1;
+    const long long total = (long long)N * Ho * Wo * ((Cout + 3) / 4);
+    const int blocks = ysod_cdiv(total, 256);
+#define LAUNCH(TI, TO)                                                                                                    \
+    conv_direct_kernel<TI, TO><<<blocks, 256, 0, stream>>>((const TI*)x, (const TI*)w, bias, (const TI*)res, (TO*)out, N, H, W, \
+                                                           Cin, xcs, Ho, Wo, Cout, ocs, rcs, k, s, pad, groups, act)
+    if (dtype == YSOD_F32 && out_dtype == YSOD_F32) LAUNCH(float, float);
+    else if (dtype == YSOD_BF16 && out_dtype == YSOD_BF16) LAUNCH(__nv_bfloat16, __nv_bfloat16);
+    else if (dtype == YSOD_BF16 && out_dtype == YSOD_F32) LAUNCH(__nv_bfloat16, float);
+    else {
+        ysod_set_error("ysod_conv_direct: unsupported dtype combination %d -> %d", dtype, out_dtype);
+        return YSOD_ERR_UNSUPPORTED;
+    }
+#undef LAUNCH
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+int ysod_dwconv(const void* x, int dtype, int N, int H, int W, int C, int xcs, const void* w, const float* bias, int k, int s,
+                int pad, void* out, int ocs, const void* res, int rcs, int act, cudaStream_t stream) {
+    YSOD_CHECK_ARG(x && w && bias && out, "ysod_dwconv: null pointer");
+    YSOD_CHECK_ARG(C % 8 == 0 && xcs % 8 == 0 && ocs % 8 == 0, "ysod_dwconv: channels must be a multiple of 8");
+    const int Ho = (H + 2 * pad - k) / s + 1, Wo = (W + 2 * pad - k) / s + 1;
+    const long long total = (long long)N * Ho * Wo * (C / 8);
+    const int blocks = ysod_cdiv(total, 256);
+    if (dtype == YSOD_F32)
+        dwconv_kernel<float><<<blocks, 256, 0, stream>>>((const float*)x, (const float*)w, bias, (const float*)res, (float*)out, N,
+                                                         H, W, C, xcs, Ho, Wo, ocs, rcs, k, s, pad, act);
+    else
+        dwconv_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias,
+                                                                 (const __nv_bfloat16*)res, (__nv_bfloat16*)out, N, H, W, C, xcs,
+                                                                 Ho, Wo, ocs, rcs, k, s, pad, act);
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+// img: (N,3,H,W) fp32 NCHW, exactly what the reference's DetectionModel.forward receives (tasks.py:129).
+int ysod_stem_conv(const float* img, int N, int H, int W, const float* w, const float* bias, int Cout, int k, int s, int pad,
+                   void* out, int out_dtype, int ocs, int act, cudaStream_t stream) {
+    YSOD_CHECK_ARG(img && w && bias && out, "ysod_stem_conv: null pointer");
+    YSOD_CHECK_ARG(Cout % 8 == 0 && ocs % 8 == 0, "ysod_stem_conv: Cout must be a multiple of 8");
+    const int Ho = (H + 2 * pad - k) / s + 1, Wo = (W + 2 * pad - k) / s + 1;
+    const long long total = (long long)N * Ho * Wo * (Cout / 8);
+    const int blocks = ysod_cdiv(total, 256);
+    const size_t smem = (size_t)(Cout * k * k * 3 + Cout) * sizeof(float);
+    YSOD_CHECK_ARG(smem <= 48 * 1024, "ysod_stem_conv: weights do not fit in shared memory");
+    if (out_dtype == YSOD_F32)
+        stem_conv_kernel<float><<<blocks, 256, smem, stream>>>(img, w, bias, (float*)out, N, H, W, Ho, Wo, Cout, ocs, k, s, pad, act);
+    else
+        stem_conv_kernel<__nv_bfloat16><<<blocks, 256, smem, stream>>>(img, w, bias, (__nv_bfloat16*)out, N, H, W, Ho, Wo, Cout, ocs,
+                                                                       k, s, pad, act);
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,387 @@
+// Batched, host-sync-free NMS for the detection hot path.
+//
+// Replaces (reference, relative to the checkout):
+//   ultralytics/utils/ops.py:167-316  non_max_suppression  (per-image Python loop + host syncs)
+//   torchvision.ops.nms (ops.py:296)  greedy IoU suppression
+//
+// Pipeline, all on one stream, no host round trip:
+//   K1 nms_score   grid-wide : best class + confidence gate (+ class filter) per anchor (ops.py:234,274-281)
+//   K2 nms_sort    CTA/image : order-preserving compaction, then a stable LSD radix sort on the score
+//                              (== stable descending sort: equal scores keep ascending anchor index,
+//                              which is what torchvision's `scores.sort(stable=True, descending=True)` yields),
+//                              truncated to max_nms (ops.py:285-286)
+//   K3 nms_gather  grid-wide : xywh->xyxy (ops.py:416-433) + fp32 class offset cls*max_wh (ops.py:289,295)
+//   K4 nms_greedy  CTA/image : lazy greedy sweep. Only kept boxes ever suppress anything and the caller keeps at
+//                              most max_det of them (ops.py:297), so instead of the full n^2 bitmask only
+//                              <= max_det mask rows are evaluated: the CTA finds the next unsuppressed box in a
+//                              shared-memory bitset, evaluates its IoU row (one warp per 32-box word, ballot ->
+//                              one OR into the bitset) and repeats. Output prefix is identical to the full sweep.
+//
+// Bit-exactness contract: every IoU step is an explicitly rounded fp32 op (__fsub_rn/__fmul_rn/__fadd_rn/
+// __fdiv_rn: no FMA contraction, IEEE division), max/min are written as the comparisons std::max/std::min
+// perform, and the `float IoU > double thr` comparison is done against the largest float <= thr (computed on
+// the host), which is equivalent for every float IoU.
+#include "common.cuh"
+
+namespace {
+
+constexpr int SORT_THREADS = 1024;
+constexpr int GREEDY_THREADS = 1024;
+
+__global__ void nms_score_kernel(const float* __restrict__ pred, int nc, int A, float conf_thres,
+                                 const int* __restrict__ classes, int n_classes, int multi_label,
+                                 float* __restrict__ conf, int* __restrict__ cls) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (a >= A) return;
+    const float* p = pred + ((size_t)b * (4 + nc) + 4) * A + a;
+    if (!multi_label) {
+        float best = p[0];
+        int bi = 0;
+        for (int c = 1; c < nc; ++c) {
+            float v = p[(size_t)c * A];
+            if (v > best) { best = v; bi = c; }  // first maximal index, as torch.max(dim)
+        }
+        bool pass = best > conf_thres;
+        if (pass && n_classes > 0) {
+            bool hit = false;
+            for (int k = 0; k < n_classes; ++k) hit |= (classes[k] == bi);
+            pass = hit;
+        }
+        conf[(size_t)b * A + a] = pass ? best : 0.0f;
+        cls[(size_t)b * A + a] = bi;
+    } else {
+        // validator path (ops.py:270-272): one candidate per (anchor, class) pair, anchor-major order
+        for (int c = 0; c < nc; ++c) {
+            float v = p[(size_t)c * A];
+            bool pass = v > conf_thres;
+            if (pass && n_classes > 0) {
+                bool hit = false;
+                for (int k = 0; k < n_classes; ++k) hit |= (classes[k] == c);
+                pass = hit;
+            }
+            conf[((size_t)b * A + a) * nc + c] = pass ? v : 0.0f;
+        }
+    }
+}
+
+// One CTA per image. conf: M entries (0 = not a candidate, >0 = score).
+__global__ void __launch_bounds__(SORT_THREADS, 1)
+nms_sort_kernel(const float* __restrict__ conf_all, int M, int cap, uint32_t* __restrict__ ws_keys0,
+                uint32_t* __restrict__ ws_vals0, uint32_t* __restrict__ ws_keys1, uint32_t* __restrict__ ws_vals1,
+                int* __restrict__ order_all, float* __restrict__ sscore_all, int* __restrict__ count_all) {
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* conf = conf_all + (size_t)b * M;
+    uint32_t* kin = ws_keys0 + (size_t)b * M;
+    uint32_t* vin = ws_vals0 + (size_t)b * M;
+    uint32_t* kout = ws_keys1 + (size_t)b * M;
+    uint32_t* vout = ws_vals1 + (size_t)b * M;
+
+    __shared__ int s_warp_cnt[32];
+    __shared__ int s_warp_off[32];
+    __shared__ int s_chunk_total;
+    __shared__ int s_hist[256];
+    __shared__ int s_bin_base[256];
+    __shared__ int s_wh[32 * 256];
+
+    // ---- phase 1: order-preserving compaction -------------------------------------------------------
+    int n = 0;
+    for (int start = 0; start < M; start += SORT_THREADS) {
+        const int i = start + tid;
+        const float s = (i < M) ? conf[i] : 0.0f;
+        const bool p = s > 0.0f;
+        const unsigned bal = __ballot_sync(0xffffffffu, p);
+        if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        if (warp == 0) {
+            int v = s_warp_cnt[lane];
+            int inc = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            s_warp_off[lane] = inc - v;
+            if (lane == 31) s_chunk_total = inc;
+        }
+        __syncthreads();
+        if (p) {
+            const int pos = n + s_warp_off[warp] + __popc(bal & ((1u << lane) - 1u));
+            kin[pos] = ~__float_as_uint(s);  // positive floats: ascending ~bits == descending score
+            vin[pos] = (uint32_t)i;
+        }
+        n += s_chunk_total;
+    }
+    __syncthreads();
+
+    // ---- phase 2: stable LSD radix sort, 8-bit digits ------------------------------------------------
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = pass * 8;
+        if (tid < 256) s_hist[tid] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += SORT_THREADS) atomicAdd(&s_hist[(kin[i] >> shift) & 255], 1);
+        __syncthreads();
+        const int single = __syncthreads_or(tid < 256 && n > 0 && s_hist[tid] == n);
+        if (single || n <= 1) continue;  // every key shares this digit: the pass is the identity
+        if (warp == 0) {
+            int local[8];
+            int sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { local[k] = sum; sum += s_hist[lane * 8 + k]; }
+            int inc = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            const int base = inc - sum;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s_bin_base[lane * 8 + k] = base + local[k];
+        }
+        __syncthreads();
+        for (int start = 0; start < n; start += SORT_THREADS) {
+            for (int j = tid; j < 32 * 256; j += SORT_THREADS) s_wh[j] = 0;
+            __syncthreads();
+            const int i = start + tid;
+            const bool valid = i < n;
+            const uint32_t key = valid ? kin[i] : 0u;
+            const uint32_t val = valid ? vin[i] : 0u;
+            const uint32_t d = (key >> shift) & 255u;
+            const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : (0x100u | (uint32_t)lane));
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            if (valid && rank == 0) s_wh[warp * 256 + d] = __popc(peers);
+            __syncthreads();
+            if (tid < 256) {
+                int run = s_bin_base[tid];
+#pragma unroll 8
+                for (int w = 0; w < 32; ++w) {
+                    const int t = s_wh[w * 256 + tid];
+                    s_wh[w * 256 + tid] = run;
+                    run += t;
+                }
+                s_bin_base[tid] = run;
+            }
+            __syncthreads();
+            if (valid) {
+                const int pos = s_wh[warp * 256 + d] + rank;
+                kout[pos] = key;
+                vout[pos] = val;
+            }
+            __syncthreads();
+        }
+        uint32_t* t;
+        t = kin; kin = kout; kout = t;
+        t = vin; vin = vout; vout = t;
+        __syncthreads();
+    }
+
+    const int m = n < cap ? n : cap;  // ops.py:285-286: keep the max_nms highest scores
+    int* order = order_all + (size_t)b * cap;
+    float* sscore = sscore_all + (size_t)b * cap;
+    for (int i = tid; i < m; i += SORT_THREADS) {
+        order[i] = (int)vin[i];
+        sscore[i] = __uint_as_float(~kin[i]);
+    }
+    if (tid == 0) count_all[b] = m;
+}
+
+__device__ __forceinline__ float4 load_xyxy(const float* __restrict__ pred, int b, int nc, int A, int a) {
+    const float* p = pred + (size_t)b * (4 + nc) * A + a;
+    const float cx = p[0], cy = p[(size_t)A], w = p[(size_t)2 * A], h = p[(size_t)3 * A];
+    const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);  // ops.py:429 wh = x[..., 2:] / 2
+    return make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+}
+
+__global__ void nms_gather_kernel(const float* __restrict__ pred, int nc, int A, int cap, int multi_label,
+                                  const int* __restrict__ order_all, const int* __restrict__ cls_all,
+                                  const int* __restrict__ count_all, float class_mult, float4* __restrict__ boxes_all) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (r >= count_all[b]) return;
+    const int id = order_all[(size_t)b * cap + r];
+    const int a = multi_label ? id / nc : id;
+    const int c = multi_label ? id % nc : cls_all[(size_t)b * A + a];
+    const float4 q = load_xyxy(pred, b, nc, A, a);
+    const float off = __fmul_rn((float)c, class_mult);  // ops.py:289 c = x[:, 5:6] * (0 if agnostic else max_wh)
+    boxes_all[(size_t)b * cap + r] =
+        make_float4(__fadd_rn(q.x, off), __fadd_rn(q.y, off), __fadd_rn(q.z, off), __fadd_rn(q.w, off));
+}
+
+// std::max(a, b) == (a < b) ? b : a ; std::min(a, b) == (b < a) ? b : a   (NaN behaviour included)
+__device__ __forceinline__ float std_max(float a, float b) { return (a < b) ? b : a; }
+__device__ __forceinline__ float std_min(float a, float b) { return (b < a) ? b : a; }
+
+__global__ void __launch_bounds__(GREEDY_THREADS, 1)
+nms_greedy_kernel(const float* __restrict__ pred, int nc, int A, int cap, int multi_label, int max_det,
+                  float thr_f, const float4* __restrict__ boxes_all, const int* __restrict__ order_all,
+                  const float* __restrict__ sscore_all, const int* __restrict__ cls_all,
+                  const int* __restrict__ count_all, float* __restrict__ det_all, int* __restrict__ index_all,
+                  int* __restrict__ nkeep_all) {
+    extern __shared__ uint32_t smem_u32[];
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = count_all[b];
+    const int nwords = (n + 31) >> 5;
+    uint32_t* removed = smem_u32;                       // cap/32 words
+    int* keep_idx = (int*)(smem_u32 + ((cap + 31) >> 5));  // max_det ints
+    __shared__ int s_next;
+    const float4* boxes = boxes_all + (size_t)b * cap;
+
+    for (int w = tid; w < nwords; w += GREEDY_THREADS) removed[w] = 0u;
+    __syncthreads();
+
+    int kept = 0, pos = 0;
+    while (kept < max_det && pos < n) {
+        if (warp == 0) {
+            int found = -1;
+            for (int w0 = pos >> 5; w0 < nwords && found < 0; w0 += 32) {
+                const int w = w0 + lane;
+                uint32_t bits = (w < nwords) ? ~removed[w] : 0u;
+                if (w == (pos >> 5)) bits &= 0xffffffffu << (pos & 31);
+                const int valid = n - w * 32;
+                if (valid < 32) bits &= (valid <= 0) ? 0u : ((1u << valid) - 1u);
+                const unsigned bal = __ballot_sync(0xffffffffu, bits != 0u);
+                if (bal) {
+                    const int src = __ffs(bal) - 1;
+                    const uint32_t bb = __shfl_sync(0xffffffffu, bits, src);
+                    found = (w0 + src) * 32 + __ffs(bb) - 1;
+                }
+            }
+            if (lane == 0) s_next = found;
+        }
+        __syncthreads();
+        const int i = s_next;
+        if (i < 0) break;
+        if (tid == 0) keep_idx[kept] = i;
+        ++kept;
+        pos = i + 1;
+        if (kept < max_det) {
+            const float4 bi = boxes[i];
+            const float iarea = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+            for (int w = (pos >> 5) + warp; w < nwords; w += GREEDY_THREADS / 32) {
+                const int j = w * 32 + lane;
+                bool sup = false;
+                if (j > i && j < n) {
+                    const float4 bj = boxes[j];
+                    const float jarea = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
+                    const float xx1 = std_max(bi.x, bj.x), yy1 = std_max(bi.y, bj.y);
+                    const float xx2 = std_min(bi.z, bj.z), yy2 = std_min(bi.w, bj.w);
+                    const float ww = std_max(0.0f, __fsub_rn(xx2, xx1));
+                    const float hh = std_max(0.0f, __fsub_rn(yy2, yy1));
+                    const float inter = __fmul_rn(ww, hh);
+                    const float uni = __fsub_rn(__fadd_rn(iarea, jarea), inter);
+                    const float ovr = __fdiv_rn(inter, uni);
+                    sup = ovr > thr_f;
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, sup);
+                if (lane == 0 && bal) removed[w] |= bal;  // this warp is the only writer of word w this round
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+
+    // emit detections [x1,y1,x2,y2,conf,cls] (un-offset boxes) + the candidate index of each keep
+    float* det = det_all + (size_t)b * max_det * 6;
+    int* index = index_all + (size_t)b * max_det;
+    for (int t = tid; t < max_det; t += GREEDY_THREADS) {
+        if (t < kept) {
+            const int r = keep_idx[t];
+            const int id = order_all[(size_t)b * cap + r];
+            const int a = multi_label ? id / nc : id;
+            const int c = multi_label ? id % nc : cls_all[(size_t)b * A + a];
+            const float4 q = load_xyxy(pred, b, nc, A, a);
+            det[t * 6 + 0] = q.x; det[t * 6 + 1] = q.y; det[t * 6 + 2] = q.z; det[t * 6 + 3] = q.w;
+            det[t * 6 + 4] = sscore_all[(size_t)b * cap + r];
+            det[t * 6 + 5] = (float)c;
+            index[t] = id;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) det[t * 6 + k] = 0.0f;
+            index[t] = -1;
+        }
+    }
+    if (tid == 0) nkeep_all[b] = kept;
+}
+
+struct NmsWs {
+    float* conf; int* cls; uint32_t *k0, *v0, *k1, *v1; int* order; float* sscore; int* count; float4* boxes;
+    size_t total;
+};
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+NmsWs carve(char* base, int B, int nc, int A, int cap, int multi_label) {
+    NmsWs w;
+    const size_t M = multi_label ? (size_t)A * nc : (size_t)A;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align256(bytes); return p; };
+    w.conf = (float*)take(sizeof(float) * B * M);
+    w.cls = (int*)take(sizeof(int) * (size_t)B * A);
+    w.k0 = (uint32_t*)take(4 * B * M);
+    w.v0 = (uint32_t*)take(4 * B * M);
+    w.k1 = (uint32_t*)take(4 * B * M);
+    w.v1 = (uint32_t*)take(4 * B * M);
+    w.order = (int*)take(sizeof(int) * (size_t)B * cap);
+    w.sscore = (float*)take(sizeof(float) * (size_t)B * cap);
+    w.count = (int*)take(sizeof(int) * (size_t)B);
+    w.boxes = (float4*)take(sizeof(float4) * (size_t)B * cap);
+    w.total = off;
+    return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+long long ysod_nms_workspace_bytes(int B, int nc, int A, int max_nms, int multi_label) {
+    const long long M = multi_label ? (long long)A * nc : (long long)A;
+    const int cap = (int)(M < max_nms ? M : max_nms);
+    return (long long)carve(nullptr, B, nc, A, cap > 0 ? cap : 1, multi_label).total;
+}
+
+// pred: (B, 4+nc, A) fp32 device, xywh + class scores (what Detect._inference returns, head.py:100-131).
+// thr_f: largest float <= the (double) IoU threshold. classes: device int array or NULL.
+// out_det: (B, max_det, 6) fp32; out_index: (B, max_det) int32 candidate ids (anchor, or anchor*nc+cls if
+// multi_label); out_count: (B) int32. Asynchronous on `stream`; no host sync; no global state.
+int ysod_nms_batched(const float* pred, int B, int nc, int A, float conf_thres, float thr_f, const int* classes,
+                     int n_classes, int agnostic, int multi_label, int max_det, int max_nms, float max_wh,
+                     float* out_det, int* out_index, int* out_count, void* workspace, long long workspace_bytes,
+                     cudaStream_t stream) {
+    YSOD_CHECK_ARG(pred && out_det && out_index && out_count && workspace, "ysod_nms_batched: null pointer");
+    YSOD_CHECK_ARG(B > 0 && nc > 0 && A > 0 && max_det > 0 && max_nms > 0, "ysod_nms_batched: bad sizes");
+    YSOD_CHECK_ARG(conf_thres >= 0.0f && conf_thres <= 1.0f, "Invalid Confidence threshold %f", conf_thres);
+    const long long M = multi_label ? (long long)A * nc : (long long)A;
+    const int cap = (int)(M < max_nms ? M : max_nms);
+    NmsWs w = carve((char*)workspace, B, nc, A, cap, multi_label);
+    if ((long long)w.total > workspace_bytes) {
+        ysod_set_error("ysod_nms_batched: workspace too small (%lld < %zu)", workspace_bytes, w.total);
+        return YSOD_ERR_WORKSPACE;
+    }
+    const size_t greedy_smem = (size_t)(((cap + 31) >> 5) + max_det) * 4;
+    YSOD_CHECK_ARG(greedy_smem <= 200 * 1024, "ysod_nms_batched: max_nms/max_det too large for shared memory");
+    {
+        dim3 grid(ysod_cdiv(A, 256), B);
+        nms_score_kernel<<<grid, 256, 0, stream>>>(pred, nc, A, conf_thres, classes, n_classes, multi_label, w.conf, w.cls);
+        YSOD_LAUNCH_CHECK();
+    }
+    nms_sort_kernel<<<B, SORT_THREADS, 0, stream>>>(w.conf, (int)M, cap, w.k0, w.v0, w.k1, w.v1, w.order, w.sscore, w.count);
+    YSOD_LAUNCH_CHECK();
+    {
+        dim3 grid(ysod_cdiv(cap, 256), B);
+        nms_gather_kernel<<<grid, 256, 0, stream>>>(pred, nc, A, cap, multi_label, w.order, w.cls, w.count,
+                                                    agnostic ? 0.0f : max_wh, w.boxes);
+        YSOD_LAUNCH_CHECK();
+    }
+    if (greedy_smem > 48 * 1024) {
+        YSOD_CUDA(cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)greedy_smem));
+    }
+    nms_greedy_kernel<<<B, GREEDY_THREADS, greedy_smem, stream>>>(pred, nc, A, cap, multi_label, max_det, thr_f, w.boxes,
+                                                                  w.order, w.sscore, w.cls, w.count, out_det, out_index,
+                                                                  out_count);
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,409 @@
+// Implicit-GEMM convolution / linear layer on the 5th-gen tensor cores (tcgen05 + TMEM), operands fed by TMA.
+//
+// Replaces (reference): every dense Conv2d(+BN)+act on the path -- ultralytics/nn/modules/conv.py:37-55 (Conv),
+// block.py:233-356 (C2f/Bottleneck convs), head.py:43-57 (Detect cv2/cv3), and the nn.Linear / in_proj / out_proj
+// GEMMs of nn.MultiheadAttention (blocks_transformer.py:98-106, a2_attn.py:29) -- which the reference hands to
+// cuDNN/cuBLAS plus separate BN / SiLU / add / cat kernels.
+//
+// GEMM view: D[M = pixels, N = Cout] = sum over K = (r, s, cin) of A[pixel shifted by tap (r,s), cin] * Wt[cout, K].
+//   * activations are NHWC bf16 (any channel-sliced view: pixel stride `xcs`), weights [Cout_pad][k*k*Cin] bf16
+//     (K-major, BN already folded in), bias fp32.
+//   * A CTA owns one TH x TW patch of output pixels of one image (TH*TW <= 128 = UMMA M) and BN output channels.
+//   * For every K block (one filter tap x BK input channels) ONE 4-D tiled TMA box {BK, TW, TH, 1} lands the
+//     shifted patch directly in the canonical K-major 128B/64B-swizzled UMMA layout (row = pixel, 128/64 B of
+//     channels); the conv zero padding is TMA out-of-bounds fill; stride-2 convs use TMA element strides {1,2,2,1}.
+//     No im2col buffer ever exists in HBM.
+//   * warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + tcgen05.mma issuer (one lane),
+//     warps 2..5 = epilogue: tcgen05.ld -> +bias -> act -> (+residual) -> bf16/fp32 -> 16 B stores into a channel
+//     slice of the consumer's NHWC buffer (this is what removes Concat/chunk copies).
+//   * smem ring of `stages` {A,B} tiles with full/empty mbarriers; accumulator (128 lanes x BN fp32 columns) in TMEM.
+//
+// BN/BK/stage count are runtime values (instruction + smem descriptors are built from them), so one kernel
+// serves every layer shape; two CTAs per SM co-reside for the common configs to hide prologue/epilogue.
+#include "common.cuh"
+#include <cuda.h>
+#include <new>
+
+namespace {
+
+struct TcParams {
+    int N, Ho, Wo, TH, TW, tiles_h, tiles_w;
+    int Cin, ksize, stride, pad;
+    int BN, BK, stages, tmem_cols, num_k;
+    int Cout;
+    void* out;
+    int out_f32;
+    int ocs;
+    const float* bias;
+    const __nv_bfloat16* res;
+    int rcs;
+    int act;
+    uint32_t idesc;
+    uint32_t desc_hi;  // SBO | version | layout type (upper 32 bits of the smem descriptor)
+    uint32_t a_bytes, b_bytes, a_tx;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+// the "+r" operands tie the loaded registers to the wait so no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait(uint32_t* v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :
+                 : "memory");
+}
+
+constexpr int TC_THREADS = 192;
+
+__global__ void __launch_bounds__(TC_THREADS)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_base = base;
+    const uint32_t b_base = base + (uint32_t)p.stages * p.a_bytes;
+    const uint32_t bar_base = b_base + (uint32_t)p.stages * p.b_bytes;  // 8-byte aligned (tiles are 1 KB multiples)
+    // full[s] = bar_base + 8*s ; empty[s] = bar_base + 8*(stages+s) ; tmem_full = bar_base + 16*stages ; slot after
+    const uint32_t tmem_full_bar = bar_base + 16u * p.stages;
+    const uint32_t tmem_slot = tmem_full_bar + 8u;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // tile coordinates
+    const int tiles_per_img = p.tiles_h * p.tiles_w;
+    const int img = blockIdx.x / tiles_per_img;
+    const int trem = blockIdx.x - img * tiles_per_img;
+    const int oh0 = (trem / p.tiles_w) * p.TH;
+    const int ow0 = (trem % p.tiles_w) * p.TW;
+    const int n0 = blockIdx.y * p.BN;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(bar_base + 8u * s, 1);
+            mbar_init(bar_base + 8u * (p.stages + s), 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_acc;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_acc) : "r"(tmem_slot) : "memory");
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            const int cchunks = p.Cin / p.BK;
+            const uint32_t tx = p.a_tx + p.b_bytes;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < p.num_k; ++kb) {
+                mbar_wait(bar_base + 8u * (p.stages + stage), phase ^ 1u);
+                const int tap = kb / cchunks;
+                const int cc = kb - tap * cchunks;
+                const int r = tap / p.ksize, s = tap - r * p.ksize;
+                const uint32_t full = bar_base + 8u * stage;
+                mbar_expect_tx(full, tx);
+                tma_load_4d(a_base + (uint32_t)stage * p.a_bytes, &tmA, full, cc * p.BK, ow0 * p.stride + s - p.pad,
+                            oh0 * p.stride + r - p.pad, img);
+                tma_load_2d(b_base + (uint32_t)stage * p.b_bytes, &tmB, full, tap * p.Cin + cc * p.BK, n0);
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            const int ksteps = p.BK / 16;
+            for (int kb = 0; kb < p.num_k; ++kb) {
+                mbar_wait(bar_base + 8u * stage, phase);
+                tc_fence_after();
+                const uint32_t a_addr = a_base + (uint32_t)stage * p.a_bytes;
+                const uint32_t b_addr = b_base + (uint32_t)stage * p.b_bytes;
+                for (int k = 0; k < ksteps; ++k) {
+                    // descriptor: start address (>>4) advanced by 32 B per UMMA_K inside the swizzle row; LBO = 1
+                    const uint64_t adesc = ((uint64_t)p.desc_hi << 32) | (uint64_t)(((a_addr + 32u * k) >> 4) & 0x3FFFu) | (1ull << 16);
+                    const uint64_t bdesc = ((uint64_t)p.desc_hi << 32) | (uint64_t)(((b_addr + 32u * k) >> 4) & 0x3FFFu) | (1ull << 16);
+                    tc_mma_bf16(tmem_acc, adesc, bdesc, p.idesc, (uint32_t)((kb | k) != 0));
+                }
+                tc_commit(bar_base + 8u * (p.stages + stage));  // frees the smem slot when these MMAs retire
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
+            tc_commit(tmem_full_bar);  // accumulator complete
+        }
+    } else {
+        // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4 =====
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const int th = m / p.TW, tw = m - th * p.TW;
+        const int oh = oh0 + th, ow = ow0 + tw;
+        const bool valid = (m < p.TH * p.TW) && (oh < p.Ho) && (ow < p.Wo);
+        const size_t pix = ((size_t)img * p.Ho + oh) * p.Wo + ow;
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_acc + ((uint32_t)(q * 32) << 16);
+        for (int c0 = 0; c0 < p.BN; c0 += 16) {
+            const int col = n0 + c0;
+            if (col >= p.Cout) break;  // warp-uniform
+            uint32_t v[16];
+            tmem_ld16(trow + (uint32_t)c0, v);
+            tmem_ld_wait(v);
+            if (!valid) continue;
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = ysod_act(__uint_as_float(v[j]) + __ldg(p.bias + col + j), p.act);
+            const bool full_chunk = (col + 16 <= p.Cout);
+            if (p.res != nullptr) {
+                const __nv_bfloat16* rp = p.res + pix * p.rcs + col;
+                if (full_chunk) {
+                    float r8[8];
+                    ysod_vec8<__nv_bfloat16>::load(rp, r8);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[j] += r8[j];
+                    ysod_vec8<__nv_bfloat16>::load(rp + 8, r8);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[8 + j] += r8[j];
+                } else {
+                    for (int j = 0; j < 16 && col + j < p.Cout; ++j) f[j] += __bfloat162float(rp[j]);
+                }
+            }
+            if (p.out_f32) {
+                float* op = (float*)p.out + pix * p.ocs + col;
+                if (full_chunk) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                } else {
+                    for (int j = 0; j < 16 && col + j < p.Cout; ++j) op[j] = f[j];
+                }
+            } else {
+                __nv_bfloat16* op = (__nv_bfloat16*)p.out + pix * p.ocs + col;
+                if (full_chunk) {
+                    ysod_vec8<__nv_bfloat16>::store(op, f);
+                    ysod_vec8<__nv_bfloat16>::store(op + 8, f + 8);
+                } else {
+                    for (int j = 0; j < 16 && col + j < p.Cout; ++j) op[j] = __float2bfloat16_rn(f[j]);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
+// ---- host side --------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+struct ConvTc {
+    CUtensorMap tmA, tmB;
+    TcParams p;
+    dim3 grid;
+    size_t smem;
+};
+
+}  // namespace
+
+struct ysod_conv_tc { ConvTc c; };
+
+extern "C" {
+
+// Creates a launch plan (TMA descriptors + tiling) for one conv / linear layer with fixed device pointers.
+//   x      : NHWC bf16 input view, N x H x W x Cin, pixel stride xcs elements (xcs % 8 == 0, 16 B aligned)
+//   wgt    : [Cout_pad][ksize*ksize*Cin] bf16, K ordered (r, s, cin); Cout_pad % 16 == 0, rows >= Cout are zero
+//   bias   : [Cout_pad] fp32 (BN folded / conv bias / zeros)
+//   out    : NHWC view, pixel stride ocs elements; out_dtype YSOD_BF16 or YSOD_F32
+//   res    : optional NHWC bf16 residual added AFTER the activation (Bottleneck / transformer skip), stride rcs
+// ksize in {1,3}, stride in {1,2} (pad = ksize/2, conv.py:28 autopad), groups == 1, Cin % 32 == 0.
+int ysod_conv_tc_create(ysod_conv_tc** handle, const void* x, int N, int H, int W, int Cin, int xcs, const void* wgt,
+                        const float* bias, int Cout, int Cout_pad, int ksize, int stride, void* out, int out_dtype, int ocs,
+                        const void* res, int rcs, int act) {
+    YSOD_CHECK_ARG(handle && x && wgt && bias && out, "ysod_conv_tc_create: null pointer");
+    YSOD_CHECK_ARG(ksize == 1 || ksize == 3, "ysod_conv_tc_create: ksize %d unsupported", ksize);
+    YSOD_CHECK_ARG(stride == 1 || stride == 2, "ysod_conv_tc_create: stride %d unsupported", stride);
+    YSOD_CHECK_ARG(Cin % 32 == 0 && Cin >= 32, "ysod_conv_tc_create: Cin %d must be a multiple of 32", Cin);
+    YSOD_CHECK_ARG(Cout_pad % 16 == 0 && Cout <= Cout_pad && Cout > 0, "ysod_conv_tc_create: bad Cout %d / pad %d", Cout, Cout_pad);
+    YSOD_CHECK_ARG(xcs % 8 == 0 && ((uintptr_t)x % 16) == 0, "ysod_conv_tc_create: input view not 16 B aligned");
+    YSOD_CHECK_ARG(out_dtype == YSOD_BF16 || out_dtype == YSOD_F32, "ysod_conv_tc_create: bad out dtype");
+    const int oalign = out_dtype == YSOD_BF16 ? 8 : 4;
+    YSOD_CHECK_ARG(ocs % oalign == 0 && ((uintptr_t)out % 16) == 0, "ysod_conv_tc_create: output view not 16 B aligned");
+    YSOD_CHECK_ARG(!res || (rcs % 8 == 0 && ((uintptr_t)res % 16) == 0), "ysod_conv_tc_create: residual view not 16 B aligned");
+    YSOD_CHECK_ARG(stride == 1 || (H % 2 == 0 && W % 2 == 0), "ysod_conv_tc_create: stride-2 needs even H, W");
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        ysod_set_error("ysod_conv_tc_create: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+        return YSOD_ERR_CUDA;
+    }
+    ConvTc c;
+    memset(&c, 0, sizeof(c));
+    TcParams& p = c.p;
+    const int pad = ksize / 2;
+    const int Ho = (H + 2 * pad - ksize) / stride + 1, Wo = (W + 2 * pad - ksize) / stride + 1;
+    // pick the output patch TH x TW (<= 128 pixels) with the best row utilisation of the M = 128 MMA
+    int bestTW = 1, bestTH = 1;
+    double best = -1.0;
+    const int maxTW = Wo < 128 ? Wo : 128;
+    for (int tw = 1; tw <= maxTW; ++tw) {
+        int th = 128 / tw;
+        if (th > Ho) th = Ho;
+        if (th > 128) th = 128;
+        const long long tiles = (long long)ysod_cdiv(Ho, th) * ysod_cdiv(Wo, tw);
+        const double util = (double)Ho * Wo / ((double)tiles * 128.0);
+        if (util > best + 1e-9 || (util > best - 1e-9 && tw > bestTW && tw <= 32)) { best = util; bestTW = tw; bestTH = th; }
+    }
+    p.N = N; p.Ho = Ho; p.Wo = Wo; p.TH = bestTH; p.TW = bestTW;
+    p.tiles_h = ysod_cdiv(Ho, bestTH); p.tiles_w = ysod_cdiv(Wo, bestTW);
+    p.Cin = Cin; p.ksize = ksize; p.stride = stride; p.pad = pad;
+    p.BK = (Cin % 64 == 0) ? 64 : 32;
+    int BN = Cout_pad;
+    if (BN > 256) {
+        BN = 256;
+        while (Cout_pad % BN != 0) BN -= 16;  // largest multiple of 16 <= 256 dividing Cout_pad
+    }
+    p.BN = BN;
+    p.tmem_cols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    p.num_k = ksize * ksize * (Cin / p.BK);
+    p.Cout = Cout;
+    p.out = out; p.out_f32 = (out_dtype == YSOD_F32); p.ocs = ocs;
+    p.bias = bias; p.res = (const __nv_bfloat16*)res; p.rcs = rcs; p.act = act;
+    p.a_bytes = 128u * p.BK * 2u;
+    p.b_bytes = (uint32_t)BN * p.BK * 2u;
+    p.a_tx = (uint32_t)(bestTH * bestTW) * p.BK * 2u;
+    // instruction descriptor (kind::f16): D=f32, A=B=bf16, both K-major, N>>3 @17, M>>4 @24
+    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+    // smem descriptor high word: SBO (8 rows x swizzle span) >> 4 @ bits 32-45, version 1 @ 46, layout @ 61
+    const uint32_t sbo = (p.BK == 64 ? 1024u : 512u) >> 4;
+    const uint32_t layout = (p.BK == 64) ? 2u : 4u;  // SWIZZLE_128B : SWIZZLE_64B
+    p.desc_hi = sbo | (1u << 14) | (layout << 29);
+    const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+    uint32_t budget = (3u * stage_bytes <= 100u * 1024u) ? 100u * 1024u : 200u * 1024u;
+    int stages = (int)(budget / stage_bytes);
+    if (stages > 8) stages = 8;
+    if (stages > p.num_k) stages = p.num_k;
+    if (stages < 1) stages = 1;
+    p.stages = stages;
+    c.smem = (size_t)stages * stage_bytes + 1024 + 16 * stages + 64;
+    c.grid = dim3((unsigned)((long long)N * p.tiles_h * p.tiles_w), (unsigned)(Cout_pad / BN), 1);
+
+    const CUtensorMapSwizzle swz = p.BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)xcs * 2, (cuuint64_t)W * xcs * 2, (cuuint64_t)H * W * xcs * 2};
+        cuuint32_t box[4] = {(cuuint32_t)p.BK, (cuuint32_t)(bestTW * stride), (cuuint32_t)(bestTH * stride), 1};
+        cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+        CUresult r = enc(&c.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            ysod_set_error("ysod_conv_tc_create: cuTensorMapEncodeTiled(A) failed with %d (Cin %d W %d H %d N %d xcs %d box %d,%d,%d)",
+                           (int)r, Cin, W, H, N, xcs, p.BK, bestTW * stride, bestTH * stride);
+            return YSOD_ERR_CUDA;
+        }
+    }
+    {
+        const cuuint64_t K = (cuuint64_t)ksize * ksize * Cin;
+        cuuint64_t dims[2] = {K, (cuuint64_t)Cout_pad};
+        cuuint64_t strides[1] = {K * 2};
+        cuuint32_t box[2] = {(cuuint32_t)p.BK, (cuuint32_t)BN};
+        cuuint32_t es[2] = {1, 1};
+        CUresult r = enc(&c.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wgt), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            ysod_set_error("ysod_conv_tc_create: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+            return YSOD_ERR_CUDA;
+        }
+    }
+    YSOD_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    ysod_conv_tc* h = new (std::nothrow) ysod_conv_tc;
+    YSOD_CHECK_ARG(h, "ysod_conv_tc_create: out of memory");
+    h->c = c;
+    *handle = h;
+    return YSOD_OK;
+}
+
+int ysod_conv_tc_run(ysod_conv_tc* h, cudaStream_t stream) {
+    YSOD_CHECK_ARG(h, "ysod_conv_tc_run: null handle");
+    conv_tc_kernel<<<h->c.grid, TC_THREADS, h->c.smem, stream>>>(h->c.tmA, h->c.tmB, h->c.p);
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+// tiling chosen for a plan: out[0..7] = TH, TW, BN, BK, stages, grid.x, grid.y, smem bytes
+int ysod_conv_tc_info(ysod_conv_tc* h, int* out8) {
+    YSOD_CHECK_ARG(h && out8, "ysod_conv_tc_info: null");
+    out8[0] = h->c.p.TH; out8[1] = h->c.p.TW; out8[2] = h->c.p.BN; out8[3] = h->c.p.BK; out8[4] = h->c.p.stages;
+    out8[5] = (int)h->c.grid.x; out8[6] = (int)h->c.grid.y; out8[7] = (int)h->c.smem;
+    return YSOD_OK;
+}
+
+void ysod_conv_tc_destroy(ysod_conv_tc* h) { delete h; }
+
+}  // extern "C"
