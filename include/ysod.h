@@ -1,0 +1,101 @@
+/* ysod.h -- C ABI of libysod.so: hand-written sm_100a kernels for the YOLOv12-SOD inference hot path.
+ *
+ * The reference (quitedob/yolo-sod) is 100% Python and has no C/FFI/plugin ABI; its seams are the
+ * Python objects `DetectionModel.forward` and `ops.non_max_suppression`. This header is therefore the boundary a
+ * maintainer would bind from Python with ctypes (INTEGRATION.md shows the stub); each entry point cites the reference
+ * code it replaces (paths relative to the reference checkout).
+ *
+ * Conventions: plain pointers and sizes, no torch types. Every function returns 0 on success, non-zero on error
+ * (ysod_last_error() gives the text), is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant, keeps no
+ * global state, performs no hidden host synchronisation and allocates nothing -- the caller owns all buffers.
+ * Device only: there is no CPU fallback. Activations are NHWC "views": element (n,h,w,c) at base[((n*H+h)*W+w)*cs + c]
+ * with `cs` = pixel stride in elements (>= C), which is how producers write into channel slices of a consumer's buffer.
+ * dtype: 0 = fp32, 1 = bf16 (storage; all math is fp32 / fp32-accumulate). act: 0 none 1 SiLU 2 GELU(erf) 3 ReLU
+ * 4 sigmoid 5 h-sigmoid. Channel counts and pixel strides of vectorised kernels must be multiples of 8.
+ */
+#ifndef YSOD_H
+#define YSOD_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int ysod_version(void);
+const char* ysod_last_error(void);
+int ysod_compiled_arch(void); /* 100 = sm_100a */
+
+/* ---- NMS: ultralytics/utils/ops.py:167-316 non_max_suppression + torchvision.ops.nms (ops.py:296) ---------------- */
+long long ysod_nms_workspace_bytes(int B, int nc, int A, int max_nms, int multi_label);
+/* pred (B,4+nc,A) fp32 xywh+scores; thr_f = largest float <= IoU threshold; classes = device int[n_classes] or NULL.
+ * out_det (B,max_det,6) [x1,y1,x2,y2,conf,cls]; out_index (B,max_det) kept candidate ids; out_count (B). */
+int ysod_nms_batched(const float* pred, int B, int nc, int A, float conf_thres, float thr_f, const int* classes,
+                     int n_classes, int agnostic, int multi_label, int max_det, int max_nms, float max_wh,
+                     float* out_det, int* out_index, int* out_count, void* workspace, long long workspace_bytes, void* stream);
+
+/* torchvision.ops.nms(boxes, scores, iou) drop-in (call site ops.py:296): boxes (n,4) xyxy, scores (n), device fp32.
+ * keep_out int32[max_keep] (score-descending, -1 padded), nkeep_out int32[1]. */
+long long ysod_nms_boxes_workspace_bytes(int n);
+int ysod_nms_boxes(const float* boxes, const float* scores, int n, float thr_f, int max_keep, int* keep_out, int* nkeep_out,
+                   void* workspace, long long workspace_bytes, void* stream);
+
+/* ---- Detect decode: head.py:100-131 _inference, block.py:64-83 DFL, tal.py:333-357 make_anchors/dist2bbox --------- */
+int ysod_dfl_decode(const void* raw, int dtype, int B, int H, int W, int cs, int nc, int reg_max, float stride, float* y,
+                    int A_total, int a_off, void* stream);
+
+/* ---- tensor-core implicit-GEMM conv / linear: conv.py:37-55 Conv (BN folded, torch_utils.py:238-265),
+ *      block.py:233-356 C2f/Bottleneck, head.py:43-57 Detect stacks, nn.MultiheadAttention / nn.Linear GEMMs ---------- */
+typedef struct ysod_conv_tc ysod_conv_tc;
+int ysod_conv_tc_create(ysod_conv_tc** handle, const void* x, int N, int H, int W, int Cin, int xcs, const void* wgt,
+                        const float* bias, int Cout, int Cout_pad, int ksize, int stride, void* out, int out_dtype, int ocs,
+                        const void* res, int rcs, int act);
+int ysod_conv_tc_run(ysod_conv_tc* handle, void* stream);
+int ysod_conv_tc_info(ysod_conv_tc* handle, int* out8);
+void ysod_conv_tc_destroy(ysod_conv_tc* handle);
+
+/* ---- CUDA-core convs: stem (Cin=3, NCHW fp32 image in), depthwise, grouped, and the fp32 parity mode ---------------- */
+int ysod_conv_direct(const void* x, int dtype, int N, int H, int W, int Cin, int xcs, const void* w, const float* bias,
+                     int Cout, int k, int s, int pad, int groups, void* out, int out_dtype, int ocs, const void* res, int rcs,
+                     int act, void* stream);
+int ysod_dwconv(const void* x, int dtype, int N, int H, int W, int C, int xcs, const void* w, const float* bias, int k, int s,
+                int pad, void* out, int ocs, const void* res, int rcs, int act, void* stream);
+int ysod_stem_conv(const float* img, int N, int H, int W, const float* w, const float* bias, int Cout, int k, int s, int pad,
+                   void* out, int out_dtype, int ocs, int act, void* stream);
+
+/* ---- SE: smallobj_modules.py:57-92 ; CBAM: cbam_block.py:8-55 ; CoordAtt: ca_block.py:16-59 ------------------------- */
+int ysod_gap_partial(const void* x, int dtype, int N, int HW, int C, int xcs, int S, float* psum, float* pmax, void* stream);
+int ysod_se_gate(const float* psum, int N, int S, int HW, int C, const float* w1, const float* b1, const float* w2,
+                 const float* b2, int hid, float* gate, void* stream);
+int ysod_cbam_gate(const float* psum, const float* pmax, int N, int S, int HW, int C, const float* w1, const float* w2, int hid,
+                   float* gate, void* stream);
+int ysod_scale_channels(const void* x, int dtype, int N, int HW, int C, int xcs, const float* gate, void* out, int ocs, void* stream);
+int ysod_cbam_stats(const void* x, int dtype, int N, int HW, int C, int xcs, const float* gate, float* stats, void* stream);
+int ysod_cbam_apply(const void* x, int dtype, int N, int H, int W, int C, int xcs, const float* gate, const float* stats,
+                    const float* wsp, int ks, void* out, int ocs, void* stream);
+int ysod_ca_pool(const void* x, int dtype, int N, int H, int W, int C, int xcs, float* pooled, void* stream);
+int ysod_ca_gate(const float* pooled, int N, int H, int W, int C, int mip, const float* w1, const float* b1, const float* wh,
+                 const float* bh, const float* ww, const float* bw, float* att, void* stream);
+int ysod_ca_apply(const void* x, int dtype, int N, int H, int W, int C, int xcs, const float* att, void* out, int ocs, void* stream);
+
+/* ---- SPPF pooling: block.py:178-197 ; nn.Upsample(nearest)+Concat: tasks.py:184, conv.py:323-334 -------------------- */
+int ysod_sppf_pool(const void* y0, int dtype, int N, int H, int W, int C, int xcs, int k, void* o1, void* o2, void* o3, int ocs,
+                   void* stream);
+int ysod_upsample_copy(const void* x, int dtype, int N, int H, int W, int C, int xcs, int scale, void* out, int ocs, void* stream);
+
+/* ---- Swin window attention plumbing: blocks_transformer.py:8-79,98-131 ; A2_Attn pooling/upsample: a2_attn.py:44-60 - */
+int ysod_layernorm(const void* x, int dtype, long long rows, int C, int ldx, const float* gamma, const float* beta, float eps,
+                   void* out, int ldo, void* stream);
+int ysod_window_partition_ln(const void* x, int dtype, int N, int H, int W, int C, int xcs, int wh, int ww, int nWh, int nWw,
+                             const float* gamma, const float* beta, float eps, void* raw_out, void* norm_out, int ldo, void* stream);
+int ysod_window_reverse(const void* tok, int dtype, int ldt, int N, int H, int W, int C, int wh, int ww, int nWh, int nWw, void* out,
+                        int ocs, void* stream);
+int ysod_adaptive_pool_rows(const void* x, int dtype, int N, int H, int W, int C, int xcs, int OH, void* out, int ocs, void* stream);
+int ysod_bilinear_rows(const void* x, int dtype, int N, int IH, int W, int C, int xcs, int OH, void* out, int ocs, void* stream);
+
+/* ---- softmax attention core: nn.MultiheadAttention internals (blocks_transformer.py:116, a2_attn.py:53) and the manual
+ *      path of AAttn (block.py:1348-1357). q/k/v addressed as ptr + batch*bs + token*ld + head*D (elements). ----------- */
+int ysod_mha_core(const void* q, const void* k, const void* v, int dtype, int batch, int L, int heads, int D, int ldq, int ldk,
+                  int ldv, long long bsq, long long bsk, long long bsv, float scale, void* out, int ldo, long long bso, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YSOD_H */

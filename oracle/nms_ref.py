@@ -130,7 +130,7 @@ def _nan_sort(scores):
 
 def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False,
                         multi_label=False, labels=(), max_det=300, nc=0, max_time_img=0.05,
-                        max_nms=30000, max_wh=7680, in_place=True, rotated=False):
+                        max_nms=30000, max_wh=7680, in_place=True, rotated=False, return_index=False):
     """ops.py:167-316 restated for the detection hot path (nm == 0, labels == (), not rotated).
 
     prediction: (B, 4+nc, A) float32, xywh + class scores. Returns a list of (n_i, 6) float32
@@ -152,8 +152,10 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
     xc = prediction[:, 4:4 + nc].max(1) > conf_t
     pred = np.transpose(prediction, (0, 2, 1))  # (B, A, 4+nc)
     out = [np.zeros((0, 6), dtype=F32) for _ in range(bs)]
+    out_idx = [np.zeros((0,), dtype=np.int64) for _ in range(bs)]  # candidate id: anchor, or anchor*nc+cls if multi_label
     for xi in range(bs):
         x = pred[xi][xc[xi]]
+        ids = np.nonzero(xc[xi])[0]
         if not x.shape[0]:
             continue
         box = xywh2xyxy(x[:, :4])
@@ -161,21 +163,26 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
         if multi_label and nc > 1:
             i, j = np.nonzero(cls > conf_t)
             x = np.concatenate((box[i], cls[i, j][:, None], j[:, None].astype(F32)), 1)
+            ids = ids[i] * nc + j
         else:
             j = cls.argmax(1)  # first maximal index, as torch.max(dim)
             conf = cls[np.arange(cls.shape[0]), j]
             x = np.concatenate((box, conf[:, None], j[:, None].astype(F32)), 1)[conf > conf_t]
+            ids = ids[conf > conf_t]
         if classes is not None:
-            x = x[np.isin(x[:, 5], np.asarray(classes, dtype=F32))]
+            sel = np.isin(x[:, 5], np.asarray(classes, dtype=F32))
+            x, ids = x[sel], ids[sel]
         n = x.shape[0]
         if not n:
             continue
         if n > max_nms:
             # reference: unstable argsort(descending); ties are implementation-defined there.
             # restated as stable (lower index first), which is what torch's CPU sort yields.
-            x = x[np.argsort(-x[:, 4].astype(np.float64), kind="stable")[:max_nms]]
+            top = np.argsort(-x[:, 4].astype(np.float64), kind="stable")[:max_nms]
+            x, ids = x[top], ids[top]
         c = x[:, 5:6] * F32(0 if agnostic else max_wh)
         boxes = x[:, :4] + c
         keep = (nms_c if (_clib() and not np.isnan(x[:, 4]).any()) else nms)(boxes, x[:, 4], iou_thres, limit=max_det)[:max_det]
         out[xi] = x[keep]
-    return out
+        out_idx[xi] = ids[keep]
+    return (out, out_idx) if return_index else out

@@ -1,0 +1,144 @@
+"""GPU parity of the tcgen05 implicit-GEMM conv (csrc/tc_conv.cu) and the CUDA-core convs against a plain torch fp32
+reference of the same op (CPU, on the bf16-rounded operands)."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import yolo_sod_b200  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+
+def _act(y, act):
+    return {"none": lambda t: t, "silu": F.silu, "gelu": F.gelu, "relu": F.relu}[act](y)
+
+
+def _run_tc(N, H, W, Cin, Cout, k, s, act="silu", res=False, out_f32=False, xcs_extra=0, ocs_extra=0, seed=0):
+    from yolo_sod_b200 import lib
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(N, H, W, Cin, generator=g).bfloat16()
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).bfloat16()
+    b = torch.randn(Cout, generator=g) * 0.1
+    pad = k // 2
+    Ho, Wo = (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1
+    r = torch.randn(N, Ho, Wo, Cout, generator=g).bfloat16() if res else None
+    ref = _act(F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, s, pad), act)
+    if res:
+        ref = ref + r.float().permute(0, 3, 1, 2)
+    # device buffers, optionally as channel slices of wider buffers
+    xcs, ocs = Cin + xcs_extra, Cout + ocs_extra
+    xb = torch.zeros(N, H, W, xcs, dtype=torch.bfloat16, device="cuda")
+    xb[..., xcs_extra:] = x.cuda()
+    ob = torch.full((N, Ho, Wo, ocs), 7.0, dtype=torch.float32 if out_f32 else torch.bfloat16, device="cuda")
+    cpad = (Cout + 15) // 16 * 16
+    wk = torch.zeros(cpad, k * k * Cin)
+    wk[:Cout] = w.float().permute(0, 2, 3, 1).reshape(Cout, -1)
+    wd = wk.bfloat16().cuda()
+    bd = torch.zeros(cpad)
+    bd[:Cout] = b
+    bd = bd.cuda()
+    rd = r.cuda().contiguous() if res else None
+    h = C.c_void_p()
+    lib.call("ysod_conv_tc_create", C.byref(h), lib.ptr(xb, xcs_extra), N, H, W, Cin, xcs, lib.ptr(wd), lib.ptr(bd), Cout, cpad, k, s,
+             lib.ptr(ob, ocs_extra), lib.F32 if out_f32 else lib.BF16, ocs, lib.ptr(rd) if res else None, Cout if res else 0,
+             lib.ACT[act])
+    info = (C.c_int * 8)()
+    lib.call("ysod_conv_tc_info", h, info)
+    lib.call("ysod_conv_tc_run", h, lib.stream_ptr())
+    torch.cuda.synchronize()
+    lib.load().ysod_conv_tc_destroy(h)
+    got = ob[..., ocs_extra:].float().cpu().permute(0, 3, 1, 2)
+    if ocs_extra:
+        assert bool((ob[..., :ocs_extra] == 7.0).all()), "kernel wrote outside its channel slice"
+    tol = 1e-4 if out_f32 else 1.0 / 128
+    err = (got - ref).abs()
+    bound = tol * ref.abs() + tol * ref.abs().max() + 1e-5
+    assert bool((err <= bound).all()), f"tile {list(info)} max err {err.max().item():.5f} (ref max {ref.abs().max().item():.3f})"
+
+
+CASES = [
+    # N, H, W, Cin, Cout, k, s, kwargs
+    (1, 16, 16, 64, 64, 1, 1, {}),                                  # single K block, BK=64
+    (2, 16, 32, 64, 64, 3, 1, {}),                                  # 3x3: 9 taps, zero padding through TMA OOB fill
+    (1, 40, 40, 64, 64, 3, 1, dict(res=True)),                      # 40x40 map (TW=40,TH=3, ragged last tile) + residual
+    (1, 20, 20, 256, 256, 3, 1, {}),                                # P5-like map, BN=256
+    (2, 32, 32, 64, 128, 3, 2, {}),                                 # stride 2 through TMA element strides
+    (1, 40, 40, 128, 256, 3, 2, dict(act="none")),
+    (1, 16, 16, 96, 64, 1, 1, {}),                                  # Cin=96 -> BK=32 / 64B swizzle
+    (1, 16, 16, 32, 32, 3, 1, {}),                                  # Cin=32 3x3 (32->32 @160 in the model)
+    (1, 8, 8, 256, 512, 1, 1, {}),                                  # two N tiles of 256
+    (1, 16, 16, 64, 10, 1, 1, dict(act="none", out_f32=True)),      # cls head: Cout 10 padded to 16, fp32 out
+    (1, 16, 16, 64, 64, 1, 1, dict(act="none", out_f32=True, ocs_extra=16)),  # box head into a slice of the raw map
+    (1, 1, 300, 64, 192, 1, 1, dict(act="none")),                   # linear: tokens x qkv (N=192)
+    (1, 1, 1000, 128, 64, 1, 1, dict(act="gelu", res=True)),        # linear + GELU + residual
+    (2, 16, 16, 64, 64, 3, 1, dict(xcs_extra=64, ocs_extra=32)),    # channel-sliced input and output views
+    (1, 24, 24, 512, 64, 3, 1, {}),                                 # long K (72 K blocks), ring wraps many times
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "x".join(str(v) for v in c[:7]))
+def test_conv_tc(case):
+    *dims, kw = case
+    _run_tc(*dims, **kw)
+
+
+def _run_direct(dtype, N, H, W, Cin, Cout, k, s, g, act="silu", res=False, pad=None):
+    from yolo_sod_b200 import lib
+    gen = torch.Generator().manual_seed(1)
+    td = torch.float32 if dtype == "f32" else torch.bfloat16
+    code = lib.F32 if dtype == "f32" else lib.BF16
+    pad = k // 2 if pad is None else pad
+    x = torch.randn(N, H, W, Cin, generator=gen).to(td)
+    w = (torch.randn(Cout, Cin // g, k, k, generator=gen) / (Cin // g * k * k) ** 0.5).to(td)
+    b = torch.randn(Cout, generator=gen) * 0.1
+    Ho, Wo = (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1
+    r = torch.randn(N, Ho, Wo, Cout, generator=gen).to(td) if res else None
+    ref = _act(F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, s, pad, 1, g), act)
+    if res:
+        ref = ref + r.float().permute(0, 3, 1, 2)
+    xd, bd = x.cuda(), b.cuda()
+    od = torch.empty(N, Ho, Wo, Cout, dtype=td, device="cuda")
+    rd = r.cuda() if res else None
+    if g == Cin == Cout and g > 1:
+        wd = w.view(Cout, k, k).permute(1, 2, 0).contiguous().cuda()
+        lib.call("ysod_dwconv", lib.ptr(xd), code, N, H, W, Cin, Cin, lib.ptr(wd), lib.ptr(bd), k, s, pad, lib.ptr(od), Cout,
+                 lib.ptr(rd) if res else None, Cout if res else 0, lib.ACT[act], lib.stream_ptr())
+    else:
+        wd = w.permute(0, 2, 3, 1).contiguous().cuda()
+        lib.call("ysod_conv_direct", lib.ptr(xd), code, N, H, W, Cin, Cin, lib.ptr(wd), lib.ptr(bd), Cout, k, s, pad, g, lib.ptr(od),
+                 code, Cout, lib.ptr(rd) if res else None, Cout if res else 0, lib.ACT[act], lib.stream_ptr())
+    torch.cuda.synchronize()
+    got = od.float().cpu().permute(0, 3, 1, 2)
+    tol = 1e-4 if dtype == "f32" else 1.0 / 128
+    err = (got - ref).abs()
+    assert bool((err <= tol * ref.abs() + tol * ref.abs().max() + 1e-5).all()), err.max().item()
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("case", [
+    (2, 12, 12, 64, 64, 3, 1, 1, {}), (1, 16, 16, 64, 128, 3, 2, 1, dict(res=True)), (1, 16, 16, 32, 64, 3, 2, 2, {}),
+    (1, 16, 16, 64, 64, 3, 2, 4, {}), (1, 9, 9, 64, 10, 1, 1, 1, dict(act="none")), (1, 12, 12, 64, 64, 3, 1, 64, dict(act="none")),
+    (1, 12, 12, 64, 64, 5, 1, 64, dict(act="none", res=True, pad=2)), (1, 14, 14, 96, 64, 1, 1, 1, dict(act="gelu")),
+], ids=lambda c: "x".join(str(v) for v in c[:8]))
+def test_conv_direct(dtype, case):
+    *dims, kw = case
+    _run_direct(dtype, *dims, **kw)
+
+
+@pytest.mark.parametrize("out", ["f32", "bf16"])
+def test_stem(out):
+    from yolo_sod_b200 import lib
+    gen = torch.Generator().manual_seed(2)
+    img = torch.rand(2, 3, 32, 48, generator=gen)
+    w = torch.randn(32, 3, 3, 3, generator=gen) / 27 ** 0.5
+    b = torch.randn(32, generator=gen) * 0.1
+    ref = F.silu(F.conv2d(img, w, b, 2, 1))
+    td = torch.float32 if out == "f32" else torch.bfloat16
+    od = torch.empty(2, 16, 24, 32, dtype=td, device="cuda")
+    lib.call("ysod_stem_conv", lib.ptr(img.cuda()), 2, 32, 48, lib.ptr(w.permute(0, 2, 3, 1).contiguous().cuda()), lib.ptr(b.cuda()), 32, 3, 2,
+             1, lib.ptr(od), lib.F32 if out == "f32" else lib.BF16, 32, lib.ACT["silu"], lib.stream_ptr())
+    torch.cuda.synchronize()
+    tol = 1e-5 if out == "f32" else 1.0 / 128
+    assert torch.allclose(od.float().cpu().permute(0, 3, 1, 2), ref, rtol=tol, atol=tol)

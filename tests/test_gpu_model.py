@@ -1,0 +1,131 @@
+"""GPU parity of the whole forward path (engine + every kernel) against the oracle and the live-reference goldens.
+
+Tolerances are the ones north_star states: raw head maps within rtol 1e-4 in fp32 mode and rtol 2e-2 in bf16 mode
+(plus an absolute floor of the same fraction of max|ref| for near-zero elements)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import yolo_sod_b200  # noqa: F401
+from yolo_sod_b200 import cfg as ycfg, synth
+from oracle import model_ref, nms_ref
+from tests.golden.make_golden_model import CASES as GOLD_CASES
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "model_golden.npz")
+SOD = "yolov12-sod-fusion-v5-simple"
+
+
+def _close(got, ref, tol):
+    err = (got - ref).abs()
+    bound = tol * ref.abs() + tol * ref.abs().max()
+    return bool((err <= bound).all()), float(err.max()), float(ref.abs().max())
+
+
+def _build(name, dtype, **kw):
+    from yolo_sod_b200.model import DetectionModel
+    spec = ycfg.get_spec(name)
+    sd = synth.synth_state_dict(spec, name, 0)
+    return spec, sd, DetectionModel(name, weights=sd, dtype=dtype, **kw)
+
+
+def _check(name, dtype, B, sz, tol, layer_tol=None, seed=11, **kw):
+    spec, sd, model = _build(name, dtype, **kw)
+    x = synth.synth_images(B, sz, seed=seed)
+    y, raw = model(x.cuda())
+    torch.cuda.synchronize()
+    (y_ref, raw_ref), layers = model_ref.forward(spec, sd, x, ycfg.strides_of(spec), return_layers=True)
+    report = []
+    for i in range(len(spec.layers) - 1):
+        got = model.layer_output(x, i).cpu()
+        ok, e, m = _close(got, layers[i], layer_tol or tol)
+        report.append((i, spec.layers[i].type, ok, round(e, 5), round(m, 3)))
+    bad = [r for r in report if not r[2]]
+    for l, (a, b) in enumerate(zip(raw, raw_ref)):
+        ok, e, m = _close(a.float().cpu(), b, tol)
+        assert ok, f"raw map {l}: max err {e} (ref max {m}); first bad layers: {bad[:4]}"
+    assert not bad, f"layer mismatches: {bad[:6]}"
+    # decoded boxes / scores: fp32 decode of our own raw maps must match the oracle decode of the same maps
+    y_dec = model_ref.detect_decode([r.float().cpu() for r in raw], ycfg.strides_of(spec), spec.nc)
+    assert torch.allclose(y.cpu(), y_dec, rtol=1e-4, atol=2e-3), float((y.cpu() - y_dec).abs().max())
+    return model, x, y, y_ref
+
+
+def test_sod_fp32_mode():
+    _check(SOD, torch.float32, 2, 128, 1e-4, layer_tol=2e-4)
+
+
+def test_sod_bf16_tensor_core_path():
+    model, x, y, y_ref = _check(SOD, torch.bfloat16, 2, 160, 2e-2, layer_tol=3e-2)
+    prog = model.program(2, 160, 160)
+    assert prog.n_tc > 60, "the dense convs must run on the tcgen05 kernel"
+
+
+def test_sod_bf16_cuda_core_crosscheck():
+    _check(SOD, torch.bfloat16, 1, 128, 2e-2, layer_tol=3e-2, use_tc=False)
+
+
+def test_sod_bf16_640_batch2():
+    _check(SOD, torch.bfloat16, 2, 640, 2e-2, layer_tol=3e-2, seed=99)
+
+
+def test_yolov12n_fp32_and_bf16():
+    _check("yolov12n", torch.float32, 2, 128, 1e-4, layer_tol=2e-4)
+    _check("yolov12n", torch.bfloat16, 1, 640, 2e-2, layer_tol=3e-2)
+
+
+def test_yolov12m_bf16():
+    _check("yolov12m", torch.bfloat16, 1, 128, 2e-2, layer_tol=3e-2)
+
+
+@pytest.mark.parametrize("case", GOLD_CASES, ids=lambda c: c[0])
+def test_against_live_reference_goldens(case):
+    key, name, _, b, sz = case
+    g = np.load(GOLD)
+    spec, sd, model = _build(name, torch.float32)
+    x = synth.synth_images(b, sz, seed=7)
+    y, raw = model(x.cuda())
+    assert np.allclose(y.cpu().numpy(), g[f"{key}_y"], rtol=1e-3, atol=5e-3)
+    for l, r in enumerate(raw):
+        ok, e, m = _close(r.float().cpu(), torch.from_numpy(g[f"{key}_raw{l}"].astype(np.float32)), 2e-3)
+        assert ok, (key, l, e, m)
+    spec, sd, model = _build(name, torch.bfloat16)
+    y, raw = model(x.cuda())
+    for l, r in enumerate(raw):
+        ok, e, m = _close(r.float().cpu(), torch.from_numpy(g[f"{key}_raw{l}"].astype(np.float32)), 2e-2)
+        assert ok, (key, l, e, m)
+
+
+def test_graph_replay_equals_eager_and_is_deterministic():
+    spec, sd, m_graph = _build(SOD, torch.bfloat16, use_graph=True)
+    _, _, m_eager = _build(SOD, torch.bfloat16, use_graph=False)
+    x = synth.synth_images(2, 128, seed=3).cuda()
+    y1 = m_graph(x)[0].clone()
+    y2 = m_eager(x)[0].clone()
+    y3 = m_graph(x)[0].clone()
+    assert torch.equal(y1, y2) and torch.equal(y1, y3)
+
+
+def test_predict_end_to_end_matches_oracle_nms():
+    from yolo_sod_b200.model import YOLO
+    from yolo_sod_b200 import ops
+    yolo = YOLO(SOD, dtype=torch.bfloat16)
+    x = synth.synth_images(2, 320, seed=21)
+    res = yolo.predict(x.cuda(), conf=0.25, iou=0.7, max_det=300)
+    y, _ = yolo.model(x.cuda())
+    want = nms_ref.non_max_suppression(y.cpu().numpy(), 0.25, 0.7, max_det=300)
+    assert len(res) == 2
+    for r, w in zip(res, want):
+        w = w.copy()
+        w[:, [0, 2]] = w[:, [0, 2]].clip(0, 320)
+        w[:, [1, 3]] = w[:, [1, 3]].clip(0, 320)
+        assert np.array_equal(r.boxes.data.cpu().numpy(), w)
+    assert sum(len(r) for r in res) > 0, "synthetic weights must produce detections"
+
+
+def test_missing_library_or_cpu_input_fails_loudly():
+    from yolo_sod_b200 import ops, lib
+    with pytest.raises(lib.YsodError):
+        ops.non_max_suppression(torch.zeros(1, 14, 100), 0.25, 0.7)

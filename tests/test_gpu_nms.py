@@ -1,0 +1,104 @@
+"""GPU parity: csrc/nms.cu (through the C ABI via yolo_sod_b200.ops) vs the oracle -- bit-exact keep indices and rows."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import yolo_sod_b200  # noqa: F401
+from oracle import nms_ref
+from tests import nms_cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from yolo_sod_b200 import ops
+    return ops
+
+
+@pytest.mark.parametrize("case", nms_cases.BOX_CASES, ids=lambda c: c[0])
+def test_box_nms_bit_exact(case):
+    name, fn, thr = case
+    boxes, scores = fn()
+    want = nms_ref.nms(boxes, scores, thr)
+    got = _ops().nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), thr).cpu().numpy()
+    assert np.array_equal(want, got), name
+    if len(want) > 5:
+        got5 = _ops().nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), thr, max_keep=5).cpu().numpy()
+        assert np.array_equal(want[:5], got5)
+
+
+@pytest.mark.parametrize("case", nms_cases.PRED_CASES + nms_cases.PRED_CASES_MULTILABEL, ids=lambda c: c[0])
+def test_pipeline_bit_exact(case):
+    name, fn, kw = case
+    pred = fn()
+    want, want_idx = nms_ref.non_max_suppression(pred.copy(), return_index=True, **kw)
+    got = _ops().non_max_suppression(torch.from_numpy(pred).cuda(), **kw)
+    assert len(want) == len(got)
+    for w, g in zip(want, got):
+        assert tuple(g.shape) == w.shape, (name, g.shape, w.shape)
+        assert np.array_equal(g.cpu().numpy(), w), name
+    kw2 = {k: v for k, v in kw.items()}
+    det, count, index = _ops().nms_padded(torch.from_numpy(pred).cuda(), **kw2)
+    for b, wi in enumerate(want_idx):
+        n = int(count[b])
+        assert n == len(wi)
+        assert np.array_equal(index[b, :n].cpu().numpy().astype(np.int64), wi), name
+
+
+def test_golden_fixture_from_live_reference():
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "nms_golden.npz"))
+    cases = nms_cases.PRED_CASES
+    for k in range(int(g["n_cases"])):
+        name, fn, kw = cases[k]
+        assert str(g[f"name{k}"]) == name
+        got = _ops().non_max_suppression(torch.from_numpy(fn()).cuda(), **kw)
+        for b, d in enumerate(got):
+            ref = g[f"c{k}_b{b}"]
+            assert ref.shape == tuple(d.shape) and np.array_equal(ref, d.cpu().numpy()), (name, b)
+
+
+def test_input_not_modified_and_asserts():
+    pred = torch.from_numpy(nms_cases.make_pred(1, 10, 500, 3)).cuda()
+    keep = pred.clone()
+    _ops().non_max_suppression(pred, 0.25, 0.7)
+    assert torch.equal(pred, keep)
+    with pytest.raises(AssertionError):
+        _ops().non_max_suppression(pred, 1.5, 0.7)
+    with pytest.raises(AssertionError):
+        _ops().non_max_suppression(pred, 0.25, -0.1)
+
+
+@pytest.mark.parametrize("clustered", [False, True])
+def test_stress_30k_vs_c_oracle(clustered):
+    """BASELINE.json config 5 at reduced batch: 30 000 candidates x 10 classes, IoU 0.7, max_det 300."""
+    pred = nms_cases.stress_pred(3, A=30000, clustered=clustered)
+    want, want_idx = nms_ref.non_max_suppression(pred.copy(), 0.25, 0.7, max_det=300, return_index=True)
+    det, count, index = _ops().nms_padded(torch.from_numpy(pred).cuda(), 0.25, 0.7, max_det=300)
+    for b in range(3):
+        n = int(count[b])
+        assert n == len(want[b])
+        assert np.array_equal(det[b, :n].cpu().numpy(), want[b])
+        assert np.array_equal(index[b, :n].cpu().numpy().astype(np.int64), want_idx[b])
+
+
+def test_full_size_properties_b64():
+    """Config 5 at full size (B=64): size-independent properties instead of an oracle run."""
+    pred = torch.from_numpy(nms_cases.stress_pred(64, A=30000, clustered=True)).cuda()
+    det, count, index = _ops().nms_padded(pred, 0.25, 0.7, max_det=300)
+    torch.cuda.synchronize()
+    cnt = count.cpu().numpy()
+    assert (cnt > 0).all() and (cnt <= 300).all()
+    d = det.cpu().numpy()
+    for b in range(0, 64, 7):
+        n = cnt[b]
+        s = d[b, :n, 4]
+        assert (np.diff(s) <= 0).all(), "scores must be non-increasing"
+        # idempotence: NMS over the kept boxes (with their class offsets) keeps every one of them
+        boxes = d[b, :n, :4] + d[b, :n, 5:6] * np.float32(7680)
+        again = nms_ref.nms_c(boxes, s, 0.7)
+        assert np.array_equal(again, np.arange(n))
+    # determinism
+    det2, count2, _ = _ops().nms_padded(pred, 0.25, 0.7, max_det=300)
+    assert torch.equal(det, det2) and torch.equal(count, count2)

@@ -65,9 +65,18 @@ __global__ void nms_score_kernel(const float* __restrict__ pred, int nc, int A, 
     }
 }
 
-// One CTA per image. conf: M entries (0 = not a candidate, >0 = score).
+// order-preserving float <-> uint32 map (negative floats reversed, sign bit flipped)
+__device__ __forceinline__ uint32_t float_to_ordered(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(uint32_t o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
+// One CTA per image. conf: M entries (0 = not a candidate, >0 = score) unless all_candidates.
 __global__ void __launch_bounds__(SORT_THREADS, 1)
-nms_sort_kernel(const float* __restrict__ conf_all, int M, int cap, uint32_t* __restrict__ ws_keys0,
+nms_sort_kernel(const float* __restrict__ conf_all, int M, int cap, int all_candidates, uint32_t* __restrict__ ws_keys0,
                 uint32_t* __restrict__ ws_vals0, uint32_t* __restrict__ ws_keys1, uint32_t* __restrict__ ws_vals1,
                 int* __restrict__ order_all, float* __restrict__ sscore_all, int* __restrict__ count_all) {
     const int b = blockIdx.x;
@@ -90,7 +99,7 @@ nms_sort_kernel(const float* __restrict__ conf_all, int M, int cap, uint32_t* __
     for (int start = 0; start < M; start += SORT_THREADS) {
         const int i = start + tid;
         const float s = (i < M) ? conf[i] : 0.0f;
-        const bool p = s > 0.0f;
+        const bool p = (i < M) && (all_candidates || s > 0.0f);
         const unsigned bal = __ballot_sync(0xffffffffu, p);
         if (lane == 0) s_warp_cnt[warp] = __popc(bal);
         __syncthreads();
@@ -108,7 +117,7 @@ nms_sort_kernel(const float* __restrict__ conf_all, int M, int cap, uint32_t* __
         __syncthreads();
         if (p) {
             const int pos = n + s_warp_off[warp] + __popc(bal & ((1u << lane) - 1u));
-            kin[pos] = ~__float_as_uint(s);  // positive floats: ascending ~bits == descending score
+            kin[pos] = ~float_to_ordered(s);  // ascending key == descending score (NaN first, like torch.sort)
             vin[pos] = (uint32_t)i;
         }
         n += s_chunk_total;
@@ -181,7 +190,7 @@ nms_sort_kernel(const float* __restrict__ conf_all, int M, int cap, uint32_t* __
     float* sscore = sscore_all + (size_t)b * cap;
     for (int i = tid; i < m; i += SORT_THREADS) {
         order[i] = (int)vin[i];
-        sscore[i] = __uint_as_float(~kin[i]);
+        sscore[i] = ordered_to_float(~kin[i]);
     }
     if (tid == 0) count_all[b] = m;
 }
@@ -289,17 +298,19 @@ nms_greedy_kernel(const float* __restrict__ pred, int nc, int A, int cap, int mu
         if (t < kept) {
             const int r = keep_idx[t];
             const int id = order_all[(size_t)b * cap + r];
+            index[t] = id;
+            if (pred == nullptr) continue;  // plain box-NMS mode: keep indices only
             const int a = multi_label ? id / nc : id;
             const int c = multi_label ? id % nc : cls_all[(size_t)b * A + a];
             const float4 q = load_xyxy(pred, b, nc, A, a);
             det[t * 6 + 0] = q.x; det[t * 6 + 1] = q.y; det[t * 6 + 2] = q.z; det[t * 6 + 3] = q.w;
             det[t * 6 + 4] = sscore_all[(size_t)b * cap + r];
             det[t * 6 + 5] = (float)c;
-            index[t] = id;
         } else {
+            index[t] = -1;
+            if (pred == nullptr) continue;
 #pragma unroll
             for (int k = 0; k < 6; ++k) det[t * 6 + k] = 0.0f;
-            index[t] = -1;
         }
     }
     if (tid == 0) nkeep_all[b] = kept;
@@ -366,7 +377,7 @@ int ysod_nms_batched(const float* pred, int B, int nc, int A, float conf_thres, 
         nms_score_kernel<<<grid, 256, 0, stream>>>(pred, nc, A, conf_thres, classes, n_classes, multi_label, w.conf, w.cls);
         YSOD_LAUNCH_CHECK();
     }
-    nms_sort_kernel<<<B, SORT_THREADS, 0, stream>>>(w.conf, (int)M, cap, w.k0, w.v0, w.k1, w.v1, w.order, w.sscore, w.count);
+    nms_sort_kernel<<<B, SORT_THREADS, 0, stream>>>(w.conf, (int)M, cap, 0, w.k0, w.v0, w.k1, w.v1, w.order, w.sscore, w.count);
     YSOD_LAUNCH_CHECK();
     {
         dim3 grid(ysod_cdiv(cap, 256), B);
@@ -380,6 +391,60 @@ int ysod_nms_batched(const float* pred, int B, int nc, int A, float conf_thres, 
     nms_greedy_kernel<<<B, GREEDY_THREADS, greedy_smem, stream>>>(pred, nc, A, cap, multi_label, max_det, thr_f, w.boxes,
                                                                   w.order, w.sscore, w.cls, w.count, out_det, out_index,
                                                                   out_count);
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+// Plain greedy NMS on explicit boxes: the drop-in for `torchvision.ops.nms(boxes, scores, iou)` (ops.py:296).
+// boxes (n,4) xyxy fp32, scores (n) fp32, both on the device. keep_out: int32[max_keep] indices into boxes,
+// score-descending (stable), -1 padded; nkeep_out: int32[1]. workspace >= ysod_nms_boxes_workspace_bytes(n).
+long long ysod_nms_boxes_workspace_bytes(int n) {
+    const size_t m = (size_t)(n > 0 ? n : 1);
+    return (long long)(4 * align256(4 * m) + align256(4 * m) + align256(4 * m) + align256(4) + align256(16 * m));
+}
+
+__global__ void nms_reorder_boxes_kernel(const float4* __restrict__ boxes, const int* __restrict__ order, const int* __restrict__ count,
+                                         float4* __restrict__ sorted) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < count[0]) sorted[r] = boxes[order[r]];
+}
+
+int ysod_nms_boxes(const float* boxes, const float* scores, int n, float thr_f, int max_keep, int* keep_out, int* nkeep_out,
+                   void* workspace, long long workspace_bytes, cudaStream_t stream) {
+    YSOD_CHECK_ARG(keep_out && nkeep_out && workspace && max_keep > 0, "ysod_nms_boxes: null pointer");
+    if (n <= 0) {
+        YSOD_CUDA(cudaMemsetAsync(nkeep_out, 0, sizeof(int), stream));
+        YSOD_CUDA(cudaMemsetAsync(keep_out, 0xff, sizeof(int) * (size_t)max_keep, stream));
+        return YSOD_OK;
+    }
+    YSOD_CHECK_ARG(boxes && scores, "ysod_nms_boxes: null pointer");
+    YSOD_CHECK_ARG(((uintptr_t)boxes % 16) == 0, "ysod_nms_boxes: boxes must be 16 B aligned");
+    if (ysod_nms_boxes_workspace_bytes(n) > workspace_bytes) {
+        ysod_set_error("ysod_nms_boxes: workspace too small");
+        return YSOD_ERR_WORKSPACE;
+    }
+    char* base = (char*)workspace;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* p = base + off; off += align256(bytes); return p; };
+    uint32_t* k0 = (uint32_t*)take(4 * (size_t)n);
+    uint32_t* v0 = (uint32_t*)take(4 * (size_t)n);
+    uint32_t* k1 = (uint32_t*)take(4 * (size_t)n);
+    uint32_t* v1 = (uint32_t*)take(4 * (size_t)n);
+    int* order = (int*)take(4 * (size_t)n);
+    float* sscore = (float*)take(4 * (size_t)n);
+    int* count = (int*)take(4);
+    float4* sorted = (float4*)take(16 * (size_t)n);
+    const size_t greedy_smem = (size_t)(((n + 31) >> 5) + max_keep) * 4;
+    YSOD_CHECK_ARG(greedy_smem <= 200 * 1024, "ysod_nms_boxes: n/max_keep too large for shared memory");
+    nms_sort_kernel<<<1, SORT_THREADS, 0, stream>>>(scores, n, n, 1, k0, v0, k1, v1, order, sscore, count);
+    YSOD_LAUNCH_CHECK();
+    nms_reorder_boxes_kernel<<<ysod_cdiv(n, 256), 256, 0, stream>>>((const float4*)boxes, order, count, sorted);
+    YSOD_LAUNCH_CHECK();
+    if (greedy_smem > 48 * 1024) {
+        YSOD_CUDA(cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)greedy_smem));
+    }
+    nms_greedy_kernel<<<1, GREEDY_THREADS, greedy_smem, stream>>>(nullptr, 0, 0, n, 0, max_keep, thr_f, sorted, order, sscore, nullptr,
+                                                                  count, nullptr, keep_out, nkeep_out);
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }

@@ -1,0 +1,585 @@
+"""Compiles a detector (layer spec + reference-named state_dict) into a static program of sm_100a kernel launches.
+
+This is the host side of the forward hot path. It replaces the reference's Python layer loop
+(ultralytics/nn/tasks.py:165-192 `_predict_once`), `BaseModel.fuse` (tasks.py:227-255 + utils/torch_utils.py:238-265
+BN folding, eps 1e-3) and the per-module forward methods, by:
+  * folding every BatchNorm (incl. the raw ones in SwinBlock.bn / CA_Block.bn1) into conv weights + fp32 bias,
+  * repacking weights K-major ([Cout][kh][kw][Cin]) in bf16 (fp32 in fp32 mode),
+  * planning NHWC activation buffers so that producers write straight into channel slices of their consumer's
+    buffer (Concat / chunk / cat never copy),
+  * emitting one flat list of C-ABI calls (lib.py) that is replayed per batch, optionally under a CUDA graph.
+Nothing here computes on the CPU at run time; if libysod.so or the GPU is missing it raises.
+"""
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from . import cfg as _cfg
+from . import lib as _lib
+
+BN_EPS = 1e-3   # utils/torch_utils.py:416-418
+LN_EPS = 1e-5   # torch.nn.LayerNorm default
+RAW_CS = 80     # pixel stride of the raw head maps (64 box + nc class channels, padded to a multiple of 8)
+
+
+@dataclass
+class View:
+    """NHWC view: element (n,h,w,c) lives at buf[off + ((n*H + h)*W + w)*cs + c]."""
+    buf: torch.Tensor
+    off: int
+    N: int
+    H: int
+    W: int
+    C: int
+    cs: int
+
+    def ptr(self):
+        return C.c_void_p(self.buf.data_ptr() + self.off * self.buf.element_size())
+
+    def slice(self, c0, c1):
+        return View(self.buf, self.off + c0, self.N, self.H, self.W, c1 - c0, self.cs)
+
+    def torch_nhwc(self):
+        t = self.buf[self.off:].as_strided((self.N, self.H, self.W, self.C), (self.H * self.W * self.cs, self.W * self.cs, self.cs, 1))
+        return t
+
+    def torch_nchw(self):
+        return self.torch_nhwc().permute(0, 3, 1, 2)
+
+
+class Program:
+    """A compiled forward for one (batch, H, W): buffers + launch list."""
+
+    def __init__(self, model: "B200DetectionModel", B: int, H: int, W: int):
+        self.m = model
+        self.B, self.H, self.W = B, H, W
+        self.dev = model.device
+        self.dt = model.dtype
+        self.code = _lib.BF16 if self.dt == torch.bfloat16 else _lib.F32
+        self.ops: List[tuple] = []       # (cfunc, args-without-stream)
+        self.keep: List[object] = []     # tensors / handles that must stay alive
+        self.tc_handles: List[C.c_void_p] = []
+        self.n_launches = 0
+        self.n_tc = 0
+        self.layer_out: Dict[int, View] = {}
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.img = torch.zeros((B, 3, H, W), device=self.dev, dtype=torch.float32)
+        self._build()
+
+    # ---- buffers -----------------------------------------------------------------------------------------
+    def new(self, N, H, W, Cc, dtype=None, zero=False):
+        dtype = dtype or self.dt
+        n = N * H * W * Cc
+        buf = (torch.zeros if zero else torch.empty)(n + 64, device=self.dev, dtype=dtype)
+        self.keep.append(buf)
+        return View(buf, 0, N, H, W, Cc, Cc)
+
+    def f32(self, *shape):
+        t = torch.empty(shape, device=self.dev, dtype=torch.float32)
+        self.keep.append(t)
+        return t
+
+    def dev_t(self, t, dtype=None):
+        t = t.detach().to(device=self.dev, dtype=dtype or torch.float32).contiguous()
+        self.keep.append(t)
+        return t
+
+    def emit(self, name, *args):
+        self.ops.append((getattr(_lib.load(), name), args, name))
+        self.n_launches += 1
+
+    # ---- conv emission -----------------------------------------------------------------------------------
+    def folded(self, pfx):
+        sd = self.m.sd
+        w = sd[f"{pfx}.conv.weight"].float()
+        g, b = sd[f"{pfx}.bn.weight"].float(), sd[f"{pfx}.bn.bias"].float()
+        mu, var = sd[f"{pfx}.bn.running_mean"].float(), sd[f"{pfx}.bn.running_var"].float()
+        s = g / torch.sqrt(var + BN_EPS)
+        return w * s.view(-1, 1, 1, 1), b - mu * s
+
+    def conv(self, x: View, w: torch.Tensor, bias: torch.Tensor, k, s, g, act, out: View, res: View = None,
+             out_f32=False, pad=None):
+        """w: (Cout, Cin/g, k, k) fp32 with BN folded; bias fp32 (Cout)."""
+        pad = k // 2 if pad is None else pad
+        Cout, Cin = w.shape[0], x.C
+        assert w.shape[1] * g == Cin, (w.shape, Cin, g)
+        Ho, Wo = (x.H + 2 * pad - k) // s + 1, (x.W + 2 * pad - k) // s + 1
+        assert (out.N, out.H, out.W, out.C) == (x.N, Ho, Wo, Cout), ((out.N, out.H, out.W, out.C), (x.N, Ho, Wo, Cout))
+        actc = _lib.ACT[act]
+        odt = _lib.F32 if out_f32 else self.code
+        if res is not None:
+            assert (res.N, res.H, res.W, res.C) == (out.N, out.H, out.W, out.C)
+        use_tc = (self.m.use_tc and self.code == _lib.BF16 and g == 1 and k in (1, 3) and s in (1, 2) and pad == k // 2
+                  and Cin % 32 == 0 and (s == 1 or (x.H % 2 == 0 and x.W % 2 == 0)))
+        if use_tc:
+            cpad = (Cout + 15) // 16 * 16
+            wk = torch.zeros((cpad, k * k * Cin), dtype=torch.float32)
+            wk[:Cout] = w.permute(0, 2, 3, 1).reshape(Cout, -1)
+            bk = torch.zeros(cpad, dtype=torch.float32)
+            bk[:Cout] = bias
+            wd, bd = self.dev_t(wk, torch.bfloat16), self.dev_t(bk)
+            h = C.c_void_p()
+            _lib.call("ysod_conv_tc_create", C.byref(h), x.ptr(), x.N, x.H, x.W, Cin, x.cs, _lib.ptr(wd), _lib.ptr(bd), Cout, cpad,
+                      k, s, out.ptr(), odt, out.cs, res.ptr() if res is not None else None, res.cs if res is not None else 0, actc)
+            self.tc_handles.append(h)
+            self.ops.append((_lib.load().ysod_conv_tc_run, (h,), "ysod_conv_tc_run"))
+            self.n_launches += 1
+            self.n_tc += 1
+            return
+        if g == Cin and g == Cout and g > 1:
+            wd = self.dev_t(w.view(Cout, k, k).permute(1, 2, 0), self.dt)  # [k][k][C]
+            bd = self.dev_t(bias)
+            assert not out_f32
+            self.emit("ysod_dwconv", x.ptr(), self.code, x.N, x.H, x.W, Cin, x.cs, _lib.ptr(wd), _lib.ptr(bd), k, s, pad, out.ptr(),
+                      out.cs, res.ptr() if res is not None else None, res.cs if res is not None else 0, actc)
+            return
+        wd = self.dev_t(w.permute(0, 2, 3, 1), self.dt)  # [Cout][k][k][Cin/g]
+        bd = self.dev_t(bias)
+        self.emit("ysod_conv_direct", x.ptr(), self.code, x.N, x.H, x.W, Cin, x.cs, _lib.ptr(wd), _lib.ptr(bd), Cout, k, s, pad, g,
+                  out.ptr(), odt, out.cs, res.ptr() if res is not None else None, res.cs if res is not None else 0, actc)
+
+    def conv_bn(self, x, pfx, k=1, s=1, g=1, act=True, out=None, res=None, pad=None):
+        """Reference `Conv` wrapper (conv.py:37-55) with BN folded."""
+        w, b = self.folded(pfx)
+        if out is None:
+            p = k // 2 if pad is None else pad
+            out = self.new(x.N, (x.H + 2 * p - k) // s + 1, (x.W + 2 * p - k) // s + 1, w.shape[0])
+        self.conv(x, w, b, k, s, g, "silu" if act else "none", out, res, pad=pad)
+        return out
+
+    def linear(self, x: View, w, b, act="none", out=None, res=None):
+        """x: token matrix as a (1,1,T,C) view; w: (out,in)."""
+        if out is None:
+            out = self.new(1, 1, x.W, w.shape[0])
+        self.conv(x, w.float().view(w.shape[0], w.shape[1], 1, 1), b.float(), 1, 1, 1, act, out, res)
+        return out
+
+    # ---- modules -----------------------------------------------------------------------------------------
+    def bottleneck(self, x, pfx, shortcut, g, out, k=(3, 3), e=1.0):
+        """block.py:343-356."""
+        mid = self.conv_bn(x, f"{pfx}.cv1", k[0])
+        add = shortcut and x.C == out.C
+        self.conv_bn(mid, f"{pfx}.cv2", k[1], 1, g, out=out, res=x if add else None)
+
+    def c2f(self, x, P, p, c2, out, c3k2=False):
+        """block.py:233-248 (C2f) / :733-741 (C3k2): cv1 -> chunk(2) -> n blocks -> cat -> cv2, with the cat buffer
+        written slice by slice."""
+        n = p["n"]
+        c = int(c2 * p["e"])
+        cat = self.new(x.N, x.H, x.W, (2 + n) * c)
+        self.conv_bn(x, f"{P}.cv1", out=cat.slice(0, 2 * c))
+        for j in range(n):
+            src, dst = cat.slice((1 + j) * c, (2 + j) * c), cat.slice((2 + j) * c, (3 + j) * c)
+            if c3k2 and p["c3k"]:
+                self.c3k(src, f"{P}.m.{j}", 2, p["shortcut"], p["g"], dst)
+            elif c3k2:
+                mid = self.conv_bn(src, f"{P}.m.{j}.cv1", 3)          # Bottleneck(c, c, shortcut, g) default e=0.5
+                self.conv_bn(mid, f"{P}.m.{j}.cv2", 3, 1, p["g"], out=dst, res=src if p["shortcut"] else None)
+            else:
+                self.bottleneck(src, f"{P}.m.{j}", p["shortcut"], p["g"], dst)
+        self.conv_bn(cat, f"{P}.cv2", out=out)
+
+    def c3k(self, x, P, n, shortcut, g, out):
+        """block.py:744-752 / :258-273: cv3(cat(m(cv1(x)), cv2(x)))."""
+        c_ = self.m.sd[f"{P}.cv1.conv.weight"].shape[0]
+        cat = self.new(x.N, x.H, x.W, 2 * c_)
+        cur = self.conv_bn(x, f"{P}.cv1") if n > 0 else None
+        for j in range(n):
+            dst = cat.slice(0, c_) if j == n - 1 else self.new(x.N, x.H, x.W, c_)
+            self.bottleneck(cur, f"{P}.m.{j}", shortcut, g, dst)
+            cur = dst
+        self.conv_bn(x, f"{P}.cv2", out=cat.slice(c_, 2 * c_))
+        self.conv_bn(cat, f"{P}.cv3", out=out)
+
+    def mha(self, tokens_norm: View, P, heads, batch, L, res: View = None):
+        """nn.MultiheadAttention self-attention (batch_first): packed in_proj -> core -> out_proj (+ residual)."""
+        sd = self.m.sd
+        E = tokens_norm.C
+        qkv = self.linear(tokens_norm, sd[f"{P}.in_proj_weight"], sd[f"{P}.in_proj_bias"])
+        ao = self.new(1, 1, tokens_norm.W, E)
+        D = E // heads
+        esz = 1
+        self.emit("ysod_mha_core", qkv.ptr(), qkv.slice(E, 2 * E).ptr(), qkv.slice(2 * E, 3 * E).ptr(), self.code, batch, L, heads, D,
+                  3 * E, 3 * E, 3 * E, L * 3 * E * esz, L * 3 * E * esz, L * 3 * E * esz, 1.0 / math.sqrt(D), ao.ptr(), E, L * E)
+        return self.linear(ao, sd[f"{P}.out_proj.weight"], sd[f"{P}.out_proj.bias"], res=res)
+
+    def swin(self, x, P, p, out):
+        """blocks_transformer.py:133-171."""
+        sd = self.m.sd
+        Cc, ws = x.C, p["window_size"]
+        dww = sd[f"{P}.dw.weight"].float()
+        y = self.new(x.N, x.H, x.W, Cc)
+        self.conv(x, dww, torch.zeros(Cc), 3, 1, Cc, "none", y)
+        wh, ww = min(ws, x.H), min(ws, x.W)
+        if x.H <= ws and x.W <= ws:
+            nWh = nWw = 1
+        else:
+            nWh, nWw = -(-x.H // wh), -(-x.W // ww)
+        T = x.N * nWh * nWw * wh * ww
+        A = f"{P}.window_attn"
+        raw, nrm = self.new(1, 1, T, Cc), self.new(1, 1, T, Cc)
+        g1, b1 = self.dev_t(sd[f"{A}.norm1.weight"]), self.dev_t(sd[f"{A}.norm1.bias"])
+        self.emit("ysod_window_partition_ln", y.ptr(), self.code, x.N, x.H, x.W, Cc, y.cs, wh, ww, nWh, nWw, _lib.ptr(g1), _lib.ptr(b1),
+                  LN_EPS, raw.ptr(), nrm.ptr(), Cc)
+        w2 = self.mha(nrm, f"{A}.attn", p["num_heads"], x.N * nWh * nWw, wh * ww, res=raw)
+        n2 = self.new(1, 1, T, Cc)
+        g2, b2 = self.dev_t(sd[f"{A}.norm2.weight"]), self.dev_t(sd[f"{A}.norm2.bias"])
+        self.emit("ysod_layernorm", w2.ptr(), self.code, T, Cc, w2.cs, _lib.ptr(g2), _lib.ptr(b2), LN_EPS, n2.ptr(), n2.cs)
+        h = self.linear(n2, sd[f"{A}.mlp.0.weight"], sd[f"{A}.mlp.0.bias"], act="gelu")
+        w3 = self.linear(h, sd[f"{A}.mlp.2.weight"], sd[f"{A}.mlp.2.bias"], res=w2)
+        r = self.new(x.N, x.H, x.W, Cc)
+        self.emit("ysod_window_reverse", w3.ptr(), self.code, w3.cs, x.N, x.H, x.W, Cc, wh, ww, nWh, nWw, r.ptr(), r.cs)
+        # pw 1x1 (no bias) -> BN -> SiLU -> + identity
+        pw = sd[f"{P}.pw.weight"].float()
+        g, b = sd[f"{P}.bn.weight"].float(), sd[f"{P}.bn.bias"].float()
+        s = g / torch.sqrt(sd[f"{P}.bn.running_var"].float() + BN_EPS)
+        self.conv(r, pw * s.view(-1, 1, 1, 1), b - sd[f"{P}.bn.running_mean"].float() * s, 1, 1, 1, "silu", out, res=x)
+
+    def a2attn(self, x, P, p, out):
+        """a2_attn.py:35-69."""
+        sd = self.m.sd
+        Cc, na = x.C, p["num_areas"]
+        xp = self.conv_bn(x, f"{P}.proj")
+        pooled = self.new(x.N, na, x.W, Cc)
+        self.emit("ysod_adaptive_pool_rows", xp.ptr(), self.code, x.N, x.H, x.W, Cc, xp.cs, na, pooled.ptr(), pooled.cs)
+        T = x.N * na * x.W
+        seq = View(pooled.buf, pooled.off, 1, 1, T, Cc, Cc)
+        sn = self.new(1, 1, T, Cc)
+        g, b = self.dev_t(sd[f"{P}.layer_norm.weight"]), self.dev_t(sd[f"{P}.layer_norm.bias"])
+        self.emit("ysod_layernorm", seq.ptr(), self.code, T, Cc, Cc, _lib.ptr(g), _lib.ptr(b), LN_EPS, sn.ptr(), Cc)
+        ao = self.mha(sn, f"{P}.attention", p["num_heads"], x.N, na * x.W)
+        up = self.new(x.N, x.H, x.W, Cc)
+        self.emit("ysod_bilinear_rows", ao.ptr(), self.code, x.N, na, x.W, Cc, ao.cs, x.H, up.ptr(), up.cs)
+        self.conv_bn(up, f"{P}.out_proj", out=out, res=x)
+
+    def ablock(self, x, P, heads, area, out):
+        """block.py:1367-1416 ABlock with AAttn (:1298-1365, manual-softmax semantics)."""
+        Cc = x.C
+        A = f"{P}.attn"
+        qk = self.conv_bn(x, f"{A}.qk", act=False)
+        v = self.conv_bn(x, f"{A}.v", act=False)
+        L = x.H * x.W
+        if area > 1:
+            assert L % area == 0, "AAttn: H*W must be divisible by area"
+            L //= area
+        batch = x.N * max(area, 1)
+        D = Cc // heads
+        ao = self.new(x.N, x.H, x.W, Cc)
+        self.emit("ysod_mha_core", qk.ptr(), qk.slice(Cc, 2 * Cc).ptr(), v.ptr(), self.code, batch, L, heads, D, 2 * Cc, 2 * Cc, Cc,
+                  L * 2 * Cc, L * 2 * Cc, L * Cc, D ** -0.5, ao.ptr(), Cc, L * Cc)
+        s = self.conv_bn(v, f"{A}.pe", 5, 1, Cc, act=False, res=ao, pad=2)     # pe(v) + attention output
+        x1 = self.conv_bn(s, f"{A}.proj", act=False, res=x)                    # x + proj(...)
+        h = self.conv_bn(x1, f"{P}.mlp.0")
+        self.conv_bn(h, f"{P}.mlp.1", act=False, out=out, res=x1)
+
+    def a2c2f(self, x, P, p, c2, out):
+        """block.py:1418-1472."""
+        if p["a2"] and p["residual"]:
+            raise NotImplementedError("A2C2f residual/gamma variant (l/x scales) is outside the supported configs")
+        n = p["n"]
+        c_ = int(c2 * p["e"])
+        cat = self.new(x.N, x.H, x.W, (1 + n) * c_)
+        self.conv_bn(x, f"{P}.cv1", out=cat.slice(0, c_))
+        for j in range(n):
+            src, dst = cat.slice(j * c_, (j + 1) * c_), cat.slice((j + 1) * c_, (j + 2) * c_)
+            if p["a2"]:
+                mid = self.new(x.N, x.H, x.W, c_)
+                self.ablock(src, f"{P}.m.{j}.0", c_ // 32, p["area"], mid)
+                self.ablock(mid, f"{P}.m.{j}.1", c_ // 32, p["area"], dst)
+            else:
+                self.c3k(src, f"{P}.m.{j}", 2, p["shortcut"], p["g"], dst)
+        self.conv_bn(cat, f"{P}.cv2", out=out)
+
+    def sppf(self, x, P, p, out):
+        c_ = x.C // 2
+        cat = self.new(x.N, x.H, x.W, 4 * c_)
+        self.conv_bn(x, f"{P}.cv1", out=cat.slice(0, c_))
+        self.emit("ysod_sppf_pool", cat.ptr(), self.code, x.N, x.H, x.W, c_, cat.cs, p["k"], cat.slice(c_, 2 * c_).ptr(),
+                  cat.slice(2 * c_, 3 * c_).ptr(), cat.slice(3 * c_, 4 * c_).ptr(), cat.cs)
+        self.conv_bn(cat, f"{P}.cv2", out=out)
+
+    def _splits(self, N, HW):
+        return max(1, min(HW // 64 if HW >= 64 else 1, -(-296 // N)))
+
+    def se(self, x, P, out):
+        sd = self.m.sd
+        Cc, HW = x.C, x.H * x.W
+        hid = sd[f"{P}.fc1.weight"].shape[0]
+        S = self._splits(x.N, HW)
+        psum, gate = self.f32(x.N, S, Cc), self.f32(x.N, Cc)
+        w1, b1 = self.dev_t(sd[f"{P}.fc1.weight"].reshape(hid, Cc)), self.dev_t(sd[f"{P}.fc1.bias"])
+        w2, b2 = self.dev_t(sd[f"{P}.fc2.weight"].reshape(Cc, hid)), self.dev_t(sd[f"{P}.fc2.bias"])
+        self.emit("ysod_gap_partial", x.ptr(), self.code, x.N, HW, Cc, x.cs, S, _lib.ptr(psum), None)
+        self.emit("ysod_se_gate", _lib.ptr(psum), x.N, S, HW, Cc, _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), hid, _lib.ptr(gate))
+        self.emit("ysod_scale_channels", x.ptr(), self.code, x.N, HW, Cc, x.cs, _lib.ptr(gate), out.ptr(), out.cs)
+
+    def cbam(self, x, P, out):
+        sd = self.m.sd
+        Cc, HW = x.C, x.H * x.W
+        hid = sd[f"{P}.channel_attention.fc.0.weight"].shape[0]
+        S = self._splits(x.N, HW)
+        psum, pmax, gate = self.f32(x.N, S, Cc), self.f32(x.N, S, Cc), self.f32(x.N, Cc)
+        stats = self.f32(x.N, HW, 2)
+        w1 = self.dev_t(sd[f"{P}.channel_attention.fc.0.weight"].reshape(hid, Cc))
+        w2 = self.dev_t(sd[f"{P}.channel_attention.fc.2.weight"].reshape(Cc, hid))
+        wsp = self.dev_t(sd[f"{P}.spatial_attention.conv1.weight"].reshape(2, 7, 7))
+        self.emit("ysod_gap_partial", x.ptr(), self.code, x.N, HW, Cc, x.cs, S, _lib.ptr(psum), _lib.ptr(pmax))
+        self.emit("ysod_cbam_gate", _lib.ptr(psum), _lib.ptr(pmax), x.N, S, HW, Cc, _lib.ptr(w1), _lib.ptr(w2), hid, _lib.ptr(gate))
+        self.emit("ysod_cbam_stats", x.ptr(), self.code, x.N, HW, Cc, x.cs, _lib.ptr(gate), _lib.ptr(stats))
+        self.emit("ysod_cbam_apply", x.ptr(), self.code, x.N, x.H, x.W, Cc, x.cs, _lib.ptr(gate), _lib.ptr(stats), _lib.ptr(wsp), 7,
+                  out.ptr(), out.cs)
+
+    def ca(self, x, P, out):
+        sd = self.m.sd
+        Cc = x.C
+        mip = sd[f"{P}.conv1.weight"].shape[0]
+        s = sd[f"{P}.bn1.weight"].float() / torch.sqrt(sd[f"{P}.bn1.running_var"].float() + BN_EPS)
+        w1 = self.dev_t(sd[f"{P}.conv1.weight"].float().reshape(mip, Cc) * s.view(-1, 1))
+        b1 = self.dev_t((sd[f"{P}.conv1.bias"].float() - sd[f"{P}.bn1.running_mean"].float()) * s + sd[f"{P}.bn1.bias"].float())
+        wh, bh = self.dev_t(sd[f"{P}.conv_h.weight"].reshape(Cc, mip)), self.dev_t(sd[f"{P}.conv_h.bias"])
+        ww, bw = self.dev_t(sd[f"{P}.conv_w.weight"].reshape(Cc, mip)), self.dev_t(sd[f"{P}.conv_w.bias"])
+        pooled, att = self.f32(x.N, x.H + x.W, Cc), self.f32(x.N, x.H + x.W, Cc)
+        self.emit("ysod_ca_pool", x.ptr(), self.code, x.N, x.H, x.W, Cc, x.cs, _lib.ptr(pooled))
+        self.emit("ysod_ca_gate", _lib.ptr(pooled), x.N, x.H, x.W, Cc, mip, _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(wh), _lib.ptr(bh),
+                  _lib.ptr(ww), _lib.ptr(bw), _lib.ptr(att))
+        self.emit("ysod_ca_apply", x.ptr(), self.code, x.N, x.H, x.W, Cc, x.cs, _lib.ptr(att), out.ptr(), out.cs)
+
+    def detect(self, xs, P, p):
+        """head.py:64-131: per-level cv2/cv3 stacks -> raw maps (fp32 NHWC, stride RAW_CS) -> fused decode."""
+        sd = self.m.sd
+        nc = p["nc"]
+        no = 64 + nc
+        raw_cs = max(RAW_CS, (no + 7) // 8 * 8)
+        A = sum(v.H * v.W for v in xs)
+        y = torch.empty((self.B, 4 + nc, A), device=self.dev, dtype=torch.float32)
+        self.keep.append(y)
+        raws = []
+        a_off = 0
+        for i, x in enumerate(xs):
+            raw = self.new(x.N, x.H, x.W, raw_cs, dtype=torch.float32, zero=True)
+            a = self.conv_bn(x, f"{P}.cv2.{i}.0", 3)
+            a = self.conv_bn(a, f"{P}.cv2.{i}.1", 3)
+            self.conv(a, sd[f"{P}.cv2.{i}.2.weight"].float(), sd[f"{P}.cv2.{i}.2.bias"].float(), 1, 1, 1, "none", raw.slice(0, 64),
+                      out_f32=True)
+            if p["legacy"]:
+                c = self.conv_bn(x, f"{P}.cv3.{i}.0", 3)
+                c = self.conv_bn(c, f"{P}.cv3.{i}.1", 3)
+            else:
+                c = self.conv_bn(x, f"{P}.cv3.{i}.0.0", 3, 1, x.C)
+                c = self.conv_bn(c, f"{P}.cv3.{i}.0.1", 1)
+                c = self.conv_bn(c, f"{P}.cv3.{i}.1.0", 3, 1, c.C)
+                c = self.conv_bn(c, f"{P}.cv3.{i}.1.1", 1)
+            self.conv(c, sd[f"{P}.cv3.{i}.2.weight"].float(), sd[f"{P}.cv3.{i}.2.bias"].float(), 1, 1, 1, "none", raw.slice(64, 64 + nc),
+                      out_f32=True)
+            self.emit("ysod_dfl_decode", raw.ptr(), _lib.F32, x.N, x.H, x.W, raw.cs, nc, 16, float(self.m.stride_list[i]), _lib.ptr(y), A,
+                      a_off)
+            a_off += x.H * x.W
+            raws.append(raw.slice(0, no))
+        self.y = y
+        self.raws = raws
+
+    # ---- graph walk --------------------------------------------------------------------------------------
+    def _build(self):
+        spec = self.m.spec
+        layers = spec.layers
+        # shapes of every layer output
+        shp = {}
+        for L in layers:
+            if L.i == 0:
+                cin_hw = (self.H, self.W)
+            src = L.f if isinstance(L.f, int) else L.f[0]
+            src = L.i - 1 if src == -1 else src
+            h, w = (self.H, self.W) if L.i == 0 else shp[src][:2]
+            if L.type == "Conv":
+                k, s = L.p["k"], L.p["s"]
+                pd = k // 2 if L.p["p"] is None else L.p["p"]
+                h, w = (h + 2 * pd - k) // s + 1, (w + 2 * pd - k) // s + 1
+            elif L.type == "nn.Upsample":
+                h, w = h * L.p["scale"], w * L.p["scale"]
+            shp[L.i] = (h, w, L.c2)
+        # homes: outputs that are produced directly inside a Concat buffer
+        home: Dict[int, View] = {}
+        cat_buf: Dict[int, View] = {}
+        for L in layers:
+            if L.type == "Concat":
+                h, w, c = shp[L.i]
+                cb = self.new(self.B, h, w, c)
+                cat_buf[L.i] = cb
+                c0 = 0
+                for j, src in enumerate(L.f):
+                    src = L.i - 1 if src == -1 else src
+                    cj = L.c1[j]
+                    if src not in home and layers[src].type not in ("Concat", "Detect"):
+                        home[src] = cb.slice(c0, c0 + cj)
+                    c0 += cj
+        out = self.layer_out
+        for L in layers:
+            P, p, t = f"model.{L.i}", L.p, L.type
+            if t == "Detect":
+                self.detect([out[j] for j in L.f], P, p)
+                continue
+            if t == "Concat":
+                cb = cat_buf[L.i]
+                c0 = 0
+                for j, src in enumerate(L.f):
+                    src = L.i - 1 if src == -1 else src
+                    cj = L.c1[j]
+                    sv, dv = out[src], cb.slice(c0, c0 + cj)
+                    if not (sv.buf is dv.buf and sv.off == dv.off):
+                        self.emit("ysod_upsample_copy", sv.ptr(), self.code, sv.N, sv.H, sv.W, sv.C, sv.cs, 1, dv.ptr(), dv.cs)
+                    c0 += cj
+                out[L.i] = cb
+                continue
+            h, w, c = shp[L.i]
+            o = home[L.i] if L.i in home else self.new(self.B, h, w, c)
+            src = L.i - 1 if L.f == -1 else L.f
+            x = None if L.i == 0 else out[src]
+            if t == "Conv":
+                if L.i == 0:
+                    wf, bf = self.folded(P)
+                    k, s = p["k"], p["s"]
+                    assert p["g"] == 1 and wf.shape[1] == 3, "stem must be a dense conv on a 3-channel image"
+                    wd, bd = self.dev_t(wf.permute(0, 2, 3, 1)), self.dev_t(bf)
+                    self.emit("ysod_stem_conv", _lib.ptr(self.img), self.B, self.H, self.W, _lib.ptr(wd), _lib.ptr(bd), wf.shape[0], k, s,
+                              k // 2 if p["p"] is None else p["p"], o.ptr(), self.code, o.cs, _lib.ACT["silu" if p["act"] else "none"])
+                else:
+                    self.conv_bn(x, P, p["k"], p["s"], p["g"], p["act"], out=o, pad=p["p"])
+            elif t == "C2f":
+                self.c2f(x, P, p, L.c2, o)
+            elif t == "C3k2":
+                self.c2f(x, P, p, L.c2, o, c3k2=True)
+            elif t == "A2C2f":
+                self.a2c2f(x, P, p, L.c2, o)
+            elif t == "SPPF":
+                self.sppf(x, P, p, o)
+            elif t in ("SE_Block", "SE"):
+                self.se(x, P, o)
+            elif t == "CBAM_Block":
+                self.cbam(x, P, o)
+            elif t == "CA_Block":
+                self.ca(x, P, o)
+            elif t == "SwinBlock":
+                self.swin(x, P, p, o)
+            elif t == "A2_Attn":
+                self.a2attn(x, P, p, o)
+            elif t == "nn.Upsample":
+                self.emit("ysod_upsample_copy", x.ptr(), self.code, x.N, x.H, x.W, x.C, x.cs, p["scale"], o.ptr(), o.cs)
+            else:
+                raise NotImplementedError(t)
+            out[L.i] = o
+
+    # ---- execution ---------------------------------------------------------------------------------------
+    def launch_all(self):
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for fn, args, name in self.ops:
+            rc = fn(*args, st)
+            if rc:
+                _lib.check(rc, name)
+
+    def capture(self):
+        """Capture the launch list into a CUDA graph (batch-1 latency is launch-bound otherwise)."""
+        torch.cuda.synchronize()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self.launch_all()  # warm-up outside capture
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.launch_all()
+        self.graph = g
+
+    def run(self, x: torch.Tensor):
+        self.img.copy_(x, non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.launch_all()
+        raw = [r.torch_nchw() for r in self.raws]
+        if self.m.static_outputs:
+            return self.y, raw      # views of the program's own buffers: overwritten by the next forward of this shape
+        return self.y.clone(), [r.clone() for r in raw]
+
+    def __del__(self):
+        try:
+            lib = _lib.load()
+            for h in self.tc_handles:
+                lib.ysod_conv_tc_destroy(h)
+        except Exception:
+            pass
+
+
+class B200DetectionModel:
+    """Drop-in for the reference's `DetectionModel` forward seam (tasks.py:129-163): `model(x) -> (y, [raw...])`.
+
+    cfg        : config name / YAML path / dict (see cfg.py)
+    state_dict : reference-named weights (e.g. `ref_model.state_dict()`); fp32 CPU or CUDA tensors
+    dtype      : torch.bfloat16 (tensor-core path) or torch.float32 (CUDA-core parity mode, rtol 1e-4)
+    """
+
+    def __init__(self, cfg, state_dict, dtype=torch.bfloat16, device="cuda:0", use_tc=True, use_graph=True, nc=None,
+                 static_outputs=True):
+        _lib.require_cuda()
+        _lib.load()
+        self.spec = cfg if isinstance(cfg, _cfg.ModelSpec) else _cfg.get_spec(cfg, nc=nc)
+        self.sd = {k: v.detach().cpu() for k, v in state_dict.items()}
+        missing = [k for k in _cfg.param_shapes(self.spec) if k not in self.sd]
+        if missing:
+            raise KeyError(f"state_dict is missing {len(missing)} tensors, e.g. {missing[:3]}")
+        assert dtype in (torch.bfloat16, torch.float32)
+        self.dtype = dtype
+        self.device = torch.device(device)
+        self.use_tc = use_tc
+        self.use_graph = use_graph
+        self.static_outputs = static_outputs
+        self.stride_list = _cfg.strides_of(self.spec)
+        self.stride = torch.tensor([float(s) for s in self.stride_list])
+        self.nc = self.spec.nc
+        self.names = {i: f"{i}" for i in range(self.nc)}  # tasks.py:351 default names
+        self.yaml = self.spec.yaml
+        self.reg_max = 16
+        self.no = self.nc + 64
+        self.nl = len(self.stride_list)
+        self.programs: Dict[tuple, Program] = {}
+
+    def program(self, B, H, W) -> Program:
+        key = (B, H, W)
+        if key not in self.programs:
+            s = max(self.stride_list)
+            if H % s or W % s:
+                raise ValueError(f"input {H}x{W} must be a multiple of the max stride {s}")
+            with torch.cuda.device(self.device):
+                prog = Program(self, B, H, W)
+                if self.use_graph:
+                    prog.capture()
+            self.programs[key] = prog
+        return self.programs[key]
+
+    @torch.no_grad()
+    def forward(self, x, *args, **kwargs):
+        """x: (B,3,H,W) float tensor in [0,1] (NCHW, as the reference takes it). Returns (y, [raw maps])."""
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError(f"expected (B,3,H,W), got {tuple(x.shape)}")
+        if not x.is_cuda:
+            x = x.to(self.device, non_blocking=True)
+        prog = self.program(int(x.shape[0]), int(x.shape[2]), int(x.shape[3]))
+        with torch.cuda.device(self.device):
+            return prog.run(x)
+
+    __call__ = forward
+    predict = forward
+
+    def eval(self):
+        return self
+
+    def fuse(self, verbose=False):
+        return self  # BN is always folded at compile time
+
+    def layer_output(self, x, idx):
+        """Debug/test helper: NCHW fp32 copy of layer `idx`'s output for the last forward with this shape."""
+        prog = self.program(int(x.shape[0]), int(x.shape[2]), int(x.shape[3]))
+        return prog.layer_out[idx].torch_nchw().float()

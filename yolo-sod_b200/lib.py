@@ -1,0 +1,96 @@
+"""ctypes binding of the C-ABI shared library (include/ysod.h). The library is the product: if it is missing, or
+there is no CUDA device, every entry point raises -- there is no CPU or PyTorch fallback."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libysod.so")
+
+F32, BF16 = 0, 1
+ACT = {"none": 0, "silu": 1, "gelu": 2, "relu": 3, "sigmoid": 4, "hsigmoid": 5}
+
+vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+
+# name -> (restype, argtypes); mirrors include/ysod.h one to one
+PROTOTYPES = {
+    "ysod_version": (i32, []),
+    "ysod_last_error": (C.c_char_p, []),
+    "ysod_compiled_arch": (i32, []),
+    "ysod_nms_workspace_bytes": (i64, [i32, i32, i32, i32, i32]),
+    "ysod_nms_batched": (i32, [vp, i32, i32, i32, f32, f32, vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp, i64, vp]),
+    "ysod_nms_boxes_workspace_bytes": (i64, [i32]),
+    "ysod_nms_boxes": (i32, [vp, vp, i32, f32, i32, vp, vp, vp, i64, vp]),
+    "ysod_dfl_decode": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, f32, vp, i32, i32, vp]),
+    "ysod_conv_tc_create": (i32, [C.POINTER(vp), vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, i32, vp, i32, i32, vp, i32, i32]),
+    "ysod_conv_tc_run": (i32, [vp, vp]),
+    "ysod_conv_tc_info": (i32, [vp, C.POINTER(i32)]),
+    "ysod_conv_tc_destroy": (None, [vp]),
+    "ysod_conv_direct": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, vp, i32, i32, vp]),
+    "ysod_dwconv": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, vp, i32, vp, i32, i32, vp]),
+    "ysod_stem_conv": (i32, [vp, i32, i32, i32, vp, vp, i32, i32, i32, i32, vp, i32, i32, i32, vp]),
+    "ysod_gap_partial": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "ysod_se_gate": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp]),
+    "ysod_cbam_gate": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, i32, vp, vp]),
+    "ysod_scale_channels": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, i32, vp]),
+    "ysod_cbam_stats": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "ysod_cbam_apply": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, i32, vp]),
+    "ysod_ca_pool": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "ysod_ca_gate": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "ysod_ca_apply": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp]),
+    "ysod_sppf_pool": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp]),
+    "ysod_upsample_copy": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
+    "ysod_layernorm": (i32, [vp, i32, i64, i32, i32, vp, vp, f32, vp, i32, vp]),
+    "ysod_window_partition_ln": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, f32, vp, vp, i32, vp]),
+    "ysod_window_reverse": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
+    "ysod_adaptive_pool_rows": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
+    "ysod_bilinear_rows": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
+    "ysod_mha_core": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i64, i64, i64, f32, vp, i32, i64, vp]),
+}
+
+_lib = None
+
+
+class YsodError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen libysod.so and attach prototypes. Raises if the library has not been built (`__graft_entry__.build()`)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise YsodError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                            "There is no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(lib, name)  # AttributeError here == header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().ysod_last_error().decode("utf-8", "replace")
+        raise YsodError(f"{what} failed (code {rc}): {msg}")
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise YsodError("no CUDA device: yolo-sod_b200 runs on sm_100a GPUs only (no CPU fallback)")
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t, offset_elems=0):
+    """device pointer of a torch tensor (+ element offset)."""
+    return C.c_void_p(t.data_ptr() + offset_elems * t.element_size())
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args), name)

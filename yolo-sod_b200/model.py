@@ -1,0 +1,147 @@
+"""The reference's Python surface for the inference hot path, backed by the B200 engine.
+
+    YOLO(cfg).predict(tensor, conf=, iou=, ...)        engine/model.py:501-560  -> list of Results-like objects
+    DetectionModel(cfg)(x) -> (y, [raw maps])          nn/tasks.py:129-163 / head.py:73-74
+    AutoBackend(model)(im), .warmup(), .stride, ...    nn/autobackend.py:54,503-524,718-731 (the predictor's model seam)
+
+Only what the predictor reads is mirrored; sources other than image tensors (files, streams, PIL, numpy
+letterboxing) belong to the reference's `ultralytics.data` package and are out of scope.
+"""
+from types import SimpleNamespace
+from typing import List, Optional
+
+import torch
+
+from . import cfg as _cfg
+from . import ops as _ops
+from . import synth as _synth
+from .engine import B200DetectionModel
+
+
+class DetectionModel(B200DetectionModel):
+    """`DetectionModel(cfg='yolov12n.yaml', ch=3, nc=None)` as in nn/tasks.py:336-379. With no `weights`, deterministic
+    synthetic weights are generated (there are no checkpoints / no network); pass `weights=ref_model.state_dict()` to run a
+    trained reference model."""
+
+    def __init__(self, cfg="yolov12-sod-fusion-v5-simple", ch=3, nc=None, verbose=False, weights=None, dtype=torch.bfloat16,
+                 device="cuda:0", seed=0, **kw):
+        if ch != 3:
+            raise NotImplementedError("only 3-channel image input is on the hot path")
+        spec = _cfg.get_spec(cfg, ch=ch, nc=nc)
+        name = cfg if isinstance(cfg, str) else "custom"
+        name = name.rsplit("/", 1)[-1]
+        name = name[:-5] if name.endswith(".yaml") else name
+        name = _cfg.ALIASES.get(name, name)
+        if weights is None:
+            weights = _synth.synth_state_dict(spec, name, seed)
+        super().__init__(spec, weights, dtype=dtype, device=device, **kw)
+        self.cfg_name = name
+        det = spec.layers[-1]
+        # what callers read off `model.model[-1]`
+        head = SimpleNamespace(nc=self.nc, nl=self.nl, reg_max=16, no=self.no, stride=self.stride, legacy=det.p["legacy"],
+                               f=det.f, i=det.i, type="ultralytics.nn.modules.head.Detect")
+        self.model = [SimpleNamespace(i=L.i, f=L.f, type=L.type) for L in spec.layers[:-1]] + [head]
+        self.save = spec.save
+        self.task = "detect"
+
+
+class AutoBackend:
+    """The attribute set and call signature `BasePredictor` expects from `AutoBackend` (engine/predictor.py:131,143,158-159,
+    193,239,306-321). Single backend: the sm_100a library. `fp16=True` is rejected: the reference's half mode is IEEE fp16,
+    which this build does not provide; the low-precision mode here is bf16 (selected by the model's dtype)."""
+
+    def __init__(self, weights: DetectionModel, device=None, dnn=False, data=None, fp16=False, batch=1, fuse=True, verbose=False):
+        if not isinstance(weights, B200DetectionModel):
+            raise TypeError("AutoBackend(weights=...) must be a yolo_sod_b200 DetectionModel (in-memory module path, "
+                            "autobackend.py:145-155); exported-format backends are out of scope")
+        if fp16:
+            raise NotImplementedError("half=True (fp16) is not provided; build the model with dtype=torch.bfloat16")
+        self.model = weights
+        self.device = weights.device
+        self.fp16 = False
+        self.stride = int(max(weights.stride_list))
+        self.names = weights.names
+        self.pt = True
+        self.jit = self.onnx = self.engine = self.triton = self.imx = self.dynamic = self.nhwc = False
+        self.task = "detect"
+
+    def forward(self, im, augment=False, visualize=False, embed=None):
+        if augment or visualize or embed is not None:
+            raise NotImplementedError("augment / visualize / embed are outside the inference hot path")
+        return self.model(im)
+
+    __call__ = forward
+
+    def eval(self):
+        return self
+
+    def warmup(self, imgsz=(1, 3, 640, 640)):
+        """autobackend.py:718-731: compile + capture the program for this shape and run it once."""
+        im = torch.zeros(*imgsz, dtype=torch.float32, device=self.device)
+        self.forward(im)
+        torch.cuda.synchronize(self.device)
+
+
+class Boxes:
+    """Minimal stand-in for engine/results.py `Boxes` (asserts last dim in {6,7} there, :1005): xyxy, conf, cls views."""
+
+    def __init__(self, data: torch.Tensor, orig_shape):
+        assert data.shape[-1] == 6
+        self.data = data
+        self.orig_shape = orig_shape
+
+    xyxy = property(lambda s: s.data[:, :4])
+    conf = property(lambda s: s.data[:, 4])
+    cls = property(lambda s: s.data[:, 5])
+
+    def __len__(self):
+        return self.data.shape[0]
+
+
+class Results:
+    def __init__(self, boxes: torch.Tensor, orig_shape, names, speed=None):
+        self.boxes = Boxes(boxes, orig_shape)
+        self.orig_shape = orig_shape
+        self.names = names
+        self.speed = speed or {}
+
+    def __len__(self):
+        return len(self.boxes)
+
+
+class YOLO:
+    """`YOLO(cfg_yaml)` facade (models/yolo/model.py:14-23, engine/model.py:84-151,501-560) for tensor sources."""
+
+    def __init__(self, model="yolov12-sod-fusion-v5-simple", task="detect", verbose=False, weights=None, dtype=torch.bfloat16,
+                 device="cuda:0", seed=0):
+        if task not in (None, "detect"):
+            raise NotImplementedError("only task='detect' is on the hot path")
+        self.model = model if isinstance(model, B200DetectionModel) else DetectionModel(model, weights=weights, dtype=dtype,
+                                                                                        device=device, seed=seed)
+        self.backend = AutoBackend(self.model)
+        self.task = "detect"
+        self.names = self.model.names
+
+    @torch.no_grad()
+    def predict(self, source, stream=False, conf=0.25, iou=0.7, max_det=300, classes=None, agnostic_nms=False, imgsz=None,
+                half=False, **kwargs) -> List[Results]:
+        """Defaults follow cfg/default.yaml:51-54 and engine/model.py:547 (conf 0.25, iou 0.7, max_det 300)."""
+        if not torch.is_tensor(source):
+            raise NotImplementedError("only (B,3,H,W) float tensors in [0,1] are accepted (predictor.py:116-134 tensor branch); "
+                                      "file/stream sources need the reference's ultralytics.data, which is out of scope")
+        if half:
+            raise NotImplementedError("half=True (fp16) is not provided")
+        im = source if source.dim() == 4 else source[None]
+        preds = self.backend(im.float())
+        dets = _ops.non_max_suppression(preds, conf, iou, classes=classes, agnostic=agnostic_nms, max_det=max_det)
+        h, w = int(im.shape[2]), int(im.shape[3])
+        out = []
+        for d in dets:
+            d = d.clone()
+            # scale_boxes(img.shape[2:], boxes, orig_shape) with identical shapes == clip_boxes (ops.py:92-127,319-338)
+            d[:, [0, 2]] = d[:, [0, 2]].clamp(0, w)
+            d[:, [1, 3]] = d[:, [1, 3]].clamp(0, h)
+            out.append(Results(d, (h, w), self.names))
+        return out
+
+    __call__ = predict
