@@ -15,7 +15,7 @@ def _act(y, act):
     return {"none": lambda t: t, "silu": F.silu, "gelu": F.gelu, "relu": F.relu}[act](y)
 
 
-def _run_tc(N, H, W, Cin, Cout, k, s, act="silu", res=False, out_f32=False, xcs_extra=0, ocs_extra=0, seed=0):
+def _run_tc(N, H, W, Cin, Cout, k, s, act="silu", res=False, out_f32=False, xcs_extra=0, ocs_extra=0, seed=0, out_first=False):
     from yolo_sod_b200 import lib
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(N, H, W, Cin, generator=g).bfloat16()
@@ -42,16 +42,18 @@ def _run_tc(N, H, W, Cin, Cout, k, s, act="silu", res=False, out_f32=False, xcs_
     rd = r.cuda().contiguous() if res else None
     h = C.c_void_p()
     lib.call("ysod_conv_tc_create", C.byref(h), lib.ptr(xb, xcs_extra), N, H, W, Cin, xcs, lib.ptr(wd), lib.ptr(bd), Cout, cpad, k, s,
-             lib.ptr(ob, ocs_extra), lib.F32 if out_f32 else lib.BF16, ocs, lib.ptr(rd) if res else None, Cout if res else 0,
+             lib.ptr(ob, 0 if out_first else ocs_extra), lib.F32 if out_f32 else lib.BF16, ocs, lib.ptr(rd) if res else None, Cout if res else 0,
              lib.ACT[act])
     info = (C.c_int * 8)()
     lib.call("ysod_conv_tc_info", h, info)
     lib.call("ysod_conv_tc_run", h, lib.stream_ptr())
     torch.cuda.synchronize()
     lib.load().ysod_conv_tc_destroy(h)
-    got = ob[..., ocs_extra:].float().cpu().permute(0, 3, 1, 2)
+    oslice = slice(0, Cout) if out_first else slice(ocs_extra, None)
+    untouched = slice(Cout, None) if out_first else slice(0, ocs_extra)
+    got = ob[..., oslice].float().cpu().permute(0, 3, 1, 2)
     if ocs_extra:
-        assert bool((ob[..., :ocs_extra] == 7.0).all()), "kernel wrote outside its channel slice"
+        assert bool((ob[..., untouched] == 7.0).all()), "kernel wrote outside its channel slice"
     tol = 1e-4 if out_f32 else 1.0 / 128
     err = (got - ref).abs()
     bound = tol * ref.abs() + tol * ref.abs().max() + 1e-5
@@ -69,7 +71,7 @@ CASES = [
     (1, 16, 16, 96, 64, 1, 1, {}),                                  # Cin=96 -> BK=32 / 64B swizzle
     (1, 16, 16, 32, 32, 3, 1, {}),                                  # Cin=32 3x3 (32->32 @160 in the model)
     (1, 8, 8, 256, 512, 1, 1, {}),                                  # two N tiles of 256
-    (1, 16, 16, 64, 10, 1, 1, dict(act="none", out_f32=True)),      # cls head: Cout 10 padded to 16, fp32 out
+    (1, 16, 16, 64, 10, 1, 1, dict(act="none", out_f32=True, ocs_extra=6, out_first=True)),  # cls head: Cout 10 (pad 16), fp32, stride 16
     (1, 16, 16, 64, 64, 1, 1, dict(act="none", out_f32=True, ocs_extra=16)),  # box head into a slice of the raw map
     (1, 1, 300, 64, 192, 1, 1, dict(act="none")),                   # linear: tokens x qkv (N=192)
     (1, 1, 1000, 128, 64, 1, 1, dict(act="gelu", res=True)),        # linear + GELU + residual
@@ -137,7 +139,8 @@ def test_stem(out):
     ref = F.silu(F.conv2d(img, w, b, 2, 1))
     td = torch.float32 if out == "f32" else torch.bfloat16
     od = torch.empty(2, 16, 24, 32, dtype=td, device="cuda")
-    lib.call("ysod_stem_conv", lib.ptr(img.cuda()), 2, 32, 48, lib.ptr(w.permute(0, 2, 3, 1).contiguous().cuda()), lib.ptr(b.cuda()), 32, 3, 2,
+    imgd, wd, bd = img.cuda(), w.permute(0, 2, 3, 1).contiguous().cuda(), b.cuda()  # keep alive across the async launch
+    lib.call("ysod_stem_conv", lib.ptr(imgd), 2, 32, 48, lib.ptr(wd), lib.ptr(bd), 32, 3, 2,
              1, lib.ptr(od), lib.F32 if out == "f32" else lib.BF16, 32, lib.ACT["silu"], lib.stream_ptr())
     torch.cuda.synchronize()
     tol = 1e-5 if out == "f32" else 1.0 / 128

@@ -64,6 +64,10 @@ class Program:
         self.tc_handles: List[C.c_void_p] = []
         self.n_launches = 0
         self.n_tc = 0
+        self.tc_flops = 0        # algorithmic FLOPs (2*M*N*K, unpadded) of all tcgen05 conv launches of one forward
+        self.op_flops: List[float] = []   # per op, parallel to self.ops (0 for non-GEMM ops)
+        self.op_desc: List[str] = []      # per op, human-readable shape
+        self._ctx = ""
         self.layer_out: Dict[int, View] = {}
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.img = torch.zeros((B, 3, H, W), device=self.dev, dtype=torch.float32)
@@ -87,8 +91,10 @@ class Program:
         self.keep.append(t)
         return t
 
-    def emit(self, name, *args):
+    def emit(self, name, *args, flops=0.0, desc=""):
         self.ops.append((getattr(_lib.load(), name), args, name))
+        self.op_flops.append(float(flops))
+        self.op_desc.append(f"{self._ctx} {desc}".strip())
         self.n_launches += 1
 
     # ---- conv emission -----------------------------------------------------------------------------------
@@ -126,6 +132,13 @@ class Program:
                       k, s, out.ptr(), odt, out.cs, res.ptr() if res is not None else None, res.cs if res is not None else 0, actc)
             self.tc_handles.append(h)
             self.ops.append((_lib.load().ysod_conv_tc_run, (h,), "ysod_conv_tc_run"))
+            fl = 2.0 * x.N * Ho * Wo * Cout * k * k * Cin
+            self.op_flops.append(fl)
+            info = (C.c_int * 8)()
+            _lib.call("ysod_conv_tc_info", h, info)
+            self.op_desc.append(f"{self._ctx} tc {Cin}->{Cout} k{k}s{s} @{Ho}x{Wo} N{x.N} tile{info[0]}x{info[1]} BN{info[2]} BK{info[3]} "
+                                f"st{info[4]} grid{info[5]}x{info[6]} smem{info[7]}")
+            self.tc_flops += fl
             self.n_launches += 1
             self.n_tc += 1
             return
@@ -134,12 +147,14 @@ class Program:
             bd = self.dev_t(bias)
             assert not out_f32
             self.emit("ysod_dwconv", x.ptr(), self.code, x.N, x.H, x.W, Cin, x.cs, _lib.ptr(wd), _lib.ptr(bd), k, s, pad, out.ptr(),
-                      out.cs, res.ptr() if res is not None else None, res.cs if res is not None else 0, actc)
+                      out.cs, res.ptr() if res is not None else None, res.cs if res is not None else 0, actc,
+                      flops=2.0 * x.N * Ho * Wo * Cout * k * k, desc=f"dw {Cin} k{k} @{Ho}x{Wo}")
             return
         wd = self.dev_t(w.permute(0, 2, 3, 1), self.dt)  # [Cout][k][k][Cin/g]
         bd = self.dev_t(bias)
         self.emit("ysod_conv_direct", x.ptr(), self.code, x.N, x.H, x.W, Cin, x.cs, _lib.ptr(wd), _lib.ptr(bd), Cout, k, s, pad, g,
-                  out.ptr(), odt, out.cs, res.ptr() if res is not None else None, res.cs if res is not None else 0, actc)
+                  out.ptr(), odt, out.cs, res.ptr() if res is not None else None, res.cs if res is not None else 0, actc,
+                  flops=2.0 * x.N * Ho * Wo * Cout * k * k * Cin / g, desc=f"direct {Cin}->{Cout} k{k}s{s}g{g} @{Ho}x{Wo}")
 
     def conv_bn(self, x, pfx, k=1, s=1, g=1, act=True, out=None, res=None, pad=None):
         """Reference `Conv` wrapper (conv.py:37-55) with BN folded."""
@@ -418,6 +433,7 @@ class Program:
         out = self.layer_out
         for L in layers:
             P, p, t = f"model.{L.i}", L.p, L.type
+            self._ctx = f"L{L.i}:{t}"
             if t == "Detect":
                 self.detect([out[j] for j in L.f], P, p)
                 continue
@@ -478,6 +494,35 @@ class Program:
             rc = fn(*args, st)
             if rc:
                 _lib.check(rc, name)
+
+    def profile(self, iters=3):
+        """Eager replay with a CUDA event pair around every launch (on the launching stream). Returns
+        {kernel entry point: {"ms": mean ms per forward, "launches": n per forward, "flops": algorithmic flops per forward}}."""
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        acc: Dict[str, list] = {}
+        per_op = [0.0] * len(self.ops)
+        for it in range(iters + 1):
+            evs = []
+            for fn, args, name in self.ops:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                rc = fn(*args, st)
+                e1.record()
+                if rc:
+                    _lib.check(rc, name)
+                evs.append((e0, e1))
+            torch.cuda.synchronize()
+            if it == 0:
+                continue  # warm-up pass
+            for i, ((fn, args, name), (e0, e1), fl) in enumerate(zip(self.ops, evs, self.op_flops)):
+                a = acc.setdefault(name, [0.0, 0, 0.0])
+                per_op[i] += e0.elapsed_time(e1)
+                a[0] += e0.elapsed_time(e1)
+                a[1] += 1
+                a[2] += fl
+        self.last_per_op = [{"op": i, "kernel": self.ops[i][2], "desc": self.op_desc[i], "ms": per_op[i] / iters,
+                             "gflop": self.op_flops[i] / 1e9} for i in range(len(self.ops))]
+        return {k: {"ms": v[0] / iters, "launches": v[1] // iters, "flops": v[2] / iters} for k, v in acc.items()}
 
     def capture(self):
         """Capture the launch list into a CUDA graph (batch-1 latency is launch-bound otherwise)."""
@@ -564,8 +609,7 @@ class B200DetectionModel:
         """x: (B,3,H,W) float tensor in [0,1] (NCHW, as the reference takes it). Returns (y, [raw maps])."""
         if x.dim() != 4 or x.shape[1] != 3:
             raise ValueError(f"expected (B,3,H,W), got {tuple(x.shape)}")
-        if not x.is_cuda:
-            x = x.to(self.device, non_blocking=True)
+        # host tensors are copied straight into the program's input buffer (pinned memory makes this asynchronous)
         prog = self.program(int(x.shape[0]), int(x.shape[2]), int(x.shape[3]))
         with torch.cuda.device(self.device):
             return prog.run(x)
