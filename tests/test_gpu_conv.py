@@ -50,7 +50,9 @@ def _run_tc(N, H, W, Cin, Cout, k, s, act="silu", res=False, out_f32=False, xcs_
     torch.cuda.synchronize()
     lib.load().ysod_conv_tc_destroy(h)
     oslice = slice(0, Cout) if out_first else slice(ocs_extra, None)
-    untouched = slice(Cout, None) if out_first else slice(0, ocs_extra)
+    # TMA stores have 16-byte granularity along channels: up to 16 B past a ragged Cout are written (zeros); the caller owns them
+    gran = 4 if out_f32 else 8
+    untouched = slice((Cout + gran - 1) // gran * gran, None) if out_first else slice(0, ocs_extra)
     got = ob[..., oslice].float().cpu().permute(0, 3, 1, 2)
     if ocs_extra:
         assert bool((ob[..., untouched] == 7.0).all()), "kernel wrote outside its channel slice"

@@ -363,35 +363,40 @@ __global__ void upsample_copy_kernel(const T* __restrict__ x, int H, int W, int 
     }
 }
 
-// LayerNorm over the last dim, one warp per row (eps inside sqrt, biased variance, as torch.nn.LayerNorm)
+// LayerNorm over the last dim (eps inside sqrt, biased variance, as torch.nn.LayerNorm). A group of G lanes (power of two,
+// G = min(32, C/8 rounded up)) owns one row, so narrow rows (C = 64 -> 8 lanes) still fill the warp: 32/G rows per warp.
 template <typename T, bool GATHER>
 __global__ void layernorm_kernel(const T* __restrict__ x, long long rows, int C, int ldx, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, float eps, T* __restrict__ out, int ldo,
+                                 const float* __restrict__ beta, float eps, T* __restrict__ out, int ldo, int G,
                                  // window-partition gather (GATHER): x is NHWC, rows are window tokens
                                  int H, int W, int wh, int ww, int nWh, int nWw, T* __restrict__ raw_out) {
-    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (row >= rows) return;
+    const int gl = lane % G;
+    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long row = warp_id * (32 / G) + lane / G;
+    const bool valid = row < rows;
     const int c8n = C >> 3;
     const T* src = nullptr;
-    if (GATHER) {
-        const int tpw = wh * ww;
-        const int t = (int)(row % tpw);
-        const long long win = row / tpw;
-        const int wj = (int)(win % nWw);
-        const int wi = (int)((win / nWw) % nWh);
-        const int n = (int)(win / ((long long)nWw * nWh));
-        const int h = wi * wh + t / ww, w = wj * ww + t % ww;
-        if (h < H && w < W) src = x + (((size_t)n * H + h) * W + w) * ldx;  // else: zero-padded token (blocks_transformer.py:31-36)
-    } else {
-        src = x + (size_t)row * ldx;
+    if (valid) {
+        if (GATHER) {
+            const int tpw = wh * ww;
+            const int t = (int)(row % tpw);
+            const long long win = row / tpw;
+            const int wj = (int)(win % nWw);
+            const int wi = (int)((win / nWw) % nWh);
+            const int n = (int)(win / ((long long)nWw * nWh));
+            const int h = wi * wh + t / ww, w = wj * ww + t % ww;
+            if (h < H && w < W) src = x + (((size_t)n * H + h) * W + w) * ldx;  // else: zero-padded token (blocks_transformer.py:31-36)
+        } else {
+            src = x + (size_t)row * ldx;
+        }
     }
-    constexpr int MAXG = 8;  // C <= 2048
+    constexpr int MAXG = 8;  // C <= 8 * 8 * G
     float v[MAXG][8];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXG; ++i) {
-        const int cg = lane + 32 * i;
+        const int cg = gl + G * i;
         if (cg < c8n) {
             if (src) ysod_vec8<T>::load(src + cg * 8, v[i]);
             else {
@@ -402,22 +407,23 @@ __global__ void layernorm_kernel(const T* __restrict__ x, long long rows, int C,
             for (int e = 0; e < 8; ++e) s += v[i][e];
         }
     }
-    s = ysod_warp_sum(s);
+    for (int o = G >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float mean = s / (float)C;
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXG; ++i) {
-        const int cg = lane + 32 * i;
+        const int cg = gl + G * i;
         if (cg < c8n) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) { const float d = v[i][e] - mean; q += d * d; }
         }
     }
-    q = ysod_warp_sum(q);
+    for (int o = G >> 1; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     const float rstd = rsqrtf(q / (float)C + eps);
+    if (!valid) return;
 #pragma unroll
     for (int i = 0; i < MAXG; ++i) {
-        const int cg = lane + 32 * i;
+        const int cg = gl + G * i;
         if (cg < c8n) {
             if (GATHER && raw_out) ysod_vec8<T>::store(raw_out + (size_t)row * ldo + cg * 8, v[i]);
             float o[8];
@@ -501,6 +507,11 @@ __global__ void bilinear_rows_kernel(const T* __restrict__ x, int IH, int W, int
 }
 
 inline int blocks_for(long long total, int threads) { return ysod_cdiv(total, threads); }
+inline int ln_group(int C) {
+    int g = 1;
+    while (g < 32 && g < C / 8) g <<= 1;
+    return g;
+}
 
 }  // namespace
 
@@ -625,8 +636,9 @@ int ysod_upsample_copy(const void* x, int dtype, int N, int H, int W, int C, int
 int ysod_layernorm(const void* x, int dtype, long long rows, int C, int ldx, const float* gamma, const float* beta, float eps,
                    void* out, int ldo, cudaStream_t st) {
     YSOD_CHECK_ARG(x && gamma && beta && out && C % 8 == 0 && C <= 2048 && ldx % 8 == 0 && ldo % 8 == 0, "ysod_layernorm: bad args");
-    YSOD_DISPATCH(dtype, (layernorm_kernel<T, false><<<blocks_for(rows * 32, 256), 256, 0, st>>>(
-                             (const T*)x, rows, C, ldx, gamma, beta, eps, (T*)out, ldo, 0, 0, 1, 1, 1, 1, nullptr)));
+    const int G = ln_group(C);
+    YSOD_DISPATCH(dtype, (layernorm_kernel<T, false><<<blocks_for(rows * G, 256), 256, 0, st>>>(
+                             (const T*)x, rows, C, ldx, gamma, beta, eps, (T*)out, ldo, G, 0, 0, 1, 1, 1, 1, nullptr)));
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }
@@ -637,8 +649,9 @@ int ysod_window_partition_ln(const void* x, int dtype, int N, int H, int W, int 
                              cudaStream_t st) {
     YSOD_CHECK_ARG(x && gamma && beta && norm_out && C % 8 == 0 && C <= 2048 && xcs % 8 == 0 && ldo % 8 == 0, "ysod_window_partition_ln: bad args");
     const long long rows = (long long)N * nWh * nWw * wh * ww;
-    YSOD_DISPATCH(dtype, (layernorm_kernel<T, true><<<blocks_for(rows * 32, 256), 256, 0, st>>>(
-                             (const T*)x, rows, C, xcs, gamma, beta, eps, (T*)norm_out, ldo, H, W, wh, ww, nWh, nWw, (T*)raw_out)));
+    const int G = ln_group(C);
+    YSOD_DISPATCH(dtype, (layernorm_kernel<T, true><<<blocks_for(rows * G, 256), 256, 0, st>>>(
+                             (const T*)x, rows, C, xcs, gamma, beta, eps, (T*)norm_out, ldo, G, H, W, wh, ww, nWh, nWw, (T*)raw_out)));
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }

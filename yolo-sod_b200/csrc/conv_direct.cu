@@ -152,6 +152,76 @@ __global__ void stem_conv_kernel(const float* __restrict__ img, const float* __r
     ysod_vec8<TO>::store(out + (size_t)pix * ocs + c0, acc);
 }
 
+// Stem fast path (3x3, stride 2, pad 1): a CTA computes a 32 x 8 tile of output pixels for CO output channels at a time.
+// The 3 x 17 x 65 input patch is staged once in shared memory with coalesced row loads (this is also where NCHW becomes
+// NHWC); each thread owns one pixel and CO accumulators, weights are read as float4 shared-memory broadcasts.
+template <typename TO, int CO>
+__global__ void __launch_bounds__(256)
+stem_conv3x3s2_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
+                      TO* __restrict__ out, int H, int W, int Ho, int Wo, int Cout, int ocs, int act) {
+    constexpr int PH = 17, PW = 65, PWP = 66;
+    __shared__ float patch[3 * PH * PWP];
+    __shared__ __align__(16) float sw[27 * CO];
+    __shared__ float sb[CO];
+    const int n = blockIdx.z;
+    const int oh0 = blockIdx.y * 8, ow0 = blockIdx.x * 32;
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int ih0 = 2 * oh0 - 1, iw0 = 2 * ow0 - 1;
+    for (int i = tid; i < 3 * PH * PW; i += 256) {
+        const int c = i / (PH * PW);
+        const int r = (i / PW) % PH;
+        const int q = i % PW;
+        const int ih = ih0 + r, iw = iw0 + q;
+        float v = 0.f;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(img + (((size_t)n * 3 + c) * H + ih) * W + iw);
+        patch[(c * PH + r) * PWP + q] = v;
+    }
+    const int oh = oh0 + threadIdx.y, ow = ow0 + threadIdx.x;
+    const bool valid = oh < Ho && ow < Wo;
+    for (int co0 = 0; co0 < Cout; co0 += CO) {
+        __syncthreads();
+        // weights arrive as [Cout][3][3][3] (co, r, s, c); stage transposed as [tap*3 + c][CO]
+        for (int i = tid; i < 27 * CO; i += 256) {
+            const int t = i / CO, co = i % CO;
+            sw[i] = w[(size_t)(co0 + co) * 27 + t];
+        }
+        for (int i = tid; i < CO; i += 256) sb[i] = bias[co0 + i];
+        __syncthreads();
+        float acc[CO];
+#pragma unroll
+        for (int e = 0; e < CO; ++e) acc[e] = sb[e];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float xv = patch[(c * PH + 2 * threadIdx.y + r) * PWP + 2 * threadIdx.x + q];
+                    const float4* wp = reinterpret_cast<const float4*>(&sw[((r * 3 + q) * 3 + c) * CO]);
+#pragma unroll
+                    for (int e = 0; e < CO / 4; ++e) {
+                        const float4 w4 = wp[e];
+                        acc[4 * e] = fmaf(xv, w4.x, acc[4 * e]);
+                        acc[4 * e + 1] = fmaf(xv, w4.y, acc[4 * e + 1]);
+                        acc[4 * e + 2] = fmaf(xv, w4.z, acc[4 * e + 2]);
+                        acc[4 * e + 3] = fmaf(xv, w4.w, acc[4 * e + 3]);
+                    }
+                }
+            }
+        }
+        if (valid) {
+            TO* op = out + (((size_t)n * Ho + oh) * Wo + ow) * ocs + co0;
+#pragma unroll
+            for (int e = 0; e < CO; e += 8) {
+                float o8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o8[j] = ysod_act(acc[e + j], act);
+                ysod_vec8<TO>::store(op + e, o8);
+            }
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -205,6 +275,18 @@ int ysod_stem_conv(const float* img, int N, int H, int W, const float* w, const 
     YSOD_CHECK_ARG(img && w && bias && out, "ysod_stem_conv: null pointer");
     YSOD_CHECK_ARG(Cout % 8 == 0 && ocs % 8 == 0, "ysod_stem_conv: Cout must be a multiple of 8");
     const int Ho = (H + 2 * pad - k) / s + 1, Wo = (W + 2 * pad - k) / s + 1;
+    if (k == 3 && s == 2 && pad == 1 && Cout % 16 == 0) {
+        dim3 grid(ysod_cdiv(Wo, 32), ysod_cdiv(Ho, 8), N), block(32, 8);
+        if (Cout % 32 == 0) {
+            if (out_dtype == YSOD_F32) stem_conv3x3s2_kernel<float, 32><<<grid, block, 0, stream>>>(img, w, bias, (float*)out, H, W, Ho, Wo, Cout, ocs, act);
+            else stem_conv3x3s2_kernel<__nv_bfloat16, 32><<<grid, block, 0, stream>>>(img, w, bias, (__nv_bfloat16*)out, H, W, Ho, Wo, Cout, ocs, act);
+        } else {
+            if (out_dtype == YSOD_F32) stem_conv3x3s2_kernel<float, 16><<<grid, block, 0, stream>>>(img, w, bias, (float*)out, H, W, Ho, Wo, Cout, ocs, act);
+            else stem_conv3x3s2_kernel<__nv_bfloat16, 16><<<grid, block, 0, stream>>>(img, w, bias, (__nv_bfloat16*)out, H, W, Ho, Wo, Cout, ocs, act);
+        }
+        YSOD_LAUNCH_CHECK();
+        return YSOD_OK;
+    }
     const long long total = (long long)N * Ho * Wo * (Cout / 8);
     const int blocks = ysod_cdiv(total, 256);
     const size_t smem = (size_t)(Cout * k * k * 3 + Cout) * sizeof(float);

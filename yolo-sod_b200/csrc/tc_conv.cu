@@ -29,7 +29,7 @@ namespace {
 struct TcParams {
     int N, Ho, Wo, TH, TW, tiles_h, tiles_w;
     int Cin, ksize, stride, pad;
-    int BN, BK, stages, tmem_cols, num_k;
+    int BN, BK, stages, tmem_cols, num_k, n_tiles;
     int Cout;
     void* out;
     int out_f32;
@@ -41,6 +41,9 @@ struct TcParams {
     uint32_t idesc;
     uint32_t desc_hi;  // SBO | version | layout type (upper 32 bits of the smem descriptor)
     uint32_t a_bytes, b_bytes, a_tx;
+    // epilogue staging: output rows of `row_bytes` (<= 128 B, one swizzle span) per store unit of `unit_cols` columns
+    int unit_cols, n_units, swz_mask, cout_pad;
+    uint32_t row_bytes;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
@@ -78,6 +81,27 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -109,38 +133,67 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t* v) {
 
 constexpr int TC_THREADS = 192;
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int ACT>
+__device__ __forceinline__ void act16(float* f) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        if (ACT == YSOD_ACT_SILU) {  // x*sigmoid(x) = h + h*tanh(h), h = x/2: one MUFU op per element
+            const float h = 0.5f * f[j];
+            f[j] = fmaf(h, tanh_approx(h), h);
+        }
+        else if (ACT == YSOD_ACT_GELU) f[j] = 0.5f * f[j] * (1.0f + erff(f[j] * 0.70710678118654752440f));
+        else if (ACT == YSOD_ACT_RELU) f[j] = fmaxf(f[j], 0.0f);
+    }
+}
+
+// Persistent, warp-specialised: each CTA loops over output tiles (tile = blockIdx.x + i*gridDim.x). The smem ring keeps
+// streaming across tile boundaries and the accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue of
+// tile i overlaps the TMA/MMA main loop of tile i+1; barriers and TMEM are set up once per CTA.
 __global__ void __launch_bounds__(TC_THREADS)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_base = base;
     const uint32_t b_base = base + (uint32_t)p.stages * p.a_bytes;
     const uint32_t bar_base = b_base + (uint32_t)p.stages * p.b_bytes;  // 8-byte aligned (tiles are 1 KB multiples)
-    // full[s] = bar_base + 8*s ; empty[s] = bar_base + 8*(stages+s) ; tmem_full = bar_base + 16*stages ; slot after
-    const uint32_t tmem_full_bar = bar_base + 16u * p.stages;
-    const uint32_t tmem_slot = tmem_full_bar + 8u;
+    // full[s] = bar_base + 8*s ; empty[s] = bar_base + 8*(stages+s) ; then tfull[2], tempty[2], tmem slot
+    const uint32_t tfull_bar = bar_base + 16u * p.stages;
+    const uint32_t tempty_bar = tfull_bar + 16u;
+    const uint32_t tmem_slot = tempty_bar + 16u;
+    // after the barriers: bias[cout_pad] fp32, then two 16 KB (1 KB aligned) output staging buffers
+    const uint32_t bias_smem = tmem_slot + 16u;
+    const uint32_t stage_out = (bias_smem + 4u * (uint32_t)p.cout_pad + 1023u) & ~1023u;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    // tile coordinates
     const int tiles_per_img = p.tiles_h * p.tiles_w;
-    const int img = blockIdx.x / tiles_per_img;
-    const int trem = blockIdx.x - img * tiles_per_img;
-    const int oh0 = (trem / p.tiles_w) * p.TH;
-    const int ow0 = (trem % p.tiles_w) * p.TW;
-    const int n0 = blockIdx.y * p.BN;
+    const int m_tiles = p.N * tiles_per_img;
+    const int total_tiles = m_tiles * p.n_tiles;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(bar_base + 8u * s, 1);
             mbar_init(bar_base + 8u * (p.stages + s), 1);
         }
-        mbar_init(tmem_full_bar, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar + 8u * a, 1);
+            mbar_init(tempty_bar + 8u * a, 4);  // one arrive per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2) {
+        for (int i = threadIdx.x - 64; i < p.cout_pad; i += 128) {
+            const float bv = __ldg(p.bias + i);
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_smem + 4u * i), "f"(bv) : "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -155,95 +208,153 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t tx = p.a_tx + p.b_bytes;
             int stage = 0;
             uint32_t phase = 0;
-            for (int kb = 0; kb < p.num_k; ++kb) {
-                mbar_wait(bar_base + 8u * (p.stages + stage), phase ^ 1u);
-                const int tap = kb / cchunks;
-                const int cc = kb - tap * cchunks;
-                const int r = tap / p.ksize, s = tap - r * p.ksize;
-                const uint32_t full = bar_base + 8u * stage;
-                mbar_expect_tx(full, tx);
-                tma_load_4d(a_base + (uint32_t)stage * p.a_bytes, &tmA, full, cc * p.BK, ow0 * p.stride + s - p.pad,
-                            oh0 * p.stride + r - p.pad, img);
-                tma_load_2d(b_base + (uint32_t)stage * p.b_bytes, &tmB, full, tap * p.Cin + cc * p.BK, n0);
-                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int nt = t / m_tiles, mt = t - nt * m_tiles;
+                const int img = mt / tiles_per_img;
+                const int trem = mt - img * tiles_per_img;
+                const int oh0 = (trem / p.tiles_w) * p.TH, ow0 = (trem % p.tiles_w) * p.TW;
+                const int n0 = nt * p.BN;
+                for (int kb = 0; kb < p.num_k; ++kb) {
+                    mbar_wait(bar_base + 8u * (p.stages + stage), phase ^ 1u);
+                    const int tap = kb / cchunks;
+                    const int cc = kb - tap * cchunks;
+                    const int r = tap / p.ksize, s = tap - r * p.ksize;
+                    const uint32_t full = bar_base + 8u * stage;
+                    mbar_expect_tx(full, tx);
+                    tma_load_4d(a_base + (uint32_t)stage * p.a_bytes, &tmA, full, cc * p.BK, ow0 * p.stride + s - p.pad,
+                                oh0 * p.stride + r - p.pad, img);
+                    tma_load_2d(b_base + (uint32_t)stage * p.b_bytes, &tmB, full, tap * p.Cin + cc * p.BK, n0);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
             const int ksteps = p.BK / 16;
-            for (int kb = 0; kb < p.num_k; ++kb) {
-                mbar_wait(bar_base + 8u * stage, phase);
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                mbar_wait(tempty_bar + 8u * acc, acc_phase ^ 1u);  // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t a_addr = a_base + (uint32_t)stage * p.a_bytes;
-                const uint32_t b_addr = b_base + (uint32_t)stage * p.b_bytes;
-                for (int k = 0; k < ksteps; ++k) {
-                    // descriptor: start address (>>4) advanced by 32 B per UMMA_K inside the swizzle row; LBO = 1
-                    const uint64_t adesc = ((uint64_t)p.desc_hi << 32) | (uint64_t)(((a_addr + 32u * k) >> 4) & 0x3FFFu) | (1ull << 16);
-                    const uint64_t bdesc = ((uint64_t)p.desc_hi << 32) | (uint64_t)(((b_addr + 32u * k) >> 4) & 0x3FFFu) | (1ull << 16);
-                    tc_mma_bf16(tmem_acc, adesc, bdesc, p.idesc, (uint32_t)((kb | k) != 0));
+                const uint32_t d_tmem = tmem_acc + (uint32_t)(acc * p.BN);
+                for (int kb = 0; kb < p.num_k; ++kb) {
+                    mbar_wait(bar_base + 8u * stage, phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = a_base + (uint32_t)stage * p.a_bytes;
+                    const uint32_t b_addr = b_base + (uint32_t)stage * p.b_bytes;
+                    for (int k = 0; k < ksteps; ++k) {
+                        // descriptor: start address (>>4) advanced by 32 B per UMMA_K inside the swizzle row; LBO = 1
+                        const uint64_t adesc = ((uint64_t)p.desc_hi << 32) | (uint64_t)(((a_addr + 32u * k) >> 4) & 0x3FFFu) | (1ull << 16);
+                        const uint64_t bdesc = ((uint64_t)p.desc_hi << 32) | (uint64_t)(((b_addr + 32u * k) >> 4) & 0x3FFFu) | (1ull << 16);
+                        tc_mma_bf16(d_tmem, adesc, bdesc, p.idesc, (uint32_t)((kb | k) != 0));
+                    }
+                    tc_commit(bar_base + 8u * (p.stages + stage));  // frees the smem slot when these MMAs retire
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
-                tc_commit(bar_base + 8u * (p.stages + stage));  // frees the smem slot when these MMAs retire
-                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                tc_commit(tfull_bar + 8u * acc);  // accumulator complete
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
             }
-            tc_commit(tmem_full_bar);  // accumulator complete
         }
     } else {
         // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4 =====
+        // TMEM -> registers -> (+bias, act, +residual) -> 128B/64B/32B-swizzled shared-memory rows -> one TMA tensor store per
+        // unit of <= 128 B of channels. TMA clips ragged tiles and the Cout padding, and writes whole lines to L2.
         const int q = warp & 3;
         const int m = q * 32 + lane;
         const int th = m / p.TW, tw = m - th * p.TW;
-        const int oh = oh0 + th, ow = ow0 + tw;
-        const bool valid = (m < p.TH * p.TW) && (oh < p.Ho) && (ow < p.Wo);
-        const size_t pix = ((size_t)img * p.Ho + oh) * p.Wo + ow;
-        mbar_wait(tmem_full_bar, 0);
-        tc_fence_after();
-        const uint32_t trow = tmem_acc + ((uint32_t)(q * 32) << 16);
-        for (int c0 = 0; c0 < p.BN; c0 += 16) {
-            const int col = n0 + c0;
-            if (col >= p.Cout) break;  // warp-uniform
-            uint32_t v[16];
-            tmem_ld16(trow + (uint32_t)c0, v);
-            tmem_ld_wait(v);
-            if (!valid) continue;
-            float f[16];
+        const bool store_leader = (threadIdx.x == 64);
+        int acc = 0, sbuf = 0;
+        uint32_t acc_phase = 0;
+        const int chunks_per_unit = p.unit_cols >> 4;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int nt = t / m_tiles, mt = t - nt * m_tiles;
+            const int img = mt / tiles_per_img;
+            const int trem = mt - img * tiles_per_img;
+            const int oh0 = (trem / p.tiles_w) * p.TH, ow0 = (trem % p.tiles_w) * p.TW;
+            const int oh = oh0 + th, ow = ow0 + tw;
+            const int n0 = nt * p.BN;
+            const bool valid = (m < p.TH * p.TW) && (oh < p.Ho) && (ow < p.Wo);
+            const size_t pix = ((size_t)img * p.Ho + oh) * p.Wo + ow;
+            mbar_wait(tfull_bar + 8u * acc, acc_phase);
+            tc_fence_after();
+            const uint32_t trow = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+            for (int u = 0; u < p.n_units; ++u) {
+                const uint32_t sb = stage_out + (uint32_t)sbuf * 16384u;
+                // the bulk store issued from this buffer two units ago must have finished reading it
+                if (store_leader) bulk_wait_read<1>();
+                epi_barrier();
+                const uint32_t row_addr = sb + (uint32_t)m * p.row_bytes;
+                for (int ch = 0; ch < chunks_per_unit; ++ch) {
+                    const int c0 = u * p.unit_cols + ch * 16;
+                    if (c0 >= p.BN) break;  // warp-uniform
+                    uint32_t v[16];
+                    tmem_ld16(trow + (uint32_t)c0, v);
+                    tmem_ld_wait(v);
+                    float f[16];
+                    const uint32_t bsm = bias_smem + 4u * (uint32_t)(n0 + c0);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = ysod_act(__uint_as_float(v[j]) + __ldg(p.bias + col + j), p.act);
-            const bool full_chunk = (col + 16 <= p.Cout);
-            if (p.res != nullptr) {
-                const __nv_bfloat16* rp = p.res + pix * p.rcs + col;
-                if (full_chunk) {
-                    float r8[8];
-                    ysod_vec8<__nv_bfloat16>::load(rp, r8);
+                    for (int j = 0; j < 4; ++j) {
+                        float b0, b1, b2, b3;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3) : "r"(bsm + 16u * j));
+                        f[4 * j] = __uint_as_float(v[4 * j]) + b0;
+                        f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b1;
+                        f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b2;
+                        f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b3;
+                    }
+                    if (p.act == YSOD_ACT_SILU) act16<YSOD_ACT_SILU>(f);
+                    else if (p.act == YSOD_ACT_GELU) act16<YSOD_ACT_GELU>(f);
+                    else if (p.act == YSOD_ACT_RELU) act16<YSOD_ACT_RELU>(f);
+                    if (p.res != nullptr && valid) {
+                        const __nv_bfloat16* rp = p.res + pix * p.rcs + n0 + c0;
+                        float r8[8];
+                        ysod_vec8<__nv_bfloat16>::load(rp, r8);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) f[j] += r8[j];
-                    ysod_vec8<__nv_bfloat16>::load(rp + 8, r8);
+                        for (int j = 0; j < 8; ++j) f[j] += r8[j];
+                        ysod_vec8<__nv_bfloat16>::load(rp + 8, r8);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) f[8 + j] += r8[j];
-                } else {
-                    for (int j = 0; j < 16 && col + j < p.Cout; ++j) f[j] += __bfloat162float(rp[j]);
+                        for (int j = 0; j < 8; ++j) f[8 + j] += r8[j];
+                    }
+                    // swizzled store: 16-byte piece index ^= (address bits [7..]) & mask  (== the TMA swizzle of tmO)
+                    if (p.out_f32) {
+                        const uint32_t off0 = (uint32_t)(ch * 64);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint32_t a = row_addr + off0 + 16u * j;
+                            a ^= ((a >> 7) & (uint32_t)p.swz_mask) << 4;
+                            st_shared_v4(a, __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
+                                         __float_as_uint(f[4 * j + 3]));
+                        }
+                    } else {
+                        const uint32_t off0 = (uint32_t)(ch * 32);
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            uint32_t a = row_addr + off0 + 16u * j;
+                            a ^= ((a >> 7) & (uint32_t)p.swz_mask) << 4;
+                            st_shared_v4(a, pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                                         pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+                        }
+                    }
                 }
+                if (u == p.n_units - 1) {
+                    // all TMEM reads of this warp are complete (tcgen05.wait::ld above): hand the accumulator back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty_bar + 8u * acc);
+                }
+                fence_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+                epi_barrier();
+                if (store_leader) {
+                    tma_store_4d(&tmO, sb, n0 + u * p.unit_cols, ow0, oh0, img);
+                    bulk_commit();
+                }
+                sbuf ^= 1;
             }
-            if (p.out_f32) {
-                float* op = (float*)p.out + pix * p.ocs + col;
-                if (full_chunk) {
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                } else {
-                    for (int j = 0; j < 16 && col + j < p.Cout; ++j) op[j] = f[j];
-                }
-            } else {
-                __nv_bfloat16* op = (__nv_bfloat16*)p.out + pix * p.ocs + col;
-                if (full_chunk) {
-                    ysod_vec8<__nv_bfloat16>::store(op, f);
-                    ysod_vec8<__nv_bfloat16>::store(op + 8, f + 8);
-                } else {
-                    for (int j = 0; j < 16 && col + j < p.Cout; ++j) op[j] = __float2bfloat16_rn(f[j]);
-                }
-            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
         }
+        if (store_leader) bulk_wait_read<0>();  // smem must stay valid until the last bulk store has read it
     }
 
     tc_fence_before();
@@ -270,7 +381,7 @@ EncodeTiledFn get_encode() {
 }
 
 struct ConvTc {
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmO;
     TcParams p;
     dim3 grid;
     size_t smem;
@@ -335,7 +446,8 @@ int ysod_conv_tc_create(ysod_conv_tc** handle, const void* x, int N, int H, int 
         while (Cout_pad % BN != 0) BN -= 16;  // largest multiple of 16 <= 256 dividing Cout_pad
     }
     p.BN = BN;
-    p.tmem_cols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    p.tmem_cols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;  // double-buffered accumulator
+    p.n_tiles = Cout_pad / BN;
     p.num_k = ksize * ksize * (Cin / p.BK);
     p.Cout = Cout;
     p.out = out; p.out_f32 = (out_dtype == YSOD_F32); p.ocs = ocs;
@@ -350,14 +462,38 @@ int ysod_conv_tc_create(ysod_conv_tc** handle, const void* x, int N, int H, int 
     const uint32_t layout = (p.BK == 64) ? 2u : 4u;  // SWIZZLE_128B : SWIZZLE_64B
     p.desc_hi = sbo | (1u << 14) | (layout << 29);
     const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
-    uint32_t budget = (3u * stage_bytes <= 100u * 1024u) ? 100u * 1024u : 200u * 1024u;
+    const uint32_t fixed = 2u * 16384u + 4u * (uint32_t)Cout_pad + 3u * 1024u;   // staging + bias + slack
+    uint32_t budget = (3u * stage_bytes + fixed <= 112u * 1024u) ? 112u * 1024u - fixed : 224u * 1024u - fixed;
     int stages = (int)(budget / stage_bytes);
-    if (stages > 8) stages = 8;
-    if (stages > p.num_k) stages = p.num_k;
-    if (stages < 1) stages = 1;
+    if (stages > 8) stages = 8;   // persistent kernel: the ring streams across tiles, so depth is not capped by num_k
+    if (stages < 2) stages = 2;
     p.stages = stages;
-    c.smem = (size_t)stages * stage_bytes + 1024 + 16 * stages + 64;
-    c.grid = dim3((unsigned)((long long)N * p.tiles_h * p.tiles_w), (unsigned)(Cout_pad / BN), 1);
+    {
+        const uint32_t es = p.out_f32 ? 4u : 2u;
+        uint32_t rb = 32;
+        while (rb < 128 && rb < (uint32_t)BN * es) rb <<= 1;
+        p.row_bytes = rb;
+        p.unit_cols = (int)(rb / es);
+        p.n_units = (int)(((uint32_t)BN * es + rb - 1) / rb);
+        p.swz_mask = rb == 128 ? 7 : rb == 64 ? 3 : 1;
+        p.cout_pad = Cout_pad;
+    }
+    // ring + 1 KB alignment slack + barriers/slot + bias + alignment + two 16 KB output staging buffers
+    c.smem = (size_t)stages * stage_bytes + 1024 + (16 * stages + 64) + 4 * (size_t)Cout_pad + 1024 + 2 * 16384;
+    {
+        int dev = 0, sms = 148;
+        YSOD_CUDA(cudaGetDevice(&dev));
+        YSOD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        // co-resident persistent CTAs per SM: limited by shared memory (227 KB) and TMEM (512 columns)
+        int per_sm = (int)((227u * 1024u) / (c.smem + 1024));
+        if (per_sm > 512 / p.tmem_cols) per_sm = 512 / p.tmem_cols;
+        if (per_sm > 2) per_sm = 2;
+        if (per_sm < 1) per_sm = 1;
+        const long long total = (long long)N * p.tiles_h * p.tiles_w * p.n_tiles;
+        long long g = (long long)sms * per_sm;
+        if (g > total) g = total;
+        c.grid = dim3((unsigned)g, 1, 1);
+    }
 
     const CUtensorMapSwizzle swz = p.BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     {
@@ -386,7 +522,26 @@ int ysod_conv_tc_create(ysod_conv_tc** handle, const void* x, int N, int H, int 
             return YSOD_ERR_CUDA;
         }
     }
-    YSOD_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    {
+        // output map: channel slice [Cout] x Wo x Ho x N, box = {unit_cols, TW, TH, 1}; stores clip ragged tiles / Cout padding
+        const cuuint64_t es = p.out_f32 ? 4 : 2;
+        cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)ocs * es, (cuuint64_t)Wo * ocs * es, (cuuint64_t)Ho * Wo * ocs * es};
+        cuuint32_t box[4] = {(cuuint32_t)p.unit_cols, (cuuint32_t)bestTW, (cuuint32_t)bestTH, 1};
+        cuuint32_t es1[4] = {1, 1, 1, 1};
+        const CUtensorMapSwizzle oswz = p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                      : p.row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+        CUresult r = enc(&c.tmO, p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, dims, strides,
+                         box, es1, CU_TENSOR_MAP_INTERLEAVE_NONE, oswz, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            ysod_set_error("ysod_conv_tc_create: cuTensorMapEncodeTiled(O) failed with %d (Cout %d ocs %d unit %d)", (int)r, Cout, ocs,
+                           p.unit_cols);
+            return YSOD_ERR_CUDA;
+        }
+    }
+    YSOD_CHECK_ARG(!res || Cout % 16 == 0, "ysod_conv_tc_create: residual needs Cout %% 16 == 0");
+    YSOD_CHECK_ARG(c.smem <= 227 * 1024, "ysod_conv_tc_create: shared memory plan too large (%zu)", c.smem);
+    YSOD_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     ysod_conv_tc* h = new (std::nothrow) ysod_conv_tc;
     YSOD_CHECK_ARG(h, "ysod_conv_tc_create: out of memory");
     h->c = c;
@@ -396,7 +551,7 @@ int ysod_conv_tc_create(ysod_conv_tc** handle, const void* x, int N, int H, int 
 
 int ysod_conv_tc_run(ysod_conv_tc* h, cudaStream_t stream) {
     YSOD_CHECK_ARG(h, "ysod_conv_tc_run: null handle");
-    conv_tc_kernel<<<h->c.grid, TC_THREADS, h->c.smem, stream>>>(h->c.tmA, h->c.tmB, h->c.p);
+    conv_tc_kernel<<<h->c.grid, TC_THREADS, h->c.smem, stream>>>(h->c.tmA, h->c.tmB, h->c.tmO, h->c.p);
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }
@@ -405,7 +560,7 @@ int ysod_conv_tc_run(ysod_conv_tc* h, cudaStream_t stream) {
 int ysod_conv_tc_info(ysod_conv_tc* h, int* out8) {
     YSOD_CHECK_ARG(h && out8, "ysod_conv_tc_info: null");
     out8[0] = h->c.p.TH; out8[1] = h->c.p.TW; out8[2] = h->c.p.BN; out8[3] = h->c.p.BK; out8[4] = h->c.p.stages;
-    out8[5] = (int)h->c.grid.x; out8[6] = (int)h->c.grid.y; out8[7] = (int)h->c.smem;
+    out8[5] = (int)h->c.grid.x; out8[6] = h->c.p.n_tiles; out8[7] = (int)h->c.smem;
     return YSOD_OK;
 }
 
