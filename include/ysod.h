@@ -47,6 +47,10 @@ typedef struct ysod_conv_tc ysod_conv_tc;
 int ysod_conv_tc_create(ysod_conv_tc** handle, const void* x, int N, int H, int W, int Cin, int xcs, const void* wgt,
                         const float* bias, int Cout, int Cout_pad, int ksize, int stride, void* out, int out_dtype, int ocs,
                         const void* res, int rcs, int act);
+/* mode: 0 auto, 1 generic per-tap kernel, 2 force the 3x3/s1 halo-reuse kernel */
+int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, int W, int Cin, int xcs, const void* wgt,
+                           const float* bias, int Cout, int Cout_pad, int ksize, int stride, void* out, int out_dtype, int ocs,
+                           const void* res, int rcs, int act, int mode);
 int ysod_conv_tc_run(ysod_conv_tc* handle, void* stream);
 int ysod_conv_tc_info(ysod_conv_tc* handle, int* out8);
 void ysod_conv_tc_destroy(ysod_conv_tc* handle);

@@ -15,7 +15,8 @@ def _act(y, act):
     return {"none": lambda t: t, "silu": F.silu, "gelu": F.gelu, "relu": F.relu}[act](y)
 
 
-def _run_tc(N, H, W, Cin, Cout, k, s, act="silu", res=False, out_f32=False, xcs_extra=0, ocs_extra=0, seed=0, out_first=False):
+def _run_tc(N, H, W, Cin, Cout, k, s, act="silu", res=False, out_f32=False, xcs_extra=0, ocs_extra=0, seed=0, out_first=False,
+            mode=1):
     from yolo_sod_b200 import lib
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(N, H, W, Cin, generator=g).bfloat16()
@@ -41,9 +42,9 @@ def _run_tc(N, H, W, Cin, Cout, k, s, act="silu", res=False, out_f32=False, xcs_
     bd = bd.cuda()
     rd = r.cuda().contiguous() if res else None
     h = C.c_void_p()
-    lib.call("ysod_conv_tc_create", C.byref(h), lib.ptr(xb, xcs_extra), N, H, W, Cin, xcs, lib.ptr(wd), lib.ptr(bd), Cout, cpad, k, s,
+    lib.call("ysod_conv_tc_create_ex", C.byref(h), lib.ptr(xb, xcs_extra), N, H, W, Cin, xcs, lib.ptr(wd), lib.ptr(bd), Cout, cpad, k, s,
              lib.ptr(ob, 0 if out_first else ocs_extra), lib.F32 if out_f32 else lib.BF16, ocs, lib.ptr(rd) if res else None, Cout if res else 0,
-             lib.ACT[act])
+             lib.ACT[act], mode)
     info = (C.c_int * 8)()
     lib.call("ysod_conv_tc_info", h, info)
     lib.call("ysod_conv_tc_run", h, lib.stream_ptr())
@@ -86,6 +87,24 @@ CASES = [
 def test_conv_tc(case):
     *dims, kw = case
     _run_tc(*dims, **kw)
+
+
+HALO_CASES = [
+    (1, 16, 8, 64, 64, 3, 1, {}),                                   # exactly one tile, weights resident
+    (2, 40, 40, 64, 64, 3, 1, dict(res=True)),                      # ragged tiles in both directions + residual
+    (3, 160, 160, 64, 64, 3, 1, {}),                                # the top-FLOP layer shape; many tiles per CTA
+    (2, 80, 80, 128, 64, 3, 1, {}),                                 # two channel chunks, streamed weight taps
+    (2, 40, 40, 128, 128, 3, 1, dict(act="none")),                  # BN=128
+    (1, 32, 32, 256, 64, 3, 1, dict(xcs_extra=64, ocs_extra=64)),   # four chunks, sliced views
+    (1, 48, 24, 64, 64, 3, 1, dict(out_f32=True, act="none")),      # fp32 output (two store units)
+    (1, 20, 20, 64, 32, 3, 1, {}),                                  # BN=32 (64 B staging rows), low-utilisation map forced
+]
+
+
+@pytest.mark.parametrize("case", HALO_CASES, ids=lambda c: "x".join(str(v) for v in c[:7]))
+def test_conv_tc_halo(case):
+    *dims, kw = case
+    _run_tc(*dims, mode=2, **kw)
 
 
 def _run_direct(dtype, N, H, W, Cin, Cout, k, s, g, act="silu", res=False, pad=None):

@@ -14,6 +14,7 @@ from yolo_sod_b200 import lib  # noqa: E402
 
 N, H, W, Cin, Cout, k, s = [int(v) for v in sys.argv[1:8]]
 iters = int(sys.argv[8]) if len(sys.argv) > 8 else 5
+mode = int(sys.argv[9]) if len(sys.argv) > 9 else 0
 pad = k // 2
 Ho, Wo = (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1
 x = torch.randn(N, H, W, Cin, device="cuda").bfloat16()
@@ -22,8 +23,8 @@ w = (torch.randn(cpad, k * k * Cin, device="cuda") / (k * k * Cin) ** 0.5).bfloa
 b = torch.zeros(cpad, device="cuda")
 o = torch.empty(N, Ho, Wo, Cout, device="cuda", dtype=torch.bfloat16)
 h = C.c_void_p()
-lib.call("ysod_conv_tc_create", C.byref(h), lib.ptr(x), N, H, W, Cin, Cin, lib.ptr(w), lib.ptr(b), Cout, cpad, k, s, lib.ptr(o), lib.BF16,
-         Cout, None, 0, lib.ACT["silu"])
+lib.call("ysod_conv_tc_create_ex", C.byref(h), lib.ptr(x), N, H, W, Cin, Cin, lib.ptr(w), lib.ptr(b), Cout, cpad, k, s, lib.ptr(o), lib.BF16,
+         Cout, None, 0, lib.ACT["silu"], mode)
 info = (C.c_int * 8)()
 lib.call("ysod_conv_tc_info", h, info)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -38,5 +39,5 @@ for i in range(iters):
     ts.append(e0.elapsed_time(e1))
 fl = 2.0 * N * Ho * Wo * Cout * k * k * Cin
 t = sorted(ts)[len(ts) // 2]
-print(f"conv {Cin}->{Cout} k{k}s{s} N{N} {H}x{W}: tile {info[0]}x{info[1]} BN{info[2]} BK{info[3]} stages{info[4]} grid {info[5]}x{info[6]} "
+print(f"conv mode{mode} {Cin}->{Cout} k{k}s{s} N{N} {H}x{W}: tile {info[0]}x{info[1]} BN{info[2]} BK{info[3]} stages{info[4]} grid {info[5]}x{info[6]} "
       f"smem {info[7]}  median {t * 1e3:.1f} us  {fl / t / 1e9:.1f} TFLOP/s  ({fl / 1e9:.1f} GFLOP)")

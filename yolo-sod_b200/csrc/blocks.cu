@@ -340,6 +340,55 @@ __global__ void sppf_pool_kernel(const T* __restrict__ y0, int H, int W, int C, 
     ysod_vec8<T>::store(o3 + (size_t)pix * ocs + cg * 8, m3);
 }
 
+// SPPF for small maps (H*W <= 1024, i.e. P5 up to 1024^2 inputs): one CTA per (image, 8-channel group) keeps the plane in
+// shared memory and applies the separable 5x5 max three times (row pass, column pass), writing o1, o2, o3.
+template <typename T>
+__global__ void __launch_bounds__(256)
+sppf_plane_kernel(const T* __restrict__ y0, int H, int W, int xcs, int k, T* __restrict__ o1, T* __restrict__ o2,
+                  T* __restrict__ o3, int ocs) {
+    extern __shared__ float sppf_sm[];
+    const int n = blockIdx.y, cg = blockIdx.x;
+    const int HW = H * W, r = k / 2;
+    float* a = sppf_sm;
+    float* b = sppf_sm + HW * 8;
+    for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+        float v[8];
+        ysod_vec8<T>::load(y0 + ((size_t)n * HW + p) * xcs + cg * 8, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a[p * 8 + e] = v[e];
+    }
+    __syncthreads();
+    T* outs[3] = {o1, o2, o3};
+    for (int pass = 0; pass < 3; ++pass) {
+        for (int i = threadIdx.x; i < HW * 8; i += blockDim.x) {  // row max: a -> b
+            const int e = i & 7, p = i >> 3, h = p / W, w = p % W;
+            float m = -INFINITY;
+            for (int d = -r; d <= r; ++d) {
+                const int ww = w + d;
+                if (ww >= 0 && ww < W) m = fmaxf(m, a[(h * W + ww) * 8 + e]);
+            }
+            b[i] = m;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < HW * 8; i += blockDim.x) {  // column max: b -> a
+            const int e = i & 7, p = i >> 3, h = p / W, w = p % W;
+            float m = -INFINITY;
+            for (int d = -r; d <= r; ++d) {
+                const int hh = h + d;
+                if (hh >= 0 && hh < H) m = fmaxf(m, b[(hh * W + w) * 8 + e]);
+            }
+            a[i] = m;
+        }
+        __syncthreads();
+        for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = a[p * 8 + e];
+            ysod_vec8<T>::store(outs[pass] + ((size_t)n * HW + p) * ocs + cg * 8, v);
+        }
+    }
+}
+
 // nearest-neighbour upsample by `scale` (1 = plain slice copy) into a channel slice
 template <typename T>
 __global__ void upsample_copy_kernel(const T* __restrict__ x, int H, int W, int C, int xcs, int scale, T* __restrict__ out,
@@ -618,6 +667,17 @@ int ysod_ca_apply(const void* x, int dtype, int N, int H, int W, int C, int xcs,
 int ysod_sppf_pool(const void* y0, int dtype, int N, int H, int W, int C, int xcs, int k, void* o1, void* o2, void* o3, int ocs,
                    cudaStream_t st) {
     YSOD_CHECK_ARG(y0 && o1 && o2 && o3 && C % 8 == 0 && xcs % 8 == 0 && ocs % 8 == 0 && (k & 1), "ysod_sppf_pool: bad args");
+    if (H * W <= 1024) {
+        dim3 grid(C / 8, N);
+        const size_t smem = (size_t)2 * H * W * 8 * sizeof(float);
+        if (smem > 48 * 1024) {
+            YSOD_CUDA(cudaFuncSetAttribute(sppf_plane_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            YSOD_CUDA(cudaFuncSetAttribute(sppf_plane_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        }
+        YSOD_DISPATCH(dtype, (sppf_plane_kernel<T><<<grid, 256, smem, st>>>((const T*)y0, H, W, xcs, k, (T*)o1, (T*)o2, (T*)o3, ocs)));
+        YSOD_LAUNCH_CHECK();
+        return YSOD_OK;
+    }
     const long long total = (long long)N * H * W * (C / 8);
     YSOD_DISPATCH(dtype, (sppf_pool_kernel<T><<<blocks_for(total, 128), 128, 0, st>>>((const T*)y0, H, W, C, xcs, k, (T*)o1, (T*)o2, (T*)o3, ocs, total)));
     YSOD_LAUNCH_CHECK();

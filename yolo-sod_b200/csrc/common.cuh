@@ -65,6 +65,18 @@ template <> __device__ __forceinline__ void ysod_st<__nv_bfloat16>(__nv_bfloat16
 
 __device__ __forceinline__ float ysod_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7): one rcp + one exp instead of erff's long polynomial path
+__device__ __forceinline__ float ysod_erf_fast(float x) {
+    const float ax = fabsf(x);
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = 1.0f - p * t * __expf(-ax * ax);
+    return copysignf(e, x);
+}
+
 __device__ __forceinline__ float ysod_act(float x, int act) {
     switch (act) {
         case YSOD_ACT_SILU: return x / (1.0f + expf(-x));

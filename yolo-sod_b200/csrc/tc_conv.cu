@@ -30,6 +30,7 @@ struct TcParams {
     int N, Ho, Wo, TH, TW, tiles_h, tiles_w;
     int Cin, ksize, stride, pad;
     int BN, BK, stages, tmem_cols, num_k, n_tiles;
+    int a_stages, b_stages, b_resident, cchunks;   // halo mode (3x3/s1): separate A (halo copies) and B (weight taps) rings
     int Cout;
     void* out;
     int out_f32;
@@ -145,7 +146,7 @@ __device__ __forceinline__ void act16(float* f) {
             const float h = 0.5f * f[j];
             f[j] = fmaf(h, tanh_approx(h), h);
         }
-        else if (ACT == YSOD_ACT_GELU) f[j] = 0.5f * f[j] * (1.0f + erff(f[j] * 0.70710678118654752440f));
+        else if (ACT == YSOD_ACT_GELU) f[j] = 0.5f * f[j] * (1.0f + ysod_erf_fast(f[j] * 0.70710678118654752440f));
         else if (ACT == YSOD_ACT_RELU) f[j] = fmaxf(f[j], 0.0f);
     }
 }
@@ -153,16 +154,27 @@ __device__ __forceinline__ void act16(float* f) {
 // Persistent, warp-specialised: each CTA loops over output tiles (tile = blockIdx.x + i*gridDim.x). The smem ring keeps
 // streaming across tile boundaries and the accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue of
 // tile i overlaps the TMA/MMA main loop of tile i+1; barriers and TMEM are set up once per CTA.
+//
+// HALO = true is the 3x3 / stride-1 specialisation that removes the 9x re-fetch of the activation tile from L2: an output
+// tile is 16 rows x 8 columns; for every 64-channel chunk THREE column-shifted halo copies (18 rows x 8 px x 128 B, one per
+// filter column s) are landed by TMA, and the three filter rows r are plain +1024 B (one 8-row swizzle atom) offsets of the
+// UMMA descriptor start address into the same copy -- always atom-aligned, so the canonical SW128 K-major layout holds.
+// A traffic per tile drops from 9 x 16 KB to 3 x 18 KB; weight taps stream through their own ring, or stay resident in
+// shared memory for the whole CTA lifetime when they fit (64->64: 72 KB).
+template <bool HALO>
 __global__ void __launch_bounds__(TC_THREADS)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_base = base;
-    const uint32_t b_base = base + (uint32_t)p.stages * p.a_bytes;
-    const uint32_t bar_base = b_base + (uint32_t)p.stages * p.b_bytes;  // 8-byte aligned (tiles are 1 KB multiples)
-    // full[s] = bar_base + 8*s ; empty[s] = bar_base + 8*(stages+s) ; then tfull[2], tempty[2], tmem slot
-    const uint32_t tfull_bar = bar_base + 16u * p.stages;
+    const uint32_t b_base = base + (uint32_t)p.a_stages * p.a_bytes;
+    const uint32_t bar_base = b_base + (uint32_t)p.b_stages * p.b_bytes;  // 8-byte aligned (tiles are 1 KB multiples)
+    // fullA[i], emptyA[i] (i < a_stages), fullB[i], emptyB[i] (i < b_stages), then tfull[2], tempty[2], tmem slot.
+    // Generic mode uses the A barriers for the combined {A,B} stage.
+    const uint32_t fullA = bar_base, emptyA = bar_base + 8u * p.a_stages;
+    const uint32_t fullB = bar_base + 16u * p.a_stages, emptyB = fullB + 8u * p.b_stages;
+    const uint32_t tfull_bar = fullB + 16u * p.b_stages;
     const uint32_t tempty_bar = tfull_bar + 16u;
     const uint32_t tmem_slot = tempty_bar + 16u;
     // after the barriers: bias[cout_pad] fp32, then two 16 KB (1 KB aligned) output staging buffers
@@ -175,9 +187,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int total_tiles = m_tiles * p.n_tiles;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; ++s) {
-            mbar_init(bar_base + 8u * s, 1);
-            mbar_init(bar_base + 8u * (p.stages + s), 1);
+        for (int s = 0; s < p.a_stages; ++s) {
+            mbar_init(fullA + 8u * s, 1);
+            mbar_init(emptyA + 8u * s, 1);
+        }
+        for (int s = 0; s < p.b_stages; ++s) {
+            mbar_init(fullB + 8u * s, 1);
+            mbar_init(emptyB + 8u * s, 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar + 8u * a, 1);
@@ -204,57 +220,129 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            const int cchunks = p.Cin / p.BK;
-            const uint32_t tx = p.a_tx + p.b_bytes;
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int nt = t / m_tiles, mt = t - nt * m_tiles;
-                const int img = mt / tiles_per_img;
-                const int trem = mt - img * tiles_per_img;
-                const int oh0 = (trem / p.tiles_w) * p.TH, ow0 = (trem % p.tiles_w) * p.TW;
-                const int n0 = nt * p.BN;
-                for (int kb = 0; kb < p.num_k; ++kb) {
-                    mbar_wait(bar_base + 8u * (p.stages + stage), phase ^ 1u);
-                    const int tap = kb / cchunks;
-                    const int cc = kb - tap * cchunks;
-                    const int r = tap / p.ksize, s = tap - r * p.ksize;
-                    const uint32_t full = bar_base + 8u * stage;
-                    mbar_expect_tx(full, tx);
-                    tma_load_4d(a_base + (uint32_t)stage * p.a_bytes, &tmA, full, cc * p.BK, ow0 * p.stride + s - p.pad,
-                                oh0 * p.stride + r - p.pad, img);
-                    tma_load_2d(b_base + (uint32_t)stage * p.b_bytes, &tmB, full, tap * p.Cin + cc * p.BK, n0);
-                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            const int cchunks = p.cchunks;
+            if (!HALO) {
+                const uint32_t tx = p.a_tx + p.b_bytes;
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                    const int nt = t / m_tiles, mt = t - nt * m_tiles;
+                    const int img = mt / tiles_per_img;
+                    const int trem = mt - img * tiles_per_img;
+                    const int oh0 = (trem / p.tiles_w) * p.TH, ow0 = (trem % p.tiles_w) * p.TW;
+                    const int n0 = nt * p.BN;
+                    for (int kb = 0; kb < p.num_k; ++kb) {
+                        mbar_wait(emptyA + 8u * stage, phase ^ 1u);
+                        const int tap = kb / cchunks;
+                        const int cc = kb - tap * cchunks;
+                        const int r = tap / p.ksize, s = tap - r * p.ksize;
+                        const uint32_t full = fullA + 8u * stage;
+                        mbar_expect_tx(full, tx);
+                        tma_load_4d(a_base + (uint32_t)stage * p.a_bytes, &tmA, full, cc * p.BK, ow0 * p.stride + s - p.pad,
+                                    oh0 * p.stride + r - p.pad, img);
+                        tma_load_2d(b_base + (uint32_t)stage * p.b_bytes, &tmB, full, tap * p.Cin + cc * p.BK, n0);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            } else {
+                int sa = 0, sb = 0;
+                uint32_t pa = 0, pb = 0;
+                bool first = true;
+                for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                    const int nt = t / m_tiles, mt = t - nt * m_tiles;
+                    const int img = mt / tiles_per_img;
+                    const int trem = mt - img * tiles_per_img;
+                    const int oh0 = (trem / p.tiles_w) * 16, ow0 = (trem % p.tiles_w) * 8;
+                    const int n0 = nt * p.BN;
+                    for (int cc = 0; cc < cchunks; ++cc) {
+                        for (int s = 0; s < 3; ++s) {
+                            mbar_wait(emptyA + 8u * sa, pa ^ 1u);
+                            mbar_expect_tx(fullA + 8u * sa, p.a_bytes);
+                            tma_load_4d(a_base + (uint32_t)sa * p.a_bytes, &tmA, fullA + 8u * sa, cc * 64, ow0 + s - 1, oh0 - 1, img);
+                            if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
+                            if (p.b_resident && !first) continue;  // weights already in shared memory
+                            for (int r = 0; r < 3; ++r) {
+                                const int slot = p.b_resident ? (cc * 9 + s * 3 + r) : sb;
+                                if (!p.b_resident) mbar_wait(emptyB + 8u * slot, pb ^ 1u);
+                                mbar_expect_tx(fullB + 8u * slot, p.b_bytes);
+                                tma_load_2d(b_base + (uint32_t)slot * p.b_bytes, &tmB, fullB + 8u * slot, (r * 3 + s) * p.Cin + cc * 64, n0);
+                                if (!p.b_resident && ++sb == p.b_stages) { sb = 0; pb ^= 1u; }
+                            }
+                        }
+                    }
+                    first = false;
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0;
-            const int ksteps = p.BK / 16;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                mbar_wait(tempty_bar + 8u * acc, acc_phase ^ 1u);  // epilogue has drained this accumulator
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_acc + (uint32_t)(acc * p.BN);
-                for (int kb = 0; kb < p.num_k; ++kb) {
-                    mbar_wait(bar_base + 8u * stage, phase);
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            if (!HALO) {
+                int stage = 0;
+                uint32_t phase = 0;
+                const int ksteps = p.BK / 16;
+                for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                    mbar_wait(tempty_bar + 8u * acc, acc_phase ^ 1u);  // epilogue has drained this accumulator
                     tc_fence_after();
-                    const uint32_t a_addr = a_base + (uint32_t)stage * p.a_bytes;
-                    const uint32_t b_addr = b_base + (uint32_t)stage * p.b_bytes;
-                    for (int k = 0; k < ksteps; ++k) {
-                        // descriptor: start address (>>4) advanced by 32 B per UMMA_K inside the swizzle row; LBO = 1
-                        const uint64_t adesc = ((uint64_t)p.desc_hi << 32) | (uint64_t)(((a_addr + 32u * k) >> 4) & 0x3FFFu) | (1ull << 16);
-                        const uint64_t bdesc = ((uint64_t)p.desc_hi << 32) | (uint64_t)(((b_addr + 32u * k) >> 4) & 0x3FFFu) | (1ull << 16);
-                        tc_mma_bf16(d_tmem, adesc, bdesc, p.idesc, (uint32_t)((kb | k) != 0));
+                    const uint32_t d_tmem = tmem_acc + (uint32_t)(acc * p.BN);
+                    for (int kb = 0; kb < p.num_k; ++kb) {
+                        mbar_wait(fullA + 8u * stage, phase);
+                        tc_fence_after();
+                        const uint32_t a_addr = a_base + (uint32_t)stage * p.a_bytes;
+                        const uint32_t b_addr = b_base + (uint32_t)stage * p.b_bytes;
+                        for (int k = 0; k < ksteps; ++k) {
+                            // descriptor: start address (>>4) advanced by 32 B per UMMA_K inside the swizzle row; LBO = 1
+                            const uint64_t adesc = ((uint64_t)p.desc_hi << 32) | (uint64_t)(((a_addr + 32u * k) >> 4) & 0x3FFFu) | (1ull << 16);
+                            const uint64_t bdesc = ((uint64_t)p.desc_hi << 32) | (uint64_t)(((b_addr + 32u * k) >> 4) & 0x3FFFu) | (1ull << 16);
+                            tc_mma_bf16(d_tmem, adesc, bdesc, p.idesc, (uint32_t)((kb | k) != 0));
+                        }
+                        tc_commit(emptyA + 8u * stage);  // frees the smem slot when these MMAs retire
+                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                     }
-                    tc_commit(bar_base + 8u * (p.stages + stage));  // frees the smem slot when these MMAs retire
-                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                    tc_commit(tfull_bar + 8u * acc);  // accumulator complete
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1u;
                 }
-                tc_commit(tfull_bar + 8u * acc);  // accumulator complete
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1u;
+            } else {
+                int sa = 0, sb = 0;
+                uint32_t pa = 0, pb = 0;
+                for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                    mbar_wait(tempty_bar + 8u * acc, acc_phase ^ 1u);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_acc + (uint32_t)(acc * p.BN);
+                    uint32_t started = 0;
+                    for (int cc = 0; cc < p.cchunks; ++cc) {
+                        for (int s = 0; s < 3; ++s) {
+                            mbar_wait(fullA + 8u * sa, pa);
+                            const uint32_t a_copy = a_base + (uint32_t)sa * p.a_bytes;
+                            for (int r = 0; r < 3; ++r) {
+                                const int slot = p.b_resident ? (cc * 9 + s * 3 + r) : sb;
+                                mbar_wait(fullB + 8u * slot, p.b_resident ? 0u : pb);
+                                tc_fence_after();
+                                const uint32_t a_addr = a_copy + 1024u * r;  // filter row r = +8 halo rows = one swizzle atom
+                                const uint32_t b_addr = b_base + (uint32_t)slot * p.b_bytes;
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const uint64_t adesc = ((uint64_t)p.desc_hi << 32) | (uint64_t)(((a_addr + 32u * k) >> 4) & 0x3FFFu) | (1ull << 16);
+                                    const uint64_t bdesc = ((uint64_t)p.desc_hi << 32) | (uint64_t)(((b_addr + 32u * k) >> 4) & 0x3FFFu) | (1ull << 16);
+                                    tc_mma_bf16(d_tmem, adesc, bdesc, p.idesc, started);
+                                    started = 1;
+                                }
+                                if (!p.b_resident) {
+                                    tc_commit(emptyB + 8u * slot);
+                                    if (++sb == p.b_stages) { sb = 0; pb ^= 1u; }
+                                }
+                            }
+                            tc_commit(emptyA + 8u * sa);
+                            if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
+                        }
+                    }
+                    tc_commit(tfull_bar + 8u * acc);
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1u;
+                }
             }
         }
     } else {
@@ -381,6 +469,7 @@ EncodeTiledFn get_encode() {
 }
 
 struct ConvTc {
+    bool halo;
     CUtensorMap tmA, tmB, tmO;
     TcParams p;
     dim3 grid;
@@ -400,9 +489,10 @@ extern "C" {
 //   out    : NHWC view, pixel stride ocs elements; out_dtype YSOD_BF16 or YSOD_F32
 //   res    : optional NHWC bf16 residual added AFTER the activation (Bottleneck / transformer skip), stride rcs
 // ksize in {1,3}, stride in {1,2} (pad = ksize/2, conv.py:28 autopad), groups == 1, Cin % 32 == 0.
-int ysod_conv_tc_create(ysod_conv_tc** handle, const void* x, int N, int H, int W, int Cin, int xcs, const void* wgt,
-                        const float* bias, int Cout, int Cout_pad, int ksize, int stride, void* out, int out_dtype, int ocs,
-                        const void* res, int rcs, int act) {
+// mode: 0 = auto, 1 = generic per-tap kernel, 2 = force the 3x3 halo-reuse kernel (error if the shape does not qualify).
+int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, int W, int Cin, int xcs, const void* wgt,
+                           const float* bias, int Cout, int Cout_pad, int ksize, int stride, void* out, int out_dtype, int ocs,
+                           const void* res, int rcs, int act, int mode) {
     YSOD_CHECK_ARG(handle && x && wgt && bias && out, "ysod_conv_tc_create: null pointer");
     YSOD_CHECK_ARG(ksize == 1 || ksize == 3, "ysod_conv_tc_create: ksize %d unsupported", ksize);
     YSOD_CHECK_ARG(stride == 1 || stride == 2, "ysod_conv_tc_create: stride %d unsupported", stride);
@@ -436,6 +526,14 @@ int ysod_conv_tc_create(ysod_conv_tc** handle, const void* x, int N, int H, int 
         const double util = (double)Ho * Wo / ((double)tiles * 128.0);
         if (util > best + 1e-9 || (util > best - 1e-9 && tw > bestTW && tw <= 32)) { best = util; bestTW = tw; bestTH = th; }
     }
+    // 3x3 / stride-1 halo-reuse specialisation: fixed 16 x 8 output tile; worth it when that tiling wastes < 25 % of M
+    bool halo = false;
+    if (ksize == 3 && stride == 1 && Cin % 64 == 0) {
+        const double hutil = (double)Ho * Wo / ((double)ysod_cdiv(Ho, 16) * ysod_cdiv(Wo, 8) * 128.0);
+        halo = (mode == 2) || (mode == 0 && hutil >= 0.75);
+    }
+    YSOD_CHECK_ARG(mode != 2 || halo, "ysod_conv_tc_create_ex: shape does not qualify for the halo kernel");
+    if (halo) { bestTH = 16; bestTW = 8; }
     p.N = N; p.Ho = Ho; p.Wo = Wo; p.TH = bestTH; p.TW = bestTW;
     p.tiles_h = ysod_cdiv(Ho, bestTH); p.tiles_w = ysod_cdiv(Wo, bestTW);
     p.Cin = Cin; p.ksize = ksize; p.stride = stride; p.pad = pad;
@@ -461,13 +559,39 @@ int ysod_conv_tc_create(ysod_conv_tc** handle, const void* x, int N, int H, int 
     const uint32_t sbo = (p.BK == 64 ? 1024u : 512u) >> 4;
     const uint32_t layout = (p.BK == 64) ? 2u : 4u;  // SWIZZLE_128B : SWIZZLE_64B
     p.desc_hi = sbo | (1u << 14) | (layout << 29);
-    const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+    p.cchunks = Cin / p.BK;
     const uint32_t fixed = 2u * 16384u + 4u * (uint32_t)Cout_pad + 3u * 1024u;   // staging + bias + slack
-    uint32_t budget = (3u * stage_bytes + fixed <= 112u * 1024u) ? 112u * 1024u - fixed : 224u * 1024u - fixed;
-    int stages = (int)(budget / stage_bytes);
-    if (stages > 8) stages = 8;   // persistent kernel: the ring streams across tiles, so depth is not capped by num_k
-    if (stages < 2) stages = 2;
-    p.stages = stages;
+    size_t ring_bytes = 0;
+    int nbar = 0;
+    if (!halo) {
+        const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
+        uint32_t budget = (3u * stage_bytes + fixed <= 112u * 1024u) ? 112u * 1024u - fixed : 224u * 1024u - fixed;
+        int stages = (int)(budget / stage_bytes);
+        if (stages > 8) stages = 8;   // persistent kernel: the ring streams across tiles, so depth is not capped by num_k
+        if (stages < 2) stages = 2;
+        p.stages = p.a_stages = p.b_stages = stages;
+        ring_bytes = (size_t)stages * stage_bytes;
+        nbar = 4 * stages;
+    } else {
+        p.a_bytes = 18u * 8u * 128u;   // one column-shifted halo copy: 18 rows x 8 px x 64 ch bf16
+        p.a_tx = p.a_bytes;
+        const uint32_t avail = 224u * 1024u - fixed;
+        const uint32_t b_all = 9u * (uint32_t)p.cchunks * p.b_bytes;
+        if (b_all + 4u * p.a_bytes <= avail) {   // all weight taps stay resident; >= 4 halo copies in flight
+            p.b_resident = 1;
+            p.b_stages = 9 * p.cchunks;
+            p.a_stages = (int)((avail - b_all) / p.a_bytes);
+        } else {
+            p.b_resident = 0;
+            p.b_stages = 4;
+            p.a_stages = (int)((avail - 4u * p.b_bytes) / p.a_bytes);
+        }
+        if (p.a_stages > 6) p.a_stages = 6;
+        YSOD_CHECK_ARG(p.a_stages >= 3, "ysod_conv_tc_create: halo plan does not fit in shared memory (BN %d)", BN);
+        p.stages = p.a_stages;
+        ring_bytes = (size_t)p.a_stages * p.a_bytes + (size_t)p.b_stages * p.b_bytes;
+        nbar = 2 * p.a_stages + 2 * p.b_stages;
+    }
     {
         const uint32_t es = p.out_f32 ? 4u : 2u;
         uint32_t rb = 32;
@@ -479,7 +603,8 @@ int ysod_conv_tc_create(ysod_conv_tc** handle, const void* x, int N, int H, int 
         p.cout_pad = Cout_pad;
     }
     // ring + 1 KB alignment slack + barriers/slot + bias + alignment + two 16 KB output staging buffers
-    c.smem = (size_t)stages * stage_bytes + 1024 + (16 * stages + 64) + 4 * (size_t)Cout_pad + 1024 + 2 * 16384;
+    c.smem = ring_bytes + 1024 + (8 * (size_t)nbar + 64) + 4 * (size_t)Cout_pad + 1024 + 2 * 16384;
+    c.halo = halo;
     {
         int dev = 0, sms = 148;
         YSOD_CUDA(cudaGetDevice(&dev));
@@ -500,6 +625,7 @@ int ysod_conv_tc_create(ysod_conv_tc** handle, const void* x, int N, int H, int 
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
         cuuint64_t strides[3] = {(cuuint64_t)xcs * 2, (cuuint64_t)W * xcs * 2, (cuuint64_t)H * W * xcs * 2};
         cuuint32_t box[4] = {(cuuint32_t)p.BK, (cuuint32_t)(bestTW * stride), (cuuint32_t)(bestTH * stride), 1};
+        if (halo) { box[1] = 8; box[2] = 18; }   // one column-shifted halo copy (rows oh0-1 .. oh0+16)
         cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
         CUresult r = enc(&c.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -541,7 +667,8 @@ int ysod_conv_tc_create(ysod_conv_tc** handle, const void* x, int N, int H, int 
     }
     YSOD_CHECK_ARG(!res || Cout % 16 == 0, "ysod_conv_tc_create: residual needs Cout %% 16 == 0");
     YSOD_CHECK_ARG(c.smem <= 227 * 1024, "ysod_conv_tc_create: shared memory plan too large (%zu)", c.smem);
-    YSOD_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    YSOD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    YSOD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     ysod_conv_tc* h = new (std::nothrow) ysod_conv_tc;
     YSOD_CHECK_ARG(h, "ysod_conv_tc_create: out of memory");
     h->c = c;
@@ -549,9 +676,17 @@ int ysod_conv_tc_create(ysod_conv_tc** handle, const void* x, int N, int H, int 
     return YSOD_OK;
 }
 
+int ysod_conv_tc_create(ysod_conv_tc** handle, const void* x, int N, int H, int W, int Cin, int xcs, const void* wgt,
+                        const float* bias, int Cout, int Cout_pad, int ksize, int stride, void* out, int out_dtype, int ocs,
+                        const void* res, int rcs, int act) {
+    return ysod_conv_tc_create_ex(handle, x, N, H, W, Cin, xcs, wgt, bias, Cout, Cout_pad, ksize, stride, out, out_dtype, ocs, res, rcs,
+                                  act, 0);
+}
+
 int ysod_conv_tc_run(ysod_conv_tc* h, cudaStream_t stream) {
     YSOD_CHECK_ARG(h, "ysod_conv_tc_run: null handle");
-    conv_tc_kernel<<<h->c.grid, TC_THREADS, h->c.smem, stream>>>(h->c.tmA, h->c.tmB, h->c.tmO, h->c.p);
+    if (h->c.halo) conv_tc_kernel<true><<<h->c.grid, TC_THREADS, h->c.smem, stream>>>(h->c.tmA, h->c.tmB, h->c.tmO, h->c.p);
+    else conv_tc_kernel<false><<<h->c.grid, TC_THREADS, h->c.smem, stream>>>(h->c.tmA, h->c.tmB, h->c.tmO, h->c.p);
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }
@@ -560,7 +695,8 @@ int ysod_conv_tc_run(ysod_conv_tc* h, cudaStream_t stream) {
 int ysod_conv_tc_info(ysod_conv_tc* h, int* out8) {
     YSOD_CHECK_ARG(h && out8, "ysod_conv_tc_info: null");
     out8[0] = h->c.p.TH; out8[1] = h->c.p.TW; out8[2] = h->c.p.BN; out8[3] = h->c.p.BK; out8[4] = h->c.p.stages;
-    out8[5] = (int)h->c.grid.x; out8[6] = h->c.p.n_tiles; out8[7] = (int)h->c.smem;
+    out8[5] = (int)h->c.grid.x; out8[6] = h->c.halo ? (100 + 10 * h->c.p.b_resident + h->c.p.b_stages % 10) : h->c.p.n_tiles;
+    out8[7] = (int)h->c.smem;
     return YSOD_OK;
 }
 
