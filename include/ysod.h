@@ -54,6 +54,8 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
 int ysod_conv_tc_run(ysod_conv_tc* handle, void* stream);
 int ysod_conv_tc_info(ysod_conv_tc* handle, int* out8);
 void ysod_conv_tc_destroy(ysod_conv_tc* handle);
+/* profiling aid (not part of the drop-in surface): pipeline trace of the last launch created with mode = 32 << 8 */
+int ysod_debug_trace(unsigned long long* out, int cap);
 
 /* ---- CUDA-core convs: stem (Cin=3, NCHW fp32 image in), depthwise, grouped, and the fp32 parity mode ---------------- */
 int ysod_conv_direct(const void* x, int dtype, int N, int H, int W, int Cin, int xcs, const void* w, const float* bias,

@@ -1,6 +1,6 @@
 """Runs one tcgen05 conv shape a few times (for `ncu --set full -k regex:conv_tc_kernel`) and prints its event timing.
 
-    python tools/prof_conv.py <N> <H> <W> <Cin> <Cout> <k> <s> [iters]
+    python tools/prof_conv.py <N> <H> <W> <Cin> <Cout> <k> <s> [iters] [mode] [act]
 """
 import ctypes as C
 import os
@@ -15,6 +15,7 @@ from yolo_sod_b200 import lib  # noqa: E402
 N, H, W, Cin, Cout, k, s = [int(v) for v in sys.argv[1:8]]
 iters = int(sys.argv[8]) if len(sys.argv) > 8 else 5
 mode = int(sys.argv[9]) if len(sys.argv) > 9 else 0
+act = sys.argv[10] if len(sys.argv) > 10 else "silu"
 pad = k // 2
 Ho, Wo = (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1
 x = torch.randn(N, H, W, Cin, device="cuda").bfloat16()
@@ -24,7 +25,7 @@ b = torch.zeros(cpad, device="cuda")
 o = torch.empty(N, Ho, Wo, Cout, device="cuda", dtype=torch.bfloat16)
 h = C.c_void_p()
 lib.call("ysod_conv_tc_create_ex", C.byref(h), lib.ptr(x), N, H, W, Cin, Cin, lib.ptr(w), lib.ptr(b), Cout, cpad, k, s, lib.ptr(o), lib.BF16,
-         Cout, None, 0, lib.ACT["silu"], mode)
+         Cout, None, 0, lib.ACT[act], mode)
 info = (C.c_int * 8)()
 lib.call("ysod_conv_tc_info", h, info)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")

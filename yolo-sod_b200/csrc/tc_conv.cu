@@ -30,7 +30,11 @@ struct TcParams {
     int N, Ho, Wo, TH, TW, tiles_h, tiles_w;
     int Cin, ksize, stride, pad;
     int BN, BK, stages, tmem_cols, num_k, n_tiles;
-    int a_stages, b_stages, b_resident, cchunks;   // halo mode (3x3/s1): separate A (halo copies) and B (weight taps) rings
+    int step_tw, step_th, step_img, step_nt;   // gridDim.x decomposed in the mixed radix (tiles_w, tiles_h, N): per-tile coordinate update without divisions
+    int kgroup;      // generic mode: K blocks (slots) per pipeline stage = per mbarrier handshake / per elected issue burst
+    int sgroup;      // halo mode: filter columns (A copies) per issue burst (3 when the weights are resident, else 1)
+    int a_stages, b_stages, b_resident, cchunks;   // stages per sub-ring
+    int a_slots, b_slots;                          // total smem slots / barrier pairs carved for A and B   // halo mode (3x3/s1): separate A (halo copies) and B (weight taps) rings
     int Cout;
     void* out;
     int out_f32;
@@ -43,8 +47,10 @@ struct TcParams {
     uint32_t desc_hi;  // SBO | version | layout type (upper 32 bits of the smem descriptor)
     uint32_t a_bytes, b_bytes, a_tx;
     // epilogue staging: output rows of `row_bytes` (<= 128 B, one swizzle span) per store unit of `unit_cols` columns
-    int unit_cols, n_units, swz_mask, cout_pad;
+    int unit_cols, n_units, swz_mask, cout_pad, stage_bufs;
     uint32_t row_bytes;
+    int debug;  // profiling only (mode >> 8): 1 = epilogue drains without work, 2 = producer skips TMA, 4 = MMA issuer skips tcgen05.mma,
+                // 8 = epilogue skips the TMA store, 16 = epilogue skips the activation
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
@@ -56,20 +62,24 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: a waiting warp sleeps in hardware until the phase completes instead of spinning in the
+// issue slots. (The SMSP arbiter favours higher warp ids, so a spinning epilogue warp starves a lower-numbered issuer warp.)
 __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
-        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        "}" : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
     return ok;
 }
-// Bounded wait: a protocol bug (wrong tx count, bad descriptor) traps after ~seconds instead of hanging the GPU.
+// Bounded wait: a protocol bug (wrong tx count, bad descriptor) traps after ~2 s instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    for (uint32_t spins = 0; !mbar_try(bar, parity); ++spins) {
-        if (spins > (1u << 24)) __trap();
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
     }
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
@@ -90,7 +100,7 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_barrier(int grp) { asm volatile("bar.sync %0, 256;" ::"r"(grp + 1) : "memory"); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -132,11 +142,51 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t* v) {
                  : "memory");
 }
 
-constexpr int TC_THREADS = 192;
+// Profiling aid (debug bit 32): CTA 0 logs clock64() at pipeline events of its tiles; read back with ysod_debug_trace().
+// Record = (role << 56 | event << 48 | tile << 32 | index) , clock.  roles: 0 producer, 1 MMA issuer 0, 2 epilogue (warp 0
+// lane 0), 3 MMA issuer 1. Each role appends to its own quarter of the buffer with a private counter (no atomics: a trace
+// point is one clock read + one fire-and-forget store).
+constexpr int TRACE_CAP = 8192;
+__device__ unsigned long long g_trace[2 * TRACE_CAP];
+__device__ __forceinline__ void trace(bool on, int role, int ev, int tile, int idx, unsigned int& cnt) {
+    if (on && cnt < TRACE_CAP / 4) {
+        const unsigned int i = role * (TRACE_CAP / 4) + cnt++;
+        g_trace[2 * i] = ((unsigned long long)role << 56) | ((unsigned long long)ev << 48) | ((unsigned long long)tile << 32) | (unsigned int)idx;
+        g_trace[2 * i + 1] = clock64();
+    }
+}
+
+// One fat persistent CTA per SM: warps 0..15 epilogue, warp 16 TMA producer, warps 17 and 18 MMA issuers.
+//  * 16 epilogue warps = 4 per SMSP: enough warps to hide TMEM-load / MUFU / shared-store latency. Warp w owns TMEM lane
+//    quarter w % 4 (a hardware rule) and the 16-column chunks  w / 4, w / 4 + 4, ...  of the accumulator.
+//  * two issuers ping-pong over the CTA's tiles (issuer i takes every second tile and always accumulator i): a
+//    tcgen05.mma burst blocks its issuing thread at tensor-pipe rate (the hardware queue is shallow), so with a single
+//    issuer the barrier handshakes between bursts (~1000+ cycles, measured) leave the tensor pipe idle.
+//  * the issuer/producer warps carry the highest warp ids of their SMSPs, which the hi-wid-first arbiter favours.
+constexpr int EPI_WARPS = 16;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
+constexpr int TC_THREADS = EPI_THREADS + 96;
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// One elected lane of a converged warp. Unlike `lane == 0`, the compiler knows the branch holds exactly one thread, so
+// tcgen05.mma / tcgen05.commit / TMA (which take uniform-register operands) are emitted straight, without a per-lane
+// ELECT + BRA.U.ANY serialisation loop around every instruction (that loop cost ~150 cycles per MMA).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t desc_hi, uint32_t lo) { return ((uint64_t)desc_hi << 32) | (uint64_t)lo; }
+// low word of the smem descriptor: start address >> 4 (14 bits) | LBO = 1 (ignored for swizzled K-major) @16
+__device__ __forceinline__ uint32_t umma_lo(uint32_t addr) { return ((addr >> 4) & 0x3FFFu) | (1u << 16); }
 
 template <int ACT>
 __device__ __forceinline__ void act16(float* f) {
@@ -151,6 +201,26 @@ __device__ __forceinline__ void act16(float* f) {
     }
 }
 
+// Output-tile coordinates of a persistent CTA, advanced by gridDim.x tiles per step with carries instead of div/mod: a
+// single-thread role pays ~150-200 cycles per integer division (a dependent ~35-instruction chain), and four of them per
+// tile used to cost more than the tile's MMAs.
+struct TileIter {
+    int tw, th, img, nt;
+    __device__ __forceinline__ void init(int t, const TcParams& p) {
+        tw = t % p.tiles_w; t /= p.tiles_w;
+        th = t % p.tiles_h; t /= p.tiles_h;
+        img = t % p.N;
+        nt = t / p.N;
+    }
+    __device__ __forceinline__ void step(const TcParams& p) {
+        tw += p.step_tw; if (tw >= p.tiles_w) { tw -= p.tiles_w; ++th; }
+        th += p.step_th; if (th >= p.tiles_h) { th -= p.tiles_h; ++img; }
+        img += p.step_img; if (img >= p.N) { img -= p.N; ++nt; }
+        nt += p.step_nt;
+    }
+    __device__ __forceinline__ bool valid(const TcParams& p) const { return nt < p.n_tiles; }
+};
+
 // Persistent, warp-specialised: each CTA loops over output tiles (tile = blockIdx.x + i*gridDim.x). The smem ring keeps
 // streaming across tile boundaries and the accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue of
 // tile i overlaps the TMA/MMA main loop of tile i+1; barriers and TMEM are set up once per CTA.
@@ -162,54 +232,53 @@ __device__ __forceinline__ void act16(float* f) {
 // A traffic per tile drops from 9 x 16 KB to 3 x 18 KB; weight taps stream through their own ring, or stay resident in
 // shared memory for the whole CTA lifetime when they fit (64->64: 72 KB).
 template <bool HALO>
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
-    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem0 = smem_u32(smem_raw);
+    const uint32_t base = (smem0 + 1023u) & ~1023u;
     const uint32_t a_base = base;
-    const uint32_t b_base = base + (uint32_t)p.a_stages * p.a_bytes;
-    const uint32_t bar_base = b_base + (uint32_t)p.b_stages * p.b_bytes;  // 8-byte aligned (tiles are 1 KB multiples)
+    const int a_slots = p.a_slots, b_slots = p.b_slots;   // total ring slots (both sub-rings)
+    const uint32_t b_base = base + (uint32_t)a_slots * p.a_bytes;
+    const uint32_t bar_base = b_base + (uint32_t)b_slots * p.b_bytes;  // 8-byte aligned (tiles are 1 KB multiples)
     // fullA[i], emptyA[i] (i < a_stages), fullB[i], emptyB[i] (i < b_stages), then tfull[2], tempty[2], tmem slot.
     // Generic mode uses the A barriers for the combined {A,B} stage.
-    const uint32_t fullA = bar_base, emptyA = bar_base + 8u * p.a_stages;
-    const uint32_t fullB = bar_base + 16u * p.a_stages, emptyB = fullB + 8u * p.b_stages;
-    const uint32_t tfull_bar = fullB + 16u * p.b_stages;
+    const uint32_t fullA = bar_base, emptyA = bar_base + 8u * a_slots;
+    const uint32_t fullB = bar_base + 16u * a_slots, emptyB = fullB + 8u * b_slots;
+    const uint32_t tfull_bar = fullB + 16u * b_slots;
     const uint32_t tempty_bar = tfull_bar + 16u;
     const uint32_t tmem_slot = tempty_bar + 16u;
-    // after the barriers: bias[cout_pad] fp32, then two 16 KB (1 KB aligned) output staging buffers
+    // after the barriers: bias[cout_pad] fp32, then the (1 KB aligned) output staging: nbuf x n_units x 128 rows x row_bytes
     const uint32_t bias_smem = tmem_slot + 16u;
     const uint32_t stage_out = (bias_smem + 4u * (uint32_t)p.cout_pad + 1023u) & ~1023u;
+    float* const bias_s = reinterpret_cast<float*>(smem_raw + (bias_smem - smem0));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tiles_per_img = p.tiles_h * p.tiles_w;
-    const int m_tiles = p.N * tiles_per_img;
-    const int total_tiles = m_tiles * p.n_tiles;
+    const bool tr = (p.debug & 32) && blockIdx.x == 0;
+    unsigned int tcnt = 0;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.a_stages; ++s) {
+        for (int s = 0; s < a_slots; ++s) {
             mbar_init(fullA + 8u * s, 1);
             mbar_init(emptyA + 8u * s, 1);
         }
-        for (int s = 0; s < p.b_stages; ++s) {
+        for (int s = 0; s < b_slots; ++s) {
             mbar_init(fullB + 8u * s, 1);
             mbar_init(emptyB + 8u * s, 1);
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar + 8u * a, 1);
-            mbar_init(tempty_bar + 8u * a, 4);  // one arrive per epilogue warp
+            mbar_init(tempty_bar + 8u * a, EPI_WARPS / 2);  // one arrive per warp of the accumulator's epilogue group
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < p.cout_pad; i += 128) {
-            const float bv = __ldg(p.bias + i);
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_smem + 4u * i), "f"(bv) : "memory");
-        }
+    if (warp < EPI_WARPS) {
+        for (int i = threadIdx.x; i < p.cout_pad; i += EPI_THREADS) bias_s[i] = __ldg(p.bias + i);
     }
     tc_fence_before();
     __syncthreads();
@@ -217,237 +286,330 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t tmem_acc;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_acc) : "r"(tmem_slot) : "memory");
 
-    if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
+    if (warp == PRODUCER_WARP) {
+        // ===== TMA producer (one elected lane) =====
+        if (elect_one()) {
             const int cchunks = p.cchunks;
             if (!HALO) {
                 const uint32_t tx = p.a_tx + p.b_bytes;
-                int stage = 0;
-                uint32_t phase = 0;
-                for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                    const int nt = t / m_tiles, mt = t - nt * m_tiles;
-                    const int img = mt / tiles_per_img;
-                    const int trem = mt - img * tiles_per_img;
-                    const int oh0 = (trem / p.tiles_w) * p.TH, ow0 = (trem % p.tiles_w) * p.TW;
-                    const int n0 = nt * p.BN;
-                    for (int kb = 0; kb < p.num_k; ++kb) {
-                        mbar_wait(emptyA + 8u * stage, phase ^ 1u);
-                        const int tap = kb / cchunks;
-                        const int cc = kb - tap * cchunks;
-                        const int r = tap / p.ksize, s = tap - r * p.ksize;
+                const int nstages = p.stages, G = p.kgroup, ngroups = p.num_k / p.kgroup, BK = p.BK, ksize = p.ksize, cstride = p.stride, pad = p.pad, Cin = p.Cin;
+                // two sub-rings of `nstages` stages: even tiles (issuer 0) use stages [0, nstages), odd tiles [nstages, 2*nstages)
+                int st_c = 0, st_o = 0, base_c = 0, base_o = nstages;
+                uint32_t ph_c = 0, ph_o = 0;
+                TileIter ti;
+                ti.init(blockIdx.x, p);
+                for (int tcount = 0; ti.valid(p); ti.step(p), ++tcount) {
+                    const int img = ti.img;
+                    const int oh0 = ti.th * p.TH, ow0 = ti.tw * p.TW;
+                    const int n0 = ti.nt * p.BN;
+                    int tap = 0, cc = 0, r = 0, s = 0;
+                    for (int grp = 0; grp < ngroups; ++grp) {
+                        const int stage = base_c + st_c;
+                        mbar_wait(emptyA + 8u * stage, ph_c ^ 1u);
+                        trace(tr, 0, 1, tcount, grp, tcnt);
                         const uint32_t full = fullA + 8u * stage;
-                        mbar_expect_tx(full, tx);
-                        tma_load_4d(a_base + (uint32_t)stage * p.a_bytes, &tmA, full, cc * p.BK, ow0 * p.stride + s - p.pad,
-                                    oh0 * p.stride + r - p.pad, img);
-                        tma_load_2d(b_base + (uint32_t)stage * p.b_bytes, &tmB, full, tap * p.Cin + cc * p.BK, n0);
-                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                        if (p.debug & 2) mbar_arrive(full);
+                        else mbar_expect_tx(full, tx * (uint32_t)G);
+                        for (int g = 0; g < G; ++g) {
+                            const uint32_t slot = (uint32_t)(stage * G + g);
+                            if (!(p.debug & 2)) {
+                                tma_load_4d(a_base + slot * p.a_bytes, &tmA, full, cc * BK, ow0 * cstride + s - pad, oh0 * cstride + r - pad, img);
+                                tma_load_2d(b_base + slot * p.b_bytes, &tmB, full, tap * Cin + cc * BK, n0);
+                            }
+                            if (++cc == cchunks) {
+                                cc = 0; ++tap;
+                                if (++s == ksize) { s = 0; ++r; }
+                            }
+                        }
+                        if (++st_c == nstages) { st_c = 0; ph_c ^= 1u; }
                     }
+                    { int x = st_c; st_c = st_o; st_o = x; x = base_c; base_c = base_o; base_o = x; }
+                    { uint32_t x = ph_c; ph_c = ph_o; ph_o = x; }
                 }
             } else {
-                int sa = 0, sb = 0;
-                uint32_t pa = 0, pb = 0;
+                // sub-rings: even tiles use A slots [0, ah) and streamed-B slots [0, bh); odd tiles the second halves
+                const int ah = p.a_stages, bh = p.b_stages;
+                const bool b_res = p.b_resident != 0;
+                int sa_c = 0, sa_o = 0, sb_c = 0, sb_o = 0, abase_c = 0, abase_o = ah, bbase_c = 0, bbase_o = b_res ? 0 : bh;
+                uint32_t pa_c = 0, pa_o = 0, pb_c = 0, pb_o = 0;
                 bool first = true;
-                for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                    const int nt = t / m_tiles, mt = t - nt * m_tiles;
-                    const int img = mt / tiles_per_img;
-                    const int trem = mt - img * tiles_per_img;
-                    const int oh0 = (trem / p.tiles_w) * 16, ow0 = (trem % p.tiles_w) * 8;
-                    const int n0 = nt * p.BN;
+                TileIter ti;
+                ti.init(blockIdx.x, p);
+                for (int tcount = 0; ti.valid(p); ti.step(p), ++tcount) {
+                    const int img = ti.img;
+                    const int oh0 = ti.th * 16, ow0 = ti.tw * 8;
+                    const int n0 = ti.nt * p.BN;
                     for (int cc = 0; cc < cchunks; ++cc) {
                         for (int s = 0; s < 3; ++s) {
-                            mbar_wait(emptyA + 8u * sa, pa ^ 1u);
-                            mbar_expect_tx(fullA + 8u * sa, p.a_bytes);
-                            tma_load_4d(a_base + (uint32_t)sa * p.a_bytes, &tmA, fullA + 8u * sa, cc * 64, ow0 + s - 1, oh0 - 1, img);
-                            if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
-                            if (p.b_resident && !first) continue;  // weights already in shared memory
+                            const int aslot = abase_c + sa_c;
+                            mbar_wait(emptyA + 8u * aslot, pa_c ^ 1u);
+                            trace(tr, 0, 1, tcount, cc * 3 + s, tcnt);             // A slot free
+                            if (p.debug & 2) mbar_arrive(fullA + 8u * aslot);
+                            else {
+                                mbar_expect_tx(fullA + 8u * aslot, p.a_bytes);
+                                tma_load_4d(a_base + (uint32_t)aslot * p.a_bytes, &tmA, fullA + 8u * aslot, cc * 64, ow0 + s - 1, oh0 - 1, img);
+                            }
+                            if (++sa_c == ah) { sa_c = 0; pa_c ^= 1u; }
+                            if (b_res && !first) continue;  // weights already in shared memory
                             for (int r = 0; r < 3; ++r) {
-                                const int slot = p.b_resident ? (cc * 9 + s * 3 + r) : sb;
-                                if (!p.b_resident) mbar_wait(emptyB + 8u * slot, pb ^ 1u);
+                                const int slot = b_res ? (cc * 9 + s * 3 + r) : (bbase_c + sb_c);
+                                if (!b_res) mbar_wait(emptyB + 8u * slot, pb_c ^ 1u);
                                 mbar_expect_tx(fullB + 8u * slot, p.b_bytes);
                                 tma_load_2d(b_base + (uint32_t)slot * p.b_bytes, &tmB, fullB + 8u * slot, (r * 3 + s) * p.Cin + cc * 64, n0);
-                                if (!p.b_resident && ++sb == p.b_stages) { sb = 0; pb ^= 1u; }
+                                if (!b_res && ++sb_c == bh) { sb_c = 0; pb_c ^= 1u; }
                             }
                         }
                     }
                     first = false;
+                    { int x = sa_c; sa_c = sa_o; sa_o = x; x = sb_c; sb_c = sb_o; sb_o = x; x = abase_c; abase_c = abase_o; abase_o = x; x = bbase_c; bbase_c = bbase_o; bbase_o = x; }
+                    { uint32_t x = pa_c; pa_c = pa_o; pa_o = x; x = pb_c; pb_c = pb_o; pb_o = x; }
                 }
             }
         }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            if (!HALO) {
-                int stage = 0;
-                uint32_t phase = 0;
-                const int ksteps = p.BK / 16;
-                for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                    mbar_wait(tempty_bar + 8u * acc, acc_phase ^ 1u);  // epilogue has drained this accumulator
+    } else if (warp == MMA_WARP || warp == MMA_WARP + 1) {
+        // ===== MMA issuers: the whole warp walks the pipeline (converged), one elected lane issues. Issuer `me` owns the
+        //       CTA's tiles me, me + 2, ... and TMEM accumulator `me`; ring positions follow from the tile counter. =====
+        const int me = warp - MMA_WARP;
+        const int trole = me ? 3 : 1;
+        const uint32_t idesc = p.idesc, desc_hi = p.desc_hi;
+        const uint32_t a_bytes = p.a_bytes, b_bytes = p.b_bytes;
+        const bool no_mma = (p.debug & 4) != 0;
+        const uint32_t d_tmem = tmem_acc + (uint32_t)(me * p.BN);
+        const uint32_t my_tfull = tfull_bar + 8u * me, my_tempty = tempty_bar + 8u * me;
+        uint32_t acc_phase = 0;
+        if (!HALO) {
+            const int nstages = p.stages, G = p.kgroup, ngroups = p.num_k / p.kgroup;
+            const bool k4 = (p.BK == 64);
+            int st = 0;
+            uint32_t phase = 0;
+            const int sbase = me * nstages;   // this issuer's sub-ring
+            TileIter ti;
+            ti.init(blockIdx.x, p);
+            if (me) ti.step(p);
+            for (int tcount = me; ti.valid(p); ti.step(p), ti.step(p), tcount += 2) {
+                mbar_wait(my_tempty, acc_phase ^ 1u);  // epilogue has drained this accumulator
+                trace(tr && lane == 0, trole, 1, tcount, 0, tcnt);
+                tc_fence_after();
+                for (int grp = 0; grp < ngroups; ++grp) {
+                    const int stage = sbase + st;
+                    mbar_wait(fullA + 8u * stage, phase);
+                    trace(tr && lane == 0, trole, 2, tcount, grp, tcnt);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_acc + (uint32_t)(acc * p.BN);
-                    for (int kb = 0; kb < p.num_k; ++kb) {
-                        mbar_wait(fullA + 8u * stage, phase);
-                        tc_fence_after();
-                        const uint32_t a_addr = a_base + (uint32_t)stage * p.a_bytes;
-                        const uint32_t b_addr = b_base + (uint32_t)stage * p.b_bytes;
-                        for (int k = 0; k < ksteps; ++k) {
-                            // descriptor: start address (>>4) advanced by 32 B per UMMA_K inside the swizzle row; LBO = 1
-                            const uint64_t adesc = ((uint64_t)p.desc_hi << 32) | (uint64_t)(((a_addr + 32u * k) >> 4) & 0x3FFFu) | (1ull << 16);
-                            const uint64_t bdesc = ((uint64_t)p.desc_hi << 32) | (uint64_t)(((b_addr + 32u * k) >> 4) & 0x3FFFu) | (1ull << 16);
-                            tc_mma_bf16(d_tmem, adesc, bdesc, p.idesc, (uint32_t)((kb | k) != 0));
-                        }
-                        tc_commit(emptyA + 8u * stage);  // frees the smem slot when these MMAs retire
-                        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
-                    }
-                    tc_commit(tfull_bar + 8u * acc);  // accumulator complete
-                    acc ^= 1;
-                    if (acc == 0) acc_phase ^= 1u;
-                }
-            } else {
-                int sa = 0, sb = 0;
-                uint32_t pa = 0, pb = 0;
-                for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                    mbar_wait(tempty_bar + 8u * acc, acc_phase ^ 1u);
-                    tc_fence_after();
-                    const uint32_t d_tmem = tmem_acc + (uint32_t)(acc * p.BN);
-                    uint32_t started = 0;
-                    for (int cc = 0; cc < p.cchunks; ++cc) {
-                        for (int s = 0; s < 3; ++s) {
-                            mbar_wait(fullA + 8u * sa, pa);
-                            const uint32_t a_copy = a_base + (uint32_t)sa * p.a_bytes;
-                            for (int r = 0; r < 3; ++r) {
-                                const int slot = p.b_resident ? (cc * 9 + s * 3 + r) : sb;
-                                mbar_wait(fullB + 8u * slot, p.b_resident ? 0u : pb);
-                                tc_fence_after();
-                                const uint32_t a_addr = a_copy + 1024u * r;  // filter row r = +8 halo rows = one swizzle atom
-                                const uint32_t b_addr = b_base + (uint32_t)slot * p.b_bytes;
-#pragma unroll
-                                for (int k = 0; k < 4; ++k) {
-                                    const uint64_t adesc = ((uint64_t)p.desc_hi << 32) | (uint64_t)(((a_addr + 32u * k) >> 4) & 0x3FFFu) | (1ull << 16);
-                                    const uint64_t bdesc = ((uint64_t)p.desc_hi << 32) | (uint64_t)(((b_addr + 32u * k) >> 4) & 0x3FFFu) | (1ull << 16);
-                                    tc_mma_bf16(d_tmem, adesc, bdesc, p.idesc, started);
-                                    started = 1;
+                    if (elect_one()) {
+                        // one burst = G K-blocks; descriptor start address advances by 32 B (>>4 = 2) per UMMA_K = 16
+                        uint32_t a_lo = umma_lo(a_base + (uint32_t)(stage * G) * a_bytes);
+                        uint32_t b_lo = umma_lo(b_base + (uint32_t)(stage * G) * b_bytes);
+                        const uint32_t a_step = a_bytes >> 4, b_step = b_bytes >> 4;
+                        if (!no_mma) {
+                            for (int g = 0; g < G; ++g) {
+                                tc_mma_bf16(d_tmem, umma_desc(desc_hi, a_lo), umma_desc(desc_hi, b_lo), idesc, (uint32_t)((grp | g) != 0));
+                                tc_mma_bf16(d_tmem, umma_desc(desc_hi, a_lo + 2u), umma_desc(desc_hi, b_lo + 2u), idesc, 1u);
+                                if (k4) {
+                                    tc_mma_bf16(d_tmem, umma_desc(desc_hi, a_lo + 4u), umma_desc(desc_hi, b_lo + 4u), idesc, 1u);
+                                    tc_mma_bf16(d_tmem, umma_desc(desc_hi, a_lo + 6u), umma_desc(desc_hi, b_lo + 6u), idesc, 1u);
                                 }
-                                if (!p.b_resident) {
-                                    tc_commit(emptyB + 8u * slot);
-                                    if (++sb == p.b_stages) { sb = 0; pb ^= 1u; }
+                                a_lo += a_step;
+                                b_lo += b_step;
+                            }
+                        }
+                        tc_commit(emptyA + 8u * stage);  // frees the smem slots when these MMAs retire
+                        if (grp == ngroups - 1) tc_commit(my_tfull);  // accumulator complete
+                        trace(tr, trole, 3, tcount, grp, tcnt);
+                    }
+                    __syncwarp();
+                    if (++st == nstages) { st = 0; phase ^= 1u; }
+                }
+                acc_phase ^= 1u;
+            }
+        } else {
+            const int a_stages = p.a_stages, b_stages = p.b_stages, cchunks = p.cchunks, SG = p.sgroup;
+            const bool b_res = p.b_resident != 0;
+            bool first = true;
+            int sa = 0, sb = 0;          // positions inside this issuer's sub-rings
+            uint32_t pa = 0, pb = 0;
+            const int abase = me * a_stages, bbase = b_res ? 0 : me * b_stages;
+            TileIter ti;
+            ti.init(blockIdx.x, p);
+            if (me) ti.step(p);
+            for (int tcount = me; ti.valid(p); ti.step(p), ti.step(p), tcount += 2) {
+                mbar_wait(my_tempty, acc_phase ^ 1u);
+                trace(tr && lane == 0, trole, 1, tcount, 0, tcnt);                     // accumulator free
+                tc_fence_after();
+                for (int cc = 0; cc < cchunks; ++cc) {
+                    for (int s0 = 0; s0 < 3; s0 += SG) {
+                        // a_stages % SG == 0, so the SG halo copies of a burst are consecutive ring slots of one phase
+                        for (int j = 0; j < SG; ++j) mbar_wait(fullA + 8u * (abase + sa + j), pa);
+                        if (b_res) {
+                            if (first) {  // resident weights land once, during the CTA's first tile
+                                for (int j = 0; j < 3 * SG; ++j) mbar_wait(fullB + 8u * (cc * 9 + s0 * 3 + j), 0u);
+                            }
+                        } else {
+                            // the three weight taps of this filter column occupy consecutive ring slots (b_stages % 3 == 0)
+#pragma unroll
+                            for (int r = 0; r < 3; ++r) mbar_wait(fullB + 8u * (bbase + sb + r), pb);
+                        }
+                        tc_fence_after();
+                        trace(tr && lane == 0, trole, 2, tcount, cc * 3 + s0, tcnt);   // operands landed
+                        if (elect_one()) {
+                            if (!no_mma) {
+                                for (int j = 0; j < SG; ++j) {
+                                    const uint32_t a_lo0 = umma_lo(a_base + (uint32_t)(abase + sa + j) * a_bytes);
+                                    const uint32_t slot0 = b_res ? (uint32_t)(cc * 9 + (s0 + j) * 3) : (uint32_t)(bbase + sb);
+#pragma unroll
+                                    for (int r = 0; r < 3; ++r) {
+                                        const uint32_t a_lo = a_lo0 + 64u * r;  // filter row r = +8 halo rows = one 1024 B swizzle atom
+                                        const uint32_t b_lo = umma_lo(b_base + (slot0 + r) * b_bytes);
+#pragma unroll
+                                        for (int k = 0; k < 4; ++k)
+                                            tc_mma_bf16(d_tmem, umma_desc(desc_hi, a_lo + 2u * k), umma_desc(desc_hi, b_lo + 2u * k), idesc,
+                                                        (uint32_t)((cc | s0 | j | r | k) != 0));
+                                    }
                                 }
                             }
-                            tc_commit(emptyA + 8u * sa);
-                            if (++sa == p.a_stages) { sa = 0; pa ^= 1u; }
+                            if (!b_res) {
+#pragma unroll
+                                for (int r = 0; r < 3; ++r) tc_commit(emptyB + 8u * (bbase + sb + r));
+                            }
+                            for (int j = 0; j < SG; ++j) tc_commit(emptyA + 8u * (abase + sa + j));
+                            if (cc == cchunks - 1 && s0 + SG == 3) tc_commit(my_tfull);
+                            trace(tr, trole, 3, tcount, cc * 3 + s0, tcnt);           // burst issued + committed
                         }
+                        __syncwarp();
+                        if (!b_res) { sb += 3; if (sb == b_stages) { sb = 0; pb ^= 1u; } }
+                        sa += SG;
+                        if (sa == a_stages) { sa = 0; pa ^= 1u; }
                     }
-                    tc_commit(tfull_bar + 8u * acc);
-                    acc ^= 1;
-                    if (acc == 0) acc_phase ^= 1u;
                 }
+                first = false;
+                acc_phase ^= 1u;
             }
         }
     } else {
-        // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4 =====
-        // TMEM -> registers -> (+bias, act, +residual) -> 128B/64B/32B-swizzled shared-memory rows -> one TMA tensor store per
-        // unit of <= 128 B of channels. TMA clips ragged tiles and the Cout padding, and writes whole lines to L2.
+        // ===== epilogue (warps 0..15) = two groups of 8 warps; group g owns the CTA's tiles g, g + 2, ..., TMEM accumulator g
+        //       and staging buffer g, so one group's per-tile bookkeeping / barriers / store issue overlap the other's math.
+        //       Inside a group: TMEM lane quarter = warp % 4 (hardware rule), 16-column chunks  (warp%8)/4, +2, +4 ... =====
+        // Per tile: TMEM -> registers -> (+bias, act, +residual) -> swizzled shared-memory rows of the whole BN-wide tile
+        // (n_units sub-buffers of <= 128 B rows) -> ONE named barrier -> n_units TMA tensor stores. TMA clips ragged tiles
+        // and the Cout padding, and writes whole lines to L2.
+        const int grp = warp >> 3;
         const int q = warp & 3;
+        const int cg = (warp & 7) >> 2;
         const int m = q * 32 + lane;
-        const int th = m / p.TW, tw = m - th * p.TW;
-        const bool store_leader = (threadIdx.x == 64);
-        int acc = 0, sbuf = 0;
+        const int TW = p.TW, TH = p.TH, BN = p.BN, unit_cols = p.unit_cols, n_units = p.n_units, act = (p.debug & 16) ? YSOD_ACT_NONE : p.act;
+        const int th = m / TW, tw = m - th * TW;
+        const bool out_f32 = p.out_f32 != 0;
+        const uint32_t swz_mask = (uint32_t)p.swz_mask;
+        const uint32_t unit_bytes = 128u * p.row_bytes;
+        const int chunks_per_unit = unit_cols >> 4;
+        const int nchunks = BN >> 4;
+        const __nv_bfloat16* const res = p.res;
+        const bool leader_warp = (warp & 7) == 0;
+        const bool tre = tr && leader_warp && lane == 0 && grp == 0;
+        const uint32_t sb = stage_out + (uint32_t)grp * ((uint32_t)n_units * unit_bytes);
+        const uint32_t my_tfull = tfull_bar + 8u * grp, my_tempty = tempty_bar + 8u * grp;
+        const uint32_t trow = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * BN);
+        const uint32_t row0 = sb + (uint32_t)m * p.row_bytes;
         uint32_t acc_phase = 0;
-        const int chunks_per_unit = p.unit_cols >> 4;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-            const int nt = t / m_tiles, mt = t - nt * m_tiles;
-            const int img = mt / tiles_per_img;
-            const int trem = mt - img * tiles_per_img;
-            const int oh0 = (trem / p.tiles_w) * p.TH, ow0 = (trem % p.tiles_w) * p.TW;
-            const int oh = oh0 + th, ow = ow0 + tw;
-            const int n0 = nt * p.BN;
-            const bool valid = (m < p.TH * p.TW) && (oh < p.Ho) && (ow < p.Wo);
-            const size_t pix = ((size_t)img * p.Ho + oh) * p.Wo + ow;
-            mbar_wait(tfull_bar + 8u * acc, acc_phase);
+        TileIter ti;
+        ti.init(blockIdx.x, p);
+        if (grp) ti.step(p);
+        for (int tcount = grp; ti.valid(p); ti.step(p), ti.step(p), tcount += 2) {
+            const int img = ti.img;
+            const int oh0 = ti.th * TH, ow0 = ti.tw * TW;
+            const int n0 = ti.nt * BN;
+            // residual rows do not depend on the accumulator: fetch the first chunk's before waiting for the MMAs
+            bool add_res = false;
+            const __nv_bfloat16* rp = nullptr;
+            uint4 ra = make_uint4(0, 0, 0, 0), rb = ra;
+            if (res != nullptr) {
+                const int oh = oh0 + th, ow = ow0 + tw;
+                add_res = (m < TH * TW) && (oh < p.Ho) && (ow < p.Wo);
+                rp = res + (((size_t)img * p.Ho + oh) * p.Wo + ow) * p.rcs + n0;
+                if (add_res && cg < nchunks) { ra = *reinterpret_cast<const uint4*>(rp + cg * 16); rb = *reinterpret_cast<const uint4*>(rp + cg * 16 + 8); }
+            }
+            mbar_wait(my_tfull, acc_phase);
+            trace(tre, 2, 1, tcount, 0, tcnt);       // accumulator full seen
             tc_fence_after();
-            const uint32_t trow = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
-            for (int u = 0; u < p.n_units; ++u) {
-                const uint32_t sb = stage_out + (uint32_t)sbuf * 16384u;
-                // the bulk store issued from this buffer two units ago must have finished reading it
-                if (store_leader) bulk_wait_read<1>();
-                epi_barrier();
-                const uint32_t row_addr = sb + (uint32_t)m * p.row_bytes;
-                for (int ch = 0; ch < chunks_per_unit; ++ch) {
-                    const int c0 = u * p.unit_cols + ch * 16;
-                    if (c0 >= p.BN) break;  // warp-uniform
-                    uint32_t v[16];
-                    tmem_ld16(trow + (uint32_t)c0, v);
-                    tmem_ld_wait(v);
-                    float f[16];
-                    const uint32_t bsm = bias_smem + 4u * (uint32_t)(n0 + c0);
+            if (p.debug & 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(my_tempty);
+                acc_phase ^= 1u;
+                continue;
+            }
+            // the bulk stores issued from this group's staging buffer (previous own tile) must have finished reading it
+            if (leader_warp) bulk_wait_read<0>();
+            epi_barrier(grp);
+            trace(tre, 2, 2, tcount, 0, tcnt);       // staging buffer free
+            for (int ch = cg; ch < nchunks; ch += 2) {
+                const int c0 = ch * 16;
+                uint32_t v[16];
+                tmem_ld16(trow + (uint32_t)c0, v);
+                const float4* bs = reinterpret_cast<const float4*>(bias_s + n0 + c0);
+                const float4 b0 = bs[0], b1 = bs[1], b2 = bs[2], b3 = bs[3];
+                tmem_ld_wait(v);
+                float f[16];
+                f[0] = __uint_as_float(v[0]) + b0.x; f[1] = __uint_as_float(v[1]) + b0.y; f[2] = __uint_as_float(v[2]) + b0.z; f[3] = __uint_as_float(v[3]) + b0.w;
+                f[4] = __uint_as_float(v[4]) + b1.x; f[5] = __uint_as_float(v[5]) + b1.y; f[6] = __uint_as_float(v[6]) + b1.z; f[7] = __uint_as_float(v[7]) + b1.w;
+                f[8] = __uint_as_float(v[8]) + b2.x; f[9] = __uint_as_float(v[9]) + b2.y; f[10] = __uint_as_float(v[10]) + b2.z; f[11] = __uint_as_float(v[11]) + b2.w;
+                f[12] = __uint_as_float(v[12]) + b3.x; f[13] = __uint_as_float(v[13]) + b3.y; f[14] = __uint_as_float(v[14]) + b3.z; f[15] = __uint_as_float(v[15]) + b3.w;
+                if (act == YSOD_ACT_SILU) act16<YSOD_ACT_SILU>(f);
+                else if (act == YSOD_ACT_GELU) act16<YSOD_ACT_GELU>(f);
+                else if (act == YSOD_ACT_RELU) act16<YSOD_ACT_RELU>(f);
+                if (add_res) {
+                    const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        f[2 * j] += __uint_as_float(rw[j] << 16);
+                        f[2 * j + 1] += __uint_as_float(rw[j] & 0xffff0000u);
+                    }
+                    if (ch + 2 < nchunks) { ra = *reinterpret_cast<const uint4*>(rp + c0 + 32); rb = *reinterpret_cast<const uint4*>(rp + c0 + 40); }
+                }
+                // swizzled store into unit u = ch / chunks_per_unit: 16-byte piece index ^= (address bits [7..]) & mask (== TMA swizzle)
+                const int u = ch / chunks_per_unit, cu = ch - u * chunks_per_unit;
+                const uint32_t row_addr = row0 + (uint32_t)u * unit_bytes;
+                if (out_f32) {
+                    const uint32_t off0 = (uint32_t)(cu * 64);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        float b0, b1, b2, b3;
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b0), "=f"(b1), "=f"(b2), "=f"(b3) : "r"(bsm + 16u * j));
-                        f[4 * j] = __uint_as_float(v[4 * j]) + b0;
-                        f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b1;
-                        f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b2;
-                        f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b3;
+                        uint32_t a = row_addr + off0 + 16u * j;
+                        a ^= ((a >> 7) & swz_mask) << 4;
+                        st_shared_v4(a, __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
+                                     __float_as_uint(f[4 * j + 3]));
                     }
-                    if (p.act == YSOD_ACT_SILU) act16<YSOD_ACT_SILU>(f);
-                    else if (p.act == YSOD_ACT_GELU) act16<YSOD_ACT_GELU>(f);
-                    else if (p.act == YSOD_ACT_RELU) act16<YSOD_ACT_RELU>(f);
-                    if (p.res != nullptr && valid) {
-                        const __nv_bfloat16* rp = p.res + pix * p.rcs + n0 + c0;
-                        float r8[8];
-                        ysod_vec8<__nv_bfloat16>::load(rp, r8);
+                } else {
+                    const uint32_t off0 = (uint32_t)(cu * 32);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) f[j] += r8[j];
-                        ysod_vec8<__nv_bfloat16>::load(rp + 8, r8);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) f[8 + j] += r8[j];
-                    }
-                    // swizzled store: 16-byte piece index ^= (address bits [7..]) & mask  (== the TMA swizzle of tmO)
-                    if (p.out_f32) {
-                        const uint32_t off0 = (uint32_t)(ch * 64);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint32_t a = row_addr + off0 + 16u * j;
-                            a ^= ((a >> 7) & (uint32_t)p.swz_mask) << 4;
-                            st_shared_v4(a, __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
-                                         __float_as_uint(f[4 * j + 3]));
-                        }
-                    } else {
-                        const uint32_t off0 = (uint32_t)(ch * 32);
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            uint32_t a = row_addr + off0 + 16u * j;
-                            a ^= ((a >> 7) & (uint32_t)p.swz_mask) << 4;
-                            st_shared_v4(a, pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                                         pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
-                        }
+                    for (int j = 0; j < 2; ++j) {
+                        uint32_t a = row_addr + off0 + 16u * j;
+                        a ^= ((a >> 7) & swz_mask) << 4;
+                        st_shared_v4(a, pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                                     pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
                     }
                 }
-                if (u == p.n_units - 1) {
-                    // all TMEM reads of this warp are complete (tcgen05.wait::ld above): hand the accumulator back
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tempty_bar + 8u * acc);
-                }
-                fence_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
-                epi_barrier();
-                if (store_leader) {
-                    tma_store_4d(&tmO, sb, n0 + u * p.unit_cols, ow0, oh0, img);
-                    bulk_commit();
-                }
-                sbuf ^= 1;
             }
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1u;
+            // all TMEM reads of this warp are complete (tcgen05.wait::ld above): hand the accumulator back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(my_tempty);
+            trace(tre, 2, 3, tcount, 0, tcnt);       // accumulator handed back
+            fence_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+            epi_barrier(grp);
+            if (leader_warp && elect_one()) {
+                if (!(p.debug & 8)) {
+                    for (int u = 0; u < n_units; ++u) tma_store_4d(&tmO, sb + (uint32_t)u * unit_bytes, n0 + u * unit_cols, ow0, oh0, img);
+                }
+                bulk_commit();
+            }
+            trace(tre, 2, 4, tcount, 0, tcnt);       // stores issued
+            acc_phase ^= 1u;
         }
-        if (store_leader) bulk_wait_read<0>();  // smem must stay valid until the last bulk store has read it
+        if (leader_warp) bulk_wait_read<0>();  // smem must stay valid until the last bulk store has read it
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)p.tmem_cols) : "memory");
     }
 }
@@ -528,20 +690,25 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
     }
     // 3x3 / stride-1 halo-reuse specialisation: fixed 16 x 8 output tile; worth it when that tiling wastes < 25 % of M
     bool halo = false;
+    const int dbg = mode >> 8;
+    mode &= 0xff;
     if (ksize == 3 && stride == 1 && Cin % 64 == 0) {
         const double hutil = (double)Ho * Wo / ((double)ysod_cdiv(Ho, 16) * ysod_cdiv(Wo, 8) * 128.0);
         halo = (mode == 2) || (mode == 0 && hutil >= 0.75);
     }
     YSOD_CHECK_ARG(mode != 2 || halo, "ysod_conv_tc_create_ex: shape does not qualify for the halo kernel");
+    p.debug = dbg;
     if (halo) { bestTH = 16; bestTW = 8; }
     p.N = N; p.Ho = Ho; p.Wo = Wo; p.TH = bestTH; p.TW = bestTW;
     p.tiles_h = ysod_cdiv(Ho, bestTH); p.tiles_w = ysod_cdiv(Wo, bestTW);
     p.Cin = Cin; p.ksize = ksize; p.stride = stride; p.pad = pad;
     p.BK = (Cin % 64 == 0) ? 64 : 32;
     int BN = Cout_pad;
-    if (BN > 256) {
-        BN = 256;
-        while (Cout_pad % BN != 0) BN -= 16;  // largest multiple of 16 <= 256 dividing Cout_pad
+    if (BN > 128) {
+        // <= 128 output channels per tile: the two epilogue groups each stage a whole tile (<= 32 KB), wide layers get more
+        // (smaller) tiles to spread over the 148 SMs, and N = 128 MMAs already run at 93 % of the N = 256 rate
+        BN = 128;
+        while (Cout_pad % BN != 0) BN -= 16;  // largest multiple of 16 <= 128 dividing Cout_pad
     }
     p.BN = BN;
     p.tmem_cols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;  // double-buffered accumulator
@@ -560,38 +727,6 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
     const uint32_t layout = (p.BK == 64) ? 2u : 4u;  // SWIZZLE_128B : SWIZZLE_64B
     p.desc_hi = sbo | (1u << 14) | (layout << 29);
     p.cchunks = Cin / p.BK;
-    const uint32_t fixed = 2u * 16384u + 4u * (uint32_t)Cout_pad + 3u * 1024u;   // staging + bias + slack
-    size_t ring_bytes = 0;
-    int nbar = 0;
-    if (!halo) {
-        const uint32_t stage_bytes = p.a_bytes + p.b_bytes;
-        uint32_t budget = (3u * stage_bytes + fixed <= 112u * 1024u) ? 112u * 1024u - fixed : 224u * 1024u - fixed;
-        int stages = (int)(budget / stage_bytes);
-        if (stages > 8) stages = 8;   // persistent kernel: the ring streams across tiles, so depth is not capped by num_k
-        if (stages < 2) stages = 2;
-        p.stages = p.a_stages = p.b_stages = stages;
-        ring_bytes = (size_t)stages * stage_bytes;
-        nbar = 4 * stages;
-    } else {
-        p.a_bytes = 18u * 8u * 128u;   // one column-shifted halo copy: 18 rows x 8 px x 64 ch bf16
-        p.a_tx = p.a_bytes;
-        const uint32_t avail = 224u * 1024u - fixed;
-        const uint32_t b_all = 9u * (uint32_t)p.cchunks * p.b_bytes;
-        if (b_all + 4u * p.a_bytes <= avail) {   // all weight taps stay resident; >= 4 halo copies in flight
-            p.b_resident = 1;
-            p.b_stages = 9 * p.cchunks;
-            p.a_stages = (int)((avail - b_all) / p.a_bytes);
-        } else {
-            p.b_resident = 0;
-            p.b_stages = 4;
-            p.a_stages = (int)((avail - 4u * p.b_bytes) / p.a_bytes);
-        }
-        if (p.a_stages > 6) p.a_stages = 6;
-        YSOD_CHECK_ARG(p.a_stages >= 3, "ysod_conv_tc_create: halo plan does not fit in shared memory (BN %d)", BN);
-        p.stages = p.a_stages;
-        ring_bytes = (size_t)p.a_stages * p.a_bytes + (size_t)p.b_stages * p.b_bytes;
-        nbar = 2 * p.a_stages + 2 * p.b_stages;
-    }
     {
         const uint32_t es = p.out_f32 ? 4u : 2u;
         uint32_t rb = 32;
@@ -602,22 +737,84 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
         p.swz_mask = rb == 128 ? 7 : rb == 64 ? 3 : 1;
         p.cout_pad = Cout_pad;
     }
-    // ring + 1 KB alignment slack + barriers/slot + bias + alignment + two 16 KB output staging buffers
-    c.smem = ring_bytes + 1024 + (8 * (size_t)nbar + 64) + 4 * (size_t)Cout_pad + 1024 + 2 * 16384;
+    // epilogue staging holds the whole BN-wide output tile (n_units sub-buffers of 128 rows); double-buffered up to 32 KB
+    const uint32_t tile_stage_bytes = (uint32_t)p.n_units * 128u * p.row_bytes;
+    p.stage_bufs = 2;   // one per epilogue group
+    const uint32_t staging = (uint32_t)p.stage_bufs * tile_stage_bytes;
+    const uint32_t fixed = staging + 4u * (uint32_t)Cout_pad + 3u * 1024u;   // staging + bias + slack
+    size_t ring_bytes = 0;
+    int nbar = 0;
+    if (!halo) {
+        // Pipeline stage = G K-blocks ("slots") behind one mbarrier pair: with narrow N an MMA retires in N/2 cycles, so a
+        // stage must carry enough MMAs (>= ~512 tensor-pipe cycles) to amortise the issuer's per-handshake cost.
+        const uint32_t slot_bytes = p.a_bytes + p.b_bytes;
+        const uint32_t budget = 224u * 1024u - fixed;   // one fat CTA per SM
+        int slots = (int)(budget / slot_bytes);
+        if (slots > 16) slots = 16;
+        const int kb_cycles = (p.BK / 16) * (BN / 2);
+        int gmax = 512 / kb_cycles;
+        if (gmax < 1) gmax = 1;
+        if (gmax > slots / 4) gmax = slots / 4;   // keep >= 2 stages per sub-ring
+        if (gmax < 1) gmax = 1;
+        int G = 1;
+        for (int g = 1; g <= gmax; ++g)
+            if (p.num_k % g == 0) G = g;
+        int stages = slots / (2 * G);   // stages per sub-ring (one sub-ring per MMA issuer / tile parity)
+        if (stages > 4) stages = 4;
+        if (stages < 1) stages = 1;
+        p.kgroup = G;
+        p.sgroup = 1;
+        p.stages = stages;
+        p.a_stages = p.b_stages = 2 * stages * G;   // smem carve-up counts slots; barriers are per stage (<= slots)
+        ring_bytes = (size_t)2 * stages * G * slot_bytes;
+        nbar = 4 * 2 * stages * G;
+    } else {
+        p.a_bytes = 18u * 8u * 128u;   // one column-shifted halo copy: 18 rows x 8 px x 64 ch bf16
+        p.a_tx = p.a_bytes;
+        const uint32_t avail = 224u * 1024u - fixed;
+        const uint32_t b_all = 9u * (uint32_t)p.cchunks * p.b_bytes;
+        // p.a_stages / p.b_stages are PER SUB-RING (one sub-ring per MMA issuer / tile parity); resident weights are shared
+        int a_total;
+        if (b_all + 6u * p.a_bytes <= avail) {   // all weight taps stay resident; one full tile of halo copies per sub-ring
+            p.b_resident = 1;
+            p.b_stages = 9 * p.cchunks;
+            a_total = 6;
+            p.sgroup = 3;
+            ring_bytes = (size_t)a_total * p.a_bytes + (size_t)p.b_stages * p.b_bytes;
+            nbar = 2 * a_total + 2 * p.b_stages;
+        } else {
+            p.b_resident = 0;
+            p.b_stages = 3;   // per sub-ring: the three filter-row taps of one filter column
+            YSOD_CHECK_ARG(6u * p.b_bytes + 2u * p.a_bytes <= avail, "ysod_conv_tc_create: halo plan does not fit in shared memory (BN %d)", BN);
+            a_total = (int)((avail - 6u * p.b_bytes) / p.a_bytes);
+            if (a_total > 6) a_total = 6;
+            a_total &= ~1;
+            p.sgroup = 1;
+            ring_bytes = (size_t)a_total * p.a_bytes + (size_t)6 * p.b_bytes;
+            nbar = 2 * a_total + 2 * 6;
+        }
+        p.kgroup = 1;
+        p.a_stages = a_total / 2;
+        p.stages = p.a_stages;
+    }
+    if (!halo) { p.a_slots = p.b_slots = p.a_stages; p.a_stages = p.b_stages = p.stages; }
+    else { p.a_slots = 2 * p.a_stages; p.b_slots = p.b_resident ? p.b_stages : 2 * p.b_stages; }
+    // ring + 1 KB alignment slack + barriers/slot + bias + alignment + output staging
+    c.smem = ring_bytes + 1024 + (8 * (size_t)nbar + 64) + 4 * (size_t)Cout_pad + 1024 + staging;
     c.halo = halo;
     {
         int dev = 0, sms = 148;
         YSOD_CUDA(cudaGetDevice(&dev));
         YSOD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        // co-resident persistent CTAs per SM: limited by shared memory (227 KB) and TMEM (512 columns)
-        int per_sm = (int)((227u * 1024u) / (c.smem + 1024));
-        if (per_sm > 512 / p.tmem_cols) per_sm = 512 / p.tmem_cols;
-        if (per_sm > 2) per_sm = 2;
-        if (per_sm < 1) per_sm = 1;
         const long long total = (long long)N * p.tiles_h * p.tiles_w * p.n_tiles;
-        long long g = (long long)sms * per_sm;
+        long long g = (long long)sms;   // one persistent CTA per SM
         if (g > total) g = total;
         c.grid = dim3((unsigned)g, 1, 1);
+        long long r = g;
+        p.step_tw = (int)(r % p.tiles_w); r /= p.tiles_w;
+        p.step_th = (int)(r % p.tiles_h); r /= p.tiles_h;
+        p.step_img = (int)(r % N);
+        p.step_nt = (int)(r / N);
     }
 
     const CUtensorMapSwizzle swz = p.BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -695,11 +892,22 @@ int ysod_conv_tc_run(ysod_conv_tc* h, cudaStream_t stream) {
 int ysod_conv_tc_info(ysod_conv_tc* h, int* out8) {
     YSOD_CHECK_ARG(h && out8, "ysod_conv_tc_info: null");
     out8[0] = h->c.p.TH; out8[1] = h->c.p.TW; out8[2] = h->c.p.BN; out8[3] = h->c.p.BK; out8[4] = h->c.p.stages;
-    out8[5] = (int)h->c.grid.x; out8[6] = h->c.halo ? (100 + 10 * h->c.p.b_resident + h->c.p.b_stages % 10) : h->c.p.n_tiles;
+    out8[5] = (int)h->c.grid.x; out8[6] = h->c.halo ? (100 + 10 * h->c.p.b_resident + h->c.p.b_stages % 10) : (10 * h->c.p.kgroup + h->c.p.n_tiles);
     out8[7] = (int)h->c.smem;
     return YSOD_OK;
 }
 
 void ysod_conv_tc_destroy(ysod_conv_tc* h) { delete h; }
+
+// Profiling aid: copies the pipeline trace of the last launch with debug bit 32 (mode = 32 << 8) to the host and resets it.
+// out: 2 * cap uint64 (tag, clock64); returns the number of records. Synchronises the device.
+int ysod_debug_trace(unsigned long long* out, int cap) {
+    if (cudaDeviceSynchronize() != cudaSuccess || cap < TRACE_CAP) return -1;
+    if (cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * 2 * TRACE_CAP) != cudaSuccess) return -1;
+    void* sym = nullptr;
+    if (cudaGetSymbolAddress(&sym, g_trace) != cudaSuccess) return -1;
+    cudaMemset(sym, 0, sizeof(unsigned long long) * 2 * TRACE_CAP);
+    return TRACE_CAP;
+}
 
 }  // extern "C"

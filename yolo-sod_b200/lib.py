@@ -26,6 +26,7 @@ PROTOTYPES = {
     "ysod_conv_tc_run": (i32, [vp, vp]),
     "ysod_conv_tc_info": (i32, [vp, C.POINTER(i32)]),
     "ysod_conv_tc_destroy": (None, [vp]),
+    "ysod_debug_trace": (i32, [vp, i32]),
     "ysod_conv_direct": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, vp, i32, i32, vp]),
     "ysod_dwconv": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, vp, i32, vp, i32, i32, vp]),
     "ysod_stem_conv": (i32, [vp, i32, i32, i32, vp, vp, i32, i32, i32, i32, vp, i32, i32, i32, vp]),
