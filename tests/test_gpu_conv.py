@@ -80,6 +80,12 @@ CASES = [
     (1, 1, 1000, 128, 64, 1, 1, dict(act="gelu", res=True)),        # linear + GELU + residual
     (2, 16, 16, 64, 64, 3, 1, dict(xcs_extra=64, ocs_extra=32)),    # channel-sliced input and output views
     (1, 24, 24, 512, 64, 3, 1, {}),                                 # long K (72 K blocks), ring wraps many times
+    # many tiles per persistent CTA: both MMA issuers / both epilogue groups / both sub-rings wrap several times
+    (8, 160, 160, 64, 64, 1, 1, dict(res=True)),
+    (4, 160, 160, 64, 128, 3, 2, {}),
+    (8, 80, 80, 256, 128, 1, 1, {}),
+    (4, 160, 160, 32, 32, 3, 1, dict(res=True)),
+    (2, 64, 64, 64, 192, 1, 1, dict(act="none")),                   # three N tiles of 64 (192 is not a multiple of 128)
 ]
 
 
@@ -98,6 +104,8 @@ HALO_CASES = [
     (1, 32, 32, 256, 64, 3, 1, dict(xcs_extra=64, ocs_extra=64)),   # four chunks, sliced views
     (1, 48, 24, 64, 64, 3, 1, dict(out_f32=True, act="none")),      # fp32 output (two store units)
     (1, 20, 20, 64, 32, 3, 1, {}),                                  # BN=32 (64 B staging rows), low-utilisation map forced
+    (8, 80, 80, 128, 128, 3, 1, {}),                                # streamed taps, many tiles per CTA (ring / sub-ring wrap)
+    (6, 160, 160, 64, 64, 3, 1, dict(res=True)),                    # resident taps, ~9 tiles per CTA
 ]
 
 

@@ -31,6 +31,7 @@ struct TcParams {
     int Cin, ksize, stride, pad;
     int BN, BK, stages, tmem_cols, num_k, n_tiles;
     int step_tw, step_th, step_img, step_nt;   // gridDim.x decomposed in the mixed radix (tiles_w, tiles_h, N): per-tile coordinate update without divisions
+    int issuers;     // MMA issuer threads: 2 = tiles alternate between two issuers on separate sub-rings (short tiles), 1 = one issuer, whole ring
     int kgroup;      // generic mode: K blocks (slots) per pipeline stage = per mbarrier handshake / per elected issue burst
     int sgroup;      // halo mode: filter columns (A copies) per issue burst (3 when the weights are resident, else 1)
     int a_stages, b_stages, b_resident, cchunks;   // stages per sub-ring
@@ -226,11 +227,12 @@ struct TileIter {
 // tile i overlaps the TMA/MMA main loop of tile i+1; barriers and TMEM are set up once per CTA.
 //
 // HALO = true is the 3x3 / stride-1 specialisation that removes the 9x re-fetch of the activation tile from L2: an output
-// tile is 16 rows x 8 columns; for every 64-channel chunk THREE column-shifted halo copies (18 rows x 8 px x 128 B, one per
-// filter column s) are landed by TMA, and the three filter rows r are plain +1024 B (one 8-row swizzle atom) offsets of the
-// UMMA descriptor start address into the same copy -- always atom-aligned, so the canonical SW128 K-major layout holds.
-// A traffic per tile drops from 9 x 16 KB to 3 x 18 KB; weight taps stream through their own ring, or stay resident in
-// shared memory for the whole CTA lifetime when they fit (64->64: 72 KB).
+// tile is 16 rows x 8 columns; for every 64-channel chunk ONE halo copy (18 rows x 10 px x 128 B = 22.5 KB) is landed by TMA
+// as a flat array of 128 B pixel rows (SWIZZLE_128B, conv zero padding = TMA out-of-bounds fill). Filter tap (r, s) is then
+// just a different UMMA A descriptor into the same copy: start address = copy + (r*10 + s) * 128 B, the 16 groups of 8
+// output pixels (one output row each) are SBO = 10 pixels = 1280 B apart. The 128 B swizzle is a function of absolute
+// shared-memory address bits (verified on B200: base_offset = 0 is correct for any 128 B-aligned start in a 1 KB-aligned slot). A traffic per tile drops from 9 x 16 KB to 22.5 KB; weight taps stay
+// resident in shared memory for the whole CTA lifetime when they fit (64->64: 72 KB), else stream through their own ring.
 template <bool HALO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -247,8 +249,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t fullA = bar_base, emptyA = bar_base + 8u * a_slots;
     const uint32_t fullB = bar_base + 16u * a_slots, emptyB = fullB + 8u * b_slots;
     const uint32_t tfull_bar = fullB + 16u * b_slots;
-    const uint32_t tempty_bar = tfull_bar + 16u;
-    const uint32_t tmem_slot = tempty_bar + 16u;
+    const uint32_t tempty_bar = tfull_bar + 32u;   // 4 accumulators: 2 per issuer / epilogue group (double-buffered per tile parity)
+    const uint32_t tmem_slot = tempty_bar + 32u;
     // after the barriers: bias[cout_pad] fp32, then the (1 KB aligned) output staging: nbuf x n_units x 128 rows x row_bytes
     const uint32_t bias_smem = tmem_slot + 16u;
     const uint32_t stage_out = (bias_smem + 4u * (uint32_t)p.cout_pad + 1023u) & ~1023u;
@@ -267,7 +269,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(fullB + 8u * s, 1);
             mbar_init(emptyB + 8u * s, 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < 4; ++a) {
             mbar_init(tfull_bar + 8u * a, 1);
             mbar_init(tempty_bar + 8u * a, EPI_WARPS / 2);  // one arrive per warp of the accumulator's epilogue group
         }
@@ -290,11 +292,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===== TMA producer (one elected lane) =====
         if (elect_one()) {
             const int cchunks = p.cchunks;
+            const bool two = p.issuers == 2;
             if (!HALO) {
                 const uint32_t tx = p.a_tx + p.b_bytes;
                 const int nstages = p.stages, G = p.kgroup, ngroups = p.num_k / p.kgroup, BK = p.BK, ksize = p.ksize, cstride = p.stride, pad = p.pad, Cin = p.Cin;
                 // two sub-rings of `nstages` stages: even tiles (issuer 0) use stages [0, nstages), odd tiles [nstages, 2*nstages)
-                int st_c = 0, st_o = 0, base_c = 0, base_o = nstages;
+                int st_c = 0, st_o = 0, base_c = 0, base_o = two ? nstages : 0;
                 uint32_t ph_c = 0, ph_o = 0;
                 TileIter ti;
                 ti.init(blockIdx.x, p);
@@ -323,14 +326,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                         if (++st_c == nstages) { st_c = 0; ph_c ^= 1u; }
                     }
-                    { int x = st_c; st_c = st_o; st_o = x; x = base_c; base_c = base_o; base_o = x; }
-                    { uint32_t x = ph_c; ph_c = ph_o; ph_o = x; }
+                    if (two) {
+                        { int x = st_c; st_c = st_o; st_o = x; x = base_c; base_c = base_o; base_o = x; }
+                        { uint32_t x = ph_c; ph_c = ph_o; ph_o = x; }
+                    }
                 }
             } else {
                 // sub-rings: even tiles use A slots [0, ah) and streamed-B slots [0, bh); odd tiles the second halves
                 const int ah = p.a_stages, bh = p.b_stages;
                 const bool b_res = p.b_resident != 0;
-                int sa_c = 0, sa_o = 0, sb_c = 0, sb_o = 0, abase_c = 0, abase_o = ah, bbase_c = 0, bbase_o = b_res ? 0 : bh;
+                int sa_c = 0, sa_o = 0, sb_c = 0, sb_o = 0, abase_c = 0, abase_o = two ? ah : 0, bbase_c = 0, bbase_o = (b_res || !two) ? 0 : bh;
                 uint32_t pa_c = 0, pa_o = 0, pb_c = 0, pb_o = 0;
                 bool first = true;
                 TileIter ti;
@@ -340,17 +345,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int oh0 = ti.th * 16, ow0 = ti.tw * 8;
                     const int n0 = ti.nt * p.BN;
                     for (int cc = 0; cc < cchunks; ++cc) {
+                        // ONE halo copy per 64-channel chunk: input rows oh0-1..oh0+16, columns ow0-1..ow0+8 (180 pixel rows of 128 B)
+                        const int aslot = abase_c + sa_c;
+                        mbar_wait(emptyA + 8u * aslot, pa_c ^ 1u);
+                        trace(tr, 0, 1, tcount, cc, tcnt);             // A slot free
+                        if (p.debug & 2) mbar_arrive(fullA + 8u * aslot);
+                        else {
+                            mbar_expect_tx(fullA + 8u * aslot, p.a_tx);
+                            tma_load_4d(a_base + (uint32_t)aslot * p.a_bytes, &tmA, fullA + 8u * aslot, cc * 64, ow0 - 1, oh0 - 1, img);
+                        }
+                        if (++sa_c == ah) { sa_c = 0; pa_c ^= 1u; }
+                        if (b_res && !first) continue;  // weights already in shared memory
                         for (int s = 0; s < 3; ++s) {
-                            const int aslot = abase_c + sa_c;
-                            mbar_wait(emptyA + 8u * aslot, pa_c ^ 1u);
-                            trace(tr, 0, 1, tcount, cc * 3 + s, tcnt);             // A slot free
-                            if (p.debug & 2) mbar_arrive(fullA + 8u * aslot);
-                            else {
-                                mbar_expect_tx(fullA + 8u * aslot, p.a_bytes);
-                                tma_load_4d(a_base + (uint32_t)aslot * p.a_bytes, &tmA, fullA + 8u * aslot, cc * 64, ow0 + s - 1, oh0 - 1, img);
-                            }
-                            if (++sa_c == ah) { sa_c = 0; pa_c ^= 1u; }
-                            if (b_res && !first) continue;  // weights already in shared memory
                             for (int r = 0; r < 3; ++r) {
                                 const int slot = b_res ? (cc * 9 + s * 3 + r) : (bbase_c + sb_c);
                                 if (!b_res) mbar_wait(emptyB + 8u * slot, pb_c ^ 1u);
@@ -361,45 +367,52 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                     }
                     first = false;
-                    { int x = sa_c; sa_c = sa_o; sa_o = x; x = sb_c; sb_c = sb_o; sb_o = x; x = abase_c; abase_c = abase_o; abase_o = x; x = bbase_c; bbase_c = bbase_o; bbase_o = x; }
-                    { uint32_t x = pa_c; pa_c = pa_o; pa_o = x; x = pb_c; pb_c = pb_o; pb_o = x; }
+                    if (two) {
+                        { int x = sa_c; sa_c = sa_o; sa_o = x; x = sb_c; sb_c = sb_o; sb_o = x; x = abase_c; abase_c = abase_o; abase_o = x; x = bbase_c; bbase_c = bbase_o; bbase_o = x; }
+                        { uint32_t x = pa_c; pa_c = pa_o; pa_o = x; x = pb_c; pb_c = pb_o; pb_o = x; }
+                    }
                 }
             }
         }
     } else if (warp == MMA_WARP || warp == MMA_WARP + 1) {
-        // ===== MMA issuers: the whole warp walks the pipeline (converged), one elected lane issues. Issuer `me` owns the
-        //       CTA's tiles me, me + 2, ... and TMEM accumulator `me`; ring positions follow from the tile counter. =====
+        // ===== MMA issuers: one elected thread per issuer warp runs the whole loop (tcgen05.mma / commit / mbarrier waits are
+        //       per-thread operations; staying inside one elected branch avoids a warp reconvergence per burst).
+        //       two issuers (p.issuers == 2): issuer `me` owns the CTA's tiles me, me + 2, ... and sub-ring `me`;
+        //       one issuer: issuer 0 owns every tile and the whole ring. Accumulator of tile i = i % 4. =====
         const int me = warp - MMA_WARP;
-        const int trole = me ? 3 : 1;
-        const uint32_t idesc = p.idesc, desc_hi = p.desc_hi;
-        const uint32_t a_bytes = p.a_bytes, b_bytes = p.b_bytes;
-        const bool no_mma = (p.debug & 4) != 0;
-        const uint32_t d_tmem = tmem_acc + (uint32_t)(me * p.BN);
-        const uint32_t my_tfull = tfull_bar + 8u * me, my_tempty = tempty_bar + 8u * me;
-        uint32_t acc_phase = 0;
-        if (!HALO) {
-            const int nstages = p.stages, G = p.kgroup, ngroups = p.num_k / p.kgroup;
-            const bool k4 = (p.BK == 64);
-            int st = 0;
-            uint32_t phase = 0;
-            const int sbase = me * nstages;   // this issuer's sub-ring
+        const bool two = p.issuers == 2;
+        if ((me == 0 || two) && elect_one()) {
+            const int trole = me ? 3 : 1;
+            const uint32_t idesc = p.idesc, desc_hi = p.desc_hi;
+            const uint32_t a_bytes = p.a_bytes, b_bytes = p.b_bytes;
+            const bool no_mma = (p.debug & 4) != 0;
+            const int BN = p.BN;
+            const int astep = two ? 2 : 1;   // accumulator / tile stride of this issuer
+            int aidx = me;                   // accumulator of the current tile (tile index % 4)
+            uint32_t acc_phase = 0;
             TileIter ti;
             ti.init(blockIdx.x, p);
             if (me) ti.step(p);
-            for (int tcount = me; ti.valid(p); ti.step(p), ti.step(p), tcount += 2) {
-                mbar_wait(my_tempty, acc_phase ^ 1u);  // epilogue has drained this accumulator
-                trace(tr && lane == 0, trole, 1, tcount, 0, tcnt);
-                tc_fence_after();
-                for (int grp = 0; grp < ngroups; ++grp) {
-                    const int stage = sbase + st;
-                    mbar_wait(fullA + 8u * stage, phase);
-                    trace(tr && lane == 0, trole, 2, tcount, grp, tcnt);
+            if (!HALO) {
+                const int nstages = p.stages, G = p.kgroup, ngroups = p.num_k / p.kgroup;
+                const bool k4 = (p.BK == 64);
+                int st = 0;
+                uint32_t phase = 0;
+                const int sbase = me * nstages;   // this issuer's sub-ring (0 when there is a single issuer)
+                const uint32_t a_step = a_bytes >> 4, b_step = b_bytes >> 4;
+                for (int tcount = me; ti.valid(p); tcount += astep) {
+                    const uint32_t d_tmem = tmem_acc + (uint32_t)(aidx * BN);
+                    mbar_wait(tempty_bar + 8u * aidx, acc_phase ^ 1u);  // epilogue has drained this accumulator
+                    trace(tr, trole, 1, tcount, 0, tcnt);
                     tc_fence_after();
-                    if (elect_one()) {
+                    for (int grp = 0; grp < ngroups; ++grp) {
+                        const int stage = sbase + st;
+                        mbar_wait(fullA + 8u * stage, phase);
+                        trace(tr, trole, 2, tcount, grp, tcnt);
+                        tc_fence_after();
                         // one burst = G K-blocks; descriptor start address advances by 32 B (>>4 = 2) per UMMA_K = 16
                         uint32_t a_lo = umma_lo(a_base + (uint32_t)(stage * G) * a_bytes);
                         uint32_t b_lo = umma_lo(b_base + (uint32_t)(stage * G) * b_bytes);
-                        const uint32_t a_step = a_bytes >> 4, b_step = b_bytes >> 4;
                         if (!no_mma) {
                             for (int g = 0; g < G; ++g) {
                                 tc_mma_bf16(d_tmem, umma_desc(desc_hi, a_lo), umma_desc(desc_hi, b_lo), idesc, (uint32_t)((grp | g) != 0));
@@ -413,75 +426,79 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             }
                         }
                         tc_commit(emptyA + 8u * stage);  // frees the smem slots when these MMAs retire
-                        if (grp == ngroups - 1) tc_commit(my_tfull);  // accumulator complete
+                        if (grp == ngroups - 1) tc_commit(tfull_bar + 8u * aidx);  // accumulator complete
                         trace(tr, trole, 3, tcount, grp, tcnt);
+                        if (++st == nstages) { st = 0; phase ^= 1u; }
                     }
-                    __syncwarp();
-                    if (++st == nstages) { st = 0; phase ^= 1u; }
+                    aidx += astep;
+                    if (aidx >= 4) { aidx -= 4; acc_phase ^= 1u; }
+                    ti.step(p);
+                    if (two) ti.step(p);
                 }
-                acc_phase ^= 1u;
-            }
-        } else {
-            const int a_stages = p.a_stages, b_stages = p.b_stages, cchunks = p.cchunks, SG = p.sgroup;
-            const bool b_res = p.b_resident != 0;
-            bool first = true;
-            int sa = 0, sb = 0;          // positions inside this issuer's sub-rings
-            uint32_t pa = 0, pb = 0;
-            const int abase = me * a_stages, bbase = b_res ? 0 : me * b_stages;
-            TileIter ti;
-            ti.init(blockIdx.x, p);
-            if (me) ti.step(p);
-            for (int tcount = me; ti.valid(p); ti.step(p), ti.step(p), tcount += 2) {
-                mbar_wait(my_tempty, acc_phase ^ 1u);
-                trace(tr && lane == 0, trole, 1, tcount, 0, tcnt);                     // accumulator free
-                tc_fence_after();
-                for (int cc = 0; cc < cchunks; ++cc) {
-                    for (int s0 = 0; s0 < 3; s0 += SG) {
-                        // a_stages % SG == 0, so the SG halo copies of a burst are consecutive ring slots of one phase
-                        for (int j = 0; j < SG; ++j) mbar_wait(fullA + 8u * (abase + sa + j), pa);
-                        if (b_res) {
-                            if (first) {  // resident weights land once, during the CTA's first tile
-                                for (int j = 0; j < 3 * SG; ++j) mbar_wait(fullB + 8u * (cc * 9 + s0 * 3 + j), 0u);
-                            }
-                        } else {
-                            // the three weight taps of this filter column occupy consecutive ring slots (b_stages % 3 == 0)
-#pragma unroll
-                            for (int r = 0; r < 3; ++r) mbar_wait(fullB + 8u * (bbase + sb + r), pb);
+            } else {
+                const int a_stages = p.a_stages, b_stages = p.b_stages, cchunks = p.cchunks, SG = p.sgroup;
+                const bool b_res = p.b_resident != 0;
+                const uint32_t halo_desc_hi = (1280u >> 4) | (1u << 14) | (2u << 29);   // SBO = 10 pixels, SWIZZLE_128B
+                bool first = true;
+                int sa = 0, sb = 0;          // positions inside this issuer's (sub-)rings
+                uint32_t pa = 0, pb = 0;
+                const int abase = me * a_stages, bbase = b_res ? 0 : me * b_stages;
+                for (int tcount = me; ti.valid(p); tcount += astep) {
+                    const uint32_t d_tmem = tmem_acc + (uint32_t)(aidx * BN);
+                    mbar_wait(tempty_bar + 8u * aidx, acc_phase ^ 1u);
+                    trace(tr, trole, 1, tcount, 0, tcnt);                     // accumulator free
+                    tc_fence_after();
+                    for (int cc = 0; cc < cchunks; ++cc) {
+                        const int aslot = abase + sa;
+                        mbar_wait(fullA + 8u * aslot, pa);
+                        if (b_res && first) {  // resident weights land once, during the CTA's first tile
+                            for (int j = 0; j < 9; ++j) mbar_wait(fullB + 8u * (cc * 9 + j), 0u);
                         }
-                        tc_fence_after();
-                        trace(tr && lane == 0, trole, 2, tcount, cc * 3 + s0, tcnt);   // operands landed
-                        if (elect_one()) {
+                        const uint32_t a_slot_addr = a_base + (uint32_t)aslot * a_bytes;
+                        // resident weights: one burst of 36 MMAs per chunk; streamed weights: one burst of 12 per filter column
+                        for (int s0 = 0; s0 < 3; s0 += SG) {
+                            if (!b_res) {
+#pragma unroll
+                                for (int r = 0; r < 3; ++r) mbar_wait(fullB + 8u * (bbase + sb + r), pb);
+                            }
+                            tc_fence_after();
+                            trace(tr, trole, 2, tcount, cc * 3 + s0, tcnt);   // operands landed
                             if (!no_mma) {
-                                for (int j = 0; j < SG; ++j) {
-                                    const uint32_t a_lo0 = umma_lo(a_base + (uint32_t)(abase + sa + j) * a_bytes);
-                                    const uint32_t slot0 = b_res ? (uint32_t)(cc * 9 + (s0 + j) * 3) : (uint32_t)(bbase + sb);
+                                for (int s = s0; s < s0 + SG; ++s) {
+                                    const uint32_t slot0 = b_res ? (uint32_t)(cc * 9 + s * 3) : (uint32_t)(bbase + sb);
 #pragma unroll
                                     for (int r = 0; r < 3; ++r) {
-                                        const uint32_t a_lo = a_lo0 + 64u * r;  // filter row r = +8 halo rows = one 1024 B swizzle atom
+                                        // tap (r, s): the MMA's pixel rows start (r*10 + s) pixels into the 18 x 10 halo copy; the
+                                        // 8-pixel row groups are 10 pixels (SBO = 1280 B) apart.
+                                        const uint32_t a_lo = umma_lo(a_slot_addr + (uint32_t)(r * 10 + s) * 128u);
                                         const uint32_t b_lo = umma_lo(b_base + (slot0 + r) * b_bytes);
 #pragma unroll
                                         for (int k = 0; k < 4; ++k)
-                                            tc_mma_bf16(d_tmem, umma_desc(desc_hi, a_lo + 2u * k), umma_desc(desc_hi, b_lo + 2u * k), idesc,
-                                                        (uint32_t)((cc | s0 | j | r | k) != 0));
+                                            tc_mma_bf16(d_tmem, umma_desc(halo_desc_hi, a_lo + 2u * k), umma_desc(desc_hi, b_lo + 2u * k), idesc,
+                                                        (uint32_t)((cc | s | r | k) != 0));
                                     }
                                 }
                             }
                             if (!b_res) {
 #pragma unroll
                                 for (int r = 0; r < 3; ++r) tc_commit(emptyB + 8u * (bbase + sb + r));
+                                sb += 3;
+                                if (sb == b_stages) { sb = 0; pb ^= 1u; }
                             }
-                            for (int j = 0; j < SG; ++j) tc_commit(emptyA + 8u * (abase + sa + j));
-                            if (cc == cchunks - 1 && s0 + SG == 3) tc_commit(my_tfull);
+                            if (s0 + SG == 3) {
+                                tc_commit(emptyA + 8u * aslot);
+                                if (cc == cchunks - 1) tc_commit(tfull_bar + 8u * aidx);
+                            }
                             trace(tr, trole, 3, tcount, cc * 3 + s0, tcnt);           // burst issued + committed
                         }
-                        __syncwarp();
-                        if (!b_res) { sb += 3; if (sb == b_stages) { sb = 0; pb ^= 1u; } }
-                        sa += SG;
-                        if (sa == a_stages) { sa = 0; pa ^= 1u; }
+                        if (++sa == a_stages) { sa = 0; pa ^= 1u; }
                     }
+                    first = false;
+                    aidx += astep;
+                    if (aidx >= 4) { aidx -= 4; acc_phase ^= 1u; }
+                    ti.step(p);
+                    if (two) ti.step(p);
                 }
-                first = false;
-                acc_phase ^= 1u;
             }
         }
     } else {
@@ -506,8 +523,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool leader_warp = (warp & 7) == 0;
         const bool tre = tr && leader_warp && lane == 0 && grp == 0;
         const uint32_t sb = stage_out + (uint32_t)grp * ((uint32_t)n_units * unit_bytes);
-        const uint32_t my_tfull = tfull_bar + 8u * grp, my_tempty = tempty_bar + 8u * grp;
-        const uint32_t trow = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * BN);
+        const uint32_t trow0 = tmem_acc + ((uint32_t)(q * 32) << 16);
+        int asel = 0;   // accumulator of tile i is i % 4 = 2 * asel + grp for this group's tiles
         const uint32_t row0 = sb + (uint32_t)m * p.row_bytes;
         uint32_t acc_phase = 0;
         TileIter ti;
@@ -527,6 +544,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 rp = res + (((size_t)img * p.Ho + oh) * p.Wo + ow) * p.rcs + n0;
                 if (add_res && cg < nchunks) { ra = *reinterpret_cast<const uint4*>(rp + cg * 16); rb = *reinterpret_cast<const uint4*>(rp + cg * 16 + 8); }
             }
+            const int aidx = 2 * asel + grp;
+            const uint32_t my_tfull = tfull_bar + 8u * aidx, my_tempty = tempty_bar + 8u * aidx;
+            const uint32_t trow = trow0 + (uint32_t)(aidx * BN);
             mbar_wait(my_tfull, acc_phase);
             trace(tre, 2, 1, tcount, 0, tcnt);       // accumulator full seen
             tc_fence_after();
@@ -534,7 +554,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(my_tempty);
-                acc_phase ^= 1u;
+                asel ^= 1;
+                if (asel == 0) acc_phase ^= 1u;
                 continue;
             }
             // the bulk stores issued from this group's staging buffer (previous own tile) must have finished reading it
@@ -602,7 +623,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 bulk_commit();
             }
             trace(tre, 2, 4, tcount, 0, tcnt);       // stores issued
-            acc_phase ^= 1u;
+            asel ^= 1;
+            if (asel == 0) acc_phase ^= 1u;
         }
         if (leader_warp) bulk_wait_read<0>();  // smem must stay valid until the last bulk store has read it
     }
@@ -708,10 +730,10 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
         // <= 128 output channels per tile: the two epilogue groups each stage a whole tile (<= 32 KB), wide layers get more
         // (smaller) tiles to spread over the 148 SMs, and N = 128 MMAs already run at 93 % of the N = 256 rate
         BN = 128;
-        while (Cout_pad % BN != 0) BN -= 16;  // largest multiple of 16 <= 128 dividing Cout_pad
+        while (Cout_pad % BN != 0) BN >>= 1;  // 128 / 64 / 32 / 16: with several N tiles every store unit must be full width
     }
     p.BN = BN;
-    p.tmem_cols = 2 * BN <= 32 ? 32 : 2 * BN <= 64 ? 64 : 2 * BN <= 128 ? 128 : 2 * BN <= 256 ? 256 : 512;  // double-buffered accumulator
+    p.tmem_cols = 4 * BN <= 32 ? 32 : 4 * BN <= 64 ? 64 : 4 * BN <= 128 ? 128 : 4 * BN <= 256 ? 256 : 512;  // 2 issuers x double-buffered accumulator
     p.n_tiles = Cout_pad / BN;
     p.num_k = ksize * ksize * (Cin / p.BK);
     p.Cout = Cout;
@@ -744,63 +766,70 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
     const uint32_t fixed = staging + 4u * (uint32_t)Cout_pad + 3u * 1024u;   // staging + bias + slack
     size_t ring_bytes = 0;
     int nbar = 0;
+    // p.stages / p.a_stages / p.b_stages count stages PER (SUB-)RING: with two issuers the ring is split into one sub-ring per
+    // issuer (tile parity), with one issuer there is a single ring. p.a_slots / p.b_slots are the smem slots carved in total.
     if (!halo) {
-        // Pipeline stage = G K-blocks ("slots") behind one mbarrier pair: with narrow N an MMA retires in N/2 cycles, so a
+        // Pipeline stage = G K-blocks ("slots") behind one mbarrier pair: with narrow N an MMA retires in ~N/2 cycles, so a
         // stage must carry enough MMAs (>= ~512 tensor-pipe cycles) to amortise the issuer's per-handshake cost.
         const uint32_t slot_bytes = p.a_bytes + p.b_bytes;
         const uint32_t budget = 224u * 1024u - fixed;   // one fat CTA per SM
         int slots = (int)(budget / slot_bytes);
         if (slots > 16) slots = 16;
         const int kb_cycles = (p.BK / 16) * (BN / 2);
+        // two issuers only pay off for tiles with a single short burst (1x1 convs with K <= 64..128)
+        p.issuers = (p.num_k * kb_cycles <= 512 && slots >= 2 * p.num_k) ? 2 : 1;
+        const int rings = p.issuers;
         int gmax = 512 / kb_cycles;
         if (gmax < 1) gmax = 1;
-        if (gmax > slots / 4) gmax = slots / 4;   // keep >= 2 stages per sub-ring
+        if (gmax > slots / (2 * rings)) gmax = slots / (2 * rings);   // keep >= 2 stages per (sub-)ring
         if (gmax < 1) gmax = 1;
         int G = 1;
         for (int g = 1; g <= gmax; ++g)
             if (p.num_k % g == 0) G = g;
-        int stages = slots / (2 * G);   // stages per sub-ring (one sub-ring per MMA issuer / tile parity)
-        if (stages > 4) stages = 4;
+        int stages = slots / (rings * G);
+        if (stages > 8) stages = 8;
         if (stages < 1) stages = 1;
         p.kgroup = G;
         p.sgroup = 1;
-        p.stages = stages;
-        p.a_stages = p.b_stages = 2 * stages * G;   // smem carve-up counts slots; barriers are per stage (<= slots)
-        ring_bytes = (size_t)2 * stages * G * slot_bytes;
-        nbar = 4 * 2 * stages * G;
+        p.stages = p.a_stages = p.b_stages = stages;
+        p.a_slots = p.b_slots = rings * stages * G;
+        ring_bytes = (size_t)p.a_slots * slot_bytes;
+        nbar = 4 * p.a_slots;
     } else {
-        p.a_bytes = 18u * 8u * 128u;   // one column-shifted halo copy: 18 rows x 8 px x 64 ch bf16
-        p.a_tx = p.a_bytes;
+        p.a_tx = 18u * 10u * 128u;     // one halo copy: 18 rows x 10 px x 64 ch bf16
+        p.a_bytes = 23u * 1024u;       // slot stride (1 KB aligned)
         const uint32_t avail = 224u * 1024u - fixed;
         const uint32_t b_all = 9u * (uint32_t)p.cchunks * p.b_bytes;
-        // p.a_stages / p.b_stages are PER SUB-RING (one sub-ring per MMA issuer / tile parity); resident weights are shared
         int a_total;
-        if (b_all + 6u * p.a_bytes <= avail) {   // all weight taps stay resident; one full tile of halo copies per sub-ring
+        if (b_all + 2u * p.a_bytes <= avail) {   // all weight taps stay resident in shared memory for the CTA lifetime
             p.b_resident = 1;
+            p.issuers = 2;            // one 36-MMA burst per tile and chunk: ping-pong two issuers over the tiles
             p.b_stages = 9 * p.cchunks;
-            a_total = 6;
+            p.b_slots = p.b_stages;
+            a_total = (int)((avail - b_all) / p.a_bytes);
+            if (a_total > 8) a_total = 8;
+            a_total &= ~1;
+            p.a_stages = a_total / 2;
             p.sgroup = 3;
-            ring_bytes = (size_t)a_total * p.a_bytes + (size_t)p.b_stages * p.b_bytes;
-            nbar = 2 * a_total + 2 * p.b_stages;
         } else {
             p.b_resident = 0;
-            p.b_stages = 3;   // per sub-ring: the three filter-row taps of one filter column
+            p.issuers = 1;            // many bursts per tile: one issuer, one deep ring
+            p.b_stages = 6;           // two filter columns of three taps in flight
+            p.b_slots = 6;
             YSOD_CHECK_ARG(6u * p.b_bytes + 2u * p.a_bytes <= avail, "ysod_conv_tc_create: halo plan does not fit in shared memory (BN %d)", BN);
             a_total = (int)((avail - 6u * p.b_bytes) / p.a_bytes);
-            if (a_total > 6) a_total = 6;
-            a_total &= ~1;
+            if (a_total > 4) a_total = 4;
+            p.a_stages = a_total;
             p.sgroup = 1;
-            ring_bytes = (size_t)a_total * p.a_bytes + (size_t)6 * p.b_bytes;
-            nbar = 2 * a_total + 2 * 6;
         }
+        p.a_slots = a_total;
+        ring_bytes = (size_t)p.a_slots * p.a_bytes + (size_t)p.b_slots * p.b_bytes;
+        nbar = 2 * p.a_slots + 2 * p.b_slots;
         p.kgroup = 1;
-        p.a_stages = a_total / 2;
         p.stages = p.a_stages;
     }
-    if (!halo) { p.a_slots = p.b_slots = p.a_stages; p.a_stages = p.b_stages = p.stages; }
-    else { p.a_slots = 2 * p.a_stages; p.b_slots = p.b_resident ? p.b_stages : 2 * p.b_stages; }
     // ring + 1 KB alignment slack + barriers/slot + bias + alignment + output staging
-    c.smem = ring_bytes + 1024 + (8 * (size_t)nbar + 64) + 4 * (size_t)Cout_pad + 1024 + staging;
+    c.smem = ring_bytes + 1024 + (8 * (size_t)nbar + 128) + 4 * (size_t)Cout_pad + 1024 + staging;
     c.halo = halo;
     {
         int dev = 0, sms = 148;
@@ -822,7 +851,7 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
         cuuint64_t strides[3] = {(cuuint64_t)xcs * 2, (cuuint64_t)W * xcs * 2, (cuuint64_t)H * W * xcs * 2};
         cuuint32_t box[4] = {(cuuint32_t)p.BK, (cuuint32_t)(bestTW * stride), (cuuint32_t)(bestTH * stride), 1};
-        if (halo) { box[1] = 8; box[2] = 18; }   // one column-shifted halo copy (rows oh0-1 .. oh0+16)
+        if (halo) { box[1] = 10; box[2] = 18; }   // the halo copy: rows oh0-1 .. oh0+16, columns ow0-1 .. ow0+8
         cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
         CUresult r = enc(&c.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -892,7 +921,7 @@ int ysod_conv_tc_run(ysod_conv_tc* h, cudaStream_t stream) {
 int ysod_conv_tc_info(ysod_conv_tc* h, int* out8) {
     YSOD_CHECK_ARG(h && out8, "ysod_conv_tc_info: null");
     out8[0] = h->c.p.TH; out8[1] = h->c.p.TW; out8[2] = h->c.p.BN; out8[3] = h->c.p.BK; out8[4] = h->c.p.stages;
-    out8[5] = (int)h->c.grid.x; out8[6] = h->c.halo ? (100 + 10 * h->c.p.b_resident + h->c.p.b_stages % 10) : (10 * h->c.p.kgroup + h->c.p.n_tiles);
+    out8[5] = (int)h->c.grid.x; out8[6] = h->c.halo ? (1000 + 100 * h->c.p.issuers + 10 * h->c.p.b_resident + h->c.p.n_tiles) : (100 * h->c.p.issuers + 10 * h->c.p.kgroup + h->c.p.n_tiles);
     out8[7] = (int)h->c.smem;
     return YSOD_OK;
 }
