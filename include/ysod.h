@@ -66,6 +66,12 @@ int ysod_dwconv(const void* x, int dtype, int N, int H, int W, int C, int xcs, c
 int ysod_stem_conv(const float* img, int N, int H, int W, const float* w, const float* bias, int Cout, int k, int s, int pad,
                    void* out, int out_dtype, int ocs, int act, void* stream);
 
+/* tensor-core stem (3x3 / stride 2 / pad 1, Cout 16|32|64, bf16 out). src_fmt 0: img = (N,3,H,W) fp32 in [0,1] (tasks.py:129);
+ * src_fmt 1: img = (N,H,W,3) uint8 BGR frames, with BasePredictor.preprocess (engine/predictor.py:116-134: BGR->RGB, HWC->CHW,
+ * /255) fused into the load. wk = [Cout][32] bf16, column (r*3+s)*3+c, columns 27..31 zero. */
+int ysod_stem_mma(const void* img, int src_fmt, int N, int H, int W, const void* wk, const float* bias, int Cout, void* out, int ocs,
+                  int act, void* stream);
+
 /* ---- SE: smallobj_modules.py:57-92 ; CBAM: cbam_block.py:8-55 ; CoordAtt: ca_block.py:16-59 ------------------------- */
 int ysod_gap_partial(const void* x, int dtype, int N, int HW, int C, int xcs, int S, float* psum, float* pmax, void* stream);
 int ysod_se_gate(const float* psum, int N, int S, int HW, int C, const float* w1, const float* b1, const float* w2,

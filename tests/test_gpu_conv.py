@@ -174,3 +174,35 @@ def test_stem(out):
     torch.cuda.synchronize()
     tol = 1e-5 if out == "f32" else 1.0 / 128
     assert torch.allclose(od.float().cpu().permute(0, 3, 1, 2), ref, rtol=tol, atol=tol)
+
+
+@pytest.mark.parametrize("cout", [16, 32, 64])
+@pytest.mark.parametrize("src", ["f32_nchw", "u8_bgr_nhwc"])
+@pytest.mark.parametrize("W", [136, 138])   # W % 4 == 0: vectorised row loads; else the scalar-load variant
+def test_stem_mma(cout, src, W):
+    """tensor-core stem vs torch conv2d on the bf16-rounded operands; the uint8 source fuses BGR->RGB, HWC->CHW, /255."""
+    from yolo_sod_b200 import lib
+    gen = torch.Generator().manual_seed(3)
+    N, H = 2, 40   # ragged tiles in both directions (Ho=20 -> 5 row tiles, Wo=68/69 -> 2 column tiles)
+    if src == "u8_bgr_nhwc":
+        frames = torch.randint(0, 256, (N, H, W, 3), generator=gen, dtype=torch.uint8)
+        img = frames.flip(-1).permute(0, 3, 1, 2).float() / 255          # predictor.py:127-133
+        dev_img, fmt = frames.cuda(), 1
+    else:
+        img = torch.rand(N, 3, H, W, generator=gen)
+        dev_img, fmt = img.cuda(), 0
+    w = torch.randn(cout, 3, 3, 3, generator=gen) / 27 ** 0.5
+    b = torch.randn(cout, generator=gen) * 0.1
+    ref = F.silu(F.conv2d(img.bfloat16().float(), w.bfloat16().float(), b, 2, 1))
+    wk = torch.zeros(cout, 32)
+    wk[:, :27] = w.permute(0, 2, 3, 1).reshape(cout, 27)
+    wd, bd = wk.bfloat16().cuda(), b.cuda()
+    od = torch.full((N, H // 2, W // 2, cout + 8), 7.0, dtype=torch.bfloat16, device="cuda")
+    lib.call("ysod_stem_mma", lib.ptr(dev_img), fmt, N, H, W, lib.ptr(wd), lib.ptr(bd), cout, lib.ptr(od), cout + 8, lib.ACT["silu"],
+             lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert bool((od[..., cout:] == 7.0).all()), "kernel wrote outside its channel slice"
+    got = od[..., :cout].float().cpu().permute(0, 3, 1, 2)
+    err = (got - ref).abs()
+    tol = 1.0 / 128
+    assert bool((err <= tol * ref.abs() + tol * ref.abs().max() + 1e-5).all()), err.max().item()

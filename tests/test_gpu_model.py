@@ -138,6 +138,17 @@ def test_predict_end_to_end_matches_oracle_nms():
     assert sum(len(r) for r in res) > 0, "synthetic weights must produce detections"
 
 
+def test_uint8_frames_equal_preprocessed_tensor():
+    """(B,H,W,3) uint8 BGR frames through the fused stem == the reference's preprocess (predictor.py:127-133) + tensor input."""
+    spec, sd, model = _build(SOD, torch.bfloat16)
+    g = torch.Generator().manual_seed(5)
+    frames = torch.randint(0, 256, (2, 160, 160, 3), generator=g, dtype=torch.uint8)
+    x = frames.flip(-1).permute(0, 3, 1, 2).float() / 255
+    y_u8 = model(frames.cuda())[0].clone()
+    y_f = model(x.cuda())[0].clone()
+    assert torch.equal(y_u8, y_f)
+
+
 def test_missing_library_or_cpu_input_fails_loudly():
     from yolo_sod_b200 import ops, lib
     with pytest.raises(lib.YsodError):

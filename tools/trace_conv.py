@@ -37,3 +37,17 @@ for t, role, ev, tile, idx in rec:
     if 3 <= tile <= 7:
         col = {0: 0, 1: 1, 3: 2, 2: 3}[role]
         print(f"{t - t0:8d}  {' ' * 22 * col}{names.get((role, ev), (role, ev))} t{tile} #{idx}")
+
+# steady-state summary: per role, time between consecutive tiles at the role's last event
+import collections
+last = collections.defaultdict(dict)
+for t, role, ev, tile, idx in rec:
+    last[(role, ev)][tile] = t
+for (role, ev), d in sorted(last.items()):
+    tiles = sorted(d)
+    if len(tiles) < 4:
+        continue
+    ts = [d[k] for k in tiles]
+    deltas = [b - a for a, b in zip(ts, ts[1:])]
+    print(f"role {role} ev {ev}: {len(tiles)} tiles, first at {ts[0] - t0}, last at {ts[-1] - t0}, per-own-tile delta min {min(deltas)} "
+          f"median {sorted(deltas)[len(deltas) // 2]} max {max(deltas)}; deltas[:12]={deltas[:12]} deltas[-6:]={deltas[-6:]}")

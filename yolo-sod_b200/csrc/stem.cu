@@ -1,0 +1,236 @@
+// Stem convolution (3x3, stride 2, pad 1, Cin = 3 -> Cout in {16, 32, 64}) for the bf16 path, on tensor cores.
+//
+// Replaces (reference): layer 0 `Conv(3, c, 3, 2)` (ultralytics/nn/modules/conv.py:37-55, BN folded) together with what feeds
+// it: either the predictor's float image tensor (B,3,H,W) in [0,1] (engine/predictor.py:116-134, tensor branch), or -- for the
+// end-to-end path -- the predictor's raw uint8 BGR HWC frames, in which case `im[..., ::-1].transpose(0,3,1,2) / 255`
+// (predictor.py:127-133) is fused into the load.
+//
+// The op is HBM-bound (K = 27: 1.2-12 B of input and 64 B of output per output pixel) but 864 MACs per pixel make a CUDA-core
+// version FMA-bound at ~5x the memory time, so the MACs go to the tensor cores. K = 27 (padded to 32) is far too short for a
+// tcgen05/TMEM pipeline to pay off (one M=128,N=32 MMA pair per tile, accumulator round trip through TMEM); warp-level
+// mma.sync m16n8k16 with register accumulators is the right tool here: a warp owns 16 output pixels x Cout, gathers its
+// im2col A fragments straight from a shared-memory copy of the input patch and keeps the whole weight matrix in registers.
+// CTA tile = 4 output rows x 64 output columns; output is staged in shared memory and written as full 64-byte pixel rows.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TH = 4, TW = 64;                 // output tile
+constexpr int PH = 2 * TH + 1, PW = 2 * TW + 1;  // input patch 9 x 129
+constexpr int PWP = 132;                       // padded patch row (bf16 elements)
+constexpr int PLANE = PH * PWP;
+
+__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// patch offset of im2col column k = (r*3 + s)*3 + c  (k >= 27: padding column, weight is zero; read element 0)
+__device__ __forceinline__ int koff(int k) {
+    if (k >= 27) return 0;
+    const int tap = k / 3, c = k - tap * 3;
+    const int r = tap / 3, s = tap - r * 3;
+    return c * PLANE + r * PWP + s;
+}
+
+// SRC = 0: img is (N,3,H,W) fp32 in [0,1];  SRC = 1: img is (N,H,W,3) uint8 BGR in 0..255 (-> RGB, /255)
+template <int COUT, int SRC, bool VEC>
+__global__ void __launch_bounds__(256)
+stem_mma_kernel(const void* __restrict__ img_, const __nv_bfloat16* __restrict__ wk, const float* __restrict__ bias,
+                __nv_bfloat16* __restrict__ out, int H, int W, int Ho, int Wo, int ocs, int act) {
+    constexpr int NB = COUT / 8;
+    __shared__ __align__(16) __nv_bfloat16 patch[3 * PLANE];
+    __shared__ __align__(16) __nv_bfloat16 stage[TH * TW * (COUT + 8)];   // +8: keeps the 4-byte fragment stores conflict-free
+    const int n = blockIdx.z;
+    const int oh0 = blockIdx.y * TH, ow0 = blockIdx.x * TW;
+    const int ih0 = 2 * oh0 - 1, iw0 = 2 * ow0 - 1;
+    const int tid = threadIdx.x;
+
+    // ---- stage the input patch, converting to bf16 exactly like the reference's cast of the image tensor. Patch column j holds
+    //      image column 2*ow0 - 4 + j (so rows start 16-byte aligned); all loads of a thread are issued before any is used.
+    if (SRC == 0) {
+        const float* img = static_cast<const float*>(img_);
+        if (VEC) {
+            constexpr int NV = 3 * PH * 33;   // float4 pieces
+            float4 v[(NV + 255) / 256];
+#pragma unroll
+            for (int it = 0; it < (NV + 255) / 256; ++it) {
+                const int i = tid + it * 256;
+                v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < NV) {
+                    const int cr = i / 33, j = i - cr * 33;
+                    const int c = cr / PH, r = cr - c * PH;
+                    const int ih = ih0 + r, iw = 2 * ow0 - 4 + 4 * j;
+                    if (ih >= 0 && ih < H && iw >= 0 && iw < W) v[it] = __ldg(reinterpret_cast<const float4*>(img + (((size_t)n * 3 + c) * H + ih) * W + iw));
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < (NV + 255) / 256; ++it) {
+                const int i = tid + it * 256;
+                if (i < NV) {
+                    const int cr = i / 33, j = i - cr * 33;
+                    __nv_bfloat162* d = reinterpret_cast<__nv_bfloat162*>(&patch[cr * PWP + 4 * j]);
+                    d[0] = __floats2bfloat162_rn(v[it].x, v[it].y);
+                    d[1] = __floats2bfloat162_rn(v[it].z, v[it].w);
+                }
+            }
+        } else {
+            for (int i = tid; i < 3 * PH * PW; i += 256) {
+                const int c = i / (PH * PW);
+                const int rem = i - c * (PH * PW);
+                const int r = rem / PW, q = rem - r * PW;
+                const int ih = ih0 + r, iw = iw0 + q;
+                float v = 0.f;
+                if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(img + (((size_t)n * 3 + c) * H + ih) * W + iw);
+                patch[c * PLANE + r * PWP + q + 3] = __float2bfloat16_rn(v);
+            }
+        }
+    } else {
+        const uint8_t* img = static_cast<const uint8_t*>(img_);
+        if (VEC) {
+            constexpr int NV = PH * 99;   // 4-byte words: 132 pixels x 3 bytes per patch row
+            uint32_t v[(NV + 255) / 256];
+#pragma unroll
+            for (int it = 0; it < (NV + 255) / 256; ++it) {
+                const int i = tid + it * 256;
+                v[it] = 0u;
+                if (i < NV) {
+                    const int r = i / 99, j = i - r * 99;
+                    const int ih = ih0 + r;
+                    const int b0 = (2 * ow0 - 4) * 3 + 4 * j;          // byte offset inside the image row
+                    if (ih >= 0 && ih < H && b0 >= 0 && b0 + 3 < W * 3) v[it] = __ldg(reinterpret_cast<const uint32_t*>(img + ((size_t)n * H + ih) * W * 3 + b0));
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < (NV + 255) / 256; ++it) {
+                const int i = tid + it * 256;
+                if (i < NV) {
+                    const int r = i / 99, j = i - r * 99;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int bi = 4 * j + e;
+                        const int q = bi / 3, cs = bi - q * 3;           // cs = channel in the BGR source
+                        const float f = (float)((v[it] >> (8 * e)) & 0xffu) / 255.0f;
+                        patch[(2 - cs) * PLANE + r * PWP + q] = __float2bfloat16_rn(f);
+                    }
+                }
+            }
+        } else {
+            for (int i = tid; i < PH * PW * 3; i += 256) {
+                const int r = i / (PW * 3);
+                const int rem = i - r * (PW * 3);
+                const int q = rem / 3, cs = rem - q * 3;
+                const int ih = ih0 + r, iw = iw0 + q;
+                float v = 0.f;
+                if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = (float)__ldg(img + (((size_t)n * H + ih) * W + iw) * 3 + cs) / 255.0f;
+                patch[(2 - cs) * PLANE + r * PWP + q + 3] = __float2bfloat16_rn(v);
+            }
+        }
+    }
+
+    // ---- weights: B fragments of the [COUT][32] bf16 matrix, held in registers for the whole CTA
+    const int lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    uint32_t bf[NB][2][2];
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const __nv_bfloat16* wp = wk + (size_t)(nb * 8 + g) * 32 + ks * 16 + 2 * t;
+            bf[nb][ks][0] = *reinterpret_cast<const uint32_t*>(wp);
+            bf[nb][ks][1] = *reinterpret_cast<const uint32_t*>(wp + 8);
+        }
+    }
+    // im2col gather offsets of this thread's 16 A columns (k = ks*16 + {2t, 2t+1, 2t+8, 2t+9})
+    int ko[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        ko[ks][0] = koff(ks * 16 + 2 * t);
+        ko[ks][1] = koff(ks * 16 + 2 * t + 1);
+        ko[ks][2] = koff(ks * 16 + 2 * t + 8);
+        ko[ks][3] = koff(ks * 16 + 2 * t + 9);
+    }
+    float bv[NB][2];
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) { bv[nb][0] = __ldg(bias + nb * 8 + 2 * t); bv[nb][1] = __ldg(bias + nb * 8 + 2 * t + 1); }
+    __syncthreads();
+
+    const unsigned short* ps = reinterpret_cast<const unsigned short*>(patch);
+    // 16 m-tiles (16 consecutive output columns of one output row each); warp w takes m-tiles 2w, 2w+1
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi) {
+        const int mt = warp * 2 + mi;
+        const int row = mt >> 2, col0 = (mt & 3) * 16;
+        const int base0 = (2 * row) * PWP + 2 * (col0 + g) + 3;    // pixel g of the m-tile (patch column 3 = image column 2*ow0-1)
+        const int base1 = base0 + 16;                               // pixel g + 8
+        float acc[NB][4];
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) { acc[nb][0] = bv[nb][0]; acc[nb][1] = bv[nb][1]; acc[nb][2] = bv[nb][0]; acc[nb][3] = bv[nb][1]; }
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            uint32_t a[4];
+            a[0] = (uint32_t)ps[base0 + ko[ks][0]] | ((uint32_t)ps[base0 + ko[ks][1]] << 16);
+            a[1] = (uint32_t)ps[base1 + ko[ks][0]] | ((uint32_t)ps[base1 + ko[ks][1]] << 16);
+            a[2] = (uint32_t)ps[base0 + ko[ks][2]] | ((uint32_t)ps[base0 + ko[ks][3]] << 16);
+            a[3] = (uint32_t)ps[base1 + ko[ks][2]] | ((uint32_t)ps[base1 + ko[ks][3]] << 16);
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) mma_bf16_16816(acc[nb], a, bf[nb][ks][0], bf[nb][ks][1]);
+        }
+        // activation -> bf16 -> staging tile [pixel][COUT + 8]
+        const int p0 = row * TW + col0 + g;
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+            float v0 = acc[nb][0], v1 = acc[nb][1], v2 = acc[nb][2], v3 = acc[nb][3];
+            if (act == YSOD_ACT_SILU) {
+                v0 = v0 / (1.0f + __expf(-v0)); v1 = v1 / (1.0f + __expf(-v1));
+                v2 = v2 / (1.0f + __expf(-v2)); v3 = v3 / (1.0f + __expf(-v3));
+            }
+            *reinterpret_cast<__nv_bfloat162*>(&stage[(size_t)p0 * (COUT + 8) + nb * 8 + 2 * t]) = __floats2bfloat162_rn(v0, v1);
+            *reinterpret_cast<__nv_bfloat162*>(&stage[(size_t)(p0 + 8) * (COUT + 8) + nb * 8 + 2 * t]) = __floats2bfloat162_rn(v2, v3);
+        }
+    }
+    __syncthreads();
+    // ---- coalesced write-out: 16-byte pieces, consecutive threads -> consecutive channels then pixels
+    constexpr int PIECES = COUT / 8;
+    for (int i = tid; i < TH * TW * PIECES; i += 256) {
+        const int pix = i / PIECES, pc = i - pix * PIECES;
+        const int r = pix / TW, q = pix - r * TW;
+        const int oh = oh0 + r, ow = ow0 + q;
+        if (oh < Ho && ow < Wo) {
+            const uint4 v = *reinterpret_cast<const uint4*>(&stage[(size_t)pix * (COUT + 8) + pc * 8]);
+            *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + oh) * Wo + ow) * ocs + pc * 8) = v;
+        }
+    }
+}
+
+}  // namespace
+
+// img: src_fmt 0 = (N,3,H,W) fp32 in [0,1] (what DetectionModel.forward receives, tasks.py:129);
+//      src_fmt 1 = (N,H,W,3) uint8 BGR frames (what BasePredictor.preprocess receives, predictor.py:116-134).
+// wk: [Cout][32] bf16, column k = (r*3 + s)*3 + c (RGB channel c), columns 27..31 zero; bias fp32 [Cout] (BN folded).
+// out: NHWC bf16 view with pixel stride ocs. 3x3 / stride 2 / pad 1 only; H, W even.
+extern "C" int ysod_stem_mma(const void* img, int src_fmt, int N, int H, int W, const void* wk, const float* bias, int Cout, void* out,
+                             int ocs, int act, cudaStream_t stream) {
+    YSOD_CHECK_ARG(img && wk && bias && out, "ysod_stem_mma: null pointer");
+    YSOD_CHECK_ARG(Cout == 16 || Cout == 32 || Cout == 64, "ysod_stem_mma: Cout %d unsupported (16, 32, 64)", Cout);
+    YSOD_CHECK_ARG(src_fmt == 0 || src_fmt == 1, "ysod_stem_mma: bad source format %d", src_fmt);
+    YSOD_CHECK_ARG(H % 2 == 0 && W % 2 == 0 && ocs % 8 == 0 && ((uintptr_t)out % 16) == 0, "ysod_stem_mma: bad geometry / alignment");
+    YSOD_CHECK_ARG(act == YSOD_ACT_SILU || act == YSOD_ACT_NONE, "ysod_stem_mma: activation %d unsupported", act);
+    const int Ho = H / 2, Wo = W / 2;
+    dim3 grid(ysod_cdiv(Wo, TW), ysod_cdiv(Ho, TH), N);
+    const __nv_bfloat16* w = (const __nv_bfloat16*)wk;
+    __nv_bfloat16* o = (__nv_bfloat16*)out;
+    const bool vec = (W % 4 == 0) && ((uintptr_t)img % 16 == 0);   // aligned 16 B / 4 B row loads
+#define LAUNCH(CO, SRC)                                                                                          \
+    do {                                                                                                         \
+        if (vec) stem_mma_kernel<CO, SRC, true><<<grid, 256, 0, stream>>>(img, w, bias, o, H, W, Ho, Wo, ocs, act);   \
+        else stem_mma_kernel<CO, SRC, false><<<grid, 256, 0, stream>>>(img, w, bias, o, H, W, Ho, Wo, ocs, act);      \
+    } while (0)
+    if (Cout == 16) { if (src_fmt) LAUNCH(16, 1); else LAUNCH(16, 0); }
+    else if (Cout == 32) { if (src_fmt) LAUNCH(32, 1); else LAUNCH(32, 0); }
+    else { if (src_fmt) LAUNCH(64, 1); else LAUNCH(64, 0); }
+#undef LAUNCH
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}

@@ -53,9 +53,10 @@ class View:
 class Program:
     """A compiled forward for one (batch, H, W): buffers + launch list."""
 
-    def __init__(self, model: "B200DetectionModel", B: int, H: int, W: int):
+    def __init__(self, model: "B200DetectionModel", B: int, H: int, W: int, src_u8: bool = False):
         self.m = model
         self.B, self.H, self.W = B, H, W
+        self.src_u8 = src_u8   # input is (B,H,W,3) uint8 BGR frames (predictor.py:116-134) instead of (B,3,H,W) float
         self.dev = model.device
         self.dt = model.dtype
         self.code = _lib.BF16 if self.dt == torch.bfloat16 else _lib.F32
@@ -70,7 +71,10 @@ class Program:
         self._ctx = ""
         self.layer_out: Dict[int, View] = {}
         self.graph: Optional[torch.cuda.CUDAGraph] = None
-        self.img = torch.zeros((B, 3, H, W), device=self.dev, dtype=torch.float32)
+        if src_u8:
+            self.img = torch.zeros((B, H, W, 3), device=self.dev, dtype=torch.uint8)
+        else:
+            self.img = torch.zeros((B, 3, H, W), device=self.dev, dtype=torch.float32)
         self._build()
 
     # ---- buffers -----------------------------------------------------------------------------------------
@@ -458,9 +462,22 @@ class Program:
                     wf, bf = self.folded(P)
                     k, s = p["k"], p["s"]
                     assert p["g"] == 1 and wf.shape[1] == 3, "stem must be a dense conv on a 3-channel image"
-                    wd, bd = self.dev_t(wf.permute(0, 2, 3, 1)), self.dev_t(bf)
-                    self.emit("ysod_stem_conv", _lib.ptr(self.img), self.B, self.H, self.W, _lib.ptr(wd), _lib.ptr(bd), wf.shape[0], k, s,
-                              k // 2 if p["p"] is None else p["p"], o.ptr(), self.code, o.cs, _lib.ACT["silu" if p["act"] else "none"])
+                    pd = k // 2 if p["p"] is None else p["p"]
+                    co = wf.shape[0]
+                    if (self.code == _lib.BF16 and self.m.use_tc and k == 3 and s == 2 and pd == 1 and co in (16, 32, 64)
+                            and self.H % 2 == 0 and self.W % 2 == 0):
+                        # tensor-core stem: weights as [Cout][32] bf16, column (r*3+s)*3+c, zero padded
+                        wk = torch.zeros((co, 32), dtype=torch.float32)
+                        wk[:, :27] = wf.permute(0, 2, 3, 1).reshape(co, 27)
+                        wd, bd = self.dev_t(wk, torch.bfloat16), self.dev_t(bf)
+                        self.emit("ysod_stem_mma", _lib.ptr(self.img), 1 if self.src_u8 else 0, self.B, self.H, self.W, _lib.ptr(wd),
+                                  _lib.ptr(bd), co, o.ptr(), o.cs, _lib.ACT["silu" if p["act"] else "none"], desc=f"stem 3->{co}")
+                    else:
+                        if self.src_u8:
+                            raise NotImplementedError("uint8 frame input needs the bf16 tensor-core stem (3x3/s2, Cout 16/32/64)")
+                        wd, bd = self.dev_t(wf.permute(0, 2, 3, 1)), self.dev_t(bf)
+                        self.emit("ysod_stem_conv", _lib.ptr(self.img), self.B, self.H, self.W, _lib.ptr(wd), _lib.ptr(bd), co, k, s,
+                                  pd, o.ptr(), self.code, o.cs, _lib.ACT["silu" if p["act"] else "none"])
                 else:
                     self.conv_bn(x, P, p["k"], p["s"], p["g"], p["act"], out=o, pad=p["p"])
             elif t == "C2f":
@@ -591,14 +608,14 @@ class B200DetectionModel:
         self.nl = len(self.stride_list)
         self.programs: Dict[tuple, Program] = {}
 
-    def program(self, B, H, W) -> Program:
-        key = (B, H, W)
+    def program(self, B, H, W, src_u8=False) -> Program:
+        key = (B, H, W, bool(src_u8))
         if key not in self.programs:
             s = max(self.stride_list)
             if H % s or W % s:
                 raise ValueError(f"input {H}x{W} must be a multiple of the max stride {s}")
             with torch.cuda.device(self.device):
-                prog = Program(self, B, H, W)
+                prog = Program(self, B, H, W, src_u8)
                 if self.use_graph:
                     prog.capture()
             self.programs[key] = prog
@@ -606,11 +623,17 @@ class B200DetectionModel:
 
     @torch.no_grad()
     def forward(self, x, *args, **kwargs):
-        """x: (B,3,H,W) float tensor in [0,1] (NCHW, as the reference takes it). Returns (y, [raw maps])."""
-        if x.dim() != 4 or x.shape[1] != 3:
-            raise ValueError(f"expected (B,3,H,W), got {tuple(x.shape)}")
+        """x: (B,3,H,W) float tensor in [0,1] (NCHW, as the reference's forward takes it), or (B,H,W,3) uint8 BGR frames (what
+        BasePredictor.preprocess receives, predictor.py:116-134; BGR->RGB, HWC->CHW and /255 are fused into the stem kernel).
+        Returns (y, [raw maps])."""
+        u8 = x.dtype == torch.uint8
+        if x.dim() != 4 or (x.shape[3] if u8 else x.shape[1]) != 3:
+            raise ValueError(f"expected (B,3,H,W) float or (B,H,W,3) uint8, got {tuple(x.shape)} {x.dtype}")
         # host tensors are copied straight into the program's input buffer (pinned memory makes this asynchronous)
-        prog = self.program(int(x.shape[0]), int(x.shape[2]), int(x.shape[3]))
+        if u8:
+            prog = self.program(int(x.shape[0]), int(x.shape[1]), int(x.shape[2]), True)
+        else:
+            prog = self.program(int(x.shape[0]), int(x.shape[2]), int(x.shape[3]))
         with torch.cuda.device(self.device):
             return prog.run(x)
 
@@ -625,5 +648,6 @@ class B200DetectionModel:
 
     def layer_output(self, x, idx):
         """Debug/test helper: NCHW fp32 copy of layer `idx`'s output for the last forward with this shape."""
-        prog = self.program(int(x.shape[0]), int(x.shape[2]), int(x.shape[3]))
+        u8 = x.dtype == torch.uint8
+        prog = self.program(int(x.shape[0]), int(x.shape[1 if u8 else 2]), int(x.shape[2 if u8 else 3]), u8)
         return prog.layer_out[idx].torch_nchw().float()

@@ -127,14 +127,18 @@ class YOLO:
                 half=False, **kwargs) -> List[Results]:
         """Defaults follow cfg/default.yaml:51-54 and engine/model.py:547 (conf 0.25, iou 0.7, max_det 300)."""
         if not torch.is_tensor(source):
-            raise NotImplementedError("only (B,3,H,W) float tensors in [0,1] are accepted (predictor.py:116-134 tensor branch); "
+            raise NotImplementedError("only (B,3,H,W) float tensors in [0,1] (predictor.py:116-134 tensor branch) or (B,H,W,3) uint8 BGR frames are accepted; "
                                       "file/stream sources need the reference's ultralytics.data, which is out of scope")
         if half:
             raise NotImplementedError("half=True (fp16) is not provided")
         im = source if source.dim() == 4 else source[None]
-        preds = self.backend(im.float())
+        if im.dtype == torch.uint8:   # raw BGR HWC frames: preprocess (predictor.py:127-133) is fused into the stem kernel
+            preds = self.backend(im)
+            h, w = int(im.shape[1]), int(im.shape[2])
+        else:
+            preds = self.backend(im.float())
+            h, w = int(im.shape[2]), int(im.shape[3])
         dets = _ops.non_max_suppression(preds, conf, iou, classes=classes, agnostic=agnostic_nms, max_det=max_det)
-        h, w = int(im.shape[2]), int(im.shape[3])
         out = []
         for d in dets:
             d = d.clone()
