@@ -102,6 +102,14 @@ int ysod_window_reverse(const void* tok, int dtype, int ldt, int N, int H, int W
 int ysod_adaptive_pool_rows(const void* x, int dtype, int N, int H, int W, int C, int xcs, int OH, void* out, int ocs, void* stream);
 int ysod_bilinear_rows(const void* x, int dtype, int N, int IH, int W, int C, int xcs, int OH, void* out, int ocs, void* stream);
 
+/* Fully fused SwinBlock (blocks_transformer.py:133-171) for C = 64, 2 heads, 7x7 windows (the P2 level): dw3x3 -> window partition
+ * (zero padded) -> x + MHA(LN x) -> x + MLP(LN x) -> window reverse / crop -> pw1x1 + BN + SiLU + identity, one kernel.
+ * wbf16 (37440 bf16): dw[3][3][64] | in_proj_weight[192][64] | out_proj.weight[64][64] | mlp.0.weight[128][64] | mlp.2.weight[64][128] |
+ * pw.weight with BN folded [64][64].  pf32 (768 fp32): norm1.weight | norm1.bias | in_proj_bias | out_proj.bias | norm2.weight |
+ * norm2.bias | mlp.0.bias | mlp.2.bias | folded BN bias. */
+int ysod_swin64_fused(const void* x, int N, int H, int W, int xcs, const void* wbf16, const float* pf32, void* out, int ocs, int window,
+                      int heads, void* stream);
+
 /* ---- softmax attention core: nn.MultiheadAttention internals (blocks_transformer.py:116, a2_attn.py:53) and the manual
  *      path of AAttn (block.py:1348-1357). q/k/v addressed as ptr + batch*bs + token*ld + head*D (elements). ----------- */
 int ysod_mha_core(const void* q, const void* k, const void* v, int dtype, int batch, int L, int heads, int D, int ldq, int ldk,

@@ -138,6 +138,24 @@ def test_predict_end_to_end_matches_oracle_nms():
     assert sum(len(r) for r in res) > 0, "synthetic weights must produce detections"
 
 
+def test_fused_swin_block_matches_oracle_and_unfused_path():
+    """Layer 28 (P2 SwinBlock, 64 ch): the single fused kernel vs the oracle layer output and vs the eleven-launch path.
+    161 is not a multiple of 7 at 640^2 -> 160x160 maps exercise the zero-padded windows; 96^2 input -> 24x24 map (4x4 windows, ragged)."""
+    for sz in (96, 224):
+        spec, sd, m_f = _build(SOD, torch.bfloat16)
+        _, _, m_u = _build(SOD, torch.bfloat16, fuse_swin=False)
+        x = synth.synth_images(2, sz, seed=13)
+        m_f(x.cuda()); m_u(x.cuda())
+        torch.cuda.synchronize()
+        (_, _), layers = model_ref.forward(spec, sd, x, ycfg.strides_of(spec), return_layers=True)
+        got_f, got_u, ref = m_f.layer_output(x, 28).cpu(), m_u.layer_output(x, 28).cpu(), layers[28]
+        ok, e, m, l2 = _close(got_f, ref, 3e-2)
+        assert ok, ("fused vs oracle", sz, e, m, l2)
+        ok, e, m, l2u = _close(got_u, ref, 3e-2)
+        assert l2 <= l2u * 1.25 + 1e-3, ("fused path must not be less accurate than the unfused one", l2, l2u)
+        assert any(o[2] == "ysod_swin64_fused" for o in m_f.program(2, sz, sz).ops)
+
+
 def test_uint8_frames_equal_preprocessed_tensor():
     """(B,H,W,3) uint8 BGR frames through the fused stem == the reference's preprocess (predictor.py:127-133) + tensor input."""
     spec, sd, model = _build(SOD, torch.bfloat16)

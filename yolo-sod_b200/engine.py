@@ -230,6 +230,26 @@ class Program:
         sd = self.m.sd
         Cc, ws = x.C, p["window_size"]
         dww = sd[f"{P}.dw.weight"].float()
+        A = f"{P}.window_attn"
+        if (self.m.use_tc and self.code == _lib.BF16 and Cc == 64 and p["num_heads"] == 2 and ws == 7 and x.H > ws and x.W > ws
+                and self.m.fuse_swin):
+            # P2-level block: the whole SwinBlock is one kernel (csrc/swin_fused.cu)
+            g, b = sd[f"{P}.bn.weight"].float(), sd[f"{P}.bn.bias"].float()
+            sc = g / torch.sqrt(sd[f"{P}.bn.running_var"].float() + BN_EPS)
+            pw = sd[f"{P}.pw.weight"].float().view(64, 64) * sc.view(-1, 1)
+            wb = torch.cat([dww.view(64, 3, 3).permute(1, 2, 0).reshape(-1), sd[f"{A}.attn.in_proj_weight"].float().reshape(-1),
+                            sd[f"{A}.attn.out_proj.weight"].float().reshape(-1), sd[f"{A}.mlp.0.weight"].float().reshape(-1),
+                            sd[f"{A}.mlp.2.weight"].float().reshape(-1), pw.reshape(-1)])
+            pf = torch.cat([sd[f"{A}.norm1.weight"].float(), sd[f"{A}.norm1.bias"].float(), sd[f"{A}.attn.in_proj_bias"].float(),
+                            sd[f"{A}.attn.out_proj.bias"].float(), sd[f"{A}.norm2.weight"].float(), sd[f"{A}.norm2.bias"].float(),
+                            sd[f"{A}.mlp.0.bias"].float(), sd[f"{A}.mlp.2.bias"].float(),
+                            b - sd[f"{P}.bn.running_mean"].float() * sc])
+            assert wb.numel() == 37440 and pf.numel() == 768
+            wbd, pfd = self.dev_t(wb, torch.bfloat16), self.dev_t(pf)
+            T = x.N * (-(-x.H // ws)) * (-(-x.W // ws)) * ws * ws
+            self.emit("ysod_swin64_fused", x.ptr(), x.N, x.H, x.W, x.cs, _lib.ptr(wbd), _lib.ptr(pfd), out.ptr(), out.cs, ws, 2,
+                      flops=2.0 * T * (64 * 192 + 64 * 64 + 2 * 64 * 128 + 64 * 64 + 2 * 49 * 64), desc=f"swin64 fused @{x.H}x{x.W}")
+            return
         y = self.new(x.N, x.H, x.W, Cc)
         self.conv(x, dww, torch.zeros(Cc), 3, 1, Cc, "none", y)
         wh, ww = min(ws, x.H), min(ws, x.W)
@@ -238,7 +258,6 @@ class Program:
         else:
             nWh, nWw = -(-x.H // wh), -(-x.W // ww)
         T = x.N * nWh * nWw * wh * ww
-        A = f"{P}.window_attn"
         raw, nrm = self.new(1, 1, T, Cc), self.new(1, 1, T, Cc)
         g1, b1 = self.dev_t(sd[f"{A}.norm1.weight"]), self.dev_t(sd[f"{A}.norm1.bias"])
         self.emit("ysod_window_partition_ln", y.ptr(), self.code, x.N, x.H, x.W, Cc, y.cs, wh, ww, nWh, nWw, _lib.ptr(g1), _lib.ptr(b1),
@@ -584,7 +603,7 @@ class B200DetectionModel:
     """
 
     def __init__(self, cfg, state_dict, dtype=torch.bfloat16, device="cuda:0", use_tc=True, use_graph=True, nc=None,
-                 static_outputs=True):
+                 static_outputs=True, fuse_swin=True):
         _lib.require_cuda()
         _lib.load()
         self.spec = cfg if isinstance(cfg, _cfg.ModelSpec) else _cfg.get_spec(cfg, nc=nc)
@@ -597,6 +616,7 @@ class B200DetectionModel:
         self.device = torch.device(device)
         self.use_tc = use_tc
         self.use_graph = use_graph
+        self.fuse_swin = fuse_swin
         self.static_outputs = static_outputs
         self.stride_list = _cfg.strides_of(self.spec)
         self.stride = torch.tensor([float(s) for s in self.stride_list])

@@ -47,6 +47,7 @@ PROTOTYPES = {
     "ysod_window_reverse": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
     "ysod_adaptive_pool_rows": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
     "ysod_bilinear_rows": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
+    "ysod_swin64_fused": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, i32, i32, i32, vp]),
     "ysod_mha_core": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i64, i64, i64, f32, vp, i32, i64, vp]),
 }
 
