@@ -206,3 +206,25 @@ def test_stem_mma(cout, src, W):
     err = (got - ref).abs()
     tol = 1.0 / 128
     assert bool((err <= tol * ref.abs() + tol * ref.abs().max() + 1e-5).all()), err.max().item()
+
+
+@pytest.mark.parametrize("case", [(5, 49, 2, 32), (3, 49, 4, 64), (2, 64, 2, 64), (2, 33, 1, 32), (2, 160, 8, 64), (1, 400, 2, 32)],
+                         ids=lambda c: "x".join(str(v) for v in c))
+def test_mha_core(case):
+    """softmax(q k^T / sqrt(d)) v on packed [L][3E] projections (as nn.MultiheadAttention's in_proj lays them out) vs torch
+    fp32 on the bf16-rounded operands. L <= 64 takes the tensor-core window kernel, longer sequences the streaming one."""
+    from yolo_sod_b200 import lib
+    batch, L, heads, D = case
+    E = heads * D
+    gen = torch.Generator().manual_seed(4)
+    qkv = torch.randn(batch, L, 3 * E, generator=gen).bfloat16()
+    qf, kf, vf = [t.float().view(batch, L, heads, D).transpose(1, 2) for t in qkv.split(E, dim=-1)]
+    ref = torch.softmax(qf @ kf.transpose(-1, -2) / D ** 0.5, -1) @ vf            # (batch, heads, L, D)
+    ref = ref.transpose(1, 2).reshape(batch, L, E)
+    d = qkv.cuda()
+    o = torch.empty(batch, L, E, dtype=torch.bfloat16, device="cuda")
+    lib.call("ysod_mha_core", lib.ptr(d), lib.ptr(d, E), lib.ptr(d, 2 * E), lib.BF16, batch, L, heads, D, 3 * E, 3 * E, 3 * E,
+             L * 3 * E, L * 3 * E, L * 3 * E, 1.0 / D ** 0.5, lib.ptr(o), E, L * E, lib.stream_ptr())
+    torch.cuda.synchronize()
+    err = (o.float().cpu() - ref).abs()
+    assert bool((err <= 1.0 / 64 * ref.abs() + 1.0 / 64 * ref.abs().max()).all()), err.max().item()

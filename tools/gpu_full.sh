@@ -7,7 +7,7 @@ timeout 900 python bench.py --steps 20 --warmup 5 --profile-out gpurun_out/kerne
 timeout 300 python bench.py --quick --steps 2 --warmup 3 > gpurun_out/quick.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python bench.py --quick --steps 2 --warmup 3 > gpurun_out/ncu_quick.log 2>&1
 timeout 300 python bench.py --quick --steps 2 --warmup 3 > gpurun_out/quick2.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 300 -c 12 -o gpurun_out/prof_step_conv python bench.py --quick --steps 2 --warmup 3 > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"conv_tc_kernel|swin64_fused|stem_mma" -s 267 -c 89 -o gpurun_out/prof_step_conv python bench.py --quick --steps 2 --warmup 3 > gpurun_out/ncu_full.log 2>&1
 echo "== tests"; tail -n 8 gpurun_out/t_gpu.log
 echo "== bench"; cut -c1-1800 gpurun_out/bench.json; tail -n 3 gpurun_out/bench.err
 echo "== ncu"; tail -n 3 gpurun_out/ncu_quick.log; wc -l gpurun_out/launches.csv; tail -n 2 gpurun_out/ncu_full.log

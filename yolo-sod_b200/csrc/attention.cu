@@ -87,6 +87,117 @@ mha_core_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __res
     }
 }
 
+// ---- windowed variant: L <= 64 tokens (Swin 7x7 windows, 49 tokens), bf16, on warp-level tensor cores --------------------------
+// One CTA of 4 warps per (batch = window, head); warp w owns query rows 16w..16w+15. Q, K ([token][D]) and V^T ([D][token]) are
+// staged in shared memory (padded rows: conflict-free 32-bit fragment loads), S = QK^T and O = PV are mma.sync m16n8k16 with
+// fp32 accumulators, the softmax lives in registers (quad shuffles), P is re-packed from the S accumulators into A fragments.
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t ld32s(const __nv_bfloat16* p) { return *reinterpret_cast<const uint32_t*>(p); }
+__device__ __forceinline__ uint32_t pack2bf(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int D>
+__global__ void __launch_bounds__(128)
+mha_win_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v, int L,
+               int ldq, int ldk, int ldv, long long bsq, long long bsk, long long bsv, float scale, __nv_bfloat16* __restrict__ out,
+               int ldo, long long bso) {
+    constexpr int LDQ = D + 8, LDV = 64 + 8;
+    __shared__ __align__(16) __nv_bfloat16 Qs[64 * LDQ];
+    __shared__ __align__(16) __nv_bfloat16 Ks[64 * LDQ];
+    __shared__ __align__(16) __nv_bfloat16 Vt[D * LDV];
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const __nv_bfloat16* qb = q + (size_t)b * bsq + h * D;
+    const __nv_bfloat16* kb = k + (size_t)b * bsk + h * D;
+    const __nv_bfloat16* vb = v + (size_t)b * bsv + h * D;
+    for (int i = tid; i < 64 * (D / 8); i += 128) {
+        const int r = i / (D / 8), pc = i - r * (D / 8);
+        uint4 qv = make_uint4(0, 0, 0, 0), kv = qv, vv = qv;
+        if (r < L) {
+            qv = *reinterpret_cast<const uint4*>(qb + (size_t)r * ldq + pc * 8);
+            kv = *reinterpret_cast<const uint4*>(kb + (size_t)r * ldk + pc * 8);
+            vv = *reinterpret_cast<const uint4*>(vb + (size_t)r * ldv + pc * 8);
+        }
+        *reinterpret_cast<uint4*>(&Qs[r * LDQ + pc * 8]) = qv;
+        *reinterpret_cast<uint4*>(&Ks[r * LDQ + pc * 8]) = kv;
+        const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) Vt[(pc * 8 + e) * LDV + r] = ve[e];
+    }
+    __syncthreads();
+    const int row0 = warp * 16 + g;
+    uint32_t qf[D / 16][4];
+#pragma unroll
+    for (int ks = 0; ks < D / 16; ++ks) {
+        qf[ks][0] = ld32s(&Qs[row0 * LDQ + ks * 16 + 2 * t]);
+        qf[ks][1] = ld32s(&Qs[(row0 + 8) * LDQ + ks * 16 + 2 * t]);
+        qf[ks][2] = ld32s(&Qs[row0 * LDQ + ks * 16 + 8 + 2 * t]);
+        qf[ks][3] = ld32s(&Qs[(row0 + 8) * LDQ + ks * 16 + 8 + 2 * t]);
+    }
+    float s[8][4];
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+        s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
+        const __nv_bfloat16* kr = &Ks[(nb * 8 + g) * LDQ + 2 * t];
+#pragma unroll
+        for (int ks = 0; ks < D / 16; ++ks) mma16816(s[nb], qf[ks], ld32s(kr + ks * 16), ld32s(kr + ks * 16 + 8));
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+        const int key = nb * 8 + 2 * t;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s[nb][e] *= scale;
+        if (key >= L) { s[nb][0] = -INFINITY; s[nb][2] = -INFINITY; }
+        if (key + 1 >= L) { s[nb][1] = -INFINITY; s[nb][3] = -INFINITY; }
+        mx0 = fmaxf(mx0, fmaxf(s[nb][0], s[nb][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nb][2], s[nb][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+        s[nb][0] = __expf(s[nb][0] - mx0); s[nb][1] = __expf(s[nb][1] - mx0);
+        s[nb][2] = __expf(s[nb][2] - mx1); s[nb][3] = __expf(s[nb][3] - mx1);
+        l0 += s[nb][0] + s[nb][1];
+        l1 += s[nb][2] + s[nb][3];
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+    uint32_t pf[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        pf[i][0] = pack2bf(s[2 * i][0], s[2 * i][1]);
+        pf[i][1] = pack2bf(s[2 * i][2], s[2 * i][3]);
+        pf[i][2] = pack2bf(s[2 * i + 1][0], s[2 * i + 1][1]);
+        pf[i][3] = pack2bf(s[2 * i + 1][2], s[2 * i + 1][3]);
+    }
+    __syncthreads();   // every warp has read its Q rows: Qs becomes the output staging tile
+#pragma unroll
+    for (int nb = 0; nb < D / 8; ++nb) {
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        const __nv_bfloat16* vr = &Vt[(nb * 8 + g) * LDV + 2 * t];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mma16816(o, pf[i], ld32s(vr + i * 16), ld32s(vr + i * 16 + 8));
+        *reinterpret_cast<uint32_t*>(&Qs[row0 * LDQ + nb * 8 + 2 * t]) = pack2bf(o[0] * inv0, o[1] * inv0);
+        *reinterpret_cast<uint32_t*>(&Qs[(row0 + 8) * LDQ + nb * 8 + 2 * t]) = pack2bf(o[2] * inv1, o[3] * inv1);
+    }
+    __syncthreads();
+    __nv_bfloat16* ob = out + (size_t)b * bso + h * D;
+    for (int i = tid; i < L * (D / 8); i += 128) {
+        const int r = i / (D / 8), pc = i - r * (D / 8);
+        *reinterpret_cast<uint4*>(ob + (size_t)r * ldo + pc * 8) = *reinterpret_cast<const uint4*>(&Qs[r * LDQ + pc * 8]);
+    }
+}
+
 }  // namespace
 
 extern "C" int ysod_mha_core(const void* q, const void* k, const void* v, int dtype, int batch, int L, int heads, int D, int ldq,
@@ -95,6 +206,18 @@ extern "C" int ysod_mha_core(const void* q, const void* k, const void* v, int dt
     YSOD_CHECK_ARG(q && k && v && out, "ysod_mha_core: null pointer");
     YSOD_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "ysod_mha_core: row strides must be multiples of 8");
     YSOD_CHECK_ARG(batch <= 65535 || true, "ysod_mha_core: batch");
+    if (dtype == YSOD_BF16 && L <= 64 && (D == 32 || D == 64) && batch <= 65535 && ((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 &&
+        ((uintptr_t)v % 16) == 0 && ((uintptr_t)out % 16) == 0 && bsq % 8 == 0 && bsk % 8 == 0 && bsv % 8 == 0 && bso % 8 == 0) {
+        dim3 wgrid(heads, batch);
+        if (D == 32)
+            mha_win_kernel<32><<<wgrid, 128, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, L, ldq, ldk, ldv,
+                                                      bsq, bsk, bsv, scale, (__nv_bfloat16*)out, ldo, bso);
+        else
+            mha_win_kernel<64><<<wgrid, 128, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, L, ldq, ldk, ldv,
+                                                      bsq, bsk, bsv, scale, (__nv_bfloat16*)out, ldo, bso);
+        YSOD_LAUNCH_CHECK();
+        return YSOD_OK;
+    }
     dim3 grid(ysod_cdiv(L, 64), heads, batch);
     YSOD_CHECK_ARG(batch <= 65535 && heads <= 65535, "ysod_mha_core: grid too large (batch %d)", batch);
 #define LAUNCH(T, DD) \

@@ -31,9 +31,23 @@ __global__ void gap_partial_kernel(const T* __restrict__ x, int HW, int C, int x
 #pragma unroll
     for (int e = 0; e < 8; ++e) { su[e] = 0.f; mx[e] = -INFINITY; }
     if (pl < PL) {
-        for (int p = p0 + pl; p < p1; p += PL) {
+        const T* xb = x + (size_t)n * HW * xcs + cg * 8;
+        int p = p0 + pl;
+        for (; p + 3 * PL < p1; p += 4 * PL) {   // four independent 16 B loads in flight per thread
+            float v0[8], v1[8], v2[8], v3[8];
+            ysod_vec8<T>::load(xb + (size_t)p * xcs, v0);
+            ysod_vec8<T>::load(xb + (size_t)(p + PL) * xcs, v1);
+            ysod_vec8<T>::load(xb + (size_t)(p + 2 * PL) * xcs, v2);
+            ysod_vec8<T>::load(xb + (size_t)(p + 3 * PL) * xcs, v3);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                su[e] += (v0[e] + v1[e]) + (v2[e] + v3[e]);
+                mx[e] = fmaxf(fmaxf(mx[e], fmaxf(v0[e], v1[e])), fmaxf(v2[e], v3[e]));
+            }
+        }
+        for (; p < p1; p += PL) {
             float v[8];
-            ysod_vec8<T>::load(x + ((size_t)n * HW + p) * xcs + cg * 8, v);
+            ysod_vec8<T>::load(xb + (size_t)p * xcs, v);
 #pragma unroll
             for (int e = 0; e < 8; ++e) { su[e] += v[e]; mx[e] = fmaxf(mx[e], v[e]); }
         }
@@ -124,23 +138,43 @@ __global__ void cbam_gate_kernel(const float* __restrict__ psum, const float* __
     }
 }
 
-// out = x * gate[n][c]
+// Streaming-kernel indexing: a thread keeps one fixed 8-channel group (cg) and walks pixels pix0, pix0 + pstep, ... with 32-bit
+// arithmetic (the grid size is a multiple of C/8 threads), so the loops contain no 64-bit divisions.
+struct StreamIdx {
+    unsigned cg, pix0, pstep;
+    __device__ __forceinline__ StreamIdx(int c8n) {
+        const unsigned gtid = blockIdx.x * blockDim.x + threadIdx.x;
+        cg = gtid % (unsigned)c8n;
+        pix0 = gtid / (unsigned)c8n;
+        pstep = (gridDim.x * blockDim.x) / (unsigned)c8n;
+    }
+};
+
+// out = x * gate[n][c]. Grid-stride, four independent 16 B loads in flight per thread.
 template <typename T>
 __global__ void scale_channels_kernel(const T* __restrict__ x, int HW, int C, int xcs, const float* __restrict__ gate,
-                                      T* __restrict__ out, int ocs, long long total) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int c8n = C >> 3;
-    const int cg = (int)(idx % c8n);
-    const long long pix = idx / c8n;
-    const int n = (int)(pix / HW);
-    float v[8];
-    ysod_vec8<T>::load(x + (size_t)pix * xcs + cg * 8, v);
-    const float4 g0 = *reinterpret_cast<const float4*>(gate + (size_t)n * C + cg * 8);
-    const float4 g1 = *reinterpret_cast<const float4*>(gate + (size_t)n * C + cg * 8 + 4);
-    v[0] *= g0.x; v[1] *= g0.y; v[2] *= g0.z; v[3] *= g0.w;
-    v[4] *= g1.x; v[5] *= g1.y; v[6] *= g1.z; v[7] *= g1.w;
-    ysod_vec8<T>::store(out + (size_t)pix * ocs + cg * 8, v);
+                                      T* __restrict__ out, int ocs, unsigned npix) {
+    const StreamIdx si(C >> 3);
+    for (unsigned p0 = si.pix0; p0 < npix; p0 += 4 * si.pstep) {
+        float v[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned pix = p0 + u * si.pstep;
+            if (pix < npix) ysod_vec8<T>::load(x + (size_t)pix * xcs + si.cg * 8, v[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned pix = p0 + u * si.pstep;
+            if (pix < npix) {
+                const unsigned n = pix / (unsigned)HW;
+                const float4 g0 = *reinterpret_cast<const float4*>(gate + (size_t)n * C + si.cg * 8);
+                const float4 g1 = *reinterpret_cast<const float4*>(gate + (size_t)n * C + si.cg * 8 + 4);
+                v[u][0] *= g0.x; v[u][1] *= g0.y; v[u][2] *= g0.z; v[u][3] *= g0.w;
+                v[u][4] *= g1.x; v[u][5] *= g1.y; v[u][6] *= g1.z; v[u][7] *= g1.w;
+                ysod_vec8<T>::store(out + (size_t)pix * ocs + si.cg * 8, v[u]);
+            }
+        }
+    }
 }
 
 // CBAM spatial statistics of x*gate: stats[pix] = (mean_c, max_c). A group of G lanes (G = min(C/8,32)) per pixel.
@@ -223,6 +257,110 @@ __global__ void cbam_apply_kernel(const T* __restrict__ x, int H, int W, int C, 
     }
 }
 
+// CBAM spatial statistics, streaming variant for C <= 256 (G = C/8 lanes own one pixel, one 16 B load each): grid-stride with
+// four pixels in flight per lane group; the trip count is uniform across the grid so the shuffles stay warp-converged.
+template <typename T>
+__global__ void cbam_stats_stream_kernel(const T* __restrict__ x, int HW, int C, int xcs, const float* __restrict__ gate,
+                                         float2* __restrict__ stats, long long npix, int iters) {
+    const int G = C >> 3;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % G;
+    const long long ngroups = ((long long)gridDim.x * blockDim.x) / G;
+    const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    for (int it = 0; it < iters; ++it) {
+        const long long pix0 = gid + (long long)it * 4 * ngroups;
+        float v[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long pix = pix0 + u * ngroups;
+            if (pix < npix) ysod_vec8<T>::load(x + (size_t)pix * xcs + gl * 8, v[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long pix = pix0 + u * ngroups;
+            float su = 0.f, mx = -INFINITY;
+            if (pix < npix) {
+                const float* g = gate + (size_t)(pix / HW) * C + gl * 8;
+                const float4 g0 = *reinterpret_cast<const float4*>(g), g1 = *reinterpret_cast<const float4*>(g + 4);
+                const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float tv = v[u][e] * gg[e];
+                    su += tv;
+                    mx = fmaxf(mx, tv);
+                }
+            }
+            for (int o = G >> 1; o > 0; o >>= 1) {
+                su += __shfl_xor_sync(0xffffffffu, su, o);
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            }
+            if (pix < npix && gl == 0) stats[pix] = make_float2(su / (float)C, mx);
+        }
+    }
+}
+
+// CBAM apply: sa = sigmoid(conv7x7([mean,max])) ; out = x * gate * sa. One CTA = a 16 x 16 pixel tile of one image: the
+// (16+6)^2 statistics halo is staged in shared memory, each thread evaluates the 7x7x2 filter for one pixel, then the CTA
+// streams the tile's channels with four 16 B loads in flight per thread.
+template <typename T>
+__global__ void __launch_bounds__(256)
+cbam_apply_tile_kernel(const T* __restrict__ x, int H, int W, int C, int xcs, const float* __restrict__ gate,
+                       const float2* __restrict__ stats, const float* __restrict__ wsp, T* __restrict__ out, int ocs) {
+    constexpr int TS = 16, HALO = 3, PS = TS + 2 * HALO;
+    __shared__ float2 st[PS * PS];
+    __shared__ float swsp[2 * 49];
+    __shared__ float sa_s[TS * TS];
+    const int n = blockIdx.z, h0 = blockIdx.y * TS, w0 = blockIdx.x * TS;
+    const int tid = threadIdx.x;
+    if (tid < 98) swsp[tid] = wsp[tid];
+    for (int i = tid; i < PS * PS; i += 256) {
+        const int ih = h0 - HALO + i / PS, iw = w0 - HALO + i % PS;
+        st[i] = (ih >= 0 && ih < H && iw >= 0 && iw < W) ? stats[((size_t)n * H + ih) * W + iw] : make_float2(0.f, 0.f);
+    }
+    __syncthreads();
+    {
+        const int ph = tid / TS, pw = tid % TS;
+        float a = 0.f;
+#pragma unroll
+        for (int r = 0; r < 7; ++r)
+#pragma unroll
+            for (int q = 0; q < 7; ++q) {
+                const float2 v = st[(ph + r) * PS + pw + q];
+                a = fmaf(swsp[r * 7 + q], v.x, a);
+                a = fmaf(swsp[49 + r * 7 + q], v.y, a);
+            }
+        sa_s[tid] = ysod_sigmoid(a);
+    }
+    __syncthreads();
+    const int c8n = C >> 3;
+    const int total = TS * TS * c8n;
+    const float* gn = gate + (size_t)n * C;
+    for (int base = tid; base < total; base += 4 * 256) {
+        float v[4][8];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + u * 256;
+            const int p = i / c8n, cg = i - p * c8n;
+            const int h = h0 + p / TS, w = w0 + p % TS;
+            ok[u] = (i < total) && h < H && w < W;
+            if (ok[u]) ysod_vec8<T>::load(x + (((size_t)n * H + h) * W + w) * xcs + cg * 8, v[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (!ok[u]) continue;
+            const int i = base + u * 256;
+            const int p = i / c8n, cg = i - p * c8n;
+            const int h = h0 + p / TS, w = w0 + p % TS;
+            const float sa = sa_s[p];
+            const float4 g0 = *reinterpret_cast<const float4*>(gn + cg * 8), g1 = *reinterpret_cast<const float4*>(gn + cg * 8 + 4);
+            v[u][0] *= g0.x * sa; v[u][1] *= g0.y * sa; v[u][2] *= g0.z * sa; v[u][3] *= g0.w * sa;
+            v[u][4] *= g1.x * sa; v[u][5] *= g1.y * sa; v[u][6] *= g1.z * sa; v[u][7] *= g1.w * sa;
+            ysod_vec8<T>::store(out + (((size_t)n * H + h) * W + w) * ocs + cg * 8, v[u]);
+        }
+    }
+}
+
 // CoordAtt strip pools -> pooled[n][H + W][C] fp32: rows [0,H) = mean over w, rows [H,H+W) = mean over h (ca_block.py:42-45)
 template <typename T>
 __global__ void ca_pool_kernel(const T* __restrict__ x, int H, int W, int C, int xcs, float* __restrict__ pooled) {
@@ -281,25 +419,33 @@ __global__ void ca_gate_kernel(const float* __restrict__ pooled, int H, int W, i
     }
 }
 
-// out = x * a_w[n][w][c] * a_h[n][h][c]  (ca_block.py:57)
+// out = x * a_w[n][w][c] * a_h[n][h][c]  (ca_block.py:57). Grid-stride, four independent 16 B loads in flight per thread.
 template <typename T>
 __global__ void ca_apply_kernel(const T* __restrict__ x, int H, int W, int C, int xcs, const float* __restrict__ att,
-                                T* __restrict__ out, int ocs, long long total) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int c8n = C >> 3;
-    const int cg = (int)(idx % c8n);
-    const long long pix = idx / c8n;
-    const int w = (int)(pix % W);
-    const int h = (int)((pix / W) % H);
-    const int n = (int)(pix / ((long long)W * H));
-    float v[8], ah[8], aw[8];
-    ysod_vec8<T>::load(x + (size_t)pix * xcs + cg * 8, v);
-    ysod_vec8<float>::load(att + ((size_t)n * (H + W) + h) * C + cg * 8, ah);
-    ysod_vec8<float>::load(att + ((size_t)n * (H + W) + H + w) * C + cg * 8, aw);
+                                T* __restrict__ out, int ocs, unsigned npix) {
+    const StreamIdx si(C >> 3);
+    for (unsigned p0 = si.pix0; p0 < npix; p0 += 4 * si.pstep) {
+        float v[4][8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = v[e] * aw[e] * ah[e];
-    ysod_vec8<T>::store(out + (size_t)pix * ocs + cg * 8, v);
+        for (int u = 0; u < 4; ++u) {
+            const unsigned pix = p0 + u * si.pstep;
+            if (pix < npix) ysod_vec8<T>::load(x + (size_t)pix * xcs + si.cg * 8, v[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned pix = p0 + u * si.pstep;
+            if (pix < npix) {
+                const unsigned row = pix / (unsigned)W, w = pix - row * (unsigned)W;
+                const unsigned n = row / (unsigned)H, h = row - n * (unsigned)H;
+                float ah[8], aw[8];
+                ysod_vec8<float>::load(att + ((size_t)n * (H + W) + h) * C + si.cg * 8, ah);
+                ysod_vec8<float>::load(att + ((size_t)n * (H + W) + H + w) * C + si.cg * 8, aw);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[u][e] = v[u][e] * aw[e] * ah[e];
+                ysod_vec8<T>::store(out + (size_t)pix * ocs + si.cg * 8, v[u]);
+            }
+        }
+    }
 }
 
 // SPPF: o1 = max 5x5, o2 = max 9x9, o3 = max 13x13 of y0 (== three chained 5x5/s1/p2 max pools)
@@ -389,26 +535,28 @@ sppf_plane_kernel(const T* __restrict__ y0, int H, int W, int xcs, int k, T* __r
     }
 }
 
-// nearest-neighbour upsample by `scale` (1 = plain slice copy) into a channel slice
+// nearest-neighbour upsample by `scale` (1 = plain slice copy) into a channel slice. Grid-stride, four loads in flight.
 template <typename T>
 __global__ void upsample_copy_kernel(const T* __restrict__ x, int H, int W, int C, int xcs, int scale, T* __restrict__ out,
-                                     int ocs, long long total) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int c8n = C >> 3;
-    const int cg = (int)(idx % c8n);
-    const long long pix = idx / c8n;
-    const int Wo = W * scale, Ho = H * scale;
-    const int ow = (int)(pix % Wo);
-    const int oh = (int)((pix / Wo) % Ho);
-    const int n = (int)(pix / ((long long)Wo * Ho));
-    const uint4* src = reinterpret_cast<const uint4*>(x + (((size_t)n * H + oh / scale) * W + ow / scale) * xcs + cg * 8);
-    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)pix * ocs + cg * 8);
-    if (sizeof(T) == 2) {
-        dst[0] = src[0];
-    } else {
-        dst[0] = src[0];
-        dst[1] = src[1];
+                                     int ocs, unsigned npix) {
+    const StreamIdx si(C >> 3);
+    const unsigned Wo = W * scale, Ho = H * scale;
+    for (unsigned p0 = si.pix0; p0 < npix; p0 += 4 * si.pstep) {
+        float v[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned pix = p0 + u * si.pstep;
+            if (pix < npix) {
+                const unsigned row = pix / Wo, ow = pix - row * Wo;
+                const unsigned n = row / Ho, oh = row - n * Ho;
+                ysod_vec8<T>::load(x + (((size_t)n * H + oh / scale) * W + ow / scale) * xcs + si.cg * 8, v[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned pix = p0 + u * si.pstep;
+            if (pix < npix) ysod_vec8<T>::store(out + (size_t)pix * ocs + si.cg * 8, v[u]);
+        }
     }
 }
 
@@ -483,23 +631,94 @@ __global__ void layernorm_kernel(const T* __restrict__ x, long long rows, int C,
     }
 }
 
-// window tokens -> NHWC (crop the padding) (blocks_transformer.py:49-79,125-129)
+// LayerNorm, streaming variant for C <= 256 (G = C/8 lanes own one row, one 16 B load each): grid-stride with four rows in
+// flight per lane group and a grid-uniform trip count (the shuffles stay warp-converged). GATHER = window-partition gather.
+template <typename T, bool GATHER>
+__global__ void layernorm_stream_kernel(const T* __restrict__ x, long long rows, int C, int ldx, const float* __restrict__ gamma,
+                                        const float* __restrict__ beta, float eps, T* __restrict__ out, int ldo, int iters,
+                                        int H, int W, int wh, int ww, int nWh, int nWw, T* __restrict__ raw_out) {
+    const int G = C >> 3;
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % G;
+    const long long ngroups = ((long long)gridDim.x * blockDim.x) / G;
+    const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    float gm[8], bt[8];
+    ysod_vec8<float>::load(gamma + gl * 8, gm);
+    ysod_vec8<float>::load(beta + gl * 8, bt);
+    const float invC = 1.0f / (float)C;
+    for (int it = 0; it < iters; ++it) {
+        const long long row0 = gid + (long long)it * 4 * ngroups;
+        float v[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long row = row0 + u * ngroups;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[u][e] = 0.f;
+            if (row < rows) {
+                const T* src;
+                if (GATHER) {
+                    const int tpw = wh * ww;
+                    const int t = (int)(row % tpw);
+                    const long long win = row / tpw;
+                    const int wj = (int)(win % nWw);
+                    const int wi = (int)((win / nWw) % nWh);
+                    const int n = (int)(win / ((long long)nWw * nWh));
+                    const int h = wi * wh + t / ww, w = wj * ww + t % ww;
+                    src = (h < H && w < W) ? x + (((size_t)n * H + h) * W + w) * ldx : nullptr;   // else zero-padded token
+                } else {
+                    src = x + (size_t)row * ldx;
+                }
+                if (src) ysod_vec8<T>::load(src + gl * 8, v[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long row = row0 + u * ngroups;
+            float s = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s += v[u][e];
+            for (int o = G >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float mean = s * invC;
+            float q = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { const float d = v[u][e] - mean; q += d * d; }
+            for (int o = G >> 1; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+            const float rstd = rsqrtf(q * invC + eps);
+            if (row < rows) {
+                if (GATHER && raw_out) ysod_vec8<T>::store(raw_out + (size_t)row * ldo + gl * 8, v[u]);
+                float o8[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o8[e] = (v[u][e] - mean) * rstd * gm[e] + bt[e];
+                ysod_vec8<T>::store(out + (size_t)row * ldo + gl * 8, o8);
+            }
+        }
+    }
+}
+
+// window tokens -> NHWC (crop the padding) (blocks_transformer.py:49-79,125-129). Grid-stride, four loads in flight.
 template <typename T>
 __global__ void window_reverse_kernel(const T* __restrict__ tok, int ldt, int H, int W, int C, int wh, int ww, int nWh, int nWw,
-                                      T* __restrict__ out, int ocs, long long total) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int c8n = C >> 3;
-    const int cg = (int)(idx % c8n);
-    const long long pix = idx / c8n;
-    const int w = (int)(pix % W);
-    const int h = (int)((pix / W) % H);
-    const int n = (int)(pix / ((long long)W * H));
-    const long long win = ((long long)n * nWh + h / wh) * nWw + w / ww;
-    const long long row = win * (wh * ww) + (h % wh) * ww + (w % ww);
-    float v[8];
-    ysod_vec8<T>::load(tok + (size_t)row * ldt + cg * 8, v);
-    ysod_vec8<T>::store(out + (size_t)pix * ocs + cg * 8, v);
+                                      T* __restrict__ out, int ocs, unsigned npix) {
+    const StreamIdx si(C >> 3);
+    for (unsigned p0 = si.pix0; p0 < npix; p0 += 4 * si.pstep) {
+        float v[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned pix = p0 + u * si.pstep;
+            if (pix < npix) {
+                const unsigned r = pix / (unsigned)W, w = pix - r * (unsigned)W;
+                const unsigned n = r / (unsigned)H, h = r - n * (unsigned)H;
+                const unsigned win = (n * nWh + h / wh) * nWw + w / ww;
+                const size_t row = (size_t)win * (wh * ww) + (h % wh) * ww + (w % ww);
+                ysod_vec8<T>::load(tok + row * ldt + si.cg * 8, v[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned pix = p0 + u * si.pstep;
+            if (pix < npix) ysod_vec8<T>::store(out + (size_t)pix * ocs + si.cg * 8, v[u]);
+        }
+    }
 }
 
 // adaptive_avg_pool2d over H only: (H, W) -> (OH, W); bin i = [floor(i*H/OH), ceil((i+1)*H/OH))
@@ -556,6 +775,14 @@ __global__ void bilinear_rows_kernel(const T* __restrict__ x, int IH, int W, int
 }
 
 inline int blocks_for(long long total, int threads) { return ysod_cdiv(total, threads); }
+// grid for a grid-stride streaming kernel with `unroll` items in flight per thread: enough CTAs to fill 148 SMs x 8, no more
+inline int stream_blocks(long long total, int threads, int unroll) {
+    const long long need = (total + (long long)threads * unroll - 1) / ((long long)threads * unroll);
+    const long long cap = 148 * 16;
+    return (int)(need < 1 ? 1 : (need > cap ? cap : need));
+}
+// block size for StreamIdx kernels: a multiple of C/8 so that every thread keeps a fixed channel group
+inline int stream_threads(int C) { const int c8n = C / 8; return c8n >= 256 ? c8n : (256 / c8n) * c8n; }
 inline int ln_group(int C) {
     int g = 1;
     while (g < 32 && g < C / 8) g <<= 1;
@@ -606,7 +833,7 @@ int ysod_scale_channels(const void* x, int dtype, int N, int HW, int C, int xcs,
                         cudaStream_t st) {
     YSOD_CHECK_ARG(x && gate && out && C % 8 == 0 && xcs % 8 == 0 && ocs % 8 == 0, "ysod_scale_channels: bad args");
     const long long total = (long long)N * HW * (C / 8);
-    YSOD_DISPATCH(dtype, (scale_channels_kernel<T><<<blocks_for(total, 256), 256, 0, st>>>((const T*)x, HW, C, xcs, gate, (T*)out, ocs, total)));
+    YSOD_DISPATCH(dtype, (scale_channels_kernel<T><<<stream_blocks(total, stream_threads(C), 4), stream_threads(C), 0, st>>>((const T*)x, HW, C, xcs, gate, (T*)out, ocs, (unsigned)(total / (C / 8)))));
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }
@@ -617,6 +844,14 @@ int ysod_cbam_stats(const void* x, int dtype, int N, int HW, int C, int xcs, con
     YSOD_CHECK_ARG((c8n & (c8n - 1)) == 0, "ysod_cbam_stats: C/8 must be a power of two");
     const int G = c8n < 32 ? c8n : 32;
     const long long npix = (long long)N * HW;
+    if (c8n <= 32) {   // streaming variant: one 16 B load per lane and pixel, four pixels in flight
+        const int blocks = stream_blocks(npix * c8n, 256, 4);
+        const long long ngroups = (long long)blocks * 256 / c8n;
+        const int iters = (int)((npix + 4 * ngroups - 1) / (4 * ngroups));
+        YSOD_DISPATCH(dtype, (cbam_stats_stream_kernel<T><<<blocks, 256, 0, st>>>((const T*)x, HW, C, xcs, gate, (float2*)stats, npix, iters)));
+        YSOD_LAUNCH_CHECK();
+        return YSOD_OK;
+    }
     const long long warps = (npix + (32 / G) - 1) / (32 / G);
     YSOD_DISPATCH(dtype, (cbam_stats_kernel<T><<<blocks_for(warps * 32, 256), 256, 0, st>>>((const T*)x, HW, C, xcs, gate, (float2*)stats, npix)));
     YSOD_LAUNCH_CHECK();
@@ -630,6 +865,12 @@ int ysod_cbam_apply(const void* x, int dtype, int N, int H, int W, int C, int xc
     YSOD_CHECK_ARG((c8n & (c8n - 1)) == 0, "ysod_cbam_apply: C/8 must be a power of two");
     const int G = c8n < 32 ? c8n : 32;
     const long long npix = (long long)N * H * W;
+    if (ks == 7 && N <= 65535) {   // tiled variant (cbam_block.py:27: kernel_size 7)
+        dim3 grid(ysod_cdiv(W, 16), ysod_cdiv(H, 16), N);
+        YSOD_DISPATCH(dtype, (cbam_apply_tile_kernel<T><<<grid, 256, 0, st>>>((const T*)x, H, W, C, xcs, gate, (const float2*)stats, wsp, (T*)out, ocs)));
+        YSOD_LAUNCH_CHECK();
+        return YSOD_OK;
+    }
     const long long warps = (npix + (32 / G) - 1) / (32 / G);
     YSOD_DISPATCH(dtype, (cbam_apply_kernel<T><<<blocks_for(warps * 32, 256), 256, 2 * ks * ks * sizeof(float), st>>>(
                              (const T*)x, H, W, C, xcs, gate, (const float2*)stats, wsp, ks, (T*)out, ocs, npix)));
@@ -659,7 +900,7 @@ int ysod_ca_apply(const void* x, int dtype, int N, int H, int W, int C, int xcs,
                   cudaStream_t st) {
     YSOD_CHECK_ARG(x && att && out && C % 8 == 0 && xcs % 8 == 0 && ocs % 8 == 0, "ysod_ca_apply: bad args");
     const long long total = (long long)N * H * W * (C / 8);
-    YSOD_DISPATCH(dtype, (ca_apply_kernel<T><<<blocks_for(total, 256), 256, 0, st>>>((const T*)x, H, W, C, xcs, att, (T*)out, ocs, total)));
+    YSOD_DISPATCH(dtype, (ca_apply_kernel<T><<<stream_blocks(total, stream_threads(C), 4), stream_threads(C), 0, st>>>((const T*)x, H, W, C, xcs, att, (T*)out, ocs, (unsigned)(total / (C / 8)))));
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }
@@ -688,7 +929,7 @@ int ysod_upsample_copy(const void* x, int dtype, int N, int H, int W, int C, int
                        cudaStream_t st) {
     YSOD_CHECK_ARG(x && out && C % 8 == 0 && xcs % 8 == 0 && ocs % 8 == 0 && scale >= 1, "ysod_upsample_copy: bad args");
     const long long total = (long long)N * H * scale * W * scale * (C / 8);
-    YSOD_DISPATCH(dtype, (upsample_copy_kernel<T><<<blocks_for(total, 256), 256, 0, st>>>((const T*)x, H, W, C, xcs, scale, (T*)out, ocs, total)));
+    YSOD_DISPATCH(dtype, (upsample_copy_kernel<T><<<stream_blocks(total, stream_threads(C), 4), stream_threads(C), 0, st>>>((const T*)x, H, W, C, xcs, scale, (T*)out, ocs, (unsigned)(total / (C / 8)))));
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }
@@ -697,6 +938,15 @@ int ysod_layernorm(const void* x, int dtype, long long rows, int C, int ldx, con
                    void* out, int ldo, cudaStream_t st) {
     YSOD_CHECK_ARG(x && gamma && beta && out && C % 8 == 0 && C <= 2048 && ldx % 8 == 0 && ldo % 8 == 0, "ysod_layernorm: bad args");
     const int G = ln_group(C);
+    if (C / 8 <= 32 && ((C / 8) & (C / 8 - 1)) == 0) {
+        const int blocks = stream_blocks(rows * (C / 8), 256, 4);
+        const long long ngroups = (long long)blocks * 256 / (C / 8);
+        const int iters = (int)((rows + 4 * ngroups - 1) / (4 * ngroups));
+        YSOD_DISPATCH(dtype, (layernorm_stream_kernel<T, false><<<blocks, 256, 0, st>>>((const T*)x, rows, C, ldx, gamma, beta, eps, (T*)out, ldo,
+                                                                                      iters, 0, 0, 1, 1, 1, 1, nullptr)));
+        YSOD_LAUNCH_CHECK();
+        return YSOD_OK;
+    }
     YSOD_DISPATCH(dtype, (layernorm_kernel<T, false><<<blocks_for(rows * G, 256), 256, 0, st>>>(
                              (const T*)x, rows, C, ldx, gamma, beta, eps, (T*)out, ldo, G, 0, 0, 1, 1, 1, 1, nullptr)));
     YSOD_LAUNCH_CHECK();
@@ -710,6 +960,15 @@ int ysod_window_partition_ln(const void* x, int dtype, int N, int H, int W, int 
     YSOD_CHECK_ARG(x && gamma && beta && norm_out && C % 8 == 0 && C <= 2048 && xcs % 8 == 0 && ldo % 8 == 0, "ysod_window_partition_ln: bad args");
     const long long rows = (long long)N * nWh * nWw * wh * ww;
     const int G = ln_group(C);
+    if (C / 8 <= 32 && ((C / 8) & (C / 8 - 1)) == 0) {
+        const int blocks = stream_blocks(rows * (C / 8), 256, 4);
+        const long long ngroups = (long long)blocks * 256 / (C / 8);
+        const int iters = (int)((rows + 4 * ngroups - 1) / (4 * ngroups));
+        YSOD_DISPATCH(dtype, (layernorm_stream_kernel<T, true><<<blocks, 256, 0, st>>>((const T*)x, rows, C, xcs, gamma, beta, eps, (T*)norm_out, ldo,
+                                                                                     iters, H, W, wh, ww, nWh, nWw, (T*)raw_out)));
+        YSOD_LAUNCH_CHECK();
+        return YSOD_OK;
+    }
     YSOD_DISPATCH(dtype, (layernorm_kernel<T, true><<<blocks_for(rows * G, 256), 256, 0, st>>>(
                              (const T*)x, rows, C, xcs, gamma, beta, eps, (T*)norm_out, ldo, G, H, W, wh, ww, nWh, nWw, (T*)raw_out)));
     YSOD_LAUNCH_CHECK();
@@ -720,7 +979,7 @@ int ysod_window_reverse(const void* tok, int dtype, int ldt, int N, int H, int W
                         int ocs, cudaStream_t st) {
     YSOD_CHECK_ARG(tok && out && C % 8 == 0 && ldt % 8 == 0 && ocs % 8 == 0, "ysod_window_reverse: bad args");
     const long long total = (long long)N * H * W * (C / 8);
-    YSOD_DISPATCH(dtype, (window_reverse_kernel<T><<<blocks_for(total, 256), 256, 0, st>>>((const T*)tok, ldt, H, W, C, wh, ww, nWh, nWw, (T*)out, ocs, total)));
+    YSOD_DISPATCH(dtype, (window_reverse_kernel<T><<<stream_blocks(total, stream_threads(C), 4), stream_threads(C), 0, st>>>((const T*)tok, ldt, H, W, C, wh, ww, nWh, nWw, (T*)out, ocs, (unsigned)(total / (C / 8)))));
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }
