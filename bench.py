@@ -112,16 +112,24 @@ def cpu_reference_leg(steps, warmup, sample_batch=2, threads=None):
             "ms_per_step": 1e3 * dt / steps}
 
 
+def workload_config(B, world):
+    """The `config` object shared by both arms (the reference arm must report the B200 arm's config)."""
+    return {"workload": f"{CFG} fwd+decode+NMS", "imgsz": IMGSZ, "batch_per_gpu": B, "global_batch": B * world,
+            "conf": CONF, "iou": IOU, "max_det": MAX_DET, "weights": "synthetic calibrated-random, seed 0",
+            "parallelism": f"dp{world} (batch-sharded replicas, NCCL all_gather of detections)" if world > 1 else "single GPU"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     leg = cpu_reference_leg(max(1, args.steps), max(0, args.warmup))
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     line = {"impl": "reference", "metric": METRIC, "value": leg["value"], "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": leg["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{CFG} fwd+NMS 640x640 (reference CPU path, bounded sample)", "imgsz": IMGSZ, "conf": CONF,
-                       "iou": IOU, "max_det": MAX_DET},
+            "config": dict(workload_config(args.batch, world), note="reference CPU path (oracle port of the pure-Python reference: the "
+                           "same ATen CPU kernels), each step a bounded sample of 2 images of this workload"),
             "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": leg["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -306,11 +314,9 @@ def main():
         "metric": METRIC, "value": imgs / (ms * 1e-3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"{CFG} fwd+decode+NMS", "imgsz": IMGSZ, "batch_per_gpu": B, "global_batch": B * world,
-                   "conf": CONF, "iou": IOU, "max_det": MAX_DET, "weights": "synthetic calibrated-random, seed 0",
-                   "parallelism": f"dp{world} (batch-sharded replicas, NCCL all_gather of detections)" if world > 1 else "single GPU",
-                   "l2": "4 rotating input batches of 157 MB; ~5 GB of activations touched per step (>> 126 MB L2)",
-                   "detections_last_step": ndet},
+        "config": dict(workload_config(B, world),
+                       l2="4 rotating input batches of 157 MB; ~2 GB of activations touched per step (>> 126 MB L2)",
+                       detections_last_step=ndet),
         "clocks": clocks,
         "e2e": {"value": world * B * k2 / e2e_s, "unit": "images/s", "h2d_bytes_per_step": B * 3 * IMGSZ * IMGSZ,
                 "d2h_bytes_per_step": B * MAX_DET * 6 * 4 + B * 4, "steps": k2, "detections_last_step": e2e_ndet,

@@ -119,6 +119,11 @@ def test_graph_replay_equals_eager_and_is_deterministic():
     y2 = m_eager(x)[0].clone()
     y3 = m_graph(x)[0].clone()
     assert torch.equal(y1, y2) and torch.equal(y1, y3)
+    # the Detect-level branches on side streams (multi_stream) must not change a single bit either
+    _, _, m_single = _build(SOD, torch.bfloat16, multi_stream=False)
+    assert m_graph.program(2, 128, 128).n_lanes == 4 and m_single.program(2, 128, 128).n_lanes == 1
+    for _ in range(3):
+        assert torch.equal(m_graph(x)[0], m_single(x)[0])
 
 
 def test_predict_end_to_end_matches_oracle_nms():

@@ -226,7 +226,7 @@ nms_greedy_kernel(const float* __restrict__ pred, int nc, int A, int cap, int mu
                   float thr_f, const float4* __restrict__ boxes_all, const int* __restrict__ order_all,
                   const float* __restrict__ sscore_all, const int* __restrict__ cls_all,
                   const int* __restrict__ count_all, float* __restrict__ det_all, int* __restrict__ index_all,
-                  int* __restrict__ nkeep_all) {
+                  int* __restrict__ nkeep_all, int box_cache) {
     extern __shared__ uint32_t smem_u32[];
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -234,10 +234,15 @@ nms_greedy_kernel(const float* __restrict__ pred, int nc, int A, int cap, int mu
     const int nwords = (n + 31) >> 5;
     uint32_t* removed = smem_u32;                       // cap/32 words
     int* keep_idx = (int*)(smem_u32 + ((cap + 31) >> 5));  // max_det ints
+    // the first `ncache` (score-sorted) boxes live in shared memory: every sweep iteration re-reads them, and an L2 round
+    // trip per iteration (~700 cycles) used to dominate the 300-iteration serial chain
+    float4* sbox = reinterpret_cast<float4*>(smem_u32 + ((((cap + 31) >> 5) + max_det + 3) & ~3));
     __shared__ int s_next;
     const float4* boxes = boxes_all + (size_t)b * cap;
+    const int nc_box = n < box_cache ? n : box_cache;
 
     for (int w = tid; w < nwords; w += GREEDY_THREADS) removed[w] = 0u;
+    for (int j = tid; j < nc_box; j += GREEDY_THREADS) sbox[j] = boxes[j];
     __syncthreads();
 
     int kept = 0, pos = 0;
@@ -266,13 +271,13 @@ nms_greedy_kernel(const float* __restrict__ pred, int nc, int A, int cap, int mu
         ++kept;
         pos = i + 1;
         if (kept < max_det) {
-            const float4 bi = boxes[i];
+            const float4 bi = (i < nc_box) ? sbox[i] : boxes[i];
             const float iarea = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
             for (int w = (pos >> 5) + warp; w < nwords; w += GREEDY_THREADS / 32) {
                 const int j = w * 32 + lane;
                 bool sup = false;
                 if (j > i && j < n) {
-                    const float4 bj = boxes[j];
+                    const float4 bj = (j < nc_box) ? sbox[j] : boxes[j];
                     const float jarea = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
                     const float xx1 = std_max(bi.x, bj.x), yy1 = std_max(bi.y, bj.y);
                     const float xx2 = std_min(bi.z, bj.z), yy2 = std_min(bi.w, bj.w);
@@ -370,8 +375,10 @@ int ysod_nms_batched(const float* pred, int B, int nc, int A, float conf_thres, 
         ysod_set_error("ysod_nms_batched: workspace too small (%lld < %zu)", workspace_bytes, w.total);
         return YSOD_ERR_WORKSPACE;
     }
-    const size_t greedy_smem = (size_t)(((cap + 31) >> 5) + max_det) * 4;
-    YSOD_CHECK_ARG(greedy_smem <= 200 * 1024, "ysod_nms_batched: max_nms/max_det too large for shared memory");
+    const size_t greedy_base = (size_t)((((cap + 31) >> 5) + max_det + 3) & ~3) * 4;
+    YSOD_CHECK_ARG(greedy_base <= 96 * 1024, "ysod_nms_batched: max_nms/max_det too large for shared memory");
+    const int box_cache = cap < 6144 ? cap : 6144;   // up to 96 KB of sorted boxes cached per image
+    const size_t greedy_smem = greedy_base + (size_t)box_cache * 16;
     {
         dim3 grid(ysod_cdiv(A, 256), B);
         nms_score_kernel<<<grid, 256, 0, stream>>>(pred, nc, A, conf_thres, classes, n_classes, multi_label, w.conf, w.cls);
@@ -390,7 +397,7 @@ int ysod_nms_batched(const float* pred, int B, int nc, int A, float conf_thres, 
     }
     nms_greedy_kernel<<<B, GREEDY_THREADS, greedy_smem, stream>>>(pred, nc, A, cap, multi_label, max_det, thr_f, w.boxes,
                                                                   w.order, w.sscore, w.cls, w.count, out_det, out_index,
-                                                                  out_count);
+                                                                  out_count, box_cache);
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }
@@ -434,8 +441,10 @@ int ysod_nms_boxes(const float* boxes, const float* scores, int n, float thr_f, 
     float* sscore = (float*)take(4 * (size_t)n);
     int* count = (int*)take(4);
     float4* sorted = (float4*)take(16 * (size_t)n);
-    const size_t greedy_smem = (size_t)(((n + 31) >> 5) + max_keep) * 4;
-    YSOD_CHECK_ARG(greedy_smem <= 200 * 1024, "ysod_nms_boxes: n/max_keep too large for shared memory");
+    const size_t greedy_base = (size_t)((((n + 31) >> 5) + max_keep + 3) & ~3) * 4;
+    YSOD_CHECK_ARG(greedy_base <= 128 * 1024, "ysod_nms_boxes: n/max_keep too large for shared memory");
+    const int box_cache = n < 6144 ? n : 6144;
+    const size_t greedy_smem = greedy_base + (size_t)box_cache * 16;
     nms_sort_kernel<<<1, SORT_THREADS, 0, stream>>>(scores, n, n, 1, k0, v0, k1, v1, order, sscore, count);
     YSOD_LAUNCH_CHECK();
     nms_reorder_boxes_kernel<<<ysod_cdiv(n, 256), 256, 0, stream>>>((const float4*)boxes, order, count, sorted);
@@ -444,7 +453,7 @@ int ysod_nms_boxes(const float* boxes, const float* scores, int n, float thr_f, 
         YSOD_CUDA(cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)greedy_smem));
     }
     nms_greedy_kernel<<<1, GREEDY_THREADS, greedy_smem, stream>>>(nullptr, 0, 0, n, 0, max_keep, thr_f, sorted, order, sscore, nullptr,
-                                                                  count, nullptr, keep_out, nkeep_out);
+                                                                  count, nullptr, keep_out, nkeep_out, box_cache);
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }

@@ -60,7 +60,10 @@ class Program:
         self.dev = model.device
         self.dt = model.dtype
         self.code = _lib.BF16 if self.dt == torch.bfloat16 else _lib.F32
-        self.ops: List[tuple] = []       # (cfunc, args-without-stream)
+        self.ops: List[tuple] = []       # (cfunc, args-without-stream, entry point name)
+        self.sched: List[tuple] = []     # launch schedule: ("op", op index, lane) | ("record", mark, lane) | ("wait", mark, lane)
+        self._lane = 0                   # stream lane new ops are issued on (0 = main chain; 1.. = Detect level branches)
+        self.n_lanes = 1
         self.keep: List[object] = []     # tensors / handles that must stay alive
         self.tc_handles: List[C.c_void_p] = []
         self.n_launches = 0
@@ -97,6 +100,7 @@ class Program:
 
     def emit(self, name, *args, flops=0.0, desc=""):
         self.ops.append((getattr(_lib.load(), name), args, name))
+        self.sched.append(("op", len(self.ops) - 1, self._lane))
         self.op_flops.append(float(flops))
         self.op_desc.append(f"{self._ctx} {desc}".strip())
         self.n_launches += 1
@@ -136,6 +140,7 @@ class Program:
                       k, s, out.ptr(), odt, out.cs, res.ptr() if res is not None else None, res.cs if res is not None else 0, actc)
             self.tc_handles.append(h)
             self.ops.append((_lib.load().ysod_conv_tc_run, (h,), "ysod_conv_tc_run"))
+            self.sched.append(("op", len(self.ops) - 1, self._lane))
             fl = 2.0 * x.N * Ho * Wo * Cout * k * k * Cin
             self.op_flops.append(fl)
             info = (C.c_int * 8)()
@@ -385,7 +390,7 @@ class Program:
                   _lib.ptr(ww), _lib.ptr(bw), _lib.ptr(att))
         self.emit("ysod_ca_apply", x.ptr(), self.code, x.N, x.H, x.W, Cc, x.cs, _lib.ptr(att), out.ptr(), out.cs)
 
-    def detect(self, xs, P, p):
+    def detect(self, xs, P, p, src_layers):
         """head.py:64-131: per-level cv2/cv3 stacks -> raw maps (fp32 NHWC, stride RAW_CS) -> fused decode."""
         sd = self.m.sd
         nc = p["nc"]
@@ -396,7 +401,15 @@ class Program:
         self.keep.append(y)
         raws = []
         a_off = 0
+        nl = len(xs)
         for i, x in enumerate(xs):
+            # Each level's head chain only depends on its own input map: all but the last level run on their own stream lane,
+            # forked right after the layer that produced the input (the P2 head overlaps the rest of the neck), joined at the end.
+            branch = self.m.multi_stream and i < nl - 1
+            if branch:
+                self._lane = 1 + i
+                self.n_lanes = max(self.n_lanes, 2 + i)
+                self.sched.append(("wait", f"L{src_layers[i]}", self._lane))
             raw = self.new(x.N, x.H, x.W, raw_cs, dtype=torch.float32, zero=True)
             if p["legacy"] and self.m.use_tc and self.code == _lib.BF16:
                 # cv2[i][0] and cv3[i][0] are 3x3 convs on the same input: run them as ONE conv with N = c2 + c3 output channels
@@ -427,6 +440,12 @@ class Program:
                       a_off)
             a_off += x.H * x.W
             raws.append(raw.slice(0, no))
+            if branch:
+                self.sched.append(("record", f"det{i}", self._lane))
+                self._lane = 0
+        for i in range(nl - 1):
+            if self.m.multi_stream:
+                self.sched.append(("wait", f"det{i}", 0))
         self.y = y
         self.raws = raws
 
@@ -465,11 +484,12 @@ class Program:
                         home[src] = cb.slice(c0, c0 + cj)
                     c0 += cj
         out = self.layer_out
+        det_inputs = set(layers[-1].f) if layers[-1].type == "Detect" else set()
         for L in layers:
             P, p, t = f"model.{L.i}", L.p, L.type
             self._ctx = f"L{L.i}:{t}"
             if t == "Detect":
-                self.detect([out[j] for j in L.f], P, p)
+                self.detect([out[j] for j in L.f], P, p, list(L.f))
                 continue
             if t == "Concat":
                 cb = cat_buf[L.i]
@@ -482,6 +502,8 @@ class Program:
                         self.emit("ysod_upsample_copy", sv.ptr(), self.code, sv.N, sv.H, sv.W, sv.C, sv.cs, 1, dv.ptr(), dv.cs)
                     c0 += cj
                 out[L.i] = cb
+                if L.i in det_inputs:
+                    self.sched.append(("record", f"L{L.i}", 0))
                 continue
             h, w, c = shp[L.i]
             o = home[L.i] if L.i in home else self.new(self.B, h, w, c)
@@ -533,14 +555,31 @@ class Program:
             else:
                 raise NotImplementedError(t)
             out[L.i] = o
+            if L.i in det_inputs:
+                self.sched.append(("record", f"L{L.i}", 0))
 
     # ---- execution ---------------------------------------------------------------------------------------
     def launch_all(self):
-        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        for fn, args, name in self.ops:
-            rc = fn(*args, st)
-            if rc:
-                _lib.check(rc, name)
+        """Issues the schedule: lane 0 on the current stream, Detect-level branches on side streams forked / joined with events
+        (under graph capture these become graph edges, so independent branches run concurrently inside one CUDA graph)."""
+        main = torch.cuda.current_stream()
+        if self.n_lanes > 1 and not hasattr(self, "_side"):
+            self._side = [torch.cuda.Stream(device=self.dev) for _ in range(self.n_lanes - 1)]
+        streams = [main] + (self._side if self.n_lanes > 1 else [])
+        ptrs = [C.c_void_p(s.cuda_stream) for s in streams]
+        marks = {}
+        for kind, what, lane in self.sched:
+            if kind == "op":
+                fn, args, name = self.ops[what]
+                rc = fn(*args, ptrs[lane])
+                if rc:
+                    _lib.check(rc, name)
+            elif kind == "record":
+                ev = torch.cuda.Event()
+                ev.record(streams[lane])
+                marks[what] = ev
+            else:
+                streams[lane].wait_event(marks[what])
 
     def profile(self, iters=3):
         """Eager replay with a CUDA event pair around every launch (on the launching stream). Returns
@@ -614,7 +653,7 @@ class B200DetectionModel:
     """
 
     def __init__(self, cfg, state_dict, dtype=torch.bfloat16, device="cuda:0", use_tc=True, use_graph=True, nc=None,
-                 static_outputs=True, fuse_swin=True):
+                 static_outputs=True, fuse_swin=True, multi_stream=True):
         _lib.require_cuda()
         _lib.load()
         self.spec = cfg if isinstance(cfg, _cfg.ModelSpec) else _cfg.get_spec(cfg, nc=nc)
@@ -628,6 +667,7 @@ class B200DetectionModel:
         self.use_tc = use_tc
         self.use_graph = use_graph
         self.fuse_swin = fuse_swin
+        self.multi_stream = multi_stream
         self.static_outputs = static_outputs
         self.stride_list = _cfg.strides_of(self.spec)
         self.stride = torch.tensor([float(s) for s in self.stride_list])
