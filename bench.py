@@ -292,6 +292,20 @@ def main():
         json.dump({"batch": B, "imgsz": IMGSZ, "sum_ms": tot_ms, "kernels": table, "per_op": prog.last_per_op},
                   open(args.profile_out, "w"), indent=1)
 
+    # ---- split of the step: forward graph alone vs NMS alone (device events, same stream, 10 runs each)
+    def timed(fn, n=10):
+        fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(n):
+            fn()
+        b.record()
+        b.synchronize()
+        return a.elapsed_time(b) / n
+    y_last, _ = model(xs[0])
+    split = {"forward_graph_ms": round(timed(lambda: model(xs[1])), 4),
+             "nms_ms": round(timed(lambda: ops.nms_padded(y_last, CONF, IOU, max_det=MAX_DET)), 4)}
+
     # ---- batch-1 latency (second half of the BASELINE metric) -----------------------------------------------------
     x1 = synth.synth_images(1, IMGSZ, seed=7).to(dev)
     for _ in range(5):
@@ -326,6 +340,7 @@ def main():
         "gpu_launches": args.steps * (prog.n_launches + n_nms),
         "launches_per_step": prog.n_launches + n_nms,
         "roofline": roofline,
+        "step_split_ms": split,
         "latency_b1_ms": {"p50": lat[len(lat) // 2], "p90": lat[int(len(lat) * 0.9)], "min": lat[0], "runs": len(lat)},
     }
     if cpu:

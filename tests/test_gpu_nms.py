@@ -102,3 +102,36 @@ def test_full_size_properties_b64():
     # determinism
     det2, count2, _ = _ops().nms_padded(pred, 0.25, 0.7, max_det=300)
     assert torch.equal(det, det2) and torch.equal(count, count2)
+
+
+def test_iou_threshold_boundary_is_bit_exact():
+    """The greedy sweep classifies most pairs without the IEEE division (2^-20 guard band around the threshold). Thresholds
+    placed exactly on, one ulp below and one ulp above the fp32 IoU of a pair must still agree with the oracle."""
+    rng = np.random.default_rng(7)
+    ops = _ops()
+    bad = []
+    for k in range(150):
+        a = rng.uniform(0, 600, 2).astype(np.float32)
+        wh = rng.uniform(5, 80, 2).astype(np.float32)
+        d = (rng.uniform(-0.6, 0.6, 2) * wh).astype(np.float32)
+        wh2 = (wh * rng.uniform(0.6, 1.5, 2)).astype(np.float32)
+        boxes = np.stack([np.concatenate([a, a + wh]), np.concatenate([a + d, a + d + wh2])]).astype(np.float32)
+        scores = np.array([0.9, 0.8], dtype=np.float32)
+        x1, y1 = np.maximum(boxes[0, :2], boxes[1, :2])
+        x2, y2 = np.minimum(boxes[0, 2:], boxes[1, 2:])
+        w, h = np.float32(max(np.float32(0), np.float32(x2 - x1))), np.float32(max(np.float32(0), np.float32(y2 - y1)))
+        inter = np.float32(w * h)
+        area = lambda b: np.float32(np.float32(b[2] - b[0]) * np.float32(b[3] - b[1]))
+        uni = np.float32(np.float32(area(boxes[0]) + area(boxes[1])) - inter)
+        if not inter > 0:
+            continue
+        iou = np.float32(inter / uni)
+        for thr in (float(iou), float(np.nextafter(iou, np.float32(0))), float(np.nextafter(iou, np.float32(1))),
+                    float(iou) * (1 + 2.0 ** -21), float(iou) * (1 - 2.0 ** -21)):
+            if not 0 <= thr <= 1:
+                continue
+            want = nms_ref.nms(boxes, scores, thr)
+            got = ops.nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), thr).cpu().numpy()
+            if not np.array_equal(want, got):
+                bad.append((k, thr, float(iou), want.tolist(), got.tolist()))
+    assert not bad, bad[:5]

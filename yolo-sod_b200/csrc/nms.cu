@@ -273,29 +273,152 @@ nms_greedy_kernel(const float* __restrict__ pred, int nc, int A, int cap, int mu
         if (kept < max_det) {
             const float4 bi = (i < nc_box) ? sbox[i] : boxes[i];
             const float iarea = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+            const float thr_hi = __fmul_rn(thr_f, 1.0000009537f), thr_lo = __fmul_rn(thr_f, 0.9999990463f);   // thr * (1 +- 2^-20)
             for (int w = (pos >> 5) + warp; w < nwords; w += GREEDY_THREADS / 32) {
                 const int j = w * 32 + lane;
+                const uint32_t already = removed[w];   // boxes suppressed earlier need no evaluation (their bit stays set)
                 bool sup = false;
-                if (j > i && j < n) {
+                if (j > i && j < n && !((already >> lane) & 1u)) {
                     const float4 bj = (j < nc_box) ? sbox[j] : boxes[j];
-                    const float jarea = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
                     const float xx1 = std_max(bi.x, bj.x), yy1 = std_max(bi.y, bj.y);
                     const float xx2 = std_min(bi.z, bj.z), yy2 = std_min(bi.w, bj.w);
                     const float ww = std_max(0.0f, __fsub_rn(xx2, xx1));
                     const float hh = std_max(0.0f, __fsub_rn(yy2, yy1));
                     const float inter = __fmul_rn(ww, hh);
-                    const float uni = __fsub_rn(__fadd_rn(iarea, jarea), inter);
-                    const float ovr = __fdiv_rn(inter, uni);
-                    sup = ovr > thr_f;
+                    if (inter > 0.0f || !(inter == 0.0f)) {   // disjoint boxes: inter == +0 -> IoU is 0 (or NaN when the union is 0): never > thr
+                        const float jarea = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
+                        const float uni = __fsub_rn(__fadd_rn(iarea, jarea), inter);
+                        // Division-free classification with a 2^-20 guard band around the threshold (the rounded quotient of
+                        // torchvision's `inter / union > thr` can only differ from the exact one by 2^-24 relative); the IEEE
+                        // division is evaluated only inside the band or for non-positive / non-finite unions.
+                        if (uni > 1.0e-30f && uni < 3.0e38f && inter > __fmul_rn(thr_hi, uni)) sup = true;
+                        else if (uni > 1.0e-30f && uni < 3.0e38f && inter < __fmul_rn(thr_lo, uni)) sup = false;
+                        else sup = __fdiv_rn(inter, uni) > thr_f;
+                    }
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, sup);
-                if (lane == 0 && bal) removed[w] |= bal;  // this warp is the only writer of word w this round
+                if (lane == 0 && bal) removed[w] = already | bal;  // this warp is the only writer of word w this round
             }
         }
         __syncthreads();
     }
     __syncthreads();
 
+    // emit detections [x1,y1,x2,y2,conf,cls] (un-offset boxes) + the candidate index of each keep
+    float* det = det_all + (size_t)b * max_det * 6;
+    int* index = index_all + (size_t)b * max_det;
+    for (int t = tid; t < max_det; t += GREEDY_THREADS) {
+        if (t < kept) {
+            const int r = keep_idx[t];
+            const int id = order_all[(size_t)b * cap + r];
+            index[t] = id;
+            if (pred == nullptr) continue;  // plain box-NMS mode: keep indices only
+            const int a = multi_label ? id / nc : id;
+            const int c = multi_label ? id % nc : cls_all[(size_t)b * A + a];
+            const float4 q = load_xyxy(pred, b, nc, A, a);
+            det[t * 6 + 0] = q.x; det[t * 6 + 1] = q.y; det[t * 6 + 2] = q.z; det[t * 6 + 3] = q.w;
+            det[t * 6 + 4] = sscore_all[(size_t)b * cap + r];
+            det[t * 6 + 5] = (float)c;
+        } else {
+            index[t] = -1;
+            if (pred == nullptr) continue;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) det[t * 6 + k] = 0.0f;
+        }
+    }
+    if (tid == 0) nkeep_all[b] = kept;
+}
+
+// Exact pairwise test of torchvision's nms_kernel_impl: suppress j when inter / (area_i + area_j - inter) > thr, every step a
+// separately rounded fp32 operation. Most pairs are classified without the IEEE division (2^-20 guard band, see above).
+__device__ __forceinline__ bool iou_exceeds(const float4 bi, const float iarea, const float4 bj, const float thr_f, const float thr_hi,
+                                            const float thr_lo) {
+    const float xx1 = std_max(bi.x, bj.x), yy1 = std_max(bi.y, bj.y);
+    const float xx2 = std_min(bi.z, bj.z), yy2 = std_min(bi.w, bj.w);
+    const float ww = std_max(0.0f, __fsub_rn(xx2, xx1));
+    const float hh = std_max(0.0f, __fsub_rn(yy2, yy1));
+    const float inter = __fmul_rn(ww, hh);
+    if (inter == 0.0f) return false;   // IoU is +-0 or NaN: never > thr (thr >= 0)
+    const float jarea = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
+    const float uni = __fsub_rn(__fadd_rn(iarea, jarea), inter);
+    if (uni > 1.0e-30f && uni < 3.0e38f) {
+        if (inter > __fmul_rn(thr_hi, uni)) return true;
+        if (inter < __fmul_rn(thr_lo, uni)) return false;
+    }
+    return __fdiv_rn(inter, uni) > thr_f;
+}
+
+// Greedy NMS in "kept-list" form for small max_det (the detection path keeps <= 300 boxes, ops.py:297): candidates are visited
+// in score order, 32 at a time. A chunk is (a) tested against every box kept so far (1024 threads = 32 candidates x 32 slices of
+// the kept list), (b) tested pairwise inside the chunk (one pair per thread), (c) resolved serially by one thread with bit
+// operations. A candidate is dropped iff an earlier KEPT box overlaps it -- the same pairwise tests as the sequential sweep, so
+// the result is identical; the work is (#candidates visited until max_det are kept) x (#kept) instead of max_det x n.
+__global__ void __launch_bounds__(GREEDY_THREADS, 1)
+nms_chunk_kernel(const float* __restrict__ pred, int nc, int A, int cap, int multi_label, int max_det, float thr_f,
+                 const float4* __restrict__ boxes_all, const int* __restrict__ order_all, const float* __restrict__ sscore_all,
+                 const int* __restrict__ cls_all, const int* __restrict__ count_all, float* __restrict__ det_all,
+                 int* __restrict__ index_all, int* __restrict__ nkeep_all) {
+    extern __shared__ uint32_t smem_u32[];
+    float4* kbox = reinterpret_cast<float4*>(smem_u32);                    // max_det kept boxes
+    float* karea = reinterpret_cast<float*>(kbox + max_det);               // their areas
+    int* keep_idx = reinterpret_cast<int*>(karea + max_det);               // their sorted positions
+    __shared__ uint32_t s_sup, s_row[32];
+    __shared__ int s_kept;
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = count_all[b];
+    const float4* boxes = boxes_all + (size_t)b * cap;
+    const float thr_hi = __fmul_rn(thr_f, 1.0000009537f), thr_lo = __fmul_rn(thr_f, 0.9999990463f);   // thr * (1 +- 2^-20)
+    if (tid == 0) s_kept = 0;
+    __syncthreads();
+    int kept = 0;
+    for (int c0 = 0; c0 < n && kept < max_det; c0 += 32) {
+        const int m = min(32, n - c0);
+        if (tid == 0) s_sup = 0u;
+        if (tid < 32) s_row[tid] = 0u;
+        __syncthreads();
+        // candidate `lane` of the chunk
+        const bool cvalid = lane < m;
+        const float4 cj = cvalid ? boxes[c0 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+        // (a) against the kept list: warp w takes kept boxes w, w + 32, ...
+        bool sup = false;
+        if (cvalid) {
+            for (int i = warp; i < kept && !sup; i += 32) sup = iou_exceeds(kbox[i], karea[i], cj, thr_f, thr_hi, thr_lo);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, sup);
+        if (lane == 0 && bal) atomicOr(&s_sup, bal);
+        // (b) inside the chunk: warp a = earlier candidate, lane = later candidate
+        {
+            const int a = warp;
+            bool s2 = false;
+            if (a < m && cvalid && lane > a) {
+                const float4 ba = boxes[c0 + a];
+                const float aarea = __fmul_rn(__fsub_rn(ba.z, ba.x), __fsub_rn(ba.w, ba.y));
+                s2 = iou_exceeds(ba, aarea, cj, thr_f, thr_hi, thr_lo);
+            }
+            const unsigned row = __ballot_sync(0xffffffffu, s2);
+            if (lane == 0) s_row[a] = row;
+        }
+        __syncthreads();
+        // (c) serial resolution of the chunk
+        if (tid == 0) {
+            uint32_t alive = ~s_sup & (m == 32 ? 0xffffffffu : ((1u << m) - 1u));
+            int k = kept;
+            while (alive && k < max_det) {
+                const int a = __ffs(alive) - 1;
+                alive &= ~(1u << a);
+                alive &= ~s_row[a];
+                const float4 ba = boxes[c0 + a];
+                kbox[k] = ba;
+                karea[k] = __fmul_rn(__fsub_rn(ba.z, ba.x), __fsub_rn(ba.w, ba.y));
+                keep_idx[k] = c0 + a;
+                ++k;
+            }
+            s_kept = k;
+        }
+        __syncthreads();
+        kept = s_kept;
+    }
     // emit detections [x1,y1,x2,y2,conf,cls] (un-offset boxes) + the candidate index of each keep
     float* det = det_all + (size_t)b * max_det * 6;
     int* index = index_all + (size_t)b * max_det;
@@ -392,6 +515,12 @@ int ysod_nms_batched(const float* pred, int B, int nc, int A, float conf_thres, 
                                                     agnostic ? 0.0f : max_wh, w.boxes);
         YSOD_LAUNCH_CHECK();
     }
+    if (max_det <= 2048) {   // kept-list formulation: the detection path (max_det = 300)
+        nms_chunk_kernel<<<B, GREEDY_THREADS, (size_t)max_det * 24, stream>>>(pred, nc, A, cap, multi_label, max_det, thr_f, w.boxes, w.order,
+                                                                              w.sscore, w.cls, w.count, out_det, out_index, out_count);
+        YSOD_LAUNCH_CHECK();
+        return YSOD_OK;
+    }
     if (greedy_smem > 48 * 1024) {
         YSOD_CUDA(cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)greedy_smem));
     }
@@ -449,6 +578,12 @@ int ysod_nms_boxes(const float* boxes, const float* scores, int n, float thr_f, 
     YSOD_LAUNCH_CHECK();
     nms_reorder_boxes_kernel<<<ysod_cdiv(n, 256), 256, 0, stream>>>((const float4*)boxes, order, count, sorted);
     YSOD_LAUNCH_CHECK();
+    if (max_keep <= 2048) {
+        nms_chunk_kernel<<<1, GREEDY_THREADS, (size_t)max_keep * 24, stream>>>(nullptr, 0, 0, n, 0, max_keep, thr_f, sorted, order, sscore, nullptr,
+                                                                               count, nullptr, keep_out, nkeep_out);
+        YSOD_LAUNCH_CHECK();
+        return YSOD_OK;
+    }
     if (greedy_smem > 48 * 1024) {
         YSOD_CUDA(cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)greedy_smem));
     }
