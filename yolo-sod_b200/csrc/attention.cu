@@ -198,6 +198,125 @@ mha_win_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restr
     }
 }
 
+// ---- general variant: any L, bf16, flash-style on warp-level tensor cores -------------------------------------------------------
+// CTA = 64 query rows of one (batch, head) (warp w: rows 16w..16w+15), looping over key blocks of 64 with an online softmax:
+// m' = max(m, rowmax S), P = exp(S - m'), l = l*exp(m - m') + rowsum P, O = O*exp(m - m') + P V. Used by A2_Attn (L = 8*W) and the
+// yolov12 area attention (L = H*W/area), whose reference semantics are the manual softmax path (block.py:1348-1357).
+template <int D>
+__global__ void __launch_bounds__(128)
+mha_flash_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v, int L,
+                 int ldq, int ldk, int ldv, long long bsq, long long bsk, long long bsv, float scale, __nv_bfloat16* __restrict__ out,
+                 int ldo, long long bso) {
+    constexpr int LDQ = D + 8, LDV = 64 + 8;
+    __shared__ __align__(16) __nv_bfloat16 Qs[64 * LDQ];
+    __shared__ __align__(16) __nv_bfloat16 Ks[64 * LDQ];
+    __shared__ __align__(16) __nv_bfloat16 Vt[D * LDV];
+    const int q0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const __nv_bfloat16* qb = q + (size_t)b * bsq + h * D;
+    const __nv_bfloat16* kb = k + (size_t)b * bsk + h * D;
+    const __nv_bfloat16* vb = v + (size_t)b * bsv + h * D;
+    for (int i = tid; i < 64 * (D / 8); i += 128) {
+        const int r = i / (D / 8), pc = i - r * (D / 8);
+        uint4 qv = make_uint4(0, 0, 0, 0);
+        if (q0 + r < L) qv = *reinterpret_cast<const uint4*>(qb + (size_t)(q0 + r) * ldq + pc * 8);
+        *reinterpret_cast<uint4*>(&Qs[r * LDQ + pc * 8]) = qv;
+    }
+    __syncthreads();
+    const int row0 = warp * 16 + g;
+    uint32_t qf[D / 16][4];
+#pragma unroll
+    for (int ks = 0; ks < D / 16; ++ks) {
+        qf[ks][0] = ld32s(&Qs[row0 * LDQ + ks * 16 + 2 * t]);
+        qf[ks][1] = ld32s(&Qs[(row0 + 8) * LDQ + ks * 16 + 2 * t]);
+        qf[ks][2] = ld32s(&Qs[row0 * LDQ + ks * 16 + 8 + 2 * t]);
+        qf[ks][3] = ld32s(&Qs[(row0 + 8) * LDQ + ks * 16 + 8 + 2 * t]);
+    }
+    float o[D / 8][4];
+#pragma unroll
+    for (int nb = 0; nb < D / 8; ++nb) o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    for (int k0 = 0; k0 < L; k0 += 64) {
+        __syncthreads();   // previous block's K / V^T fully consumed
+        for (int i = tid; i < 64 * (D / 8); i += 128) {
+            const int r = i / (D / 8), pc = i - r * (D / 8);
+            uint4 kv = make_uint4(0, 0, 0, 0), vv = kv;
+            if (k0 + r < L) {
+                kv = *reinterpret_cast<const uint4*>(kb + (size_t)(k0 + r) * ldk + pc * 8);
+                vv = *reinterpret_cast<const uint4*>(vb + (size_t)(k0 + r) * ldv + pc * 8);
+            }
+            *reinterpret_cast<uint4*>(&Ks[r * LDQ + pc * 8]) = kv;
+            const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) Vt[(pc * 8 + e) * LDV + r] = ve[e];
+        }
+        __syncthreads();
+        float s[8][4];
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+            s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
+            const __nv_bfloat16* kr = &Ks[(nb * 8 + g) * LDQ + 2 * t];
+#pragma unroll
+            for (int ks = 0; ks < D / 16; ++ks) mma16816(s[nb], qf[ks], ld32s(kr + ks * 16), ld32s(kr + ks * 16 + 8));
+        }
+        float mx0 = m0, mx1 = m1;
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+            const int key = k0 + nb * 8 + 2 * t;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) s[nb][e] *= scale;
+            if (key >= L) { s[nb][0] = -INFINITY; s[nb][2] = -INFINITY; }
+            if (key + 1 >= L) { s[nb][1] = -INFINITY; s[nb][3] = -INFINITY; }
+            mx0 = fmaxf(mx0, fmaxf(s[nb][0], s[nb][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[nb][2], s[nb][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float c0 = __expf(m0 - mx0), c1 = __expf(m1 - mx1);   // exp(-inf) = 0 on the first block
+        m0 = mx0; m1 = mx1;
+        float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+            s[nb][0] = __expf(s[nb][0] - m0); s[nb][1] = __expf(s[nb][1] - m0);
+            s[nb][2] = __expf(s[nb][2] - m1); s[nb][3] = __expf(s[nb][3] - m1);
+            r0 += s[nb][0] + s[nb][1];
+            r1 += s[nb][2] + s[nb][3];
+        }
+        r0 += __shfl_xor_sync(0xffffffffu, r0, 1); r0 += __shfl_xor_sync(0xffffffffu, r0, 2);
+        r1 += __shfl_xor_sync(0xffffffffu, r1, 1); r1 += __shfl_xor_sync(0xffffffffu, r1, 2);
+        l0 = l0 * c0 + r0;
+        l1 = l1 * c1 + r1;
+        uint32_t pf[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            pf[i][0] = pack2bf(s[2 * i][0], s[2 * i][1]);
+            pf[i][1] = pack2bf(s[2 * i][2], s[2 * i][3]);
+            pf[i][2] = pack2bf(s[2 * i + 1][0], s[2 * i + 1][1]);
+            pf[i][3] = pack2bf(s[2 * i + 1][2], s[2 * i + 1][3]);
+        }
+#pragma unroll
+        for (int nb = 0; nb < D / 8; ++nb) {
+            o[nb][0] *= c0; o[nb][1] *= c0; o[nb][2] *= c1; o[nb][3] *= c1;
+            const __nv_bfloat16* vr = &Vt[(nb * 8 + g) * LDV + 2 * t];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) mma16816(o[nb], pf[i], ld32s(vr + i * 16), ld32s(vr + i * 16 + 8));
+        }
+    }
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+    // Qs rows of this warp were only read by this warp (fragments are in registers): reuse them as the output staging tile
+#pragma unroll
+    for (int nb = 0; nb < D / 8; ++nb) {
+        *reinterpret_cast<uint32_t*>(&Qs[row0 * LDQ + nb * 8 + 2 * t]) = pack2bf(o[nb][0] * inv0, o[nb][1] * inv0);
+        *reinterpret_cast<uint32_t*>(&Qs[(row0 + 8) * LDQ + nb * 8 + 2 * t]) = pack2bf(o[nb][2] * inv1, o[nb][3] * inv1);
+    }
+    __syncthreads();
+    __nv_bfloat16* ob = out + (size_t)b * bso + h * D;
+    for (int i = tid; i < 64 * (D / 8); i += 128) {
+        const int r = i / (D / 8), pc = i - r * (D / 8);
+        if (q0 + r < L) *reinterpret_cast<uint4*>(ob + (size_t)(q0 + r) * ldo + pc * 8) = *reinterpret_cast<const uint4*>(&Qs[r * LDQ + pc * 8]);
+    }
+}
+
 }  // namespace
 
 extern "C" int ysod_mha_core(const void* q, const void* k, const void* v, int dtype, int batch, int L, int heads, int D, int ldq,
@@ -220,6 +339,17 @@ extern "C" int ysod_mha_core(const void* q, const void* k, const void* v, int dt
     }
     dim3 grid(ysod_cdiv(L, 64), heads, batch);
     YSOD_CHECK_ARG(batch <= 65535 && heads <= 65535, "ysod_mha_core: grid too large (batch %d)", batch);
+    if (dtype == YSOD_BF16 && (D == 32 || D == 64) && ((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && ((uintptr_t)v % 16) == 0 &&
+        ((uintptr_t)out % 16) == 0 && bsq % 8 == 0 && bsk % 8 == 0 && bsv % 8 == 0 && bso % 8 == 0) {
+        if (D == 32)
+            mha_flash_kernel<32><<<grid, 128, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, L, ldq, ldk, ldv,
+                                                       bsq, bsk, bsv, scale, (__nv_bfloat16*)out, ldo, bso);
+        else
+            mha_flash_kernel<64><<<grid, 128, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, L, ldq, ldk, ldv,
+                                                       bsq, bsk, bsv, scale, (__nv_bfloat16*)out, ldo, bso);
+        YSOD_LAUNCH_CHECK();
+        return YSOD_OK;
+    }
 #define LAUNCH(T, DD) \
     mha_core_kernel<T, DD><<<grid, 64, 0, st>>>((const T*)q, (const T*)k, (const T*)v, L, ldq, ldk, ldv, bsq, bsk, bsv, scale, (T*)out, ldo, bso)
     if (dtype == YSOD_F32 && D == 32) LAUNCH(float, 32);

@@ -7,8 +7,8 @@
 // for the shape it takes at P2 (layer 28 of yolov12-sod-fusion-v5-simple: 64 channels, 160x160 @640 -> 529 windows per image,
 // 829 k tokens per 32-image batch). Unfused, the eleven launches move ~3.4 GB through HBM for 210 MB of real input+output.
 //
-// One group of 4 warps owns one window (49 tokens padded to 64 MMA rows, warp w = token rows 16w..16w+15), two groups per
-// persistent CTA share the ~82 KB of weights kept in shared memory. Everything between the input patch load and the output
+// One group of 4 warps owns one window (49 tokens padded to 64 MMA rows, warp w = token rows 16w..16w+15), three groups per
+// persistent CTA share the ~82 KB of weights kept in shared memory (12 warps per SM). Everything between the input patch load and the output
 // store lives in registers / shared memory: every GEMM (QKV, QK^T, PV, out_proj, MLP, pw) is warp-level mma.sync m16n8k16
 // (bf16 in, fp32 accumulate) with the accumulator -> A-fragment register re-packing trick, LayerNorm / softmax row
 // reductions are quad shuffles. K = 32..128 per GEMM and M = 49 tokens per window make this the wrong shape for a
@@ -25,7 +25,7 @@ constexpr int LDW2 = 128 + 8;     // rows of the 128-wide mlp.2 weight
 constexpr int LDK = HD + 8;       // K rows  [key][d]
 constexpr int LDV = 64 + 8;       // V^T rows [d][key]
 constexpr int PATCH = 81;         // 9 x 9 input pixels around a 7 x 7 window
-constexpr int NGROUP = 2;         // windows in flight per CTA
+constexpr int NGROUP = 3;         // windows in flight per CTA
 constexpr int THREADS = NGROUP * 128;
 
 // bf16 weight blob offsets (elements) in global memory: dw[9][64] | wqkv[192][64] | wo[64][64] | w1[128][64] | w2[64][128] | wpw[64][64]
