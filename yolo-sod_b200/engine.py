@@ -126,6 +126,14 @@ class Program:
         odt = _lib.F32 if out_f32 else self.code
         if res is not None:
             assert (res.N, res.H, res.W, res.C) == (out.N, out.H, out.W, out.C)
+        if (g > 1 and not (g == Cin and g == Cout) and self.m.use_tc and self.code == _lib.BF16 and (Cin // g) % 32 == 0
+                and (Cout // g) % 8 == 0 and res is None):
+            # grouped conv (yolov12.yaml:20,22) = g dense convs on channel slices of the same NHWC buffers: tensor-core kernel per group
+            ci, co = Cin // g, Cout // g
+            for j in range(g):
+                self.conv(x.slice(j * ci, (j + 1) * ci), w[j * co:(j + 1) * co], bias[j * co:(j + 1) * co], k, s, 1, act,
+                          out.slice(j * co, (j + 1) * co), None, out_f32, pad)
+            return
         use_tc = (self.m.use_tc and self.code == _lib.BF16 and g == 1 and k in (1, 3) and s in (1, 2) and pad == k // 2
                   and Cin % 32 == 0 and (s == 1 or (x.H % 2 == 0 and x.W % 2 == 0)))
         if use_tc:
