@@ -106,6 +106,8 @@ HALO_CASES = [
     (1, 20, 20, 64, 32, 3, 1, {}),                                  # BN=32 (64 B staging rows), low-utilisation map forced
     (8, 80, 80, 128, 128, 3, 1, {}),                                # streamed taps, many tiles per CTA (ring / sub-ring wrap)
     (6, 160, 160, 64, 64, 3, 1, dict(res=True)),                    # resident taps, ~9 tiles per CTA
+    (4, 160, 160, 32, 32, 3, 1, dict(res=True)),                    # Cin = 32: 64 B pixel rows / SWIZZLE_64B halo copy
+    (1, 24, 40, 32, 64, 3, 1, {}),                                  # Cin = 32, ragged tiles
 ]
 
 

@@ -352,7 +352,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (p.debug & 2) mbar_arrive(fullA + 8u * aslot);
                         else {
                             mbar_expect_tx(fullA + 8u * aslot, p.a_tx);
-                            tma_load_4d(a_base + (uint32_t)aslot * p.a_bytes, &tmA, fullA + 8u * aslot, cc * 64, ow0 - 1, oh0 - 1, img);
+                            tma_load_4d(a_base + (uint32_t)aslot * p.a_bytes, &tmA, fullA + 8u * aslot, cc * p.BK, ow0 - 1, oh0 - 1, img);
                         }
                         if (++sa_c == ah) { sa_c = 0; pa_c ^= 1u; }
                         if (b_res && !first) continue;  // weights already in shared memory
@@ -361,7 +361,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 const int slot = b_res ? (cc * 9 + s * 3 + r) : (bbase_c + sb_c);
                                 if (!b_res) mbar_wait(emptyB + 8u * slot, pb_c ^ 1u);
                                 mbar_expect_tx(fullB + 8u * slot, p.b_bytes);
-                                tma_load_2d(b_base + (uint32_t)slot * p.b_bytes, &tmB, fullB + 8u * slot, (r * 3 + s) * p.Cin + cc * 64, n0);
+                                tma_load_2d(b_base + (uint32_t)slot * p.b_bytes, &tmB, fullB + 8u * slot, (r * 3 + s) * p.Cin + cc * p.BK, n0);
                                 if (!b_res && ++sb_c == bh) { sb_c = 0; pb_c ^= 1u; }
                             }
                         }
@@ -438,7 +438,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {
                 const int a_stages = p.a_stages, b_stages = p.b_stages, cchunks = p.cchunks, SG = p.sgroup;
                 const bool b_res = p.b_resident != 0;
-                const uint32_t halo_desc_hi = (1280u >> 4) | (1u << 14) | (2u << 29);   // SBO = 10 pixels, SWIZZLE_128B
+                const uint32_t row_b = 2u * (uint32_t)p.BK;                       // bytes of one pixel row of the halo copy (128 or 64)
+                const uint32_t halo_desc_hi = ((10u * row_b) >> 4) | (1u << 14) | ((p.BK == 64 ? 2u : 4u) << 29);   // SBO = 10 pixels
+                const int ksteps = p.BK >> 4;
                 bool first = true;
                 int sa = 0, sb = 0;          // positions inside this issuer's (sub-)rings
                 uint32_t pa = 0, pb = 0;
@@ -470,10 +472,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                     for (int r = 0; r < 3; ++r) {
                                         // tap (r, s): the MMA's pixel rows start (r*10 + s) pixels into the 18 x 10 halo copy; the
                                         // 8-pixel row groups are 10 pixels (SBO = 1280 B) apart.
-                                        const uint32_t a_lo = umma_lo(a_slot_addr + (uint32_t)(r * 10 + s) * 128u);
+                                        const uint32_t a_lo = umma_lo(a_slot_addr + (uint32_t)(r * 10 + s) * row_b);
                                         const uint32_t b_lo = umma_lo(b_base + (slot0 + r) * b_bytes);
-#pragma unroll
-                                        for (int k = 0; k < 4; ++k)
+#pragma unroll 4
+                                        for (int k = 0; k < ksteps; ++k)
                                             tc_mma_bf16(d_tmem, umma_desc(halo_desc_hi, a_lo + 2u * k), umma_desc(desc_hi, b_lo + 2u * k), idesc,
                                                         (uint32_t)((cc | s | r | k) != 0));
                                     }
@@ -714,7 +716,7 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
     bool halo = false;
     const int dbg = mode >> 8;
     mode &= 0xff;
-    if (ksize == 3 && stride == 1 && Cin % 64 == 0) {
+    if (ksize == 3 && stride == 1 && (Cin % 64 == 0 || Cin == 32)) {
         const double hutil = (double)Ho * Wo / ((double)ysod_cdiv(Ho, 16) * ysod_cdiv(Wo, 8) * 128.0);
         halo = (mode == 2) || (mode == 0 && hutil >= 0.75);
     }
@@ -796,8 +798,8 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
         ring_bytes = (size_t)p.a_slots * slot_bytes;
         nbar = 4 * p.a_slots;
     } else {
-        p.a_tx = 18u * 10u * 128u;     // one halo copy: 18 rows x 10 px x 64 ch bf16
-        p.a_bytes = 23u * 1024u;       // slot stride (1 KB aligned)
+        p.a_tx = 18u * 10u * 2u * (uint32_t)p.BK;     // one halo copy: 18 rows x 10 px x BK ch bf16 (22.5 KB / 11.25 KB)
+        p.a_bytes = (p.a_tx + 1023u) & ~1023u;        // slot stride (1 KB aligned)
         const uint32_t avail = 224u * 1024u - fixed;
         const uint32_t b_all = 9u * (uint32_t)p.cchunks * p.b_bytes;
         int a_total;
