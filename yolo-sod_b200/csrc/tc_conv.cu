@@ -169,6 +169,11 @@ constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int PRODUCER_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
 constexpr int TC_THREADS = EPI_THREADS + 96;
 
+// Programmatic dependent launch: the next kernel in the stream may start its prologue while this grid drains; everything that
+// touches activations produced by the previous kernel happens after pdl_wait().
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -287,6 +292,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     uint32_t tmem_acc;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_acc) : "r"(tmem_slot) : "memory");
+    pdl_launch_dependents();   // the next kernel's CTAs may be scheduled as soon as SMs free up (they block in pdl_wait())
 
     if (warp == PRODUCER_WARP) {
         // ===== TMA producer (one elected lane) =====
@@ -301,6 +307,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint32_t ph_c = 0, ph_o = 0;
                 TileIter ti;
                 ti.init(blockIdx.x, p);
+                pdl_wait();   // the input activations are written by the previous kernel
                 for (int tcount = 0; ti.valid(p); ti.step(p), ++tcount) {
                     const int img = ti.img;
                     const int oh0 = ti.th * p.TH, ow0 = ti.tw * p.TW;
@@ -340,6 +347,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 bool first = true;
                 TileIter ti;
                 ti.init(blockIdx.x, p);
+                if (b_res && ti.valid(p) && p.n_tiles == 1) {
+                    // resident weights are static: fetch them while the previous kernel is still draining
+                    for (int cc = 0; cc < cchunks; ++cc)
+                        for (int s = 0; s < 3; ++s)
+                            for (int r = 0; r < 3; ++r) {
+                                const int slot = cc * 9 + s * 3 + r;
+                                mbar_expect_tx(fullB + 8u * slot, p.b_bytes);
+                                tma_load_2d(b_base + (uint32_t)slot * p.b_bytes, &tmB, fullB + 8u * slot, (r * 3 + s) * p.Cin + cc * p.BK, 0);
+                            }
+                    first = false;
+                }
+                pdl_wait();   // the input activations are written by the previous kernel
                 for (int tcount = 0; ti.valid(p); ti.step(p), ++tcount) {
                     const int img = ti.img;
                     const int oh0 = ti.th * 16, ow0 = ti.tw * 8;
@@ -532,6 +551,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         TileIter ti;
         ti.init(blockIdx.x, p);
         if (grp) ti.step(p);
+        if (res != nullptr) pdl_wait();   // the residual may be the previous kernel's output
         for (int tcount = grp; ti.valid(p); ti.step(p), ti.step(p), tcount += 2) {
             const int img = ti.img;
             const int oh0 = ti.th * TH, ow0 = ti.tw * TW;
@@ -913,8 +933,19 @@ int ysod_conv_tc_create(ysod_conv_tc** handle, const void* x, int N, int H, int 
 
 int ysod_conv_tc_run(ysod_conv_tc* h, cudaStream_t stream) {
     YSOD_CHECK_ARG(h, "ysod_conv_tc_run: null handle");
-    if (h->c.halo) conv_tc_kernel<true><<<h->c.grid, TC_THREADS, h->c.smem, stream>>>(h->c.tmA, h->c.tmB, h->c.tmO, h->c.p);
-    else conv_tc_kernel<false><<<h->c.grid, TC_THREADS, h->c.smem, stream>>>(h->c.tmA, h->c.tmB, h->c.tmO, h->c.p);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = h->c.grid;
+    cfg.blockDim = dim3(TC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = h->c.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: prologue overlaps the previous kernel's tail
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (h->c.halo) YSOD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, h->c.tmA, h->c.tmB, h->c.tmO, h->c.p));
+    else YSOD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, h->c.tmA, h->c.tmB, h->c.tmO, h->c.p));
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }
