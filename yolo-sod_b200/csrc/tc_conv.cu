@@ -285,7 +285,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp < EPI_WARPS) {
-        for (int i = threadIdx.x; i < p.cout_pad; i += EPI_THREADS) bias_s[i] = __ldg(p.bias + i);
+        // SiLU layers keep 0.5 * bias: the epilogue needs h = (acc + bias) / 2 = fma(acc, 0.5, 0.5 * bias), one instruction
+        const float bscale = (p.act == YSOD_ACT_SILU && !(p.debug & 16)) ? 0.5f : 1.0f;
+        for (int i = threadIdx.x; i < p.cout_pad; i += EPI_THREADS) bias_s[i] = bscale * __ldg(p.bias + i);
     }
     tc_fence_before();
     __syncthreads();
@@ -547,6 +549,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t trow0 = tmem_acc + ((uint32_t)(q * 32) << 16);
         int asel = 0;   // accumulator of tile i is i % 4 = 2 * asel + grp for this group's tiles
         const uint32_t row0 = sb + (uint32_t)m * p.row_bytes;
+        const uint32_t swz_x = (row0 >> 7) & swz_mask;   // swizzle XOR term of this thread's staging row
         uint32_t acc_phase = 0;
         TileIter ti;
         ti.init(blockIdx.x, p);
@@ -592,13 +595,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const float4 b0 = bs[0], b1 = bs[1], b2 = bs[2], b3 = bs[3];
                 tmem_ld_wait(v);
                 float f[16];
-                f[0] = __uint_as_float(v[0]) + b0.x; f[1] = __uint_as_float(v[1]) + b0.y; f[2] = __uint_as_float(v[2]) + b0.z; f[3] = __uint_as_float(v[3]) + b0.w;
-                f[4] = __uint_as_float(v[4]) + b1.x; f[5] = __uint_as_float(v[5]) + b1.y; f[6] = __uint_as_float(v[6]) + b1.z; f[7] = __uint_as_float(v[7]) + b1.w;
-                f[8] = __uint_as_float(v[8]) + b2.x; f[9] = __uint_as_float(v[9]) + b2.y; f[10] = __uint_as_float(v[10]) + b2.z; f[11] = __uint_as_float(v[11]) + b2.w;
-                f[12] = __uint_as_float(v[12]) + b3.x; f[13] = __uint_as_float(v[13]) + b3.y; f[14] = __uint_as_float(v[14]) + b3.z; f[15] = __uint_as_float(v[15]) + b3.w;
-                if (act == YSOD_ACT_SILU) act16<YSOD_ACT_SILU>(f);
-                else if (act == YSOD_ACT_GELU) act16<YSOD_ACT_GELU>(f);
-                else if (act == YSOD_ACT_RELU) act16<YSOD_ACT_RELU>(f);
+                const float bb[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
+                if (act == YSOD_ACT_SILU) {
+                    // x * sigmoid(x) = h + h * tanh(h) with h = x / 2: FFMA + MUFU + FFMA per element
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float h = fmaf(__uint_as_float(v[j]), 0.5f, bb[j]);
+                        f[j] = fmaf(h, tanh_approx(h), h);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + bb[j];
+                    if (act == YSOD_ACT_GELU) act16<YSOD_ACT_GELU>(f);
+                    else if (act == YSOD_ACT_RELU) act16<YSOD_ACT_RELU>(f);
+                }
                 if (add_res) {
                     const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
 #pragma unroll
@@ -608,27 +618,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     if (ch + 2 < nchunks) { ra = *reinterpret_cast<const uint4*>(rp + c0 + 32); rb = *reinterpret_cast<const uint4*>(rp + c0 + 40); }
                 }
-                // swizzled store into unit u = ch / chunks_per_unit: 16-byte piece index ^= (address bits [7..]) & mask (== TMA swizzle)
+                // swizzled store into unit u = ch / chunks_per_unit: 16-byte piece index ^= (address bits [7..]) & mask (== TMA swizzle).
+                // The staging units are 1 KB aligned and a thread always writes row m, so the XOR term is a per-thread constant.
                 const int u = ch / chunks_per_unit, cu = ch - u * chunks_per_unit;
                 const uint32_t row_addr = row0 + (uint32_t)u * unit_bytes;
                 if (out_f32) {
-                    const uint32_t off0 = (uint32_t)(cu * 64);
+                    const uint32_t p0 = (uint32_t)(cu * 4);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint32_t a = row_addr + off0 + 16u * j;
-                        a ^= ((a >> 7) & swz_mask) << 4;
-                        st_shared_v4(a, __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
-                                     __float_as_uint(f[4 * j + 3]));
-                    }
+                    for (int j = 0; j < 4; ++j)
+                        st_shared_v4(row_addr + (((p0 + j) ^ swz_x) << 4), __float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]),
+                                     __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
                 } else {
-                    const uint32_t off0 = (uint32_t)(cu * 32);
+                    const uint32_t p0 = (uint32_t)(cu * 2);
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        uint32_t a = row_addr + off0 + 16u * j;
-                        a ^= ((a >> 7) & swz_mask) << 4;
-                        st_shared_v4(a, pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
+                    for (int j = 0; j < 2; ++j)
+                        st_shared_v4(row_addr + (((p0 + j) ^ swz_x) << 4), pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
                                      pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
-                    }
                 }
             }
             // all TMEM reads of this warp are complete (tcgen05.wait::ld above): hand the accumulator back
