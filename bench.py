@@ -83,8 +83,9 @@ class ClockSampler:
         return out
 
 
-def cpu_reference_leg(steps, warmup, sample_batch=2, threads=None):
-    """The reference's CPU path (oracle port) on a bounded sample: forward + NMS on `sample_batch` 640^2 images per step."""
+def cpu_reference_leg(steps, warmup, sample_batch=BATCH, threads=None):
+    """The reference's CPU path (oracle port) on a bounded sample: forward + NMS on `sample_batch` 640^2 images per step
+    (default: one full batch of the workload, ~1.5 s on 24 cores)."""
     import torch
     import yolo_sod_b200  # noqa: F401
     from yolo_sod_b200 import cfg as ycfg, synth
@@ -129,7 +130,7 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": leg["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(args.batch, world), note="reference CPU path (oracle port of the pure-Python reference: the "
-                           "same ATen CPU kernels), each step a bounded sample of 2 images of this workload"),
+                           "same ATen CPU kernels), each step = one batch of this workload on all host cores"),
             "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": leg["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -281,8 +282,14 @@ def main():
     pk, pk_src = peaks()
     peak_tf = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1400.0)))
     ach_tf = (tc["flops"] / (tc["ms"] * 1e-3)) / 1e12 if tc["ms"] > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")   # dram__bytes_read+write per conv_tc launch, from the committed ncu launch list
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("conv_tc_kernel_dram_bytes_per_launch")
     roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv/linear)", "achieved": round(ach_tf, 2),
-                "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach_tf / peak_tf, 4), "traffic": None,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": round(ach_tf / peak_tf, 4), "traffic": traffic,
+                "traffic_unit": "bytes of DRAM read+write per launch (ncu, average over the launches of one step)",
+                "algorithmic_gflop_per_launch": round(tc["flops"] / 1e9 / max(tc["launches"], 1), 2),
                 "peak_source": f"{pk_src} bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches_per_step": tc["launches"], "algorithmic_gflop_per_step": round(tc["flops"] / 1e9, 2),
                 "share_of_step": round(tc["ms"] / tot_ms, 4) if tot_ms else None,
@@ -321,7 +328,7 @@ def main():
         lat.append(a.elapsed_time(b))
     lat.sort()
 
-    cpu = None if args.no_cpu_baseline else cpu_reference_leg(3, 1)
+    cpu = None if args.no_cpu_baseline else cpu_reference_leg(8, 1)   # ~10-15 s of CPU work
     n_nms = 4
     imgs = world * B * args.steps
     line = {
