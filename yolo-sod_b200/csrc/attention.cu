@@ -17,6 +17,7 @@ template <typename T, int D>
 __global__ void __launch_bounds__(64)
 mha_core_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, int L, int ldq, int ldk, int ldv,
                 long long bsq, long long bsk, long long bsv, float scale, T* __restrict__ out, int ldo, long long bso) {
+    ysod_pdl_sync();
     constexpr int KC = 64;
     constexpr int LDS = D + 4;
     __shared__ float Ks[KC * LDS];
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(128)
 mha_win_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v, int L,
                int ldq, int ldk, int ldv, long long bsq, long long bsk, long long bsv, float scale, __nv_bfloat16* __restrict__ out,
                int ldo, long long bso) {
+    ysod_pdl_sync();
     constexpr int LDQ = D + 8, LDV = 64 + 8;
     __shared__ __align__(16) __nv_bfloat16 Qs[64 * LDQ];
     __shared__ __align__(16) __nv_bfloat16 Ks[64 * LDQ];
@@ -207,6 +209,7 @@ __global__ void __launch_bounds__(128)
 mha_flash_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v, int L,
                  int ldq, int ldk, int ldv, long long bsq, long long bsk, long long bsv, float scale, __nv_bfloat16* __restrict__ out,
                  int ldo, long long bso) {
+    ysod_pdl_sync();
     constexpr int LDQ = D + 8, LDV = 64 + 8;
     __shared__ __align__(16) __nv_bfloat16 Qs[64 * LDQ];
     __shared__ __align__(16) __nv_bfloat16 Ks[64 * LDQ];
@@ -329,10 +332,10 @@ extern "C" int ysod_mha_core(const void* q, const void* k, const void* v, int dt
         ((uintptr_t)v % 16) == 0 && ((uintptr_t)out % 16) == 0 && bsq % 8 == 0 && bsk % 8 == 0 && bsv % 8 == 0 && bso % 8 == 0) {
         dim3 wgrid(heads, batch);
         if (D == 32)
-            mha_win_kernel<32><<<wgrid, 128, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, L, ldq, ldk, ldv,
+            ysod_launch(mha_win_kernel<32>, wgrid, 128, 0, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, L, ldq, ldk, ldv,
                                                       bsq, bsk, bsv, scale, (__nv_bfloat16*)out, ldo, bso);
         else
-            mha_win_kernel<64><<<wgrid, 128, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, L, ldq, ldk, ldv,
+            ysod_launch(mha_win_kernel<64>, wgrid, 128, 0, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, L, ldq, ldk, ldv,
                                                       bsq, bsk, bsv, scale, (__nv_bfloat16*)out, ldo, bso);
         YSOD_LAUNCH_CHECK();
         return YSOD_OK;
@@ -342,16 +345,16 @@ extern "C" int ysod_mha_core(const void* q, const void* k, const void* v, int dt
     if (dtype == YSOD_BF16 && (D == 32 || D == 64) && ((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && ((uintptr_t)v % 16) == 0 &&
         ((uintptr_t)out % 16) == 0 && bsq % 8 == 0 && bsk % 8 == 0 && bsv % 8 == 0 && bso % 8 == 0) {
         if (D == 32)
-            mha_flash_kernel<32><<<grid, 128, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, L, ldq, ldk, ldv,
+            ysod_launch(mha_flash_kernel<32>, grid, 128, 0, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, L, ldq, ldk, ldv,
                                                        bsq, bsk, bsv, scale, (__nv_bfloat16*)out, ldo, bso);
         else
-            mha_flash_kernel<64><<<grid, 128, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, L, ldq, ldk, ldv,
+            ysod_launch(mha_flash_kernel<64>, grid, 128, 0, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, L, ldq, ldk, ldv,
                                                        bsq, bsk, bsv, scale, (__nv_bfloat16*)out, ldo, bso);
         YSOD_LAUNCH_CHECK();
         return YSOD_OK;
     }
 #define LAUNCH(T, DD) \
-    mha_core_kernel<T, DD><<<grid, 64, 0, st>>>((const T*)q, (const T*)k, (const T*)v, L, ldq, ldk, ldv, bsq, bsk, bsv, scale, (T*)out, ldo, bso)
+    ysod_launch(mha_core_kernel<T, DD>, grid, 64, 0, st, (const T*)q, (const T*)k, (const T*)v, L, ldq, ldk, ldv, bsq, bsk, bsv, scale, (T*)out, ldo, bso)
     if (dtype == YSOD_F32 && D == 32) LAUNCH(float, 32);
     else if (dtype == YSOD_F32 && D == 64) LAUNCH(float, 64);
     else if (dtype == YSOD_BF16 && D == 32) LAUNCH(__nv_bfloat16, 32);

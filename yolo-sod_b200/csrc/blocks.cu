@@ -20,6 +20,7 @@ namespace {
 template <typename T>
 __global__ void gap_partial_kernel(const T* __restrict__ x, int HW, int C, int xcs, int S, float* __restrict__ psum,
                                    float* __restrict__ pmax) {
+    ysod_pdl_sync();
     extern __shared__ float sm[];  // [PL][C] sums, then [PL][C] maxes
     const int n = blockIdx.y, s = blockIdx.x;
     const int c8n = C >> 3;
@@ -70,6 +71,7 @@ __global__ void gap_partial_kernel(const T* __restrict__ x, int HW, int C, int x
 __global__ void se_gate_kernel(const float* __restrict__ psum, int S, int HW, int C, const float* __restrict__ w1,
                                const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2, int hid,
                                float* __restrict__ gate) {
+    ysod_pdl_sync();
     extern __shared__ float sm[];  // mean[C], h[hid]
     float* mean = sm;
     float* h = sm + C;
@@ -98,6 +100,7 @@ __global__ void se_gate_kernel(const float* __restrict__ psum, int S, int HW, in
 // CBAM channel gate: sigmoid(fc(avg) + fc(max)), fc = conv1x1(no bias) -> ReLU -> conv1x1(no bias) (cbam_block.py:14-23)
 __global__ void cbam_gate_kernel(const float* __restrict__ psum, const float* __restrict__ pmax, int S, int HW, int C,
                                  const float* __restrict__ w1, const float* __restrict__ w2, int hid, float* __restrict__ gate) {
+    ysod_pdl_sync();
     extern __shared__ float sm[];  // avg[C], mx[C], ha[hid], hm[hid]
     float* avg = sm;
     float* mx = sm + C;
@@ -154,6 +157,7 @@ struct StreamIdx {
 template <typename T>
 __global__ void scale_channels_kernel(const T* __restrict__ x, int HW, int C, int xcs, const float* __restrict__ gate,
                                       T* __restrict__ out, int ocs, unsigned npix) {
+    ysod_pdl_sync();
     const StreamIdx si(C >> 3);
     for (unsigned p0 = si.pix0; p0 < npix; p0 += 4 * si.pstep) {
         float v[4][8];
@@ -181,6 +185,7 @@ __global__ void scale_channels_kernel(const T* __restrict__ x, int HW, int C, in
 template <typename T>
 __global__ void cbam_stats_kernel(const T* __restrict__ x, int HW, int C, int xcs, const float* __restrict__ gate,
                                   float2* __restrict__ stats, long long npix) {
+    ysod_pdl_sync();
     const int c8n = C >> 3;
     const int G = c8n < 32 ? c8n : 32;
     const int lane = threadIdx.x & 31;
@@ -215,6 +220,7 @@ template <typename T>
 __global__ void cbam_apply_kernel(const T* __restrict__ x, int H, int W, int C, int xcs, const float* __restrict__ gate,
                                   const float2* __restrict__ stats, const float* __restrict__ wsp, int ks, T* __restrict__ out,
                                   int ocs, long long npix) {
+    ysod_pdl_sync();
     extern __shared__ float swsp[];  // [2][ks][ks]
     for (int i = threadIdx.x; i < 2 * ks * ks; i += blockDim.x) swsp[i] = wsp[i];
     __syncthreads();
@@ -262,6 +268,7 @@ __global__ void cbam_apply_kernel(const T* __restrict__ x, int H, int W, int C, 
 template <typename T>
 __global__ void cbam_stats_stream_kernel(const T* __restrict__ x, int HW, int C, int xcs, const float* __restrict__ gate,
                                          float2* __restrict__ stats, long long npix, int iters) {
+    ysod_pdl_sync();
     const int G = C >> 3;
     const int lane = threadIdx.x & 31;
     const int gl = lane % G;
@@ -306,6 +313,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 cbam_apply_tile_kernel(const T* __restrict__ x, int H, int W, int C, int xcs, const float* __restrict__ gate,
                        const float2* __restrict__ stats, const float* __restrict__ wsp, T* __restrict__ out, int ocs) {
+    ysod_pdl_sync();
     constexpr int TS = 16, HALO = 3, PS = TS + 2 * HALO;
     __shared__ float2 st[PS * PS];
     __shared__ float swsp[2 * 49];
@@ -364,6 +372,7 @@ cbam_apply_tile_kernel(const T* __restrict__ x, int H, int W, int C, int xcs, co
 // CoordAtt strip pools -> pooled[n][H + W][C] fp32: rows [0,H) = mean over w, rows [H,H+W) = mean over h (ca_block.py:42-45)
 template <typename T>
 __global__ void ca_pool_kernel(const T* __restrict__ x, int H, int W, int C, int xcs, float* __restrict__ pooled) {
+    ysod_pdl_sync();
     const int n = blockIdx.y;
     const int row = blockIdx.x;  // 0..H+W-1
     const int c8n = C >> 3;
@@ -399,6 +408,7 @@ __global__ void ca_pool_kernel(const T* __restrict__ x, int H, int W, int C, int
 __global__ void ca_gate_kernel(const float* __restrict__ pooled, int H, int W, int C, int mip, const float* __restrict__ w1,
                                const float* __restrict__ b1, const float* __restrict__ wh, const float* __restrict__ bh,
                                const float* __restrict__ ww, const float* __restrict__ bw, float* __restrict__ att) {
+    ysod_pdl_sync();
     extern __shared__ float sm[];  // y[mip]
     const int n = blockIdx.y, row = blockIdx.x;
     const float* p = pooled + ((size_t)n * (H + W) + row) * C;
@@ -423,6 +433,7 @@ __global__ void ca_gate_kernel(const float* __restrict__ pooled, int H, int W, i
 template <typename T>
 __global__ void ca_apply_kernel(const T* __restrict__ x, int H, int W, int C, int xcs, const float* __restrict__ att,
                                 T* __restrict__ out, int ocs, unsigned npix) {
+    ysod_pdl_sync();
     const StreamIdx si(C >> 3);
     for (unsigned p0 = si.pix0; p0 < npix; p0 += 4 * si.pstep) {
         float v[4][8];
@@ -452,6 +463,7 @@ __global__ void ca_apply_kernel(const T* __restrict__ x, int H, int W, int C, in
 template <typename T>
 __global__ void sppf_pool_kernel(const T* __restrict__ y0, int H, int W, int C, int xcs, int k, T* __restrict__ o1,
                                  T* __restrict__ o2, T* __restrict__ o3, int ocs, long long total) {
+    ysod_pdl_sync();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int c8n = C >> 3;
@@ -492,6 +504,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 sppf_plane_kernel(const T* __restrict__ y0, int H, int W, int xcs, int k, T* __restrict__ o1, T* __restrict__ o2,
                   T* __restrict__ o3, int ocs) {
+    ysod_pdl_sync();
     extern __shared__ float sppf_sm[];
     const int n = blockIdx.y, cg = blockIdx.x;
     const int HW = H * W, r = k / 2;
@@ -539,6 +552,7 @@ sppf_plane_kernel(const T* __restrict__ y0, int H, int W, int xcs, int k, T* __r
 template <typename T>
 __global__ void upsample_copy_kernel(const T* __restrict__ x, int H, int W, int C, int xcs, int scale, T* __restrict__ out,
                                      int ocs, unsigned npix) {
+    ysod_pdl_sync();
     const StreamIdx si(C >> 3);
     const unsigned Wo = W * scale, Ho = H * scale;
     for (unsigned p0 = si.pix0; p0 < npix; p0 += 4 * si.pstep) {
@@ -567,6 +581,7 @@ __global__ void layernorm_kernel(const T* __restrict__ x, long long rows, int C,
                                  const float* __restrict__ beta, float eps, T* __restrict__ out, int ldo, int G,
                                  // window-partition gather (GATHER): x is NHWC, rows are window tokens
                                  int H, int W, int wh, int ww, int nWh, int nWw, T* __restrict__ raw_out) {
+    ysod_pdl_sync();
     const int lane = threadIdx.x & 31;
     const int gl = lane % G;
     const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -637,6 +652,7 @@ template <typename T, bool GATHER>
 __global__ void layernorm_stream_kernel(const T* __restrict__ x, long long rows, int C, int ldx, const float* __restrict__ gamma,
                                         const float* __restrict__ beta, float eps, T* __restrict__ out, int ldo, int iters,
                                         int H, int W, int wh, int ww, int nWh, int nWw, T* __restrict__ raw_out) {
+    ysod_pdl_sync();
     const int G = C >> 3;
     const int lane = threadIdx.x & 31;
     const int gl = lane % G;
@@ -699,6 +715,7 @@ __global__ void layernorm_stream_kernel(const T* __restrict__ x, long long rows,
 template <typename T>
 __global__ void window_reverse_kernel(const T* __restrict__ tok, int ldt, int H, int W, int C, int wh, int ww, int nWh, int nWw,
                                       T* __restrict__ out, int ocs, unsigned npix) {
+    ysod_pdl_sync();
     const StreamIdx si(C >> 3);
     for (unsigned p0 = si.pix0; p0 < npix; p0 += 4 * si.pstep) {
         float v[4][8];
@@ -725,6 +742,7 @@ __global__ void window_reverse_kernel(const T* __restrict__ tok, int ldt, int H,
 template <typename T>
 __global__ void adaptive_pool_rows_kernel(const T* __restrict__ x, int H, int W, int C, int xcs, int OH, T* __restrict__ out,
                                           int ocs, long long total) {
+    ysod_pdl_sync();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int c8n = C >> 3;
@@ -752,6 +770,7 @@ __global__ void adaptive_pool_rows_kernel(const T* __restrict__ x, int H, int W,
 template <typename T>
 __global__ void bilinear_rows_kernel(const T* __restrict__ x, int IH, int W, int C, int xcs, int OH, T* __restrict__ out, int ocs,
                                      long long total) {
+    ysod_pdl_sync();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= total) return;
     const int c8n = C >> 3;
@@ -808,7 +827,7 @@ int ysod_gap_partial(const void* x, int dtype, int N, int HW, int C, int xcs, in
     const size_t smem = (size_t)2 * PL * C * sizeof(float);
     YSOD_CHECK_ARG(smem <= 48 * 1024, "ysod_gap_partial: smem");
     dim3 grid(S, N);
-    YSOD_DISPATCH(dtype, (gap_partial_kernel<T><<<grid, 256, smem, st>>>((const T*)x, HW, C, xcs, S, psum, pmax)));
+    YSOD_DISPATCH(dtype, (ysod_launch(gap_partial_kernel<T>, grid, 256, smem, st, (const T*)x, HW, C, xcs, S, psum, pmax)));
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }
@@ -816,7 +835,7 @@ int ysod_gap_partial(const void* x, int dtype, int N, int HW, int C, int xcs, in
 int ysod_se_gate(const float* psum, int N, int S, int HW, int C, const float* w1, const float* b1, const float* w2,
                  const float* b2, int hid, float* gate, cudaStream_t st) {
     YSOD_CHECK_ARG(psum && w1 && b1 && w2 && b2 && gate, "ysod_se_gate: null pointer");
-    se_gate_kernel<<<N, 256, (C + hid) * sizeof(float), st>>>(psum, S, HW, C, w1, b1, w2, b2, hid, gate);
+    ysod_launch(se_gate_kernel, N, 256, (C + hid) * sizeof(float), st, psum, S, HW, C, w1, b1, w2, b2, hid, gate);
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }
@@ -824,7 +843,7 @@ int ysod_se_gate(const float* psum, int N, int S, int HW, int C, const float* w1
 int ysod_cbam_gate(const float* psum, const float* pmax, int N, int S, int HW, int C, const float* w1, const float* w2, int hid,
                    float* gate, cudaStream_t st) {
     YSOD_CHECK_ARG(psum && pmax && w1 && w2 && gate, "ysod_cbam_gate: null pointer");
-    cbam_gate_kernel<<<N, 256, (2 * C + 2 * hid) * sizeof(float), st>>>(psum, pmax, S, HW, C, w1, w2, hid, gate);
+    ysod_launch(cbam_gate_kernel, N, 256, (2 * C + 2 * hid) * sizeof(float), st, psum, pmax, S, HW, C, w1, w2, hid, gate);
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }
@@ -833,7 +852,7 @@ int ysod_scale_channels(const void* x, int dtype, int N, int HW, int C, int xcs,
                         cudaStream_t st) {
     YSOD_CHECK_ARG(x && gate && out && C % 8 == 0 && xcs % 8 == 0 && ocs % 8 == 0, "ysod_scale_channels: bad args");
     const long long total = (long long)N * HW * (C / 8);
-    YSOD_DISPATCH(dtype, (scale_channels_kernel<T><<<stream_blocks(total, stream_threads(C), 4), stream_threads(C), 0, st>>>((const T*)x, HW, C, xcs, gate, (T*)out, ocs, (unsigned)(total / (C / 8)))));
+    YSOD_DISPATCH(dtype, (ysod_launch(scale_channels_kernel<T>, stream_blocks(total, stream_threads(C), 4), stream_threads(C), 0, st, (const T*)x, HW, C, xcs, gate, (T*)out, ocs, (unsigned)(total / (C / 8)))));
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }
@@ -848,12 +867,12 @@ int ysod_cbam_stats(const void* x, int dtype, int N, int HW, int C, int xcs, con
         const int blocks = stream_blocks(npix * c8n, 256, 4);
         const long long ngroups = (long long)blocks * 256 / c8n;
         const int iters = (int)((npix + 4 * ngroups - 1) / (4 * ngroups));
-        YSOD_DISPATCH(dtype, (cbam_stats_stream_kernel<T><<<blocks, 256, 0, st>>>((const T*)x, HW, C, xcs, gate, (float2*)stats, npix, iters)));
+        YSOD_DISPATCH(dtype, (ysod_launch(cbam_stats_stream_kernel<T>, blocks, 256, 0, st, (const T*)x, HW, C, xcs, gate, (float2*)stats, npix, iters)));
         YSOD_LAUNCH_CHECK();
         return YSOD_OK;
     }
     const long long warps = (npix + (32 / G) - 1) / (32 / G);
-    YSOD_DISPATCH(dtype, (cbam_stats_kernel<T><<<blocks_for(warps * 32, 256), 256, 0, st>>>((const T*)x, HW, C, xcs, gate, (float2*)stats, npix)));
+    YSOD_DISPATCH(dtype, (ysod_launch(cbam_stats_kernel<T>, blocks_for(warps * 32, 256), 256, 0, st, (const T*)x, HW, C, xcs, gate, (float2*)stats, npix)));
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }
@@ -867,12 +886,12 @@ int ysod_cbam_apply(const void* x, int dtype, int N, int H, int W, int C, int xc
     const long long npix = (long long)N * H * W;
     if (ks == 7 && N <= 65535) {   // tiled variant (cbam_block.py:27: kernel_size 7)
         dim3 grid(ysod_cdiv(W, 16), ysod_cdiv(H, 16), N);
-        YSOD_DISPATCH(dtype, (cbam_apply_tile_kernel<T><<<grid, 256, 0, st>>>((const T*)x, H, W, C, xcs, gate, (const float2*)stats, wsp, (T*)out, ocs)));
+        YSOD_DISPATCH(dtype, (ysod_launch(cbam_apply_tile_kernel<T>, grid, 256, 0, st, (const T*)x, H, W, C, xcs, gate, (const float2*)stats, wsp, (T*)out, ocs)));
         YSOD_LAUNCH_CHECK();
         return YSOD_OK;
     }
     const long long warps = (npix + (32 / G) - 1) / (32 / G);
-    YSOD_DISPATCH(dtype, (cbam_apply_kernel<T><<<blocks_for(warps * 32, 256), 256, 2 * ks * ks * sizeof(float), st>>>(
+    YSOD_DISPATCH(dtype, (ysod_launch(cbam_apply_kernel<T>, blocks_for(warps * 32, 256), 256, 2 * ks * ks * sizeof(float), st, 
                              (const T*)x, H, W, C, xcs, gate, (const float2*)stats, wsp, ks, (T*)out, ocs, npix)));
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
@@ -882,7 +901,7 @@ int ysod_ca_pool(const void* x, int dtype, int N, int H, int W, int C, int xcs, 
     YSOD_CHECK_ARG(x && pooled && C % 8 == 0 && xcs % 8 == 0, "ysod_ca_pool: bad args");
     dim3 grid(H + W, N);
     const int threads = (C / 8) < 32 ? 32 : ((C / 8 + 31) / 32) * 32;
-    YSOD_DISPATCH(dtype, (ca_pool_kernel<T><<<grid, threads > 256 ? 256 : threads, 0, st>>>((const T*)x, H, W, C, xcs, pooled)));
+    YSOD_DISPATCH(dtype, (ysod_launch(ca_pool_kernel<T>, grid, threads > 256 ? 256 : threads, 0, st, (const T*)x, H, W, C, xcs, pooled)));
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }
@@ -891,7 +910,7 @@ int ysod_ca_gate(const float* pooled, int N, int H, int W, int C, int mip, const
                  const float* bh, const float* ww, const float* bw, float* att, cudaStream_t st) {
     YSOD_CHECK_ARG(pooled && w1 && b1 && wh && bh && ww && bw && att, "ysod_ca_gate: null pointer");
     dim3 grid(H + W, N);
-    ca_gate_kernel<<<grid, 128, mip * sizeof(float), st>>>(pooled, H, W, C, mip, w1, b1, wh, bh, ww, bw, att);
+    ysod_launch(ca_gate_kernel, grid, 128, mip * sizeof(float), st, pooled, H, W, C, mip, w1, b1, wh, bh, ww, bw, att);
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }
@@ -900,7 +919,7 @@ int ysod_ca_apply(const void* x, int dtype, int N, int H, int W, int C, int xcs,
                   cudaStream_t st) {
     YSOD_CHECK_ARG(x && att && out && C % 8 == 0 && xcs % 8 == 0 && ocs % 8 == 0, "ysod_ca_apply: bad args");
     const long long total = (long long)N * H * W * (C / 8);
-    YSOD_DISPATCH(dtype, (ca_apply_kernel<T><<<stream_blocks(total, stream_threads(C), 4), stream_threads(C), 0, st>>>((const T*)x, H, W, C, xcs, att, (T*)out, ocs, (unsigned)(total / (C / 8)))));
+    YSOD_DISPATCH(dtype, (ysod_launch(ca_apply_kernel<T>, stream_blocks(total, stream_threads(C), 4), stream_threads(C), 0, st, (const T*)x, H, W, C, xcs, att, (T*)out, ocs, (unsigned)(total / (C / 8)))));
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }
@@ -915,12 +934,12 @@ int ysod_sppf_pool(const void* y0, int dtype, int N, int H, int W, int C, int xc
             YSOD_CUDA(cudaFuncSetAttribute(sppf_plane_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             YSOD_CUDA(cudaFuncSetAttribute(sppf_plane_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         }
-        YSOD_DISPATCH(dtype, (sppf_plane_kernel<T><<<grid, 256, smem, st>>>((const T*)y0, H, W, xcs, k, (T*)o1, (T*)o2, (T*)o3, ocs)));
+        YSOD_DISPATCH(dtype, (ysod_launch(sppf_plane_kernel<T>, grid, 256, smem, st, (const T*)y0, H, W, xcs, k, (T*)o1, (T*)o2, (T*)o3, ocs)));
         YSOD_LAUNCH_CHECK();
         return YSOD_OK;
     }
     const long long total = (long long)N * H * W * (C / 8);
-    YSOD_DISPATCH(dtype, (sppf_pool_kernel<T><<<blocks_for(total, 128), 128, 0, st>>>((const T*)y0, H, W, C, xcs, k, (T*)o1, (T*)o2, (T*)o3, ocs, total)));
+    YSOD_DISPATCH(dtype, (ysod_launch(sppf_pool_kernel<T>, blocks_for(total, 128), 128, 0, st, (const T*)y0, H, W, C, xcs, k, (T*)o1, (T*)o2, (T*)o3, ocs, total)));
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }
@@ -929,7 +948,7 @@ int ysod_upsample_copy(const void* x, int dtype, int N, int H, int W, int C, int
                        cudaStream_t st) {
     YSOD_CHECK_ARG(x && out && C % 8 == 0 && xcs % 8 == 0 && ocs % 8 == 0 && scale >= 1, "ysod_upsample_copy: bad args");
     const long long total = (long long)N * H * scale * W * scale * (C / 8);
-    YSOD_DISPATCH(dtype, (upsample_copy_kernel<T><<<stream_blocks(total, stream_threads(C), 4), stream_threads(C), 0, st>>>((const T*)x, H, W, C, xcs, scale, (T*)out, ocs, (unsigned)(total / (C / 8)))));
+    YSOD_DISPATCH(dtype, (ysod_launch(upsample_copy_kernel<T>, stream_blocks(total, stream_threads(C), 4), stream_threads(C), 0, st, (const T*)x, H, W, C, xcs, scale, (T*)out, ocs, (unsigned)(total / (C / 8)))));
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }
@@ -942,12 +961,12 @@ int ysod_layernorm(const void* x, int dtype, long long rows, int C, int ldx, con
         const int blocks = stream_blocks(rows * (C / 8), 256, 4);
         const long long ngroups = (long long)blocks * 256 / (C / 8);
         const int iters = (int)((rows + 4 * ngroups - 1) / (4 * ngroups));
-        YSOD_DISPATCH(dtype, (layernorm_stream_kernel<T, false><<<blocks, 256, 0, st>>>((const T*)x, rows, C, ldx, gamma, beta, eps, (T*)out, ldo,
+        YSOD_DISPATCH(dtype, (ysod_launch(layernorm_stream_kernel<T, false>, blocks, 256, 0, st, (const T*)x, rows, C, ldx, gamma, beta, eps, (T*)out, ldo,
                                                                                       iters, 0, 0, 1, 1, 1, 1, nullptr)));
         YSOD_LAUNCH_CHECK();
         return YSOD_OK;
     }
-    YSOD_DISPATCH(dtype, (layernorm_kernel<T, false><<<blocks_for(rows * G, 256), 256, 0, st>>>(
+    YSOD_DISPATCH(dtype, (ysod_launch(layernorm_kernel<T, false>, blocks_for(rows * G, 256), 256, 0, st, 
                              (const T*)x, rows, C, ldx, gamma, beta, eps, (T*)out, ldo, G, 0, 0, 1, 1, 1, 1, nullptr)));
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
@@ -964,12 +983,12 @@ int ysod_window_partition_ln(const void* x, int dtype, int N, int H, int W, int 
         const int blocks = stream_blocks(rows * (C / 8), 256, 4);
         const long long ngroups = (long long)blocks * 256 / (C / 8);
         const int iters = (int)((rows + 4 * ngroups - 1) / (4 * ngroups));
-        YSOD_DISPATCH(dtype, (layernorm_stream_kernel<T, true><<<blocks, 256, 0, st>>>((const T*)x, rows, C, xcs, gamma, beta, eps, (T*)norm_out, ldo,
+        YSOD_DISPATCH(dtype, (ysod_launch(layernorm_stream_kernel<T, true>, blocks, 256, 0, st, (const T*)x, rows, C, xcs, gamma, beta, eps, (T*)norm_out, ldo,
                                                                                      iters, H, W, wh, ww, nWh, nWw, (T*)raw_out)));
         YSOD_LAUNCH_CHECK();
         return YSOD_OK;
     }
-    YSOD_DISPATCH(dtype, (layernorm_kernel<T, true><<<blocks_for(rows * G, 256), 256, 0, st>>>(
+    YSOD_DISPATCH(dtype, (ysod_launch(layernorm_kernel<T, true>, blocks_for(rows * G, 256), 256, 0, st, 
                              (const T*)x, rows, C, xcs, gamma, beta, eps, (T*)norm_out, ldo, G, H, W, wh, ww, nWh, nWw, (T*)raw_out)));
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
@@ -979,7 +998,7 @@ int ysod_window_reverse(const void* tok, int dtype, int ldt, int N, int H, int W
                         int ocs, cudaStream_t st) {
     YSOD_CHECK_ARG(tok && out && C % 8 == 0 && ldt % 8 == 0 && ocs % 8 == 0, "ysod_window_reverse: bad args");
     const long long total = (long long)N * H * W * (C / 8);
-    YSOD_DISPATCH(dtype, (window_reverse_kernel<T><<<stream_blocks(total, stream_threads(C), 4), stream_threads(C), 0, st>>>((const T*)tok, ldt, H, W, C, wh, ww, nWh, nWw, (T*)out, ocs, (unsigned)(total / (C / 8)))));
+    YSOD_DISPATCH(dtype, (ysod_launch(window_reverse_kernel<T>, stream_blocks(total, stream_threads(C), 4), stream_threads(C), 0, st, (const T*)tok, ldt, H, W, C, wh, ww, nWh, nWw, (T*)out, ocs, (unsigned)(total / (C / 8)))));
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }
@@ -988,7 +1007,7 @@ int ysod_adaptive_pool_rows(const void* x, int dtype, int N, int H, int W, int C
                             cudaStream_t st) {
     YSOD_CHECK_ARG(x && out && C % 8 == 0 && xcs % 8 == 0 && ocs % 8 == 0 && OH >= 1, "ysod_adaptive_pool_rows: bad args");
     const long long total = (long long)N * OH * W * (C / 8);
-    YSOD_DISPATCH(dtype, (adaptive_pool_rows_kernel<T><<<blocks_for(total, 256), 256, 0, st>>>((const T*)x, H, W, C, xcs, OH, (T*)out, ocs, total)));
+    YSOD_DISPATCH(dtype, (ysod_launch(adaptive_pool_rows_kernel<T>, blocks_for(total, 256), 256, 0, st, (const T*)x, H, W, C, xcs, OH, (T*)out, ocs, total)));
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }
@@ -996,7 +1015,7 @@ int ysod_adaptive_pool_rows(const void* x, int dtype, int N, int H, int W, int C
 int ysod_bilinear_rows(const void* x, int dtype, int N, int IH, int W, int C, int xcs, int OH, void* out, int ocs, cudaStream_t st) {
     YSOD_CHECK_ARG(x && out && C % 8 == 0 && xcs % 8 == 0 && ocs % 8 == 0 && OH >= 1, "ysod_bilinear_rows: bad args");
     const long long total = (long long)N * OH * W * (C / 8);
-    YSOD_DISPATCH(dtype, (bilinear_rows_kernel<T><<<blocks_for(total, 256), 256, 0, st>>>((const T*)x, IH, W, C, xcs, OH, (T*)out, ocs, total)));
+    YSOD_DISPATCH(dtype, (ysod_launch(bilinear_rows_kernel<T>, blocks_for(total, 256), 256, 0, st, (const T*)x, IH, W, C, xcs, OH, (T*)out, ocs, total)));
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }

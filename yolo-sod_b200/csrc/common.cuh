@@ -56,6 +56,29 @@ static inline int ysod_cdiv(long long a, long long b) { return (int)((a + b - 1)
 #define YSOD_ACT_HSIGMOID 5  // relu6(x+3)/6
 
 #ifdef __CUDACC__
+// Programmatic dependent launch (PDL): every kernel is launched with programmaticStreamSerializationAllowed, so its CTAs may be
+// scheduled while the previous kernel in the stream is still draining; ysod_pdl_sync() at the top of the kernel blocks until
+// the previous grid has completed and its memory is visible, then lets the next kernel start launching in turn. This hides
+// launch latency and CTA scheduling between the ~130 back-to-back kernels of one forward (inside or outside a CUDA graph).
+__device__ __forceinline__ void ysod_pdl_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t ysod_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 template <typename T> __device__ __forceinline__ float ysod_ld(const T* p);
 template <> __device__ __forceinline__ float ysod_ld<float>(const float* p) { return *p; }
 template <> __device__ __forceinline__ float ysod_ld<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }

@@ -15,6 +15,7 @@ template <typename TI, typename TO>
 __global__ void conv_direct_kernel(const TI* __restrict__ x, const TI* __restrict__ w, const float* __restrict__ bias,
                                    const TI* __restrict__ res, TO* __restrict__ out, int N, int H, int W, int Cin, int xcs,
                                    int Ho, int Wo, int Cout, int ocs, int rcs, int k, int s, int pad, int groups, int act) {
+    ysod_pdl_sync();
     const int cog_n = (Cout + 3) >> 2;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)N * Ho * Wo * cog_n;
@@ -73,6 +74,7 @@ template <typename T>
 __global__ void dwconv_kernel(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
                               const T* __restrict__ res, T* __restrict__ out, int N, int H, int W, int C, int xcs, int Ho,
                               int Wo, int ocs, int rcs, int k, int s, int pad, int act) {
+    ysod_pdl_sync();
     const int c8n = C >> 3;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)N * Ho * Wo * c8n;
@@ -114,6 +116,7 @@ template <typename TO>
 __global__ void stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
                                  TO* __restrict__ out, int N, int H, int W, int Ho, int Wo, int Cout, int ocs, int k, int s,
                                  int pad, int act) {
+    ysod_pdl_sync();
     extern __shared__ float sw[];  // [Cout][k*k*3] + bias
     const int wn = Cout * k * k * 3;
     for (int i = threadIdx.x; i < wn; i += blockDim.x) sw[i] = w[i];
@@ -159,6 +162,7 @@ template <typename TO, int CO>
 __global__ void __launch_bounds__(256)
 stem_conv3x3s2_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
                       TO* __restrict__ out, int H, int W, int Ho, int Wo, int Cout, int ocs, int act) {
+    ysod_pdl_sync();
     constexpr int PH = 17, PW = 65, PWP = 66;
     __shared__ float patch[3 * PH * PWP];
     __shared__ __align__(16) float sw[27 * CO];
@@ -237,7 +241,7 @@ int ysod_conv_direct(const void* x, int dtype, int N, int H, int W, int Cin, int
     const long long total = (long long)N * Ho * Wo * ((Cout + 3) / 4);
     const int blocks = ysod_cdiv(total, 256);
 #define LAUNCH(TI, TO)                                                                                                    \
-    conv_direct_kernel<TI, TO><<<blocks, 256, 0, stream>>>((const TI*)x, (const TI*)w, bias, (const TI*)res, (TO*)out, N, H, W, \
+    ysod_launch(conv_direct_kernel<TI, TO>, blocks, 256, 0, stream, (const TI*)x, (const TI*)w, bias, (const TI*)res, (TO*)out, N, H, W, \
                                                            Cin, xcs, Ho, Wo, Cout, ocs, rcs, k, s, pad, groups, act)
     if (dtype == YSOD_F32 && out_dtype == YSOD_F32) LAUNCH(float, float);
     else if (dtype == YSOD_BF16 && out_dtype == YSOD_BF16) LAUNCH(__nv_bfloat16, __nv_bfloat16);
@@ -259,10 +263,10 @@ int ysod_dwconv(const void* x, int dtype, int N, int H, int W, int C, int xcs, c
     const long long total = (long long)N * Ho * Wo * (C / 8);
     const int blocks = ysod_cdiv(total, 256);
     if (dtype == YSOD_F32)
-        dwconv_kernel<float><<<blocks, 256, 0, stream>>>((const float*)x, (const float*)w, bias, (const float*)res, (float*)out, N,
+        ysod_launch(dwconv_kernel<float>, blocks, 256, 0, stream, (const float*)x, (const float*)w, bias, (const float*)res, (float*)out, N,
                                                          H, W, C, xcs, Ho, Wo, ocs, rcs, k, s, pad, act);
     else
-        dwconv_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias,
+        ysod_launch(dwconv_kernel<__nv_bfloat16>, blocks, 256, 0, stream, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias,
                                                                  (const __nv_bfloat16*)res, (__nv_bfloat16*)out, N, H, W, C, xcs,
                                                                  Ho, Wo, ocs, rcs, k, s, pad, act);
     YSOD_LAUNCH_CHECK();
@@ -278,11 +282,11 @@ int ysod_stem_conv(const float* img, int N, int H, int W, const float* w, const 
     if (k == 3 && s == 2 && pad == 1 && Cout % 16 == 0) {
         dim3 grid(ysod_cdiv(Wo, 32), ysod_cdiv(Ho, 8), N), block(32, 8);
         if (Cout % 32 == 0) {
-            if (out_dtype == YSOD_F32) stem_conv3x3s2_kernel<float, 32><<<grid, block, 0, stream>>>(img, w, bias, (float*)out, H, W, Ho, Wo, Cout, ocs, act);
-            else stem_conv3x3s2_kernel<__nv_bfloat16, 32><<<grid, block, 0, stream>>>(img, w, bias, (__nv_bfloat16*)out, H, W, Ho, Wo, Cout, ocs, act);
+            if (out_dtype == YSOD_F32) ysod_launch(stem_conv3x3s2_kernel<float, 32>, grid, block, 0, stream, img, w, bias, (float*)out, H, W, Ho, Wo, Cout, ocs, act);
+            else ysod_launch(stem_conv3x3s2_kernel<__nv_bfloat16, 32>, grid, block, 0, stream, img, w, bias, (__nv_bfloat16*)out, H, W, Ho, Wo, Cout, ocs, act);
         } else {
-            if (out_dtype == YSOD_F32) stem_conv3x3s2_kernel<float, 16><<<grid, block, 0, stream>>>(img, w, bias, (float*)out, H, W, Ho, Wo, Cout, ocs, act);
-            else stem_conv3x3s2_kernel<__nv_bfloat16, 16><<<grid, block, 0, stream>>>(img, w, bias, (__nv_bfloat16*)out, H, W, Ho, Wo, Cout, ocs, act);
+            if (out_dtype == YSOD_F32) ysod_launch(stem_conv3x3s2_kernel<float, 16>, grid, block, 0, stream, img, w, bias, (float*)out, H, W, Ho, Wo, Cout, ocs, act);
+            else ysod_launch(stem_conv3x3s2_kernel<__nv_bfloat16, 16>, grid, block, 0, stream, img, w, bias, (__nv_bfloat16*)out, H, W, Ho, Wo, Cout, ocs, act);
         }
         YSOD_LAUNCH_CHECK();
         return YSOD_OK;
@@ -292,9 +296,9 @@ int ysod_stem_conv(const float* img, int N, int H, int W, const float* w, const 
     const size_t smem = (size_t)(Cout * k * k * 3 + Cout) * sizeof(float);
     YSOD_CHECK_ARG(smem <= 48 * 1024, "ysod_stem_conv: weights do not fit in shared memory");
     if (out_dtype == YSOD_F32)
-        stem_conv_kernel<float><<<blocks, 256, smem, stream>>>(img, w, bias, (float*)out, N, H, W, Ho, Wo, Cout, ocs, k, s, pad, act);
+        ysod_launch(stem_conv_kernel<float>, blocks, 256, smem, stream, img, w, bias, (float*)out, N, H, W, Ho, Wo, Cout, ocs, k, s, pad, act);
     else
-        stem_conv_kernel<__nv_bfloat16><<<blocks, 256, smem, stream>>>(img, w, bias, (__nv_bfloat16*)out, N, H, W, Ho, Wo, Cout, ocs,
+        ysod_launch(stem_conv_kernel<__nv_bfloat16>, blocks, 256, smem, stream, img, w, bias, (__nv_bfloat16*)out, N, H, W, Ho, Wo, Cout, ocs,
                                                                        k, s, pad, act);
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;

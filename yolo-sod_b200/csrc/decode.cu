@@ -15,6 +15,7 @@ namespace {
 template <typename T, int REG>
 __global__ void dfl_decode_kernel(const T* __restrict__ raw, int H, int W, int cs, int nc, float stride,
                                   float* __restrict__ y, int A_total, int a_off) {
+    ysod_pdl_sync();
     const int hw = H * W;
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
@@ -58,9 +59,9 @@ extern "C" int ysod_dfl_decode(const void* raw, int dtype, int B, int H, int W, 
     YSOD_CHECK_ARG(a_off >= 0 && a_off + H * W <= A_total, "ysod_dfl_decode: anchor range out of bounds");
     dim3 grid(ysod_cdiv(H * W, 128), B);
     if (dtype == YSOD_F32)
-        dfl_decode_kernel<float, 16><<<grid, 128, 0, stream>>>((const float*)raw, H, W, cs, nc, stride, y, A_total, a_off);
+        ysod_launch(dfl_decode_kernel<float, 16>, grid, 128, 0, stream, (const float*)raw, H, W, cs, nc, stride, y, A_total, a_off);
     else if (dtype == YSOD_BF16)
-        dfl_decode_kernel<__nv_bfloat16, 16><<<grid, 128, 0, stream>>>((const __nv_bfloat16*)raw, H, W, cs, nc, stride, y, A_total, a_off);
+        ysod_launch(dfl_decode_kernel<__nv_bfloat16, 16>, grid, 128, 0, stream, (const __nv_bfloat16*)raw, H, W, cs, nc, stride, y, A_total, a_off);
     else {
         ysod_set_error("ysod_dfl_decode: bad dtype %d", dtype);
         return YSOD_ERR_INVALID;

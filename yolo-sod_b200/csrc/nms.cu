@@ -31,6 +31,7 @@ constexpr int GREEDY_THREADS = 1024;
 __global__ void nms_score_kernel(const float* __restrict__ pred, int nc, int A, float conf_thres,
                                  const int* __restrict__ classes, int n_classes, int multi_label,
                                  float* __restrict__ conf, int* __restrict__ cls) {
+    ysod_pdl_sync();
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     if (a >= A) return;
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 1)
 nms_sort_kernel(const float* __restrict__ conf_all, int M, int cap, int all_candidates, uint32_t* __restrict__ ws_keys0,
                 uint32_t* __restrict__ ws_vals0, uint32_t* __restrict__ ws_keys1, uint32_t* __restrict__ ws_vals1,
                 int* __restrict__ order_all, float* __restrict__ sscore_all, int* __restrict__ count_all) {
+    ysod_pdl_sync();
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* conf = conf_all + (size_t)b * M;
@@ -205,6 +207,7 @@ __device__ __forceinline__ float4 load_xyxy(const float* __restrict__ pred, int 
 __global__ void nms_gather_kernel(const float* __restrict__ pred, int nc, int A, int cap, int multi_label,
                                   const int* __restrict__ order_all, const int* __restrict__ cls_all,
                                   const int* __restrict__ count_all, float class_mult, float4* __restrict__ boxes_all) {
+    ysod_pdl_sync();
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = blockIdx.y;
     if (r >= count_all[b]) return;
@@ -227,6 +230,7 @@ nms_greedy_kernel(const float* __restrict__ pred, int nc, int A, int cap, int mu
                   const float* __restrict__ sscore_all, const int* __restrict__ cls_all,
                   const int* __restrict__ count_all, float* __restrict__ det_all, int* __restrict__ index_all,
                   int* __restrict__ nkeep_all, int box_cache) {
+    ysod_pdl_sync();
     extern __shared__ uint32_t smem_u32[];
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -358,6 +362,7 @@ nms_chunk_kernel(const float* __restrict__ pred, int nc, int A, int cap, int mul
                  const float4* __restrict__ boxes_all, const int* __restrict__ order_all, const float* __restrict__ sscore_all,
                  const int* __restrict__ cls_all, const int* __restrict__ count_all, float* __restrict__ det_all,
                  int* __restrict__ index_all, int* __restrict__ nkeep_all) {
+    ysod_pdl_sync();
     extern __shared__ uint32_t smem_u32[];
     float4* kbox = reinterpret_cast<float4*>(smem_u32);                    // max_det kept boxes
     float* karea = reinterpret_cast<float*>(kbox + max_det);               // their areas
@@ -504,19 +509,19 @@ int ysod_nms_batched(const float* pred, int B, int nc, int A, float conf_thres, 
     const size_t greedy_smem = greedy_base + (size_t)box_cache * 16;
     {
         dim3 grid(ysod_cdiv(A, 256), B);
-        nms_score_kernel<<<grid, 256, 0, stream>>>(pred, nc, A, conf_thres, classes, n_classes, multi_label, w.conf, w.cls);
+        ysod_launch(nms_score_kernel, grid, 256, 0, stream, pred, nc, A, conf_thres, classes, n_classes, multi_label, w.conf, w.cls);
         YSOD_LAUNCH_CHECK();
     }
-    nms_sort_kernel<<<B, SORT_THREADS, 0, stream>>>(w.conf, (int)M, cap, 0, w.k0, w.v0, w.k1, w.v1, w.order, w.sscore, w.count);
+    ysod_launch(nms_sort_kernel, B, SORT_THREADS, 0, stream, w.conf, (int)M, cap, 0, w.k0, w.v0, w.k1, w.v1, w.order, w.sscore, w.count);
     YSOD_LAUNCH_CHECK();
     {
         dim3 grid(ysod_cdiv(cap, 256), B);
-        nms_gather_kernel<<<grid, 256, 0, stream>>>(pred, nc, A, cap, multi_label, w.order, w.cls, w.count,
+        ysod_launch(nms_gather_kernel, grid, 256, 0, stream, pred, nc, A, cap, multi_label, w.order, w.cls, w.count,
                                                     agnostic ? 0.0f : max_wh, w.boxes);
         YSOD_LAUNCH_CHECK();
     }
     if (max_det <= 2048) {   // kept-list formulation: the detection path (max_det = 300)
-        nms_chunk_kernel<<<B, GREEDY_THREADS, (size_t)max_det * 24, stream>>>(pred, nc, A, cap, multi_label, max_det, thr_f, w.boxes, w.order,
+        ysod_launch(nms_chunk_kernel, B, GREEDY_THREADS, (size_t)max_det * 24, stream, pred, nc, A, cap, multi_label, max_det, thr_f, w.boxes, w.order,
                                                                               w.sscore, w.cls, w.count, out_det, out_index, out_count);
         YSOD_LAUNCH_CHECK();
         return YSOD_OK;
@@ -524,7 +529,7 @@ int ysod_nms_batched(const float* pred, int B, int nc, int A, float conf_thres, 
     if (greedy_smem > 48 * 1024) {
         YSOD_CUDA(cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)greedy_smem));
     }
-    nms_greedy_kernel<<<B, GREEDY_THREADS, greedy_smem, stream>>>(pred, nc, A, cap, multi_label, max_det, thr_f, w.boxes,
+    ysod_launch(nms_greedy_kernel, B, GREEDY_THREADS, greedy_smem, stream, pred, nc, A, cap, multi_label, max_det, thr_f, w.boxes,
                                                                   w.order, w.sscore, w.cls, w.count, out_det, out_index,
                                                                   out_count, box_cache);
     YSOD_LAUNCH_CHECK();
@@ -541,6 +546,7 @@ long long ysod_nms_boxes_workspace_bytes(int n) {
 
 __global__ void nms_reorder_boxes_kernel(const float4* __restrict__ boxes, const int* __restrict__ order, const int* __restrict__ count,
                                          float4* __restrict__ sorted) {
+    ysod_pdl_sync();
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < count[0]) sorted[r] = boxes[order[r]];
 }
@@ -574,12 +580,12 @@ int ysod_nms_boxes(const float* boxes, const float* scores, int n, float thr_f, 
     YSOD_CHECK_ARG(greedy_base <= 128 * 1024, "ysod_nms_boxes: n/max_keep too large for shared memory");
     const int box_cache = n < 6144 ? n : 6144;
     const size_t greedy_smem = greedy_base + (size_t)box_cache * 16;
-    nms_sort_kernel<<<1, SORT_THREADS, 0, stream>>>(scores, n, n, 1, k0, v0, k1, v1, order, sscore, count);
+    ysod_launch(nms_sort_kernel, 1, SORT_THREADS, 0, stream, scores, n, n, 1, k0, v0, k1, v1, order, sscore, count);
     YSOD_LAUNCH_CHECK();
-    nms_reorder_boxes_kernel<<<ysod_cdiv(n, 256), 256, 0, stream>>>((const float4*)boxes, order, count, sorted);
+    ysod_launch(nms_reorder_boxes_kernel, ysod_cdiv(n, 256), 256, 0, stream, (const float4*)boxes, order, count, sorted);
     YSOD_LAUNCH_CHECK();
     if (max_keep <= 2048) {
-        nms_chunk_kernel<<<1, GREEDY_THREADS, (size_t)max_keep * 24, stream>>>(nullptr, 0, 0, n, 0, max_keep, thr_f, sorted, order, sscore, nullptr,
+        ysod_launch(nms_chunk_kernel, 1, GREEDY_THREADS, (size_t)max_keep * 24, stream, nullptr, 0, 0, n, 0, max_keep, thr_f, sorted, order, sscore, nullptr,
                                                                                count, nullptr, keep_out, nkeep_out);
         YSOD_LAUNCH_CHECK();
         return YSOD_OK;
@@ -587,7 +593,7 @@ int ysod_nms_boxes(const float* boxes, const float* scores, int n, float thr_f, 
     if (greedy_smem > 48 * 1024) {
         YSOD_CUDA(cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)greedy_smem));
     }
-    nms_greedy_kernel<<<1, GREEDY_THREADS, greedy_smem, stream>>>(nullptr, 0, 0, n, 0, max_keep, thr_f, sorted, order, sscore, nullptr,
+    ysod_launch(nms_greedy_kernel, 1, GREEDY_THREADS, greedy_smem, stream, nullptr, 0, 0, n, 0, max_keep, thr_f, sorted, order, sscore, nullptr,
                                                                   count, nullptr, keep_out, nkeep_out, box_cache);
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;

@@ -39,6 +39,7 @@ template <int COUT, int SRC, bool VEC>
 __global__ void __launch_bounds__(256)
 stem_mma_kernel(const void* __restrict__ img_, const __nv_bfloat16* __restrict__ wk, const float* __restrict__ bias,
                 __nv_bfloat16* __restrict__ out, int H, int W, int Ho, int Wo, int ocs, int act) {
+    ysod_pdl_sync();
     constexpr int NB = COUT / 8;
     __shared__ __align__(16) __nv_bfloat16 patch[3 * PLANE];
     __shared__ __align__(16) __nv_bfloat16 stage[TH * TW * (COUT + 8)];   // +8: keeps the 4-byte fragment stores conflict-free
@@ -224,8 +225,8 @@ extern "C" int ysod_stem_mma(const void* img, int src_fmt, int N, int H, int W, 
     const bool vec = (W % 4 == 0) && ((uintptr_t)img % 16 == 0);   // aligned 16 B / 4 B row loads
 #define LAUNCH(CO, SRC)                                                                                          \
     do {                                                                                                         \
-        if (vec) stem_mma_kernel<CO, SRC, true><<<grid, 256, 0, stream>>>(img, w, bias, o, H, W, Ho, Wo, ocs, act);   \
-        else stem_mma_kernel<CO, SRC, false><<<grid, 256, 0, stream>>>(img, w, bias, o, H, W, Ho, Wo, ocs, act);      \
+        if (vec) ysod_launch(stem_mma_kernel<CO, SRC, true>, grid, 256, 0, stream, img, w, bias, o, H, W, Ho, Wo, ocs, act);   \
+        else ysod_launch(stem_mma_kernel<CO, SRC, false>, grid, 256, 0, stream, img, w, bias, o, H, W, Ho, Wo, ocs, act);      \
     } while (0)
     if (Cout == 16) { if (src_fmt) LAUNCH(16, 1); else LAUNCH(16, 0); }
     else if (Cout == 32) { if (src_fmt) LAUNCH(32, 1); else LAUNCH(32, 0); }

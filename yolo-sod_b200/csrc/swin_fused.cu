@@ -131,6 +131,7 @@ __device__ __forceinline__ void layernorm_frag(uint32_t (*a)[4], const float (*v
 __global__ void __launch_bounds__(THREADS, 1)
 swin64_fused_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int xcs, const __nv_bfloat16* __restrict__ wb,
                     const float* __restrict__ pf, __nv_bfloat16* __restrict__ out, int ocs, int nWh, int nWw) {
+    ysod_pdl_sync();
     extern __shared__ __align__(16) uint8_t smem_raw[];
     Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -387,7 +388,7 @@ extern "C" int ysod_swin64_fused(const void* x, int N, int H, int W, int xcs, co
     if (grid > sms) grid = sms;
     const size_t smem = sizeof(Smem);
     YSOD_CUDA(cudaFuncSetAttribute(swin64_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    swin64_fused_kernel<<<(unsigned)grid, THREADS, smem, stream>>>((const __nv_bfloat16*)x, N, H, W, xcs, (const __nv_bfloat16*)wbf16, pf32,
+    ysod_launch(swin64_fused_kernel, (unsigned)grid, THREADS, smem, stream, (const __nv_bfloat16*)x, N, H, W, xcs, (const __nv_bfloat16*)wbf16, pf32,
                                                                    (__nv_bfloat16*)out, ocs, nWh, nWw);
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
