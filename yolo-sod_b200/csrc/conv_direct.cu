@@ -111,6 +111,71 @@ __global__ void dwconv_kernel(const T* __restrict__ x, const T* __restrict__ w, 
     ysod_vec8<T>::store(out + (size_t)pix * ocs + c0, acc);
 }
 
+// depthwise k x k, stride 1: a thread owns a horizontal strip of 4 output pixels x 8 channels and slides the filter window over
+// the k x (k + 3) input patch it loads once (2x fewer 16 B loads than one pixel per thread for 3x3, 2.5x for 5x5).
+template <typename T, int K>
+__global__ void dwconv_strip_kernel(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
+                                    const T* __restrict__ res, T* __restrict__ out, int N, int H, int W, int C, int xcs, int ocs, int rcs,
+                                    int act) {
+    ysod_pdl_sync();
+    constexpr int PAD = K / 2, SW = 4;
+    const int c8n = C >> 3;
+    const int wstrips = (W + SW - 1) / SW;
+    const unsigned total = (unsigned)N * H * wstrips * c8n;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c0 = (int)(idx % c8n) * 8;
+    unsigned r = idx / c8n;
+    const int ws = (int)(r % wstrips); r /= wstrips;
+    const int oh = (int)(r % H);
+    const int n = (int)(r / H);
+    const int ow0 = ws * SW;
+    float acc[SW][8];
+#pragma unroll
+    for (int p = 0; p < SW; ++p)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[p][e] = bias[c0 + e];
+#pragma unroll
+    for (int kr = 0; kr < K; ++kr) {
+        const int ih = oh + kr - PAD;
+        if (ih < 0 || ih >= H) continue;
+        float wv[K][8];
+#pragma unroll
+        for (int kq = 0; kq < K; ++kq) ysod_vec8<T>::load(w + (size_t)(kr * K + kq) * C + c0, wv[kq]);
+        const T* xr = x + ((size_t)n * H + ih) * W * xcs + c0;
+#pragma unroll
+        for (int q = 0; q < SW + K - 1; ++q) {
+            const int iw = ow0 + q - PAD;
+            if (iw < 0 || iw >= W) continue;
+            float xv[8];
+            ysod_vec8<T>::load(xr + (size_t)iw * xcs, xv);
+#pragma unroll
+            for (int p = 0; p < SW; ++p) {
+                const int kq = q - p;   // input column q feeds output p through tap kq
+                if (kq >= 0 && kq < K) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[p][e] = fmaf(xv[e], wv[kq][e], acc[p][e]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < SW; ++p) {
+        const int ow = ow0 + p;
+        if (ow >= W) break;
+        const size_t pix = ((size_t)n * H + oh) * W + ow;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[p][e] = ysod_act(acc[p][e], act);
+        if (res) {
+            float rv[8];
+            ysod_vec8<T>::load(res + pix * rcs + c0, rv);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[p][e] += rv[e];
+        }
+        ysod_vec8<T>::store(out + pix * ocs + c0, acc[p]);
+    }
+}
+
 // stem: NCHW fp32 image -> k x k stride-s conv (Cin = 3) -> NHWC; thread = (pixel, 8 output channels)
 template <typename TO>
 __global__ void stem_conv_kernel(const float* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias,
@@ -262,6 +327,18 @@ int ysod_dwconv(const void* x, int dtype, int N, int H, int W, int C, int xcs, c
     const int Ho = (H + 2 * pad - k) / s + 1, Wo = (W + 2 * pad - k) / s + 1;
     const long long total = (long long)N * Ho * Wo * (C / 8);
     const int blocks = ysod_cdiv(total, 256);
+    if (dtype == YSOD_BF16 && s == 1 && pad == k / 2 && (k == 3 || k == 5) && total < (1ll << 31)) {
+        const long long strips = (long long)N * H * ((W + 3) / 4) * (C / 8);
+        const int sb = ysod_cdiv(strips, 128);
+        if (k == 3)
+            ysod_launch(dwconv_strip_kernel<__nv_bfloat16, 3>, sb, 128, 0, stream, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias,
+                        (const __nv_bfloat16*)res, (__nv_bfloat16*)out, N, H, W, C, xcs, ocs, rcs, act);
+        else
+            ysod_launch(dwconv_strip_kernel<__nv_bfloat16, 5>, sb, 128, 0, stream, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias,
+                        (const __nv_bfloat16*)res, (__nv_bfloat16*)out, N, H, W, C, xcs, ocs, rcs, act);
+        YSOD_LAUNCH_CHECK();
+        return YSOD_OK;
+    }
     if (dtype == YSOD_F32)
         ysod_launch(dwconv_kernel<float>, blocks, 256, 0, stream, (const float*)x, (const float*)w, bias, (const float*)res, (float*)out, N,
                                                          H, W, C, xcs, Ho, Wo, ocs, rcs, k, s, pad, act);
