@@ -31,10 +31,10 @@ rec = [(int(buf[2 * i + 1]), int(buf[2 * i]) >> 56, (int(buf[2 * i]) >> 48) & 0x
 rec.sort()
 t0 = rec[0][0]
 names = {(3, 1): "M1 acc free", (3, 2): "M1 operands landed", (3, 3): "M1 burst issued", (0, 1): "P  slot free", (1, 1): "M  acc free", (1, 2): "M  operands landed", (1, 3): "M  burst issued", (2, 1): "E  acc full",
-         (1, 5): "M  mmas issued", (1, 6): "M  reconverged", (1, 7): "M  loop top", (2, 2): "E  barrier1", (2, 3): "E  acc released", (2, 4): "E  barrier2"}
+         (1, 5): "M  mmas issued", (1, 6): "M  reconverged", (1, 7): "M  loop top", (2, 10): "CTA kernel entry", (2, 11): "CTA prologue done", (2, 12): "CTA all roles done", (2, 2): "E  barrier1", (2, 3): "E  acc released", (2, 4): "E  barrier2"}
 print(f"{n} records; extra dbg {extra}")
 for t, role, ev, tile, idx in rec:
-    if (0 if len(sys.argv) > 9 else 3) <= tile <= 7:
+    if (0 if len(sys.argv) > 9 else 3) <= tile <= 7 or ev >= 10:
         col = {0: 0, 1: 1, 3: 2, 2: 3}[role]
         print(f"{t - t0:8d}  {' ' * 22 * col}{names.get((role, ev), (role, ev))} t{tile} #{idx}")
 

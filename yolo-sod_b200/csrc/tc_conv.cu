@@ -264,6 +264,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool tr = (p.debug & 32) && blockIdx.x == 0;
     unsigned int tcnt = 0;
+    trace(tr && threadIdx.x == 0, 2, 10, 0, 0, tcnt);   // kernel entry (epilogue warp 0 lane 0 logs CTA-level events)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < a_slots; ++s) {
@@ -295,6 +296,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t tmem_acc;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_acc) : "r"(tmem_slot) : "memory");
     pdl_launch_dependents();   // the next kernel's CTAs may be scheduled as soon as SMs free up (they block in pdl_wait())
+    trace(tr && threadIdx.x == 0, 2, 11, 0, 0, tcnt);   // prologue done (barriers, TMEM, bias)
 
     if (warp == PRODUCER_WARP) {
         // ===== TMA producer (one elected lane) =====
@@ -658,6 +660,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     tc_fence_before();
     __syncthreads();
+    trace(tr && threadIdx.x == 0, 2, 12, 0, 0, tcnt);   // all roles finished (stores read out)
     if (warp == MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)p.tmem_cols) : "memory");
     }
