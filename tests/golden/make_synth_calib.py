@@ -2,7 +2,7 @@
 weights, and the per-level class-bias shift. Uses the oracle forward (test infrastructure) with its BN hook patched so that
 every BN is calibrated on inputs produced by already-calibrated earlier layers (one sequential pass).
 
-    python tools/make_synth_calib.py
+    python tests/golden/make_synth_calib.py   (fixture generator: lives with the other golden generators because it imports oracle/)
 """
 import json
 import os
@@ -10,7 +10,7 @@ import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import yolo_sod_b200  # noqa: E402,F401
 from yolo_sod_b200 import cfg as ycfg, synth  # noqa: E402

@@ -84,6 +84,12 @@ def test_sod_bf16_640_batch2():
     _check(SOD, torch.bfloat16, 2, 640, 2e-2, layer_tol=3e-2, seed=99)
 
 
+def test_sod_bf16_1024_single_image():
+    """BASELINE config C3 (VisDrone-scale 1024^2: 87 040 anchors, 1369 P2 windows of which the last row / column are zero-padded)."""
+    model, x, y, y_ref = _check(SOD, torch.bfloat16, 1, 1024, 2e-2, layer_tol=3e-2, seed=5)
+    assert y.shape[2] == 87040
+
+
 def test_yolov12n_fp32_and_bf16():
     _check("yolov12n", torch.float32, 2, 128, 1e-4, layer_tol=2e-4)
     _check("yolov12n", torch.bfloat16, 1, 640, 2e-2, layer_tol=4e-2)  # attention-heavy: diagnostic layer bound 4 %

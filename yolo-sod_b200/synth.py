@@ -4,7 +4,7 @@ No checkpoints ship with the reference and there is no network, so every run use
 architecture. Plain default init is degenerate for this network (activations collapse to std 4e-7 by
 layer 8, zero NMS candidates), so the recipe is: fan-in-normalised Gaussian weights, BN gamma~U(.75,1.25), beta~N(0,.2^2),
 and BN running statistics set *per layer* to the scalar mean / variance that layer's conv output has under these weights
-(data/synth_calib.json, produced once by tools/make_synth_calib.py), plus a per-level class-bias shift so that a few
+(data/synth_calib.json, produced once by tests/golden/make_synth_calib.py), plus a per-level class-bias shift so that a few
 percent of the anchors clear conf 0.25. The same state_dict (reference parameter names) feeds the live reference, the
 oracle and the CUDA path.
 """
