@@ -72,6 +72,7 @@ CFG = {
     "yolov12n": "ultralytics/cfg/models/v12/yolov12n.yaml",
     "yolov12s": "ultralytics/cfg/models/v12/yolov12s.yaml",
     "yolov12m": "ultralytics/cfg/models/v12/yolov12m.yaml",
+    **{f"E{i}": f"ultralytics/cfg/models/new/E{i}.yaml" for i in range(1, 7)},   # the ablation ladder (README.md:131-137)
 }
 
 

@@ -90,6 +90,12 @@ def test_sod_bf16_1024_single_image():
     assert y.shape[2] == 87040
 
 
+@pytest.mark.parametrize("name", ["E1", "E2", "E3", "E4", "E5", "E6"])
+def test_ablation_ladder_bf16(name):
+    """The paper's ablation models (cfg/models/new/E1..E6.yaml; E1 has three heads, no P2): same kernels, fewer blocks."""
+    _check(name, torch.bfloat16, 1, 160, 2e-2, layer_tol=4e-2, seed=17)   # raw head maps at 2 %; intermediate layers are diagnostics (4 %)
+
+
 def test_yolov12n_fp32_and_bf16():
     _check("yolov12n", torch.float32, 2, 128, 1e-4, layer_tol=2e-4)
     _check("yolov12n", torch.bfloat16, 1, 640, 2e-2, layer_tol=4e-2)  # attention-heavy: diagnostic layer bound 4 %

@@ -9,6 +9,7 @@ A user can pass their own reference YAML (path or dict); the two architectures t
 
     "yolov12-sod-fusion-v5-simple"      ultralytics/cfg/models/new/yolov12-sod-fusion-v5-simple.yaml   (13.56 M params)
     "yolov12{n,s,m}"                    ultralytics/cfg/models/v12/yolov12.yaml + scale
+    "E1" .. "E6"                        ultralytics/cfg/models/new/E1..E6.yaml (the ablation ladder, derived from the full model)
 """
 import math
 import re
@@ -56,7 +57,56 @@ _YOLOV12 = {
     ],
 }
 
-BUILTIN = {"yolov12-sod-fusion-v5-simple": _SOD_SIMPLE, "yolov12": _YOLOV12}
+
+
+def _ablate(base: dict, drop, detect_from=None) -> dict:
+    """An ablation of the SOD architecture: `base` without the layers whose indices are in `drop`. References (`from`) are
+    re-indexed; a reference to a dropped layer falls through to the nearest kept layer before it -- which is how the
+    reference's hand-written ablation YAMLs (ultralytics/cfg/models/new/E1..E6.yaml) route around the removed attention blocks."""
+    rows = base["backbone"] + base.get("neck", []) + base["head"]
+    drop = set(drop)
+    new_index, k = {}, 0
+    for i in range(len(rows)):
+        if i not in drop:
+            new_index[i] = k
+            k += 1
+
+    def remap(i):
+        while i in drop:
+            i -= 1
+        return new_index[i]
+
+    out = []
+    for i, (f, n, m, args) in enumerate(rows):
+        if i in drop:
+            continue
+        if m == "Detect" and detect_from is not None:
+            f = [remap(j) for j in detect_from]
+        elif isinstance(f, list):
+            f = [(-1 if j == -1 else remap(j)) for j in f]
+        elif f != -1:
+            f = remap(f)
+        out.append([f, n, m, list(args)])
+    nb = sum(1 for i in range(len(base["backbone"])) if i not in drop)
+    return {"nc": base["nc"], "depth_multiple": base["depth_multiple"], "width_multiple": base["width_multiple"], "ch": base["ch"],
+            "backbone": out[:nb], "neck": out[nb:-1], "head": out[-1:]}
+
+
+# attention blocks of the full model by layer index (SURVEY.md section 3.3): SE {1, 23}, CBAM {4, 18}, Swin {9, 28}, A2 {12}, CA {32}
+_SE, _CBAM, _SWIN, _A2, _CA = {1, 23}, {4, 18}, {9, 28}, {12}, {32}
+_P2_PATH = {24, 25, 26, 27, 29, 30, 31}   # top-down P3->P2 branch and the P2->P3 bottom-up step
+
+BUILTIN = {
+    "yolov12-sod-fusion-v5-simple": _SOD_SIMPLE, "yolov12": _YOLOV12,
+    # the paper's ablation ladder (README.md:131-137; cfg/models/new/E1..E6.yaml): E1 plain PANet with P3-P5 heads, E2 + P2 head,
+    # E3 + SE, E4 + CBAM, E5 + Swin, E6 + A2 (the complete model adds CoordAtt)
+    "E1": _ablate(_SOD_SIMPLE, _SE | _CBAM | _SWIN | _A2 | _CA | _P2_PATH, detect_from=[22, 35, 38]),
+    "E2": _ablate(_SOD_SIMPLE, _SE | _CBAM | _SWIN | _A2 | _CA),
+    "E3": _ablate(_SOD_SIMPLE, _CBAM | _SWIN | _A2 | _CA),
+    "E4": _ablate(_SOD_SIMPLE, _SWIN | _A2 | _CA),
+    "E5": _ablate(_SOD_SIMPLE, _A2 | _CA),
+    "E6": _ablate(_SOD_SIMPLE, _CA),
+}
 ALIASES = {"sod": "yolov12-sod-fusion-v5-simple", "yolov12-sod": "yolov12-sod-fusion-v5-simple"}
 
 
