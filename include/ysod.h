@@ -47,7 +47,10 @@ typedef struct ysod_conv_tc ysod_conv_tc;
 int ysod_conv_tc_create(ysod_conv_tc** handle, const void* x, int N, int H, int W, int Cin, int xcs, const void* wgt,
                         const float* bias, int Cout, int Cout_pad, int ksize, int stride, void* out, int out_dtype, int ocs,
                         const void* res, int rcs, int act);
-/* mode: 0 auto, 1 generic per-tap kernel, 2 force the 3x3/s1 halo-reuse kernel */
+/* mode: 0 auto, 1 generic per-tap kernel, 2 force the 3x3/s1 halo-reuse kernel; | 0x40 (YSOD_CONV_UP2): fuse the following
+ * nn.Upsample(scale_factor=2, mode="nearest") (yaml neck rows `[-1, 1, nn.Upsample, [None, 2, "nearest"]]`) into the store --
+ * `out` is then the N x 2Ho x 2Wo x Cout destination view and every output pixel is written to its 2 x 2 block. */
+#define YSOD_CONV_UP2 0x40
 int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, int W, int Cin, int xcs, const void* wgt,
                            const float* bias, int Cout, int Cout_pad, int ksize, int stride, void* out, int out_dtype, int ocs,
                            const void* res, int rcs, int act, int mode);

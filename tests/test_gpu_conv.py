@@ -16,7 +16,7 @@ def _act(y, act):
 
 
 def _run_tc(N, H, W, Cin, Cout, k, s, act="silu", res=False, out_f32=False, xcs_extra=0, ocs_extra=0, seed=0, out_first=False,
-            mode=1):
+            mode=1, up2=False):
     from yolo_sod_b200 import lib
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(N, H, W, Cin, generator=g).bfloat16()
@@ -32,7 +32,10 @@ def _run_tc(N, H, W, Cin, Cout, k, s, act="silu", res=False, out_f32=False, xcs_
     xcs, ocs = Cin + xcs_extra, Cout + ocs_extra
     xb = torch.zeros(N, H, W, xcs, dtype=torch.bfloat16, device="cuda")
     xb[..., xcs_extra:] = x.cuda()
-    ob = torch.full((N, Ho, Wo, ocs), 7.0, dtype=torch.float32 if out_f32 else torch.bfloat16, device="cuda")
+    us = 2 if up2 else 1   # fused nn.Upsample(2, nearest): destination is 2Ho x 2Wo
+    if up2:
+        ref = F.interpolate(ref, scale_factor=2, mode="nearest")
+    ob = torch.full((N, us * Ho, us * Wo, ocs), 7.0, dtype=torch.float32 if out_f32 else torch.bfloat16, device="cuda")
     cpad = (Cout + 15) // 16 * 16
     wk = torch.zeros(cpad, k * k * Cin)
     wk[:Cout] = w.float().permute(0, 2, 3, 1).reshape(Cout, -1)
@@ -44,7 +47,7 @@ def _run_tc(N, H, W, Cin, Cout, k, s, act="silu", res=False, out_f32=False, xcs_
     h = C.c_void_p()
     lib.call("ysod_conv_tc_create_ex", C.byref(h), lib.ptr(xb, xcs_extra), N, H, W, Cin, xcs, lib.ptr(wd), lib.ptr(bd), Cout, cpad, k, s,
              lib.ptr(ob, 0 if out_first else ocs_extra), lib.F32 if out_f32 else lib.BF16, ocs, lib.ptr(rd) if res else None, Cout if res else 0,
-             lib.ACT[act], mode)
+             lib.ACT[act], mode | (lib.CONV_UP2 if up2 else 0))
     info = (C.c_int * 8)()
     lib.call("ysod_conv_tc_info", h, info)
     lib.call("ysod_conv_tc_run", h, lib.stream_ptr())
@@ -87,6 +90,22 @@ CASES = [
     (4, 160, 160, 32, 32, 3, 1, dict(res=True)),
     (2, 64, 64, 64, 192, 1, 1, dict(act="none")),                   # three N tiles of 64 (192 is not a multiple of 128)
 ]
+
+
+UP2_CASES = [
+    (2, 20, 20, 512, 256, 1, 1, {}),                                # L14: P5 -> P4 top-down conv, ragged 6x20 tiles
+    (2, 40, 40, 256, 128, 1, 1, dict(ocs_extra=128)),               # L19, stored into the first slice of a concat buffer
+    (3, 80, 80, 128, 64, 1, 1, dict(ocs_extra=64)),                 # L24: the P2 branch
+    (1, 24, 24, 64, 64, 3, 1, dict(act="none")),                    # 3x3 producer
+    (1, 16, 16, 64, 128, 3, 2, {}),                                 # stride-2 producer
+]
+
+
+@pytest.mark.parametrize("case", UP2_CASES, ids=lambda c: "x".join(str(v) for v in c[:7]))
+def test_conv_tc_fused_upsample(case):
+    """Conv -> nn.Upsample(scale_factor=2, 'nearest') in one launch (YSOD_CONV_UP2): TMA stores with element stride 2."""
+    *dims, kw = case
+    _run_tc(*dims, mode=0, up2=True, **kw)
 
 
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "x".join(str(v) for v in c[:7]))

@@ -306,6 +306,57 @@ __global__ void cbam_stats_stream_kernel(const T* __restrict__ x, int HW, int C,
     }
 }
 
+// CBAM spatial statistics, per-image variant for C <= 256: grid (pixel chunks, images). G = C/8 lanes own one pixel (one 16 B
+// load each, four pixels in flight per lane group); the lane's eight gate values live in registers for the whole CTA, so the
+// inner loop has no division and no gate loads. The trip count is uniform per CTA so the shuffles stay warp-converged.
+template <typename T>
+__global__ void __launch_bounds__(256)
+cbam_stats_img_kernel(const T* __restrict__ x, int HW, int C, int xcs, const float* __restrict__ gate, float2* __restrict__ stats,
+                      int chunk, int iters) {
+    ysod_pdl_sync();
+    const int G = C >> 3;
+    const int lg = __ffs(G) - 1;
+    const int n = blockIdx.y;
+    const int gl = threadIdx.x & (G - 1), grp = threadIdx.x >> lg, ngr = blockDim.x >> lg;
+    const int p0 = blockIdx.x * chunk, p1 = min(HW, p0 + chunk);
+    float gg[8];
+    {
+        const float4 g0 = *reinterpret_cast<const float4*>(gate + (size_t)n * C + gl * 8);
+        const float4 g1 = *reinterpret_cast<const float4*>(gate + (size_t)n * C + gl * 8 + 4);
+        gg[0] = g0.x; gg[1] = g0.y; gg[2] = g0.z; gg[3] = g0.w; gg[4] = g1.x; gg[5] = g1.y; gg[6] = g1.z; gg[7] = g1.w;
+    }
+    const T* xb = x + (size_t)n * HW * xcs + gl * 8;
+    float2* sb = stats + (size_t)n * HW;
+    const float inv_c = 1.0f / (float)C;
+    for (int it = 0; it < iters; ++it) {
+        const int pb = p0 + grp + it * 4 * ngr;
+        float v[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int pix = pb + u * ngr;
+            if (pix < p1) ysod_vec8<T>::load(xb + (size_t)pix * xcs, v[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int pix = pb + u * ngr;
+            float su = 0.f, mx = -INFINITY;
+            if (pix < p1) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float tv = v[u][e] * gg[e];
+                    su += tv;
+                    mx = fmaxf(mx, tv);
+                }
+            }
+            for (int o = G >> 1; o > 0; o >>= 1) {
+                su += __shfl_xor_sync(0xffffffffu, su, o);
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            }
+            if (pix < p1 && gl == 0) sb[pix] = make_float2(su * inv_c, mx);
+        }
+    }
+}
+
 // CBAM apply: sa = sigmoid(conv7x7([mean,max])) ; out = x * gate * sa. One CTA = a 16 x 16 pixel tile of one image: the
 // (16+6)^2 statistics halo is staged in shared memory, each thread evaluates the 7x7x2 filter for one pixel, then the CTA
 // streams the tile's channels with four 16 B loads in flight per thread.
@@ -340,31 +391,40 @@ cbam_apply_tile_kernel(const T* __restrict__ x, int H, int W, int C, int xcs, co
         sa_s[tid] = ysod_sigmoid(a);
     }
     __syncthreads();
+    // C/8 is a power of two <= 256 (host check): a thread keeps one channel group for the whole tile, its eight gate values in
+    // registers; pixel / channel-group indices are shifts
     const int c8n = C >> 3;
+    const int lg = __ffs(c8n) - 1;
     const int total = TS * TS * c8n;
-    const float* gn = gate + (size_t)n * C;
+    const int cg = tid & (c8n - 1);
+    float gg[8];
+    {
+        const float* gn = gate + (size_t)n * C + cg * 8;
+        const float4 g0 = *reinterpret_cast<const float4*>(gn), g1 = *reinterpret_cast<const float4*>(gn + 4);
+        gg[0] = g0.x; gg[1] = g0.y; gg[2] = g0.z; gg[3] = g0.w; gg[4] = g1.x; gg[5] = g1.y; gg[6] = g1.z; gg[7] = g1.w;
+    }
+    const T* xn = x + (size_t)n * H * W * xcs + cg * 8;
+    T* on = out + (size_t)n * H * W * ocs + cg * 8;
     for (int base = tid; base < total; base += 4 * 256) {
         float v[4][8];
         bool ok[4];
+        int pl[4], gp[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int i = base + u * 256;
-            const int p = i / c8n, cg = i - p * c8n;
-            const int h = h0 + p / TS, w = w0 + p % TS;
+            pl[u] = i >> lg;
+            const int h = h0 + (pl[u] >> 4), w = w0 + (pl[u] & 15);
+            gp[u] = h * W + w;
             ok[u] = (i < total) && h < H && w < W;
-            if (ok[u]) ysod_vec8<T>::load(x + (((size_t)n * H + h) * W + w) * xcs + cg * 8, v[u]);
+            if (ok[u]) ysod_vec8<T>::load(xn + (size_t)gp[u] * xcs, v[u]);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             if (!ok[u]) continue;
-            const int i = base + u * 256;
-            const int p = i / c8n, cg = i - p * c8n;
-            const int h = h0 + p / TS, w = w0 + p % TS;
-            const float sa = sa_s[p];
-            const float4 g0 = *reinterpret_cast<const float4*>(gn + cg * 8), g1 = *reinterpret_cast<const float4*>(gn + cg * 8 + 4);
-            v[u][0] *= g0.x * sa; v[u][1] *= g0.y * sa; v[u][2] *= g0.z * sa; v[u][3] *= g0.w * sa;
-            v[u][4] *= g1.x * sa; v[u][5] *= g1.y * sa; v[u][6] *= g1.z * sa; v[u][7] *= g1.w * sa;
-            ysod_vec8<T>::store(out + (((size_t)n * H + h) * W + w) * ocs + cg * 8, v[u]);
+            const float sa = sa_s[pl[u]];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[u][e] *= gg[e] * sa;
+            ysod_vec8<T>::store(on + (size_t)gp[u] * ocs, v[u]);
         }
     }
 }
@@ -545,6 +605,72 @@ sppf_plane_kernel(const T* __restrict__ y0, int H, int W, int xcs, int k, T* __r
             for (int e = 0; e < 8; ++e) v[e] = a[p * 8 + e];
             ysod_vec8<T>::store(outs[pass] + ((size_t)n * HW + p) * ocs + cg * 8, v);
         }
+    }
+}
+
+// bf16 variant of the plane kernel: one 1024-thread CTA per (image, 16-channel group); every item is one pixel x 8 channels
+// held as a uint4 of four bf16x2 (max is exact in bf16, so the result equals the fp32-staged kernel bit for bit). A thread
+// owns ITEMS fixed items, so pixel coordinates are computed once; the three chained 5x5 pools are six separable passes of packed
+// __hmax2 over shared memory. (Kept small on purpose: a fully unrolled 8-items-per-thread version stalled on instruction fetch.)
+__device__ __forceinline__ uint4 sppf_max4(uint4 a, uint4 b) {
+    uint4 r;
+    const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(&a);
+    const __nv_bfloat162* y = reinterpret_cast<const __nv_bfloat162*>(&b);
+    __nv_bfloat162* z = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) z[i] = __hmax2(x[i], y[i]);
+    return r;
+}
+template <int ITEMS>
+__global__ void __launch_bounds__(1024)
+sppf_plane_bf16_kernel(const __nv_bfloat16* __restrict__ y0, int H, int W, int xcs, int k, __nv_bfloat16* __restrict__ o1,
+                       __nv_bfloat16* __restrict__ o2, __nv_bfloat16* __restrict__ o3, int ocs) {
+    ysod_pdl_sync();
+    extern __shared__ uint4 sppf_q[];
+    const int n = blockIdx.y, c0 = blockIdx.x * 16;
+    const int HW = H * W, r = k / 2, items = HW * 2;
+    uint4* a = sppf_q;
+    uint4* b = sppf_q + items;
+    int ph[ITEMS], pw[ITEMS];   // item = pixel * 2 + half
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+        const int it = threadIdx.x + j * 1024;
+        const int p = it >> 1;
+        ph[j] = p / W;
+        pw[j] = p - ph[j] * W;
+        if (it < items) a[it] = *reinterpret_cast<const uint4*>(y0 + ((size_t)n * HW + p) * xcs + c0 + (it & 1) * 8);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int pass = 0; pass < 3; ++pass) {
+        __nv_bfloat16* outp = pass == 0 ? o1 : (pass == 1 ? o2 : o3);
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {   // row max: a -> b
+            const int it = threadIdx.x + j * 1024;
+            if (it < items) {
+                uint4 m = a[it];
+                for (int d = 1; d <= r; ++d) {
+                    if (pw[j] - d >= 0) m = sppf_max4(m, a[it - 2 * d]);
+                    if (pw[j] + d < W) m = sppf_max4(m, a[it + 2 * d]);
+                }
+                b[it] = m;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {   // column max: b -> a, and out
+            const int it = threadIdx.x + j * 1024;
+            if (it < items) {
+                uint4 m = b[it];
+                for (int d = 1; d <= r; ++d) {
+                    if (ph[j] - d >= 0) m = sppf_max4(m, b[it - 2 * d * W]);
+                    if (ph[j] + d < H) m = sppf_max4(m, b[it + 2 * d * W]);
+                }
+                a[it] = m;
+                *reinterpret_cast<uint4*>(outp + ((size_t)n * HW + (it >> 1)) * ocs + c0 + (it & 1) * 8) = m;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -863,6 +989,18 @@ int ysod_cbam_stats(const void* x, int dtype, int N, int HW, int C, int xcs, con
     YSOD_CHECK_ARG((c8n & (c8n - 1)) == 0, "ysod_cbam_stats: C/8 must be a power of two");
     const int G = c8n < 32 ? c8n : 32;
     const long long npix = (long long)N * HW;
+    if (c8n <= 32 && N <= 65535) {   // per-image streaming variant: one 16 B load per lane and pixel, four pixels in flight, gate in registers
+        int S = ysod_cdiv(1184, N);                      // ~8 CTAs per SM in total
+        const int ngr = 256 / c8n;
+        if (S > ysod_cdiv(HW, 4 * ngr)) S = ysod_cdiv(HW, 4 * ngr);
+        const int chunk = ysod_cdiv(HW, S);
+        S = ysod_cdiv(HW, chunk);
+        const int iters = ysod_cdiv(chunk, 4 * ngr);
+        dim3 grid(S, N);
+        YSOD_DISPATCH(dtype, (ysod_launch(cbam_stats_img_kernel<T>, grid, 256, 0, st, (const T*)x, HW, C, xcs, gate, (float2*)stats, chunk, iters)));
+        YSOD_LAUNCH_CHECK();
+        return YSOD_OK;
+    }
     if (c8n <= 32) {   // streaming variant: one 16 B load per lane and pixel, four pixels in flight
         const int blocks = stream_blocks(npix * c8n, 256, 4);
         const long long ngroups = (long long)blocks * 256 / c8n;
@@ -884,7 +1022,7 @@ int ysod_cbam_apply(const void* x, int dtype, int N, int H, int W, int C, int xc
     YSOD_CHECK_ARG((c8n & (c8n - 1)) == 0, "ysod_cbam_apply: C/8 must be a power of two");
     const int G = c8n < 32 ? c8n : 32;
     const long long npix = (long long)N * H * W;
-    if (ks == 7 && N <= 65535) {   // tiled variant (cbam_block.py:27: kernel_size 7)
+    if (ks == 7 && N <= 65535 && c8n <= 256) {   // tiled variant (cbam_block.py:27: kernel_size 7)
         dim3 grid(ysod_cdiv(W, 16), ysod_cdiv(H, 16), N);
         YSOD_DISPATCH(dtype, (ysod_launch(cbam_apply_tile_kernel<T>, grid, 256, 0, st, (const T*)x, H, W, C, xcs, gate, (const float2*)stats, wsp, (T*)out, ocs)));
         YSOD_LAUNCH_CHECK();
@@ -927,6 +1065,20 @@ int ysod_ca_apply(const void* x, int dtype, int N, int H, int W, int C, int xcs,
 int ysod_sppf_pool(const void* y0, int dtype, int N, int H, int W, int C, int xcs, int k, void* o1, void* o2, void* o3, int ocs,
                    cudaStream_t st) {
     YSOD_CHECK_ARG(y0 && o1 && o2 && o3 && C % 8 == 0 && xcs % 8 == 0 && ocs % 8 == 0 && (k & 1), "ysod_sppf_pool: bad args");
+    if (dtype == YSOD_BF16 && C % 16 == 0 && H * W <= 1024) {
+        dim3 grid(C / 16, N);
+        const size_t smem = (size_t)2 * H * W * 2 * sizeof(uint4);
+        const __nv_bfloat16* yi = (const __nv_bfloat16*)y0;
+        __nv_bfloat16 *p1 = (__nv_bfloat16*)o1, *p2 = (__nv_bfloat16*)o2, *p3 = (__nv_bfloat16*)o3;
+        if (H * W <= 512) {
+            ysod_launch(sppf_plane_bf16_kernel<1>, grid, 1024, smem, st, yi, H, W, xcs, k, p1, p2, p3, ocs);
+        } else {
+            YSOD_CUDA(cudaFuncSetAttribute(sppf_plane_bf16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            ysod_launch(sppf_plane_bf16_kernel<2>, grid, 1024, smem, st, yi, H, W, xcs, k, p1, p2, p3, ocs);
+        }
+        YSOD_LAUNCH_CHECK();
+        return YSOD_OK;
+    }
     if (H * W <= 1024) {
         dim3 grid(C / 8, N);
         const size_t smem = (size_t)2 * H * W * 8 * sizeof(float);

@@ -26,6 +26,13 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ float silu_tanh(float x) {
+    const float h = 0.5f * x;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
+
 // patch offset of im2col column k = (r*3 + s)*3 + c  (k >= 27: padding column, weight is zero; read element 0)
 __device__ __forceinline__ int koff(int k) {
     if (k >= 27) return 0;
@@ -183,9 +190,8 @@ stem_mma_kernel(const void* __restrict__ img_, const __nv_bfloat16* __restrict__
 #pragma unroll
         for (int nb = 0; nb < NB; ++nb) {
             float v0 = acc[nb][0], v1 = acc[nb][1], v2 = acc[nb][2], v3 = acc[nb][3];
-            if (act == YSOD_ACT_SILU) {
-                v0 = v0 / (1.0f + __expf(-v0)); v1 = v1 / (1.0f + __expf(-v1));
-                v2 = v2 / (1.0f + __expf(-v2)); v3 = v3 / (1.0f + __expf(-v3));
+            if (act == YSOD_ACT_SILU) {   // x * sigmoid(x) = h + h * tanh(h), h = x / 2 (same form as the tcgen05 conv epilogue)
+                v0 = silu_tanh(v0); v1 = silu_tanh(v1); v2 = silu_tanh(v2); v3 = silu_tanh(v3);
             }
             *reinterpret_cast<__nv_bfloat162*>(&stage[(size_t)p0 * (COUT + 8) + nb * 8 + 2 * t]) = __floats2bfloat162_rn(v0, v1);
             *reinterpret_cast<__nv_bfloat162*>(&stage[(size_t)(p0 + 8) * (COUT + 8) + nb * 8 + 2 * t]) = __floats2bfloat162_rn(v2, v3);

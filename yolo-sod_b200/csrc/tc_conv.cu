@@ -50,6 +50,7 @@ struct TcParams {
     // epilogue staging: output rows of `row_bytes` (<= 128 B, one swizzle span) per store unit of `unit_cols` columns
     int unit_cols, n_units, swz_mask, cout_pad, stage_bufs;
     uint32_t row_bytes;
+    int up2;    // nn.Upsample(scale 2, nearest) fused into the store: every output pixel is written to its 2 x 2 block of the 2Ho x 2Wo destination
     int debug;  // profiling only (mode >> 8): 1 = epilogue drains without work, 2 = producer skips TMA, 4 = MMA issuer skips tcgen05.mma,
                 // 8 = epilogue skips the TMA store, 16 = epilogue skips the activation
 };
@@ -647,7 +648,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             epi_barrier(grp);
             if (leader_warp && elect_one()) {
                 if (!(p.debug & 8)) {
-                    for (int u = 0; u < n_units; ++u) tma_store_4d(&tmO, sb + (uint32_t)u * unit_bytes, n0 + u * unit_cols, ow0, oh0, img);
+                    if (p.up2) {
+                        // the output map walks the 2x-upsampled destination with element strides {1,2,2,1}: four stores of the
+                        // same staged tile, one per (dy, dx) phase of the 2 x 2 replication
+                        for (int u = 0; u < n_units; ++u)
+#pragma unroll
+                            for (int d = 0; d < 4; ++d)
+                                tma_store_4d(&tmO, sb + (uint32_t)u * unit_bytes, n0 + u * unit_cols, 2 * ow0 + (d & 1), 2 * oh0 + (d >> 1), img);
+                    } else {
+                        for (int u = 0; u < n_units; ++u) tma_store_4d(&tmO, sb + (uint32_t)u * unit_bytes, n0 + u * unit_cols, ow0, oh0, img);
+                    }
                 }
                 bulk_commit();
             }
@@ -703,7 +713,8 @@ extern "C" {
 //   out    : NHWC view, pixel stride ocs elements; out_dtype YSOD_BF16 or YSOD_F32
 //   res    : optional NHWC bf16 residual added AFTER the activation (Bottleneck / transformer skip), stride rcs
 // ksize in {1,3}, stride in {1,2} (pad = ksize/2, conv.py:28 autopad), groups == 1, Cin % 32 == 0.
-// mode: 0 = auto, 1 = generic per-tap kernel, 2 = force the 3x3 halo-reuse kernel (error if the shape does not qualify).
+// mode: 0 = auto, 1 = generic per-tap kernel, 2 = force the 3x3 halo-reuse kernel (error if the shape does not qualify);
+//       | 0x40 = fuse nn.Upsample(scale_factor=2, mode='nearest') into the store: `out` is the N x 2Ho x 2Wo destination view.
 int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, int W, int Cin, int xcs, const void* wgt,
                            const float* bias, int Cout, int Cout_pad, int ksize, int stride, void* out, int out_dtype, int ocs,
                            const void* res, int rcs, int act, int mode) {
@@ -743,13 +754,15 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
     // 3x3 / stride-1 halo-reuse specialisation: fixed 16 x 8 output tile; worth it when that tiling wastes < 25 % of M
     bool halo = false;
     const int dbg = mode >> 8;
-    mode &= 0xff;
+    const bool up2 = (mode & 0x40) != 0;
+    mode &= 0x3f;
     if (ksize == 3 && stride == 1 && (Cin % 64 == 0 || Cin == 32)) {
         const double hutil = (double)Ho * Wo / ((double)ysod_cdiv(Ho, 16) * ysod_cdiv(Wo, 8) * 128.0);
         halo = (mode == 2) || (mode == 0 && hutil >= 0.75);
     }
     YSOD_CHECK_ARG(mode != 2 || halo, "ysod_conv_tc_create_ex: shape does not qualify for the halo kernel");
     p.debug = dbg;
+    p.up2 = up2 ? 1 : 0;
     if (halo) { bestTH = 16; bestTW = 8; }
     p.N = N; p.Ho = Ho; p.Wo = Wo; p.TH = bestTH; p.TW = bestTW;
     p.tiles_h = ysod_cdiv(Ho, bestTH); p.tiles_w = ysod_cdiv(Wo, bestTW);
@@ -907,10 +920,11 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
     {
         // output map: channel slice [Cout] x Wo x Ho x N, box = {unit_cols, TW, TH, 1}; stores clip ragged tiles / Cout padding
         const cuuint64_t es = p.out_f32 ? 4 : 2;
-        cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)N};
-        cuuint64_t strides[3] = {(cuuint64_t)ocs * es, (cuuint64_t)Wo * ocs * es, (cuuint64_t)Ho * Wo * ocs * es};
-        cuuint32_t box[4] = {(cuuint32_t)p.unit_cols, (cuuint32_t)bestTW, (cuuint32_t)bestTH, 1};
-        cuuint32_t es1[4] = {1, 1, 1, 1};
+        const cuuint64_t us = up2 ? 2 : 1;   // fused nearest upsample: the destination is 2Ho x 2Wo, traversed with element stride 2
+        cuuint64_t dims[4] = {(cuuint64_t)Cout, us * Wo, us * Ho, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)ocs * es, us * Wo * ocs * es, us * Ho * us * Wo * ocs * es};
+        cuuint32_t box[4] = {(cuuint32_t)p.unit_cols, (cuuint32_t)(us * bestTW), (cuuint32_t)(us * bestTH), 1};
+        cuuint32_t es1[4] = {1, (cuuint32_t)us, (cuuint32_t)us, 1};
         const CUtensorMapSwizzle oswz = p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                       : p.row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
         CUresult r = enc(&c.tmO, p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, dims, strides,

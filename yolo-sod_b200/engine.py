@@ -35,6 +35,8 @@ class View:
     W: int
     C: int
     cs: int
+    sub: int = 1   # > 1: this (N,H,W) view samples every `sub`-th pixel of an (N, H*sub, W*sub) buffer (a conv whose output only
+                   # exists nearest-upsampled, see Program._build); for layer_output() only, never handed to a kernel
 
     def ptr(self):
         return C.c_void_p(self.buf.data_ptr() + self.off * self.buf.element_size())
@@ -43,7 +45,9 @@ class View:
         return View(self.buf, self.off + c0, self.N, self.H, self.W, c1 - c0, self.cs)
 
     def torch_nhwc(self):
-        t = self.buf[self.off:].as_strided((self.N, self.H, self.W, self.C), (self.H * self.W * self.cs, self.W * self.cs, self.cs, 1))
+        u = self.sub
+        t = self.buf[self.off:].as_strided((self.N, self.H, self.W, self.C),
+                                           (self.H * u * self.W * u * self.cs, u * self.W * u * self.cs, u * self.cs, 1))
         return t
 
     def torch_nchw(self):
@@ -115,13 +119,15 @@ class Program:
         return w * s.view(-1, 1, 1, 1), b - mu * s
 
     def conv(self, x: View, w: torch.Tensor, bias: torch.Tensor, k, s, g, act, out: View, res: View = None,
-             out_f32=False, pad=None):
-        """w: (Cout, Cin/g, k, k) fp32 with BN folded; bias fp32 (Cout)."""
+             out_f32=False, pad=None, up2=False):
+        """w: (Cout, Cin/g, k, k) fp32 with BN folded; bias fp32 (Cout). up2: `out` is the 2x nearest-upsampled destination
+        (tensor-core path only; the caller checks `can_up2`)."""
         pad = k // 2 if pad is None else pad
         Cout, Cin = w.shape[0], x.C
         assert w.shape[1] * g == Cin, (w.shape, Cin, g)
         Ho, Wo = (x.H + 2 * pad - k) // s + 1, (x.W + 2 * pad - k) // s + 1
-        assert (out.N, out.H, out.W, out.C) == (x.N, Ho, Wo, Cout), ((out.N, out.H, out.W, out.C), (x.N, Ho, Wo, Cout))
+        us = 2 if up2 else 1
+        assert (out.N, out.H, out.W, out.C) == (x.N, us * Ho, us * Wo, Cout), ((out.N, out.H, out.W, out.C), (x.N, Ho, Wo, Cout))
         actc = _lib.ACT[act]
         odt = _lib.F32 if out_f32 else self.code
         if res is not None:
@@ -136,6 +142,7 @@ class Program:
             return
         use_tc = (self.m.use_tc and self.code == _lib.BF16 and g == 1 and k in (1, 3) and s in (1, 2) and pad == k // 2
                   and Cin % 32 == 0 and (s == 1 or (x.H % 2 == 0 and x.W % 2 == 0)))
+        assert use_tc or not up2, "fused upsample needs the tensor-core conv"
         if use_tc:
             cpad = (Cout + 15) // 16 * 16
             wk = torch.zeros((cpad, k * k * Cin), dtype=torch.float32)
@@ -144,8 +151,9 @@ class Program:
             bk[:Cout] = bias
             wd, bd = self.dev_t(wk, torch.bfloat16), self.dev_t(bk)
             h = C.c_void_p()
-            _lib.call("ysod_conv_tc_create", C.byref(h), x.ptr(), x.N, x.H, x.W, Cin, x.cs, _lib.ptr(wd), _lib.ptr(bd), Cout, cpad,
-                      k, s, out.ptr(), odt, out.cs, res.ptr() if res is not None else None, res.cs if res is not None else 0, actc)
+            _lib.call("ysod_conv_tc_create_ex", C.byref(h), x.ptr(), x.N, x.H, x.W, Cin, x.cs, _lib.ptr(wd), _lib.ptr(bd), Cout, cpad,
+                      k, s, out.ptr(), odt, out.cs, res.ptr() if res is not None else None, res.cs if res is not None else 0, actc,
+                      _lib.CONV_UP2 if up2 else 0)
             self.tc_handles.append(h)
             self.ops.append((_lib.load().ysod_conv_tc_run, (h,), "ysod_conv_tc_run"))
             self.sched.append(("op", len(self.ops) - 1, self._lane))
@@ -153,7 +161,7 @@ class Program:
             self.op_flops.append(fl)
             info = (C.c_int * 8)()
             _lib.call("ysod_conv_tc_info", h, info)
-            self.op_desc.append(f"{self._ctx} tc {Cin}->{Cout} k{k}s{s} @{Ho}x{Wo} N{x.N} tile{info[0]}x{info[1]} BN{info[2]} BK{info[3]} "
+            self.op_desc.append(f"{self._ctx} tc {Cin}->{Cout} k{k}s{s}{'up2' if up2 else ''} @{Ho}x{Wo} N{x.N} tile{info[0]}x{info[1]} BN{info[2]} BK{info[3]} "
                                 f"st{info[4]} grid{info[5]}x{info[6]} smem{info[7]}")
             self.tc_flops += fl
             self.n_launches += 1
@@ -173,14 +181,21 @@ class Program:
                   out.ptr(), odt, out.cs, res.ptr() if res is not None else None, res.cs if res is not None else 0, actc,
                   flops=2.0 * x.N * Ho * Wo * Cout * k * k * Cin / g, desc=f"direct {Cin}->{Cout} k{k}s{s}g{g} @{Ho}x{Wo}")
 
-    def conv_bn(self, x, pfx, k=1, s=1, g=1, act=True, out=None, res=None, pad=None):
+    def conv_bn(self, x, pfx, k=1, s=1, g=1, act=True, out=None, res=None, pad=None, up2=False):
         """Reference `Conv` wrapper (conv.py:37-55) with BN folded."""
         w, b = self.folded(pfx)
         if out is None:
             p = k // 2 if pad is None else pad
             out = self.new(x.N, (x.H + 2 * p - k) // s + 1, (x.W + 2 * p - k) // s + 1, w.shape[0])
-        self.conv(x, w, b, k, s, g, "silu" if act else "none", out, res, pad=pad)
+        self.conv(x, w, b, k, s, g, "silu" if act else "none", out, res, pad=pad, up2=up2)
         return out
+
+    def can_up2(self, L, cin, h, w):
+        """A top-level Conv layer whose only consumer is nn.Upsample(2, nearest) can write the upsampled map itself
+        (tensor-core path: dense, k in {1,3}, default padding)."""
+        p = L.p
+        return (self.m.use_tc and self.code == _lib.BF16 and self.m.fuse_upsample and p["g"] == 1 and p["k"] in (1, 3)
+                and p["s"] in (1, 2) and p["p"] in (None, p["k"] // 2) and cin % 32 == 0 and (p["s"] == 1 or (h % 2 == 0 and w % 2 == 0)))
 
     def linear(self, x: View, w, b, act="none", out=None, res=None):
         """x: token matrix as a (1,1,T,C) view; w: (out,in)."""
@@ -493,6 +508,22 @@ class Program:
                     c0 += cj
         out = self.layer_out
         det_inputs = set(layers[-1].f) if layers[-1].type == "Detect" else set()
+        # Conv -> nn.Upsample(2) pairs where the conv feeds nothing else (the neck's top-down path): the conv stores straight into
+        # the upsampled map (TMA store with element stride 2, four phases) and the upsample launch disappears
+        consumers: Dict[int, list] = {}
+        for L in layers:
+            for src in (L.f if isinstance(L.f, list) else [L.f]):
+                consumers.setdefault(L.i - 1 if src == -1 else src, []).append(L.i)
+        fold_up: Dict[int, int] = {}
+        for L in layers:
+            if L.type == "nn.Upsample" and L.p["scale"] == 2 and L.p.get("mode", "nearest") == "nearest" and L.i > 0:
+                src = L.i - 1 if L.f == -1 else L.f
+                S = layers[src]
+                if (isinstance(src, int) and S.type == "Conv" and S.i > 0 and consumers.get(src) == [L.i] and src not in home
+                        and src not in det_inputs):
+                    ssrc = S.i - 1 if S.f == -1 else S.f
+                    if self.can_up2(S, shp[ssrc][2], shp[ssrc][0], shp[ssrc][1]):
+                        fold_up[src] = L.i
         for L in layers:
             P, p, t = f"model.{L.i}", L.p, L.type
             self._ctx = f"L{L.i}:{t}"
@@ -514,8 +545,20 @@ class Program:
                     self.sched.append(("record", f"L{L.i}", 0))
                 continue
             h, w, c = shp[L.i]
-            o = home[L.i] if L.i in home else self.new(self.B, h, w, c)
             src = L.i - 1 if L.f == -1 else L.f
+            if t == "nn.Upsample" and fold_up.get(src) == L.i:
+                continue                      # already written by its producer conv
+            if L.i in fold_up:
+                U = fold_up[L.i]
+                uh, uw, uc = shp[U]
+                uo = home[U] if U in home else self.new(self.B, uh, uw, uc)
+                self.conv_bn(out[src], P, p["k"], p["s"], p["g"], p["act"], out=uo, pad=p["p"], up2=True)
+                out[U] = uo
+                out[L.i] = View(uo.buf, uo.off, uo.N, h, w, c, uo.cs, sub=2)
+                if U in det_inputs:
+                    self.sched.append(("record", f"L{U}", 0))
+                continue
+            o = home[L.i] if L.i in home else self.new(self.B, h, w, c)
             x = None if L.i == 0 else out[src]
             if t == "Conv":
                 if L.i == 0:
@@ -661,7 +704,7 @@ class B200DetectionModel:
     """
 
     def __init__(self, cfg, state_dict, dtype=torch.bfloat16, device="cuda:0", use_tc=True, use_graph=True, nc=None,
-                 static_outputs=True, fuse_swin=True, multi_stream=True):
+                 static_outputs=True, fuse_swin=True, multi_stream=True, fuse_upsample=True):
         _lib.require_cuda()
         _lib.load()
         self.spec = cfg if isinstance(cfg, _cfg.ModelSpec) else _cfg.get_spec(cfg, nc=nc)
@@ -675,6 +718,7 @@ class B200DetectionModel:
         self.use_tc = use_tc
         self.use_graph = use_graph
         self.fuse_swin = fuse_swin
+        self.fuse_upsample = fuse_upsample
         self.multi_stream = multi_stream
         self.static_outputs = static_outputs
         self.stride_list = _cfg.strides_of(self.spec)
