@@ -442,8 +442,23 @@ class Program:
                 c2n = w2.shape[0]
                 both = self.new(x.N, x.H, x.W, c2n + w3.shape[0])
                 self.conv(x, torch.cat([w2, w3], 0), torch.cat([b2, b3], 0), 3, 1, 1, "silu", both)
-                a = self.conv_bn(both.slice(0, c2n), f"{P}.cv2.{i}.1", 3)
-                c = self.conv_bn(both.slice(c2n, both.C), f"{P}.cv3.{i}.1", 3)
+                c3n = sd[f"{P}.cv3.{i}.1.conv.weight"].shape[0]
+                if (c2n + c3n) % 32 == 0 and no <= 128:
+                    # cv2[i][2] and cv3[i][2] (1x1, bias, no act) as ONE block-diagonal 1x1 conv [64 + nc][c2 + c3] over the two
+                    # branch outputs stored side by side: the pair is HBM-bound, so the zero half of the weights is free and the
+                    # raw map is written by one launch (full 74-channel rows instead of two partial slices)
+                    ac = self.new(x.N, x.H, x.W, c2n + c3n)
+                    self.conv_bn(both.slice(0, c2n), f"{P}.cv2.{i}.1", 3, out=ac.slice(0, c2n))
+                    self.conv_bn(both.slice(c2n, both.C), f"{P}.cv3.{i}.1", 3, out=ac.slice(c2n, c2n + c3n))
+                    wt = torch.zeros((no, c2n + c3n, 1, 1), dtype=torch.float32)
+                    wt[:64, :c2n] = sd[f"{P}.cv2.{i}.2.weight"].float()
+                    wt[64:, c2n:] = sd[f"{P}.cv3.{i}.2.weight"].float()
+                    bt = torch.cat([sd[f"{P}.cv2.{i}.2.bias"].float(), sd[f"{P}.cv3.{i}.2.bias"].float()])
+                    self.conv(ac, wt, bt, 1, 1, 1, "none", raw.slice(0, no), out_f32=True)
+                    a = c = None
+                else:
+                    a = self.conv_bn(both.slice(0, c2n), f"{P}.cv2.{i}.1", 3)
+                    c = self.conv_bn(both.slice(c2n, both.C), f"{P}.cv3.{i}.1", 3)
             else:
                 a = self.conv_bn(x, f"{P}.cv2.{i}.0", 3)
                 a = self.conv_bn(a, f"{P}.cv2.{i}.1", 3)
@@ -455,10 +470,11 @@ class Program:
                     c = self.conv_bn(c, f"{P}.cv3.{i}.0.1", 1)
                     c = self.conv_bn(c, f"{P}.cv3.{i}.1.0", 3, 1, c.C)
                     c = self.conv_bn(c, f"{P}.cv3.{i}.1.1", 1)
-            self.conv(a, sd[f"{P}.cv2.{i}.2.weight"].float(), sd[f"{P}.cv2.{i}.2.bias"].float(), 1, 1, 1, "none", raw.slice(0, 64),
-                      out_f32=True)
-            self.conv(c, sd[f"{P}.cv3.{i}.2.weight"].float(), sd[f"{P}.cv3.{i}.2.bias"].float(), 1, 1, 1, "none", raw.slice(64, 64 + nc),
-                      out_f32=True)
+            if a is not None:
+                self.conv(a, sd[f"{P}.cv2.{i}.2.weight"].float(), sd[f"{P}.cv2.{i}.2.bias"].float(), 1, 1, 1, "none", raw.slice(0, 64),
+                          out_f32=True)
+                self.conv(c, sd[f"{P}.cv3.{i}.2.weight"].float(), sd[f"{P}.cv3.{i}.2.bias"].float(), 1, 1, 1, "none",
+                          raw.slice(64, 64 + nc), out_f32=True)
             self.emit("ysod_dfl_decode", raw.ptr(), _lib.F32, x.N, x.H, x.W, raw.cs, nc, 16, float(self.m.stride_list[i]), _lib.ptr(y), A,
                       a_off)
             a_off += x.H * x.W
