@@ -54,6 +54,10 @@ int ysod_conv_tc_create(ysod_conv_tc** handle, const void* x, int N, int H, int 
 int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, int W, int Cin, int xcs, const void* wgt,
                            const float* bias, int Cout, int Cout_pad, int ksize, int stride, void* out, int out_dtype, int ocs,
                            const void* res, int rcs, int act, int mode);
+/* head.py:100-131 Detect._inference + block.py:64-83 DFL + tal.py:333-357 make_anchors/dist2bbox fused into the epilogue of the
+ * level's final 1x1 head conv (plan: fp32 raw map out, no activation, Cout = 64 + nc): besides the raw map the launch writes
+ * y (B, 4+nc, A_total) for anchors [a_off, a_off + Ho*Wo). Equivalent to running ysod_dfl_decode on the raw map afterwards. */
+int ysod_conv_tc_set_decode(ysod_conv_tc* h, float* y, int A_total, int a_off, int nc, float stride);
 int ysod_conv_tc_run(ysod_conv_tc* handle, void* stream);
 int ysod_conv_tc_info(ysod_conv_tc* handle, int* out8);
 void ysod_conv_tc_destroy(ysod_conv_tc* handle);

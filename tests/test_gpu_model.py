@@ -173,6 +173,21 @@ def test_fused_swin_block_matches_oracle_and_unfused_path():
         assert any(o[2] == "ysod_swin64_fused" for o in m_f.program(2, sz, sz).ops)
 
 
+def test_fused_epilogues_equal_separate_kernels():
+    """Conv+Upsample in one launch and the Detect decode inside the final head conv's epilogue are pure re-schedulings: the raw maps
+    are bit-identical to the separate-kernel program and y agrees to fp32 rounding (expression order is the same; only FMA contraction may differ)."""
+    spec, sd, fused = _build(SOD, torch.bfloat16)
+    _, _, plain = _build(SOD, torch.bfloat16, fuse_upsample=False, fuse_decode=False)
+    x = synth.synth_images(2, 320, seed=23).cuda()
+    y1, r1 = fused(x)
+    y2, r2 = plain(x)
+    torch.cuda.synchronize()
+    assert fused.program(2, 320, 320).n_launches < plain.program(2, 320, 320).n_launches - 6
+    for a, b in zip(r1, r2):
+        assert torch.equal(a, b)
+    assert torch.allclose(y1, y2, rtol=1e-5, atol=1e-4), float((y1 - y2).abs().max())
+
+
 def test_uint8_frames_equal_preprocessed_tensor():
     """(B,H,W,3) uint8 BGR frames through the fused stem == the reference's preprocess (predictor.py:127-133) + tensor input."""
     spec, sd, model = _build(SOD, torch.bfloat16)

@@ -50,6 +50,12 @@ struct TcParams {
     // epilogue staging: output rows of `row_bytes` (<= 128 B, one swizzle span) per store unit of `unit_cols` columns
     int unit_cols, n_units, swz_mask, cout_pad, stage_bufs;
     uint32_t row_bytes;
+    // fused Detect decode (ysod_conv_tc_set_decode): the layer is the level's final 1x1 head conv with output channels
+    // [0,64) = DFL box logits (4 sides x 16 bins), [64,64+nc) = class logits; besides the raw map the epilogue writes
+    // y[img][0..4+nc)[a_off + pixel] = (cx, cy, w, h) * stride, sigmoid(cls)   (head.py:100-131, block.py:64-83, tal.py:333-357)
+    float* dec_y;
+    int dec_A, dec_off, dec_nc;
+    float dec_stride;
     int up2;    // nn.Upsample(scale 2, nearest) fused into the store: every output pixel is written to its 2 x 2 block of the 2Ho x 2Wo destination
     int debug;  // profiling only (mode >> 8): 1 = epilogue drains without work, 2 = producer skips TMA, 4 = MMA issuer skips tcgen05.mma,
                 // 8 = epilogue skips the TMA store, 16 = epilogue skips the activation
@@ -590,6 +596,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (leader_warp) bulk_wait_read<0>();
             epi_barrier(grp);
             trace(tre, 2, 2, tcount, 0, tcnt);       // staging buffer free
+            float dd0 = 0.f, dd1 = 0.f;   // fused decode: DFL distances of this thread's two sides (cg = 0: left, right; cg = 1: top, bottom)
+            const bool dec = p.dec_y != nullptr;
+            const int d_oh = oh0 + th, d_ow = ow0 + tw;
+            const bool d_ok = dec && (m < TH * TW) && d_oh < p.Ho && d_ow < p.Wo;
+            float* const d_y = dec ? p.dec_y + (size_t)img * (4 + p.dec_nc) * p.dec_A + p.dec_off + d_oh * p.Wo + d_ow : nullptr;
             for (int ch = cg; ch < nchunks; ch += 2) {
                 const int c0 = ch * 16;
                 uint32_t v[16];
@@ -621,6 +632,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     if (ch + 2 < nchunks) { ra = *reinterpret_cast<const uint4*>(rp + c0 + 32); rb = *reinterpret_cast<const uint4*>(rp + c0 + 40); }
                 }
+                if (dec) {
+                    if (ch < 4) {
+                        // one 16-column chunk = the 16 DFL bins of side `ch`: softmax expectation (same expression order as decode.cu)
+                        float mx = f[0];
+#pragma unroll
+                        for (int j = 1; j < 16; ++j) mx = fmaxf(mx, f[j]);
+                        float sum = 0.f, acc = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float e = expf(f[j] - mx);
+                            sum += e;
+                            acc += e * (float)j;
+                        }
+                        const float dist = acc / sum;
+                        if (ch < 2) dd0 = dist; else dd1 = dist;
+                    } else if (d_ok) {
+                        const int nc = p.dec_nc;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if ((ch - 4) * 16 + j < nc) d_y[(size_t)(4 + (ch - 4) * 16 + j) * p.dec_A] = ysod_sigmoid(f[j]);
+                    }
+                }
                 // swizzled store into unit u = ch / chunks_per_unit: 16-byte piece index ^= (address bits [7..]) & mask (== TMA swizzle).
                 // The staging units are 1 KB aligned and a thread always writes row m, so the XOR term is a per-thread constant.
                 const int u = ch / chunks_per_unit, cu = ch - u * chunks_per_unit;
@@ -638,6 +671,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         st_shared_v4(row_addr + (((p0 + j) ^ swz_x) << 4), pack_bf16(f[8 * j], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
                                      pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
                 }
+            }
+            if (d_ok) {
+                // cg = 0 holds (left, right) -> cx, w ; cg = 1 holds (top, bottom) -> cy, h   (anchor = cell centre, tal.py:341-344)
+                const float anc = (float)(cg == 0 ? d_ow : d_oh) + 0.5f;
+                const float lo = anc - dd0, hi = anc + dd1;
+                d_y[(size_t)cg * p.dec_A] = (lo + hi) * 0.5f * p.dec_stride;
+                d_y[(size_t)(2 + cg) * p.dec_A] = (hi - lo) * p.dec_stride;
             }
             // all TMEM reads of this warp are complete (tcgen05.wait::ld above): hand the accumulator back
             tc_fence_before();
@@ -969,6 +1009,20 @@ int ysod_conv_tc_run(ysod_conv_tc* h, cudaStream_t stream) {
     if (h->c.halo) YSOD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, h->c.tmA, h->c.tmB, h->c.tmO, h->c.p));
     else YSOD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, h->c.tmA, h->c.tmB, h->c.tmO, h->c.p));
     YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+// Fuses the Detect decode into the epilogue of a plan created for a level's final 1x1 head conv (fp32 raw map out, no
+// activation, one N tile, channels [0,64) = 4 x 16 DFL bins, [64, 64+nc) = class logits): in addition to the raw map the launch
+// writes y (B, 4+nc, A_total) fp32 for the anchors [a_off, a_off + Ho*Wo) of this level. Replaces ysod_dfl_decode for the level.
+int ysod_conv_tc_set_decode(ysod_conv_tc* h, float* y, int A_total, int a_off, int nc, float stride) {
+    YSOD_CHECK_ARG(h && y, "ysod_conv_tc_set_decode: null");
+    TcParams& p = h->c.p;
+    YSOD_CHECK_ARG(p.out_f32 && p.act == YSOD_ACT_NONE && p.res == nullptr && p.n_tiles == 1 && !p.up2,
+                   "ysod_conv_tc_set_decode: plan must be an fp32-output, activation-free, single-N-tile conv");
+    YSOD_CHECK_ARG(nc > 0 && p.Cout == 64 + nc && p.BN >= 64 + nc, "ysod_conv_tc_set_decode: Cout %d != 64 + nc (%d)", p.Cout, nc);
+    YSOD_CHECK_ARG(a_off >= 0 && a_off + p.Ho * p.Wo <= A_total, "ysod_conv_tc_set_decode: anchor range out of bounds");
+    p.dec_y = y; p.dec_A = A_total; p.dec_off = a_off; p.dec_nc = nc; p.dec_stride = stride;
     return YSOD_OK;
 }
 

@@ -434,6 +434,7 @@ class Program:
                 self.n_lanes = max(self.n_lanes, 2 + i)
                 self.sched.append(("wait", f"L{src_layers[i]}", self._lane))
             raw = self.new(x.N, x.H, x.W, raw_cs, dtype=torch.float32, zero=True)
+            decoded = False
             if p["legacy"] and self.m.use_tc and self.code == _lib.BF16:
                 # cv2[i][0] and cv3[i][0] are 3x3 convs on the same input: run them as ONE conv with N = c2 + c3 output channels
                 # (the activation tile is fetched once, and N = 128 MMAs run at 93 % of the tensor rate vs 60 % for N = 64)
@@ -456,6 +457,11 @@ class Program:
                     bt = torch.cat([sd[f"{P}.cv2.{i}.2.bias"].float(), sd[f"{P}.cv3.{i}.2.bias"].float()])
                     self.conv(ac, wt, bt, 1, 1, 1, "none", raw.slice(0, no), out_f32=True)
                     a = c = None
+                    if self.m.fuse_decode:
+                        # ... and the level's DFL / dist2bbox / sigmoid decode runs in that conv's epilogue (no re-read of the raw map)
+                        _lib.call("ysod_conv_tc_set_decode", self.tc_handles[-1], _lib.ptr(y), A, a_off, nc, float(self.m.stride_list[i]))
+                        self.op_desc[-1] += " +decode"
+                        decoded = True
                 else:
                     a = self.conv_bn(both.slice(0, c2n), f"{P}.cv2.{i}.1", 3)
                     c = self.conv_bn(both.slice(c2n, both.C), f"{P}.cv3.{i}.1", 3)
@@ -475,8 +481,9 @@ class Program:
                           out_f32=True)
                 self.conv(c, sd[f"{P}.cv3.{i}.2.weight"].float(), sd[f"{P}.cv3.{i}.2.bias"].float(), 1, 1, 1, "none",
                           raw.slice(64, 64 + nc), out_f32=True)
-            self.emit("ysod_dfl_decode", raw.ptr(), _lib.F32, x.N, x.H, x.W, raw.cs, nc, 16, float(self.m.stride_list[i]), _lib.ptr(y), A,
-                      a_off)
+            if not decoded:
+                self.emit("ysod_dfl_decode", raw.ptr(), _lib.F32, x.N, x.H, x.W, raw.cs, nc, 16, float(self.m.stride_list[i]), _lib.ptr(y), A,
+                          a_off)
             a_off += x.H * x.W
             raws.append(raw.slice(0, no))
             if branch:
@@ -720,7 +727,7 @@ class B200DetectionModel:
     """
 
     def __init__(self, cfg, state_dict, dtype=torch.bfloat16, device="cuda:0", use_tc=True, use_graph=True, nc=None,
-                 static_outputs=True, fuse_swin=True, multi_stream=True, fuse_upsample=True):
+                 static_outputs=True, fuse_swin=True, multi_stream=True, fuse_upsample=True, fuse_decode=True):
         _lib.require_cuda()
         _lib.load()
         self.spec = cfg if isinstance(cfg, _cfg.ModelSpec) else _cfg.get_spec(cfg, nc=nc)
@@ -735,6 +742,7 @@ class B200DetectionModel:
         self.use_graph = use_graph
         self.fuse_swin = fuse_swin
         self.fuse_upsample = fuse_upsample
+        self.fuse_decode = fuse_decode
         self.multi_stream = multi_stream
         self.static_outputs = static_outputs
         self.stride_list = _cfg.strides_of(self.spec)
