@@ -79,6 +79,17 @@ int ysod_stem_conv(const float* img, int N, int H, int W, const float* w, const 
 int ysod_stem_mma(const void* img, int src_fmt, int N, int H, int W, const void* wk, const float* bias, int Cout, void* out, int ocs,
                   int act, void* stream);
 
+/* ---- predictor glue ---------------------------------------------------------------------------
+ * engine/predictor.py:145-164 pre_transform -> LetterBox(imgsz, auto, stride): resize (cv2.INTER_LINEAR, bit-exact 8-bit fixed
+ * point) + constant border; LetterBox's source (ultralytics/data/augment.py) is absent from the reference checkout, the geometry
+ * follows upstream 8.3.63 and is computed by the host. frames: (B,H0,W0,3) uint8 BGR; out: (B,H,W,3) uint8 (feeds ysod_stem_mma). */
+int ysod_letterbox_u8(const void* frames, int B, int H0, int W0, void* out, int H, int W, int new_h, int new_w, int top, int left,
+                      int value, void* stream);
+/* utils/ops.py:92-127 scale_boxes + :319-338 clip_boxes on the padded NMS output (models/yolo/detect/predict.py:38-40), in place.
+ * det: (B, rows_per_img, row_stride >= 4) fp32 rows [x1,y1,x2,y2,...]; params: per image params_stride (>= 5) floats = gain, pad_x,
+ * pad_y, orig_w, orig_h. */
+int ysod_scale_boxes(float* det, int B, int rows_per_img, int row_stride, const float* params, int params_stride, void* stream);
+
 /* ---- SE: smallobj_modules.py:57-92 ; CBAM: cbam_block.py:8-55 ; CoordAtt: ca_block.py:16-59 ------------------------- */
 int ysod_gap_partial(const void* x, int dtype, int N, int HW, int C, int xcs, int S, float* psum, float* pmax, void* stream);
 int ysod_se_gate(const float* psum, int N, int S, int HW, int C, const float* w1, const float* b1, const float* w2,

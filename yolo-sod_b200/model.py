@@ -4,12 +4,14 @@
     DetectionModel(cfg)(x) -> (y, [raw maps])          nn/tasks.py:129-163 / head.py:73-74
     AutoBackend(model)(im), .warmup(), .stride, ...    nn/autobackend.py:54,503-524,718-731 (the predictor's model seam)
 
-Only what the predictor reads is mirrored; sources other than image tensors (files, streams, PIL, numpy
-letterboxing) belong to the reference's `ultralytics.data` package and are out of scope.
+Only what the predictor reads is mirrored. Sources: image tensors, uint8 BGR frame batches, and lists of HWC
+uint8 frames (letterboxed on the device, predictor.py); files / streams / PIL belong to the reference's `ultralytics.data` loaders
+and are out of scope.
 """
 from types import SimpleNamespace
 from typing import List, Optional
 
+import numpy as np
 import torch
 
 from . import cfg as _cfg
@@ -126,11 +128,16 @@ class YOLO:
     def predict(self, source, stream=False, conf=0.25, iou=0.7, max_det=300, classes=None, agnostic_nms=False, imgsz=None,
                 half=False, **kwargs) -> List[Results]:
         """Defaults follow cfg/default.yaml:51-54 and engine/model.py:547 (conf 0.25, iou 0.7, max_det 300)."""
-        if not torch.is_tensor(source):
-            raise NotImplementedError("only (B,3,H,W) float tensors in [0,1] (predictor.py:116-134 tensor branch) or (B,H,W,3) uint8 BGR frames are accepted; "
-                                      "file/stream sources need the reference's ultralytics.data, which is out of scope")
         if half:
             raise NotImplementedError("half=True (fp16) is not provided")
+        if isinstance(source, np.ndarray):
+            source = [source] if source.ndim == 3 else list(source)
+        if isinstance(source, (list, tuple)):
+            return self._predict_frames(list(source), conf, iou, max_det, classes, agnostic_nms, imgsz)
+        if not torch.is_tensor(source):
+            raise NotImplementedError("accepted sources: (B,3,H,W) float tensors in [0,1] (predictor.py:116-134 tensor branch), (B,H,W,3) "
+                                      "uint8 BGR frames, or a list of HWC uint8 BGR frames (numpy / torch); file and stream sources need "
+                                      "the reference's ultralytics.data loaders, which are out of scope")
         im = source if source.dim() == 4 else source[None]
         if im.dtype == torch.uint8:   # raw BGR HWC frames: preprocess (predictor.py:127-133) is fused into the stem kernel
             preds = self.backend(im)
@@ -141,11 +148,23 @@ class YOLO:
         dets = _ops.non_max_suppression(preds, conf, iou, classes=classes, agnostic=agnostic_nms, max_det=max_det)
         out = []
         for d in dets:
-            d = d.clone()
             # scale_boxes(img.shape[2:], boxes, orig_shape) with identical shapes == clip_boxes (ops.py:92-127,319-338)
-            d[:, [0, 2]] = d[:, [0, 2]].clamp(0, w)
-            d[:, [1, 3]] = d[:, [1, 3]].clamp(0, h)
-            out.append(Results(d, (h, w), self.names))
+            out.append(Results(_ops.clip_boxes(d.clone(), (h, w)), (h, w), self.names))
         return out
+
+    def _predict_frames(self, frames, conf, iou, max_det, classes, agnostic_nms, imgsz):
+        """The predictor's list-of-frames branch, on the device: pre_transform (LetterBox) -> preprocess fused into the stem ->
+        model -> NMS -> scale_boxes/clip_boxes to each original frame (predictor.py:116-164, detect/predict.py:25-45)."""
+        from . import predictor as _pred
+        bad = [f for f in frames if not (getattr(f, "ndim", 0) == 3 and f.shape[2] == 3 and str(f.dtype).endswith("uint8"))]
+        if bad:
+            raise ValueError(f"frames must be (H,W,3) uint8 BGR arrays, got {tuple(bad[0].shape)} {bad[0].dtype}")
+        imgsz = imgsz or 640
+        imgsz = (imgsz, imgsz) if isinstance(imgsz, int) else tuple(imgsz)
+        im = _pred.pre_transform(frames, imgsz, stride=self.backend.stride, device=self.model.device)
+        preds = self.backend(im)
+        shapes = [tuple(int(v) for v in f.shape[:2]) for f in frames]
+        dets = _pred.postprocess(preds, (int(im.shape[1]), int(im.shape[2])), shapes, conf, iou, agnostic_nms, max_det, classes)
+        return [Results(d, s, self.names) for d, s in zip(dets, shapes)]
 
     __call__ = predict

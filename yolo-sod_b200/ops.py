@@ -112,3 +112,33 @@ def xywh2xyxy(x: torch.Tensor) -> torch.Tensor:
     y[..., :2] = x[..., :2] - wh
     y[..., 2:] = x[..., :2] + wh
     return y
+
+
+def clip_boxes(boxes: torch.Tensor, shape):
+    """ops.py:319-338: clamp xyxy boxes to the image (h, w), in place, on the GPU kernel (gain 1, no pad)."""
+    return scale_boxes(shape, boxes, shape, ratio_pad=((1.0, 1.0), (0, 0)))
+
+
+def scale_boxes(img1_shape, boxes: torch.Tensor, img0_shape, ratio_pad=None, padding=True, xywh=False) -> torch.Tensor:
+    """ops.py:92-127: letterboxed-image xyxy boxes -> original-image pixels (subtract pad, divide by gain, clip). `boxes` is a
+    contiguous fp32 CUDA tensor (..., k >= 4) and is modified in place like the reference's."""
+    _lib.require_cuda()
+    if xywh:
+        raise NotImplementedError("xywh=True is not used by the detection predictor (detect/predict.py:39)")
+    if not (boxes.is_cuda and boxes.dtype == torch.float32 and boxes.is_contiguous() and boxes.shape[-1] >= 4):
+        raise _lib.YsodError("scale_boxes: boxes must be a contiguous fp32 CUDA tensor (..., >= 4) (no CPU fallback)")
+    if boxes.numel() == 0:
+        return boxes
+    if ratio_pad is None:
+        gain = min(img1_shape[0] / img0_shape[0], img1_shape[1] / img0_shape[1])
+        pad = (round((img1_shape[1] - img0_shape[1] * gain) / 2 - 0.1), round((img1_shape[0] - img0_shape[0] * gain) / 2 - 0.1))
+    else:
+        gain, pad = ratio_pad[0][0], ratio_pad[1]
+    if not padding:
+        pad = (0, 0)
+    params = torch.tensor([float(np.float32(gain)), float(pad[0]), float(pad[1]), float(img0_shape[1]), float(img0_shape[0])],
+                          dtype=torch.float32).to(boxes.device, non_blocking=True)
+    k = int(boxes.shape[-1])
+    with torch.cuda.device(boxes.device):
+        _lib.call("ysod_scale_boxes", _lib.ptr(boxes), 1, boxes.numel() // k, k, _lib.ptr(params), 5, _lib.stream_ptr())
+    return boxes
