@@ -69,6 +69,7 @@ def load():
 
 CFG = {
     "sod": "ultralytics/cfg/models/new/yolov12-sod-fusion-v5-simple.yaml",
+    "stable": "ultralytics/cfg/models/new/yolov12-sod-fusion-v5-stable.yaml",
     "yolov12n": "ultralytics/cfg/models/v12/yolov12n.yaml",
     "yolov12s": "ultralytics/cfg/models/v12/yolov12s.yaml",
     "yolov12m": "ultralytics/cfg/models/v12/yolov12m.yaml",

@@ -16,7 +16,7 @@ import yolo_sod_b200  # noqa: E402,F401
 from yolo_sod_b200 import cfg as ycfg, synth  # noqa: E402
 from oracle import model_ref  # noqa: E402
 
-CONFIGS = ["yolov12-sod-fusion-v5-simple", "yolov12n", "yolov12s", "yolov12m", "E1", "E2", "E3", "E4", "E5", "E6"]
+CONFIGS = ["yolov12-sod-fusion-v5-simple", "yolov12-sod-fusion-v5-stable", "yolov12n", "yolov12s", "yolov12m", "E1", "E2", "E3", "E4", "E5", "E6"]
 
 
 def calibrate(name, seed=0, target_frac=0.04):
@@ -54,10 +54,11 @@ def calibrate(name, seed=0, target_frac=0.04):
 
 
 if __name__ == "__main__":
-    out = {}
-    for name in CONFIGS:
+    path = os.path.join(ROOT, "yolo-sod_b200", "data", "synth_calib.json")
+    only = sys.argv[1:]                      # optional: recompute just these configs, keep the rest of the table
+    out = json.load(open(path)) if (only and os.path.exists(path)) else {}
+    for name in (only or CONFIGS):
         out[synth.calib_key(name, 0)] = calibrate(name, 0)
         print(name, "BN layers:", len(out[synth.calib_key(name, 0)]) - 1, "cls_bias:", out[synth.calib_key(name, 0)]["cls_bias"])
-    path = os.path.join(ROOT, "yolo-sod_b200", "data", "synth_calib.json")
     json.dump(out, open(path, "w"), indent=0, sort_keys=True)
     print("wrote", path, os.path.getsize(path), "bytes")

@@ -96,6 +96,12 @@ def test_ablation_ladder_bf16(name):
     _check(name, torch.bfloat16, 1, 160, 2e-2, layer_tol=4e-2, seed=17)   # raw head maps at 2 %; intermediate layers are diagnostics (4 %)
 
 
+def test_stable_variant_bf16():
+    """cfg/models/new/yolov12-sod-fusion-v5-stable.yaml: DetectStable head (== Detect in eval), Swin blocks at P5 (8 heads, 512 ch) and
+    P2 (4 heads: the unfused window-attention path, since the fused kernel is the 2-head instance)."""
+    _check("yolov12-sod-fusion-v5-stable", torch.bfloat16, 1, 320, 2e-2, layer_tol=4e-2, seed=19)
+
+
 def test_yolov12n_fp32_and_bf16():
     _check("yolov12n", torch.float32, 2, 128, 1e-4, layer_tol=2e-4)
     _check("yolov12n", torch.bfloat16, 1, 640, 2e-2, layer_tol=4e-2)  # attention-heavy: diagnostic layer bound 4 %

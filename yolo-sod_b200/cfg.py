@@ -10,6 +10,7 @@ A user can pass their own reference YAML (path or dict); the two architectures t
     "yolov12-sod-fusion-v5-simple"      ultralytics/cfg/models/new/yolov12-sod-fusion-v5-simple.yaml   (13.56 M params)
     "yolov12{n,s,m}"                    ultralytics/cfg/models/v12/yolov12.yaml + scale
     "E1" .. "E6"                        ultralytics/cfg/models/new/E1..E6.yaml (the ablation ladder, derived from the full model)
+    "yolov12-sod-fusion-v5-stable"      ultralytics/cfg/models/new/yolov12-sod-fusion-v5-stable.yaml (DetectStable head, 14.21 M params)
 """
 import math
 import re
@@ -96,8 +97,30 @@ def _ablate(base: dict, drop, detect_from=None) -> dict:
 _SE, _CBAM, _SWIN, _A2, _CA = {1, 23}, {4, 18}, {9, 28}, {12}, {32}
 _P2_PATH = {24, 25, 26, 27, 29, 30, 31}   # top-down P3->P2 branch and the P2->P3 bottom-up step
 
+# ultralytics/cfg/models/new/yolov12-sod-fusion-v5-stable.yaml: the "stable" training variant -- no SE/CBAM/CA/A2 blocks, Swin blocks
+# at P5 (8 heads) and P2 (4 heads), DetectStable head; its `aux_head:` (DETRAuxHead) section is not part of the inference graph
+# (parse_model only walks backbone + neck + head)
+_SOD_STABLE = {
+    "nc": 10, "depth_multiple": 0.33, "width_multiple": 0.50, "ch": 3,
+    "backbone": [
+        [-1, 1, "Conv", [64, 3, 2]], [-1, 1, "Conv", [128, 3, 2]], [-1, 3, "C2f", [128, True]], [-1, 1, "Conv", [256, 3, 2]],
+        [-1, 6, "C2f", [256, True]], [-1, 1, "Conv", [512, 3, 2]], [-1, 3, "C2f", [512, True]], [-1, 1, "C2f", [512, True]],
+        [-1, 1, "Conv", [1024, 3, 2]], [-1, 2, "C2f", [1024, True]], [-1, 1, "SwinBlock", [8, 7]], [-1, 1, "SPPF", [1024, 5]],
+    ],
+    "neck": [
+        [-1, 1, "Conv", [512, 1, 1]], [-1, 1] + UP, [[-1, 6], 1, "Concat", [1]], [-1, 3, "C2f", [512, True]],
+        [-1, 1, "Conv", [256, 1, 1]], [-1, 1] + UP, [[-1, 4], 1, "Concat", [1]], [-1, 3, "C2f", [256, True]],
+        [-1, 1, "Conv", [128, 1, 1]], [-1, 1] + UP, [[-1, 2], 1, "Concat", [1]], [-1, 3, "C2f", [128, True]],
+        [-1, 1, "SwinBlock", [4, 7]],
+        [-1, 1, "Conv", [256, 3, 2]], [[-1, 19], 1, "Concat", [1]], [-1, 3, "C2f", [256, True]],
+        [-1, 1, "Conv", [512, 3, 2]], [[-1, 15], 1, "Concat", [1]], [-1, 3, "C2f", [512, True]],
+        [-1, 1, "Conv", [1024, 3, 2]], [[-1, 11], 1, "Concat", [1]], [-1, 2, "C2f", [1024, True]],
+    ],
+    "head": [[[24, 27, 30, 33], 1, "DetectStable", ["nc"]]],
+}
+
 BUILTIN = {
-    "yolov12-sod-fusion-v5-simple": _SOD_SIMPLE, "yolov12": _YOLOV12,
+    "yolov12-sod-fusion-v5-simple": _SOD_SIMPLE, "yolov12": _YOLOV12, "yolov12-sod-fusion-v5-stable": _SOD_STABLE,
     # the paper's ablation ladder (README.md:131-137; cfg/models/new/E1..E6.yaml): E1 plain PANet with P3-P5 heads, E2 + P2 head,
     # E3 + SE, E4 + CBAM, E5 + Swin, E6 + A2 (the complete model adds CoordAtt)
     "E1": _ablate(_SOD_SIMPLE, _SE | _CBAM | _SWIN | _A2 | _CA | _P2_PATH, detect_from=[22, 35, 38]),
@@ -257,11 +280,14 @@ def parse_model(d: dict, ch: int = None, nc: int = None) -> ModelSpec:
             p = dict(scale=args[1], mode=args[2])
             if p["mode"] != "nearest" or args[0] is not None:
                 raise NotImplementedError("only nn.Upsample(None, s, 'nearest') is on the hot path")
-        elif m == "Detect":
+        elif m in ("Detect", "DetectStable"):
+            # DetectStable (nn/modules/detect_stable.py:7-34) is Detect plus a training-only per-level `active_mask` buffer: in eval
+            # mode its forward is Detect's, so it maps to the same layer type (the buffer is kept for state_dict compatibility)
             fl = f if isinstance(f, (list, tuple)) else [f]
             c1 = [chs[x] for x in fl]
             c2 = chs[fl[-1]]
-            p = dict(nc=args[0], legacy=legacy)
+            p = dict(nc=args[0], legacy=legacy, stable=(m == "DetectStable"))
+            m = "Detect"
         else:
             raise NotImplementedError(f"module {m!r} (layer {i}) is outside the hot path this library covers")
         if n != 1:
@@ -411,6 +437,8 @@ def param_shapes(spec: ModelSpec) -> "Dict[str, tuple]":
         elif t == "Detect":
             nc, ch = p["nc"], L.c1
             c2, c3 = detect_channels(nc, ch)
+            if p.get("stable"):
+                sh[f"{P}.active_mask"] = (len(ch),)
             for i, x in enumerate(ch):
                 _conv(sh, f"{P}.cv2.{i}.0", x, c2, 3)
                 _conv(sh, f"{P}.cv2.{i}.1", c2, c2, 3)

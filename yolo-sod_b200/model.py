@@ -118,6 +118,10 @@ class YOLO:
                  device="cuda:0", seed=0):
         if task not in (None, "detect"):
             raise NotImplementedError("only task='detect' is on the hot path")
+        if isinstance(model, str) and model.endswith(".pt"):
+            # engine/model.py:288-292 _load -> attempt_load_one_weight (nn/tasks.py:941-964): a trained reference checkpoint
+            from .checkpoint import attempt_load_one_weight
+            model, self.ckpt = attempt_load_one_weight(model, device=device, dtype=dtype)
         self.model = model if isinstance(model, B200DetectionModel) else DetectionModel(model, weights=weights, dtype=dtype,
                                                                                         device=device, seed=seed)
         self.backend = AutoBackend(self.model)

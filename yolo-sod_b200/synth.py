@@ -46,6 +46,8 @@ def synth_state_dict(spec: "_cfg.ModelSpec", cfg_name: str, seed: int = 0, calib
         leaf = name.rsplit(".", 1)[-1]
         if leaf == "num_batches_tracked":
             t = torch.zeros((), dtype=torch.long)
+        elif leaf == "active_mask":                       # DetectStable: every level active (detect_stable.py:13)
+            t = torch.ones(shape, dtype=torch.bool)
         elif ".bn." in name or ".bn1." in name:
             pfx = name.rsplit(".", 1)[0]
             m, v = calib.get(pfx, [0.0, 0.4])
