@@ -328,10 +328,13 @@ extern "C" int ysod_mha_core(const void* q, const void* k, const void* v, int dt
     YSOD_CHECK_ARG(q && k && v && out, "ysod_mha_core: null pointer");
     YSOD_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "ysod_mha_core: row strides must be multiples of 8");
     YSOD_CHECK_ARG(batch <= 65535 || true, "ysod_mha_core: batch");
-    if (dtype == YSOD_BF16 && L <= 64 && (D == 32 || D == 64) && batch <= 65535 && ((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 &&
+    if (dtype == YSOD_BF16 && L <= 64 && (D == 16 || D == 32 || D == 64) && batch <= 65535 && ((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 &&
         ((uintptr_t)v % 16) == 0 && ((uintptr_t)out % 16) == 0 && bsq % 8 == 0 && bsk % 8 == 0 && bsv % 8 == 0 && bso % 8 == 0) {
         dim3 wgrid(heads, batch);
-        if (D == 32)
+        if (D == 16)   // 4 heads over 64 channels: the P2 SwinBlock of yolov12-sod-fusion-v5-stable.yaml
+            ysod_launch(mha_win_kernel<16>, wgrid, 128, 0, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, L, ldq, ldk, ldv,
+                                                      bsq, bsk, bsv, scale, (__nv_bfloat16*)out, ldo, bso);
+        else if (D == 32)
             ysod_launch(mha_win_kernel<32>, wgrid, 128, 0, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, L, ldq, ldk, ldv,
                                                       bsq, bsk, bsv, scale, (__nv_bfloat16*)out, ldo, bso);
         else
@@ -355,12 +358,14 @@ extern "C" int ysod_mha_core(const void* q, const void* k, const void* v, int dt
     }
 #define LAUNCH(T, DD) \
     ysod_launch(mha_core_kernel<T, DD>, grid, 64, 0, st, (const T*)q, (const T*)k, (const T*)v, L, ldq, ldk, ldv, bsq, bsk, bsv, scale, (T*)out, ldo, bso)
-    if (dtype == YSOD_F32 && D == 32) LAUNCH(float, 32);
+    if (dtype == YSOD_F32 && D == 16) LAUNCH(float, 16);
+    else if (dtype == YSOD_BF16 && D == 16) LAUNCH(__nv_bfloat16, 16);
+    else if (dtype == YSOD_F32 && D == 32) LAUNCH(float, 32);
     else if (dtype == YSOD_F32 && D == 64) LAUNCH(float, 64);
     else if (dtype == YSOD_BF16 && D == 32) LAUNCH(__nv_bfloat16, 32);
     else if (dtype == YSOD_BF16 && D == 64) LAUNCH(__nv_bfloat16, 64);
     else {
-        ysod_set_error("ysod_mha_core: unsupported head_dim %d / dtype %d (supported: 32, 64)", D, dtype);
+        ysod_set_error("ysod_mha_core: unsupported head_dim %d / dtype %d (supported: 16, 32, 64)", D, dtype);
         return YSOD_ERR_UNSUPPORTED;
     }
 #undef LAUNCH

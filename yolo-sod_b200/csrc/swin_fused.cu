@@ -53,6 +53,13 @@ __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// x * sigmoid(x) = h + h * tanh(h), h = x / 2: one MUFU op (same form as the tcgen05 conv epilogue)
+__device__ __forceinline__ float silu_tanh(float x) {
+    const float h = 0.5f * x;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
 __device__ __forceinline__ uint32_t ld32(const __nv_bfloat16* p) { return *reinterpret_cast<const uint32_t*>(p); }
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
@@ -73,14 +80,31 @@ __device__ __forceinline__ float quad_max(float v) {
 }
 __device__ __forceinline__ void group_barrier(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
 
-// acc[NB][4] += A[KS][4] (16 rows x 16*KS) * W^T, W rows n0 + nb*8 + g (row stride ldw), columns 16*ks + 2t (+8)
+// Four 8x8 bf16 matrices in one shared-memory instruction: lane i supplies the 16 B row (i & 7) of matrix (i >> 3); every lane
+// receives, per matrix, the two elements (row lane/4, columns 2*(lane%4), +1) -- exactly the m16n8k16 B-fragment registers.
+__device__ __forceinline__ void ldsm4(uint32_t* r, const __nv_bfloat16* row) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(row);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+// B fragments of two consecutive K steps (32 columns starting at `w8`'s row base) for the 8 operand rows starting at row 0 of `W8`:
+// matrices 0..3 = columns [0,8) [8,16) [16,24) [24,32)  ->  (b0, b1) of K step 0, (b0, b1) of K step 1
+__device__ __forceinline__ void ldsm_b2(uint32_t* r, const __nv_bfloat16* W8, int ldw, int lane) {
+    ldsm4(r, W8 + (size_t)(lane & 7) * ldw + (lane >> 3) * 8);
+}
+
+// acc[NB][4] += A[KS][4] (16 rows x 16*KS) * W^T, W rows nb*8 .. nb*8+7 (row stride ldw, 16 B aligned rows), KS even
 template <int NB, int KS>
-__device__ __forceinline__ void gemm_frag(float (*acc)[4], const uint32_t (*a)[4], const __nv_bfloat16* W, int ldw, int g, int t) {
+__device__ __forceinline__ void gemm_frag(float (*acc)[4], const uint32_t (*a)[4], const __nv_bfloat16* W, int ldw, int lane) {
+    static_assert(KS % 2 == 0, "two K steps per ldmatrix.x4");
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) {
-        const __nv_bfloat16* wr = W + (size_t)(nb * 8 + g) * ldw + 2 * t;
 #pragma unroll
-        for (int ks = 0; ks < KS; ++ks) mma16816(acc[nb], a[ks], ld32(wr + ks * 16), ld32(wr + ks * 16 + 8));
+        for (int k2 = 0; k2 < KS / 2; ++k2) {
+            uint32_t b[4];
+            ldsm_b2(b, W + (size_t)(nb * 8) * ldw + k2 * 32, ldw, lane);
+            mma16816(acc[nb], a[2 * k2], b[0], b[1]);
+            mma16816(acc[nb], a[2 * k2 + 1], b[2], b[3]);
+        }
     }
 }
 // accumulator layout (row g: [nb][0..1], row g+8: [nb][2..3], columns 8nb + 2t) -> A fragments of the next GEMM (K step i = n-blocks 2i, 2i+1)
@@ -223,7 +247,7 @@ swin64_fused_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, in
         {
             float acc[8][4];
             bias_init(acc, sm.pf + F_BQKV + 64, t);                         // K = rows [64,128) of in_proj_weight
-            gemm_frag<8, 4>(acc, xn, sm.wqkv + 64 * LDW, LDW, g, t);
+            gemm_frag<8, 4>(acc, xn, sm.wqkv + 64 * LDW, LDW, lane);
 #pragma unroll
             for (int nb = 0; nb < 8; ++nb) {
                 const int h = nb >> 2, d = (nb & 3) * 8 + 2 * t;
@@ -231,7 +255,7 @@ swin64_fused_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, in
                 *reinterpret_cast<uint32_t*>(&sg.ks[(h * 64 + row0 + 8) * LDK + d]) = pack2(acc[nb][2], acc[nb][3]);
             }
             bias_init(acc, sm.pf + F_BQKV + 128, t);                        // V = rows [128,192)
-            gemm_frag<8, 4>(acc, xn, sm.wqkv + 128 * LDW, LDW, g, t);
+            gemm_frag<8, 4>(acc, xn, sm.wqkv + 128 * LDW, LDW, lane);
 #pragma unroll
             for (int nb = 0; nb < 8; ++nb) {
                 const int h = nb >> 2, d = (nb & 3) * 8 + 2 * t;
@@ -241,7 +265,7 @@ swin64_fused_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, in
                 sg.vt[(h * HD + d + 1) * LDV + row0 + 8] = __float2bfloat16_rn(acc[nb][3]);
             }
             bias_init(acc, sm.pf + F_BQKV, t);                              // Q = rows [0,64), scaled by 1/sqrt(d)
-            gemm_frag<8, 4>(acc, xn, sm.wqkv, LDW, g, t);
+            gemm_frag<8, 4>(acc, xn, sm.wqkv, LDW, lane);
 #pragma unroll
             for (int nb = 0; nb < 8; ++nb)
 #pragma unroll
@@ -258,9 +282,10 @@ swin64_fused_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, in
 #pragma unroll
             for (int nb = 0; nb < 8; ++nb) {
                 s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
-                const __nv_bfloat16* kr = &sg.ks[(h * 64 + nb * 8 + g) * LDK + 2 * t];
-                mma16816(s[nb], qf[2 * h], ld32(kr), ld32(kr + 8));
-                mma16816(s[nb], qf[2 * h + 1], ld32(kr + 16), ld32(kr + 24));
+                uint32_t kb[4];
+                ldsm_b2(kb, &sg.ks[(h * 64 + nb * 8) * LDK], LDK, lane);
+                mma16816(s[nb], qf[2 * h], kb[0], kb[1]);
+                mma16816(s[nb], qf[2 * h + 1], kb[2], kb[3]);
             }
             float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
@@ -287,9 +312,13 @@ swin64_fused_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, in
 #pragma unroll
             for (int nb = 0; nb < 4; ++nb) {
                 o[nb][0] = o[nb][1] = o[nb][2] = o[nb][3] = 0.f;
-                const __nv_bfloat16* vr = &sg.vt[(h * HD + nb * 8 + g) * LDV + 2 * t];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) mma16816(o[nb], pfr[i], ld32(vr + i * 16), ld32(vr + i * 16 + 8));
+                for (int i2 = 0; i2 < 2; ++i2) {
+                    uint32_t vb[4];
+                    ldsm_b2(vb, &sg.vt[(h * HD + nb * 8) * LDV + i2 * 32], LDV, lane);
+                    mma16816(o[nb], pfr[2 * i2], vb[0], vb[1]);
+                    mma16816(o[nb], pfr[2 * i2 + 1], vb[2], vb[3]);
+                }
                 o[nb][0] *= inv0; o[nb][1] *= inv0; o[nb][2] *= inv1; o[nb][3] *= inv1;
             }
             acc_to_frag<2>(&af[2 * h], o);
@@ -299,7 +328,7 @@ swin64_fused_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, in
         {
             float acc[8][4];
             bias_init(acc, sm.pf + F_BO, t);
-            gemm_frag<8, 4>(acc, af, sm.wo, LDW, g, t);
+            gemm_frag<8, 4>(acc, af, sm.wo, LDW, lane);
 #pragma unroll
             for (int nb = 0; nb < 8; ++nb)
 #pragma unroll
@@ -314,7 +343,7 @@ swin64_fused_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, in
             for (int half = 0; half < 2; ++half) {
                 float acc[8][4];
                 bias_init(acc, sm.pf + F_B1 + half * 64, t);
-                gemm_frag<8, 4>(acc, xn2, sm.w1 + half * 64 * LDW, LDW, g, t);
+                gemm_frag<8, 4>(acc, xn2, sm.w1 + half * 64 * LDW, LDW, lane);
 #pragma unroll
                 for (int nb = 0; nb < 8; ++nb)
 #pragma unroll
@@ -323,7 +352,7 @@ swin64_fused_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, in
             }
             float acc[8][4];
             bias_init(acc, sm.pf + F_B2, t);
-            gemm_frag<8, 8>(acc, hf, sm.w2, LDW2, g, t);
+            gemm_frag<8, 8>(acc, hf, sm.w2, LDW2, lane);
 #pragma unroll
             for (int nb = 0; nb < 8; ++nb)
 #pragma unroll
@@ -335,7 +364,7 @@ swin64_fused_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, in
             acc_to_frag<4>(xf, x1);
             float acc[8][4];
             bias_init(acc, sm.pf + F_BPW, t);
-            gemm_frag<8, 4>(acc, xf, sm.wpw, LDW, g, t);
+            gemm_frag<8, 4>(acc, xf, sm.wpw, LDW, lane);
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr) {
                 const int tk = row0 + rr * 8;
@@ -346,8 +375,8 @@ swin64_fused_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, in
                     for (int nb = 0; nb < 8; ++nb) {
                         const float2 id = unpack2(ld32(idp + nb * 8));
                         float v0 = acc[nb][2 * rr], v1 = acc[nb][2 * rr + 1];
-                        v0 = v0 / (1.0f + __expf(-v0)) + id.x;
-                        v1 = v1 / (1.0f + __expf(-v1)) + id.y;
+                        v0 = silu_tanh(v0) + id.x;
+                        v1 = silu_tanh(v1) + id.y;
                         *reinterpret_cast<uint32_t*>(&sg.tok[tk * LDW + nb * 8 + 2 * t]) = pack2(v0, v1);
                     }
                 }
