@@ -51,6 +51,8 @@ int ysod_conv_tc_create(ysod_conv_tc** handle, const void* x, int N, int H, int 
  * nn.Upsample(scale_factor=2, mode="nearest") (yaml neck rows `[-1, 1, nn.Upsample, [None, 2, "nearest"]]`) into the store --
  * `out` is then the N x 2Ho x 2Wo x Cout destination view and every output pixel is written to its 2 x 2 block. */
 #define YSOD_CONV_UP2 0x40
+/* | 0x80 (YSOD_CONV_IMG_WEIGHTS): `wgt` is [N][Cout_pad][K], one weight matrix per image (see ysod_scale_weights). */
+#define YSOD_CONV_IMG_WEIGHTS 0x80
 int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, int W, int Cin, int xcs, const void* wgt,
                            const float* bias, int Cout, int Cout_pad, int ksize, int stride, void* out, int out_dtype, int ocs,
                            const void* res, int rcs, int act, int mode);
@@ -58,6 +60,9 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
  * level's final 1x1 head conv (plan: fp32 raw map out, no activation, Cout = 64 + nc): besides the raw map the launch writes
  * y (B, 4+nc, A_total) for anchors [a_off, a_off + Ho*Wo). Equivalent to running ysod_dfl_decode on the raw map afterwards. */
 int ysod_conv_tc_set_decode(ysod_conv_tc* h, float* y, int A_total, int a_off, int nc, float stride);
+/* SE (smallobj_modules.py:57-92) folded into the conv that consumes it: conv(x * a[n]) == conv with input-channel columns of the
+ * weights scaled by a[n]. w: [rows][K] fp32 (K ordered (r,s,cin), BN folded); gate: [N][Cin] fp32; out: [N][rows][K] bf16. */
+int ysod_scale_weights(const float* w, int rows, int K, int Cin, const float* gate, int N, void* out, void* stream);
 int ysod_conv_tc_run(ysod_conv_tc* handle, void* stream);
 int ysod_conv_tc_info(ysod_conv_tc* handle, int* out8);
 void ysod_conv_tc_destroy(ysod_conv_tc* handle);

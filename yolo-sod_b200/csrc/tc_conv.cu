@@ -56,6 +56,7 @@ struct TcParams {
     float* dec_y;
     int dec_A, dec_off, dec_nc;
     float dec_stride;
+    int w_img_rows;   // > 0: per-image weights (an SE channel gate folded into the next conv): image i uses weight rows [i*w_img_rows, +Cout_pad)
     int up2;    // nn.Upsample(scale 2, nearest) fused into the store: every output pixel is written to its 2 x 2 block of the 2Ho x 2Wo destination
     int debug;  // profiling only (mode >> 8): 1 = epilogue drains without work, 2 = producer skips TMA, 4 = MMA issuer skips tcgen05.mma,
                 // 8 = epilogue skips the TMA store, 16 = epilogue skips the activation
@@ -335,7 +336,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const uint32_t slot = (uint32_t)(stage * G + g);
                             if (!(p.debug & 2)) {
                                 tma_load_4d(a_base + slot * p.a_bytes, &tmA, full, cc * BK, ow0 * cstride + s - pad, oh0 * cstride + r - pad, img);
-                                tma_load_2d(b_base + slot * p.b_bytes, &tmB, full, tap * Cin + cc * BK, n0);
+                                tma_load_2d(b_base + slot * p.b_bytes, &tmB, full, tap * Cin + cc * BK, n0 + img * p.w_img_rows);
                             }
                             if (++cc == cchunks) {
                                 cc = 0; ++tap;
@@ -716,6 +717,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+__global__ void scale_weights_kernel(const float* __restrict__ w, int rows, int K, int Cin, const float* __restrict__ gate,
+                                     __nv_bfloat16* __restrict__ out, long long total) {
+    ysod_pdl_sync();
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int k = (int)(i % K);
+    const long long rk = (long long)rows * K;
+    const int n = (int)(i / rk);
+    out[i] = __float2bfloat16_rn(w[i - (long long)n * rk] * gate[(size_t)n * Cin + (k % Cin)]);
+}
+
 // ---- host side --------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -755,6 +767,7 @@ extern "C" {
 // ksize in {1,3}, stride in {1,2} (pad = ksize/2, conv.py:28 autopad), groups == 1, Cin % 32 == 0.
 // mode: 0 = auto, 1 = generic per-tap kernel, 2 = force the 3x3 halo-reuse kernel (error if the shape does not qualify);
 //       | 0x40 = fuse nn.Upsample(scale_factor=2, mode='nearest') into the store: `out` is the N x 2Ho x 2Wo destination view.
+//       | 0x80 = per-image weights: `wgt` is [N][Cout_pad][K] (ysod_scale_weights: an SE channel gate folded into this conv).
 int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, int W, int Cin, int xcs, const void* wgt,
                            const float* bias, int Cout, int Cout_pad, int ksize, int stride, void* out, int out_dtype, int ocs,
                            const void* res, int rcs, int act, int mode) {
@@ -795,7 +808,12 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
     bool halo = false;
     const int dbg = mode >> 8;
     const bool up2 = (mode & 0x40) != 0;
+    const bool img_w = (mode & 0x80) != 0;
     mode &= 0x3f;
+    if (img_w) {
+        YSOD_CHECK_ARG(mode != 2, "ysod_conv_tc_create_ex: per-image weights need the generic kernel (resident taps are shared by all images)");
+        mode = 1;
+    }
     if (ksize == 3 && stride == 1 && (Cin % 64 == 0 || Cin == 32)) {
         const double hutil = (double)Ho * Wo / ((double)ysod_cdiv(Ho, 16) * ysod_cdiv(Wo, 8) * 128.0);
         halo = (mode == 2) || (mode == 0 && hutil >= 0.75);
@@ -803,6 +821,7 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
     YSOD_CHECK_ARG(mode != 2 || halo, "ysod_conv_tc_create_ex: shape does not qualify for the halo kernel");
     p.debug = dbg;
     p.up2 = up2 ? 1 : 0;
+    p.w_img_rows = img_w ? Cout_pad : 0;
     if (halo) { bestTH = 16; bestTW = 8; }
     p.N = N; p.Ho = Ho; p.Wo = Wo; p.TH = bestTH; p.TW = bestTW;
     p.tiles_h = ysod_cdiv(Ho, bestTH); p.tiles_w = ysod_cdiv(Wo, bestTW);
@@ -946,7 +965,7 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
     }
     {
         const cuuint64_t K = (cuuint64_t)ksize * ksize * Cin;
-        cuuint64_t dims[2] = {K, (cuuint64_t)Cout_pad};
+        cuuint64_t dims[2] = {K, (cuuint64_t)Cout_pad * (cuuint64_t)(img_w ? N : 1)};
         cuuint64_t strides[1] = {K * 2};
         cuuint32_t box[2] = {(cuuint32_t)p.BK, (cuuint32_t)BN};
         cuuint32_t es[2] = {1, 1};
@@ -1023,6 +1042,17 @@ int ysod_conv_tc_set_decode(ysod_conv_tc* h, float* y, int A_total, int a_off, i
     YSOD_CHECK_ARG(nc > 0 && p.Cout == 64 + nc && p.BN >= 64 + nc, "ysod_conv_tc_set_decode: Cout %d != 64 + nc (%d)", p.Cout, nc);
     YSOD_CHECK_ARG(a_off >= 0 && a_off + p.Ho * p.Wo <= A_total, "ysod_conv_tc_set_decode: anchor range out of bounds");
     p.dec_y = y; p.dec_A = A_total; p.dec_off = a_off; p.dec_nc = nc; p.dec_stride = stride;
+    return YSOD_OK;
+}
+
+// SE folded into the following conv (smallobj_modules.py:84-92 `x * a` followed by conv.py:37-55): conv(x * a[n]) == conv with
+// the weights' input-channel columns scaled by a[n], so the gated activation map is never written / re-read.
+// w: [rows][K] fp32 master weights (K ordered (r, s, cin), BN folded), gate: [N][Cin] fp32 -> out: [N][rows][K] bf16.
+int ysod_scale_weights(const float* w, int rows, int K, int Cin, const float* gate, int N, void* out, cudaStream_t stream) {
+    YSOD_CHECK_ARG(w && gate && out && rows > 0 && K > 0 && Cin > 0 && K % Cin == 0 && N > 0, "ysod_scale_weights: bad args");
+    const long long total = (long long)N * rows * K;
+    ysod_launch(scale_weights_kernel, ysod_cdiv(total, 256), 256, 0, stream, w, rows, K, Cin, gate, (__nv_bfloat16*)out, total);
+    YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }
 

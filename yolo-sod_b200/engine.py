@@ -54,6 +54,17 @@ class View:
         return self.torch_nhwc().permute(0, 3, 1, 2)
 
 
+@dataclass
+class GatedView:
+    """Output of an SE block whose `x * gate` was folded into the weights of the conv that consumes it (Program._build): the gated
+    map is never materialised; layer_output() reconstructs it from the block's input and the gate for the parity tests."""
+    base: View
+    gate: torch.Tensor   # (N, C) fp32
+
+    def torch_nchw(self):
+        return self.base.torch_nchw().float() * self.gate[:, :, None, None]
+
+
 class Program:
     """A compiled forward for one (batch, H, W): buffers + launch list."""
 
@@ -119,9 +130,10 @@ class Program:
         return w * s.view(-1, 1, 1, 1), b - mu * s
 
     def conv(self, x: View, w: torch.Tensor, bias: torch.Tensor, k, s, g, act, out: View, res: View = None,
-             out_f32=False, pad=None, up2=False):
+             out_f32=False, pad=None, up2=False, gate=None):
         """w: (Cout, Cin/g, k, k) fp32 with BN folded; bias fp32 (Cout). up2: `out` is the 2x nearest-upsampled destination
-        (tensor-core path only; the caller checks `can_up2`)."""
+        (tensor-core path only; the caller checks `tc_eligible`). gate: (N, Cin) fp32 device tensor of an SE block folded into this conv
+        (per-image weights W * gate[n], rebuilt every forward by ysod_scale_weights; tensor-core path only)."""
         pad = k // 2 if pad is None else pad
         Cout, Cin = w.shape[0], x.C
         assert w.shape[1] * g == Cin, (w.shape, Cin, g)
@@ -142,18 +154,28 @@ class Program:
             return
         use_tc = (self.m.use_tc and self.code == _lib.BF16 and g == 1 and k in (1, 3) and s in (1, 2) and pad == k // 2
                   and Cin % 32 == 0 and (s == 1 or (x.H % 2 == 0 and x.W % 2 == 0)))
-        assert use_tc or not up2, "fused upsample needs the tensor-core conv"
+        assert use_tc or not (up2 or gate is not None), "fused upsample / folded SE gate need the tensor-core conv"
         if use_tc:
             cpad = (Cout + 15) // 16 * 16
             wk = torch.zeros((cpad, k * k * Cin), dtype=torch.float32)
             wk[:Cout] = w.permute(0, 2, 3, 1).reshape(Cout, -1)
             bk = torch.zeros(cpad, dtype=torch.float32)
             bk[:Cout] = bias
-            wd, bd = self.dev_t(wk, torch.bfloat16), self.dev_t(bk)
+            bd = self.dev_t(bk)
+            mode = _lib.CONV_UP2 if up2 else 0
+            if gate is None:
+                wd = self.dev_t(wk, torch.bfloat16)
+            else:
+                # one weight matrix per image: fp32 master weights x gate[n] -> bf16, rebuilt by a small launch before the conv
+                wm = self.dev_t(wk)
+                wd = torch.empty((x.N, cpad, k * k * Cin), device=self.dev, dtype=torch.bfloat16)
+                self.keep.append(wd)
+                self.emit("ysod_scale_weights", _lib.ptr(wm), cpad, k * k * Cin, Cin, _lib.ptr(gate), x.N, _lib.ptr(wd), desc="SE gate -> conv weights")
+                mode |= _lib.CONV_IMG_WEIGHTS
             h = C.c_void_p()
             _lib.call("ysod_conv_tc_create_ex", C.byref(h), x.ptr(), x.N, x.H, x.W, Cin, x.cs, _lib.ptr(wd), _lib.ptr(bd), Cout, cpad,
                       k, s, out.ptr(), odt, out.cs, res.ptr() if res is not None else None, res.cs if res is not None else 0, actc,
-                      _lib.CONV_UP2 if up2 else 0)
+                      mode)
             self.tc_handles.append(h)
             self.ops.append((_lib.load().ysod_conv_tc_run, (h,), "ysod_conv_tc_run"))
             self.sched.append(("op", len(self.ops) - 1, self._lane))
@@ -161,7 +183,7 @@ class Program:
             self.op_flops.append(fl)
             info = (C.c_int * 8)()
             _lib.call("ysod_conv_tc_info", h, info)
-            self.op_desc.append(f"{self._ctx} tc {Cin}->{Cout} k{k}s{s}{'up2' if up2 else ''} @{Ho}x{Wo} N{x.N} tile{info[0]}x{info[1]} BN{info[2]} BK{info[3]} "
+            self.op_desc.append(f"{self._ctx} tc {Cin}->{Cout} k{k}s{s}{'up2' if up2 else ''}{'+SEgate' if gate is not None else ''} @{Ho}x{Wo} N{x.N} tile{info[0]}x{info[1]} BN{info[2]} BK{info[3]} "
                                 f"st{info[4]} grid{info[5]}x{info[6]} smem{info[7]}")
             self.tc_flops += fl
             self.n_launches += 1
@@ -181,20 +203,20 @@ class Program:
                   out.ptr(), odt, out.cs, res.ptr() if res is not None else None, res.cs if res is not None else 0, actc,
                   flops=2.0 * x.N * Ho * Wo * Cout * k * k * Cin / g, desc=f"direct {Cin}->{Cout} k{k}s{s}g{g} @{Ho}x{Wo}")
 
-    def conv_bn(self, x, pfx, k=1, s=1, g=1, act=True, out=None, res=None, pad=None, up2=False):
+    def conv_bn(self, x, pfx, k=1, s=1, g=1, act=True, out=None, res=None, pad=None, up2=False, gate=None):
         """Reference `Conv` wrapper (conv.py:37-55) with BN folded."""
         w, b = self.folded(pfx)
         if out is None:
             p = k // 2 if pad is None else pad
             out = self.new(x.N, (x.H + 2 * p - k) // s + 1, (x.W + 2 * p - k) // s + 1, w.shape[0])
-        self.conv(x, w, b, k, s, g, "silu" if act else "none", out, res, pad=pad, up2=up2)
+        self.conv(x, w, b, k, s, g, "silu" if act else "none", out, res, pad=pad, up2=up2, gate=gate)
         return out
 
-    def can_up2(self, L, cin, h, w):
-        """A top-level Conv layer whose only consumer is nn.Upsample(2, nearest) can write the upsampled map itself
-        (tensor-core path: dense, k in {1,3}, default padding)."""
+    def tc_eligible(self, L, cin, h, w):
+        """True when the top-level Conv layer L runs on the tensor-core kernel (dense, k in {1,3}, default padding): the precondition
+        for writing a fused nn.Upsample(2) output or taking per-image (SE-gated) weights."""
         p = L.p
-        return (self.m.use_tc and self.code == _lib.BF16 and self.m.fuse_upsample and p["g"] == 1 and p["k"] in (1, 3)
+        return (self.m.use_tc and self.code == _lib.BF16 and p["g"] == 1 and p["k"] in (1, 3)
                 and p["s"] in (1, 2) and p["p"] in (None, p["k"] // 2) and cin % 32 == 0 and (p["s"] == 1 or (h % 2 == 0 and w % 2 == 0)))
 
     def linear(self, x: View, w, b, act="none", out=None, res=None):
@@ -380,6 +402,8 @@ class Program:
         w2, b2 = self.dev_t(sd[f"{P}.fc2.weight"].reshape(Cc, hid)), self.dev_t(sd[f"{P}.fc2.bias"])
         self.emit("ysod_gap_partial", x.ptr(), self.code, x.N, HW, Cc, x.cs, S, _lib.ptr(psum), None)
         self.emit("ysod_se_gate", _lib.ptr(psum), x.N, S, HW, Cc, _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), hid, _lib.ptr(gate))
+        if out is None:
+            return gate          # `x * gate` is folded into the consumer conv's weights
         self.emit("ysod_scale_channels", x.ptr(), self.code, x.N, HW, Cc, x.cs, _lib.ptr(gate), out.ptr(), out.cs)
 
     def cbam(self, x, P, out):
@@ -545,8 +569,18 @@ class Program:
                 if (isinstance(src, int) and S.type == "Conv" and S.i > 0 and consumers.get(src) == [L.i] and src not in home
                         and src not in det_inputs):
                     ssrc = S.i - 1 if S.f == -1 else S.f
-                    if self.can_up2(S, shp[ssrc][2], shp[ssrc][0], shp[ssrc][1]):
+                    if self.m.fuse_upsample and self.tc_eligible(S, shp[ssrc][2], shp[ssrc][0], shp[ssrc][1]):
                         fold_up[src] = L.i
+        # SE -> Conv pairs where the SE output feeds nothing else: the channel gate goes into per-image conv weights
+        fold_se = set()
+        for L in layers:
+            if L.type in ("SE_Block", "SE") and L.i > 0 and self.m.fuse_se and L.i not in home and L.i not in det_inputs:
+                cons = consumers.get(L.i, [])
+                if len(cons) == 1 and layers[cons[0]].type == "Conv" and cons[0] not in fold_up:
+                    Cn = layers[cons[0]]
+                    src_hw = shp[L.i]
+                    if self.tc_eligible(Cn, src_hw[2], src_hw[0], src_hw[1]):
+                        fold_se.add(L.i)
         for L in layers:
             P, p, t = f"model.{L.i}", L.p, L.type
             self._ctx = f"L{L.i}:{t}"
@@ -581,8 +615,14 @@ class Program:
                 if U in det_inputs:
                     self.sched.append(("record", f"L{U}", 0))
                 continue
+            if L.i in fold_se:
+                out[L.i] = GatedView(out[src], self.se(out[src], P, None))
+                continue
             o = home[L.i] if L.i in home else self.new(self.B, h, w, c)
             x = None if L.i == 0 else out[src]
+            gate = None
+            if isinstance(x, GatedView):
+                x, gate = x.base, x.gate
             if t == "Conv":
                 if L.i == 0:
                     wf, bf = self.folded(P)
@@ -605,7 +645,7 @@ class Program:
                         self.emit("ysod_stem_conv", _lib.ptr(self.img), self.B, self.H, self.W, _lib.ptr(wd), _lib.ptr(bd), co, k, s,
                                   pd, o.ptr(), self.code, o.cs, _lib.ACT["silu" if p["act"] else "none"])
                 else:
-                    self.conv_bn(x, P, p["k"], p["s"], p["g"], p["act"], out=o, pad=p["p"])
+                    self.conv_bn(x, P, p["k"], p["s"], p["g"], p["act"], out=o, pad=p["p"], gate=gate)
             elif t == "C2f":
                 self.c2f(x, P, p, L.c2, o)
             elif t == "C3k2":
@@ -727,7 +767,7 @@ class B200DetectionModel:
     """
 
     def __init__(self, cfg, state_dict, dtype=torch.bfloat16, device="cuda:0", use_tc=True, use_graph=True, nc=None,
-                 static_outputs=True, fuse_swin=True, multi_stream=True, fuse_upsample=True, fuse_decode=True):
+                 static_outputs=True, fuse_swin=True, multi_stream=True, fuse_upsample=True, fuse_decode=True, fuse_se=True):
         _lib.require_cuda()
         _lib.load()
         self.spec = cfg if isinstance(cfg, _cfg.ModelSpec) else _cfg.get_spec(cfg, nc=nc)
@@ -743,6 +783,7 @@ class B200DetectionModel:
         self.fuse_swin = fuse_swin
         self.fuse_upsample = fuse_upsample
         self.fuse_decode = fuse_decode
+        self.fuse_se = fuse_se
         self.multi_stream = multi_stream
         self.static_outputs = static_outputs
         self.stride_list = _cfg.strides_of(self.spec)

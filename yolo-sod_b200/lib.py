@@ -8,6 +8,7 @@ LIB_PATH = os.path.join(_HERE, "libysod.so")
 
 F32, BF16 = 0, 1
 CONV_UP2 = 0x40   # ysod.h YSOD_CONV_UP2
+CONV_IMG_WEIGHTS = 0x80   # ysod.h YSOD_CONV_IMG_WEIGHTS
 ACT = {"none": 0, "silu": 1, "gelu": 2, "relu": 3, "sigmoid": 4, "hsigmoid": 5}
 
 vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_longlong, C.c_float
@@ -25,6 +26,7 @@ PROTOTYPES = {
     "ysod_conv_tc_create": (i32, [C.POINTER(vp), vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, i32, vp, i32, i32, vp, i32, i32]),
     "ysod_conv_tc_create_ex": (i32, [C.POINTER(vp), vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, i32, vp, i32, i32, vp, i32, i32, i32]),
     "ysod_conv_tc_set_decode": (i32, [vp, vp, i32, i32, i32, f32]),
+    "ysod_scale_weights": (i32, [vp, i32, i32, i32, vp, i32, vp, vp]),
     "ysod_conv_tc_run": (i32, [vp, vp]),
     "ysod_conv_tc_info": (i32, [vp, C.POINTER(i32)]),
     "ysod_conv_tc_destroy": (None, [vp]),
