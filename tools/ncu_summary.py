@@ -47,7 +47,12 @@ def main():
         hdr = rows[hi]
         si = hdr.index("Source")
         ci = next(i for i, c in enumerate(hdr) if c.startswith("# Samples") or c == "Warp Stall Sampling (All Samples)")
-        body = [r for r in rows[hi + 1:] if len(r) > ci]
+        def num(v):
+            try:
+                return float(v or 0)
+            except ValueError:      # a second kernel's header row inside a multi-kernel report
+                return None
+        body = [r for r in rows[hi + 1:] if len(r) > ci and num(r[ci]) is not None]
         tot = sum(float(r[ci] or 0) for r in body)
         top = sorted(body, key=lambda r: -float(r[ci] or 0))[:n]
         print(f"-- top {n} SASS lines by stall samples (total {tot:.0f}); column '{hdr[ci]}'")

@@ -34,6 +34,16 @@ __global__ void gap_partial_kernel(const T* __restrict__ x, int HW, int C, int x
     if (pl < PL) {
         const T* xb = x + (size_t)n * HW * xcs + cg * 8;
         int p = p0 + pl;
+        for (; p + 7 * PL < p1; p += 8 * PL) {   // eight independent 16 B loads in flight per thread (a pure read stream needs the depth)
+            float v[8][8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) ysod_vec8<T>::load(xb + (size_t)(p + u * PL) * xcs, v[u]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                su[e] += ((v[0][e] + v[1][e]) + (v[2][e] + v[3][e])) + ((v[4][e] + v[5][e]) + (v[6][e] + v[7][e]));
+                mx[e] = fmaxf(mx[e], fmaxf(fmaxf(fmaxf(v[0][e], v[1][e]), fmaxf(v[2][e], v[3][e])), fmaxf(fmaxf(v[4][e], v[5][e]), fmaxf(v[6][e], v[7][e]))));
+            }
+        }
         for (; p + 3 * PL < p1; p += 4 * PL) {   // four independent 16 B loads in flight per thread
             float v0[8], v1[8], v2[8], v3[8];
             ysod_vec8<T>::load(xb + (size_t)p * xcs, v0);

@@ -43,7 +43,7 @@ __device__ __forceinline__ int koff(int k) {
 
 // SRC = 0: img is (N,3,H,W) fp32 in [0,1];  SRC = 1: img is (N,H,W,3) uint8 BGR in 0..255 (-> RGB, /255)
 template <int COUT, int SRC, bool VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, COUT <= 32 ? 4 : 2)
 stem_mma_kernel(const void* __restrict__ img_, const __nv_bfloat16* __restrict__ wk, const float* __restrict__ bias,
                 __nv_bfloat16* __restrict__ out, int H, int W, int Ho, int Wo, int ocs, int act) {
     ysod_pdl_sync();

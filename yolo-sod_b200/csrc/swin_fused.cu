@@ -193,12 +193,25 @@ swin64_fused_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, in
         const int h0 = wi * WS, w0 = wj * WS;
 
         // ---- A. input patch (9 x 9 pixels x 64 ch, zero outside the image)
-        for (int i = gt; i < PATCH * 8; i += 128) {
-            const int p = i >> 3, pc = i & 7;
-            const int ih = h0 - 1 + p / 9, iw = w0 - 1 + p % 9;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = *reinterpret_cast<const uint4*>(x + (((size_t)n * H + ih) * W + iw) * xcs + pc * 8);
-            *reinterpret_cast<uint4*>(&sg.patch[p * LDW + pc * 8]) = v;
+        {
+            // all of a thread's loads are issued before the first store, so the ~6 global round trips overlap instead of serialising
+            constexpr int NIT = (PATCH * 8 + 127) / 128;
+            uint4 pv[NIT];
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int i = gt + it * 128;
+                const int p = i >> 3, pc = i & 7;
+                const int pr = p / 9;
+                const int ih = h0 - 1 + pr, iw = w0 - 1 + (p - pr * 9);
+                pv[it] = make_uint4(0, 0, 0, 0);
+                if (i < PATCH * 8 && ih >= 0 && ih < H && iw >= 0 && iw < W)
+                    pv[it] = *reinterpret_cast<const uint4*>(x + (((size_t)n * H + ih) * W + iw) * xcs + pc * 8);
+            }
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int i = gt + it * 128;
+                if (i < PATCH * 8) *reinterpret_cast<uint4*>(&sg.patch[(i >> 3) * LDW + (i & 7) * 8]) = pv[it];
+            }
         }
         group_barrier(grp);
 
