@@ -130,7 +130,7 @@ class Program:
         return w * s.view(-1, 1, 1, 1), b - mu * s
 
     def conv(self, x: View, w: torch.Tensor, bias: torch.Tensor, k, s, g, act, out: View, res: View = None,
-             out_f32=False, pad=None, up2=False, gate=None):
+             out_f32=False, pad=None, up2=False, gate=None, alg_flops=None):
         """w: (Cout, Cin/g, k, k) fp32 with BN folded; bias fp32 (Cout). up2: `out` is the 2x nearest-upsampled destination
         (tensor-core path only; the caller checks `tc_eligible`). gate: (N, Cin) fp32 device tensor of an SE block folded into this conv
         (per-image weights W * gate[n], rebuilt every forward by ysod_scale_weights; tensor-core path only)."""
@@ -179,7 +179,7 @@ class Program:
             self.tc_handles.append(h)
             self.ops.append((_lib.load().ysod_conv_tc_run, (h,), "ysod_conv_tc_run"))
             self.sched.append(("op", len(self.ops) - 1, self._lane))
-            fl = 2.0 * x.N * Ho * Wo * Cout * k * k * Cin
+            fl = 2.0 * x.N * Ho * Wo * Cout * k * k * Cin if alg_flops is None else float(alg_flops)   # algorithmic (structural zeros excluded)
             self.op_flops.append(fl)
             info = (C.c_int * 8)()
             _lib.call("ysod_conv_tc_info", h, info)
@@ -479,7 +479,8 @@ class Program:
                     wt[:64, :c2n] = sd[f"{P}.cv2.{i}.2.weight"].float()
                     wt[64:, c2n:] = sd[f"{P}.cv3.{i}.2.weight"].float()
                     bt = torch.cat([sd[f"{P}.cv2.{i}.2.bias"].float(), sd[f"{P}.cv3.{i}.2.bias"].float()])
-                    self.conv(ac, wt, bt, 1, 1, 1, "none", raw.slice(0, no), out_f32=True)
+                    self.conv(ac, wt, bt, 1, 1, 1, "none", raw.slice(0, no), out_f32=True,
+                              alg_flops=2.0 * x.N * x.H * x.W * (64 * c2n + nc * c3n))
                     a = c = None
                     if self.m.fuse_decode:
                         # ... and the level's DFL / dist2bbox / sigmoid decode runs in that conv's epilogue (no re-read of the raw map)
