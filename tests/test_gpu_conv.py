@@ -128,6 +128,8 @@ HALO_CASES = [
     (6, 160, 160, 64, 64, 3, 1, dict(res=True)),                    # resident taps, ~9 tiles per CTA
     (4, 160, 160, 32, 32, 3, 1, dict(res=True)),                    # Cin = 32: 64 B pixel rows / SWIZZLE_64B halo copy
     (1, 24, 40, 32, 64, 3, 1, {}),                                  # Cin = 32, ragged tiles
+    (2, 40, 24, 64, 128, 3, 1, dict(res=True)),                     # 64 -> 128: resident taps (144 KB) + split staging (one store unit per pass)
+    (4, 160, 160, 64, 128, 3, 1, dict(ocs_extra=64)),               # ... the fused Detect cv2/cv3 first conv at P2, ~9 tiles per CTA
 ]
 
 

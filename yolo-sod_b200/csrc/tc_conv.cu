@@ -49,6 +49,7 @@ struct TcParams {
     uint32_t a_bytes, b_bytes, a_tx;
     // epilogue staging: output rows of `row_bytes` (<= 128 B, one swizzle span) per store unit of `unit_cols` columns
     int unit_cols, n_units, swz_mask, cout_pad, stage_bufs;
+    int stage_split;   // 1: the staging buffer holds ONE store unit; the epilogue makes n_units passes (frees smem for resident weight taps)
     uint32_t row_bytes;
     // fused Detect decode (ysod_conv_tc_set_decode): the layer is the level's final 1x1 head conv with output channels
     // [0,64) = DFL box logits (4 sides x 16 bins), [64,64+nc) = class logits; besides the raw map the epilogue writes
@@ -555,7 +556,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const __nv_bfloat16* const res = p.res;
         const bool leader_warp = (warp & 7) == 0;
         const bool tre = tr && leader_warp && lane == 0 && grp == 0;
-        const uint32_t sb = stage_out + (uint32_t)grp * ((uint32_t)n_units * unit_bytes);
+        const bool split = p.stage_split != 0;
+        const int passes = split ? n_units : 1;
+        const uint32_t sb = stage_out + (uint32_t)grp * ((uint32_t)(split ? 1 : n_units) * unit_bytes);
         const uint32_t trow0 = tmem_acc + ((uint32_t)(q * 32) << 16);
         int asel = 0;   // accumulator of tile i is i % 4 = 2 * asel + grp for this group's tiles
         const uint32_t row0 = sb + (uint32_t)m * p.row_bytes;
@@ -602,7 +605,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int d_oh = oh0 + th, d_ow = ow0 + tw;
             const bool d_ok = dec && (m < TH * TW) && d_oh < p.Ho && d_ow < p.Wo;
             float* const d_y = dec ? p.dec_y + (size_t)img * (4 + p.dec_nc) * p.dec_A + p.dec_off + d_oh * p.Wo + d_ow : nullptr;
-            for (int ch = cg; ch < nchunks; ch += 2) {
+            const int chunks_per_pass = split ? chunks_per_unit : nchunks;
+            for (int ps = 0; ps < passes; ++ps) {
+            if (ps > 0) {   // split staging: the previous unit's store must have read the buffer before it is overwritten
+                if (leader_warp) bulk_wait_read<0>();
+                epi_barrier(grp);
+            }
+            for (int ch = ps * chunks_per_pass + cg; ch < (ps + 1) * chunks_per_pass; ch += 2) {
                 const int c0 = ch * 16;
                 uint32_t v[16];
                 tmem_ld16(trow + (uint32_t)c0, v);
@@ -658,7 +667,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // swizzled store into unit u = ch / chunks_per_unit: 16-byte piece index ^= (address bits [7..]) & mask (== TMA swizzle).
                 // The staging units are 1 KB aligned and a thread always writes row m, so the XOR term is a per-thread constant.
                 const int u = ch / chunks_per_unit, cu = ch - u * chunks_per_unit;
-                const uint32_t row_addr = row0 + (uint32_t)u * unit_bytes;
+                const uint32_t row_addr = row0 + (split ? 0u : (uint32_t)u * unit_bytes);
                 if (out_f32) {
                     const uint32_t p0 = (uint32_t)(cu * 4);
 #pragma unroll
@@ -673,6 +682,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                      pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
                 }
             }
+            if (ps == passes - 1) {
             if (d_ok) {
                 // cg = 0 holds (left, right) -> cx, w ; cg = 1 holds (top, bottom) -> cy, h   (anchor = cell centre, tal.py:341-344)
                 const float anc = (float)(cg == 0 ? d_ow : d_oh) + 0.5f;
@@ -685,11 +695,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) mbar_arrive(my_tempty);
             trace(tre, 2, 3, tcount, 0, tcnt);       // accumulator handed back
+            }
             fence_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
             epi_barrier(grp);
             if (leader_warp && elect_one()) {
                 if (!(p.debug & 8)) {
-                    if (p.up2) {
+                    if (split) {
+                        tma_store_4d(&tmO, sb, n0 + ps * unit_cols, ow0, oh0, img);
+                    } else if (p.up2) {
                         // the output map walks the 2x-upsampled destination with element strides {1,2,2,1}: four stores of the
                         // same staged tile, one per (dy, dx) phase of the 2 x 2 replication
                         for (int u = 0; u < n_units; ++u)
@@ -702,6 +715,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 bulk_commit();
             }
+            }   // passes
             trace(tre, 2, 4, tcount, 0, tcnt);       // stores issued
             asel ^= 1;
             if (asel == 0) acc_phase ^= 1u;
@@ -862,8 +876,23 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
         p.cout_pad = Cout_pad;
     }
     // epilogue staging holds the whole BN-wide output tile (n_units sub-buffers of 128 rows); double-buffered up to 32 KB
-    const uint32_t tile_stage_bytes = (uint32_t)p.n_units * 128u * p.row_bytes;
+    uint32_t tile_stage_bytes = (uint32_t)p.n_units * 128u * p.row_bytes;
     p.stage_bufs = 2;   // one per epilogue group
+    p.stage_split = 0;
+    if (halo && p.n_units > 1 && !up2) {
+        // 3x3 halo plan whose weight taps only fit resident if the staging buffer shrinks to one store unit (64 -> 128 at P2:
+        // 144 KB of taps): streamed taps are bound by the latency x depth of the small tap ring (measured 45 % tensor-pipe
+        // activity), so trade a second barrier per tile for resident weights. Exact shared-memory accounting, not the 224 KB rule.
+        const uint32_t a_halo = ((18u * 10u * 2u * (uint32_t)p.BK) + 1023u) & ~1023u;
+        const uint32_t b_all = 9u * (uint32_t)p.cchunks * p.b_bytes;
+        const uint32_t nbar_res = 2u * 2u + 2u * 9u * (uint32_t)p.cchunks;
+        const uint32_t full_need = b_all + 2u * a_halo + 2u * tile_stage_bytes + 4u * (uint32_t)Cout_pad + 3u * 1024u;
+        const uint32_t split_need = b_all + 2u * a_halo + 1024u + (8u * nbar_res + 128u) + 4u * (uint32_t)Cout_pad + 1024u + 2u * 128u * p.row_bytes;
+        if (full_need > 224u * 1024u && split_need <= 227u * 1024u) {
+            p.stage_split = 1;
+            tile_stage_bytes = 128u * p.row_bytes;
+        }
+    }
     const uint32_t staging = (uint32_t)p.stage_bufs * tile_stage_bytes;
     const uint32_t fixed = staging + 4u * (uint32_t)Cout_pad + 3u * 1024u;   // staging + bias + slack
     size_t ring_bytes = 0;
@@ -900,8 +929,8 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
     } else {
         p.a_tx = 18u * 10u * 2u * (uint32_t)p.BK;     // one halo copy: 18 rows x 10 px x BK ch bf16 (22.5 KB / 11.25 KB)
         p.a_bytes = (p.a_tx + 1023u) & ~1023u;        // slot stride (1 KB aligned)
-        const uint32_t avail = 224u * 1024u - fixed;
         const uint32_t b_all = 9u * (uint32_t)p.cchunks * p.b_bytes;
+        const uint32_t avail = p.stage_split ? b_all + 2u * p.a_bytes : 224u * 1024u - fixed;   // split plan: sized exactly above
         int a_total;
         if (b_all + 2u * p.a_bytes <= avail) {   // all weight taps stay resident in shared memory for the CTA lifetime
             p.b_resident = 1;
