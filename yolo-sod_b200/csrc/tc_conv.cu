@@ -701,7 +701,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (leader_warp && elect_one()) {
                 if (!(p.debug & 8)) {
                     if (split) {
-                        tma_store_4d(&tmO, sb, n0 + ps * unit_cols, ow0, oh0, img);
+                        if (p.up2) {
+#pragma unroll
+                            for (int d = 0; d < 4; ++d) tma_store_4d(&tmO, sb, n0 + ps * unit_cols, 2 * ow0 + (d & 1), 2 * oh0 + (d >> 1), img);
+                        } else {
+                            tma_store_4d(&tmO, sb, n0 + ps * unit_cols, ow0, oh0, img);
+                        }
                     } else if (p.up2) {
                         // the output map walks the 2x-upsampled destination with element strides {1,2,2,1}: four stores of the
                         // same staged tile, one per (dy, dx) phase of the 2 x 2 replication
@@ -823,7 +828,8 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
     const int dbg = mode >> 8;
     const bool up2 = (mode & 0x40) != 0;
     const bool img_w = (mode & 0x80) != 0;
-    mode &= 0x3f;
+    const int split_exp = mode & 0x10;
+    mode &= 0x2f;
     if (img_w) {
         YSOD_CHECK_ARG(mode != 2, "ysod_conv_tc_create_ex: per-image weights need the generic kernel (resident taps are shared by all images)");
         mode = 1;
@@ -879,7 +885,7 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
     uint32_t tile_stage_bytes = (uint32_t)p.n_units * 128u * p.row_bytes;
     p.stage_bufs = 2;   // one per epilogue group
     p.stage_split = 0;
-    if (halo && p.n_units > 1 && !up2) {
+    if (halo && p.n_units > 1) {
         // 3x3 halo plan whose weight taps only fit resident if the staging buffer shrinks to one store unit (64 -> 128 at P2:
         // 144 KB of taps): streamed taps are bound by the latency x depth of the small tap ring (measured 45 % tensor-pipe
         // activity), so trade a second barrier per tile for resident weights. Exact shared-memory accounting, not the 224 KB rule.
@@ -892,6 +898,14 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
             p.stage_split = 1;
             tile_stage_bytes = 128u * p.row_bytes;
         }
+    }
+    if (!halo && p.n_units > 1 && p.num_k >= 4 && !(split_exp)) {
+        // deep-K generic layers (20^2 / 40^2 maps, 1x1 with K >= 256) are bound by the latency x depth of the operand ring (L2 -> SM,
+        // measured ~66 GB/s per SM with 4 slots in flight): a one-unit staging buffer frees 32 KB = a fifth {A,B} slot, +6..10 % on
+        // every such layer (256->256 3x3 @20^2: 34.8 -> 32.8 us, 256->512 3x3/s2: 59.4 -> 53.2, 512->256 1x1 @40^2: 38.9 -> 34.8).
+        // mode bit 0x10 disables it (A/B measurements).
+        p.stage_split = 1;
+        tile_stage_bytes = 128u * p.row_bytes;
     }
     const uint32_t staging = (uint32_t)p.stage_bufs * tile_stage_bytes;
     const uint32_t fixed = staging + 4u * (uint32_t)Cout_pad + 3u * 1024u;   // staging + bias + slack
@@ -917,6 +931,7 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
         int G = 1;
         for (int g = 1; g <= gmax; ++g)
             if (p.num_k % g == 0) G = g;
+        if (p.stage_split && slots % (rings * G) != 0) G = 1;   // use the slot the split staging freed: 5 single-block stages, not 2 x 2
         int stages = slots / (rings * G);
         if (stages > 8) stages = 8;
         if (stages < 1) stages = 1;
