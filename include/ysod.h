@@ -115,6 +115,14 @@ int ysod_sppf_pool(const void* y0, int dtype, int N, int H, int W, int C, int xc
                    void* stream);
 int ysod_upsample_copy(const void* x, int dtype, int N, int H, int W, int C, int xcs, int scale, void* out, int ocs, void* stream);
 
+/* ---- MambaBlock with its GLU fallback (blocks_mamba.py:84-103, 167-236; what the reference runs when mamba_ssm is missing):
+ *      F.avg_pool2d(y, r, r) ; sigmoid(g) * a of `pw1(x).chunk(2, 1)` ; x + F.interpolate(y, size=(H, W), mode="nearest").
+ *      The 1x1 / depthwise convs of the block go through ysod_conv_tc_* / ysod_dwconv. ------------------------------------- */
+int ysod_avgpool2d(const void* x, int dtype, int N, int H, int W, int C, int xcs, int r, void* out, int ocs, void* stream);
+int ysod_glu(const void* x, int dtype, long long npix, int hid, int xcs, void* out, int ocs, void* stream);
+int ysod_upsample_add(const void* y, int dtype, int N, int Hh, int Wh, int C, int ycs, const void* res, int rcs, int H, int W, void* out,
+                      int ocs, void* stream);
+
 /* ---- Swin window attention plumbing: blocks_transformer.py:8-79,98-131 ; A2_Attn pooling/upsample: a2_attn.py:44-60 - */
 int ysod_layernorm(const void* x, int dtype, long long rows, int C, int ldx, const float* gamma, const float* beta, float eps,
                    void* out, int ldo, void* stream);

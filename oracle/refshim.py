@@ -70,6 +70,7 @@ def load():
 CFG = {
     "sod": "ultralytics/cfg/models/new/yolov12-sod-fusion-v5-simple.yaml",
     "stable": "ultralytics/cfg/models/new/yolov12-sod-fusion-v5-stable.yaml",
+    "v5": "ultralytics/cfg/models/new/yolov12-sod-fusion-v5.yaml",
     "yolov12n": "ultralytics/cfg/models/v12/yolov12n.yaml",
     "yolov12s": "ultralytics/cfg/models/v12/yolov12s.yaml",
     "yolov12m": "ultralytics/cfg/models/v12/yolov12m.yaml",

@@ -16,7 +16,7 @@ import yolo_sod_b200  # noqa: E402,F401
 from yolo_sod_b200 import cfg as ycfg, synth  # noqa: E402
 from oracle import model_ref  # noqa: E402
 
-CONFIGS = ["yolov12-sod-fusion-v5-simple", "yolov12-sod-fusion-v5-stable", "yolov12n", "yolov12s", "yolov12m", "E1", "E2", "E3", "E4", "E5", "E6"]
+CONFIGS = ["yolov12-sod-fusion-v5-simple", "yolov12-sod-fusion-v5-stable", "yolov12-sod-fusion-v5", "yolov12n", "yolov12s", "yolov12m", "E1", "E2", "E3", "E4", "E5", "E6"]
 
 
 def calibrate(name, seed=0, target_frac=0.04):

@@ -102,6 +102,13 @@ def test_stable_variant_bf16():
     _check("yolov12-sod-fusion-v5-stable", torch.bfloat16, 1, 320, 2e-2, layer_tol=4e-2, seed=19)
 
 
+def test_full_v5_with_mamba_glu_fallback():
+    """cfg/models/new/yolov12-sod-fusion-v5.yaml: the -simple graph + MambaBlock, which the reference runs through its GLU fallback when
+    mamba_ssm is not installed (blocks_mamba.py:116-165) -- fp32 parity mode and the bf16 tensor-core path."""
+    _check("yolov12-sod-fusion-v5", torch.float32, 1, 128, 1e-4, layer_tol=2e-4, seed=21)
+    _check("yolov12-sod-fusion-v5", torch.bfloat16, 1, 320, 2e-2, layer_tol=4e-2, seed=21)
+
+
 def test_yolov12n_fp32_and_bf16():
     _check("yolov12n", torch.float32, 2, 128, 1e-4, layer_tol=2e-4)
     _check("yolov12n", torch.bfloat16, 1, 640, 2e-2, layer_tol=4e-2)  # attention-heavy: diagnostic layer bound 4 %

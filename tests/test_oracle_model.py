@@ -49,7 +49,7 @@ def test_oracle_matches_golden(case):
 
 @pytest.mark.skipif(not refshim.available(), reason="live reference not present")
 @pytest.mark.parametrize("name,ref_name", [("yolov12-sod-fusion-v5-simple", "sod"), ("yolov12n", "yolov12n"), ("yolov12m", "yolov12m"),
-                                           ("E1", "E1"), ("E4", "E4"), ("E6", "E6"), ("yolov12-sod-fusion-v5-stable", "stable")])
+                                           ("E1", "E1"), ("E4", "E4"), ("E6", "E6"), ("yolov12-sod-fusion-v5-stable", "stable"), ("yolov12-sod-fusion-v5", "v5")])
 def test_oracle_matches_live_reference(name, ref_name):
     spec = ycfg.get_spec(name)
     sd = synth.synth_state_dict(spec, name, 0)
@@ -72,7 +72,7 @@ def test_oracle_matches_live_reference(name, ref_name):
 @pytest.mark.skipif(not refshim.available(), reason="live reference not present")
 def test_builtin_graph_equals_reference_yaml():
     for name, rel in [("yolov12-sod-fusion-v5-simple", refshim.CFG["sod"]), ("yolov12n", refshim.CFG["yolov12n"]),
-                      ("yolov12m", refshim.CFG["yolov12m"]), ("yolov12-sod-fusion-v5-stable", refshim.CFG["stable"])] \
+                      ("yolov12m", refshim.CFG["yolov12m"]), ("yolov12-sod-fusion-v5-stable", refshim.CFG["stable"]), ("yolov12-sod-fusion-v5", refshim.CFG["v5"])] \
             + [(f"E{i}", refshim.CFG[f"E{i}"]) for i in range(1, 7)]:
         a = ycfg.get_spec(name)
         b = ycfg.get_spec(os.path.join(refshim.REFERENCE_ROOT, rel))

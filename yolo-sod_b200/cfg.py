@@ -2,7 +2,7 @@
 
 Mirrors the *behaviour* of the reference's `parse_model` (ultralytics/nn/tasks.py:967-1169) for exactly the module set the
 named configs instantiate: Conv, C2f, C3k2, A2C2f, SPPF, SE_Block, CBAM_Block, CA_Block, SwinBlock,
-A2_Attn, nn.Upsample, Concat, Detect. Anything else raises -- there is no silent fallback.
+A2_Attn, MambaBlock (GLU fallback), nn.Upsample, Concat, Detect / DetectStable. Anything else raises -- there is no silent fallback.
 
 A user can pass their own reference YAML (path or dict); the two architectures the benchmark names are also built in
 (as plain Python data, so nothing from the reference tree is needed at run time):
@@ -11,6 +11,7 @@ A user can pass their own reference YAML (path or dict); the two architectures t
     "yolov12{n,s,m}"                    ultralytics/cfg/models/v12/yolov12.yaml + scale
     "E1" .. "E6"                        ultralytics/cfg/models/new/E1..E6.yaml (the ablation ladder, derived from the full model)
     "yolov12-sod-fusion-v5-stable"      ultralytics/cfg/models/new/yolov12-sod-fusion-v5-stable.yaml (DetectStable head, 14.21 M params)
+    "yolov12-sod-fusion-v5"             ultralytics/cfg/models/new/yolov12-sod-fusion-v5.yaml (-simple + MambaBlock with its GLU fallback, 14.04 M)
 """
 import math
 import re
@@ -119,7 +120,28 @@ _SOD_STABLE = {
     "head": [[[24, 27, 30, 33], 1, "DetectStable", ["nc"]]],
 }
 
+def _insert_layer(base: dict, at: int, row: list) -> dict:
+    """`base` with one extra row inserted before layer index `at` (absolute `from` references at or after it shift by one)."""
+    rows = base["backbone"] + base.get("neck", []) + base["head"]
+    nb = len(base["backbone"])
+
+    def sh(f):
+        return f + 1 if (f != -1 and f >= at) else f
+
+    out = []
+    for i, (f, n, m, args) in enumerate(rows):
+        if i == at:
+            out.append(list(row))
+        out.append([[sh(j) for j in f] if isinstance(f, list) else sh(f), n, m, list(args)])
+    nb2 = nb + (1 if at <= nb else 0)
+    return dict(base, backbone=out[:nb2], neck=out[nb2:-1], head=out[-1:])
+
+
+# ultralytics/cfg/models/new/yolov12-sod-fusion-v5.yaml = the -simple graph plus a MambaBlock(256, 2) after the P3 C2f (layer 7)
+_SOD_V5 = _insert_layer(_SOD_SIMPLE, 7, [-1, 1, "MambaBlock", [256, 2]])
+
 BUILTIN = {
+    "yolov12-sod-fusion-v5": _SOD_V5,
     "yolov12-sod-fusion-v5-simple": _SOD_SIMPLE, "yolov12": _YOLOV12, "yolov12-sod-fusion-v5-stable": _SOD_STABLE,
     # the paper's ablation ladder (README.md:131-137; cfg/models/new/E1..E6.yaml): E1 plain PANet with P3-P5 heads, E2 + P2 head,
     # E3 + SE, E4 + CBAM, E5 + Swin, E6 + A2 (the complete model adds CoordAtt)
@@ -200,7 +222,7 @@ class ModelSpec:
 
 _CONV_LIKE = {"Conv", "C2f", "C3k2", "A2C2f", "SPPF"}
 _REPEAT_ARG = {"C2f", "C3k2", "A2C2f"}
-_SE_FAMILY = {"SE_Block", "SE", "SwinBlock", "CA_Block", "A2_Attn", "CBAM_Block"}
+_SE_FAMILY = {"SE_Block", "SE", "SwinBlock", "CA_Block", "A2_Attn", "CBAM_Block", "MambaBlock"}
 
 
 def parse_model(d: dict, ch: int = None, nc: int = None) -> ModelSpec:
@@ -275,6 +297,10 @@ def parse_model(d: dict, ch: int = None, nc: int = None) -> ModelSpec:
                 p = dict(reduction=args[1] if len(args) > 1 else 32)   # CA_Block(c1, c2=args[0], reduction=32)
             elif m == "A2_Attn":
                 p = dict(num_areas=args[0] if len(args) > 0 else 4, num_heads=args[1] if len(args) > 1 else 4)
+            elif m == "MambaBlock":
+                # MambaBlock(c, c_hidden=args[0], seq_reduction=args[1]) (tasks.py:1126-1127, blocks_mamba.py:107); compiled with the GLU
+                # fallback the reference itself uses whenever mamba_ssm is not importable (blocks_mamba.py:116-165)
+                p = dict(c_hidden=args[0] if len(args) > 0 else 256, reduction=args[1] if len(args) > 1 else 2)
         elif m == "nn.Upsample":
             c1 = c2 = chs[f]
             p = dict(scale=args[1], mode=args[2])
@@ -427,6 +453,20 @@ def param_shapes(spec: ModelSpec) -> "Dict[str, tuple]":
             for s in ("weight", "bias", "running_mean", "running_var"):
                 sh[f"{P}.bn.{s}"] = (c,)
             sh[f"{P}.bn.num_batches_tracked"] = ()
+        elif t == "MambaBlock":
+            c, ch = L.c1, p["c_hidden"]
+            hid = 2 * ch                                   # GLUBlock(c_hidden, expansion=2)
+            for pre, ci, co in ((f"{P}.in_proj", c, ch), (f"{P}.out_proj", ch, c)):      # Conv1x1BN = Sequential(conv, bn, act)
+                sh[f"{pre}.0.weight"] = (co, ci, 1, 1)
+                for s_ in ("weight", "bias", "running_mean", "running_var"):
+                    sh[f"{pre}.1.{s_}"] = (co,)
+                sh[f"{pre}.1.num_batches_tracked"] = ()
+            sh[f"{P}.fallback.pw1.weight"] = (2 * hid, ch, 1, 1)
+            sh[f"{P}.fallback.dw.weight"] = (hid, 1, 3, 3)
+            for s_ in ("weight", "bias", "running_mean", "running_var"):
+                sh[f"{P}.fallback.bn.{s_}"] = (hid,)
+            sh[f"{P}.fallback.bn.num_batches_tracked"] = ()
+            sh[f"{P}.fallback.pw2.weight"] = (ch, hid, 1, 1)
         elif t == "A2_Attn":
             c = L.c1
             _conv(sh, f"{P}.proj", c, c, 1)

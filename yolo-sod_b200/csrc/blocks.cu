@@ -684,6 +684,71 @@ sppf_plane_bf16_kernel(const __nv_bfloat16* __restrict__ y0, int H, int W, int x
     }
 }
 
+// ---- MambaBlock (GLU fallback) plumbing: blocks_mamba.py:84-103, 167-236 -------------------------------------------------------
+// F.avg_pool2d(y, r, r): out (N, H/r, W/r, C), fp32 accumulation, divide by r*r. Thread = 8 channels of one output pixel.
+template <typename T>
+__global__ void avgpool_kernel(const T* __restrict__ x, int H, int W, int C, int xcs, int r, T* __restrict__ out, int ocs, long long total) {
+    ysod_pdl_sync();
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c8n = C >> 3, Ho = H / r, Wo = W / r;
+    const int cg = (int)(idx % c8n);
+    const long long pix = idx / c8n;
+    const int ow = (int)(pix % Wo), oh = (int)((pix / Wo) % Ho), n = (int)(pix / ((long long)Wo * Ho));
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int dh = 0; dh < r; ++dh)
+        for (int dw = 0; dw < r; ++dw) {
+            float v[8];
+            ysod_vec8<T>::load(x + (((size_t)n * H + oh * r + dh) * W + ow * r + dw) * xcs + cg * 8, v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] += v[e];
+        }
+    const float inv = 1.0f / (float)(r * r);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] *= inv;
+    ysod_vec8<T>::store(out + (size_t)pix * ocs + cg * 8, acc);
+}
+
+// GLU gate: out[p][c] = sigmoid(x[p][hid + c]) * x[p][c], c < hid  (`a, g = pw1(x).chunk(2, 1); sigmoid(g) * a`)
+template <typename T>
+__global__ void glu_kernel(const T* __restrict__ x, int hid, int xcs, T* __restrict__ out, int ocs, long long total) {
+    ysod_pdl_sync();
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c8n = hid >> 3;
+    const int cg = (int)(idx % c8n);
+    const long long pix = idx / c8n;
+    float a[8], g[8];
+    ysod_vec8<T>::load(x + (size_t)pix * xcs + cg * 8, a);
+    ysod_vec8<T>::load(x + (size_t)pix * xcs + hid + cg * 8, g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] *= ysod_sigmoid(g[e]);
+    ysod_vec8<T>::store(out + (size_t)pix * ocs + cg * 8, a);
+}
+
+// out = res + F.interpolate(y, size=(H, W), mode="nearest"): source index = min(floor(dst * in / out), in - 1) as ATen computes it
+template <typename T>
+__global__ void upsample_add_kernel(const T* __restrict__ y, int Hh, int Wh, int C, int ycs, const T* __restrict__ res, int rcs, int H, int W,
+                                    T* __restrict__ out, int ocs, long long total) {
+    ysod_pdl_sync();
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c8n = C >> 3;
+    const int cg = (int)(idx % c8n);
+    const long long pix = idx / c8n;
+    const int w = (int)(pix % W), h = (int)((pix / W) % H), n = (int)(pix / ((long long)W * H));
+    const int sh = min((int)floorf((float)h * ((float)Hh / (float)H)), Hh - 1);
+    const int sw = min((int)floorf((float)w * ((float)Wh / (float)W)), Wh - 1);
+    float a[8], b[8];
+    ysod_vec8<T>::load(y + (((size_t)n * Hh + sh) * Wh + sw) * ycs + cg * 8, a);
+    ysod_vec8<T>::load(res + (size_t)pix * rcs + cg * 8, b);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a[e] += b[e];
+    ysod_vec8<T>::store(out + (size_t)pix * ocs + cg * 8, a);
+}
+
 // nearest-neighbour upsample by `scale` (1 = plain slice copy) into a channel slice. Grid-stride, four loads in flight.
 template <typename T>
 __global__ void upsample_copy_kernel(const T* __restrict__ x, int H, int W, int C, int xcs, int scale, T* __restrict__ out,
@@ -1111,6 +1176,33 @@ int ysod_upsample_copy(const void* x, int dtype, int N, int H, int W, int C, int
     YSOD_CHECK_ARG(x && out && C % 8 == 0 && xcs % 8 == 0 && ocs % 8 == 0 && scale >= 1, "ysod_upsample_copy: bad args");
     const long long total = (long long)N * H * scale * W * scale * (C / 8);
     YSOD_DISPATCH(dtype, (ysod_launch(upsample_copy_kernel<T>, stream_blocks(total, stream_threads(C), 4), stream_threads(C), 0, st, (const T*)x, H, W, C, xcs, scale, (T*)out, ocs, (unsigned)(total / (C / 8)))));
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+int ysod_avgpool2d(const void* x, int dtype, int N, int H, int W, int C, int xcs, int r, void* out, int ocs, cudaStream_t st) {
+    YSOD_CHECK_ARG(x && out && C % 8 == 0 && xcs % 8 == 0 && ocs % 8 == 0 && r >= 1 && H >= r && W >= r, "ysod_avgpool2d: bad args");
+    const long long total = (long long)N * (H / r) * (W / r) * (C / 8);
+    YSOD_DISPATCH(dtype, (ysod_launch(avgpool_kernel<T>, blocks_for(total, 256), 256, 0, st, (const T*)x, H, W, C, xcs, r, (T*)out, ocs, total)));
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+int ysod_glu(const void* x, int dtype, long long npix, int hid, int xcs, void* out, int ocs, cudaStream_t st) {
+    YSOD_CHECK_ARG(x && out && hid % 8 == 0 && xcs % 8 == 0 && ocs % 8 == 0 && xcs >= 2 * hid && npix > 0, "ysod_glu: bad args");
+    const long long total = npix * (hid / 8);
+    YSOD_DISPATCH(dtype, (ysod_launch(glu_kernel<T>, blocks_for(total, 256), 256, 0, st, (const T*)x, hid, xcs, (T*)out, ocs, total)));
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+int ysod_upsample_add(const void* y, int dtype, int N, int Hh, int Wh, int C, int ycs, const void* res, int rcs, int H, int W, void* out,
+                      int ocs, cudaStream_t st) {
+    YSOD_CHECK_ARG(y && res && out && C % 8 == 0 && ycs % 8 == 0 && rcs % 8 == 0 && ocs % 8 == 0 && Hh > 0 && Wh > 0 && H >= Hh && W >= Wh,
+                   "ysod_upsample_add: bad args");
+    const long long total = (long long)N * H * W * (C / 8);
+    YSOD_DISPATCH(dtype, (ysod_launch(upsample_add_kernel<T>, blocks_for(total, 256), 256, 0, st, (const T*)y, Hh, Wh, C, ycs, (const T*)res, rcs, H, W,
+                                      (T*)out, ocs, total)));
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }

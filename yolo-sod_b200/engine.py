@@ -326,6 +326,41 @@ class Program:
         s = g / torch.sqrt(sd[f"{P}.bn.running_var"].float() + BN_EPS)
         self.conv(r, pw * s.view(-1, 1, 1, 1), b - sd[f"{P}.bn.running_mean"].float() * s, 1, 1, 1, "silu", out, res=x)
 
+    def fold_bn(self, w, bn):
+        """conv weight (Cout, ...) with the BatchNorm2d at state_dict prefix `bn` folded in: (w', bias)."""
+        sd = self.m.sd
+        s = sd[f"{bn}.weight"].float() / torch.sqrt(sd[f"{bn}.running_var"].float() + BN_EPS)
+        return w.float() * s.view(-1, *([1] * (w.dim() - 1))), sd[f"{bn}.bias"].float() - sd[f"{bn}.running_mean"].float() * s
+
+    def mamba(self, x, P, p, out):
+        """blocks_mamba.py:105-111,167-236 with the GLU fallback (:84-103): in_proj -> avg_pool(r) -> pw1 -> sigmoid(g)*a -> dw3x3+BN+SiLU
+        -> pw2 -> [nearest upsample -> out_proj -> + x]. out_proj (1x1 + BN + SiLU) is pointwise, so it runs on the pooled map and the
+        upsample is fused with the residual add: identical values, a quarter of the work."""
+        sd = self.m.sd
+        ch, r = p["c_hidden"], p["reduction"]
+        hid = sd[f"{P}.fallback.dw.weight"].shape[0]
+        w, b = self.fold_bn(sd[f"{P}.in_proj.0.weight"], f"{P}.in_proj.1")
+        y = self.new(x.N, x.H, x.W, ch)
+        self.conv(x, w, b, 1, 1, 1, "silu", y)
+        if r > 1:
+            yp = self.new(x.N, x.H // r, x.W // r, ch)
+            self.emit("ysod_avgpool2d", y.ptr(), self.code, y.N, y.H, y.W, ch, y.cs, r, yp.ptr(), yp.cs, desc=f"avgpool{r}")
+            y = yp
+        t = self.new(y.N, y.H, y.W, 2 * hid)
+        self.conv(y, sd[f"{P}.fallback.pw1.weight"].float(), torch.zeros(2 * hid), 1, 1, 1, "none", t)
+        gl = self.new(y.N, y.H, y.W, hid)
+        self.emit("ysod_glu", t.ptr(), self.code, y.N * y.H * y.W, hid, t.cs, gl.ptr(), gl.cs, desc="GLU gate")
+        w, b = self.fold_bn(sd[f"{P}.fallback.dw.weight"], f"{P}.fallback.bn")
+        d = self.new(y.N, y.H, y.W, hid)
+        self.conv(gl, w, b, 3, 1, hid, "silu", d)
+        q = self.new(y.N, y.H, y.W, ch)
+        self.conv(d, sd[f"{P}.fallback.pw2.weight"].float(), torch.zeros(ch), 1, 1, 1, "none", q)
+        w, b = self.fold_bn(sd[f"{P}.out_proj.0.weight"], f"{P}.out_proj.1")
+        o2 = self.new(y.N, y.H, y.W, x.C)
+        self.conv(q, w, b, 1, 1, 1, "silu", o2)
+        self.emit("ysod_upsample_add", o2.ptr(), self.code, x.N, o2.H, o2.W, x.C, o2.cs, x.ptr(), x.cs, x.H, x.W, out.ptr(), out.cs,
+                  desc="nearest upsample + residual")
+
     def a2attn(self, x, P, p, out):
         """a2_attn.py:35-69."""
         sd = self.m.sd
@@ -665,6 +700,8 @@ class Program:
                 self.swin(x, P, p, o)
             elif t == "A2_Attn":
                 self.a2attn(x, P, p, o)
+            elif t == "MambaBlock":
+                self.mamba(x, P, p, o)
             elif t == "nn.Upsample":
                 self.emit("ysod_upsample_copy", x.ptr(), self.code, x.N, x.H, x.W, x.C, x.cs, p["scale"], o.ptr(), o.cs)
             else:

@@ -48,6 +48,9 @@ PROTOTYPES = {
     "ysod_ca_apply": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp]),
     "ysod_sppf_pool": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp]),
     "ysod_upsample_copy": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
+    "ysod_avgpool2d": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]),
+    "ysod_glu": (i32, [vp, i32, i64, i32, i32, vp, i32, vp]),
+    "ysod_upsample_add": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, i32, i32, i32, vp, i32, vp]),
     "ysod_layernorm": (i32, [vp, i32, i64, i32, i32, vp, vp, f32, vp, i32, vp]),
     "ysod_window_partition_ln": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, vp, f32, vp, vp, i32, vp]),
     "ysod_window_reverse": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp]),

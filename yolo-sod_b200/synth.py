@@ -48,7 +48,7 @@ def synth_state_dict(spec: "_cfg.ModelSpec", cfg_name: str, seed: int = 0, calib
             t = torch.zeros((), dtype=torch.long)
         elif leaf == "active_mask":                       # DetectStable: every level active (detect_stable.py:13)
             t = torch.ones(shape, dtype=torch.bool)
-        elif ".bn." in name or ".bn1." in name:
+        elif ".bn." in name or ".bn1." in name or ".in_proj.1." in name or ".out_proj.1." in name:   # BatchNorm2d (incl. Conv1x1BN's [1])
             pfx = name.rsplit(".", 1)[0]
             m, v = calib.get(pfx, [0.0, 0.4])
             if leaf == "weight":
