@@ -216,20 +216,33 @@ swin64_fused_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, in
         group_barrier(grp);
 
         // ---- B. depthwise 3x3 -> tokens (bf16). Tokens beyond the image are the zero padding of window_partition.
-        for (int tk = dwr; tk < T; tk += 4) {
-            const int i = tk / WS, j = tk - i * WS;
-            float a0 = 0.f, a1 = 0.f;
-            if (h0 + i < H && w0 + j < W) {
+        //      A warp owns whole window columns (j = warp, warp + 4), a lane one channel pair: walking down the 9 patch rows of a
+        //      column, every loaded pixel feeds the three output rows it belongs to (27 shared loads per column instead of 63);
+        //      each output still accumulates its taps in (r, s) order, so the rounding is unchanged.
+        for (int j = dwr; j < WS; j += 4) {
+            float2 acc[WS];
 #pragma unroll
-                for (int r = 0; r < 3; ++r)
+            for (int i = 0; i < WS; ++i) acc[i] = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int s = 0; s < 3; ++s) {
-                        const float2 xv = unpack2(ld32(&sg.patch[((i + r) * 9 + j + s) * LDW + dwc]));
-                        a0 = fmaf(xv.x, wdw[r * 3 + s].x, a0);
-                        a1 = fmaf(xv.y, wdw[r * 3 + s].y, a1);
+            for (int ri = 0; ri < WS + 2; ++ri) {
+                const __nv_bfloat16* pr = &sg.patch[(ri * 9 + j) * LDW + dwc];
+                const float2 x0 = unpack2(ld32(pr)), x1 = unpack2(ld32(pr + LDW)), x2 = unpack2(ld32(pr + 2 * LDW));
+#pragma unroll
+                for (int r = 2; r >= 0; --r) {        // output row i = ri - r; for a fixed i the rows arrive in r = 0, 1, 2 order
+                    const int i = ri - r;
+                    if (i >= 0 && i < WS) {
+                        acc[i].x = fmaf(x0.x, wdw[r * 3].x, acc[i].x);     acc[i].y = fmaf(x0.y, wdw[r * 3].y, acc[i].y);
+                        acc[i].x = fmaf(x1.x, wdw[r * 3 + 1].x, acc[i].x); acc[i].y = fmaf(x1.y, wdw[r * 3 + 1].y, acc[i].y);
+                        acc[i].x = fmaf(x2.x, wdw[r * 3 + 2].x, acc[i].x); acc[i].y = fmaf(x2.y, wdw[r * 3 + 2].y, acc[i].y);
                     }
+                }
             }
-            *reinterpret_cast<uint32_t*>(&sg.tok[tk * LDW + dwc]) = pack2(a0, a1);
+            const bool col_in = w0 + j < W;
+#pragma unroll
+            for (int i = 0; i < WS; ++i) {
+                const bool in = col_in && (h0 + i < H);
+                *reinterpret_cast<uint32_t*>(&sg.tok[(i * WS + j) * LDW + dwc]) = in ? pack2(acc[i].x, acc[i].y) : 0u;
+            }
         }
         group_barrier(grp);
 

@@ -425,7 +425,7 @@ class Program:
         self.conv_bn(cat, f"{P}.cv2", out=out)
 
     def _splits(self, N, HW):
-        return max(1, min(HW // 256 if HW >= 256 else 1, -(-592 // N)))   # ~4 CTAs per SM, >= 256 pixels per split
+        return max(1, min(HW // 256 if HW >= 256 else 1, -(-1184 // N)))   # ~8 CTAs (2048 threads) per SM, >= 256 pixels per split
 
     def se(self, x, P, out):
         sd = self.m.sd
