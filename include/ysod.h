@@ -97,6 +97,10 @@ int ysod_scale_boxes(float* det, int B, int rows_per_img, int row_stride, const 
 
 /* ---- SE: smallobj_modules.py:57-92 ; CBAM: cbam_block.py:8-55 ; CoordAtt: ca_block.py:16-59 ------------------------- */
 int ysod_gap_partial(const void* x, int dtype, int N, int HW, int C, int xcs, int S, float* psum, float* pmax, void* stream);
+/* pool + gate in one launch (the last CTA of an image runs the gate MLP): kind 0 = SE (smallobj_modules.py:84-91), kind 1 = CBAM
+ * channel attention (cbam_block.py:14-23). counter: N zero-initialised uint32, left at zero by every call. */
+int ysod_gap_gate(const void* x, int dtype, int N, int HW, int C, int xcs, int S, float* psum, float* pmax, void* counter, int kind,
+                  const float* w1, const float* b1, const float* w2, const float* b2, int hid, float* gate, void* stream);
 int ysod_se_gate(const float* psum, int N, int S, int HW, int C, const float* w1, const float* b1, const float* w2,
                  const float* b2, int hid, float* gate, void* stream);
 int ysod_cbam_gate(const float* psum, const float* pmax, int N, int S, int HW, int C, const float* w1, const float* w2, int hid,

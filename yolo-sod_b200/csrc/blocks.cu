@@ -18,10 +18,8 @@ namespace {
 // ------------------------------------------------------------------------------------------------------------
 // global average / max pool, stage 1: partial[n][s][c] over a pixel range
 template <typename T>
-__global__ void gap_partial_kernel(const T* __restrict__ x, int HW, int C, int xcs, int S, float* __restrict__ psum,
-                                   float* __restrict__ pmax) {
-    ysod_pdl_sync();
-    extern __shared__ float sm[];  // [PL][C] sums, then [PL][C] maxes
+__device__ __forceinline__ void gap_partial_body(const T* __restrict__ x, int HW, int C, int xcs, int S, float* __restrict__ psum,
+                                                 float* __restrict__ pmax, float* sm) {
     const int n = blockIdx.y, s = blockIdx.x;
     const int c8n = C >> 3;
     const int PL = blockDim.x / c8n;
@@ -76,19 +74,24 @@ __global__ void gap_partial_kernel(const T* __restrict__ x, int HW, int C, int x
         if (pmax) pmax[((size_t)n * S + s) * C + c] = m;
     }
 }
-
-// SE gate: mean -> fc1(+bias) -> ReLU -> fc2(+bias) -> sigmoid. One CTA per image. fp32 as in the reference (:81-91).
-__global__ void se_gate_kernel(const float* __restrict__ psum, int S, int HW, int C, const float* __restrict__ w1,
-                               const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2, int hid,
-                               float* __restrict__ gate) {
+template <typename T>
+__global__ void gap_partial_kernel(const T* __restrict__ x, int HW, int C, int xcs, int S, float* __restrict__ psum,
+                                   float* __restrict__ pmax) {
     ysod_pdl_sync();
-    extern __shared__ float sm[];  // mean[C], h[hid]
+    extern __shared__ float sm[];  // [PL][C] sums, then [PL][C] maxes
+    gap_partial_body<T>(x, HW, C, xcs, S, psum, pmax, sm);
+}
+
+// SE gate: mean -> fc1(+bias) -> ReLU -> fc2(+bias) -> sigmoid for image n, by one CTA. fp32 as in the reference (:81-91).
+// sm: C + hid floats. `ld` reads the partials through L2 (they may have been written by other SMs of the same launch).
+__device__ __forceinline__ void se_gate_body(int n, const float* psum, int S, int HW, int C, const float* __restrict__ w1,
+                                             const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                                             int hid, float* __restrict__ gate, float* sm) {
     float* mean = sm;
     float* h = sm + C;
-    const int n = blockIdx.x;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float a = 0.f;
-        for (int s = 0; s < S; ++s) a += psum[((size_t)n * S + s) * C + c];
+        for (int s = 0; s < S; ++s) a += __ldcg(psum + ((size_t)n * S + s) * C + c);
         mean[c] = a / (float)HW;
     }
     __syncthreads();
@@ -106,22 +109,28 @@ __global__ void se_gate_kernel(const float* __restrict__ psum, int S, int HW, in
         gate[(size_t)n * C + c] = ysod_sigmoid(a);
     }
 }
-
-// CBAM channel gate: sigmoid(fc(avg) + fc(max)), fc = conv1x1(no bias) -> ReLU -> conv1x1(no bias) (cbam_block.py:14-23)
-__global__ void cbam_gate_kernel(const float* __restrict__ psum, const float* __restrict__ pmax, int S, int HW, int C,
-                                 const float* __restrict__ w1, const float* __restrict__ w2, int hid, float* __restrict__ gate) {
+__global__ void se_gate_kernel(const float* __restrict__ psum, int S, int HW, int C, const float* __restrict__ w1,
+                               const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2, int hid,
+                               float* __restrict__ gate) {
     ysod_pdl_sync();
-    extern __shared__ float sm[];  // avg[C], mx[C], ha[hid], hm[hid]
+    extern __shared__ float sm[];  // mean[C], h[hid]
+    se_gate_body(blockIdx.x, psum, S, HW, C, w1, b1, w2, b2, hid, gate, sm);
+}
+
+// CBAM channel gate: sigmoid(fc(avg) + fc(max)), fc = conv1x1(no bias) -> ReLU -> conv1x1(no bias) (cbam_block.py:14-23), image n,
+// one CTA. sm: 2C + 2 hid floats.
+__device__ __forceinline__ void cbam_gate_body(int n, const float* psum, const float* pmax, int S, int HW, int C,
+                                               const float* __restrict__ w1, const float* __restrict__ w2, int hid,
+                                               float* __restrict__ gate, float* sm) {
     float* avg = sm;
     float* mx = sm + C;
     float* ha = sm + 2 * C;
     float* hm = ha + hid;
-    const int n = blockIdx.x;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         float a = 0.f, m = -INFINITY;
         for (int s = 0; s < S; ++s) {
-            a += psum[((size_t)n * S + s) * C + c];
-            m = fmaxf(m, pmax[((size_t)n * S + s) * C + c]);
+            a += __ldcg(psum + ((size_t)n * S + s) * C + c);
+            m = fmaxf(m, __ldcg(pmax + ((size_t)n * S + s) * C + c));
         }
         avg[c] = a / (float)HW;
         mx[c] = m;
@@ -149,6 +158,43 @@ __global__ void cbam_gate_kernel(const float* __restrict__ psum, const float* __
         }
         gate[(size_t)n * C + c] = ysod_sigmoid(a + m);
     }
+}
+__global__ void cbam_gate_kernel(const float* __restrict__ psum, const float* __restrict__ pmax, int S, int HW, int C,
+                                 const float* __restrict__ w1, const float* __restrict__ w2, int hid, float* __restrict__ gate) {
+    ysod_pdl_sync();
+    extern __shared__ float sm[];  // avg[C], mx[C], ha[hid], hm[hid]
+    cbam_gate_body(blockIdx.x, psum, pmax, S, HW, C, w1, w2, hid, gate, sm);
+}
+
+// Pool + gate in one launch: every CTA writes its partial sums / maxes, takes a ticket on a per-image counter, and the CTA that
+// draws the last ticket of its image runs the gate MLP (kind 0 = SE, 1 = CBAM channel attention) and re-arms the counter. Saves the
+// separate one-CTA-per-image gate launch (a ~5-8 us dependent launch on a path that is launch-bound at batch 1).
+struct GateArgs {
+    unsigned* counter;     // [N], zero before the first launch; left at zero by every launch
+    int kind, hid;
+    const float *w1, *b1, *w2, *b2;
+    float* gate;
+};
+template <typename T>
+__global__ void gap_gate_kernel(const T* __restrict__ x, int HW, int C, int xcs, int S, float* __restrict__ psum, float* __restrict__ pmax,
+                                GateArgs g) {
+    ysod_pdl_sync();
+    extern __shared__ float sm[];
+    __shared__ int is_last;
+    gap_partial_body<T>(x, HW, C, xcs, S, psum, pmax, sm);
+    __threadfence();                  // this thread's partials are visible device-wide before the ticket is taken
+    __syncthreads();
+    const int n = blockIdx.y;
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(g.counter + n, 1u);
+        is_last = (t == (unsigned)S - 1u);
+        if (is_last) g.counter[n] = 0u;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (g.kind == 0) se_gate_body(n, psum, S, HW, C, g.w1, g.b1, g.w2, g.b2, g.hid, g.gate, sm);
+    else cbam_gate_body(n, psum, pmax, S, HW, C, g.w1, g.w2, g.hid, g.gate, sm);
 }
 
 // Streaming-kernel indexing: a thread keeps one fixed 8-channel group (cg) and walks pixels pix0, pix0 + pstep, ... with 32-bit
@@ -1029,6 +1075,27 @@ int ysod_gap_partial(const void* x, int dtype, int N, int HW, int C, int xcs, in
     YSOD_CHECK_ARG(smem <= 48 * 1024, "ysod_gap_partial: smem");
     dim3 grid(S, N);
     YSOD_DISPATCH(dtype, (ysod_launch(gap_partial_kernel<T>, grid, 256, smem, st, (const T*)x, HW, C, xcs, S, psum, pmax)));
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+// ysod_gap_partial + ysod_se_gate (kind 0) / ysod_cbam_gate (kind 1) in one launch. counter: N zero-initialised uint32, owned by the
+// caller, left at zero by every call. SE: w1 [hid][C], b1 [hid], w2 [C][hid], b2 [C]; CBAM: w1, w2 only (bias-free), pmax required.
+int ysod_gap_gate(const void* x, int dtype, int N, int HW, int C, int xcs, int S, float* psum, float* pmax, void* counter, int kind,
+                  const float* w1, const float* b1, const float* w2, const float* b2, int hid, float* gate, cudaStream_t st) {
+    YSOD_CHECK_ARG(x && psum && counter && w1 && w2 && gate && C % 8 == 0 && xcs % 8 == 0 && S >= 1 && hid >= 1, "ysod_gap_gate: bad args");
+    YSOD_CHECK_ARG(kind == 0 ? (b1 && b2) : (kind == 1 && pmax), "ysod_gap_gate: kind %d needs %s", kind, kind == 0 ? "biases" : "pmax");
+    const int c8n = C / 8;
+    YSOD_CHECK_ARG(c8n <= 256, "ysod_gap_gate: C too large");
+    const int PL = 256 / c8n;
+    size_t smem = (size_t)2 * PL * C * sizeof(float);
+    const size_t gate_smem = (size_t)(2 * C + 2 * hid) * sizeof(float);
+    if (smem < gate_smem) smem = gate_smem;
+    YSOD_CHECK_ARG(smem <= 48 * 1024, "ysod_gap_gate: smem");
+    GateArgs g;
+    g.counter = (unsigned*)counter; g.kind = kind; g.hid = hid; g.w1 = w1; g.b1 = b1; g.w2 = w2; g.b2 = b2; g.gate = gate;
+    dim3 grid(S, N);
+    YSOD_DISPATCH(dtype, (ysod_launch(gap_gate_kernel<T>, grid, 256, smem, st, (const T*)x, HW, C, xcs, S, psum, pmax, g)));
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }

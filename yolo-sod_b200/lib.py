@@ -38,6 +38,7 @@ PROTOTYPES = {
     "ysod_letterbox_u8": (i32, [vp, i32, i32, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
     "ysod_scale_boxes": (i32, [vp, i32, i32, i32, vp, i32, vp]),
     "ysod_gap_partial": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "ysod_gap_gate": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp, i32, vp, vp]),
     "ysod_se_gate": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp, vp]),
     "ysod_cbam_gate": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, i32, vp, vp]),
     "ysod_scale_channels": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, i32, vp]),
