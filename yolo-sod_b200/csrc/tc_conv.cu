@@ -897,6 +897,11 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
         if (full_need > 224u * 1024u && split_need <= 227u * 1024u) {
             p.stage_split = 1;
             tile_stage_bytes = 128u * p.row_bytes;
+        } else if (full_need > 224u * 1024u && !split_exp) {
+            // taps cannot be resident (Cin >= 128 at BN = 128): they stream through their own ring, whose depth x L2 latency bounds
+            // the layer. Split staging frees 32 KB = a third filter column of taps in flight (9 slots instead of 6).
+            p.stage_split = 2;   // 2 = split for the streamed-tap ring
+            tile_stage_bytes = 128u * p.row_bytes;
         }
     }
     if (!halo && p.n_units > 1 && p.num_k >= 4 && !(split_exp)) {
@@ -945,7 +950,11 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
         p.a_tx = 18u * 10u * 2u * (uint32_t)p.BK;     // one halo copy: 18 rows x 10 px x BK ch bf16 (22.5 KB / 11.25 KB)
         p.a_bytes = (p.a_tx + 1023u) & ~1023u;        // slot stride (1 KB aligned)
         const uint32_t b_all = 9u * (uint32_t)p.cchunks * p.b_bytes;
-        const uint32_t avail = p.stage_split ? b_all + 2u * p.a_bytes : 224u * 1024u - fixed;   // split plan: sized exactly above
+        // resident split plan: sized exactly above; streamed split plan: exact accounting against the 227 KB limit (<= 13 barrier
+        // pairs, bias, two 1 KB alignment pads, staging) instead of the conservative 224 KB rule -- the ninth tap slot needs it
+        const uint32_t avail = p.stage_split == 1 ? b_all + 2u * p.a_bytes
+                             : p.stage_split == 2 ? 227u * 1024u - (2048u + 8u * 26u + 128u + 4u * (uint32_t)Cout_pad + staging)
+                                                  : 224u * 1024u - fixed;
         int a_total;
         if (b_all + 2u * p.a_bytes <= avail) {   // all weight taps stay resident in shared memory for the CTA lifetime
             p.b_resident = 1;
@@ -960,10 +969,10 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
         } else {
             p.b_resident = 0;
             p.issuers = 1;            // many bursts per tile: one issuer, one deep ring
-            p.b_stages = 6;           // two filter columns of three taps in flight
-            p.b_slots = 6;
-            YSOD_CHECK_ARG(6u * p.b_bytes + 2u * p.a_bytes <= avail, "ysod_conv_tc_create: halo plan does not fit in shared memory (BN %d)", BN);
-            a_total = (int)((avail - 6u * p.b_bytes) / p.a_bytes);
+            p.b_stages = (9u * p.b_bytes + 2u * p.a_bytes <= avail) ? 9 : 6;   // three (else two) filter columns of three taps in flight
+            p.b_slots = p.b_stages;
+            YSOD_CHECK_ARG((uint32_t)p.b_stages * p.b_bytes + 2u * p.a_bytes <= avail, "ysod_conv_tc_create: halo plan does not fit in shared memory (BN %d)", BN);
+            a_total = (int)((avail - (uint32_t)p.b_stages * p.b_bytes) / p.a_bytes);
             if (a_total > 4) a_total = 4;
             p.a_stages = a_total;
             p.sgroup = 1;
