@@ -53,6 +53,9 @@ int ysod_conv_tc_create(ysod_conv_tc** handle, const void* x, int N, int H, int 
 #define YSOD_CONV_UP2 0x40
 /* | 0x80 (YSOD_CONV_IMG_WEIGHTS): `wgt` is [N][Cout_pad][K], one weight matrix per image (see ysod_scale_weights). */
 #define YSOD_CONV_IMG_WEIGHTS 0x80
+/* | 0x10 (YSOD_CONV_NO_SPLIT_STAGING): A/B switch for measurements -- keeps the full-tile epilogue staging buffer instead of the
+ * one-unit buffer that frees shared memory for a deeper operand ring on deep-K layers (tc_conv.cu). Results are identical. */
+#define YSOD_CONV_NO_SPLIT_STAGING 0x10
 int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, int W, int Cin, int xcs, const void* wgt,
                            const float* bias, int Cout, int Cout_pad, int ksize, int stride, void* out, int out_dtype, int ocs,
                            const void* res, int rcs, int act, int mode);
