@@ -98,6 +98,21 @@ __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ uint32_t ld32s(const __nv_bfloat16* p) { return *reinterpret_cast<const uint32_t*>(p); }
+// ldmatrix: lane i supplies the 16 B row (i & 7) of 8x8 bf16 matrix (i >> 3); per matrix a lane receives the element pair
+// (row lane/4, columns 2*(lane%4), +1) -- or, with .trans, (rows 2*(lane%4), +1, column lane/4): the m16n8k16 B fragment of a
+// [n][k] (plain) or [k][n] (.trans) operand.
+__device__ __forceinline__ void ldsm_x4(uint32_t* r, const __nv_bfloat16* row) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(row);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t* r, const __nv_bfloat16* row) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(row);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t* r, const __nv_bfloat16* row) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(row);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
 __device__ __forceinline__ uint32_t pack2bf(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -109,10 +124,10 @@ mha_win_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restr
                int ldq, int ldk, int ldv, long long bsq, long long bsk, long long bsv, float scale, __nv_bfloat16* __restrict__ out,
                int ldo, long long bso) {
     ysod_pdl_sync();
-    constexpr int LDQ = D + 8, LDV = 64 + 8;
+    constexpr int LDQ = D + 8;      // row stride 2D + 16 bytes: 16 B aligned, conflict-free for 8-row ldmatrix phases (D = 16, 32, 64)
     __shared__ __align__(16) __nv_bfloat16 Qs[64 * LDQ];
     __shared__ __align__(16) __nv_bfloat16 Ks[64 * LDQ];
-    __shared__ __align__(16) __nv_bfloat16 Vt[D * LDV];
+    __shared__ __align__(16) __nv_bfloat16 Vs[64 * LDQ];   // V stays row-major [key][d]; PV reads it through ldmatrix.trans
     const int h = blockIdx.x, b = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const __nv_bfloat16* qb = q + (size_t)b * bsq + h * D;
@@ -128,9 +143,7 @@ mha_win_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restr
         }
         *reinterpret_cast<uint4*>(&Qs[r * LDQ + pc * 8]) = qv;
         *reinterpret_cast<uint4*>(&Ks[r * LDQ + pc * 8]) = kv;
-        const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vv);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) Vt[(pc * 8 + e) * LDV + r] = ve[e];
+        *reinterpret_cast<uint4*>(&Vs[r * LDQ + pc * 8]) = vv;
     }
     __syncthreads();
     const int row0 = warp * 16 + g;
@@ -146,9 +159,19 @@ mha_win_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restr
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
         s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
-        const __nv_bfloat16* kr = &Ks[(nb * 8 + g) * LDQ + 2 * t];
+        // K rows nb*8 .. nb*8+7 as [n = key][k = d]: one ldmatrix.x4 = the (b0, b1) pairs of two K steps
 #pragma unroll
-        for (int ks = 0; ks < D / 16; ++ks) mma16816(s[nb], qf[ks], ld32s(kr + ks * 16), ld32s(kr + ks * 16 + 8));
+        for (int k2 = 0; k2 < D / 32; ++k2) {
+            uint32_t kb[4];
+            ldsm_x4(kb, &Ks[(nb * 8 + (lane & 7)) * LDQ + k2 * 32 + (lane >> 3) * 8]);
+            mma16816(s[nb], qf[2 * k2], kb[0], kb[1]);
+            mma16816(s[nb], qf[2 * k2 + 1], kb[2], kb[3]);
+        }
+        if (D % 32) {   // D = 16: a single K step
+            uint32_t kb[2];
+            ldsm_x2(kb, &Ks[(nb * 8 + (lane & 7)) * LDQ + (D / 32) * 32 + ((lane >> 3) & 1) * 8]);
+            mma16816(s[nb], qf[D / 16 - 1], kb[0], kb[1]);
+        }
     }
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
@@ -186,9 +209,14 @@ mha_win_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restr
 #pragma unroll
     for (int nb = 0; nb < D / 8; ++nb) {
         float o[4] = {0.f, 0.f, 0.f, 0.f};
-        const __nv_bfloat16* vr = &Vt[(nb * 8 + g) * LDV + 2 * t];
+        // V as [k = key][n = d]: ldmatrix.x4.trans over keys 32*i2 .. 32*i2+31 (lane = key row), d columns nb*8 .. +7
 #pragma unroll
-        for (int i = 0; i < 4; ++i) mma16816(o, pf[i], ld32s(vr + i * 16), ld32s(vr + i * 16 + 8));
+        for (int i2 = 0; i2 < 2; ++i2) {
+            uint32_t vb[4];
+            ldsm_x4_trans(vb, &Vs[(i2 * 32 + lane) * LDQ + nb * 8]);
+            mma16816(o, pf[2 * i2], vb[0], vb[1]);
+            mma16816(o, pf[2 * i2 + 1], vb[2], vb[3]);
+        }
         *reinterpret_cast<uint32_t*>(&Qs[row0 * LDQ + nb * 8 + 2 * t]) = pack2bf(o[0] * inv0, o[1] * inv0);
         *reinterpret_cast<uint32_t*>(&Qs[(row0 + 8) * LDQ + nb * 8 + 2 * t]) = pack2bf(o[2] * inv1, o[3] * inv1);
     }
