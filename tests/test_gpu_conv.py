@@ -81,6 +81,7 @@ CASES = [
     (1, 16, 16, 64, 64, 1, 1, dict(act="none", out_f32=True, ocs_extra=16)),  # box head into a slice of the raw map
     (2, 40, 40, 128, 74, 1, 1, dict(act="none", out_f32=True, ocs_extra=6, out_first=True)),  # fused box+cls head: N = 80 MMA, 3 store units
     (2, 24, 24, 256, 64, 1, 1, dict(act="none", out_f32=True)),     # deep K + two fp32 store units: split-pass staging, 5-slot ring
+    (2, 24, 24, 256, 74, 1, 1, dict(act="none", out_f32=True, ocs_extra=6, out_first=True)),   # ... with a partial third unit (N = 80)
     (3, 40, 40, 512, 256, 1, 1, dict(res=True)),                    # deep K, BN=128 x 2 N tiles, residual, split-pass staging
     (1, 1, 300, 64, 192, 1, 1, dict(act="none")),                   # linear: tokens x qkv (N=192)
     (1, 1, 1000, 128, 64, 1, 1, dict(act="gelu", res=True)),        # linear + GELU + residual

@@ -611,7 +611,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (leader_warp) bulk_wait_read<0>();
                 epi_barrier(grp);
             }
-            for (int ch = ps * chunks_per_pass + cg; ch < (ps + 1) * chunks_per_pass; ch += 2) {
+            for (int ch = ps * chunks_per_pass + cg; ch < (ps + 1) * chunks_per_pass && ch < nchunks; ch += 2) {   // last unit may be partial (BN = 80)
                 const int c0 = ch * 16;
                 uint32_t v[16];
                 tmem_ld16(trow + (uint32_t)c0, v);
