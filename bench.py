@@ -23,8 +23,28 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: NCCL's banner / debug output ("NCCL version ...", printed when NCCL_DEBUG is set) goes to stderr
+# stdout carries exactly one JSON line. Libraries write there too (NCCL prints its "NCCL version ..." banner on stdout), so file
+# descriptor 1 is pointed at stderr for the whole run and the result line is written to the saved original stdout by emit().
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+_RESULT_FD = None
+
+
+def _capture_stdout():
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_RESULT_FD, data)
 
 CFG = "yolov12-sod-fusion-v5-simple"
 IMGSZ = 640
@@ -136,7 +156,7 @@ def run_reference(args):
             "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": leg["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -150,6 +170,7 @@ def main():
     ap.add_argument("--profile-out", default=None, help="write the per-kernel event timing table to this JSON file")
     ap.add_argument("--quick", action="store_true", help="main timed loop only (for ncu launch lists): no e2e / per-kernel / latency legs")
     args = ap.parse_args()
+    _capture_stdout()
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
@@ -157,7 +178,7 @@ def main():
     import torch
     import torch.distributed as dist
     import yolo_sod_b200  # noqa: F401
-    from yolo_sod_b200 import ops, synth
+    from yolo_sod_b200 import dist as ydist, ops, synth
     from yolo_sod_b200.model import DetectionModel
 
     rank = int(os.environ.get("RANK", "0"))
@@ -177,15 +198,13 @@ def main():
     # 4 rotating device-resident input batches (each 157 MB fp32; a step touches ~5 GB of activations >> 126 MB L2)
     n_in = 4
     xs = [synth.synth_images(B, IMGSZ, seed=100 * rank + i).to(dev) for i in range(n_in)]
-    gathered = torch.empty((world, B, MAX_DET, 6), dtype=torch.float32, device=dev) if world > 1 else None
-    gcount = torch.empty((world, B), dtype=torch.int32, device=dev) if world > 1 else None
+    gather = ydist.DetectionGather(world, B, MAX_DET, dev) if world > 1 else None   # preallocated (world*B, 300, 6) + (world*B,) buffers
 
     def step(i):
         y, _ = model(xs[i % n_in])
         det, count, _ = ops.nms_padded(y, CONF, IOU, max_det=MAX_DET)
         if world > 1:  # the only data-path exchange: fixed-size detections over NVLink
-            dist.all_gather_into_tensor(gathered, det)
-            dist.all_gather_into_tensor(gcount, count)
+            gather(det, count)
         return det, count
 
     def barrier():
@@ -205,17 +224,13 @@ def main():
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = ydist.max_over_ranks(ms, dev)
     ndet = int(count.sum().item())
     if args.quick:
         if rank == 0:
             clocks = sampler.stop() if sampler else None
-            print(json.dumps({"metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
-                              "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "quick": True,
-                              "clocks": clocks}))
+            emit({"metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": "images/s", "n_gpus": world,
+                  "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "quick": True, "clocks": clocks})
         if world > 1:
             dist.destroy_process_group()
         return
@@ -354,7 +369,7 @@ def main():
     }
     if cpu:
         line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
