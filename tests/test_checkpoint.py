@@ -40,6 +40,16 @@ def test_refuses_foreign_globals():
         checkpoint.torch_safe_load(path)
     os.remove(path)
 
+    class EvilTorch:                                   # a torch.* callable is not a tensor rebuild helper either
+        def __reduce__(self):
+            return (torch.set_num_threads, (1,))
+    buf = io.BytesIO()
+    torch.save({"model": EvilTorch()}, buf)
+    open(path, "wb").write(buf.getvalue())
+    with pytest.raises(pickle.UnpicklingError):
+        checkpoint.torch_safe_load(path)
+    os.remove(path)
+
 
 def test_state_dict_equals_live_reference_load():
     from oracle import refshim

@@ -10,7 +10,8 @@ receives the pickled `__dict__`; real `torch.nn` leaves (Conv2d, BatchNorm2d, Mu
 that tree we read exactly what the engine compiles from: the model YAML dict (`model.yaml`), the reference-named state_dict
 (parameters + persistent buffers, walked in module order) and `names` / `nc`. No reference code is executed.
 
-Globals outside {torch, collections, numpy array reconstruction, a few builtins, ultralytics.* stand-ins} are refused.
+Globals outside {tensor / storage rebuild helpers, torch.nn module classes, plain containers, numpy array reconstruction, a few
+builtins, ultralytics.* stand-ins} are refused -- in particular arbitrary torch.* callables.
 """
 import pickle
 from collections import OrderedDict
@@ -19,7 +20,36 @@ from typing import Dict, Tuple
 import torch
 
 _SAFE_BUILTINS = {"set", "frozenset", "slice", "range", "complex", "bytearray", "dict", "list", "tuple", "int", "float", "bool", "str"}
-_SAFE_MODULE_PREFIXES = ("torch.", "collections", "numpy.", "_codecs", "pathlib", "types", "copyreg", "argparse")
+# Plain data containers / array reconstruction only. torch is NOT blanket-allowed (torch.hub.*, torch.load ... are callables a
+# crafted pickle could REDUCE): tensor / storage / parameter rebuild helpers, dtype-like singletons and nn.Module classes only.
+_SAFE_GLOBALS = {
+    ("collections", "OrderedDict"), ("collections", "defaultdict"), ("pathlib", "PosixPath"), ("pathlib", "PurePosixPath"),
+    ("types", "SimpleNamespace"), ("argparse", "Namespace"), ("_codecs", "encode"), ("copyreg", "_reconstructor"),
+    ("numpy", "ndarray"), ("numpy", "dtype"), ("numpy.core.multiarray", "_reconstruct"), ("numpy.core.multiarray", "scalar"),
+    ("numpy._core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "scalar"),
+    ("torch", "Size"), ("torch", "device"), ("torch", "Tensor"), ("torch.nn.parameter", "Parameter"),
+    ("torch.serialization", "_get_layout"),
+}
+_TORCH_DTYPES = {"float32", "float16", "bfloat16", "float64", "int64", "int32", "int16", "int8", "uint8", "bool"}
+
+
+def _torch_global_ok(module: str, name: str) -> bool:
+    if (module, name) in _SAFE_GLOBALS:
+        return True
+    if module == "torch":
+        return name in _TORCH_DTYPES or name.endswith("Storage")                  # torch.FloatStorage, torch.float32 ...
+    if module in ("torch._utils", "torch._tensor"):
+        return name.startswith("_rebuild")                                       # _rebuild_tensor_v2, _rebuild_parameter ...
+    if module == "torch.storage":
+        return name.endswith("Storage") or name == "_load_from_bytes"
+    if module.startswith("torch.nn.modules."):
+        import importlib
+        import inspect
+        obj = getattr(importlib.import_module(module), name, None)
+        return inspect.isclass(obj) and issubclass(obj, torch.nn.Module)          # Conv2d, BatchNorm2d, MultiheadAttention ...
+    return False
+
+
 _stub_cache: Dict[Tuple[str, str], type] = {}
 
 
@@ -56,7 +86,7 @@ class _Unpickler(pickle.Unpickler):
             if name in _SAFE_BUILTINS:
                 return super().find_class("builtins", name)
             raise pickle.UnpicklingError(f"refusing builtins.{name} in a checkpoint")
-        if module == "torch" or module == "numpy" or module.startswith(_SAFE_MODULE_PREFIXES):
+        if (module, name) in _SAFE_GLOBALS or (module.startswith("torch") and _torch_global_ok(module, name)):
             return super().find_class(module, name)
         raise pickle.UnpicklingError(f"refusing global {module}.{name} in a checkpoint")
 
