@@ -11,7 +11,8 @@ cv2 = pytest.importorskip("cv2")
 
 RESIZE_CASES = [((1080, 1920), (640, 360)), ((1080, 1920), (384, 216)), ((480, 640), (640, 480)), ((333, 517), (640, 412)),
                 ((1280, 1280), (640, 640)), ((100, 100), (640, 640)), ((37, 53), (200, 100)), ((1279, 1281), (640, 640)),
-                ((9, 700), (350, 5)), ((2160, 3840), (640, 360))]
+                ((9, 700), (350, 5)), ((2160, 3840), (640, 360)),
+                ((1, 1), (5, 7)), ((2, 2), (9, 3)), ((3, 3), (640, 640)), ((17, 16), (8, 8)), ((16, 16), (8, 8)), ((4000, 3), (2, 300))]
 
 
 @pytest.mark.parametrize("case", RESIZE_CASES, ids=lambda c: f"{c[0][0]}x{c[0][1]}to{c[1][1]}x{c[1][0]}")
