@@ -161,7 +161,7 @@ PRED_CASES = [
     ("stress_small", lambda: stress_pred(2, A=4000, clustered=True), dict(conf_thres=0.25, iou_thres=0.7)),
 ]
 
-# validator-style (multi_label=True): oracle-only for now
+# validator-style (multi_label=True): same bit-exact bar, run by test_gpu_nms.py::test_pipeline_bit_exact
 PRED_CASES_MULTILABEL = [
     ("multilabel", lambda: make_pred(2, 10, 2000, 24, frac=0.4, clustered=True),
      dict(conf_thres=0.25, iou_thres=0.7, multi_label=True)),
