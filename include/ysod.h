@@ -56,6 +56,10 @@ int ysod_conv_tc_create(ysod_conv_tc** handle, const void* x, int N, int H, int 
 /* | 0x10 (YSOD_CONV_NO_SPLIT_STAGING): A/B switch for measurements -- keeps the full-tile epilogue staging buffer instead of the
  * one-unit buffer that frees shared memory for a deeper operand ring on deep-K layers (tc_conv.cu). Results are identical. */
 #define YSOD_CONV_NO_SPLIT_STAGING 0x10
+/* | 0x20 (YSOD_CONV_NO_STORE): the plan's own output tensor is not written; only meaningful together with
+ * ysod_conv_tc_set_decode -- the predict path consumes `y` alone (detect/predict.py:25-32 takes preds[0]), so the fp32 raw maps
+ * Detect.forward also returns (head.py:74) need not be materialised. `out` must still be a valid 16 B aligned device address. */
+#define YSOD_CONV_NO_STORE 0x20
 int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, int W, int Cin, int xcs, const void* wgt,
                            const float* bias, int Cout, int Cout_pad, int ksize, int stride, void* out, int out_dtype, int ocs,
                            const void* res, int rcs, int act, int mode);
@@ -84,8 +88,13 @@ int ysod_stem_conv(const float* img, int N, int H, int W, const float* w, const 
 /* tensor-core stem (3x3 / stride 2 / pad 1, Cout 16|32|64, bf16 out). src_fmt 0: img = (N,3,H,W) fp32 in [0,1] (tasks.py:129);
  * src_fmt 1: img = (N,H,W,3) uint8 BGR frames, with BasePredictor.preprocess (engine/predictor.py:116-134: BGR->RGB, HWC->CHW,
  * /255) fused into the load. wk = [Cout][32] bf16, column (r*3+s)*3+c, columns 27..31 zero. */
+#define YSOD_STEM_INDIRECT 0x10 /* src_fmt | 0x10: `img` is a device slot (void**) holding the image pointer, see ysod_set_ptr */
 int ysod_stem_mma(const void* img, int src_fmt, int N, int H, int W, const void* wk, const float* bias, int Cout, void* out, int ocs,
                   int act, void* stream);
+
+/* Binds the input of a captured forward without a staging copy (the reference's forward reads the caller's tensor in place,
+ * nn/tasks.py:129-163): stores `value` in the device pointer slot that ysod_stem_mma(..., src_fmt | YSOD_STEM_INDIRECT) reads. */
+int ysod_set_ptr(void* slot, const void* value, void* stream);
 
 /* ---- predictor glue ---------------------------------------------------------------------------
  * engine/predictor.py:145-164 pre_transform -> LetterBox(imgsz, auto, stride): resize (cv2.INTER_LINEAR, bit-exact 8-bit fixed

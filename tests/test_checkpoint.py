@@ -51,6 +51,34 @@ def test_refuses_foreign_globals():
     os.remove(path)
 
 
+def test_refuses_nested_unrestricted_load():
+    """torch.storage._load_from_bytes == torch.load(BytesIO(b), weights_only=False) with the default pickle: a checkpoint that
+    REDUCEs it over an embedded payload would run any callable inside the restricted unpickler. It must be refused."""
+    import torch.storage
+
+    class Inner:
+        def __reduce__(self):
+            return (os.getcwd, ())
+    inner = io.BytesIO()
+    torch.save(Inner(), inner)
+
+    class Outer:
+        def __reduce__(self):
+            return (torch.storage._load_from_bytes, (inner.getvalue(),))
+    buf = io.BytesIO()
+    torch.save({"model": Outer()}, buf)
+    path = os.path.join(os.environ.get("TMPDIR", "/tmp"), "ysod_nested.pt")
+    open(path, "wb").write(buf.getvalue())
+    try:
+        with pytest.raises(pickle.UnpicklingError):
+            checkpoint.torch_safe_load(path)
+    finally:
+        os.remove(path)
+    # prefix / suffix look-alikes are refused too (exact-name allowlist)
+    for mod, name in [("torch._utils", "_rebuild_anything"), ("torch", "EvilStorage"), ("torch.storage", "_load_from_bytes")]:
+        assert not checkpoint._torch_global_ok(mod, name)
+
+
 def test_state_dict_equals_live_reference_load():
     from oracle import refshim
     if not refshim.available():

@@ -33,8 +33,14 @@ def _worker(rank, world, port, n_images, out_dir):
         det[: b - a] = det_all[a:b]
         count[: b - a] = count_all[a:b]
         gather = ydist.DetectionGather(world, per, MAX_DET, "cpu")
+        calls = []
+        real = dist.all_gather_into_tensor
+        dist.all_gather_into_tensor = lambda *a, **k: (calls.append(1), real(*a, **k))[1]
         for _ in range(2):                                       # buffers are reused across steps
             gd, gc = gather(det, count)
+        dist.all_gather_into_tensor = real
+        assert len(calls) == 2, "one collective per step: the count travels inside the detection buffer"
+        assert gc.dtype == torch.int32
         ms = ydist.max_over_ranks(10.0 + rank, "cpu")
         torch.save({"det": gd.clone(), "count": gc.clone(), "ms": ms, "range": (a, b)}, os.path.join(out_dir, f"r{rank}.pt"))
     finally:

@@ -235,7 +235,8 @@ def test_stem_mma(cout, src, W):
     assert bool((err <= tol * ref.abs() + tol * ref.abs().max() + 1e-5).all()), err.max().item()
 
 
-@pytest.mark.parametrize("case", [(5, 49, 2, 32), (3, 49, 4, 64), (2, 64, 2, 64), (2, 33, 1, 32), (2, 160, 8, 64), (1, 400, 2, 32), (6, 49, 4, 16), (2, 100, 4, 16)],
+@pytest.mark.parametrize("case", [(5, 49, 2, 32), (3, 49, 4, 64), (2, 64, 2, 64), (2, 33, 1, 32), (2, 160, 8, 64), (1, 400, 2, 32), (6, 49, 4, 16), (2, 100, 4, 16),
+                                  (70000, 9, 1, 32), (66000, 70, 1, 32)],   # batch > 65535: chunked over the grid.y / grid.z limit
                          ids=lambda c: "x".join(str(v) for v in c))
 def test_mha_core(case):
     """softmax(q k^T / sqrt(d)) v on packed [L][3E] projections (as nn.MultiheadAttention's in_proj lays them out) vs torch

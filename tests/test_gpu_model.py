@@ -9,6 +9,7 @@ A pure elementwise rtol 2e-2 in the max norm is not what a bf16 execution of thi
 reference's OWN code run in bf16 (model.fuse().bfloat16() on CPU) deviates from its fp32 run by 3.1-5.1 % of max|ref|
 (SOD, 160^2 and 640^2) and 4.5-9.9 % (yolov12n 640^2) on single elements, rel-L2 1.0-2.2 % -- measured in the build
 container, numbers in DESIGN.md. This path measures 2.3-5.4 % on the same inputs."""
+import json
 import os
 
 import numpy as np
@@ -25,16 +26,38 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden", "model_golden.npz")
 SOD = "yolov12-sod-fusion-v5-simple"
 
 
-def _close(got, ref, tol):
-    """tol < 1e-2: fp32 criterion; else the bf16 criterion (see module docstring). Returns (ok, max err, max|ref|, rel-L2)."""
+VIOL_SHARE = 1e-2     # bf16: allowed share of elements outside rtol*|ref| + rtol*max|ref|
+MAX_ERR_CAP = 0.10    # bf16: hard cap on any single element, as a fraction of max|ref|
+PARITY_LOG = os.environ.get("YSOD_PARITY_LOG", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out",
+                                                            "parity_records.jsonl"))
+
+
+def _record(**kw):
+    """Appends one parity measurement (rel-L2, max err / max|ref|, share of elements outside the strict bound) per raw map and test
+    to a JSON-lines file, so the bf16 allowance can be tracked and tightened (copied to profiles/ per round)."""
+    try:
+        os.makedirs(os.path.dirname(PARITY_LOG), exist_ok=True)
+        with open(PARITY_LOG, "a") as f:
+            f.write(json.dumps(kw) + "\n")
+    except OSError:
+        pass
+
+
+def _stats(got, ref, tol):
     err = (got - ref).abs()
     mx = ref.abs().max()
-    rel_l2 = float(err.norm() / ref.norm().clamp_min(1e-12))
+    return {"rel_l2": float(err.norm() / ref.norm().clamp_min(1e-12)), "max_err": float(err.max()), "max_ref": float(mx),
+            "max_err_over_max_ref": float(err.max() / mx.clamp_min(1e-30)),
+            "viol_share": float((err > tol * ref.abs() + tol * mx).float().mean())}
+
+
+def _close(got, ref, tol):
+    """tol < 1e-2: fp32 criterion; else the bf16 criterion (see module docstring). Returns (ok, max err, max|ref|, rel-L2)."""
+    st = _stats(got, ref, tol)
     if tol < 1e-2:
-        return bool((err <= tol * ref.abs() + tol * mx).all()), float(err.max()), float(mx), rel_l2
-    strict_viol = float((err > tol * ref.abs() + tol * mx).float().mean())      # share outside rtol + rtol*max
-    ok = rel_l2 <= tol and strict_viol <= 1e-2 and float(err.max()) <= 0.10 * float(mx)
-    return ok, float(err.max()), float(mx), rel_l2
+        return st["viol_share"] == 0.0, st["max_err"], st["max_ref"], st["rel_l2"]
+    ok = st["rel_l2"] <= tol and st["viol_share"] <= VIOL_SHARE and st["max_err_over_max_ref"] <= MAX_ERR_CAP
+    return ok, st["max_err"], st["max_ref"], st["rel_l2"]
 
 
 def _build(name, dtype, **kw):
@@ -44,21 +67,30 @@ def _build(name, dtype, **kw):
     return spec, sd, DetectionModel(name, weights=sd, dtype=dtype, **kw)
 
 
-def _check(name, dtype, B, sz, tol, layer_tol=None, seed=11, **kw):
+def _check(name, dtype, B, sz, tol, layer_tol=None, seed=11, layers_too=True, tag=None, **kw):
+    """layers_too=False: the full-size configs compare the raw head maps and `y` only (keeping every layer of a 32-image 640^2
+    batch in fp32 on the host is ~7 GB); per-layer parity is covered by the small cases."""
     spec, sd, model = _build(name, dtype, **kw)
     x = synth.synth_images(B, sz, seed=seed)
     y, raw = model(x.cuda())
     torch.cuda.synchronize()
-    (y_ref, raw_ref), layers = model_ref.forward(spec, sd, x, ycfg.strides_of(spec), return_layers=True)
+    if layers_too:
+        (y_ref, raw_ref), layers = model_ref.forward(spec, sd, x, ycfg.strides_of(spec), return_layers=True)
+    else:
+        y_ref, raw_ref = model_ref.forward(spec, sd, x, ycfg.strides_of(spec))
+        layers = None
     report = []
-    for i in range(len(spec.layers) - 1):
+    for i in range(len(spec.layers) - 1 if layers_too else 0):
         got = model.layer_output(x, i).cpu()
         ok, e, m, l2 = _close(got, layers[i], layer_tol or tol)
         report.append((i, spec.layers[i].type, ok, round(e, 5), round(m, 3), round(l2, 4)))
     bad = [r for r in report if not r[2]]
+    caller = tag or os.environ.get("PYTEST_CURRENT_TEST", "").split("::")[-1].split(" ")[0]
     for l, (a, b) in enumerate(zip(raw, raw_ref)):
+        st = _stats(a.float().cpu(), b, tol)
+        _record(test=caller, model=name, dtype=str(dtype).replace("torch.", ""), batch=B, imgsz=sz, raw_map=l, tol=tol, **st)
         ok, e, m, l2 = _close(a.float().cpu(), b, tol)
-        assert ok, f"raw map {l}: max err {e} (ref max {m}) rel-L2 {l2}; first bad layers: {bad[:4]}"
+        assert ok, f"raw map {l}: max err {e} (ref max {m}) rel-L2 {l2} viol {st['viol_share']}; first bad layers: {bad[:4]}"
     assert not bad, f"layer mismatches: {bad[:6]}"
     # decoded boxes / scores: fp32 decode of our own raw maps must match the oracle decode of the same maps
     y_dec = model_ref.detect_decode([r.float().cpu() for r in raw], ycfg.strides_of(spec), spec.nc)
@@ -82,6 +114,24 @@ def test_sod_bf16_cuda_core_crosscheck():
 
 def test_sod_bf16_640_batch2():
     _check(SOD, torch.bfloat16, 2, 640, 2e-2, layer_tol=3e-2, seed=99)
+
+
+def test_sod_bf16_c2_stated_config_640_batch32():
+    """BASELINE config C2 at its stated size: SOD-simple, 640^2, batch 32, bf16 -- raw head maps and y of all 32 images vs the oracle."""
+    _check(SOD, torch.bfloat16, 32, 640, 2e-2, seed=41, layers_too=False)
+
+
+def test_sod_bf16_c3_stated_config_1024_batch16():
+    """BASELINE config C3 at its stated size: SOD-simple, 1024^2, batch 16, bf16."""
+    model, x, y, y_ref = _check(SOD, torch.bfloat16, 16, 1024, 2e-2, seed=43, layers_too=False)
+    assert y.shape == (16, 14, 87040)
+
+
+def test_yolov12m_c4b_640_bf16_and_fp32_mode():
+    """BASELINE config C4 read as stock yolov12m (SURVEY 8d option ii) at 640^2: bf16 tensor-core path on a micro-batch, and the fp32
+    parity mode (rtol 1e-4) of the same model."""
+    _check("yolov12m", torch.bfloat16, 4, 640, 2e-2, seed=45, layers_too=False)
+    _check("yolov12m", torch.float32, 1, 128, 1e-4, layer_tol=2e-4, seed=45)
 
 
 def test_sod_bf16_1024_single_image():
@@ -149,6 +199,29 @@ def test_graph_replay_equals_eager_and_is_deterministic():
     assert m_graph.program(2, 128, 128).n_lanes == 4 and m_single.program(2, 128, 128).n_lanes == 1
     for _ in range(3):
         assert torch.equal(m_graph(x)[0], m_single(x)[0])
+
+
+def test_outputs_are_fresh_tensors_and_predict_path_skips_raw_maps():
+    """Drop-in semantics: forward returns fresh tensors (a second forward must not overwrite the first result), the
+    static / no-raw-map mode used by YOLO.predict gives the bit-identical `y`, strided or host inputs are staged, and the program
+    cache is bounded."""
+    spec, sd, model = _build(SOD, torch.bfloat16, max_programs=2)
+    xa, xb = synth.synth_images(2, 160, seed=1).cuda(), synth.synth_images(2, 160, seed=2).cuda()
+    ya, ra = model(xa)
+    keep = ya.clone()
+    yb, rb = model(xb)
+    assert torch.equal(ya, keep) and not torch.equal(ya, yb), "results must not alias the program's buffers"
+    ys, rs = model(xa, static=True, want_raw=False)
+    assert rs == [] and torch.equal(ys, ya), "decode-only (no raw map) program must give the same y"
+    # the same values through the staging path: a host tensor, and a strided (non-contiguous) device view
+    yh, _ = model(xa.cpu())
+    big = torch.zeros((2, 3, 160, 320), device="cuda")
+    big[..., ::2] = xa
+    yv, _ = model(big[..., ::2])
+    assert torch.equal(yh, ya) and torch.equal(yv, ya)
+    for sz in (128, 192, 224):
+        model(synth.synth_images(1, sz, seed=3).cuda())
+    assert len(model.programs) == 2, "LRU cap on compiled programs"
 
 
 def test_predict_end_to_end_matches_oracle_nms():

@@ -83,6 +83,44 @@ def test_stress_30k_vs_c_oracle(clustered):
         assert np.array_equal(index[b, :n].cpu().numpy().astype(np.int64), want_idx[b])
 
 
+def test_c5_clustered_full_batch64_vs_c_oracle_on_8_images():
+    """BASELINE config C5 at its stated size (B=64, 30 000 x 10, clustered = heavy suppression): the whole batch runs on the GPU;
+    8 of the 64 images are checked bit-exactly (rows and keep indices) against the C oracle, all 64 by count sanity."""
+    pred = nms_cases.stress_pred(64, A=30000, clustered=True)
+    det, count, index = _ops().nms_padded(torch.from_numpy(pred).cuda(), 0.25, 0.7, max_det=300)
+    torch.cuda.synchronize()
+    cnt = count.cpu().numpy()
+    assert (cnt > 0).all() and (cnt <= 300).all()
+    for b in range(0, 64, 8):
+        want, want_idx = nms_ref.non_max_suppression(pred[b:b + 1].copy(), 0.25, 0.7, max_det=300, return_index=True)
+        n = int(cnt[b])
+        assert n == len(want[0])
+        assert np.array_equal(det[b, :n].cpu().numpy(), want[0])
+        assert np.array_equal(index[b, :n].cpu().numpy().astype(np.int64), want_idx[0])
+
+
+def test_zero_threshold_and_kept_list_size_boundaries():
+    """(a) iou_thres == 0 must take the IEEE division for every pair -- a tiny intersection over a huge union underflows
+    to IoU == 0, which is NOT > 0 (torchvision keeps the pair); (b) max_keep just below / at / above the kept-list kernel's
+    shared-memory limit (2040) must all launch and agree with the oracle."""
+    ops = _ops()
+    big = np.float32(3.0e18)
+    boxes = np.array([[0, 0, big, big], [0, 0, 1e-19, 1e-19], [5, 5, 6, 6]], np.float32)
+    scores = np.array([0.9, 0.8, 0.7], np.float32)
+    want = nms_ref.nms(boxes, scores, 0.0)
+    got = ops.nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), 0.0).cpu().numpy()
+    assert np.array_equal(want, got), (want, got)
+    b, s = nms_cases.uniform_boxes(6000, 77)
+    for thr in (0.0, 1e-7, 0.3):
+        want = nms_ref.nms(b, s, thr)
+        got = ops.nms(torch.from_numpy(b).cuda(), torch.from_numpy(s).cuda(), thr).cpu().numpy()
+        assert np.array_equal(want, got), thr
+    want = nms_ref.nms(b, s, 0.7)
+    for mk in (2039, 2040, 2041, 2047, 2048, 2049):
+        got = ops.nms(torch.from_numpy(b).cuda(), torch.from_numpy(s).cuda(), 0.7, max_keep=mk).cpu().numpy()
+        assert np.array_equal(want[:mk], got), mk
+
+
 def test_full_size_properties_b64():
     """Config 5 at full size (B=64): size-independent properties instead of an oracle run."""
     pred = torch.from_numpy(nms_cases.stress_pred(64, A=30000, clustered=True)).cuda()

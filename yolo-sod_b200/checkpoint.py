@@ -33,15 +33,27 @@ _SAFE_GLOBALS = {
 _TORCH_DTYPES = {"float32", "float16", "bfloat16", "float64", "int64", "int32", "int16", "int8", "uint8", "bool"}
 
 
+# exact names only (no prefix / suffix matching): the helpers torch.save emits for tensors, parameters and storages
+_TORCH_REBUILD = {
+    ("torch._utils", "_rebuild_tensor"), ("torch._utils", "_rebuild_tensor_v2"), ("torch._utils", "_rebuild_tensor_v3"),
+    ("torch._utils", "_rebuild_parameter"), ("torch._utils", "_rebuild_parameter_with_state"),
+    ("torch._utils", "_rebuild_qtensor"), ("torch._tensor", "_rebuild_from_type_v2"),
+}
+_TORCH_STORAGES = {"FloatStorage", "HalfStorage", "BFloat16Storage", "DoubleStorage", "LongStorage", "IntStorage", "ShortStorage",
+                   "CharStorage", "ByteStorage", "BoolStorage", "UntypedStorage", "TypedStorage"}
+
+
 def _torch_global_ok(module: str, name: str) -> bool:
-    if (module, name) in _SAFE_GLOBALS:
+    """torch.storage._load_from_bytes is deliberately NOT allowed: it is `torch.load(BytesIO(b), weights_only=False)` with the
+    default, unrestricted pickle, so a checkpoint could REDUCE it over an embedded payload and run any callable. Zip-format
+    checkpoints (everything torch >= 1.6 writes) never reference it."""
+    if (module, name) in _SAFE_GLOBALS or (module, name) in _TORCH_REBUILD:
         return True
+    if module in ("torch", "torch.storage") and name in _TORCH_STORAGES:
+        import inspect
+        return inspect.isclass(getattr(__import__(module, fromlist=[name]), name, None))
     if module == "torch":
-        return name in _TORCH_DTYPES or name.endswith("Storage")                  # torch.FloatStorage, torch.float32 ...
-    if module in ("torch._utils", "torch._tensor"):
-        return name.startswith("_rebuild")                                       # _rebuild_tensor_v2, _rebuild_parameter ...
-    if module == "torch.storage":
-        return name.endswith("Storage") or name == "_load_from_bytes"
+        return name in _TORCH_DTYPES                                              # torch.float32 ...
     if module.startswith("torch.nn.modules."):
         import importlib
         import inspect

@@ -350,12 +350,9 @@ mha_flash_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __res
 
 }  // namespace
 
-extern "C" int ysod_mha_core(const void* q, const void* k, const void* v, int dtype, int batch, int L, int heads, int D, int ldq,
-                             int ldk, int ldv, long long bsq, long long bsk, long long bsv, float scale, void* out, int ldo,
-                             long long bso, cudaStream_t st) {
-    YSOD_CHECK_ARG(q && k && v && out, "ysod_mha_core: null pointer");
-    YSOD_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "ysod_mha_core: row strides must be multiples of 8");
-    YSOD_CHECK_ARG(batch <= 65535 || true, "ysod_mha_core: batch");
+static int mha_core_chunk(const void* q, const void* k, const void* v, int dtype, int batch, int L, int heads, int D, int ldq,
+                          int ldk, int ldv, long long bsq, long long bsk, long long bsv, float scale, void* out, int ldo,
+                          long long bso, cudaStream_t st) {
     if (dtype == YSOD_BF16 && L <= 64 && (D == 16 || D == 32 || D == 64) && batch <= 65535 && ((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 &&
         ((uintptr_t)v % 16) == 0 && ((uintptr_t)out % 16) == 0 && bsq % 8 == 0 && bsk % 8 == 0 && bsv % 8 == 0 && bso % 8 == 0) {
         dim3 wgrid(heads, batch);
@@ -398,5 +395,23 @@ extern "C" int ysod_mha_core(const void* q, const void* k, const void* v, int dt
     }
 #undef LAUNCH
     YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+extern "C" int ysod_mha_core(const void* q, const void* k, const void* v, int dtype, int batch, int L, int heads, int D, int ldq,
+                             int ldk, int ldv, long long bsq, long long bsk, long long bsv, float scale, void* out, int ldo,
+                             long long bso, cudaStream_t st) {
+    YSOD_CHECK_ARG(q && k && v && out, "ysod_mha_core: null pointer");
+    YSOD_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "ysod_mha_core: row strides must be multiples of 8");
+    // gridDim.y / .z are limited to 65535: large window batches (e.g. the unfused P2 SwinBlock at B >= 124) run as chunks of
+    // <= 65535 (batch, ...) slices with offset base pointers
+    const size_t es = dtype == YSOD_BF16 ? 2 : 4;
+    for (int b0 = 0; b0 < batch; b0 += 65535) {
+        const int nb = batch - b0 < 65535 ? batch - b0 : 65535;
+        const int rc = mha_core_chunk((const char*)q + (size_t)b0 * bsq * es, (const char*)k + (size_t)b0 * bsk * es,
+                                      (const char*)v + (size_t)b0 * bsv * es, dtype, nb, L, heads, D, ldq, ldk, ldv, bsq, bsk, bsv, scale,
+                                      (char*)out + (size_t)b0 * bso * es, ldo, bso, st);
+        if (rc != YSOD_OK) return rc;
+    }
     return YSOD_OK;
 }

@@ -47,6 +47,9 @@ static inline int ysod_cdiv(long long a, long long b) { return (int)((a + b - 1)
 #define YSOD_F32 0
 #define YSOD_BF16 1
 
+// ysod_stem_mma src_fmt flag (ysod.h): the image argument is a device slot holding the image pointer
+#define YSOD_STEM_INDIRECT 0x10
+
 // activation codes for fused epilogues
 #define YSOD_ACT_NONE 0
 #define YSOD_ACT_SILU 1

@@ -277,7 +277,10 @@ nms_greedy_kernel(const float* __restrict__ pred, int nc, int A, int cap, int mu
         if (kept < max_det) {
             const float4 bi = (i < nc_box) ? sbox[i] : boxes[i];
             const float iarea = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
-            const float thr_hi = __fmul_rn(thr_f, 1.0000009537f), thr_lo = __fmul_rn(thr_f, 0.9999990463f);   // thr * (1 +- 2^-20)
+            // thr * (1 +- 2^-20); thresholds at / near zero take the IEEE division for every pair (a quotient that underflows to 0 is
+            // not > 0, which the product form cannot see): +-inf bounds make both shortcut comparisons false
+            const bool band = thr_f > 1.0e-6f;
+            const float thr_hi = band ? __fmul_rn(thr_f, 1.0000009537f) : INFINITY, thr_lo = band ? __fmul_rn(thr_f, 0.9999990463f) : -INFINITY;
             for (int w = (pos >> 5) + warp; w < nwords; w += GREEDY_THREADS / 32) {
                 const int j = w * 32 + lane;
                 const uint32_t already = removed[w];   // boxes suppressed earlier need no evaluation (their bit stays set)
@@ -373,7 +376,9 @@ nms_chunk_kernel(const float* __restrict__ pred, int nc, int A, int cap, int mul
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = count_all[b];
     const float4* boxes = boxes_all + (size_t)b * cap;
-    const float thr_hi = __fmul_rn(thr_f, 1.0000009537f), thr_lo = __fmul_rn(thr_f, 0.9999990463f);   // thr * (1 +- 2^-20)
+    // thr * (1 +- 2^-20); thresholds at / near zero take the IEEE division for every pair (see nms_greedy_kernel)
+    const bool band = thr_f > 1.0e-6f;
+    const float thr_hi = band ? __fmul_rn(thr_f, 1.0000009537f) : INFINITY, thr_lo = band ? __fmul_rn(thr_f, 0.9999990463f) : -INFINITY;
     if (tid == 0) s_kept = 0;
     __syncthreads();
     int kept = 0;
@@ -520,7 +525,7 @@ int ysod_nms_batched(const float* pred, int B, int nc, int A, float conf_thres, 
                                                     agnostic ? 0.0f : max_wh, w.boxes);
         YSOD_LAUNCH_CHECK();
     }
-    if (max_det <= 2048) {   // kept-list formulation: the detection path (max_det = 300)
+    if (max_det <= 2040) {   // kept-list formulation (24 B per kept box of dynamic shared memory + 136 B static <= 48 KB): the detection path (max_det = 300)
         ysod_launch(nms_chunk_kernel, B, GREEDY_THREADS, (size_t)max_det * 24, stream, pred, nc, A, cap, multi_label, max_det, thr_f, w.boxes, w.order,
                                                                               w.sscore, w.cls, w.count, out_det, out_index, out_count);
         YSOD_LAUNCH_CHECK();
@@ -584,7 +589,7 @@ int ysod_nms_boxes(const float* boxes, const float* scores, int n, float thr_f, 
     YSOD_LAUNCH_CHECK();
     ysod_launch(nms_reorder_boxes_kernel, ysod_cdiv(n, 256), 256, 0, stream, (const float4*)boxes, order, count, sorted);
     YSOD_LAUNCH_CHECK();
-    if (max_keep <= 2048) {
+    if (max_keep <= 2040) {
         ysod_launch(nms_chunk_kernel, 1, GREEDY_THREADS, (size_t)max_keep * 24, stream, nullptr, 0, 0, n, 0, max_keep, thr_f, sorted, order, sscore, nullptr,
                                                                                count, nullptr, keep_out, nkeep_out);
         YSOD_LAUNCH_CHECK();

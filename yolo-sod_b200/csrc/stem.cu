@@ -44,9 +44,12 @@ __device__ __forceinline__ int koff(int k) {
 // SRC = 0: img is (N,3,H,W) fp32 in [0,1];  SRC = 1: img is (N,H,W,3) uint8 BGR in 0..255 (-> RGB, /255)
 template <int COUT, int SRC, bool VEC>
 __global__ void __launch_bounds__(256, COUT <= 32 ? 4 : 2)
-stem_mma_kernel(const void* __restrict__ img_, const __nv_bfloat16* __restrict__ wk, const float* __restrict__ bias,
-                __nv_bfloat16* __restrict__ out, int H, int W, int Ho, int Wo, int ocs, int act) {
+stem_mma_kernel(const void* img_, const __nv_bfloat16* __restrict__ wk, const float* __restrict__ bias,
+                __nv_bfloat16* __restrict__ out, int H, int W, int Ho, int Wo, int ocs, int act, int indirect) {
     ysod_pdl_sync();
+    // indirect: img_ is a device slot holding the image pointer (ysod_set_ptr), so a captured graph can read whichever tensor
+    // the caller passed to this forward instead of a private staging copy
+    if (indirect) img_ = *static_cast<const void* const*>(img_);
     constexpr int NB = COUT / 8;
     __shared__ __align__(16) __nv_bfloat16 patch[3 * PLANE];
     __shared__ __align__(16) __nv_bfloat16 stage[TH * TW * (COUT + 8)];   // +8: keeps the 4-byte fragment stores conflict-free
@@ -211,7 +214,18 @@ stem_mma_kernel(const void* __restrict__ img_, const __nv_bfloat16* __restrict__
     }
 }
 
+__global__ void set_ptr_kernel(const void** slot, const void* value) { *slot = value; }
+
 }  // namespace
+
+// Binds the image a captured forward reads: writes `value` into the device pointer slot the stem kernel dereferences
+// (src_fmt | YSOD_STEM_INDIRECT). Stream-ordered, so it takes effect for the launches that follow it on `stream`.
+extern "C" int ysod_set_ptr(void* slot, const void* value, cudaStream_t stream) {
+    YSOD_CHECK_ARG(slot && ((uintptr_t)slot % 8) == 0, "ysod_set_ptr: slot must be an 8 B aligned device pointer");
+    set_ptr_kernel<<<1, 1, 0, stream>>>((const void**)slot, value);
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
 
 // img: src_fmt 0 = (N,3,H,W) fp32 in [0,1] (what DetectionModel.forward receives, tasks.py:129);
 //      src_fmt 1 = (N,H,W,3) uint8 BGR frames (what BasePredictor.preprocess receives, predictor.py:116-134).
@@ -221,6 +235,8 @@ extern "C" int ysod_stem_mma(const void* img, int src_fmt, int N, int H, int W, 
                              int ocs, int act, cudaStream_t stream) {
     YSOD_CHECK_ARG(img && wk && bias && out, "ysod_stem_mma: null pointer");
     YSOD_CHECK_ARG(Cout == 16 || Cout == 32 || Cout == 64, "ysod_stem_mma: Cout %d unsupported (16, 32, 64)", Cout);
+    const int indirect = (src_fmt & YSOD_STEM_INDIRECT) ? 1 : 0;
+    src_fmt &= ~YSOD_STEM_INDIRECT;
     YSOD_CHECK_ARG(src_fmt == 0 || src_fmt == 1, "ysod_stem_mma: bad source format %d", src_fmt);
     YSOD_CHECK_ARG(H % 2 == 0 && W % 2 == 0 && ocs % 8 == 0 && ((uintptr_t)out % 16) == 0, "ysod_stem_mma: bad geometry / alignment");
     YSOD_CHECK_ARG(act == YSOD_ACT_SILU || act == YSOD_ACT_NONE, "ysod_stem_mma: activation %d unsupported", act);
@@ -228,11 +244,12 @@ extern "C" int ysod_stem_mma(const void* img, int src_fmt, int N, int H, int W, 
     dim3 grid(ysod_cdiv(Wo, TW), ysod_cdiv(Ho, TH), N);
     const __nv_bfloat16* w = (const __nv_bfloat16*)wk;
     __nv_bfloat16* o = (__nv_bfloat16*)out;
-    const bool vec = (W % 4 == 0) && ((uintptr_t)img % 16 == 0);   // aligned 16 B / 4 B row loads
+    // aligned 16 B / 4 B row loads (an indirect image pointer must be 16 B aligned: the binder checks it)
+    const bool vec = (W % 4 == 0) && (indirect || (uintptr_t)img % 16 == 0);
 #define LAUNCH(CO, SRC)                                                                                          \
     do {                                                                                                         \
-        if (vec) ysod_launch(stem_mma_kernel<CO, SRC, true>, grid, 256, 0, stream, img, w, bias, o, H, W, Ho, Wo, ocs, act);   \
-        else ysod_launch(stem_mma_kernel<CO, SRC, false>, grid, 256, 0, stream, img, w, bias, o, H, W, Ho, Wo, ocs, act);      \
+        if (vec) ysod_launch(stem_mma_kernel<CO, SRC, true>, grid, 256, 0, stream, img, w, bias, o, H, W, Ho, Wo, ocs, act, indirect);   \
+        else ysod_launch(stem_mma_kernel<CO, SRC, false>, grid, 256, 0, stream, img, w, bias, o, H, W, Ho, Wo, ocs, act, indirect);      \
     } while (0)
     if (Cout == 16) { if (src_fmt) LAUNCH(16, 1); else LAUNCH(16, 0); }
     else if (Cout == 32) { if (src_fmt) LAUNCH(32, 1); else LAUNCH(32, 0); }

@@ -58,6 +58,7 @@ struct TcParams {
     int dec_A, dec_off, dec_nc;
     float dec_stride;
     int w_img_rows;   // > 0: per-image weights (an SE channel gate folded into the next conv): image i uses weight rows [i*w_img_rows, +Cout_pad)
+    int no_store;   // the plan's own output is not written (decode-only head conv of the predict path)
     int up2;    // nn.Upsample(scale 2, nearest) fused into the store: every output pixel is written to its 2 x 2 block of the 2Ho x 2Wo destination
     int debug;  // profiling only (mode >> 8): 1 = epilogue drains without work, 2 = producer skips TMA, 4 = MMA issuer skips tcgen05.mma,
                 // 8 = epilogue skips the TMA store, 16 = epilogue skips the activation
@@ -597,8 +598,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 continue;
             }
             // the bulk stores issued from this group's staging buffer (previous own tile) must have finished reading it
-            if (leader_warp) bulk_wait_read<0>();
-            epi_barrier(grp);
+            const bool no_store = p.no_store != 0;   // decode-only plan: nothing is staged or stored, so no barriers either
+            if (!no_store) {
+                if (leader_warp) bulk_wait_read<0>();
+                epi_barrier(grp);
+            }
             trace(tre, 2, 2, tcount, 0, tcnt);       // staging buffer free
             float dd0 = 0.f, dd1 = 0.f;   // fused decode: DFL distances of this thread's two sides (cg = 0: left, right; cg = 1: top, bottom)
             const bool dec = p.dec_y != nullptr;
@@ -668,6 +672,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // The staging units are 1 KB aligned and a thread always writes row m, so the XOR term is a per-thread constant.
                 const int u = ch / chunks_per_unit, cu = ch - u * chunks_per_unit;
                 const uint32_t row_addr = row0 + (split ? 0u : (uint32_t)u * unit_bytes);
+                if (no_store) continue;
                 if (out_f32) {
                     const uint32_t p0 = (uint32_t)(cu * 4);
 #pragma unroll
@@ -696,6 +701,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (lane == 0) mbar_arrive(my_tempty);
             trace(tre, 2, 3, tcount, 0, tcnt);       // accumulator handed back
             }
+            if (no_store) continue;
             fence_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
             epi_barrier(grp);
             if (leader_warp && elect_one()) {
@@ -829,7 +835,8 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
     const bool up2 = (mode & 0x40) != 0;
     const bool img_w = (mode & 0x80) != 0;
     const int split_exp = mode & 0x10;
-    mode &= 0x2f;
+    const bool no_store = (mode & 0x20) != 0;
+    mode &= 0x0f;
     if (img_w) {
         YSOD_CHECK_ARG(mode != 2, "ysod_conv_tc_create_ex: per-image weights need the generic kernel (resident taps are shared by all images)");
         mode = 1;
@@ -841,6 +848,7 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
     YSOD_CHECK_ARG(mode != 2 || halo, "ysod_conv_tc_create_ex: shape does not qualify for the halo kernel");
     p.debug = dbg;
     p.up2 = up2 ? 1 : 0;
+    p.no_store = no_store ? 1 : 0;
     p.w_img_rows = img_w ? Cout_pad : 0;
     if (halo) { bestTH = 16; bestTW = 8; }
     p.N = N; p.Ho = Ho; p.Wo = Wo; p.TH = bestTH; p.TW = bestTW;
@@ -1094,6 +1102,7 @@ int ysod_conv_tc_set_decode(ysod_conv_tc* h, float* y, int A_total, int a_off, i
                    "ysod_conv_tc_set_decode: plan must be an fp32-output, activation-free, single-N-tile conv");
     YSOD_CHECK_ARG(nc > 0 && p.Cout == 64 + nc && p.BN >= 64 + nc, "ysod_conv_tc_set_decode: Cout %d != 64 + nc (%d)", p.Cout, nc);
     YSOD_CHECK_ARG(a_off >= 0 && a_off + p.Ho * p.Wo <= A_total, "ysod_conv_tc_set_decode: anchor range out of bounds");
+    YSOD_CHECK_ARG(!p.no_store || !p.stage_split, "ysod_conv_tc_set_decode: YSOD_CONV_NO_STORE needs the single-pass epilogue");
     p.dec_y = y; p.dec_A = A_total; p.dec_off = a_off; p.dec_nc = nc; p.dec_stride = stride;
     return YSOD_OK;
 }

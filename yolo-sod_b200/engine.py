@@ -12,6 +12,7 @@ Nothing here computes on the CPU at run time; if libysod.so or the GPU is missin
 """
 import ctypes as C
 import math
+from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -68,9 +69,10 @@ class GatedView:
 class Program:
     """A compiled forward for one (batch, H, W): buffers + launch list."""
 
-    def __init__(self, model: "B200DetectionModel", B: int, H: int, W: int, src_u8: bool = False):
+    def __init__(self, model: "B200DetectionModel", B: int, H: int, W: int, src_u8: bool = False, want_raw: bool = True):
         self.m = model
         self.B, self.H, self.W = B, H, W
+        self.want_raw = want_raw   # False: the predict path -- only `y` is consumed, the fp32 raw maps are not materialised
         self.src_u8 = src_u8   # input is (B,H,W,3) uint8 BGR frames (predictor.py:116-134) instead of (B,3,H,W) float
         self.dev = model.device
         self.dt = model.dtype
@@ -89,11 +91,19 @@ class Program:
         self._ctx = ""
         self.layer_out: Dict[int, View] = {}
         self.graph: Optional[torch.cuda.CUDAGraph] = None
-        if src_u8:
-            self.img = torch.zeros((B, H, W, 3), device=self.dev, dtype=torch.uint8)
-        else:
-            self.img = torch.zeros((B, 3, H, W), device=self.dev, dtype=torch.float32)
+        # The stem reads its image through a device pointer slot (ysod_set_ptr), so a forward consumes the caller's tensor in
+        # place, as the reference does; `img` is a private staging buffer, allocated only for inputs that cannot be bound
+        # directly (host tensors, other dtypes / layouts).
+        self.img_shape = (B, H, W, 3) if src_u8 else (B, 3, H, W)
+        self.img_dtype = torch.uint8 if src_u8 else torch.float32
+        self.img: Optional[torch.Tensor] = None
+        self.img_slot = torch.zeros(1, device=self.dev, dtype=torch.int64)
+        self.img_indirect = False
+        self._bound = 0
         self._build()
+        if not self.img_indirect:
+            self.img = torch.zeros(self.img_shape, device=self.dev, dtype=self.img_dtype)
+            self._rebind_direct()
 
     # ---- buffers -----------------------------------------------------------------------------------------
     def new(self, N, H, W, Cc, dtype=None, zero=False):
@@ -130,7 +140,7 @@ class Program:
         return w * s.view(-1, 1, 1, 1), b - mu * s
 
     def conv(self, x: View, w: torch.Tensor, bias: torch.Tensor, k, s, g, act, out: View, res: View = None,
-             out_f32=False, pad=None, up2=False, gate=None, alg_flops=None):
+             out_f32=False, pad=None, up2=False, gate=None, alg_flops=None, no_store=False):
         """w: (Cout, Cin/g, k, k) fp32 with BN folded; bias fp32 (Cout). up2: `out` is the 2x nearest-upsampled destination
         (tensor-core path only; the caller checks `tc_eligible`). gate: (N, Cin) fp32 device tensor of an SE block folded into this conv
         (per-image weights W * gate[n], rebuilt every forward by ysod_scale_weights; tensor-core path only)."""
@@ -154,7 +164,7 @@ class Program:
             return
         use_tc = (self.m.use_tc and self.code == _lib.BF16 and g == 1 and k in (1, 3) and s in (1, 2) and pad == k // 2
                   and Cin % 32 == 0 and (s == 1 or (x.H % 2 == 0 and x.W % 2 == 0)))
-        assert use_tc or not (up2 or gate is not None), "fused upsample / folded SE gate need the tensor-core conv"
+        assert use_tc or not (up2 or gate is not None or no_store), "fused upsample / folded SE gate / decode-only need the tensor-core conv"
         if use_tc:
             cpad = (Cout + 15) // 16 * 16
             wk = torch.zeros((cpad, k * k * Cin), dtype=torch.float32)
@@ -163,6 +173,8 @@ class Program:
             bk[:Cout] = bias
             bd = self.dev_t(bk)
             mode = _lib.CONV_UP2 if up2 else 0
+            if no_store:
+                mode |= _lib.CONV_NO_STORE | _lib.CONV_NO_SPLIT_STAGING
             if gate is None:
                 wd = self.dev_t(wk, torch.bfloat16)
             else:
@@ -376,7 +388,7 @@ class Program:
         ao = self.mha(sn, f"{P}.attention", p["num_heads"], x.N, na * x.W)
         up = self.new(x.N, x.H, x.W, Cc)
         self.emit("ysod_bilinear_rows", ao.ptr(), self.code, x.N, na, x.W, Cc, ao.cs, x.H, up.ptr(), up.cs)
-        self.conv_bn(up, f"{P}.out_proj", out=out, res=x)
+        self.conv_bn(up, f"{P}.out_proj", out=out, res=x if out.C == x.C else None)   # a2_attn.py:64-69: identity only if c2 == c1
 
     def ablock(self, x, P, heads, area, out):
         """block.py:1367-1416 ABlock with AAttn (:1298-1365, manual-softmax semantics)."""
@@ -504,7 +516,10 @@ class Program:
                 self._lane = 1 + i
                 self.n_lanes = max(self.n_lanes, 2 + i)
                 self.sched.append(("wait", f"L{src_layers[i]}", self._lane))
-            raw = self.new(x.N, x.H, x.W, raw_cs, dtype=torch.float32, zero=True)
+            fused_tail = (p["legacy"] and self.m.use_tc and self.code == _lib.BF16 and self.m.fuse_decode and no <= 128
+                          and (sd[f"{P}.cv2.{i}.0.conv.weight"].shape[0] + sd[f"{P}.cv3.{i}.1.conv.weight"].shape[0]) % 32 == 0)
+            skip_raw = not self.want_raw and fused_tail   # predict path: `y` is written by the tail conv's epilogue, nothing reads raw
+            raw = None if skip_raw else self.new(x.N, x.H, x.W, raw_cs, dtype=torch.float32, zero=True)
             decoded = False
             if p["legacy"] and self.m.use_tc and self.code == _lib.BF16:
                 # cv2[i][0] and cv3[i][0] are 3x3 convs on the same input: run them as ONE conv with N = c2 + c3 output channels
@@ -526,8 +541,13 @@ class Program:
                     wt[:64, :c2n] = sd[f"{P}.cv2.{i}.2.weight"].float()
                     wt[64:, c2n:] = sd[f"{P}.cv3.{i}.2.weight"].float()
                     bt = torch.cat([sd[f"{P}.cv2.{i}.2.bias"].float(), sd[f"{P}.cv3.{i}.2.bias"].float()])
-                    self.conv(ac, wt, bt, 1, 1, 1, "none", raw.slice(0, no), out_f32=True,
-                              alg_flops=2.0 * x.N * x.H * x.W * (64 * c2n + nc * c3n))
+                    if skip_raw:   # the tensor map still needs a valid address; YSOD_CONV_NO_STORE never writes through it
+                        dummy = View(y, 0, x.N, x.H, x.W, no, raw_cs)
+                        self.conv(ac, wt, bt, 1, 1, 1, "none", dummy, out_f32=True, no_store=True,
+                                  alg_flops=2.0 * x.N * x.H * x.W * (64 * c2n + nc * c3n))
+                    else:
+                        self.conv(ac, wt, bt, 1, 1, 1, "none", raw.slice(0, no), out_f32=True,
+                                  alg_flops=2.0 * x.N * x.H * x.W * (64 * c2n + nc * c3n))
                     a = c = None
                     if self.m.fuse_decode:
                         # ... and the level's DFL / dist2bbox / sigmoid decode runs in that conv's epilogue (no re-read of the raw map)
@@ -557,7 +577,8 @@ class Program:
                 self.emit("ysod_dfl_decode", raw.ptr(), _lib.F32, x.N, x.H, x.W, raw.cs, nc, 16, float(self.m.stride_list[i]), _lib.ptr(y), A,
                           a_off)
             a_off += x.H * x.W
-            raws.append(raw.slice(0, no))
+            if raw is not None:
+                raws.append(raw.slice(0, no))
             if branch:
                 self.sched.append(("record", f"det{i}", self._lane))
                 self._lane = 0
@@ -684,13 +705,15 @@ class Program:
                         wk = torch.zeros((co, 32), dtype=torch.float32)
                         wk[:, :27] = wf.permute(0, 2, 3, 1).reshape(co, 27)
                         wd, bd = self.dev_t(wk, torch.bfloat16), self.dev_t(bf)
-                        self.emit("ysod_stem_mma", _lib.ptr(self.img), 1 if self.src_u8 else 0, self.B, self.H, self.W, _lib.ptr(wd),
+                        self.img_indirect = True
+                        self.emit("ysod_stem_mma", _lib.ptr(self.img_slot), (1 if self.src_u8 else 0) | _lib.STEM_INDIRECT, self.B, self.H, self.W, _lib.ptr(wd),
                                   _lib.ptr(bd), co, o.ptr(), o.cs, _lib.ACT["silu" if p["act"] else "none"], desc=f"stem 3->{co}")
                     else:
                         if self.src_u8:
                             raise NotImplementedError("uint8 frame input needs the bf16 tensor-core stem (3x3/s2, Cout 16/32/64)")
                         wd, bd = self.dev_t(wf.permute(0, 2, 3, 1)), self.dev_t(bf)
-                        self.emit("ysod_stem_conv", _lib.ptr(self.img), self.B, self.H, self.W, _lib.ptr(wd), _lib.ptr(bd), co, k, s,
+                        self._stem_direct_op = len(self.ops)
+                        self.emit("ysod_stem_conv", None, self.B, self.H, self.W, _lib.ptr(wd), _lib.ptr(bd), co, k, s,
                                   pd, o.ptr(), self.code, o.cs, _lib.ACT["silu" if p["act"] else "none"])
                 else:
                     self.conv_bn(x, P, p["k"], p["s"], p["g"], p["act"], out=o, pad=p["p"], gate=gate)
@@ -776,6 +799,10 @@ class Program:
 
     def capture(self):
         """Capture the launch list into a CUDA graph (batch-1 latency is launch-bound otherwise)."""
+        warm = None
+        if self.img_indirect and not self._bound:
+            warm = torch.zeros(self.img_shape, device=self.dev, dtype=self.img_dtype)   # warm-up image; every run() rebinds
+            self.bind_input(warm)
         torch.cuda.synchronize()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
@@ -787,15 +814,39 @@ class Program:
         with torch.cuda.graph(g):
             self.launch_all()
         self.graph = g
+        if warm is not None:
+            torch.cuda.synchronize()
+            self._bound = 0
+            del warm
 
-    def run(self, x: torch.Tensor):
-        self.img.copy_(x, non_blocking=True)
+    def _rebind_direct(self):
+        """CUDA-core stem (fp32 parity mode): the kernel takes the image pointer as a plain argument = the private staging buffer."""
+        i = self._stem_direct_op
+        fn, args, name = self.ops[i]
+        self.ops[i] = (fn, (_lib.ptr(self.img),) + tuple(args[1:]), name)
+
+    def bind_input(self, x: torch.Tensor):
+        """Points the stem at `x` (no copy) when it is a dense, 16 B aligned tensor of the program's dtype / layout on its device;
+        anything else (host memory, other dtypes, strided views) is staged through the private buffer."""
+        direct = (self.img_indirect and x.is_cuda and x.device == self.dev and x.dtype == self.img_dtype
+                  and tuple(x.shape) == self.img_shape and x.is_contiguous() and x.data_ptr() % 16 == 0)
+        if not direct:
+            if self.img is None:
+                self.img = torch.zeros(self.img_shape, device=self.dev, dtype=self.img_dtype)
+            self.img.copy_(x, non_blocking=True)
+            x = self.img
+        if self.img_indirect and x.data_ptr() != self._bound:
+            _lib.call("ysod_set_ptr", _lib.ptr(self.img_slot), C.c_void_p(x.data_ptr()), _lib.stream_ptr())
+            self._bound = x.data_ptr()
+
+    def run(self, x: torch.Tensor, static: bool = False):
+        self.bind_input(x)
         if self.graph is not None:
             self.graph.replay()
         else:
             self.launch_all()
         raw = [r.torch_nchw() for r in self.raws]
-        if self.m.static_outputs:
+        if static:
             return self.y, raw      # views of the program's own buffers: overwritten by the next forward of this shape
         return self.y.clone(), [r.clone() for r in raw]
 
@@ -817,7 +868,7 @@ class B200DetectionModel:
     """
 
     def __init__(self, cfg, state_dict, dtype=torch.bfloat16, device="cuda:0", use_tc=True, use_graph=True, nc=None,
-                 static_outputs=True, fuse_swin=True, multi_stream=True, fuse_upsample=True, fuse_decode=True, fuse_se=True, fuse_gate=False):
+                 static_outputs=False, max_programs=8, fuse_swin=True, multi_stream=True, fuse_upsample=True, fuse_decode=True, fuse_se=True, fuse_gate=False):
         _lib.require_cuda()
         _lib.load()
         self.spec = cfg if isinstance(cfg, _cfg.ModelSpec) else _cfg.get_spec(cfg, nc=nc)
@@ -846,36 +897,46 @@ class B200DetectionModel:
         self.reg_max = 16
         self.no = self.nc + 64
         self.nl = len(self.stride_list)
-        self.programs: Dict[tuple, Program] = {}
+        # One compiled program (activation buffers + CUDA graph) per input signature, least recently used evicted beyond
+        # `max_programs`: rectangular letterbox shapes (LetterBox auto=True) would otherwise grow GPU memory without bound.
+        self.max_programs = max(1, int(max_programs))
+        self.programs: "OrderedDict[tuple, Program]" = OrderedDict()
 
-    def program(self, B, H, W, src_u8=False) -> Program:
-        key = (B, H, W, bool(src_u8))
-        if key not in self.programs:
+    def program(self, B, H, W, src_u8=False, want_raw=True) -> Program:
+        key = (B, H, W, bool(src_u8), bool(want_raw))
+        if key in self.programs:
+            self.programs.move_to_end(key)
+        else:
             s = max(self.stride_list)
             if H % s or W % s:
                 raise ValueError(f"input {H}x{W} must be a multiple of the max stride {s}")
             with torch.cuda.device(self.device):
-                prog = Program(self, B, H, W, src_u8)
+                prog = Program(self, B, H, W, src_u8, want_raw)
                 if self.use_graph:
                     prog.capture()
             self.programs[key] = prog
+            while len(self.programs) > self.max_programs:
+                self.programs.popitem(last=False)   # buffers / graph / conv plans are released with the Program
         return self.programs[key]
 
     @torch.no_grad()
-    def forward(self, x, *args, **kwargs):
+    def forward(self, x, *args, static=None, want_raw=True, **kwargs):
         """x: (B,3,H,W) float tensor in [0,1] (NCHW, as the reference's forward takes it), or (B,H,W,3) uint8 BGR frames (what
         BasePredictor.preprocess receives, predictor.py:116-134; BGR->RGB, HWC->CHW and /255 are fused into the stem kernel).
-        Returns (y, [raw maps])."""
+        Returns (y, [raw maps]) as fresh tensors, like the reference's forward. `static=True` (or `static_outputs=True` at
+        construction) returns views of the program's own buffers instead -- zero-copy, but overwritten by the next forward of the
+        same shape: for callers that consume the result immediately (YOLO.predict, bench). `want_raw=False` (predict path: only
+        `y` is consumed) skips materialising the raw maps where the decode is fused into the head conv; the list is then empty."""
         u8 = x.dtype == torch.uint8
         if x.dim() != 4 or (x.shape[3] if u8 else x.shape[1]) != 3:
             raise ValueError(f"expected (B,3,H,W) float or (B,H,W,3) uint8, got {tuple(x.shape)} {x.dtype}")
         # host tensors are copied straight into the program's input buffer (pinned memory makes this asynchronous)
         if u8:
-            prog = self.program(int(x.shape[0]), int(x.shape[1]), int(x.shape[2]), True)
+            prog = self.program(int(x.shape[0]), int(x.shape[1]), int(x.shape[2]), True, want_raw)
         else:
-            prog = self.program(int(x.shape[0]), int(x.shape[2]), int(x.shape[3]))
+            prog = self.program(int(x.shape[0]), int(x.shape[2]), int(x.shape[3]), False, want_raw)
         with torch.cuda.device(self.device):
-            return prog.run(x)
+            return prog.run(x, self.static_outputs if static is None else bool(static))
 
     __call__ = forward
     predict = forward

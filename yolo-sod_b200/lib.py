@@ -9,6 +9,9 @@ LIB_PATH = os.path.join(_HERE, "libysod.so")
 F32, BF16 = 0, 1
 CONV_UP2 = 0x40   # ysod.h YSOD_CONV_UP2
 CONV_IMG_WEIGHTS = 0x80   # ysod.h YSOD_CONV_IMG_WEIGHTS
+CONV_NO_SPLIT_STAGING = 0x10   # ysod.h YSOD_CONV_NO_SPLIT_STAGING
+CONV_NO_STORE = 0x20      # ysod.h YSOD_CONV_NO_STORE
+STEM_INDIRECT = 0x10      # ysod.h YSOD_STEM_INDIRECT
 ACT = {"none": 0, "silu": 1, "gelu": 2, "relu": 3, "sigmoid": 4, "hsigmoid": 5}
 
 vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_longlong, C.c_float
@@ -35,6 +38,7 @@ PROTOTYPES = {
     "ysod_dwconv": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, vp, i32, vp, i32, i32, vp]),
     "ysod_stem_conv": (i32, [vp, i32, i32, i32, vp, vp, i32, i32, i32, i32, vp, i32, i32, i32, vp]),
     "ysod_stem_mma": (i32, [vp, i32, i32, i32, i32, vp, vp, i32, vp, i32, i32, vp]),
+    "ysod_set_ptr": (i32, [vp, vp, vp]),
     "ysod_letterbox_u8": (i32, [vp, i32, i32, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
     "ysod_scale_boxes": (i32, [vp, i32, i32, i32, vp, i32, vp]),
     "ysod_gap_partial": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]),

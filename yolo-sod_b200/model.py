@@ -49,8 +49,7 @@ class DetectionModel(B200DetectionModel):
 
 class AutoBackend:
     """The attribute set and call signature `BasePredictor` expects from `AutoBackend` (engine/predictor.py:131,143,158-159,
-    193,239,306-321). Single backend: the sm_100a library. `fp16=True` is rejected: the reference's half mode is IEEE fp16,
-    which this build does not provide; the low-precision mode here is bf16 (selected by the model's dtype)."""
+    193,239,306-321). Single backend: the sm_100a library. Outputs are fresh tensors, as the reference's are."""
 
     def __init__(self, weights: DetectionModel, device=None, dnn=False, data=None, fp16=False, batch=1, fuse=True, verbose=False):
         if not isinstance(weights, B200DetectionModel):
@@ -67,10 +66,10 @@ class AutoBackend:
         self.jit = self.onnx = self.engine = self.triton = self.imx = self.dynamic = self.nhwc = False
         self.task = "detect"
 
-    def forward(self, im, augment=False, visualize=False, embed=None):
+    def forward(self, im, augment=False, visualize=False, embed=None, **kw):
         if augment or visualize or embed is not None:
             raise NotImplementedError("augment / visualize / embed are outside the inference hot path")
-        return self.model(im)
+        return self.model(im, **kw)
 
     __call__ = forward
 
@@ -142,19 +141,26 @@ class YOLO:
             raise NotImplementedError("accepted sources: (B,3,H,W) float tensors in [0,1] (predictor.py:116-134 tensor branch), (B,H,W,3) "
                                       "uint8 BGR frames, or a list of HWC uint8 BGR frames (numpy / torch); file and stream sources need "
                                       "the reference's ultralytics.data loaders, which are out of scope")
+        det, counts, (h, w) = self.predict_padded(source, conf, iou, max_det, classes, agnostic_nms)
+        ncount = counts.tolist()   # the one host sync of the call: the API returns variable-length per-image tensors
+        return _ops.DetList([Results(det[b, :n], (h, w), self.names) for b, n in enumerate(ncount)], det, counts)
+
+    @torch.no_grad()
+    def predict_padded(self, source, conf=0.25, iou=0.7, max_det=300, classes=None, agnostic_nms=False):
+        """predict() without the host synchronisation: (det (B,max_det,6) fp32 fresh tensor, count (B,) int32, (h, w)) on the GPU.
+        The forward runs in the zero-copy / no-raw-map mode (its `y` is consumed by the NMS launches that follow on the same
+        stream, nothing else reads it), and scale_boxes(img.shape[2:], boxes, orig_shape) with identical shapes == clip_boxes
+        (ops.py:92-127,319-338) is ONE launch over the whole padded batch."""
         im = source if source.dim() == 4 else source[None]
         if im.dtype == torch.uint8:   # raw BGR HWC frames: preprocess (predictor.py:127-133) is fused into the stem kernel
-            preds = self.backend(im)
             h, w = int(im.shape[1]), int(im.shape[2])
         else:
-            preds = self.backend(im.float())
+            im = im if im.dtype == torch.float32 else im.float()
             h, w = int(im.shape[2]), int(im.shape[3])
-        dets = _ops.non_max_suppression(preds, conf, iou, classes=classes, agnostic=agnostic_nms, max_det=max_det)
-        out = []
-        for d in dets:
-            # scale_boxes(img.shape[2:], boxes, orig_shape) with identical shapes == clip_boxes (ops.py:92-127,319-338)
-            out.append(Results(_ops.clip_boxes(d.clone(), (h, w)), (h, w), self.names))
-        return out
+        preds = self.backend(im, static=True, want_raw=False)
+        det, count, _ = _ops.nms_padded(preds[0], conf, iou, classes=classes, agnostic=agnostic_nms, max_det=max_det)
+        _ops.clip_boxes(det, (h, w))
+        return det, count, (h, w)
 
     def _predict_frames(self, frames, conf, iou, max_det, classes, agnostic_nms, imgsz):
         """The predictor's list-of-frames branch, on the device: pre_transform (LetterBox) -> preprocess fused into the stem ->
@@ -169,6 +175,6 @@ class YOLO:
         preds = self.backend(im)
         shapes = [tuple(int(v) for v in f.shape[:2]) for f in frames]
         dets = _pred.postprocess(preds, (int(im.shape[1]), int(im.shape[2])), shapes, conf, iou, agnostic_nms, max_det, classes)
-        return [Results(d, s, self.names) for d, s in zip(dets, shapes)]
+        return _ops.DetList([Results(d, s, self.names) for d, s in zip(dets, shapes)], getattr(dets, "det", None), getattr(dets, "count", None))
 
     __call__ = predict

@@ -10,6 +10,7 @@ import torch
 from . import lib as _lib
 
 _ws_cache = {}
+_params_cache = {}
 
 
 def _thr_float(iou_thres: float) -> float:
@@ -18,6 +19,15 @@ def _thr_float(iou_thres: float) -> float:
     if float(t) > float(iou_thres):
         t = np.nextafter(t, np.float32(-np.inf))
     return float(t)
+
+
+class DetList(list):
+    """The reference's return type -- a plain list of (n_i, 6) tensors -- that also keeps the padded batch its items are views of:
+    `.det` (B, max_det, 6) and `.count` (B,) int32 on the GPU, for callers that move / gather the whole batch in one transfer."""
+
+    def __init__(self, items, det, count):
+        super().__init__(items)
+        self.det, self.count = det, count
 
 
 def nms_padded(prediction: torch.Tensor, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False,
@@ -77,7 +87,7 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
         raise NotImplementedError("end-to-end (B,N,6) predictions are outside the detection hot path")
     det, count, _ = nms_padded(prediction, conf_thres, iou_thres, classes, agnostic, multi_label, max_det, nc, max_nms, max_wh)
     counts = count.tolist()  # the single host sync
-    return [det[b, :n] for b, n in enumerate(counts)]
+    return DetList([det[b, :n] for b, n in enumerate(counts)], det, count)
 
 
 def nms(boxes: torch.Tensor, scores: torch.Tensor, iou_threshold: float, max_keep: Optional[int] = None) -> torch.Tensor:
@@ -136,8 +146,14 @@ def scale_boxes(img1_shape, boxes: torch.Tensor, img0_shape, ratio_pad=None, pad
         gain, pad = ratio_pad[0][0], ratio_pad[1]
     if not padding:
         pad = (0, 0)
-    params = torch.tensor([float(np.float32(gain)), float(pad[0]), float(pad[1]), float(img0_shape[1]), float(img0_shape[0])],
-                          dtype=torch.float32).to(boxes.device, non_blocking=True)
+    vals = (float(np.float32(gain)), float(pad[0]), float(pad[1]), float(img0_shape[1]), float(img0_shape[0]))
+    pkey = (boxes.device.index, vals)
+    params = _params_cache.get(pkey)   # device-resident (gain, pad_x, pad_y, w0, h0): no per-call host->device copy
+    if params is None:
+        if len(_params_cache) > 256:
+            _params_cache.clear()
+        params = torch.tensor(vals, dtype=torch.float32).to(boxes.device)
+        _params_cache[pkey] = params
     k = int(boxes.shape[-1])
     with torch.cuda.device(boxes.device):
         _lib.call("ysod_scale_boxes", _lib.ptr(boxes), 1, boxes.numel() // k, k, _lib.ptr(params), 5, _lib.stream_ptr())

@@ -106,4 +106,4 @@ def postprocess(preds, img_shape, orig_shapes: List[tuple], conf=0.25, iou=0.7, 
     with torch.cuda.device(det.device):
         _lib.call("ysod_scale_boxes", _lib.ptr(det), int(det.shape[0]), int(det.shape[1]), 6, _lib.ptr(params), 5, _lib.stream_ptr())
     counts = count.tolist()
-    return [det[b, :n] for b, n in enumerate(counts)]
+    return _ops.DetList([det[b, :n] for b, n in enumerate(counts)], det, count)
