@@ -22,6 +22,10 @@ extern "C" {
 int ysod_version(void);
 const char* ysod_last_error(void);
 int ysod_compiled_arch(void); /* 100 = sm_100a */
+/* 16-bit storage type of the loaded build: 1 = bf16 (libysod.so), 2 = IEEE fp16 (libysod_f16.so: the same sources compiled with
+ * -DYSOD_HALF=1, the reference's `half=True` / `model.half()` mode, nn/autobackend.py:154). dtype code 1 in every entry point below
+ * means "this build's 16-bit type". */
+int ysod_storage_dtype(void);
 
 /* ---- NMS: ultralytics/utils/ops.py:167-316 non_max_suppression + torchvision.ops.nms (ops.py:296) ---------------- */
 long long ysod_nms_workspace_bytes(int B, int nc, int A, int max_nms, int multi_label);

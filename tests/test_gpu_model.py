@@ -3,8 +3,10 @@
 Tolerances (north_star: raw head maps rtol 1e-4 in fp32 mode, rtol 2e-2 in bf16 mode):
   fp32 mode : elementwise |got-ref| <= 1e-4*|ref| + 1e-4*max|ref|   (absolute floor for near-zero elements)
   bf16 mode : relative L2 error ||got-ref|| / ||ref|| <= 2e-2 on every raw head map (3e-2 on intermediate layers, which
-              are diagnostics), at most 1 % of the elements outside |got-ref| <= 2e-2*|ref| + 2e-2*max|ref|, and a hard cap
-              of 10 % of max|ref| on any single element.
+              are diagnostics), at most 0.3 % of the elements outside |got-ref| <= 2e-2*|ref| + 2e-2*max|ref|, and a hard cap
+              of 8 % of max|ref| on any single element (both tightened in round 2 from the recorded statistics).
+  fp16 mode : the reference's own `half=True`; rel-L2 <= 3e-3 against the fp32 oracle and <= 4e-3 against the oracle itself run
+              in fp16 (the reference's fp16 path), strict elementwise bound at rtol 1e-2.
 A pure elementwise rtol 2e-2 in the max norm is not what a bf16 execution of this ~100-layer network delivers: the
 reference's OWN code run in bf16 (model.fuse().bfloat16() on CPU) deviates from its fp32 run by 3.1-5.1 % of max|ref|
 (SOD, 160^2 and 640^2) and 4.5-9.9 % (yolov12n 640^2) on single elements, rel-L2 1.0-2.2 % -- measured in the build
@@ -26,8 +28,11 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden", "model_golden.npz")
 SOD = "yolov12-sod-fusion-v5-simple"
 
 
-VIOL_SHARE = 1e-2     # bf16: allowed share of elements outside rtol*|ref| + rtol*max|ref|
-MAX_ERR_CAP = 0.10    # bf16: hard cap on any single element, as a fraction of max|ref|
+# bf16 allowances, set from the recorded statistics (profiles/r02_parity_records.jsonl: 78 raw maps over every model test):
+# measured share of elements outside rtol*|ref| + rtol*max|ref| is 0 for 68 maps, <= 1.1e-4 for the SOD family, 1.8e-3 worst case
+# (yolov12n P5 map at 640^2); measured max single-element error 5.9 % of max|ref| (same map), <= 3.6 % for the SOD family.
+VIOL_SHARE = 3e-3     # allowed share of elements outside the strict bound (round 1: 1e-2)
+MAX_ERR_CAP = 0.08    # hard cap on any single element, as a fraction of max|ref| (round 1: 0.10)
 PARITY_LOG = os.environ.get("YSOD_PARITY_LOG", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out",
                                                             "parity_records.jsonl"))
 
@@ -106,6 +111,36 @@ def test_sod_bf16_tensor_core_path():
     model, x, y, y_ref = _check(SOD, torch.bfloat16, 2, 160, 2e-2, layer_tol=3e-2)
     prog = model.program(2, 160, 160)
     assert prog.n_tc > 60, "the dense convs must run on the tcgen05 kernel"
+
+
+def test_sod_fp16_half_mode():
+    """the reference's only native low-precision mode, `half=True` -> model.half() (autobackend.py:154). The fp16
+    build of the library (same sources, -DYSOD_HALF=1: IEEE fp16 storage and tensor-core inputs) against (a) the fp32 oracle and
+    (b) the oracle run in fp16 itself = the reference's fp16 path."""
+    spec, sd, model = _build(SOD, torch.float16)
+    x = synth.synth_images(2, 160, seed=11)
+    y, raw = model(x.cuda())
+    torch.cuda.synchronize()
+    assert model.program(2, 160, 160).n_tc > 60, "the dense convs must run on the tcgen05 kernel"
+    y32, raw32 = model_ref.forward(spec, sd, x, ycfg.strides_of(spec))
+    fsd = {k: (v.half() if v.is_floating_point() else v) for k, v in model_ref.fuse_state_dict(sd).items()}
+    y16, raw16 = model_ref.forward(spec, fsd, x, ycfg.strides_of(spec), dtype=torch.float16)
+    for l, (a, b32, b16) in enumerate(zip(raw, raw32, raw16)):
+        st = _stats(a.float().cpu(), b32, 1e-2)
+        _record(test="test_sod_fp16_half_mode", model=SOD, dtype="float16", batch=2, imgsz=160, raw_map=l, tol=1e-2, **st)
+        assert st["rel_l2"] <= 3e-3 and st["viol_share"] == 0.0, (l, st)
+        st16 = _stats(a.float().cpu(), b16.float(), 1e-2)
+        assert st16["rel_l2"] <= 4e-3, (l, st16)
+    # the public switches: YOLO.predict(half=True) and AutoBackend(fp16=True) run the fp16 twin of a bf16 model
+    from yolo_sod_b200.model import YOLO, AutoBackend
+    yolo = YOLO(SOD, weights=sd, dtype=torch.bfloat16)
+    be = AutoBackend(yolo.model, fp16=True)
+    assert be.fp16 and torch.equal(be(x.cuda())[0], y)
+    r16 = yolo.predict(x.cuda(), half=True)
+    r_bf = yolo.predict(x.cuda())
+    assert len(r16) == len(r_bf) == 2 and sum(len(r) for r in r16) > 0
+    # bf16 and fp16 libraries coexist in one process
+    _check(SOD, torch.bfloat16, 1, 128, 2e-2, layer_tol=3e-2)
 
 
 def test_sod_bf16_cuda_core_crosscheck():

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _built():
-    if not os.path.exists(lib.LIB_PATH):
+    if not (os.path.exists(lib.LIB_PATH) and os.path.exists(lib.LIB_PATH_F16)):
         import __graft_entry__ as g
         g.build()
 
@@ -24,12 +24,13 @@ def test_library_exports_every_declared_symbol():
     declared = set(re.findall(r"\b(ysod_[a-z0-9_]+)\s*\(", header))
     declared.discard("ysod_conv_tc")
     assert len(declared) >= 30
-    so = ctypes.CDLL(lib.LIB_PATH)
-    for name in sorted(declared):
-        assert hasattr(so, name), f"{name} declared in include/ysod.h but not exported"
+    for path in (lib.LIB_PATH, lib.LIB_PATH_F16):       # the bf16 build and the fp16 (`half=True`) build export the same ABI
+        so = ctypes.CDLL(path)
+        for name in sorted(declared):
+            assert hasattr(so, name), f"{name} declared in include/ysod.h but not exported by {os.path.basename(path)}"
     assert declared == set(lib.PROTOTYPES), "lib.py prototypes and include/ysod.h disagree"
-    lib.load()
     assert lib.load().ysod_version() == 100 and lib.load().ysod_compiled_arch() == 100
+    assert lib.load().ysod_storage_dtype() == 1 and lib.load(half=True).ysod_storage_dtype() == 2
 
 
 def test_error_reporting_without_compute():

@@ -16,4 +16,12 @@ int ysod_version(void) { return 100; }
 const char* ysod_last_error(void) { return g_err; }
 // Which device architecture the library was compiled for (sm_100a only).
 int ysod_compiled_arch(void) { return 100; }
+// 16-bit storage / tensor-core input type of this build: 1 = bf16 (libysod.so), 2 = IEEE fp16 (libysod_f16.so, -DYSOD_HALF=1).
+int ysod_storage_dtype(void) {
+#ifdef YSOD_HALF
+    return 2;
+#else
+    return 1;
+#endif
+}
 }

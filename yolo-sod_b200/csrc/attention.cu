@@ -93,7 +93,7 @@ mha_core_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __res
 // staged in shared memory (padded rows: conflict-free 32-bit fragment loads), S = QK^T and O = PV are mma.sync m16n8k16 with
 // fp32 accumulators, the softmax lives in registers (quad shuffles), P is re-packed from the S accumulators into A fragments.
 __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32." YSOD_MMA_T "." YSOD_MMA_T ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }

@@ -2,9 +2,32 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+
+// ---- 16-bit storage type of the build ---------------------------------------------------------------------------------
+// libysod.so stores activations / weights as bf16 (north_star's low-precision mode). The SAME sources compiled with
+// -DYSOD_HALF=1 give libysod_f16.so, the reference's own half mode (`model.half()`, nn/autobackend.py:154): IEEE fp16 storage
+// and fp16 tensor-core inputs, fp32 accumulation and epilogue math unchanged. Dtype code 1 (YSOD_BF16) means "the build's
+// 16-bit type" at the C ABI; ysod_storage_dtype() tells which one a library was built for.
+#ifdef YSOD_HALF
+#define __nv_bfloat16 __half
+#define __nv_bfloat162 __half2
+#define __float2bfloat16_rn __float2half_rn
+#define __float2bfloat16 __float2half
+#define __floats2bfloat162_rn __floats2half2_rn
+#define __bfloat162float __half2float
+#define __bfloat1622float2 __half22float2
+#define YSOD_MMA_T "f16"                                    // mma.sync operand type
+#define YSOD_TMAP_16 CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+#define YSOD_UMMA_AB_FORMAT 0u                              // tcgen05 kind::f16 instruction descriptor: A / B format 0 = f16
+#else
+#define YSOD_MMA_T "bf16"
+#define YSOD_TMAP_16 CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+#define YSOD_UMMA_AB_FORMAT 1u                              // 1 = bf16
+#endif
 
 #define YSOD_OK 0
 #define YSOD_ERR_INVALID 1
@@ -88,6 +111,15 @@ template <> __device__ __forceinline__ float ysod_ld<__nv_bfloat16>(const __nv_b
 template <typename T> __device__ __forceinline__ void ysod_st(T* p, float v);
 template <> __device__ __forceinline__ void ysod_st<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void ysod_st<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// two packed 16-bit activations (one 32-bit word) -> floats
+__device__ __forceinline__ float2 ysod_unpack2(uint32_t v) {
+#ifdef YSOD_HALF
+    return __half22float2(*reinterpret_cast<const __half2*>(&v));
+#else
+    return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+#endif
+}
 
 __device__ __forceinline__ float ysod_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 

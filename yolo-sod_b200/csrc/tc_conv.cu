@@ -641,8 +641,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint32_t rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        f[2 * j] += __uint_as_float(rw[j] << 16);
-                        f[2 * j + 1] += __uint_as_float(rw[j] & 0xffff0000u);
+                        const float2 r2 = ysod_unpack2(rw[j]);
+                        f[2 * j] += r2.x;
+                        f[2 * j + 1] += r2.y;
                     }
                     if (ch + 2 < nchunks) { ra = *reinterpret_cast<const uint4*>(rp + c0 + 32); rb = *reinterpret_cast<const uint4*>(rp + c0 + 40); }
                 }
@@ -873,7 +874,7 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
     p.b_bytes = (uint32_t)BN * p.BK * 2u;
     p.a_tx = (uint32_t)(bestTH * bestTW) * p.BK * 2u;
     // instruction descriptor (kind::f16): D=f32, A=B=bf16, both K-major, N>>3 @17, M>>4 @24
-    p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+    p.idesc = (1u << 4) | (YSOD_UMMA_AB_FORMAT << 7) | (YSOD_UMMA_AB_FORMAT << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
     // smem descriptor high word: SBO (8 rows x swizzle span) >> 4 @ bits 32-45, version 1 @ 46, layout @ 61
     const uint32_t sbo = (p.BK == 64 ? 1024u : 512u) >> 4;
     const uint32_t layout = (p.BK == 64) ? 2u : 4u;  // SWIZZLE_128B : SWIZZLE_64B
@@ -1016,7 +1017,7 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
         cuuint32_t box[4] = {(cuuint32_t)p.BK, (cuuint32_t)(bestTW * stride), (cuuint32_t)(bestTH * stride), 1};
         if (halo) { box[1] = 10; box[2] = 18; }   // the halo copy: rows oh0-1 .. oh0+16, columns ow0-1 .. ow0+8
         cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-        CUresult r = enc(&c.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, es,
+        CUresult r = enc(&c.tmA, YSOD_TMAP_16, 4, const_cast<void*>(x), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             ysod_set_error("ysod_conv_tc_create: cuTensorMapEncodeTiled(A) failed with %d (Cin %d W %d H %d N %d xcs %d box %d,%d,%d)",
@@ -1030,7 +1031,7 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
         cuuint64_t strides[1] = {K * 2};
         cuuint32_t box[2] = {(cuuint32_t)p.BK, (cuuint32_t)BN};
         cuuint32_t es[2] = {1, 1};
-        CUresult r = enc(&c.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(wgt), dims, strides, box, es,
+        CUresult r = enc(&c.tmB, YSOD_TMAP_16, 2, const_cast<void*>(wgt), dims, strides, box, es,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             ysod_set_error("ysod_conv_tc_create: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
@@ -1047,7 +1048,7 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
         cuuint32_t es1[4] = {1, (cuuint32_t)us, (cuuint32_t)us, 1};
         const CUtensorMapSwizzle oswz = p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                       : p.row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
-        CUresult r = enc(&c.tmO, p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, dims, strides,
+        CUresult r = enc(&c.tmO, p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : YSOD_TMAP_16, 4, out, dims, strides,
                          box, es1, CU_TENSOR_MAP_INTERLEAVE_NONE, oswz, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             ysod_set_error("ysod_conv_tc_create: cuTensorMapEncodeTiled(O) failed with %d (Cout %d ocs %d unit %d)", (int)r, Cout, ocs,

@@ -76,7 +76,9 @@ class Program:
         self.src_u8 = src_u8   # input is (B,H,W,3) uint8 BGR frames (predictor.py:116-134) instead of (B,3,H,W) float
         self.dev = model.device
         self.dt = model.dtype
-        self.code = _lib.BF16 if self.dt == torch.bfloat16 else _lib.F32
+        self.half = self.dt == torch.float16      # fp16 build of the library (the reference's half=True mode)
+        self.lib = _lib.load(self.half)
+        self.code = _lib.BF16 if self.dt in (torch.bfloat16, torch.float16) else _lib.F32   # code 1 = the build's 16-bit storage type
         self.ops: List[tuple] = []       # (cfunc, args-without-stream, entry point name)
         self.sched: List[tuple] = []     # launch schedule: ("op", op index, lane) | ("record", mark, lane) | ("wait", mark, lane)
         self._lane = 0                   # stream lane new ops are issued on (0 = main chain; 1.. = Detect level branches)
@@ -123,8 +125,11 @@ class Program:
         self.keep.append(t)
         return t
 
+    def call(self, name, *args):
+        _lib.check(getattr(self.lib, name)(*args), name, self.half)
+
     def emit(self, name, *args, flops=0.0, desc=""):
-        self.ops.append((getattr(_lib.load(), name), args, name))
+        self.ops.append((getattr(self.lib, name), args, name))
         self.sched.append(("op", len(self.ops) - 1, self._lane))
         self.op_flops.append(float(flops))
         self.op_desc.append(f"{self._ctx} {desc}".strip())
@@ -176,25 +181,25 @@ class Program:
             if no_store:
                 mode |= _lib.CONV_NO_STORE | _lib.CONV_NO_SPLIT_STAGING
             if gate is None:
-                wd = self.dev_t(wk, torch.bfloat16)
+                wd = self.dev_t(wk, self.dt)
             else:
                 # one weight matrix per image: fp32 master weights x gate[n] -> bf16, rebuilt by a small launch before the conv
                 wm = self.dev_t(wk)
-                wd = torch.empty((x.N, cpad, k * k * Cin), device=self.dev, dtype=torch.bfloat16)
+                wd = torch.empty((x.N, cpad, k * k * Cin), device=self.dev, dtype=self.dt)
                 self.keep.append(wd)
                 self.emit("ysod_scale_weights", _lib.ptr(wm), cpad, k * k * Cin, Cin, _lib.ptr(gate), x.N, _lib.ptr(wd), desc="SE gate -> conv weights")
                 mode |= _lib.CONV_IMG_WEIGHTS
             h = C.c_void_p()
-            _lib.call("ysod_conv_tc_create_ex", C.byref(h), x.ptr(), x.N, x.H, x.W, Cin, x.cs, _lib.ptr(wd), _lib.ptr(bd), Cout, cpad,
+            self.call("ysod_conv_tc_create_ex", C.byref(h), x.ptr(), x.N, x.H, x.W, Cin, x.cs, _lib.ptr(wd), _lib.ptr(bd), Cout, cpad,
                       k, s, out.ptr(), odt, out.cs, res.ptr() if res is not None else None, res.cs if res is not None else 0, actc,
                       mode)
             self.tc_handles.append(h)
-            self.ops.append((_lib.load().ysod_conv_tc_run, (h,), "ysod_conv_tc_run"))
+            self.ops.append((self.lib.ysod_conv_tc_run, (h,), "ysod_conv_tc_run"))
             self.sched.append(("op", len(self.ops) - 1, self._lane))
             fl = 2.0 * x.N * Ho * Wo * Cout * k * k * Cin if alg_flops is None else float(alg_flops)   # algorithmic (structural zeros excluded)
             self.op_flops.append(fl)
             info = (C.c_int * 8)()
-            _lib.call("ysod_conv_tc_info", h, info)
+            self.call("ysod_conv_tc_info", h, info)
             self.op_desc.append(f"{self._ctx} tc {Cin}->{Cout} k{k}s{s}{'up2' if up2 else ''}{'+SEgate' if gate is not None else ''} @{Ho}x{Wo} N{x.N} tile{info[0]}x{info[1]} BN{info[2]} BK{info[3]} "
                                 f"st{info[4]} grid{info[5]}x{info[6]} smem{info[7]}")
             self.tc_flops += fl
@@ -307,7 +312,7 @@ class Program:
                             sd[f"{A}.mlp.0.bias"].float(), sd[f"{A}.mlp.2.bias"].float(),
                             b - sd[f"{P}.bn.running_mean"].float() * sc])
             assert wb.numel() == 37440 and pf.numel() == 768
-            wbd, pfd = self.dev_t(wb, torch.bfloat16), self.dev_t(pf)
+            wbd, pfd = self.dev_t(wb, self.dt), self.dev_t(pf)
             T = x.N * (-(-x.H // ws)) * (-(-x.W // ws)) * ws * ws
             self.emit("ysod_swin64_fused", x.ptr(), x.N, x.H, x.W, x.cs, _lib.ptr(wbd), _lib.ptr(pfd), out.ptr(), out.cs, ws, 2,
                       flops=2.0 * T * (64 * 192 + 64 * 64 + 2 * 64 * 128 + 64 * 64 + 2 * 49 * 64), desc=f"swin64 fused @{x.H}x{x.W}")
@@ -551,7 +556,7 @@ class Program:
                     a = c = None
                     if self.m.fuse_decode:
                         # ... and the level's DFL / dist2bbox / sigmoid decode runs in that conv's epilogue (no re-read of the raw map)
-                        _lib.call("ysod_conv_tc_set_decode", self.tc_handles[-1], _lib.ptr(y), A, a_off, nc, float(self.m.stride_list[i]))
+                        self.call("ysod_conv_tc_set_decode", self.tc_handles[-1], _lib.ptr(y), A, a_off, nc, float(self.m.stride_list[i]))
                         self.op_desc[-1] += " +decode"
                         decoded = True
                 else:
@@ -704,7 +709,7 @@ class Program:
                         # tensor-core stem: weights as [Cout][32] bf16, column (r*3+s)*3+c, zero padded
                         wk = torch.zeros((co, 32), dtype=torch.float32)
                         wk[:, :27] = wf.permute(0, 2, 3, 1).reshape(co, 27)
-                        wd, bd = self.dev_t(wk, torch.bfloat16), self.dev_t(bf)
+                        wd, bd = self.dev_t(wk, self.dt), self.dev_t(bf)
                         self.img_indirect = True
                         self.emit("ysod_stem_mma", _lib.ptr(self.img_slot), (1 if self.src_u8 else 0) | _lib.STEM_INDIRECT, self.B, self.H, self.W, _lib.ptr(wd),
                                   _lib.ptr(bd), co, o.ptr(), o.cs, _lib.ACT["silu" if p["act"] else "none"], desc=f"stem 3->{co}")
@@ -760,7 +765,7 @@ class Program:
                 fn, args, name = self.ops[what]
                 rc = fn(*args, ptrs[lane])
                 if rc:
-                    _lib.check(rc, name)
+                    _lib.check(rc, name, self.half)
             elif kind == "record":
                 ev = torch.cuda.Event()
                 ev.record(streams[lane])
@@ -782,7 +787,7 @@ class Program:
                 rc = fn(*args, st)
                 e1.record()
                 if rc:
-                    _lib.check(rc, name)
+                    _lib.check(rc, name, self.half)
                 evs.append((e0, e1))
             torch.cuda.synchronize()
             if it == 0:
@@ -836,7 +841,7 @@ class Program:
             self.img.copy_(x, non_blocking=True)
             x = self.img
         if self.img_indirect and x.data_ptr() != self._bound:
-            _lib.call("ysod_set_ptr", _lib.ptr(self.img_slot), C.c_void_p(x.data_ptr()), _lib.stream_ptr())
+            self.call("ysod_set_ptr", _lib.ptr(self.img_slot), C.c_void_p(x.data_ptr()), _lib.stream_ptr())
             self._bound = x.data_ptr()
 
     def run(self, x: torch.Tensor, static: bool = False):
@@ -852,9 +857,8 @@ class Program:
 
     def __del__(self):
         try:
-            lib = _lib.load()
             for h in self.tc_handles:
-                lib.ysod_conv_tc_destroy(h)
+                self.lib.ysod_conv_tc_destroy(h)
         except Exception:
             pass
 
@@ -864,7 +868,8 @@ class B200DetectionModel:
 
     cfg        : config name / YAML path / dict (see cfg.py)
     state_dict : reference-named weights (e.g. `ref_model.state_dict()`); fp32 CPU or CUDA tensors
-    dtype      : torch.bfloat16 (tensor-core path) or torch.float32 (CUDA-core parity mode, rtol 1e-4)
+    dtype      : torch.bfloat16 (tensor-core path), torch.float16 (the same path on the fp16 build of the library: the reference's
+                 `half=True` / `model.half()` mode, autobackend.py:154) or torch.float32 (CUDA-core parity mode, rtol 1e-4)
     """
 
     def __init__(self, cfg, state_dict, dtype=torch.bfloat16, device="cuda:0", use_tc=True, use_graph=True, nc=None,
@@ -876,8 +881,9 @@ class B200DetectionModel:
         missing = [k for k in _cfg.param_shapes(self.spec) if k not in self.sd]
         if missing:
             raise KeyError(f"state_dict is missing {len(missing)} tensors, e.g. {missing[:3]}")
-        assert dtype in (torch.bfloat16, torch.float32)
+        assert dtype in (torch.bfloat16, torch.float16, torch.float32)
         self.dtype = dtype
+        _lib.load(dtype == torch.float16)
         self.device = torch.device(device)
         self.use_tc = use_tc
         self.use_graph = use_graph
@@ -943,6 +949,18 @@ class B200DetectionModel:
 
     def eval(self):
         return self
+
+    def half(self):
+        """`model.half()` (autobackend.py:154): the same graph and weights compiled against the fp16 build of the library. Returns a
+        new model object (compiled programs are per dtype); `self` is left untouched."""
+        if self.dtype == torch.float16:
+            return self
+        import copy
+        twin = copy.copy(self)
+        twin.dtype = torch.float16
+        twin.programs = OrderedDict()
+        _lib.load(True)
+        return twin
 
     def fuse(self, verbose=False):
         return self  # BN is always folded at compile time

@@ -5,6 +5,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libysod.so")
+LIB_PATH_F16 = os.path.join(_HERE, "libysod_f16.so")   # the same sources built with -DYSOD_HALF=1 (IEEE fp16 storage, `half=True`)
 
 F32, BF16 = 0, 1
 CONV_UP2 = 0x40   # ysod.h YSOD_CONV_UP2
@@ -21,6 +22,7 @@ PROTOTYPES = {
     "ysod_version": (i32, []),
     "ysod_last_error": (C.c_char_p, []),
     "ysod_compiled_arch": (i32, []),
+    "ysod_storage_dtype": (i32, []),
     "ysod_nms_workspace_bytes": (i64, [i32, i32, i32, i32, i32]),
     "ysod_nms_batched": (i32, [vp, i32, i32, i32, f32, f32, vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp, i64, vp]),
     "ysod_nms_boxes_workspace_bytes": (i64, [i32]),
@@ -65,32 +67,36 @@ PROTOTYPES = {
     "ysod_mha_core": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i64, i64, i64, f32, vp, i32, i64, vp]),
 }
 
-_lib = None
+_libs = {}
 
 
 class YsodError(RuntimeError):
     pass
 
 
-def load():
-    """dlopen libysod.so and attach prototypes. Raises if the library has not been built (`__graft_entry__.build()`)."""
-    global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise YsodError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+def load(half: bool = False):
+    """dlopen libysod.so (bf16 build; `half=True`: libysod_f16.so, the fp16 build of the same sources) and attach prototypes.
+    Raises if the library has not been built (`__graft_entry__.build()`)."""
+    key = bool(half)
+    if key not in _libs:
+        path = LIB_PATH_F16 if key else LIB_PATH
+        if not os.path.exists(path):
+            raise YsodError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
                             "There is no CPU fallback.")
-        lib = C.CDLL(LIB_PATH)
+        lib = C.CDLL(path)
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(lib, name)  # AttributeError here == header/library mismatch
             fn.restype = res
             fn.argtypes = args
-        _lib = lib
-    return _lib
+        if lib.ysod_storage_dtype() != (2 if key else 1):
+            raise YsodError(f"{path}: built for storage dtype {lib.ysod_storage_dtype()}, expected {2 if key else 1}")
+        _libs[key] = lib
+    return _libs[key]
 
 
-def check(rc, what=""):
+def check(rc, what="", half=False):
     if rc != 0:
-        msg = load().ysod_last_error().decode("utf-8", "replace")
+        msg = load(half).ysod_last_error().decode("utf-8", "replace")
         raise YsodError(f"{what} failed (code {rc}): {msg}")
 
 
@@ -110,5 +116,5 @@ def ptr(t, offset_elems=0):
     return C.c_void_p(t.data_ptr() + offset_elems * t.element_size())
 
 
-def call(name, *args):
-    check(getattr(load(), name)(*args), name)
+def call(name, *args, half=False):
+    check(getattr(load(half), name)(*args), name, half)

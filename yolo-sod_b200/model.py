@@ -55,11 +55,11 @@ class AutoBackend:
         if not isinstance(weights, B200DetectionModel):
             raise TypeError("AutoBackend(weights=...) must be a yolo_sod_b200 DetectionModel (in-memory module path, "
                             "autobackend.py:145-155); exported-format backends are out of scope")
-        if fp16:
-            raise NotImplementedError("half=True (fp16) is not provided; build the model with dtype=torch.bfloat16")
+        if fp16 and weights.dtype != torch.float16:
+            weights = weights.half()        # autobackend.py:154 `model.half() if fp16 else model.float()`
         self.model = weights
         self.device = weights.device
-        self.fp16 = False
+        self.fp16 = weights.dtype == torch.float16
         self.stride = int(max(weights.stride_list))
         self.names = weights.names
         self.pt = True
@@ -130,9 +130,17 @@ class YOLO:
     @torch.no_grad()
     def predict(self, source, stream=False, conf=0.25, iou=0.7, max_det=300, classes=None, agnostic_nms=False, imgsz=None,
                 half=False, **kwargs) -> List[Results]:
-        """Defaults follow cfg/default.yaml:51-54 and engine/model.py:547 (conf 0.25, iou 0.7, max_det 300)."""
-        if half:
-            raise NotImplementedError("half=True (fp16) is not provided")
+        """Defaults follow cfg/default.yaml:51-54 and engine/model.py:547 (conf 0.25, iou 0.7, max_det 300). `half=True` runs the
+        model's IEEE fp16 twin (cfg/default.yaml:60 `half`, predictor.py:309-318 -> AutoBackend(fp16=True) -> model.half())."""
+        if half and not self.backend.fp16:
+            if getattr(self, "_half_backend", None) is None:
+                self._half_backend = AutoBackend(self.model, fp16=True)
+            saved = self.backend
+            self.backend = self._half_backend
+            try:
+                return self.predict(source, stream, conf, iou, max_det, classes, agnostic_nms, imgsz, False, **kwargs)
+            finally:
+                self.backend = saved
         if isinstance(source, np.ndarray):
             source = [source] if source.ndim == 3 else list(source)
         if isinstance(source, (list, tuple)):
