@@ -165,6 +165,12 @@ int ysod_swin64_fused(const void* x, int N, int H, int W, int xcs, const void* w
  *      path of AAttn (block.py:1348-1357). q/k/v addressed as ptr + batch*bs + token*ld + head*D (elements). ----------- */
 int ysod_mha_core(const void* q, const void* k, const void* v, int dtype, int batch, int L, int heads, int D, int ldq, int ldk,
                   int ldv, long long bsq, long long bsk, long long bsv, float scale, void* out, int ldo, long long bso, void* stream);
+/* impl 0 = auto: QK^T and PV as tcgen05.mma with TMEM accumulators (attention_tc.cu) for 16-bit storage and head_dim 32 / 64 --
+ * two <= 64-token windows packed into one M = 128 tile, or 128-query tiles streaming 128-key tiles with an online softmax -- else
+ * the mma.sync / CUDA-core kernels; impl 1 = the mma.sync / CUDA-core kernels only (A/B baseline); impl 2 = tcgen05 required. */
+int ysod_mha_core_ex(const void* q, const void* k, const void* v, int dtype, int batch, int L, int heads, int D, int ldq, int ldk,
+                     int ldv, long long bsq, long long bsk, long long bsv, float scale, void* out, int ldo, long long bso, int impl,
+                     void* stream);
 
 #ifdef __cplusplus
 }

@@ -235,14 +235,24 @@ def test_stem_mma(cout, src, W):
     assert bool((err <= tol * ref.abs() + tol * ref.abs().max() + 1e-5).all()), err.max().item()
 
 
-@pytest.mark.parametrize("case", [(5, 49, 2, 32), (3, 49, 4, 64), (2, 64, 2, 64), (2, 33, 1, 32), (2, 160, 8, 64), (1, 400, 2, 32), (6, 49, 4, 16), (2, 100, 4, 16),
-                                  (70000, 9, 1, 32), (66000, 70, 1, 32)],   # batch > 65535: chunked over the grid.y / grid.z limit
-                         ids=lambda c: "x".join(str(v) for v in c))
-def test_mha_core(case):
+MHA_CASES = [(5, 49, 2, 32), (3, 49, 4, 64), (2, 64, 2, 64), (2, 33, 1, 32), (2, 160, 8, 64), (1, 400, 2, 32), (6, 49, 4, 16), (2, 100, 4, 16),
+             (1, 49, 1, 64), (7, 7, 3, 32), (2, 128, 2, 64), (2, 129, 1, 32), (3, 1600, 2, 32), (1, 1, 1, 64),
+             (70000, 9, 1, 32), (66000, 70, 1, 32)]   # batch > 65535: chunked over the grid.y / grid.z limit (mma.sync kernels)
+
+
+@pytest.mark.parametrize("impl", [0, 1, 2], ids=["auto", "mma_sync", "tcgen05"])
+@pytest.mark.parametrize("case", MHA_CASES, ids=lambda c: "x".join(str(v) for v in c))
+def test_mha_core(case, impl):
     """softmax(q k^T / sqrt(d)) v on packed [L][3E] projections (as nn.MultiheadAttention's in_proj lays them out) vs torch
-    fp32 on the bf16-rounded operands. L <= 64 takes the tensor-core window kernel, longer sequences the streaming one."""
+    fp32 on the bf16-rounded operands, for the three implementations behind ysod_mha_core_ex: auto, the mma.sync kernels (L <= 64:
+    window kernel, longer: streaming flash kernel) and the tcgen05 / TMEM kernel (head_dim 32 / 64: two windows packed per M = 128
+    tile, or 128-query tiles over streamed key tiles; ragged L, odd window counts, single tokens)."""
     from yolo_sod_b200 import lib
     batch, L, heads, D = case
+    if impl == 2 and D == 16:
+        pytest.skip("head_dim 16 stays on the mma.sync kernel")
+    if batch > 60000 and impl == 0:
+        pytest.skip("auto == impl 1 today; covered there")
     E = heads * D
     gen = torch.Generator().manual_seed(4)
     qkv = torch.randn(batch, L, 3 * E, generator=gen).bfloat16()
@@ -251,8 +261,8 @@ def test_mha_core(case):
     ref = ref.transpose(1, 2).reshape(batch, L, E)
     d = qkv.cuda()
     o = torch.empty(batch, L, E, dtype=torch.bfloat16, device="cuda")
-    lib.call("ysod_mha_core", lib.ptr(d), lib.ptr(d, E), lib.ptr(d, 2 * E), lib.BF16, batch, L, heads, D, 3 * E, 3 * E, 3 * E,
-             L * 3 * E, L * 3 * E, L * 3 * E, 1.0 / D ** 0.5, lib.ptr(o), E, L * E, lib.stream_ptr())
+    lib.call("ysod_mha_core_ex", lib.ptr(d), lib.ptr(d, E), lib.ptr(d, 2 * E), lib.BF16, batch, L, heads, D, 3 * E, 3 * E, 3 * E,
+             L * 3 * E, L * 3 * E, L * 3 * E, 1.0 / D ** 0.5, lib.ptr(o), E, L * E, impl, lib.stream_ptr())
     torch.cuda.synchronize()
     err = (o.float().cpu() - ref).abs()
     assert bool((err <= 1.0 / 64 * ref.abs() + 1.0 / 64 * ref.abs().max()).all()), err.max().item()

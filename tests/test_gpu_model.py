@@ -140,7 +140,7 @@ def test_sod_fp16_half_mode():
     r_bf = yolo.predict(x.cuda())
     assert len(r16) == len(r_bf) == 2 and sum(len(r) for r in r16) > 0
     # bf16 and fp16 libraries coexist in one process
-    _check(SOD, torch.bfloat16, 1, 128, 2e-2, layer_tol=3e-2)
+    _check(SOD, torch.bfloat16, 2, 160, 2e-2, layer_tol=3e-2)
 
 
 def test_sod_bf16_cuda_core_crosscheck():

@@ -398,11 +398,25 @@ static int mha_core_chunk(const void* q, const void* k, const void* v, int dtype
     return YSOD_OK;
 }
 
-extern "C" int ysod_mha_core(const void* q, const void* k, const void* v, int dtype, int batch, int L, int heads, int D, int ldq,
-                             int ldk, int ldv, long long bsq, long long bsk, long long bsv, float scale, void* out, int ldo,
-                             long long bso, cudaStream_t st) {
+int ysod_mha_tc_launch(const void* q, const void* k, const void* v, int batch, int L, int heads, int D, int ldq, int ldk, int ldv,
+                       long long bsq, long long bsk, long long bsv, float scale, void* out, int ldo, long long bso, cudaStream_t st);
+
+// impl: 0 = auto (see below), 1 = this file's mma.sync / CUDA-core kernels only, 2 = the tcgen05 / TMEM kernel of attention_tc.cu
+// (16-bit storage, head_dim 32 / 64; error if the shape is not covered).
+extern "C" int ysod_mha_core_ex(const void* q, const void* k, const void* v, int dtype, int batch, int L, int heads, int D, int ldq,
+                                int ldk, int ldv, long long bsq, long long bsk, long long bsv, float scale, void* out, int ldo,
+                                long long bso, int impl, cudaStream_t st) {
     YSOD_CHECK_ARG(q && k && v && out, "ysod_mha_core: null pointer");
     YSOD_CHECK_ARG(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "ysod_mha_core: row strides must be multiples of 8");
+    YSOD_CHECK_ARG(impl >= 0 && impl <= 2, "ysod_mha_core_ex: impl %d", impl);
+    // auto: the measured-faster kernel per shape (profiles/r02_ab_attention.json). The first tcgen05 version serialises load -> MMA ->
+    // softmax -> MMA inside a CTA and is 0.4-0.7x the mma.sync kernels on every shape the models launch, so auto keeps those;
+    // the tcgen05 kernel runs on request (impl 2: engine option attn_impl=2).
+    if (impl == 2 && dtype == YSOD_BF16) {
+        const int rc = ysod_mha_tc_launch(q, k, v, batch, L, heads, D, ldq, ldk, ldv, bsq, bsk, bsv, scale, out, ldo, bso, st);
+        if (rc != YSOD_ERR_UNSUPPORTED) return rc;
+    }
+    YSOD_CHECK_ARG(impl != 2, "ysod_mha_core_ex: shape not covered by the tcgen05 kernel (head_dim %d, dtype %d)", D, dtype);
     // gridDim.y / .z are limited to 65535: large window batches (e.g. the unfused P2 SwinBlock at B >= 124) run as chunks of
     // <= 65535 (batch, ...) slices with offset base pointers
     const size_t es = dtype == YSOD_BF16 ? 2 : 4;
@@ -414,4 +428,10 @@ extern "C" int ysod_mha_core(const void* q, const void* k, const void* v, int dt
         if (rc != YSOD_OK) return rc;
     }
     return YSOD_OK;
+}
+
+extern "C" int ysod_mha_core(const void* q, const void* k, const void* v, int dtype, int batch, int L, int heads, int D, int ldq,
+                             int ldk, int ldv, long long bsq, long long bsk, long long bsv, float scale, void* out, int ldo,
+                             long long bso, cudaStream_t st) {
+    return ysod_mha_core_ex(q, k, v, dtype, batch, L, heads, D, ldq, ldk, ldv, bsq, bsk, bsv, scale, out, ldo, bso, 0, st);
 }

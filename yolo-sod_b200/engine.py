@@ -288,8 +288,9 @@ class Program:
         ao = self.new(1, 1, tokens_norm.W, E)
         D = E // heads
         esz = 1
-        self.emit("ysod_mha_core", qkv.ptr(), qkv.slice(E, 2 * E).ptr(), qkv.slice(2 * E, 3 * E).ptr(), self.code, batch, L, heads, D,
-                  3 * E, 3 * E, 3 * E, L * 3 * E * esz, L * 3 * E * esz, L * 3 * E * esz, 1.0 / math.sqrt(D), ao.ptr(), E, L * E)
+        self.emit("ysod_mha_core_ex", qkv.ptr(), qkv.slice(E, 2 * E).ptr(), qkv.slice(2 * E, 3 * E).ptr(), self.code, batch, L, heads, D,
+                  3 * E, 3 * E, 3 * E, L * 3 * E * esz, L * 3 * E * esz, L * 3 * E * esz, 1.0 / math.sqrt(D), ao.ptr(), E, L * E,
+                  self.m.attn_impl, flops=4.0 * batch * heads * L * L * D, desc=f"mha b{batch} L{L} h{heads} d{D}")
         return self.linear(ao, sd[f"{P}.out_proj.weight"], sd[f"{P}.out_proj.bias"], res=res)
 
     def swin(self, x, P, p, out):
@@ -408,8 +409,9 @@ class Program:
         batch = x.N * max(area, 1)
         D = Cc // heads
         ao = self.new(x.N, x.H, x.W, Cc)
-        self.emit("ysod_mha_core", qk.ptr(), qk.slice(Cc, 2 * Cc).ptr(), v.ptr(), self.code, batch, L, heads, D, 2 * Cc, 2 * Cc, Cc,
-                  L * 2 * Cc, L * 2 * Cc, L * Cc, D ** -0.5, ao.ptr(), Cc, L * Cc)
+        self.emit("ysod_mha_core_ex", qk.ptr(), qk.slice(Cc, 2 * Cc).ptr(), v.ptr(), self.code, batch, L, heads, D, 2 * Cc, 2 * Cc, Cc,
+                  L * 2 * Cc, L * 2 * Cc, L * Cc, D ** -0.5, ao.ptr(), Cc, L * Cc, self.m.attn_impl,
+                  flops=4.0 * batch * heads * L * L * D, desc=f"area attention b{batch} L{L} h{heads} d{D}")
         s = self.conv_bn(v, f"{A}.pe", 5, 1, Cc, act=False, res=ao, pad=2)     # pe(v) + attention output
         x1 = self.conv_bn(s, f"{A}.proj", act=False, res=x)                    # x + proj(...)
         h = self.conv_bn(x1, f"{P}.mlp.0")
@@ -873,7 +875,7 @@ class B200DetectionModel:
     """
 
     def __init__(self, cfg, state_dict, dtype=torch.bfloat16, device="cuda:0", use_tc=True, use_graph=True, nc=None,
-                 static_outputs=False, max_programs=8, fuse_swin=True, multi_stream=True, fuse_upsample=True, fuse_decode=True, fuse_se=True, fuse_gate=False):
+                 static_outputs=False, max_programs=8, attn_impl=0, fuse_swin=True, multi_stream=True, fuse_upsample=True, fuse_decode=True, fuse_se=True, fuse_gate=False):
         _lib.require_cuda()
         _lib.load()
         self.spec = cfg if isinstance(cfg, _cfg.ModelSpec) else _cfg.get_spec(cfg, nc=nc)
@@ -888,6 +890,7 @@ class B200DetectionModel:
         self.use_tc = use_tc
         self.use_graph = use_graph
         self.fuse_swin = fuse_swin
+        self.attn_impl = attn_impl   # ysod_mha_core_ex impl: 0 = tcgen05 / TMEM attention core where covered, 1 = mma.sync kernels (A/B)
         self.fuse_upsample = fuse_upsample
         self.fuse_decode = fuse_decode
         self.fuse_se = fuse_se
