@@ -414,6 +414,7 @@ def main():
     h2d_bytes = hx[0].numel() * hx[0].element_size()
     hdet = [torch.empty((B, MAX_DET, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
     consumed = [0.0]
+    pending = []
     ev_in = [torch.cuda.Event() for _ in range(2)]
     ev_free = [torch.cuda.Event() for _ in range(2)]
 
@@ -429,9 +430,14 @@ def main():
         h2d(i + 1)                                      # next step's frames travel while this step computes
         main_stream.wait_event(ev_in[s])
         if is_model:
-            results = yolo.predict(stage[s], conf=CONF, iou=IOU, max_det=MAX_DET)      # the public call (host sync inside)
+            # the public call; stream=True (engine/model.py:501-560) returns a generator of Results: the batch's device work is
+            # enqueued, the host sync happens when the generator is consumed -- one step later, below
+            results = yolo.predict(stage[s], stream=True, conf=CONF, iou=IOU, max_det=MAX_DET)
             det_b, cnt_b = results.det, results.count   # the padded batch the per-image Results are views of
-            n = sum(len(r) for r in results)
+            pending.append(results)
+            n = 0
+            if len(pending) > 1:
+                n = sum(len(r) for r in pending.pop(0))   # consume step i-1's Results (host sync on ITS counts) while step i runs
         else:
             rows = ops.non_max_suppression(stage[s], CONF, IOU, max_det=MAX_DET)       # reference signature (host sync inside)
             det_b, cnt_b = rows.det, rows.count
@@ -457,6 +463,8 @@ def main():
     t0 = time.perf_counter()
     for i in range(3, 3 + k2):
         e2e_ndet = e2e_step(i)
+    while pending:
+        e2e_ndet = sum(len(r) for r in pending.pop(0))   # the last step's Results
     main_stream.synchronize()                           # the last step's D2H
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -484,10 +492,11 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_imgs / e2e_s, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": B * MAX_DET * 6 * 4 + B * 4,
                 "steps": k2, "detections_last_step": e2e_ndet, "batch_per_gpu": B,
-                "note": ("YOLO.predict(uint8 BGR HWC frames) -- the reference's public call (engine/model.py:501-560); frames come from "
-                         "pinned host memory (H2D on a copy stream every step, overlapping the previous step), preprocess is fused into "
-                         "the stem, forward + decode + NMS + clip_boxes, predict() returns per-image Results after its host sync, then "
-                         "one D2H of the detections into pinned host memory" if is_model else
+                "note": ("YOLO.predict(uint8 BGR HWC frames, stream=True) -- the reference's public call (engine/model.py:501-560) in its "
+                         "generator form; frames come from pinned host memory (H2D on a copy stream every step, overlapping the previous "
+                         "step), preprocess is fused into the stem, forward + decode + NMS + clip_boxes; the per-image Results of step i-1 "
+                         "are consumed (host sync on their counts) and its detections read back (one D2H into pinned host memory) while "
+                         "step i runs" if is_model else
                          "ops.non_max_suppression(prediction) with the reference signature: H2D of the (B,14,30000) prediction from pinned "
                          "host memory every step, NMS, host sync (variable-length list), one D2H of the detections")
                         + ("; the step's NCCL all_gather of detections is included" if world > 1 else "")},

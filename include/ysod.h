@@ -60,6 +60,12 @@ int ysod_conv_tc_create(ysod_conv_tc** handle, const void* x, int N, int H, int 
 /* | 0x10 (YSOD_CONV_NO_SPLIT_STAGING): A/B switch for measurements -- keeps the full-tile epilogue staging buffer instead of the
  * one-unit buffer that frees shared memory for a deeper operand ring on deep-K layers (tc_conv.cu). Results are identical. */
 #define YSOD_CONV_NO_SPLIT_STAGING 0x10
+/* | 0x04 (YSOD_CONV_NO_PAIR): A/B switch -- disables the tile-pair plan (two raster-adjacent output tiles share every weight fetch:
+ * tc_conv.cu TcParams::pair) that deep-K layers use by default. Results are identical. */
+#define YSOD_CONV_NO_PAIR 0x04
+/* | 0x08 (YSOD_CONV_FORCE_PAIR): A/B switch -- also pairs tiles on the generic (per-tap) kernel for deep-K layers, where it is off
+ * by default (measured neutral: the steady-state gain is cancelled by the coarser last wave). */
+#define YSOD_CONV_FORCE_PAIR 0x08
 /* | 0x20 (YSOD_CONV_NO_STORE): the plan's own output tensor is not written; only meaningful together with
  * ysod_conv_tc_set_decode -- the predict path consumes `y` alone (detect/predict.py:25-32 takes preds[0]), so the fp32 raw maps
  * Detect.forward also returns (head.py:74) need not be materialised. `out` must still be a valid 16 B aligned device address. */
@@ -125,7 +131,14 @@ int ysod_scale_channels(const void* x, int dtype, int N, int HW, int C, int xcs,
 int ysod_cbam_stats(const void* x, int dtype, int N, int HW, int C, int xcs, const float* gate, float* stats, void* stream);
 int ysod_cbam_apply(const void* x, int dtype, int N, int H, int W, int C, int xcs, const float* gate, const float* stats,
                     const float* wsp, int ks, void* out, int ocs, void* stream);
-int ysod_ca_pool(const void* x, int dtype, int N, int H, int W, int C, int xcs, float* pooled, void* stream);
+/* CBAM spatial attention in one pass (channel statistics of the tile + halo, 7x7 conv, apply): with ysod_gap_partial + ysod_cbam_gate
+ * the block reads the map twice and writes it once; ysod_cbam_stats + ysod_cbam_apply remain as the general / A-B path. */
+int ysod_cbam_spatial(const void* x, int dtype, int N, int H, int W, int C, int xcs, const float* gate, const float* wsp, int ks, void* out,
+                      int ocs, void* stream);
+/* workspace: ysod_ca_pool_workspace_floats() floats (single pass over the map: row means + per-row-block column partials, then a
+ * fixed-order column reduction), or NULL for the two-pass kernel. */
+long long ysod_ca_pool_workspace_floats(int N, int H, int W, int C);
+int ysod_ca_pool(const void* x, int dtype, int N, int H, int W, int C, int xcs, float* pooled, float* workspace, void* stream);
 int ysod_ca_gate(const float* pooled, int N, int H, int W, int C, int mip, const float* w1, const float* b1, const float* wh,
                  const float* bh, const float* ww, const float* bw, float* att, void* stream);
 int ysod_ca_apply(const void* x, int dtype, int N, int H, int W, int C, int xcs, const float* att, void* out, int ocs, void* stream);

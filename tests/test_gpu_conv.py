@@ -64,6 +64,42 @@ def _run_tc(N, H, W, Cin, Cout, k, s, act="silu", res=False, out_f32=False, xcs_
     err = (got - ref).abs()
     bound = tol * ref.abs() + tol * ref.abs().max() + 1e-5
     assert bool((err <= bound).all()), f"tile {list(info)} max err {err.max().item():.5f} (ref max {ref.abs().max().item():.3f})"
+    return ob, list(info)
+
+
+PAIR_CASES = [
+    # deep-K layers take the tile-pair plan (two raster-adjacent tiles share every weight fetch) by default
+    (1, (32, 40, 40, 512, 256, 1, 1), dict(res=True)),              # L17 / L35 cv1: 7 pairs per CTA, 2 N tiles
+    (1, (32, 20, 20, 256, 256, 3, 1), {}),                          # P5 3x3 (generic kernel, ragged 6x20 tiles)
+    (1, (8, 80, 80, 64, 128, 3, 2), {}),                            # stride-2 downsample
+    (1, (6, 20, 20, 1024, 512, 1, 1), {}),                          # 16 K blocks, 4 N tiles
+    (1, (4, 40, 40, 384, 256, 1, 1), dict(act="none", out_f32=True)),
+    (1, (2, 24, 24, 288, 64, 1, 1), {}),                            # Cin % 64 != 0: BK = 32, 9 K blocks, BN = 64
+    (1, (3, 40, 40, 256, 128, 1, 1), {}),                           # odd image count: 3 x 8 spatial tiles is still even
+    (1, (1, 20, 20, 256, 128, 3, 1), {}),                           # 4 tiles in all: two pairs
+    (1, (1, 12, 20, 256, 128, 1, 1), {}),                           # 2 spatial tiles < 4: falls back to single tiles
+    (1, (3, 18, 20, 256, 128, 1, 1), {}),                           # 3 x 3 spatial tiles (odd): falls back to single tiles
+    (2, (32, 40, 40, 128, 128, 3, 1), {}),                          # halo kernel, streamed taps: L8 / L17 / L35 bottleneck convs
+    (2, (8, 80, 80, 128, 128, 3, 1), dict(res=True)),               # Detect cv2/cv3 first conv at P3
+    (2, (4, 40, 40, 256, 128, 3, 1), dict(ocs_extra=64)),           # four channel chunks
+    (2, (1, 32, 32, 256, 64, 3, 1), dict(xcs_extra=64)),            # BN = 64 with streamed taps
+    (2, (1, 48, 24, 128, 128, 3, 1), {}),                           # 3 x 3 tiles (odd): single-tile plan
+]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES, ids=lambda c: f"m{c[0]}-" + "x".join(str(v) for v in c[1]))
+def test_conv_tc_tile_pairs(case):
+    """The pair plan against fp32 F.conv2d, and bit-for-bit against the single-tile plan (YSOD_CONV_NO_PAIR): every accumulator
+    receives the same MMA sequence either way."""
+    mode, dims, kw = case
+    got, info = _run_tc(*dims, mode=mode | 0x08, **kw)    # YSOD_CONV_FORCE_PAIR: the generic kernel pairs only on request
+    ref, info1 = _run_tc(*dims, mode=mode | 0x04, **kw)
+    assert info1[6] < 10000, "NO_PAIR must select the single-tile plan"
+    assert torch.equal(got, ref), f"pair plan {info} differs from single-tile plan {info1}"
+    if "falls back" not in "".join([]) and dims in [(1, 12, 20, 256, 128, 1, 1), (3, 18, 20, 256, 128, 1, 1), (1, 48, 24, 128, 128, 3, 1)]:
+        assert info[6] < 10000, "odd / tiny tile counts must not pair"
+    elif dims[0] >= 2 or dims[1] >= 20:
+        assert info[6] >= 10000, f"expected the pair plan, got {info}"
 
 
 CASES = [

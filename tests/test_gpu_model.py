@@ -274,6 +274,13 @@ def test_predict_end_to_end_matches_oracle_nms():
         w[:, [1, 3]] = w[:, [1, 3]].clip(0, 320)
         assert np.array_equal(r.boxes.data.cpu().numpy(), w)
     assert sum(len(r) for r in res) > 0, "synthetic weights must produce detections"
+    # stream=True (engine/model.py:501-560): a generator over the same Results; consuming it after a later batch was submitted
+    # must still give this batch's detections (at most 4 unconsumed generators may be outstanding: the count ring)
+    g1 = yolo.predict(x.cuda(), stream=True, conf=0.25, iou=0.7, max_det=300)
+    g2 = yolo.predict(synth.synth_images(2, 320, seed=22).cuda(), stream=True)
+    for r, w in zip(list(g1), res):
+        assert torch.equal(r.boxes.data, w.boxes.data)
+    assert len(list(g2)) == 2
 
 
 def test_fused_swin_block_matches_oracle_and_unfused_path():
@@ -297,8 +304,8 @@ def test_fused_swin_block_matches_oracle_and_unfused_path():
 def test_fused_epilogues_equal_separate_kernels():
     """Conv+Upsample in one launch and the Detect decode inside the final head conv's epilogue are pure re-schedulings: the raw maps
     are bit-identical to the separate-kernel program and y agrees to fp32 rounding (expression order is the same; only FMA contraction may differ)."""
-    spec, sd, fused = _build(SOD, torch.bfloat16, fuse_gate=True)     # + pool and gate MLP in one launch (ysod_gap_gate)
-    _, _, plain = _build(SOD, torch.bfloat16, fuse_upsample=False, fuse_decode=False, fuse_gate=False)
+    spec, sd, fused = _build(SOD, torch.bfloat16, fuse_gate=True, fuse_cbam=True)     # + pool and gate MLP in one launch (ysod_gap_gate), single-pass CBAM spatial stage
+    _, _, plain = _build(SOD, torch.bfloat16, fuse_upsample=False, fuse_decode=False, fuse_gate=False, fuse_cbam=False)   # + CBAM as stats / apply passes
     x = synth.synth_images(2, 320, seed=23).cuda()
     y1, r1 = fused(x)
     y2, r2 = plain(x)

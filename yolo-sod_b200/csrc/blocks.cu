@@ -427,6 +427,14 @@ cbam_apply_tile_kernel(const T* __restrict__ x, int H, int W, int C, int xcs, co
     __shared__ float sa_s[TS * TS];
     const int n = blockIdx.z, h0 = blockIdx.y * TS, w0 = blockIdx.x * TS;
     const int tid = threadIdx.x;
+    {   // request the tile's activations now: they travel to L2 while the statistics halo is staged and the 7x7 filter runs
+        const int lpp = (C * (int)sizeof(T) + 127) / 128;           // 128 B lines per pixel
+        for (int i = tid; i < TS * TS * lpp; i += 256) {
+            const int pl = i / lpp, l = i - pl * lpp;
+            const int h = h0 + (pl >> 4), w = w0 + (pl & 15);
+            if (h < H && w < W) ysod_prefetch_l2(reinterpret_cast<const char*>(x + (((size_t)n * H + h) * W + w) * xcs) + l * 128);
+        }
+    }
     if (tid < 98) swsp[tid] = wsp[tid];
     for (int i = tid; i < PS * PS; i += 256) {
         const int ih = h0 - HALO + i / PS, iw = w0 - HALO + i % PS;
@@ -483,6 +491,180 @@ cbam_apply_tile_kernel(const T* __restrict__ x, int H, int W, int C, int xcs, co
             ysod_vec8<T>::store(on + (size_t)gp[u] * ocs, v[u]);
         }
     }
+}
+
+// CBAM spatial attention in ONE pass over the map (cbam_block.py:25-55): a CTA owns a 32 x 16 pixel tile of one image. It computes the
+// channel statistics (mean_c, max_c of x * gate) of the tile plus its 3-pixel halo straight from x (38 x 22 pixels; the halo re-reads
+// are L2 hits: neighbouring tiles run at the same time), evaluates sigmoid(conv7x7([mean, max])) for the tile from shared memory and
+// streams x * gate * sa out. With the pooling pass that feeds the channel gate this makes CBAM 2 reads + 1 write of the map (the floor:
+// the gate needs the whole map first) instead of 3 + 1, and the statistics map never exists in HBM. The per-pixel arithmetic is that
+// of cbam_stats_img_kernel + cbam_apply_tile_kernel, expression for expression, so the result is bit-identical to the two-pass path.
+template <typename T>
+__global__ void __launch_bounds__(256, 3)
+cbam_spatial_fused_kernel(const T* __restrict__ x, int H, int W, int C, int xcs, const float* __restrict__ gate,
+                          const float* __restrict__ wsp, T* __restrict__ out, int ocs) {
+    ysod_pdl_sync();
+    constexpr int TW_ = 32, TH_ = 16, HALO = 3, PW_ = TW_ + 2 * HALO, PH_ = TH_ + 2 * HALO, NP = PW_ * PH_;   // 38 x 22 = 836
+    __shared__ float2 st[NP];
+    __shared__ float swsp[2 * 49];
+    __shared__ float sa_s[TW_ * TH_];
+    const int n = blockIdx.z, h0 = blockIdx.y * TH_, w0 = blockIdx.x * TW_;
+    const int tid = threadIdx.x;
+    if (tid < 98) swsp[tid] = wsp[tid];
+    const int c8n = C >> 3;                      // power of two <= 32 (host check)
+    const int lg = __ffs(c8n) - 1;
+    const int gl = tid & (c8n - 1), grp = tid >> lg, ngr = 256 >> lg;
+    float gg[8];
+    {
+        const float* gn = gate + (size_t)n * C + gl * 8;
+        const float4 g0 = *reinterpret_cast<const float4*>(gn), g1 = *reinterpret_cast<const float4*>(gn + 4);
+        gg[0] = g0.x; gg[1] = g0.y; gg[2] = g0.z; gg[3] = g0.w; gg[4] = g1.x; gg[5] = g1.y; gg[6] = g1.z; gg[7] = g1.w;
+    }
+    const T* xn = x + (size_t)n * H * W * xcs + gl * 8;
+    const float inv_c = 1.0f / (float)C;
+    // ---- statistics of the tile + halo: a group of c8n lanes per pixel, four pixels in flight per group (uniform trip count: the
+    //      shuffles stay converged); pixels outside the image are the zero padding of the 7x7 conv
+    const int iters = (NP + 4 * ngr - 1) / (4 * ngr);
+    for (int it = 0; it < iters; ++it) {
+        const int pb = grp + it * 4 * ngr;
+        float v[4][8];
+        bool in[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = pb + u * ngr;
+            const int ih = h0 - HALO + i / PW_, iw = w0 - HALO + i % PW_;
+            in[u] = i < NP && ih >= 0 && ih < H && iw >= 0 && iw < W;
+            if (in[u]) ysod_vec8<T>::load(xn + ((size_t)ih * W + iw) * xcs, v[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = pb + u * ngr;
+            float su = 0.f, mx = -INFINITY;
+            if (in[u]) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float tv = v[u][e] * gg[e];
+                    su += tv;
+                    mx = fmaxf(mx, tv);
+                }
+            }
+            for (int o = c8n >> 1; o > 0; o >>= 1) {
+                su += __shfl_xor_sync(0xffffffffu, su, o);
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            }
+            if (i < NP && gl == 0) st[i] = in[u] ? make_float2(su * inv_c, mx) : make_float2(0.f, 0.f);
+        }
+    }
+    __syncthreads();
+    // ---- sa = sigmoid(conv7x7([mean, max])): two pixels per thread
+#pragma unroll 1
+    for (int k = 0; k < 2; ++k) {
+        const int pl = tid + k * 256;
+        const int ph = pl >> 5, pw = pl & 31;
+        float a = 0.f;
+#pragma unroll
+        for (int r = 0; r < 7; ++r)
+#pragma unroll
+            for (int q = 0; q < 7; ++q) {
+                const float2 sv = st[(ph + r) * PW_ + pw + q];
+                a = fmaf(swsp[r * 7 + q], sv.x, a);
+                a = fmaf(swsp[49 + r * 7 + q], sv.y, a);
+            }
+        sa_s[pl] = ysod_sigmoid(a);
+    }
+    __syncthreads();
+    // ---- out = x * gate * sa for the tile (x was read a moment ago by this CTA: L1 / L2 hits), four 16 B loads in flight
+    T* on = out + (size_t)n * H * W * ocs + gl * 8;
+    const int total = TW_ * TH_ * c8n;
+    for (int base = tid; base < total; base += 4 * 256) {
+        float v[4][8];
+        bool ok[4];
+        int pl[4], gp[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = base + u * 256;
+            pl[u] = i >> lg;
+            const int h = h0 + (pl[u] >> 5), w = w0 + (pl[u] & 31);
+            gp[u] = h * W + w;
+            ok[u] = (i < total) && h < H && w < W;
+            if (ok[u]) ysod_vec8<T>::load(xn + (size_t)gp[u] * xcs, v[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (!ok[u]) continue;
+            const float sa = sa_s[pl[u]];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[u][e] *= gg[e] * sa;
+            ysod_vec8<T>::store(on + (size_t)gp[u] * ocs, v[u]);
+        }
+    }
+}
+
+// CoordAtt strip pools in ONE pass over the map (ca_block.py:42-45): a CTA owns 16 rows of one image; thread = (8-channel group,
+// column lane). Every pixel is read once and added to its row sum (reduced over the column lanes through shared memory, fixed
+// order) and to its column partial sum (kept in registers over the CTA's 16 rows, written as part[n][row block][w][c]); a second
+// tiny launch adds the row blocks in fixed order. Deterministic (no float atomics). The former two-pass kernel ran 16 threads per
+// CTA with one load in flight and read the map twice (25 % of HBM peak).
+template <typename T, int WL>
+__global__ void __launch_bounds__(256)
+ca_pool_rows_kernel(const T* __restrict__ x, int H, int W, int C, int xcs, float* __restrict__ pooled, float* __restrict__ part, int RB) {
+    ysod_pdl_sync();
+    constexpr int ROWS = 16, MAXW = 8;           // a column lane owns columns wl, wl + WL, ... (at most MAXW of them: W <= WL * MAXW)
+    extern __shared__ float sm[];                // [WL][C] row partials
+    const int n = blockIdx.y, rb = blockIdx.x;
+    const int c8n = C >> 3;                      // 256 / WL channel groups
+    const int cg = threadIdx.x % c8n, wl = threadIdx.x / c8n;
+    const int r0 = rb * ROWS, r1 = min(H, r0 + ROWS);
+    float col[MAXW][8];
+#pragma unroll
+    for (int j = 0; j < MAXW; ++j)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) col[j][e] = 0.f;
+    const T* xb = x + (size_t)n * H * W * xcs + cg * 8;
+    const float inv_w = 1.0f / (float)W;
+    for (int r = r0; r < r1; ++r) {
+        float v[MAXW][8];
+#pragma unroll
+        for (int j = 0; j < MAXW; ++j) {          // all of a row's loads of this thread are in flight together
+            const int w = wl + j * WL;
+            if (w < W) ysod_vec8<T>::load(xb + ((size_t)r * W + w) * xcs, v[j]);
+        }
+        float rs[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) rs[e] = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAXW; ++j) {
+            const int w = wl + j * WL;
+            if (w < W) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { rs[e] += v[j][e]; col[j][e] += v[j][e]; }
+            }
+        }
+        __syncthreads();                          // the previous row's partials have been consumed
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sm[wl * C + cg * 8 + e] = rs[e];
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += 256) {
+            float a = 0.f;
+            for (int q = 0; q < WL; ++q) a += sm[q * C + c];
+            pooled[((size_t)n * (H + W) + r) * C + c] = a * inv_w;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < MAXW; ++j) {
+        const int w = wl + j * WL;
+        if (w < W) ysod_vec8<float>::store(part + (((size_t)n * RB + rb) * W + w) * C + cg * 8, col[j]);
+    }
+}
+// pooled[n][H + w][c] = (sum over row blocks of part[n][rb][w][c]) / H
+__global__ void ca_pool_cols_kernel(const float* __restrict__ part, int H, int W, int C, int RB, float* __restrict__ pooled, int total) {
+    ysod_pdl_sync();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = i % C, w = (i / C) % W, n = i / (C * W);
+    float a = 0.f;
+    for (int rb = 0; rb < RB; ++rb) a += part[(((size_t)n * RB + rb) * W + w) * C + c];
+    pooled[((size_t)n * (H + W) + H + w) * C + c] = a / (float)H;
 }
 
 // CoordAtt strip pools -> pooled[n][H + W][C] fp32: rows [0,H) = mean over w, rows [H,H+W) = mean over h (ca_block.py:42-45)
@@ -1177,8 +1359,46 @@ int ysod_cbam_apply(const void* x, int dtype, int N, int H, int W, int C, int xc
     return YSOD_OK;
 }
 
-int ysod_ca_pool(const void* x, int dtype, int N, int H, int W, int C, int xcs, float* pooled, cudaStream_t st) {
+// CBAM spatial attention (statistics + 7x7 conv + apply) in one pass over the map: see cbam_spatial_fused_kernel. Covers kernel_size 7
+// (cbam_block.py:27) and C/8 a power of two <= 32; returns YSOD_ERR_UNSUPPORTED otherwise (callers fall back to stats + apply).
+int ysod_cbam_spatial(const void* x, int dtype, int N, int H, int W, int C, int xcs, const float* gate, const float* wsp, int ks, void* out,
+                      int ocs, cudaStream_t st) {
+    YSOD_CHECK_ARG(x && gate && wsp && out && C % 8 == 0 && xcs % 8 == 0 && ocs % 8 == 0, "ysod_cbam_spatial: bad args");
+    const int c8n = C / 8;
+    if (ks != 7 || (c8n & (c8n - 1)) != 0 || c8n > 32 || N > 65535) {
+        ysod_set_error("ysod_cbam_spatial: unsupported (ks %d, C %d)", ks, C);
+        return YSOD_ERR_UNSUPPORTED;
+    }
+    dim3 grid(ysod_cdiv(W, 32), ysod_cdiv(H, 16), N);
+    YSOD_DISPATCH(dtype, (ysod_launch(cbam_spatial_fused_kernel<T>, grid, 256, 0, st, (const T*)x, H, W, C, xcs, gate, wsp, (T*)out, ocs)));
+    YSOD_LAUNCH_CHECK();
+    return YSOD_OK;
+}
+
+// workspace floats needed by ysod_ca_pool's single-pass plan (0: the plan does not apply and the two-pass kernel runs)
+long long ysod_ca_pool_workspace_floats(int N, int H, int W, int C) {
+    const int c8n = C / 8;
+    if (C % 8 != 0 || c8n < 1 || 256 % c8n != 0) return 0;
+    const int WL = 256 / c8n;
+    if (!(WL == 8 || WL == 16 || WL == 32) || W > WL * 8) return 0;
+    return (long long)N * ysod_cdiv(H, 16) * W * C;
+}
+
+int ysod_ca_pool(const void* x, int dtype, int N, int H, int W, int C, int xcs, float* pooled, float* workspace, cudaStream_t st) {
     YSOD_CHECK_ARG(x && pooled && C % 8 == 0 && xcs % 8 == 0, "ysod_ca_pool: bad args");
+    if (workspace && ysod_ca_pool_workspace_floats(N, H, W, C) > 0 && N <= 65535) {
+        const int WL = 256 / (C / 8), RB = ysod_cdiv(H, 16);
+        dim3 g2(RB, N);
+        const size_t smem = (size_t)WL * C * sizeof(float);
+        if (WL == 8) YSOD_DISPATCH(dtype, (ysod_launch(ca_pool_rows_kernel<T, 8>, g2, 256, smem, st, (const T*)x, H, W, C, xcs, pooled, workspace, RB)));
+        else if (WL == 16) YSOD_DISPATCH(dtype, (ysod_launch(ca_pool_rows_kernel<T, 16>, g2, 256, smem, st, (const T*)x, H, W, C, xcs, pooled, workspace, RB)));
+        else YSOD_DISPATCH(dtype, (ysod_launch(ca_pool_rows_kernel<T, 32>, g2, 256, smem, st, (const T*)x, H, W, C, xcs, pooled, workspace, RB)));
+        YSOD_LAUNCH_CHECK();
+        const int total = N * W * C;
+        ysod_launch(ca_pool_cols_kernel, ysod_cdiv(total, 256), 256, 0, st, (const float*)workspace, H, W, C, RB, pooled, total);
+        YSOD_LAUNCH_CHECK();
+        return YSOD_OK;
+    }
     dim3 grid(H + W, N);
     const int threads = (C / 8) < 32 ? 32 : ((C / 8 + 31) / 32) * 32;
     YSOD_DISPATCH(dtype, (ysod_launch(ca_pool_kernel<T>, grid, threads > 256 ? 256 : threads, 0, st, (const T*)x, H, W, C, xcs, pooled)));

@@ -30,6 +30,11 @@ struct TcParams {
     int N, Ho, Wo, TH, TW, tiles_h, tiles_w;
     int Cin, ksize, stride, pad;
     int BN, BK, stages, tmem_cols, num_k, n_tiles;
+    int step2_tw, step2_th, step2_img, step2_nt;   // the same for a stride of 2 * gridDim.x tiles (epilogue groups; tile pairs)
+    int pair;        // 1: the CTA works on PAIRS of raster-adjacent output tiles (2c, 2c+1, then + 2*gridDim.x ...) that share every
+                     // weight (B) fetch: each B tile / tap landed in shared memory is multiplied with both tiles' A operands into two
+                     // TMEM accumulators. Deep layers are bound by the chip-wide L2 -> SM throughput (~12 TB/s), not by the tensor
+                     // pipe; sharing B cuts the bytes per MMA by 25 % (generic stages) to 45 % (streamed 3x3 taps).
     int step_tw, step_th, step_img, step_nt;   // gridDim.x decomposed in the mixed radix (tiles_w, tiles_h, N): per-tile coordinate update without divisions
     int issuers;     // MMA issuer threads: 2 = tiles alternate between two issuers on separate sub-rings (short tiles), 1 = one issuer, whole ring
     int kgroup;      // generic mode: K blocks (slots) per pipeline stage = per mbarrier handshake / per elected issue burst
@@ -234,6 +239,15 @@ struct TileIter {
         img += p.step_img; if (img >= p.N) { img -= p.N; ++nt; }
         nt += p.step_nt;
     }
+    __device__ __forceinline__ void step2(const TcParams& p) {   // 2 * gridDim.x tiles ahead
+        tw += p.step2_tw; if (tw >= p.tiles_w) { tw -= p.tiles_w; ++th; }
+        th += p.step2_th; if (th >= p.tiles_h) { th -= p.tiles_h; ++img; }
+        img += p.step2_img; if (img >= p.N) { img -= p.N; ++nt; }
+        nt += p.step2_nt;
+    }
+    __device__ __forceinline__ void step1(const TcParams& p) {   // the next tile in raster order
+        if (++tw >= p.tiles_w) { tw = 0; if (++th >= p.tiles_h) { th = 0; if (++img >= p.N) { img = 0; ++nt; } } }
+    }
     __device__ __forceinline__ bool valid(const TcParams& p) const { return nt < p.n_tiles; }
 };
 
@@ -313,7 +327,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (elect_one()) {
             const int cchunks = p.cchunks;
             const bool two = p.issuers == 2;
-            if (!HALO) {
+            if (!HALO && p.pair) {
+                // tile pairs: stage = {A of tile 0, A of tile 1, B}; A slots 2s / 2s + 1, B slot s
+                const uint32_t tx = 2u * p.a_tx + p.b_bytes;
+                const int nstages = p.stages, num_k = p.num_k, BK = p.BK, ksize = p.ksize, cstride = p.stride, pad = p.pad, Cin = p.Cin;
+                int st = 0;
+                uint32_t ph = 0;
+                TileIter t0;
+                t0.init(2 * blockIdx.x, p);
+                pdl_wait();
+                for (int tcount = 0; t0.valid(p); t0.step2(p), ++tcount) {
+                    TileIter t1 = t0;
+                    t1.step1(p);
+                    const int y0 = t0.th * p.TH * cstride - pad, x0 = t0.tw * p.TW * cstride - pad;
+                    const int y1 = t1.th * p.TH * cstride - pad, x1 = t1.tw * p.TW * cstride - pad;
+                    const int n0 = t0.nt * p.BN;
+                    int tap = 0, cc = 0, r = 0, s = 0;
+                    for (int kb = 0; kb < num_k; ++kb) {
+                        mbar_wait(emptyA + 8u * st, ph ^ 1u);
+                        trace(tr, 0, 1, tcount, kb, tcnt);
+                        const uint32_t full = fullA + 8u * st;
+                        if (p.debug & 2) mbar_arrive(full);
+                        else {
+                            mbar_expect_tx(full, tx);
+                            tma_load_4d(a_base + (uint32_t)(2 * st) * p.a_bytes, &tmA, full, cc * BK, x0 + s, y0 + r, t0.img);
+                            tma_load_4d(a_base + (uint32_t)(2 * st + 1) * p.a_bytes, &tmA, full, cc * BK, x1 + s, y1 + r, t1.img);
+                            tma_load_2d(b_base + (uint32_t)st * p.b_bytes, &tmB, full, tap * Cin + cc * BK, n0);
+                        }
+                        if (++cc == p.cchunks) {
+                            cc = 0; ++tap;
+                            if (++s == ksize) { s = 0; ++r; }
+                        }
+                        if (++st == nstages) { st = 0; ph ^= 1u; }
+                    }
+                }
+            } else if (!HALO) {
                 const uint32_t tx = p.a_tx + p.b_bytes;
                 const int nstages = p.stages, G = p.kgroup, ngroups = p.num_k / p.kgroup, BK = p.BK, ksize = p.ksize, cstride = p.stride, pad = p.pad, Cin = p.Cin;
                 // two sub-rings of `nstages` stages: even tiles (issuer 0) use stages [0, nstages), odd tiles [nstages, 2*nstages)
@@ -373,6 +421,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     first = false;
                 }
                 pdl_wait();   // the input activations are written by the previous kernel
+                if (p.pair) {
+                    // tile pairs with streamed taps: per 64-channel chunk the two tiles' halo copies, then the nine taps ONCE
+                    TileIter t0;
+                    t0.init(2 * blockIdx.x, p);
+                    for (int tcount = 0; t0.valid(p); t0.step2(p), ++tcount) {
+                        TileIter t1 = t0;
+                        t1.step1(p);
+                        const int n0 = t0.nt * p.BN;
+                        for (int cc = 0; cc < cchunks; ++cc) {
+#pragma unroll
+                            for (int half = 0; half < 2; ++half) {
+                                const TileIter& tt = half ? t1 : t0;
+                                mbar_wait(emptyA + 8u * sa_c, pa_c ^ 1u);
+                                trace(tr, 0, 1, tcount, cc * 2 + half, tcnt);
+                                if (p.debug & 2) mbar_arrive(fullA + 8u * sa_c);
+                                else {
+                                    mbar_expect_tx(fullA + 8u * sa_c, p.a_tx);
+                                    tma_load_4d(a_base + (uint32_t)sa_c * p.a_bytes, &tmA, fullA + 8u * sa_c, cc * p.BK, tt.tw * 8 - 1, tt.th * 16 - 1, tt.img);
+                                }
+                                if (++sa_c == ah) { sa_c = 0; pa_c ^= 1u; }
+                            }
+                            for (int s = 0; s < 3; ++s) {
+                                for (int r = 0; r < 3; ++r) {
+                                    mbar_wait(emptyB + 8u * sb_c, pb_c ^ 1u);
+                                    mbar_expect_tx(fullB + 8u * sb_c, p.b_bytes);
+                                    tma_load_2d(b_base + (uint32_t)sb_c * p.b_bytes, &tmB, fullB + 8u * sb_c, (r * 3 + s) * p.Cin + cc * p.BK, n0);
+                                    if (++sb_c == bh) { sb_c = 0; pb_c ^= 1u; }
+                                }
+                            }
+                        }
+                    }
+                } else
                 for (int tcount = 0; ti.valid(p); ti.step(p), ++tcount) {
                     const int img = ti.img;
                     const int oh0 = ti.th * 16, ow0 = ti.tw * 8;
@@ -426,7 +506,109 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             TileIter ti;
             ti.init(blockIdx.x, p);
             if (me) ti.step(p);
-            if (!HALO) {
+            if (p.pair) {
+                // ===== tile pairs (single issuer): accumulators 2*asel (tile 0) and 2*asel + 1 (tile 1) of the pair; every B operand
+                //       landed in shared memory feeds both
+                TileIter t0;
+                t0.init(2 * blockIdx.x, p);
+                const int ksteps = p.BK >> 4;
+                int asel = 0;
+                if (!HALO) {
+                    const int nstages = p.stages, num_k = p.num_k;
+                    int st = 0;
+                    uint32_t phase = 0;
+                    for (int tcount = 0; t0.valid(p); t0.step2(p), ++tcount) {
+                        const uint32_t d0 = tmem_acc + (uint32_t)(2 * asel * BN), d1 = d0 + (uint32_t)BN;
+                        mbar_wait(tempty_bar + 8u * (2 * asel), acc_phase ^ 1u);
+                        mbar_wait(tempty_bar + 8u * (2 * asel + 1), acc_phase ^ 1u);
+                        trace(tr, trole, 1, tcount, 0, tcnt);
+                        tc_fence_after();
+                        for (int kb = 0; kb < num_k; ++kb) {
+                            mbar_wait(fullA + 8u * st, phase);
+                            trace(tr, trole, 2, tcount, kb, tcnt);
+                            tc_fence_after();
+                            const uint32_t a0 = umma_lo(a_base + (uint32_t)(2 * st) * a_bytes), a1 = umma_lo(a_base + (uint32_t)(2 * st + 1) * a_bytes);
+                            const uint32_t b_lo = umma_lo(b_base + (uint32_t)st * b_bytes);
+                            if (!no_mma) {
+#pragma unroll 4
+                                for (int k = 0; k < ksteps; ++k)
+                                    tc_mma_bf16(d0, umma_desc(desc_hi, a0 + 2u * k), umma_desc(desc_hi, b_lo + 2u * k), idesc, (uint32_t)((kb | k) != 0));
+#pragma unroll 4
+                                for (int k = 0; k < ksteps; ++k)
+                                    tc_mma_bf16(d1, umma_desc(desc_hi, a1 + 2u * k), umma_desc(desc_hi, b_lo + 2u * k), idesc, (uint32_t)((kb | k) != 0));
+                            }
+                            tc_commit(emptyA + 8u * st);
+                            if (kb == num_k - 1) {
+                                tc_commit(tfull_bar + 8u * (2 * asel));
+                                tc_commit(tfull_bar + 8u * (2 * asel + 1));
+                            }
+                            trace(tr, trole, 3, tcount, kb, tcnt);
+                            if (++st == nstages) { st = 0; phase ^= 1u; }
+                        }
+                        asel ^= 1;
+                        if (asel == 0) acc_phase ^= 1u;
+                    }
+                } else {
+                    const int a_stages = p.a_stages, b_stages = p.b_stages, cchunks = p.cchunks;
+                    const uint32_t row_b = 2u * (uint32_t)p.BK;
+                    const uint32_t halo_desc_hi = ((10u * row_b) >> 4) | (1u << 14) | ((p.BK == 64 ? 2u : 4u) << 29);   // SBO = 10 pixels
+                    int sa = 0, sb = 0;
+                    uint32_t pa = 0, pb = 0;
+                    for (int tcount = 0; t0.valid(p); t0.step2(p), ++tcount) {
+                        const uint32_t d0 = tmem_acc + (uint32_t)(2 * asel * BN), d1 = d0 + (uint32_t)BN;
+                        mbar_wait(tempty_bar + 8u * (2 * asel), acc_phase ^ 1u);
+                        mbar_wait(tempty_bar + 8u * (2 * asel + 1), acc_phase ^ 1u);
+                        trace(tr, trole, 1, tcount, 0, tcnt);
+                        tc_fence_after();
+                        for (int cc = 0; cc < cchunks; ++cc) {
+                            const int as0 = sa;
+                            mbar_wait(fullA + 8u * as0, pa);
+                            if (++sa == a_stages) { sa = 0; pa ^= 1u; }
+                            const int as1 = sa;
+                            mbar_wait(fullA + 8u * as1, pa);
+                            if (++sa == a_stages) { sa = 0; pa ^= 1u; }
+                            const uint32_t a0_addr = a_base + (uint32_t)as0 * a_bytes, a1_addr = a_base + (uint32_t)as1 * a_bytes;
+                            for (int s = 0; s < 3; ++s) {
+#pragma unroll
+                                for (int r = 0; r < 3; ++r) mbar_wait(fullB + 8u * (sb + r), pb);
+                                tc_fence_after();
+                                trace(tr, trole, 2, tcount, cc * 3 + s, tcnt);
+                                if (!no_mma) {
+#pragma unroll
+                                    for (int half = 0; half < 2; ++half) {
+                                        const uint32_t dd = half ? d1 : d0;
+                                        const uint32_t aa = half ? a1_addr : a0_addr;
+#pragma unroll
+                                        for (int r = 0; r < 3; ++r) {
+                                            const uint32_t a_lo = umma_lo(aa + (uint32_t)(r * 10 + s) * row_b);
+                                            const uint32_t b_lo = umma_lo(b_base + (uint32_t)(sb + r) * b_bytes);
+#pragma unroll 4
+                                            for (int k = 0; k < ksteps; ++k)
+                                                tc_mma_bf16(dd, umma_desc(halo_desc_hi, a_lo + 2u * k), umma_desc(desc_hi, b_lo + 2u * k), idesc,
+                                                            (uint32_t)((cc | s | r | k) != 0));
+                                        }
+                                    }
+                                }
+#pragma unroll
+                                for (int r = 0; r < 3; ++r) tc_commit(emptyB + 8u * (sb + r));
+                                sb += 3;
+                                if (sb == b_stages) { sb = 0; pb ^= 1u; }
+                                if (s == 2) {
+                                    tc_commit(emptyA + 8u * as0);
+                                    tc_commit(emptyA + 8u * as1);
+                                    if (cc == cchunks - 1) {
+                                        tc_commit(tfull_bar + 8u * (2 * asel));
+                                        tc_commit(tfull_bar + 8u * (2 * asel + 1));
+                                    }
+                                }
+                                trace(tr, trole, 3, tcount, cc * 3 + s, tcnt);
+                            }
+                        }
+                        asel ^= 1;
+                        if (asel == 0) acc_phase ^= 1u;
+                    }
+                }
+            } else if (!HALO) {
                 const int nstages = p.stages, G = p.kgroup, ngroups = p.num_k / p.kgroup;
                 const bool k4 = (p.BK == 64);
                 int st = 0;
@@ -566,10 +748,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t swz_x = (row0 >> 7) & swz_mask;   // swizzle XOR term of this thread's staging row
         uint32_t acc_phase = 0;
         TileIter ti;
-        ti.init(blockIdx.x, p);
-        if (grp) ti.step(p);
+        ti.init(p.pair ? 2 * blockIdx.x + grp : blockIdx.x, p);   // pairs: group g owns tile g of every pair of this CTA
+        if (!p.pair && grp) ti.step(p);
         if (res != nullptr) pdl_wait();   // the residual may be the previous kernel's output
-        for (int tcount = grp; ti.valid(p); ti.step(p), ti.step(p), tcount += 2) {
+        for (int tcount = grp; ti.valid(p); ti.step2(p), tcount += 2) {
             const int img = ti.img;
             const int oh0 = ti.th * TH, ow0 = ti.tw * TW;
             const int n0 = ti.nt * BN;
@@ -837,7 +1019,9 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
     const bool img_w = (mode & 0x80) != 0;
     const int split_exp = mode & 0x10;
     const bool no_store = (mode & 0x20) != 0;
-    mode &= 0x0f;
+    const bool no_pair = (mode & 0x04) != 0;
+    const bool force_pair = (mode & 0x08) != 0;
+    mode &= 0x03;
     if (img_w) {
         YSOD_CHECK_ARG(mode != 2, "ysod_conv_tc_create_ex: per-image weights need the generic kernel (resident taps are shared by all images)");
         mode = 1;
@@ -930,13 +1114,37 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
     if (!halo) {
         // Pipeline stage = G K-blocks ("slots") behind one mbarrier pair: with narrow N an MMA retires in ~N/2 cycles, so a
         // stage must carry enough MMAs (>= ~512 tensor-pipe cycles) to amortise the issuer's per-handshake cost.
+        // Tile pairs (see TcParams::pair): deep-K layers whose operand stream, not the tensor pipe, bounds them. Needs an even number
+        // of spatial tiles per N tile (a pair never straddles two weight tiles), shared (not per-image) weights, >= 2 tiles per CTA.
+        const long long spatial = (long long)N * p.tiles_h * p.tiles_w;
+        // Measured (profiles/r02_conv_pair_ab.txt): the generic kernel's steady state gains 24 % per tile (512->256 1x1 @40^2: 4870 ->
+        // 3700 cycles), but these launches are 25-35 us long with ~3 pairs per CTA, so the coarser tail (pairs quantise the last wave
+        // twice as hard) and the larger first stage cancel it: off unless forced (YSOD_CONV_FORCE_PAIR). The streamed-tap 3x3 plan
+        // below, where the shared operand is 85 % of the bytes, keeps it on.
+        p.pair = (force_pair && !no_pair && !img_w && p.num_k >= 4 && BN >= 64 && spatial % 2 == 0 && spatial * p.n_tiles >= 4) ? 1 : 0;
+        if (p.pair) {
+            const uint32_t stage_bytes = 2u * p.a_bytes + p.b_bytes;
+            int stages = (int)((224u * 1024u - fixed) / stage_bytes);
+            if (stages > 6) stages = 6;
+            if (stages < 2) p.pair = 0;
+            else {
+                p.issuers = 1;
+                p.kgroup = 1;
+                p.sgroup = 1;
+                p.stages = p.a_stages = p.b_stages = stages;
+                p.a_slots = 2 * stages;
+                p.b_slots = stages;
+                ring_bytes = (size_t)stages * stage_bytes;
+                nbar = 2 * p.a_slots + 2 * p.b_slots;
+            }
+        }
         const uint32_t slot_bytes = p.a_bytes + p.b_bytes;
         const uint32_t budget = 224u * 1024u - fixed;   // one fat CTA per SM
         int slots = (int)(budget / slot_bytes);
         if (slots > 16) slots = 16;
         const int kb_cycles = (p.BK / 16) * (BN / 2);
         // two issuers only pay off for tiles with a single short burst (1x1 convs with K <= 64..128)
-        p.issuers = (p.num_k * kb_cycles <= 512 && slots >= 2 * p.num_k) ? 2 : 1;
+        if (!p.pair) p.issuers = (p.num_k * kb_cycles <= 512 && slots >= 2 * p.num_k) ? 2 : 1;
         const int rings = p.issuers;
         int gmax = 512 / kb_cycles;
         if (gmax < 1) gmax = 1;
@@ -949,12 +1157,14 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
         int stages = slots / (rings * G);
         if (stages > 8) stages = 8;
         if (stages < 1) stages = 1;
-        p.kgroup = G;
-        p.sgroup = 1;
-        p.stages = p.a_stages = p.b_stages = stages;
-        p.a_slots = p.b_slots = rings * stages * G;
-        ring_bytes = (size_t)p.a_slots * slot_bytes;
-        nbar = 4 * p.a_slots;
+        if (!p.pair) {
+            p.kgroup = G;
+            p.sgroup = 1;
+            p.stages = p.a_stages = p.b_stages = stages;
+            p.a_slots = p.b_slots = rings * stages * G;
+            ring_bytes = (size_t)p.a_slots * slot_bytes;
+            nbar = 4 * p.a_slots;
+        }
     } else {
         p.a_tx = 18u * 10u * 2u * (uint32_t)p.BK;     // one halo copy: 18 rows x 10 px x BK ch bf16 (22.5 KB / 11.25 KB)
         p.a_bytes = (p.a_tx + 1023u) & ~1023u;        // slot stride (1 KB aligned)
@@ -979,12 +1189,23 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
             p.b_resident = 0;
             p.issuers = 1;            // many bursts per tile: one issuer, one deep ring
             p.b_stages = (9u * p.b_bytes + 2u * p.a_bytes <= avail) ? 9 : 6;   // three (else two) filter columns of three taps in flight
+            {
+                // tile pairs need the two tiles' halo copies of a chunk resident at once; with room for only two copies the next
+                // chunk's halos could not be prefetched, so a pair plan trades the third tap column for four halo slots
+                const long long spatial = (long long)N * p.tiles_h * p.tiles_w;
+                const bool pair_ok = !no_pair && spatial % 2 == 0 && spatial * p.n_tiles >= 4;
+                if (pair_ok && p.b_stages == 9 && (avail - 9u * p.b_bytes) / p.a_bytes < 4u && 6u * p.b_bytes + 4u * p.a_bytes <= avail) p.b_stages = 6;
+            }
             p.b_slots = p.b_stages;
             YSOD_CHECK_ARG((uint32_t)p.b_stages * p.b_bytes + 2u * p.a_bytes <= avail, "ysod_conv_tc_create: halo plan does not fit in shared memory (BN %d)", BN);
             a_total = (int)((avail - (uint32_t)p.b_stages * p.b_bytes) / p.a_bytes);
             if (a_total > 4) a_total = 4;
             p.a_stages = a_total;
             p.sgroup = 1;
+            // streamed taps are the dominant operand stream (9 x 16 KB per chunk against one 22.5 KB halo copy): share them
+            // between the two tiles of a pair (TcParams::pair)
+            const long long spatial = (long long)N * p.tiles_h * p.tiles_w;
+            p.pair = (!no_pair && a_total >= 2 && spatial % 2 == 0 && spatial * p.n_tiles >= 4) ? 1 : 0;
         }
         p.a_slots = a_total;
         ring_bytes = (size_t)p.a_slots * p.a_bytes + (size_t)p.b_slots * p.b_bytes;
@@ -1001,13 +1222,19 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
         YSOD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         const long long total = (long long)N * p.tiles_h * p.tiles_w * p.n_tiles;
         long long g = (long long)sms;   // one persistent CTA per SM
-        if (g > total) g = total;
+        const long long units = p.pair ? total / 2 : total;   // work items: tiles, or tile pairs
+        if (g > units) g = units;
         c.grid = dim3((unsigned)g, 1, 1);
         long long r = g;
         p.step_tw = (int)(r % p.tiles_w); r /= p.tiles_w;
         p.step_th = (int)(r % p.tiles_h); r /= p.tiles_h;
         p.step_img = (int)(r % N);
         p.step_nt = (int)(r / N);
+        r = 2 * g;
+        p.step2_tw = (int)(r % p.tiles_w); r /= p.tiles_w;
+        p.step2_th = (int)(r % p.tiles_h); r /= p.tiles_h;
+        p.step2_img = (int)(r % N);
+        p.step2_nt = (int)(r / N);
     }
 
     const CUtensorMapSwizzle swz = p.BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -1124,6 +1351,7 @@ int ysod_conv_tc_info(ysod_conv_tc* h, int* out8) {
     YSOD_CHECK_ARG(h && out8, "ysod_conv_tc_info: null");
     out8[0] = h->c.p.TH; out8[1] = h->c.p.TW; out8[2] = h->c.p.BN; out8[3] = h->c.p.BK; out8[4] = h->c.p.stages;
     out8[5] = (int)h->c.grid.x; out8[6] = h->c.halo ? (1000 + 100 * h->c.p.issuers + 10 * h->c.p.b_resident + h->c.p.n_tiles) : (100 * h->c.p.issuers + 10 * h->c.p.kgroup + h->c.p.n_tiles);
+    out8[6] += 10000 * h->c.p.pair;
     out8[7] = (int)h->c.smem;
     return YSOD_OK;
 }

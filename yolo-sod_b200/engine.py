@@ -12,6 +12,7 @@ Nothing here computes on the CPU at run time; if libysod.so or the GPU is missin
 """
 import ctypes as C
 import math
+import os
 from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Dict, List, Optional
@@ -178,6 +179,10 @@ class Program:
             bk[:Cout] = bias
             bd = self.dev_t(bk)
             mode = _lib.CONV_UP2 if up2 else 0
+            if not self.m.conv_pair:
+                mode |= _lib.CONV_NO_PAIR
+            if os.environ.get("YSOD_TRACE_OP", "") == str(len(self.ops)):
+                mode |= 32 << 8   # profiling aid: CTA 0 of this op logs its pipeline events (tools/trace_in_graph.py)
             if no_store:
                 mode |= _lib.CONV_NO_STORE | _lib.CONV_NO_SPLIT_STAGING
             if gate is None:
@@ -484,6 +489,12 @@ class Program:
         else:
             self.emit("ysod_gap_partial", x.ptr(), self.code, x.N, HW, Cc, x.cs, S, _lib.ptr(psum), _lib.ptr(pmax))
             self.emit("ysod_cbam_gate", _lib.ptr(psum), _lib.ptr(pmax), x.N, S, HW, Cc, _lib.ptr(w1), _lib.ptr(w2), hid, _lib.ptr(gate))
+        c8 = Cc // 8
+        if self.m.fuse_cbam and c8 <= 32 and (c8 & (c8 - 1)) == 0:
+            # statistics + 7x7 conv + apply in one pass over the map (2 reads + 1 write for the whole block)
+            self.emit("ysod_cbam_spatial", x.ptr(), self.code, x.N, x.H, x.W, Cc, x.cs, _lib.ptr(gate), _lib.ptr(wsp), 7, out.ptr(), out.cs,
+                      desc="CBAM spatial (stats + 7x7 + apply)")
+            return
         self.emit("ysod_cbam_stats", x.ptr(), self.code, x.N, HW, Cc, x.cs, _lib.ptr(gate), _lib.ptr(stats))
         self.emit("ysod_cbam_apply", x.ptr(), self.code, x.N, x.H, x.W, Cc, x.cs, _lib.ptr(gate), _lib.ptr(stats), _lib.ptr(wsp), 7,
                   out.ptr(), out.cs)
@@ -498,7 +509,9 @@ class Program:
         wh, bh = self.dev_t(sd[f"{P}.conv_h.weight"].reshape(Cc, mip)), self.dev_t(sd[f"{P}.conv_h.bias"])
         ww, bw = self.dev_t(sd[f"{P}.conv_w.weight"].reshape(Cc, mip)), self.dev_t(sd[f"{P}.conv_w.bias"])
         pooled, att = self.f32(x.N, x.H + x.W, Cc), self.f32(x.N, x.H + x.W, Cc)
-        self.emit("ysod_ca_pool", x.ptr(), self.code, x.N, x.H, x.W, Cc, x.cs, _lib.ptr(pooled))
+        nws = int(self.lib.ysod_ca_pool_workspace_floats(x.N, x.H, x.W, Cc)) if self.m.ca_single_pass else 0
+        ws = self.f32(nws) if nws > 0 else None
+        self.emit("ysod_ca_pool", x.ptr(), self.code, x.N, x.H, x.W, Cc, x.cs, _lib.ptr(pooled), _lib.ptr(ws) if ws is not None else None)
         self.emit("ysod_ca_gate", _lib.ptr(pooled), x.N, x.H, x.W, Cc, mip, _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(wh), _lib.ptr(bh),
                   _lib.ptr(ww), _lib.ptr(bw), _lib.ptr(att))
         self.emit("ysod_ca_apply", x.ptr(), self.code, x.N, x.H, x.W, Cc, x.cs, _lib.ptr(att), out.ptr(), out.cs)
@@ -652,7 +665,7 @@ class Program:
         for L in layers:
             if L.type in ("SE_Block", "SE") and L.i > 0 and self.m.fuse_se and L.i not in home and L.i not in det_inputs:
                 cons = consumers.get(L.i, [])
-                if len(cons) == 1 and layers[cons[0]].type == "Conv" and cons[0] not in fold_up:
+                if len(cons) == 1 and layers[cons[0]].type == "Conv":   # (the consumer may itself store through a fused nn.Upsample)
                     Cn = layers[cons[0]]
                     src_hw = shp[L.i]
                     if self.tc_eligible(Cn, src_hw[2], src_hw[0], src_hw[1]):
@@ -685,7 +698,10 @@ class Program:
                 U = fold_up[L.i]
                 uh, uw, uc = shp[U]
                 uo = home[U] if U in home else self.new(self.B, uh, uw, uc)
-                self.conv_bn(out[src], P, p["k"], p["s"], p["g"], p["act"], out=uo, pad=p["p"], up2=True)
+                xin, gate = out[src], None
+                if isinstance(xin, GatedView):
+                    xin, gate = xin.base, xin.gate
+                self.conv_bn(xin, P, p["k"], p["s"], p["g"], p["act"], out=uo, pad=p["p"], up2=True, gate=gate)
                 out[U] = uo
                 out[L.i] = View(uo.buf, uo.off, uo.N, h, w, c, uo.cs, sub=2)
                 if U in det_inputs:
@@ -875,7 +891,7 @@ class B200DetectionModel:
     """
 
     def __init__(self, cfg, state_dict, dtype=torch.bfloat16, device="cuda:0", use_tc=True, use_graph=True, nc=None,
-                 static_outputs=False, max_programs=8, attn_impl=0, fuse_swin=True, multi_stream=True, fuse_upsample=True, fuse_decode=True, fuse_se=True, fuse_gate=False):
+                 static_outputs=False, max_programs=8, attn_impl=0, fuse_cbam=False, ca_single_pass=False, fuse_swin=True, multi_stream=True, fuse_upsample=True, fuse_decode=True, fuse_se=True, fuse_gate=False):
         _lib.require_cuda()
         _lib.load()
         self.spec = cfg if isinstance(cfg, _cfg.ModelSpec) else _cfg.get_spec(cfg, nc=nc)
@@ -890,6 +906,13 @@ class B200DetectionModel:
         self.use_tc = use_tc
         self.use_graph = use_graph
         self.fuse_swin = fuse_swin
+        # Single-pass variants of the CBAM spatial stage (ysod_cbam_spatial) and of the CoordAtt pooling (ysod_ca_pool with a workspace):
+        # bit-identical / fp32-rounding-identical to the multi-pass kernels but measured SLOWER on B200 (profiles/r02_ab_blocks.json:
+        # 128 vs 107 us at 64 x 160^2, 92 vs 42 us at 256 x 40^2; 120 vs 37 us for the pooling) -- one CTA per tile serialises statistics ->
+        # filter -> apply with too few bytes in flight, while the separate passes stream at full occupancy. Off by default.
+        self.fuse_cbam = fuse_cbam
+        self.ca_single_pass = ca_single_pass
+        self.conv_pair = os.environ.get("YSOD_NO_PAIR", "0") != "1"   # A/B switch of the conv kernel's tile-pair plan (ysod.h YSOD_CONV_NO_PAIR)
         self.attn_impl = attn_impl   # ysod_mha_core_ex impl: 0 = tcgen05 / TMEM attention core where covered, 1 = mma.sync kernels (A/B)
         self.fuse_upsample = fuse_upsample
         self.fuse_decode = fuse_decode

@@ -11,6 +11,7 @@ F32, BF16 = 0, 1
 CONV_UP2 = 0x40   # ysod.h YSOD_CONV_UP2
 CONV_IMG_WEIGHTS = 0x80   # ysod.h YSOD_CONV_IMG_WEIGHTS
 CONV_NO_SPLIT_STAGING = 0x10   # ysod.h YSOD_CONV_NO_SPLIT_STAGING
+CONV_NO_PAIR = 0x04       # ysod.h YSOD_CONV_NO_PAIR
 CONV_NO_STORE = 0x20      # ysod.h YSOD_CONV_NO_STORE
 STEM_INDIRECT = 0x10      # ysod.h YSOD_STEM_INDIRECT
 ACT = {"none": 0, "silu": 1, "gelu": 2, "relu": 3, "sigmoid": 4, "hsigmoid": 5}
@@ -50,7 +51,9 @@ PROTOTYPES = {
     "ysod_scale_channels": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, i32, vp]),
     "ysod_cbam_stats": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp]),
     "ysod_cbam_apply": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, i32, vp]),
-    "ysod_ca_pool": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "ysod_cbam_spatial": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp, i32, vp]),
+    "ysod_ca_pool_workspace_floats": (i64, [i32, i32, i32, i32]),
+    "ysod_ca_pool": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp, vp]),
     "ysod_ca_gate": (i32, [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]),
     "ysod_ca_apply": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, vp]),
     "ysod_sppf_pool": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp]),

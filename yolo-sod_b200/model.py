@@ -110,6 +110,32 @@ class Results:
         return len(self.boxes)
 
 
+class ResultStream:
+    """What `predict(..., stream=True)` returns: an iterator of per-image Results over a batch whose device work is in flight. `.det`
+    (B, max_det, 6) and `.count` (B,) are the padded batch on the GPU (valid once the stream that produced them has run)."""
+
+    def __init__(self, det, count, shape, names, host_count=None, ready=None):
+        self.det, self.count, self.shape, self.names = det, count, shape, names
+        self._host_count, self._ready = host_count, ready
+        self._items = None
+
+    def _materialise(self):
+        if self._items is None:
+            if self._ready is not None:
+                self._ready.synchronize()      # the host sync: this batch's counts have landed in pinned memory
+                n = self._host_count.tolist()
+            else:
+                n = self.count.tolist()
+            self._items = [Results(self.det[b, :k], self.shape, self.names) for b, k in enumerate(n)]
+        return self._items
+
+    def __iter__(self):
+        return iter(self._materialise())
+
+    def __len__(self):
+        return int(self.det.shape[0])
+
+
 class YOLO:
     """`YOLO(cfg_yaml)` facade (models/yolo/model.py:14-23, engine/model.py:84-151,501-560) for tensor sources."""
 
@@ -150,6 +176,22 @@ class YOLO:
                                       "uint8 BGR frames, or a list of HWC uint8 BGR frames (numpy / torch); file and stream sources need "
                                       "the reference's ultralytics.data loaders, which are out of scope")
         det, counts, (h, w) = self.predict_padded(source, conf, iou, max_det, classes, agnostic_nms)
+        if stream:
+            # engine/model.py:501-560 `stream=True`: a generator of Results instead of a list (predictor.py:197-205 stream_inference).
+            # All device work of the batch is already enqueued; the host synchronisation (the per-image counts) happens when the
+            # caller starts consuming the generator, so a caller may submit the next batch first.
+            # the counts travel to pinned host memory right behind the NMS; consuming the generator waits for THAT copy only (an
+            # event), not for whatever the caller enqueued afterwards
+            ring = getattr(self, "_count_ring", None)
+            if ring is None or ring[0][0].numel() < int(counts.numel()):
+                ring = self._count_ring = [(torch.empty(int(counts.numel()), dtype=torch.int32).pin_memory(), torch.cuda.Event()) for _ in range(4)]
+                self._count_next = 0
+            hbuf, ev = ring[self._count_next % len(ring)]
+            self._count_next += 1
+            hview = hbuf[: int(counts.numel())]
+            hview.copy_(counts, non_blocking=True)
+            ev.record(torch.cuda.current_stream(counts.device))
+            return ResultStream(det, counts, (h, w), self.names, hview, ev)
         ncount = counts.tolist()   # the one host sync of the call: the API returns variable-length per-image tensors
         return _ops.DetList([Results(det[b, :n], (h, w), self.names) for b, n in enumerate(ncount)], det, counts)
 
