@@ -77,6 +77,13 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
  * level's final 1x1 head conv (plan: fp32 raw map out, no activation, Cout = 64 + nc): besides the raw map the launch writes
  * y (B, 4+nc, A_total) for anchors [a_off, a_off + Ho*Wo). Equivalent to running ysod_dfl_decode on the raw map afterwards. */
 int ysod_conv_tc_set_decode(ysod_conv_tc* h, float* y, int A_total, int a_off, int nc, float stride);
+/* Back-to-back GEMM: head.py:43-57 `Conv(c, c, 3)` followed by `nn.Conv2d(c, 4*reg_max | nc, 1)` (Detect cv2[i][1..2] / cv3[i][1..2])
+ * and the level's share of the decode (head.py:100-131) in ONE launch: the staged bf16 tile of the 3x3 conv is the A operand of a
+ * second tcgen05.mma group against w2 [n2][64] bf16 (+ bias2), whose epilogue writes y (kind 1: DFL box branch -> y[0..4);
+ * kind 2: class branch -> sigmoid -> y[4..4+nc)) and, when `raw` is given, the fp32 raw map channels [raw_coff, ...). The 3x3 conv's own
+ * output is never stored. Plan requirements: Cout 64, bf16 output, no fused upsample. */
+int ysod_conv_tc_set_b2b(ysod_conv_tc* h, const void* w2, const float* bias2, int n2, int kind, float* y, int A_total, int a_off, int nc,
+                         float stride, float* raw, int raw_cs, int raw_coff);
 /* SE (smallobj_modules.py:57-92) folded into the conv that consumes it: conv(x * a[n]) == conv with input-channel columns of the
  * weights scaled by a[n]. w: [rows][K] fp32 (K ordered (r,s,cin), BN folded); gate: [N][Cin] fp32; out: [N][rows][K] bf16. */
 int ysod_scale_weights(const float* w, int rows, int K, int Cin, const float* gate, int N, void* out, void* stream);

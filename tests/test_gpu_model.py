@@ -305,7 +305,7 @@ def test_fused_epilogues_equal_separate_kernels():
     """Conv+Upsample in one launch and the Detect decode inside the final head conv's epilogue are pure re-schedulings: the raw maps
     are bit-identical to the separate-kernel program and y agrees to fp32 rounding (expression order is the same; only FMA contraction may differ)."""
     spec, sd, fused = _build(SOD, torch.bfloat16, fuse_gate=True, fuse_cbam=True)     # + pool and gate MLP in one launch (ysod_gap_gate), single-pass CBAM spatial stage
-    _, _, plain = _build(SOD, torch.bfloat16, fuse_upsample=False, fuse_decode=False, fuse_gate=False, fuse_cbam=False)   # + CBAM as stats / apply passes
+    _, _, plain = _build(SOD, torch.bfloat16, fuse_upsample=False, fuse_decode=False, fuse_gate=False, fuse_cbam=False, fuse_b2b=False)   # + CBAM as stats / apply passes
     x = synth.synth_images(2, 320, seed=23).cuda()
     y1, r1 = fused(x)
     y2, r2 = plain(x)

@@ -64,6 +64,16 @@ struct TcParams {
     float dec_stride;
     int w_img_rows;   // > 0: per-image weights (an SE channel gate folded into the next conv): image i uses weight rows [i*w_img_rows, +Cout_pad)
     int no_store;   // the plan's own output is not written (decode-only head conv of the predict path)
+    // Back-to-back GEMM (ysod_conv_tc_set_b2b): the staged bf16 output tile (128 pixels x 64 channels, 128 B swizzled rows) IS a K-major
+    // SWIZZLE_128B UMMA A operand, so a following 1x1 conv (Detect cv2[i][2] / cv3[i][2], head.py:43-57) runs as a second tcgen05.mma
+    // group straight from the staging buffer into its own TMEM columns: D2[128 x b2_n] = tile[128 x 64] * W2[b2_n x 64]. The second
+    // epilogue adds the bias and runs the Detect decode (b2b 1: DFL box branch -> y[0..4); 2: class branch -> sigmoid -> y[4..4+nc)),
+    // optionally also writing the fp32 raw map. The 3x3 conv's own output never goes to HBM.
+    int b2b, b2_n, b2_raw_cs, b2_raw_off;
+    const __nv_bfloat16* b2_w;   // [b2_n][64] bf16, K-major
+    const float* b2_bias;        // [b2_n]
+    float* b2_raw;               // NHWC fp32 raw map (pixel stride b2_raw_cs), channels [b2_raw_off, ...), or nullptr
+    float* b2_y;                 // y (B, 4+nc, A): geometry in dec_A / dec_off / dec_nc / dec_stride (dec_y stays null: no main-tile decode)
     int up2;    // nn.Upsample(scale 2, nearest) fused into the store: every output pixel is written to its 2 x 2 block of the 2Ho x 2Wo destination
     int debug;  // profiling only (mode >> 8): 1 = epilogue drains without work, 2 = producer skips TMA, 4 = MMA issuer skips tcgen05.mma,
                 // 8 = epilogue skips the TMA store, 16 = epilogue skips the activation
@@ -284,6 +294,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t bias_smem = tmem_slot + 16u;
     const uint32_t stage_out = (bias_smem + 4u * (uint32_t)p.cout_pad + 1023u) & ~1023u;
     float* const bias_s = reinterpret_cast<float*>(smem_raw + (bias_smem - smem0));
+    // back-to-back GEMM operands (b2b): W2 tile (1 KB aligned, b2_n rows of 128 B), its bias, one mbarrier per epilogue group
+    const uint32_t b2_w_smem = stage_out + (uint32_t)p.stage_bufs * (uint32_t)(p.stage_split ? 1 : p.n_units) * 128u * p.row_bytes;
+    const uint32_t b2_bias_smem = b2_w_smem + 128u * (uint32_t)p.b2_n;
+    const uint32_t b2_bar = b2_bias_smem + 4u * (uint32_t)p.b2_n;
+    float* const b2_bias_s = reinterpret_cast<float*>(smem_raw + (b2_bias_smem - smem0));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool tr = (p.debug & 32) && blockIdx.x == 0;
@@ -303,6 +318,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(tfull_bar + 8u * a, 1);
             mbar_init(tempty_bar + 8u * a, EPI_WARPS / 2);  // one arrive per warp of the accumulator's epilogue group
         }
+        if (p.b2b) {
+            mbar_init(b2_bar, 1);
+            mbar_init(b2_bar + 8u, 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) {
@@ -313,6 +332,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // SiLU layers keep 0.5 * bias: the epilogue needs h = (acc + bias) / 2 = fma(acc, 0.5, 0.5 * bias), one instruction
         const float bscale = (p.act == YSOD_ACT_SILU && !(p.debug & 16)) ? 0.5f : 1.0f;
         for (int i = threadIdx.x; i < p.cout_pad; i += EPI_THREADS) bias_s[i] = bscale * __ldg(p.bias + i);
+        if (p.b2b) {
+            // W2 rows (64 bf16 = 128 B) in the K-major SWIZZLE_128B layout: 16 B piece c of row r at r * 128 + ((c ^ (r & 7)) << 4)
+            for (int i = threadIdx.x; i < p.b2_n * 8; i += EPI_THREADS) {
+                const int r = i >> 3, c = i & 7;
+                const uint4 w = __ldg(reinterpret_cast<const uint4*>(p.b2_w + (size_t)r * 64 + c * 8));
+                st_shared_v4(b2_w_smem + (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)), w.x, w.y, w.z, w.w);
+            }
+            for (int i = threadIdx.x; i < p.b2_n; i += EPI_THREADS) b2_bias_s[i] = __ldg(p.b2_bias + i);
+            fence_async_smem();
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -746,7 +775,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int asel = 0;   // accumulator of tile i is i % 4 = 2 * asel + grp for this group's tiles
         const uint32_t row0 = sb + (uint32_t)m * p.row_bytes;
         const uint32_t swz_x = (row0 >> 7) & swz_mask;   // swizzle XOR term of this thread's staging row
-        uint32_t acc_phase = 0;
+        uint32_t acc_phase = 0, b2_phase = 0;
         TileIter ti;
         ti.init(p.pair ? 2 * blockIdx.x + grp : blockIdx.x, p);   // pairs: group g owns tile g of every pair of this CTA
         if (!p.pair && grp) ti.step(p);
@@ -780,7 +809,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 continue;
             }
             // the bulk stores issued from this group's staging buffer (previous own tile) must have finished reading it
-            const bool no_store = p.no_store != 0;   // decode-only plan: nothing is staged or stored, so no barriers either
+            const bool b2b = p.b2b != 0;
+            const bool no_store = p.no_store != 0 && !b2b;   // decode-only plan: nothing is staged or stored, so no barriers either
             if (!no_store) {
                 if (leader_warp) bulk_wait_read<0>();
                 epi_barrier(grp);
@@ -885,8 +915,77 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             trace(tre, 2, 3, tcount, 0, tcnt);       // accumulator handed back
             }
             if (no_store) continue;
-            fence_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+            fence_async_smem();  // generic-proxy smem writes -> visible to the TMA / the tensor core (async proxy)
             epi_barrier(grp);
+            if (b2b) {
+                // ===== back-to-back GEMM: the staged tile is the A operand of the 1x1 head conv =====
+                const uint32_t d2col = (uint32_t)(4 * BN + grp * p.b2_n);
+                if (leader_warp && elect_one()) {
+                    tc_fence_after();
+                    const uint32_t idesc2 = (1u << 4) | (YSOD_UMMA_AB_FORMAT << 7) | (YSOD_UMMA_AB_FORMAT << 10) | ((uint32_t)(p.b2_n >> 3) << 17) | ((128u >> 4) << 24);
+                    const uint32_t hi128 = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 8 rows x 128 B, SWIZZLE_128B
+                    const uint32_t a_lo = umma_lo(sb), b_lo = umma_lo(b2_w_smem);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc_mma_bf16(tmem_acc + d2col, umma_desc(hi128, a_lo + 2u * k), umma_desc(hi128, b_lo + 2u * k), idesc2, (uint32_t)(k != 0));
+                    tc_commit(b2_bar + 8u * grp);
+                }
+                mbar_wait(b2_bar + 8u * grp, b2_phase);
+                b2_phase ^= 1u;
+                tc_fence_after();
+                const int n2chunks = p.b2_n >> 4;
+                float* const rawp = (p.b2_raw != nullptr && (m < TH * TW) && d_oh < p.Ho && d_ow < p.Wo)
+                                        ? p.b2_raw + (((size_t)img * p.Ho + d_oh) * p.Wo + d_ow) * p.b2_raw_cs + p.b2_raw_off : nullptr;
+                const bool y_ok = (m < TH * TW) && d_oh < p.Ho && d_ow < p.Wo;
+                float* const yb = p.b2_y + (size_t)img * (4 + p.dec_nc) * p.dec_A + p.dec_off + d_oh * p.Wo + d_ow;
+                float e0 = 0.f, e1 = 0.f;   // box branch: DFL distances of this thread's two sides (cg 0: left, right; cg 1: top, bottom)
+                for (int ch2 = cg; ch2 < n2chunks; ch2 += 2) {
+                    uint32_t v2[16];
+                    tmem_ld16(trow0 + d2col + (uint32_t)(ch2 * 16), v2);
+                    tmem_ld_wait(v2);
+                    float g[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) g[j] = __uint_as_float(v2[j]) + b2_bias_s[ch2 * 16 + j];
+                    if (rawp) {
+                        const int valid = p.b2b == 1 ? 16 : min(16, p.dec_nc - ch2 * 16);   // the class branch has nc (< 16 * chunks) real channels
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4)
+                            if (j4 * 4 + 3 < valid) *reinterpret_cast<float4*>(rawp + ch2 * 16 + j4 * 4) = make_float4(g[4 * j4], g[4 * j4 + 1], g[4 * j4 + 2], g[4 * j4 + 3]);
+                            else
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    if (j4 * 4 + j < valid) rawp[ch2 * 16 + j4 * 4 + j] = g[4 * j4 + j];
+                    }
+                    if (p.b2b == 1) {
+                        // one 16-column chunk = the 16 DFL bins of side ch2 (l, t, r, b): softmax expectation, as in decode.cu
+                        float mx = g[0];
+#pragma unroll
+                        for (int j = 1; j < 16; ++j) mx = fmaxf(mx, g[j]);
+                        float sum = 0.f, acc = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float e = __expf(g[j] - mx);   // ex2.approx (2^-21 relative): this epilogue shares the SM with a tensor-bound main loop
+                            sum += e;
+                            acc = fmaf(e, (float)j, acc);
+                        }
+                        const float dist = __fdividef(acc, sum);
+                        if (ch2 < 2) e0 = dist; else e1 = dist;
+                    } else if (y_ok) {
+                        const int nc = p.dec_nc;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (ch2 * 16 + j < nc) yb[(size_t)(4 + ch2 * 16 + j) * p.dec_A] = __fdividef(1.0f, 1.0f + __expf(-g[j]));
+                    }
+                }
+                if (p.b2b == 1 && y_ok) {
+                    const float anc = (float)(cg == 0 ? d_ow : d_oh) + 0.5f;
+                    const float lo = anc - e0, hi = anc + e1;
+                    yb[(size_t)cg * p.dec_A] = (lo + hi) * 0.5f * p.dec_stride;
+                    yb[(size_t)(2 + cg) * p.dec_A] = (hi - lo) * p.dec_stride;
+                }
+                tc_fence_before();   // this warp's reads of D2 are complete before the group's next barrier lets the next MMA overwrite it
+                continue;
+            }
             if (leader_warp && elect_one()) {
                 if (!(p.debug & 8)) {
                     if (split) {
@@ -1332,6 +1431,35 @@ int ysod_conv_tc_set_decode(ysod_conv_tc* h, float* y, int A_total, int a_off, i
     YSOD_CHECK_ARG(a_off >= 0 && a_off + p.Ho * p.Wo <= A_total, "ysod_conv_tc_set_decode: anchor range out of bounds");
     YSOD_CHECK_ARG(!p.no_store || !p.stage_split, "ysod_conv_tc_set_decode: YSOD_CONV_NO_STORE needs the single-pass epilogue");
     p.dec_y = y; p.dec_A = A_total; p.dec_off = a_off; p.dec_nc = nc; p.dec_stride = stride;
+    return YSOD_OK;
+}
+
+// Back-to-back GEMM + Detect decode (TcParams::b2b): the plan must be a 64-output-channel bf16 conv whose staged tile is one 128 B
+// swizzled row per pixel (BN = 64, single store unit, no split staging, no fused upsample). w2: [n2][64] bf16 (n2 % 16 == 0, rows
+// >= the real channel count zero), bias2: [n2] fp32. kind 1: w2 = Detect cv2[i][2] (64 DFL logits, n2 = 64) -> y[0..4); kind 2: w2 =
+// cv3[i][2] (nc class logits, n2 = 16 * ceil(nc / 16)) -> y[4..4+nc). raw (optional): the level's NHWC fp32 raw map, pixel stride
+// raw_cs, written at channel offset raw_coff (0 for the box branch, 64 for the class branch). The conv's own output is not stored.
+int ysod_conv_tc_set_b2b(ysod_conv_tc* h, const void* w2, const float* bias2, int n2, int kind, float* y, int A_total, int a_off, int nc,
+                         float stride, float* raw, int raw_cs, int raw_coff) {
+    YSOD_CHECK_ARG(h && w2 && bias2 && y, "ysod_conv_tc_set_b2b: null");
+    ConvTc& c = h->c;
+    TcParams& p = c.p;
+    YSOD_CHECK_ARG(p.BN == 64 && p.n_tiles == 1 && !p.out_f32 && p.n_units == 1 && !p.stage_split && !p.up2 && p.row_bytes == 128 && p.dec_y == nullptr,
+                   "ysod_conv_tc_set_b2b: plan must be a 64-channel bf16 conv with a single 128 B staging unit (BN %d, units %d, split %d)", p.BN,
+                   p.n_units, p.stage_split);
+    YSOD_CHECK_ARG(kind == 1 || kind == 2, "ysod_conv_tc_set_b2b: kind %d", kind);
+    YSOD_CHECK_ARG(n2 % 16 == 0 && n2 >= 16 && n2 <= 128 && (kind != 1 || n2 == 64) && (kind != 2 || (nc > 0 && nc <= n2)), "ysod_conv_tc_set_b2b: bad n2 %d / nc %d", n2, nc);
+    YSOD_CHECK_ARG(a_off >= 0 && a_off + p.Ho * p.Wo <= A_total, "ysod_conv_tc_set_b2b: anchor range out of bounds");
+    YSOD_CHECK_ARG(((uintptr_t)w2 % 16) == 0 && (!raw || (((uintptr_t)raw % 16) == 0 && raw_cs % 4 == 0 && raw_coff % 4 == 0)), "ysod_conv_tc_set_b2b: alignment");
+    const size_t extra = 128u * (size_t)n2 + 4u * (size_t)n2 + 16u;
+    YSOD_CHECK_ARG(c.smem + extra <= 227 * 1024, "ysod_conv_tc_set_b2b: shared memory plan too large (%zu)", c.smem + extra);
+    YSOD_CHECK_ARG(4 * p.BN + 2 * n2 <= 512, "ysod_conv_tc_set_b2b: TMEM columns");
+    c.smem += extra;
+    p.tmem_cols = 512;
+    p.b2b = kind; p.b2_n = n2; p.b2_w = (const __nv_bfloat16*)w2; p.b2_bias = bias2;
+    p.b2_raw = raw; p.b2_raw_cs = raw_cs; p.b2_raw_off = raw_coff;
+    p.b2_y = y;
+    p.dec_A = A_total; p.dec_off = a_off; p.dec_nc = nc; p.dec_stride = stride;
     return YSOD_OK;
 }
 

@@ -554,6 +554,35 @@ class Program:
                     # cv2[i][2] and cv3[i][2] (1x1, bias, no act) as ONE block-diagonal 1x1 conv [64 + nc][c2 + c3] over the two
                     # branch outputs stored side by side: the pair is HBM-bound, so the zero half of the weights is free and the
                     # raw map is written by one launch (full 74-channel rows instead of two partial slices)
+                    if (self.m.fuse_b2b and self.m.fuse_decode and c2n == 64 and c3n == 64 and nc <= 64
+                            and sd[f"{P}.cv2.{i}.1.conv.weight"].shape[0] == 64):
+                        # back-to-back GEMM: each branch's 3x3 conv feeds its 1x1 head conv from the staged tile and decodes its share of
+                        # y in the second epilogue (ysod_conv_tc_set_b2b): no `ac` buffer, no tail launch, raw map only on request
+                        for br, (lo, hi, kind, n2, coff) in enumerate([(0, c2n, 1, 64, 0), (c2n, both.C, 2, (nc + 15) // 16 * 16, 64)]):
+                            name = f"{P}.cv{2 + br}.{i}"
+                            dummy = View(both.buf, both.off, x.N, x.H, x.W, 64, both.cs)   # never written (the tensor map needs an address)
+                            self.conv_bn(both.slice(lo, hi), f"{name}.1", 3, out=dummy)
+                            w2 = torch.zeros((n2, 64), dtype=torch.float32)
+                            b2 = torch.zeros(n2, dtype=torch.float32)
+                            wsrc = sd[f"{name}.2.weight"].float().view(-1, 64)
+                            w2[:wsrc.shape[0]] = wsrc
+                            b2[:wsrc.shape[0]] = sd[f"{name}.2.bias"].float()
+                            w2d, b2d = self.dev_t(w2, self.dt), self.dev_t(b2)
+                            self.call("ysod_conv_tc_set_b2b", self.tc_handles[-1], _lib.ptr(w2d), _lib.ptr(b2d), n2, kind, _lib.ptr(y), A, a_off, nc,
+                                      float(self.m.stride_list[i]), raw.ptr() if raw is not None else None, raw_cs, coff)
+                            fl2 = 2.0 * x.N * x.H * x.W * 64 * (64 if kind == 1 else nc)
+                            self.op_flops[-1] += fl2
+                            self.tc_flops += fl2
+                            self.op_desc[-1] += " +1x1 head conv +decode (b2b)"
+                        decoded = True
+                        a = c = None
+                        a_off += x.H * x.W
+                        if raw is not None:
+                            raws.append(raw.slice(0, no))
+                        if branch:
+                            self.sched.append(("record", f"det{i}", self._lane))
+                            self._lane = 0
+                        continue
                     ac = self.new(x.N, x.H, x.W, c2n + c3n)
                     self.conv_bn(both.slice(0, c2n), f"{P}.cv2.{i}.1", 3, out=ac.slice(0, c2n))
                     self.conv_bn(both.slice(c2n, both.C), f"{P}.cv3.{i}.1", 3, out=ac.slice(c2n, c2n + c3n))
@@ -891,7 +920,7 @@ class B200DetectionModel:
     """
 
     def __init__(self, cfg, state_dict, dtype=torch.bfloat16, device="cuda:0", use_tc=True, use_graph=True, nc=None,
-                 static_outputs=False, max_programs=8, attn_impl=0, fuse_cbam=False, ca_single_pass=False, fuse_swin=True, multi_stream=True, fuse_upsample=True, fuse_decode=True, fuse_se=True, fuse_gate=False):
+                 static_outputs=False, max_programs=8, attn_impl=0, fuse_cbam=False, ca_single_pass=False, fuse_b2b=True, fuse_swin=True, multi_stream=True, fuse_upsample=True, fuse_decode=True, fuse_se=True, fuse_gate=False):
         _lib.require_cuda()
         _lib.load()
         self.spec = cfg if isinstance(cfg, _cfg.ModelSpec) else _cfg.get_spec(cfg, nc=nc)
@@ -912,6 +941,11 @@ class B200DetectionModel:
         # filter -> apply with too few bytes in flight, while the separate passes stream at full occupancy. Off by default.
         self.fuse_cbam = fuse_cbam
         self.ca_single_pass = ca_single_pass
+        self.fuse_b2b = fuse_b2b     # Detect branch 3x3 conv -> 1x1 head conv -> decode in one launch (ysod_conv_tc_set_b2b)
+        if "YSOD_FUSE_B2B" in os.environ:       # A/B switches for measurements
+            self.fuse_b2b = os.environ["YSOD_FUSE_B2B"] == "1"
+        if "YSOD_MULTI_STREAM" in os.environ:
+            multi_stream = os.environ["YSOD_MULTI_STREAM"] == "1"
         self.conv_pair = os.environ.get("YSOD_NO_PAIR", "0") != "1"   # A/B switch of the conv kernel's tile-pair plan (ysod.h YSOD_CONV_NO_PAIR)
         self.attn_impl = attn_impl   # ysod_mha_core_ex impl: 0 = tcgen05 / TMEM attention core where covered, 1 = mma.sync kernels (A/B)
         self.fuse_upsample = fuse_upsample
