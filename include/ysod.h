@@ -173,6 +173,16 @@ int ysod_window_reverse(const void* tok, int dtype, int ldt, int N, int H, int W
 int ysod_adaptive_pool_rows(const void* x, int dtype, int N, int H, int W, int C, int xcs, int OH, void* out, int ocs, void* stream);
 int ysod_bilinear_rows(const void* x, int dtype, int N, int IH, int W, int C, int xcs, int OH, void* out, int ocs, void* stream);
 
+/* SwinBlock with the tokens kept in NHWC pixel order (swin_nhwc.cu; blocks_transformer.py:133-171 around the linears):
+ * ysod_dwconv3_ln = dw 3x3 (no bias) + LayerNorm 1 in one pass (y = raw tokens for the residual, yn = normalised tokens; w [3][3][C]
+ * fp32, C 256 | 512, 16-bit storage); ysod_mha_window_nhwc = the window attention core reading q / k / v rows and writing its output
+ * rows through the window -> pixel map (ws*ws <= 64 tokens, head_dim 32 | 64); kpad / vpad [heads*D] = key / value of a zero-padded
+ * window token = in_proj_{k,v}(LayerNorm(0) = beta) + bias. Replace ysod_dwconv + ysod_window_partition_ln ... ysod_window_reverse. */
+int ysod_dwconv3_ln(const void* x, int N, int H, int W, int C, int xcs, const float* w, const float* gamma, const float* beta, float eps,
+                    void* y, int ycs, void* yn, int ncs, void* stream);
+int ysod_mha_window_nhwc(const void* q, const void* k, const void* v, int ld, int N, int H, int W, int ws, int heads, int D, const void* kpad,
+                         const void* vpad, float scale, void* out, int ldo, void* stream);
+
 /* Fully fused SwinBlock (blocks_transformer.py:133-171) for C = 64, 2 heads, 7x7 windows (the P2 level): dw3x3 -> window partition
  * (zero padded) -> x + MHA(LN x) -> x + MLP(LN x) -> window reverse / crop -> pw1x1 + BN + SiLU + identity, one kernel.
  * wbf16 (37440 bf16): dw[3][3][64] | in_proj_weight[192][64] | out_proj.weight[64][64] | mlp.0.weight[128][64] | mlp.2.weight[64][128] |

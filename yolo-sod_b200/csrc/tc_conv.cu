@@ -305,6 +305,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     unsigned int tcnt = 0;
     trace(tr && threadIdx.x == 0, 2, 10, 0, 0, tcnt);   // kernel entry (epilogue warp 0 lane 0 logs CTA-level events)
 
+    if (threadIdx.x == 32 && !(p.debug & 64)) {
+        // the TMA unit fetches the 128 B descriptors on first use: request them now, while barriers / TMEM / bias are being set up
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmO) : "memory");
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < a_slots; ++s) {
             mbar_init(fullA + 8u * s, 1);

@@ -181,6 +181,8 @@ class Program:
             mode = _lib.CONV_UP2 if up2 else 0
             if not self.m.conv_pair:
                 mode |= _lib.CONV_NO_PAIR
+            if os.environ.get("YSOD_CONV_DEBUG"):
+                mode |= int(os.environ["YSOD_CONV_DEBUG"]) << 8   # A/B switches of the conv kernel (debug bits, tc_conv.cu)
             if os.environ.get("YSOD_TRACE_OP", "") == str(len(self.ops)):
                 mode |= 32 << 8   # profiling aid: CTA 0 of this op logs its pipeline events (tools/trace_in_graph.py)
             if no_store:
@@ -322,6 +324,43 @@ class Program:
             T = x.N * (-(-x.H // ws)) * (-(-x.W // ws)) * ws * ws
             self.emit("ysod_swin64_fused", x.ptr(), x.N, x.H, x.W, x.cs, _lib.ptr(wbd), _lib.ptr(pfd), out.ptr(), out.cs, ws, 2,
                       flops=2.0 * T * (64 * 192 + 64 * 64 + 2 * 64 * 128 + 64 * 64 + 2 * 49 * 64), desc=f"swin64 fused @{x.H}x{x.W}")
+            return
+        heads = p["num_heads"]
+        D = Cc // heads
+        if (self.m.swin_nhwc and self.m.use_tc and self.code == _lib.BF16 and Cc in (256, 512) and D in (32, 64) and ws * ws <= 64
+                and x.H > ws and x.W > ws):
+            # Tokens stay in NHWC pixel order (csrc/swin_nhwc.cu): dw 3x3 + LayerNorm 1 in one pass, the linears as 1x1 convs over the
+            # N*H*W real pixels, the attention core reads / writes through the window -> pixel map (zero-padded window tokens enter as
+            # the constant key / value of LayerNorm(0) = beta); no window_partition / window_reverse copies.
+            g1, b1 = sd[f"{A}.norm1.weight"].float(), sd[f"{A}.norm1.bias"].float()
+            y, yn = self.new(x.N, x.H, x.W, Cc), self.new(x.N, x.H, x.W, Cc)
+            wdw = self.dev_t(dww.view(Cc, 3, 3).permute(1, 2, 0).contiguous())   # [3][3][C] fp32
+            self.emit("ysod_dwconv3_ln", x.ptr(), x.N, x.H, x.W, Cc, x.cs, _lib.ptr(wdw), _lib.ptr(self.dev_t(g1)), _lib.ptr(self.dev_t(b1)),
+                      LN_EPS, y.ptr(), y.cs, yn.ptr(), yn.cs, desc=f"dw3x3 + LayerNorm {Cc} @{x.H}x{x.W}")
+            T = x.N * x.H * x.W
+            tok = lambda v: View(v.buf, v.off, 1, 1, T, v.C, v.cs)
+            Wi, bi = sd[f"{A}.attn.in_proj_weight"].float(), sd[f"{A}.attn.in_proj_bias"].float()
+            qkv = self.linear(tok(yn), Wi, bi)
+            # key / value of a zero-padded token: in_proj(LayerNorm(0)) with the operands rounded as the kernels round them
+            lp = self.dt
+            beta_lp = b1.to(lp).float()
+            kv_pad = (Wi[Cc:].to(lp).float() @ beta_lp + bi[Cc:]).to(lp)
+            kvd = self.dev_t(kv_pad, lp)
+            ao = self.new(1, 1, T, Cc)
+            self.emit("ysod_mha_window_nhwc", qkv.ptr(), qkv.slice(Cc, 2 * Cc).ptr(), qkv.slice(2 * Cc, 3 * Cc).ptr(), 3 * Cc, x.N, x.H, x.W, ws,
+                      heads, D, _lib.ptr(kvd), _lib.ptr(kvd, Cc), 1.0 / math.sqrt(D), ao.ptr(), Cc,
+                      flops=4.0 * x.N * (-(-x.H // ws)) * (-(-x.W // ws)) * heads * (ws * ws) ** 2 * D, desc=f"window attention (NHWC gather) h{heads} d{D}")
+            w2 = self.linear(ao, sd[f"{A}.attn.out_proj.weight"], sd[f"{A}.attn.out_proj.bias"], res=tok(y))
+            n2 = self.new(1, 1, T, Cc)
+            g2, b2 = self.dev_t(sd[f"{A}.norm2.weight"]), self.dev_t(sd[f"{A}.norm2.bias"])
+            self.emit("ysod_layernorm", w2.ptr(), self.code, T, Cc, w2.cs, _lib.ptr(g2), _lib.ptr(b2), LN_EPS, n2.ptr(), n2.cs)
+            hmid = self.linear(n2, sd[f"{A}.mlp.0.weight"], sd[f"{A}.mlp.0.bias"], act="gelu")
+            w3 = self.linear(hmid, sd[f"{A}.mlp.2.weight"], sd[f"{A}.mlp.2.bias"], res=w2)
+            r = View(w3.buf, w3.off, x.N, x.H, x.W, Cc, w3.cs)
+            pw = sd[f"{P}.pw.weight"].float()
+            g, b = sd[f"{P}.bn.weight"].float(), sd[f"{P}.bn.bias"].float()
+            sc = g / torch.sqrt(sd[f"{P}.bn.running_var"].float() + BN_EPS)
+            self.conv(r, pw * sc.view(-1, 1, 1, 1), b - sd[f"{P}.bn.running_mean"].float() * sc, 1, 1, 1, "silu", out, res=x)
             return
         y = self.new(x.N, x.H, x.W, Cc)
         self.conv(x, dww, torch.zeros(Cc), 3, 1, Cc, "none", y)
@@ -920,7 +959,7 @@ class B200DetectionModel:
     """
 
     def __init__(self, cfg, state_dict, dtype=torch.bfloat16, device="cuda:0", use_tc=True, use_graph=True, nc=None,
-                 static_outputs=False, max_programs=8, attn_impl=0, fuse_cbam=False, ca_single_pass=False, fuse_b2b=True, fuse_swin=True, multi_stream=True, fuse_upsample=True, fuse_decode=True, fuse_se=True, fuse_gate=False):
+                 static_outputs=False, max_programs=8, attn_impl=0, fuse_cbam=False, ca_single_pass=False, fuse_b2b=True, swin_nhwc=True, fuse_swin=True, multi_stream=True, fuse_upsample=True, fuse_decode=True, fuse_se=True, fuse_gate=False):
         _lib.require_cuda()
         _lib.load()
         self.spec = cfg if isinstance(cfg, _cfg.ModelSpec) else _cfg.get_spec(cfg, nc=nc)
@@ -942,6 +981,9 @@ class B200DetectionModel:
         self.fuse_cbam = fuse_cbam
         self.ca_single_pass = ca_single_pass
         self.fuse_b2b = fuse_b2b     # Detect branch 3x3 conv -> 1x1 head conv -> decode in one launch (ysod_conv_tc_set_b2b)
+        self.swin_nhwc = swin_nhwc   # unfused SwinBlocks keep their tokens in NHWC order (no window_partition / window_reverse copies)
+        if "YSOD_SWIN_NHWC" in os.environ:
+            self.swin_nhwc = os.environ["YSOD_SWIN_NHWC"] == "1"
         if "YSOD_FUSE_B2B" in os.environ:       # A/B switches for measurements
             self.fuse_b2b = os.environ["YSOD_FUSE_B2B"] == "1"
         if "YSOD_MULTI_STREAM" in os.environ:
