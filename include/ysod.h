@@ -84,6 +84,9 @@ int ysod_conv_tc_set_decode(ysod_conv_tc* h, float* y, int A_total, int a_off, i
  * output is never stored. Plan requirements: Cout 64, bf16 output, no fused upsample. */
 int ysod_conv_tc_set_b2b(ysod_conv_tc* h, const void* w2, const float* bias2, int n2, int kind, float* y, int A_total, int a_off, int nc,
                          float stride, float* raw, int raw_cs, int raw_coff);
+/* Plain back-to-back GEMM: a following `Conv(64, 64, 1)` + BN + act whose only input is this plan's output (block.py:233-248 C2f.cv1
+ * right after a Conv layer) as the second MMA group of the same launch; create the plan with `out` = that second layer's destination. */
+int ysod_conv_tc_set_b2b_conv(ysod_conv_tc* h, const void* w2, const float* bias2, int act2);
 /* SE (smallobj_modules.py:57-92) folded into the conv that consumes it: conv(x * a[n]) == conv with input-channel columns of the
  * weights scaled by a[n]. w: [rows][K] fp32 (K ordered (r,s,cin), BN folded); gate: [N][Cin] fp32; out: [N][rows][K] bf16. */
 int ysod_scale_weights(const float* w, int rows, int K, int Cin, const float* gate, int N, void* out, void* stream);

@@ -86,7 +86,10 @@ def _check(name, dtype, B, sz, tol, layer_tol=None, seed=11, layers_too=True, ta
         layers = None
     report = []
     for i in range(len(spec.layers) - 1 if layers_too else 0):
-        got = model.layer_output(x, i).cpu()
+        got = model.layer_output(x, i)
+        if got is None:          # not materialised: the layer's only consumer runs inside its launch (back-to-back GEMM)
+            continue
+        got = got.cpu()
         ok, e, m, l2 = _close(got, layers[i], layer_tol or tol)
         report.append((i, spec.layers[i].type, ok, round(e, 5), round(m, 3), round(l2, 4)))
     bad = [r for r in report if not r[2]]

@@ -69,7 +69,7 @@ struct TcParams {
     // group straight from the staging buffer into its own TMEM columns: D2[128 x b2_n] = tile[128 x 64] * W2[b2_n x 64]. The second
     // epilogue adds the bias and runs the Detect decode (b2b 1: DFL box branch -> y[0..4); 2: class branch -> sigmoid -> y[4..4+nc)),
     // optionally also writing the fp32 raw map. The 3x3 conv's own output never goes to HBM.
-    int b2b, b2_n, b2_raw_cs, b2_raw_off;
+    int b2b, b2_n, b2_raw_cs, b2_raw_off, b2_act;   // b2b 3: plain second layer (bias + b2_act -> bf16 -> the plan's own output map)
     const __nv_bfloat16* b2_w;   // [b2_n][64] bf16, K-major
     const float* b2_bias;        // [b2_n]
     float* b2_raw;               // NHWC fp32 raw map (pixel stride b2_raw_cs), channels [b2_raw_off, ...), or nullptr
@@ -940,6 +940,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 b2_phase ^= 1u;
                 tc_fence_after();
                 const int n2chunks = p.b2_n >> 4;
+                if (p.b2b == 3) {
+                    // plain second layer (a 1x1 Conv + BN + act, conv.py:37-55): bias, activation, bf16, back into the SAME staging
+                    // buffer (its first life, the A operand, ended when b2_bar fired) and out through the plan's own output map
+                    for (int ch2 = cg; ch2 < n2chunks; ch2 += 2) {
+                        uint32_t v2[16];
+                        tmem_ld16(trow0 + d2col + (uint32_t)(ch2 * 16), v2);
+                        tmem_ld_wait(v2);
+                        float g[16];
+                        if (p.b2_act == YSOD_ACT_SILU) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float hh = 0.5f * (__uint_as_float(v2[j]) + b2_bias_s[ch2 * 16 + j]);
+                                g[j] = fmaf(hh, tanh_approx(hh), hh);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) g[j] = __uint_as_float(v2[j]) + b2_bias_s[ch2 * 16 + j];
+                        }
+                        const uint32_t p0 = (uint32_t)(ch2 * 2);
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+                            st_shared_v4(row0 + (((p0 + j) ^ swz_x) << 4), pack_bf16(g[8 * j], g[8 * j + 1]), pack_bf16(g[8 * j + 2], g[8 * j + 3]),
+                                         pack_bf16(g[8 * j + 4], g[8 * j + 5]), pack_bf16(g[8 * j + 6], g[8 * j + 7]));
+                    }
+                    tc_fence_before();
+                    fence_async_smem();
+                    epi_barrier(grp);
+                    if (leader_warp && elect_one()) {
+                        tma_store_4d(&tmO, sb, 0, ow0, oh0, img);
+                        bulk_commit();
+                    }
+                    continue;
+                }
                 float* const rawp = (p.b2_raw != nullptr && (m < TH * TW) && d_oh < p.Ho && d_ow < p.Wo)
                                         ? p.b2_raw + (((size_t)img * p.Ho + d_oh) * p.Wo + d_ow) * p.b2_raw_cs + p.b2_raw_off : nullptr;
                 const bool y_ok = (m < TH * TW) && d_oh < p.Ho && d_ow < p.Wo;
@@ -1466,6 +1499,28 @@ int ysod_conv_tc_set_b2b(ysod_conv_tc* h, const void* w2, const float* bias2, in
     p.b2_raw = raw; p.b2_raw_cs = raw_cs; p.b2_raw_off = raw_coff;
     p.b2_y = y;
     p.dec_A = A_total; p.dec_off = a_off; p.dec_nc = nc; p.dec_stride = stride;
+    return YSOD_OK;
+}
+
+// Back-to-back GEMM, plain variant: a 1x1 Conv(64 -> 64) + BN + act that consumes ONLY this plan's output (e.g. C2f.cv1 right after
+// a Conv layer, block.py:233-248) runs as the second MMA group of the same launch. The plan must have been created with `out` = the
+// destination of that second layer (64 channels, bf16): the first layer's own output is never stored. w2: [64][64] bf16 (BN folded).
+int ysod_conv_tc_set_b2b_conv(ysod_conv_tc* h, const void* w2, const float* bias2, int act2) {
+    YSOD_CHECK_ARG(h && w2 && bias2, "ysod_conv_tc_set_b2b_conv: null");
+    ConvTc& c = h->c;
+    TcParams& p = c.p;
+    YSOD_CHECK_ARG(p.BN == 64 && p.Cout == 64 && p.n_tiles == 1 && !p.out_f32 && p.n_units == 1 && !p.stage_split && !p.up2 && p.row_bytes == 128 &&
+                   p.dec_y == nullptr && !p.b2b && !p.no_store,
+                   "ysod_conv_tc_set_b2b_conv: plan must be a 64-channel bf16 conv with a single 128 B staging unit (BN %d, units %d, split %d)", p.BN,
+                   p.n_units, p.stage_split);
+    YSOD_CHECK_ARG(act2 == YSOD_ACT_SILU || act2 == YSOD_ACT_NONE, "ysod_conv_tc_set_b2b_conv: activation %d unsupported", act2);
+    YSOD_CHECK_ARG(((uintptr_t)w2 % 16) == 0, "ysod_conv_tc_set_b2b_conv: alignment");
+    const size_t extra = 128u * 64u + 4u * 64u + 16u;
+    YSOD_CHECK_ARG(c.smem + extra <= 227 * 1024, "ysod_conv_tc_set_b2b_conv: shared memory plan too large (%zu)", c.smem + extra);
+    c.smem += extra;
+    p.tmem_cols = 512;
+    p.b2b = 3; p.b2_n = 64; p.b2_w = (const __nv_bfloat16*)w2; p.b2_bias = bias2; p.b2_act = act2;
+    p.b2_raw = nullptr; p.b2_y = nullptr;
     return YSOD_OK;
 }
 

@@ -262,8 +262,12 @@ class Program:
         written slice by slice."""
         n = p["n"]
         c = int(c2 * p["e"])
-        cat = self.new(x.N, x.H, x.W, (2 + n) * c)
-        self.conv_bn(x, f"{P}.cv1", out=cat.slice(0, 2 * c))
+        li = int(P.split(".")[1])
+        if li in getattr(self, "_c2f_pre", {}):
+            cat = self._c2f_pre[li]          # cv1 already ran inside the producer conv's launch
+        else:
+            cat = self.new(x.N, x.H, x.W, (2 + n) * c)
+            self.conv_bn(x, f"{P}.cv1", out=cat.slice(0, 2 * c))
         for j in range(n):
             src, dst = cat.slice((1 + j) * c, (2 + j) * c), cat.slice((2 + j) * c, (3 + j) * c)
             if c3k2 and p["c3k"]:
@@ -738,6 +742,19 @@ class Program:
                     src_hw = shp[L.i]
                     if self.tc_eligible(Cn, src_hw[2], src_hw[0], src_hw[1]):
                         fold_se.add(L.i)
+        # Conv -> C2f pairs where the conv (64 output channels, tensor-core path) feeds nothing else and C2f.cv1 is 64 -> 64: cv1 runs as
+        # the second MMA group of the conv's launch (ysod_conv_tc_set_b2b_conv); the conv's own output never reaches HBM
+        fold_cv1: Dict[int, int] = {}
+        self._c2f_pre: Dict[int, View] = {}
+        for L in layers:
+            if (L.type == "C2f" and self.m.fuse_b2b and isinstance(L.f, int) and self.m.use_tc and self.code == _lib.BF16):
+                src = L.i - 1 if L.f == -1 else L.f
+                S = layers[src]
+                ssrc = S.i - 1 if S.f == -1 else S.f
+                if (S.type == "Conv" and S.i > 0 and isinstance(S.f, int) and consumers.get(src) == [L.i] and src not in home and src not in det_inputs
+                        and src not in fold_up and shp[src][2] == 64 and 2 * int(L.c2 * L.p["e"]) == 64
+                        and self.tc_eligible(S, shp[ssrc][2], shp[ssrc][0], shp[ssrc][1])):
+                    fold_cv1[src] = L.i
         for L in layers:
             P, p, t = f"model.{L.i}", L.p, L.type
             self._ctx = f"L{L.i}:{t}"
@@ -778,7 +795,7 @@ class Program:
             if L.i in fold_se:
                 out[L.i] = GatedView(out[src], self.se(out[src], P, None))
                 continue
-            o = home[L.i] if L.i in home else self.new(self.B, h, w, c)
+            o = None if L.i in fold_cv1 else (home[L.i] if L.i in home else self.new(self.B, h, w, c))
             x = None if L.i == 0 else out[src]
             gate = None
             if isinstance(x, GatedView):
@@ -806,6 +823,20 @@ class Program:
                         self._stem_direct_op = len(self.ops)
                         self.emit("ysod_stem_conv", None, self.B, self.H, self.W, _lib.ptr(wd), _lib.ptr(bd), co, k, s,
                                   pd, o.ptr(), self.code, o.cs, _lib.ACT["silu" if p["act"] else "none"])
+                elif L.i in fold_cv1:
+                    J = layers[fold_cv1[L.i]]
+                    cj = int(J.c2 * J.p["e"])
+                    cat = self.new(self.B, h, w, (2 + J.p["n"]) * cj)
+                    self._c2f_pre[J.i] = cat
+                    self.conv_bn(x, P, p["k"], p["s"], p["g"], p["act"], out=cat.slice(0, 2 * cj), pad=p["p"], gate=gate)
+                    w2, b2 = self.folded(f"model.{J.i}.cv1")
+                    w2d, b2d = self.dev_t(w2.view(64, 64), self.dt), self.dev_t(b2)
+                    self.call("ysod_conv_tc_set_b2b_conv", self.tc_handles[-1], _lib.ptr(w2d), _lib.ptr(b2d), _lib.ACT["silu"])
+                    fl2 = 2.0 * self.B * h * w * 64 * 64
+                    self.op_flops[-1] += fl2
+                    self.tc_flops += fl2
+                    self.op_desc[-1] += f" +L{J.i} C2f.cv1 64->64 (b2b)"
+                    o = None    # the layer's own output is never materialised (its only consumer is the fused cv1)
                 else:
                     self.conv_bn(x, P, p["k"], p["s"], p["g"], p["act"], out=o, pad=p["p"], gate=gate)
             elif t == "C2f":
@@ -1071,4 +1102,5 @@ class B200DetectionModel:
         """Debug/test helper: NCHW fp32 copy of layer `idx`'s output for the last forward with this shape."""
         u8 = x.dtype == torch.uint8
         prog = self.program(int(x.shape[0]), int(x.shape[1 if u8 else 2]), int(x.shape[2 if u8 else 3]), u8)
-        return prog.layer_out[idx].torch_nchw().float()
+        v = prog.layer_out[idx]
+        return None if v is None else v.torch_nchw().float()   # None: fused away (e.g. a Conv whose only consumer runs inside its launch)
