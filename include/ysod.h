@@ -87,6 +87,10 @@ int ysod_conv_tc_set_b2b(ysod_conv_tc* h, const void* w2, const float* bias2, in
 /* Plain back-to-back GEMM: a following `Conv(64, 64, 1)` + BN + act whose only input is this plan's output (block.py:233-248 C2f.cv1
  * right after a Conv layer) as the second MMA group of the same launch; create the plan with `out` = that second layer's destination. */
 int ysod_conv_tc_set_b2b_conv(ysod_conv_tc* h, const void* w2, const float* bias2, int act2);
+/* Back-to-back GEMM over a concatenation: block.py:233-248 `C2f.cv2(cat(cv1 output, bottleneck output))` (1x1, 96 -> 64) inside the
+ * launch of the block's last Bottleneck conv (3x3 32 -> 32, halo plan): K = 64 channels of x2 (TMA tile per output tile) + the staged
+ * 32-channel tile. w2 [64][96] bf16 in torch.cat order; out2 = the C2f output view. */
+int ysod_conv_tc_set_b2b_cat(ysod_conv_tc* h, const void* x2, int x2cs, const void* w2, const float* bias2, int act2, void* out2, int out2cs);
 /* SE (smallobj_modules.py:57-92) folded into the conv that consumes it: conv(x * a[n]) == conv with input-channel columns of the
  * weights scaled by a[n]. w: [rows][K] fp32 (K ordered (r,s,cin), BN folded); gate: [N][Cin] fp32; out: [N][rows][K] bf16. */
 int ysod_scale_weights(const float* w, int rows, int K, int Cin, const float* gate, int N, void* out, void* stream);

@@ -102,6 +102,75 @@ def test_conv_tc_tile_pairs(case):
         assert info[6] >= 10000, f"expected the pair plan, got {info}"
 
 
+@pytest.mark.parametrize("case", [(2, 40, 40, 32, 3, 2), (1, 24, 56, 64, 3, 1), (3, 64, 64, 64, 1, 1), (1, 20, 20, 128, 3, 1)],
+                         ids=lambda c: "x".join(str(v) for v in c))
+def test_conv_tc_b2b_plain(case):
+    """ysod_conv_tc_set_b2b_conv: Conv(Cin, 64, k, s) + SiLU -> [bf16 tile in shared memory] -> Conv(64, 64, 1) + SiLU in ONE launch
+    (the C2f.cv1-after-Conv fusion) against torch fp32 on the bf16-rounded intermediate. Ragged tiles and both conv kernels."""
+    from yolo_sod_b200 import lib
+    N, H, W, Cin, k, s = case
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(N, H, W, Cin, generator=g).bfloat16()
+    w1 = (torch.randn(64, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).bfloat16()
+    b1 = torch.randn(64, generator=g) * 0.1
+    w2 = (torch.randn(64, 64, generator=g) / 8).bfloat16()
+    b2 = torch.randn(64, generator=g) * 0.1
+    pad = k // 2
+    mid = F.silu(F.conv2d(x.float().permute(0, 3, 1, 2), w1.float(), b1, s, pad)).bfloat16().float()
+    ref = F.silu(F.conv2d(mid, w2.float().view(64, 64, 1, 1), b2))
+    Ho, Wo = mid.shape[2], mid.shape[3]
+    xd, w1d = x.cuda(), w1.float().permute(0, 2, 3, 1).reshape(64, -1).bfloat16().cuda()
+    b1d, w2d, b2d = b1.cuda(), w2.cuda(), b2.cuda()
+    od = torch.full((N, Ho, Wo, 64 + 8), 7.0, dtype=torch.bfloat16, device="cuda")
+    h = C.c_void_p()
+    lib.call("ysod_conv_tc_create_ex", C.byref(h), lib.ptr(xd), N, H, W, Cin, Cin, lib.ptr(w1d), lib.ptr(b1d), 64, 64, k, s, lib.ptr(od), lib.BF16,
+             64 + 8, None, 0, lib.ACT["silu"], 0)
+    lib.call("ysod_conv_tc_set_b2b_conv", h, lib.ptr(w2d), lib.ptr(b2d), lib.ACT["silu"])
+    lib.call("ysod_conv_tc_run", h, lib.stream_ptr())
+    torch.cuda.synchronize()
+    lib.load().ysod_conv_tc_destroy(h)
+    assert bool((od[..., 64:] == 7.0).all()), "kernel wrote outside its channel slice"
+    got = od[..., :64].float().cpu().permute(0, 3, 1, 2)
+    err = (got - ref).abs()
+    assert bool((err <= ref.abs() / 64 + ref.abs().max() / 64).all()), float(err.max())
+
+
+@pytest.mark.parametrize("case", [(2, 40, 40, True), (1, 24, 56, False), (4, 160, 160, True), (1, 16, 8, True)], ids=lambda c: "x".join(str(v) for v in c))
+def test_conv_tc_b2b_over_cat(case):
+    """ysod_conv_tc_set_b2b_cat: the C2f tail in one launch -- Bottleneck.cv2 (3x3, 32 -> 32, + residual) feeding C2f.cv2 =
+    Conv(96, 64, 1) + SiLU over cat(64-channel cv1 output, that tile); torch fp32 reference on the bf16-rounded intermediate."""
+    from yolo_sod_b200 import lib
+    N, H, W, res = case
+    g = torch.Generator().manual_seed(5)
+    cat = torch.randn(N, H, W, 96, generator=g).bfloat16()          # [cv1 output 0..63 | slot of the bottleneck output 64..95]
+    xin = torch.randn(N, H, W, 32, generator=g).bfloat16()          # the bottleneck's hidden map
+    w1 = (torch.randn(32, 32, 3, 3, generator=g) / 17).bfloat16()
+    b1 = torch.randn(32, generator=g) * 0.1
+    w2 = (torch.randn(64, 96, generator=g) / 10).bfloat16()
+    b2 = torch.randn(64, generator=g) * 0.1
+    y1 = F.silu(F.conv2d(xin.float().permute(0, 3, 1, 2), w1.float(), b1, 1, 1))
+    if res:
+        y1 = y1 + cat[..., 32:64].float().permute(0, 3, 1, 2)       # Bottleneck shortcut = the second half of the cv1 output
+    y1 = y1.bfloat16().float()
+    full = torch.cat([cat[..., :64].float().permute(0, 3, 1, 2), y1], 1)
+    ref = F.silu(F.conv2d(full, w2.float().view(64, 96, 1, 1), b2))
+    catd, xd = cat.cuda(), xin.cuda()
+    w1d = w1.float().permute(0, 2, 3, 1).reshape(32, -1).bfloat16().cuda()
+    b1d, w2d, b2d = b1.cuda(), w2.cuda(), b2.cuda()
+    od = torch.full((N, H, W, 64), 7.0, dtype=torch.bfloat16, device="cuda")
+    h = C.c_void_p()
+    lib.call("ysod_conv_tc_create_ex", C.byref(h), lib.ptr(xd), N, H, W, 32, 32, lib.ptr(w1d), lib.ptr(b1d), 32, 32, 3, 1, lib.ptr(catd, 64), lib.BF16,
+             96, lib.ptr(catd, 32) if res else None, 96 if res else 0, lib.ACT["silu"], 2)
+    lib.call("ysod_conv_tc_set_b2b_cat", h, lib.ptr(catd), 96, lib.ptr(w2d), lib.ptr(b2d), lib.ACT["silu"], lib.ptr(od), 64)
+    lib.call("ysod_conv_tc_run", h, lib.stream_ptr())
+    torch.cuda.synchronize()
+    lib.load().ysod_conv_tc_destroy(h)
+    assert torch.equal(catd.cpu(), cat), "the bottleneck's own output must not be stored"
+    got = od.float().cpu().permute(0, 3, 1, 2)
+    err = (got - ref).abs()
+    assert bool((err <= ref.abs() / 64 + ref.abs().max() / 64).all()), float(err.max())
+
+
 CASES = [
     # N, H, W, Cin, Cout, k, s, kwargs
     (1, 16, 16, 64, 64, 1, 1, {}),                                  # single K block, BK=64

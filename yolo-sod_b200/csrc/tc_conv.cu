@@ -70,6 +70,8 @@ struct TcParams {
     // epilogue adds the bias and runs the Detect decode (b2b 1: DFL box branch -> y[0..4); 2: class branch -> sigmoid -> y[4..4+nc)),
     // optionally also writing the fp32 raw map. The 3x3 conv's own output never goes to HBM.
     int b2b, b2_n, b2_raw_cs, b2_raw_off, b2_act;   // b2b 3: plain second layer (bias + b2_act -> bf16 -> the plan's own output map)
+    int b2_k2;      // b2b 4 (ysod_conv_tc_set_b2b_cat): the second layer's input is cat(extra 64-channel tensor, this tile): b2_k2 = 64 extra K
+                    // channels arrive per tile by TMA (tmA2) into their own two-slot ring; the second layer's output leaves through tmO2
     const __nv_bfloat16* b2_w;   // [b2_n][64] bf16, K-major
     const float* b2_bias;        // [b2_n]
     float* b2_raw;               // NHWC fp32 raw map (pixel stride b2_raw_cs), channels [b2_raw_off, ...), or nullptr
@@ -275,7 +277,8 @@ struct TileIter {
 template <bool HALO>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmO, const TcParams p) {
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmO2,
+               const TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = smem_u32(smem_raw);
     const uint32_t base = (smem0 + 1023u) & ~1023u;
@@ -296,8 +299,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* const bias_s = reinterpret_cast<float*>(smem_raw + (bias_smem - smem0));
     // back-to-back GEMM operands (b2b): W2 tile (1 KB aligned, b2_n rows of 128 B), its bias, one mbarrier per epilogue group
     const uint32_t b2_w_smem = stage_out + (uint32_t)p.stage_bufs * (uint32_t)(p.stage_split ? 1 : p.n_units) * 128u * p.row_bytes;
-    const uint32_t b2_bias_smem = b2_w_smem + 128u * (uint32_t)p.b2_n;
-    const uint32_t b2_bar = b2_bias_smem + 4u * (uint32_t)p.b2_n;
+    const uint32_t b2_wb_smem = b2_w_smem + 128u * (uint32_t)p.b2_n;                     // b2b 4: W2 columns of the staged 32 channels (64 B rows)
+    const uint32_t b2_bias_smem = b2_wb_smem + (p.b2b == 4 ? 64u * (uint32_t)p.b2_n : 0u);
+    const uint32_t b2_bar = b2_bias_smem + 4u * (uint32_t)p.b2_n;                        // b2_bar[2], then (b2b 4) a2_full[2], a2_empty[2]
+    const uint32_t a2_full = b2_bar + 16u, a2_empty = b2_bar + 32u;
+    const uint32_t a2_smem = (b2_bar + 48u + 1023u) & ~1023u;                            // b2b 4: two 16 KB tiles of the extra operand
+    const uint32_t stage2_smem = a2_smem + 2u * 16384u;                                  // b2b 4: two 16 KB staging tiles of the second layer's output
     float* const b2_bias_s = reinterpret_cast<float*>(smem_raw + (b2_bias_smem - smem0));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -327,6 +334,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (p.b2b) {
             mbar_init(b2_bar, 1);
             mbar_init(b2_bar + 8u, 1);
+            if (p.b2b == 4) {
+                for (int g2 = 0; g2 < 2; ++g2) {
+                    mbar_init(a2_full + 8u * g2, 1);
+                    mbar_init(a2_empty + 8u * g2, 1);
+                }
+            }
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -340,10 +353,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = threadIdx.x; i < p.cout_pad; i += EPI_THREADS) bias_s[i] = bscale * __ldg(p.bias + i);
         if (p.b2b) {
             // W2 rows (64 bf16 = 128 B) in the K-major SWIZZLE_128B layout: 16 B piece c of row r at r * 128 + ((c ^ (r & 7)) << 4)
+            const int w2ld = 64 + (p.b2b == 4 ? 32 : 0);   // b2b 4: W2 rows are [64 extra-operand channels | 32 staged channels]
             for (int i = threadIdx.x; i < p.b2_n * 8; i += EPI_THREADS) {
                 const int r = i >> 3, c = i & 7;
-                const uint4 w = __ldg(reinterpret_cast<const uint4*>(p.b2_w + (size_t)r * 64 + c * 8));
+                const uint4 w = __ldg(reinterpret_cast<const uint4*>(p.b2_w + (size_t)r * w2ld + c * 8));
                 st_shared_v4(b2_w_smem + (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)), w.x, w.y, w.z, w.w);
+            }
+            if (p.b2b == 4) {   // the staged-channel columns as 64 B rows, SWIZZLE_64B: piece c of row r at r * 64 + ((c ^ ((r >> 1) & 3)) << 4)
+                for (int i = threadIdx.x; i < p.b2_n * 4; i += EPI_THREADS) {
+                    const int r = i >> 2, c = i & 3;
+                    const uint4 w = __ldg(reinterpret_cast<const uint4*>(p.b2_w + (size_t)r * w2ld + 64 + c * 8));
+                    st_shared_v4(b2_wb_smem + (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4)), w.x, w.y, w.z, w.w);
+                }
             }
             for (int i = threadIdx.x; i < p.b2_n; i += EPI_THREADS) b2_bias_s[i] = __ldg(p.b2_bias + i);
             fence_async_smem();
@@ -492,6 +513,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int img = ti.img;
                     const int oh0 = ti.th * 16, ow0 = ti.tw * 8;
                     const int n0 = ti.nt * p.BN;
+                    if (p.b2b == 4) {
+                        // the tile's 16 x 8 pixels of the second layer's other input (64 channels, 128 B rows): slot = tile parity =
+                        // the epilogue group that consumes it; freed by the commit of that group's second MMA burst
+                        const int g2 = tcount & 1;
+                        mbar_wait(a2_empty + 8u * g2, (uint32_t)(((tcount >> 1) & 1) ^ 1));
+                        mbar_expect_tx(a2_full + 8u * g2, 16384u);
+                        tma_load_4d(a2_smem + (uint32_t)g2 * 16384u, &tmA2, a2_full + 8u * g2, 0, ow0, oh0, img);
+                    }
                     for (int cc = 0; cc < cchunks; ++cc) {
                         // ONE halo copy per 64-channel chunk: input rows oh0-1..oh0+16, columns ow0-1..ow0+8 (180 pixel rows of 128 B)
                         const int aslot = abase_c + sa_c;
@@ -781,7 +810,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int asel = 0;   // accumulator of tile i is i % 4 = 2 * asel + grp for this group's tiles
         const uint32_t row0 = sb + (uint32_t)m * p.row_bytes;
         const uint32_t swz_x = (row0 >> 7) & swz_mask;   // swizzle XOR term of this thread's staging row
-        uint32_t acc_phase = 0, b2_phase = 0;
+        uint32_t acc_phase = 0, b2_phase = 0, a2_phase = 0;
         TileIter ti;
         ti.init(p.pair ? 2 * blockIdx.x + grp : blockIdx.x, p);   // pairs: group g owns tile g of every pair of this CTA
         if (!p.pair && grp) ti.step(p);
@@ -927,20 +956,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 // ===== back-to-back GEMM: the staged tile is the A operand of the 1x1 head conv =====
                 const uint32_t d2col = (uint32_t)(4 * BN + grp * p.b2_n);
                 if (leader_warp && elect_one()) {
-                    tc_fence_after();
                     const uint32_t idesc2 = (1u << 4) | (YSOD_UMMA_AB_FORMAT << 7) | (YSOD_UMMA_AB_FORMAT << 10) | ((uint32_t)(p.b2_n >> 3) << 17) | ((128u >> 4) << 24);
                     const uint32_t hi128 = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 8 rows x 128 B, SWIZZLE_128B
-                    const uint32_t a_lo = umma_lo(sb), b_lo = umma_lo(b2_w_smem);
+                    if (p.b2b == 4) {
+                        // D2 = [extra operand (64 ch, TMA tile) | staged tile (32 ch, 64 B rows)] x W2^T
+                        mbar_wait(a2_full + 8u * grp, a2_phase);
+                        tc_fence_after();
+                        const uint32_t hi64 = (512u >> 4) | (1u << 14) | (4u << 29);  // SBO = 8 rows x 64 B, SWIZZLE_64B
+                        const uint32_t x_lo = umma_lo(a2_smem + (uint32_t)grp * 16384u), wa_lo = umma_lo(b2_w_smem);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        tc_mma_bf16(tmem_acc + d2col, umma_desc(hi128, a_lo + 2u * k), umma_desc(hi128, b_lo + 2u * k), idesc2, (uint32_t)(k != 0));
+                        for (int k = 0; k < 4; ++k)
+                            tc_mma_bf16(tmem_acc + d2col, umma_desc(hi128, x_lo + 2u * k), umma_desc(hi128, wa_lo + 2u * k), idesc2, (uint32_t)(k != 0));
+                        const uint32_t s_lo = umma_lo(sb), wb_lo = umma_lo(b2_wb_smem);
+#pragma unroll
+                        for (int k = 0; k < 2; ++k)
+                            tc_mma_bf16(tmem_acc + d2col, umma_desc(hi64, s_lo + 2u * k), umma_desc(hi64, wb_lo + 2u * k), idesc2, 1u);
+                        tc_commit(a2_empty + 8u * grp);   // the extra-operand slot may be refilled when these MMAs retire
+                    } else {
+                        tc_fence_after();
+                        const uint32_t a_lo = umma_lo(sb), b_lo = umma_lo(b2_w_smem);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            tc_mma_bf16(tmem_acc + d2col, umma_desc(hi128, a_lo + 2u * k), umma_desc(hi128, b_lo + 2u * k), idesc2, (uint32_t)(k != 0));
+                    }
                     tc_commit(b2_bar + 8u * grp);
                 }
+                a2_phase ^= 1u;
                 mbar_wait(b2_bar + 8u * grp, b2_phase);
                 b2_phase ^= 1u;
                 tc_fence_after();
                 const int n2chunks = p.b2_n >> 4;
-                if (p.b2b == 3) {
+                if (p.b2b >= 3) {
                     // plain second layer (a 1x1 Conv + BN + act, conv.py:37-55): bias, activation, bf16, back into the SAME staging
                     // buffer (its first life, the A operand, ended when b2_bar fired) and out through the plan's own output map
                     for (int ch2 = cg; ch2 < n2chunks; ch2 += 2) {
@@ -958,17 +1004,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                             for (int j = 0; j < 16; ++j) g[j] = __uint_as_float(v2[j]) + b2_bias_s[ch2 * 16 + j];
                         }
+                        // kind 3 re-uses the staging buffer (128 B rows); kind 4 has its own 128 B-row output staging tile
+                        const uint32_t orow = p.b2b == 4 ? stage2_smem + (uint32_t)grp * 16384u + (uint32_t)m * 128u : row0;
+                        const uint32_t oswz = p.b2b == 4 ? (uint32_t)(m & 7) : swz_x;
                         const uint32_t p0 = (uint32_t)(ch2 * 2);
 #pragma unroll
                         for (int j = 0; j < 2; ++j)
-                            st_shared_v4(row0 + (((p0 + j) ^ swz_x) << 4), pack_bf16(g[8 * j], g[8 * j + 1]), pack_bf16(g[8 * j + 2], g[8 * j + 3]),
+                            st_shared_v4(orow + (((p0 + j) ^ oswz) << 4), pack_bf16(g[8 * j], g[8 * j + 1]), pack_bf16(g[8 * j + 2], g[8 * j + 3]),
                                          pack_bf16(g[8 * j + 4], g[8 * j + 5]), pack_bf16(g[8 * j + 6], g[8 * j + 7]));
                     }
                     tc_fence_before();
                     fence_async_smem();
                     epi_barrier(grp);
                     if (leader_warp && elect_one()) {
-                        tma_store_4d(&tmO, sb, 0, ow0, oh0, img);
+                        if (p.b2b == 4) tma_store_4d(&tmO2, stage2_smem + (uint32_t)grp * 16384u, 0, ow0, oh0, img);
+                        else tma_store_4d(&tmO, sb, 0, ow0, oh0, img);
                         bulk_commit();
                     }
                     continue;
@@ -1092,7 +1142,7 @@ EncodeTiledFn get_encode() {
 
 struct ConvTc {
     bool halo;
-    CUtensorMap tmA, tmB, tmO;
+    CUtensorMap tmA, tmB, tmO, tmA2, tmO2;
     TcParams p;
     dim3 grid;
     size_t smem;
@@ -1452,8 +1502,8 @@ int ysod_conv_tc_run(ysod_conv_tc* h, cudaStream_t stream) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (h->c.halo) YSOD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, h->c.tmA, h->c.tmB, h->c.tmO, h->c.p));
-    else YSOD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, h->c.tmA, h->c.tmB, h->c.tmO, h->c.p));
+    if (h->c.halo) YSOD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, h->c.tmA, h->c.tmB, h->c.tmO, h->c.tmA2, h->c.tmO2, h->c.p));
+    else YSOD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, h->c.tmA, h->c.tmB, h->c.tmO, h->c.tmA2, h->c.tmO2, h->c.p));
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
 }
@@ -1520,6 +1570,49 @@ int ysod_conv_tc_set_b2b_conv(ysod_conv_tc* h, const void* w2, const float* bias
     c.smem += extra;
     p.tmem_cols = 512;
     p.b2b = 3; p.b2_n = 64; p.b2_w = (const __nv_bfloat16*)w2; p.b2_bias = bias2; p.b2_act = act2;
+    p.b2_raw = nullptr; p.b2_y = nullptr;
+    return YSOD_OK;
+}
+
+// Back-to-back GEMM over a concatenation: C2f.cv2 (block.py:233-248: `cv2(cat(cv1 halves, bottleneck output))`, a 1x1 Conv(96 -> 64))
+// runs inside the launch of the block's last Bottleneck conv (3x3, 32 -> 32, halo plan). Its K = 96 input channels are the staged
+// 32-channel tile plus the 64 channels of `x2` (the cv1 output), whose 16 x 8 pixel tile is TMA-loaded per output tile into a two-slot
+// ring. w2: [64][96] bf16, columns [0,64) = the x2 channels, [64,96) = the staged channels (= torch.cat order); out2: the 64-channel
+// destination (NHWC view, pixel stride out2cs). The Bottleneck conv's own output is never stored.
+int ysod_conv_tc_set_b2b_cat(ysod_conv_tc* h, const void* x2, int x2cs, const void* w2, const float* bias2, int act2, void* out2, int out2cs) {
+    YSOD_CHECK_ARG(h && x2 && w2 && bias2 && out2, "ysod_conv_tc_set_b2b_cat: null");
+    ConvTc& c = h->c;
+    TcParams& p = c.p;
+    YSOD_CHECK_ARG(c.halo && p.BN == 32 && p.Cout == 32 && p.n_tiles == 1 && !p.out_f32 && p.n_units == 1 && !p.stage_split && !p.up2 && p.row_bytes == 64 &&
+                   p.dec_y == nullptr && !p.b2b && !p.no_store && !p.pair,
+                   "ysod_conv_tc_set_b2b_cat: plan must be a 3x3 32 -> 32 bf16 conv on the halo kernel (BN %d, units %d, split %d, pair %d)", p.BN,
+                   p.n_units, p.stage_split, p.pair);
+    YSOD_CHECK_ARG(act2 == YSOD_ACT_SILU || act2 == YSOD_ACT_NONE, "ysod_conv_tc_set_b2b_cat: activation %d unsupported", act2);
+    YSOD_CHECK_ARG(((uintptr_t)w2 % 16) == 0 && ((uintptr_t)x2 % 16) == 0 && ((uintptr_t)out2 % 16) == 0 && x2cs % 8 == 0 && out2cs % 8 == 0,
+                   "ysod_conv_tc_set_b2b_cat: alignment");
+    EncodeTiledFn enc = get_encode();
+    YSOD_CHECK_ARG(enc != nullptr, "ysod_conv_tc_set_b2b_cat: cuTensorMapEncodeTiled unavailable");
+    for (int which = 0; which < 2; ++which) {
+        void* base = which ? out2 : const_cast<void*>(x2);
+        const int cs = which ? out2cs : x2cs;
+        cuuint64_t dims[4] = {64, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.N};
+        cuuint64_t strides[3] = {(cuuint64_t)cs * 2, (cuuint64_t)p.Wo * cs * 2, (cuuint64_t)p.Ho * p.Wo * cs * 2};
+        cuuint32_t box[4] = {64, 8, 16, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = enc(which ? &c.tmO2 : &c.tmA2, YSOD_TMAP_16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, which ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            ysod_set_error("ysod_conv_tc_set_b2b_cat: cuTensorMapEncodeTiled(%s) failed with %d", which ? "out2" : "x2", (int)r);
+            return YSOD_ERR_CUDA;
+        }
+    }
+    // W2 (64 x 128 B + 64 x 64 B) + bias + 6 barriers + alignment + 2 extra-operand tiles + 2 output staging tiles
+    const size_t extra = 128u * 64u + 64u * 64u + 4u * 64u + 48u + 1024u + 4u * 16384u;
+    YSOD_CHECK_ARG(c.smem + extra <= 227 * 1024, "ysod_conv_tc_set_b2b_cat: shared memory plan too large (%zu)", c.smem + extra);
+    c.smem += extra;
+    p.tmem_cols = 256;   // 4 x 32 accumulator columns + 2 x 64 for the second layer
+    p.b2b = 4; p.b2_n = 64; p.b2_k2 = 64; p.b2_w = (const __nv_bfloat16*)w2; p.b2_bias = bias2; p.b2_act = act2;
     p.b2_raw = nullptr; p.b2_y = nullptr;
     return YSOD_OK;
 }

@@ -268,6 +268,25 @@ class Program:
         else:
             cat = self.new(x.N, x.H, x.W, (2 + n) * c)
             self.conv_bn(x, f"{P}.cv1", out=cat.slice(0, 2 * c))
+        fuse_cv2 = (self.m.fuse_b2b and not c3k2 and n == 1 and c == 32 and out.C == 64 and p["g"] == 1 and self.m.use_tc
+                    and self.code == _lib.BF16 and cat.H >= 16 and cat.W >= 8
+                    and cat.H * cat.W / (-(-cat.H // 16) * -(-cat.W // 8) * 128.0) >= 0.75)   # the halo (16 x 8 tile) plan will be chosen
+        if fuse_cv2:
+            # cv2 (1x1, 96 -> 64) runs inside the launch of the Bottleneck's second 3x3 conv (ysod_conv_tc_set_b2b_cat): its input
+            # cat(cv1 output, bottleneck output) = the 64-channel cv1 slice (TMA tile) + the staged 32-channel tile
+            src = cat.slice(c, 2 * c)
+            mid = self.conv_bn(src, f"{P}.m.0.cv1", 3)
+            dummy = View(cat.buf, cat.off + 2 * c, cat.N, cat.H, cat.W, c, cat.cs)     # never written: the tensor map needs an address
+            self.conv_bn(mid, f"{P}.m.0.cv2", 3, out=dummy, res=src if p["shortcut"] else None)
+            w2, b2 = self.folded(f"{P}.cv2")
+            w2d, b2d = self.dev_t(w2.view(64, 3 * c), self.dt), self.dev_t(b2)
+            self.call("ysod_conv_tc_set_b2b_cat", self.tc_handles[-1], cat.ptr(), cat.cs, _lib.ptr(w2d), _lib.ptr(b2d), _lib.ACT["silu"],
+                      out.ptr(), out.cs)
+            fl2 = 2.0 * cat.N * cat.H * cat.W * 64 * 3 * c
+            self.op_flops[-1] += fl2
+            self.tc_flops += fl2
+            self.op_desc[-1] += " +C2f.cv2 96->64 over cat (b2b)"
+            return
         for j in range(n):
             src, dst = cat.slice((1 + j) * c, (2 + j) * c), cat.slice((2 + j) * c, (3 + j) * c)
             if c3k2 and p["c3k"]:

@@ -34,6 +34,7 @@ PROTOTYPES = {
     "ysod_conv_tc_set_decode": (i32, [vp, vp, i32, i32, i32, f32]),
     "ysod_conv_tc_set_b2b": (i32, [vp, vp, vp, i32, i32, vp, i32, i32, i32, f32, vp, i32, i32]),
     "ysod_conv_tc_set_b2b_conv": (i32, [vp, vp, vp, i32]),
+    "ysod_conv_tc_set_b2b_cat": (i32, [vp, vp, i32, vp, vp, i32, vp, i32]),
     "ysod_scale_weights": (i32, [vp, i32, i32, i32, vp, i32, vp, vp]),
     "ysod_conv_tc_run": (i32, [vp, vp]),
     "ysod_conv_tc_info": (i32, [vp, C.POINTER(i32)]),
