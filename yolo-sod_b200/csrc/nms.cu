@@ -404,17 +404,25 @@ nms_chunk_kernel(const float* __restrict__ pred, int nc, int A, int cap, int mul
     // thr * (1 +- 2^-20); thresholds at / near zero take the IEEE division for every pair (see nms_greedy_kernel)
     const bool band = thr_f > 1.0e-6f;
     const float thr_hi = band ? __fmul_rn(thr_f, 1.0000009537f) : INFINITY, thr_lo = band ? __fmul_rn(thr_f, 0.9999990463f) : -INFINITY;
+    // The chunk's 32 candidate boxes live in shared memory, double-buffered: the next chunk's boxes are requested at the top of an
+    // iteration and parked at its end, so neither the per-chunk tests nor the serial resolution wait on a global load (the sweep is a
+    // chain of dependent chunks: its length x the latency per chunk IS the kernel time).
+    __shared__ float4 s_cbox[2][32];
     if (tid == 0) s_kept = 0;
+    if (tid < 32) s_cbox[0][tid] = tid < n ? boxes[tid] : make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     int kept = 0;
-    for (int c0 = 0; c0 < n && kept < max_det; c0 += 32) {
+    for (int c0 = 0, cur = 0; c0 < n && kept < max_det; c0 += 32, cur ^= 1) {
         const int m = min(32, n - c0);
+        const bool ldn = tid < 32 && c0 + 32 + tid < n;
+        float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ldn) nxt = boxes[c0 + 32 + tid];      // in flight during this chunk
         if (tid == 0) s_sup = 0u;
         if (tid < 32) s_row[tid] = 0u;
         __syncthreads();
         // candidate `lane` of the chunk
         const bool cvalid = lane < m;
-        const float4 cj = cvalid ? boxes[c0 + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 cj = cvalid ? s_cbox[cur][lane] : make_float4(0.f, 0.f, 0.f, 0.f);
         // (a) against the kept list: warp w takes kept boxes w, w + 32, ...
         bool sup = false;
         if (cvalid) {
@@ -427,7 +435,7 @@ nms_chunk_kernel(const float* __restrict__ pred, int nc, int A, int cap, int mul
             const int a = warp;
             bool s2 = false;
             if (a < m && cvalid && lane > a) {
-                const float4 ba = boxes[c0 + a];
+                const float4 ba = s_cbox[cur][a];
                 const float aarea = __fmul_rn(__fsub_rn(ba.z, ba.x), __fsub_rn(ba.w, ba.y));
                 s2 = iou_exceeds(ba, aarea, cj, thr_f, thr_hi, thr_lo);
             }
@@ -443,7 +451,7 @@ nms_chunk_kernel(const float* __restrict__ pred, int nc, int A, int cap, int mul
                 const int a = __ffs(alive) - 1;
                 alive &= ~(1u << a);
                 alive &= ~s_row[a];
-                const float4 ba = boxes[c0 + a];
+                const float4 ba = s_cbox[cur][a];
                 kbox[k] = ba;
                 karea[k] = __fmul_rn(__fsub_rn(ba.z, ba.x), __fsub_rn(ba.w, ba.y));
                 keep_idx[k] = c0 + a;
@@ -451,6 +459,7 @@ nms_chunk_kernel(const float* __restrict__ pred, int nc, int A, int cap, int mul
             }
             s_kept = k;
         }
+        if (tid < 32) s_cbox[cur ^ 1][tid] = nxt;
         __syncthreads();
         kept = s_kept;
     }
@@ -550,7 +559,7 @@ int ysod_nms_batched(const float* pred, int B, int nc, int A, float conf_thres, 
                                                     agnostic ? 0.0f : max_wh, w.boxes);
         YSOD_LAUNCH_CHECK();
     }
-    if (max_det <= 2040) {   // kept-list formulation (24 B per kept box of dynamic shared memory + 136 B static <= 48 KB): the detection path (max_det = 300)
+    if (max_det <= 1990) {   // kept-list formulation (24 B per kept box of dynamic shared memory + 1.2 KB static <= 48 KB): the detection path (max_det = 300)
         ysod_launch(nms_chunk_kernel, B, GREEDY_THREADS, (size_t)max_det * 24, stream, pred, nc, A, cap, multi_label, max_det, thr_f, w.boxes, w.order,
                                                                               w.sscore, w.cls, w.count, out_det, out_index, out_count);
         YSOD_LAUNCH_CHECK();
@@ -614,7 +623,7 @@ int ysod_nms_boxes(const float* boxes, const float* scores, int n, float thr_f, 
     YSOD_LAUNCH_CHECK();
     ysod_launch(nms_reorder_boxes_kernel, ysod_cdiv(n, 256), 256, 0, stream, (const float4*)boxes, order, count, sorted);
     YSOD_LAUNCH_CHECK();
-    if (max_keep <= 2040) {
+    if (max_keep <= 1990) {
         ysod_launch(nms_chunk_kernel, 1, GREEDY_THREADS, (size_t)max_keep * 24, stream, nullptr, 0, 0, n, 0, max_keep, thr_f, sorted, order, sscore, nullptr,
                                                                                count, nullptr, keep_out, nkeep_out);
         YSOD_LAUNCH_CHECK();
