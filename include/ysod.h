@@ -195,6 +195,8 @@ int ysod_mha_window_nhwc(const void* q, const void* k, const void* v, int ld, in
  * wbf16 (37440 bf16): dw[3][3][64] | in_proj_weight[192][64] | out_proj.weight[64][64] | mlp.0.weight[128][64] | mlp.2.weight[64][128] |
  * pw.weight with BN folded [64][64].  pf32 (768 fp32): norm1.weight | norm1.bias | in_proj_bias | out_proj.bias | norm2.weight |
  * norm2.bias | mlp.0.bias | mlp.2.bias | folded BN bias. */
+/* Pre-folded by the caller: norm1 gamma / beta into in_proj, norm2's into mlp.0, log2(e) / sqrt(head_dim) into in_proj's Q rows; the
+ * norm slots of pf32 are ignored (swin_fused.cu). */
 int ysod_swin64_fused(const void* x, int N, int H, int W, int xcs, const void* wbf16, const float* pf32, void* out, int ocs, int window,
                       int heads, void* stream);
 

@@ -123,8 +123,10 @@ __device__ __forceinline__ void bias_init(float (*acc)[4], const float* b, int t
         acc[nb][0] = bv.x; acc[nb][1] = bv.y; acc[nb][2] = bv.x; acc[nb][3] = bv.y;
     }
 }
-// LayerNorm over the 64 channels of rows g and g+8 (values in accumulator layout), result as A fragments
-__device__ __forceinline__ void layernorm_frag(uint32_t (*a)[4], const float (*v)[4], const float* gamma, const float* beta, int t) {
+// LayerNorm over the 64 channels of rows g and g+8 (values in accumulator layout), result as A fragments. The affine part (gamma, beta)
+// is folded into the weights / bias of the linear layer that consumes the result (W' = W diag(gamma), b' = b + W beta: the caller's
+// job, see ysod_swin64_fused), so normalising is one FFMA per element: v * rstd - mean * rstd.
+__device__ __forceinline__ void layernorm_frag(uint32_t (*a)[4], const float (*v)[4]) {
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) { s0 += v[nb][0] + v[nb][1]; s1 += v[nb][2] + v[nb][3]; }
@@ -133,21 +135,25 @@ __device__ __forceinline__ void layernorm_frag(uint32_t (*a)[4], const float (*v
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
         const float d0 = v[nb][0] - m0, d1 = v[nb][1] - m0, d2 = v[nb][2] - m1, d3 = v[nb][3] - m1;
-        q0 += d0 * d0 + d1 * d1;
-        q1 += d2 * d2 + d3 * d3;
+        q0 = fmaf(d0, d0, fmaf(d1, d1, q0));
+        q1 = fmaf(d2, d2, fmaf(d3, d3, q1));
     }
     const float r0 = rsqrtf(quad_sum(q0) * (1.0f / 64.0f) + 1e-5f), r1 = rsqrtf(quad_sum(q1) * (1.0f / 64.0f) + 1e-5f);
+    const float c0 = -m0 * r0, c1 = -m1 * r1;
     float y[8][4];
 #pragma unroll
     for (int nb = 0; nb < 8; ++nb) {
-        const float2 gm = *reinterpret_cast<const float2*>(gamma + nb * 8 + 2 * t);
-        const float2 bt = *reinterpret_cast<const float2*>(beta + nb * 8 + 2 * t);
-        y[nb][0] = (v[nb][0] - m0) * r0 * gm.x + bt.x;
-        y[nb][1] = (v[nb][1] - m0) * r0 * gm.y + bt.y;
-        y[nb][2] = (v[nb][2] - m1) * r1 * gm.x + bt.x;
-        y[nb][3] = (v[nb][3] - m1) * r1 * gm.y + bt.y;
+        y[nb][0] = fmaf(v[nb][0], r0, c0);
+        y[nb][1] = fmaf(v[nb][1], r0, c0);
+        y[nb][2] = fmaf(v[nb][2], r1, c1);
+        y[nb][3] = fmaf(v[nb][3], r1, c1);
     }
     acc_to_frag<4>(a, y);
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -183,7 +189,6 @@ swin64_fused_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, in
     __syncthreads();
 
     const long long nwin = (long long)N * nWh * nWw;
-    const float qscale = 0.17677669529663687f;   // 1 / sqrt(32)
     for (long long win = (long long)blockIdx.x * NGROUP + grp; win < nwin; win += (long long)gridDim.x * NGROUP) {
         const int wj = (int)(win % nWw);
         const int wi = (int)((win / nWw) % nWh);
@@ -264,7 +269,7 @@ swin64_fused_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, in
             f = unpack2(raw[ks][3]); x1[2 * ks + 1][2] = f.x; x1[2 * ks + 1][3] = f.y;
         }
         uint32_t xn[4][4];
-        layernorm_frag(xn, x1, sm.pf + F_LN1G, sm.pf + F_LN1B, t);
+        layernorm_frag(xn, x1);
 
         // ---- D. packed in_proj: K and V go to shared memory (all rows of the window are needed by every warp), Q stays in registers
         uint32_t qf[4][4];
@@ -289,11 +294,7 @@ swin64_fused_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, in
                 sg.vt[(h * HD + d + 1) * LDV + row0 + 8] = __float2bfloat16_rn(acc[nb][3]);
             }
             bias_init(acc, sm.pf + F_BQKV, t);                              // Q = rows [0,64), scaled by 1/sqrt(d)
-            gemm_frag<8, 4>(acc, xn, sm.wqkv, LDW, lane);
-#pragma unroll
-            for (int nb = 0; nb < 8; ++nb)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) acc[nb][e] *= qscale;
+            gemm_frag<8, 4>(acc, xn, sm.wqkv, LDW, lane);   // the caller folded log2(e) / sqrt(d) into these rows: S comes out in log2 units
             acc_to_frag<4>(qf, acc);   // K steps 0,1 = head 0 (d 0..31), 2,3 = head 1
         }
         group_barrier(grp);
@@ -324,8 +325,8 @@ swin64_fused_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, in
             float l0 = 0.f, l1 = 0.f;
 #pragma unroll
             for (int nb = 0; nb < 8; ++nb) {
-                s[nb][0] = __expf(s[nb][0] - mx0); s[nb][1] = __expf(s[nb][1] - mx0);
-                s[nb][2] = __expf(s[nb][2] - mx1); s[nb][3] = __expf(s[nb][3] - mx1);
+                s[nb][0] = ex2_approx(s[nb][0] - mx0); s[nb][1] = ex2_approx(s[nb][1] - mx0);
+                s[nb][2] = ex2_approx(s[nb][2] - mx1); s[nb][3] = ex2_approx(s[nb][3] - mx1);
                 l0 += s[nb][0] + s[nb][1];
                 l1 += s[nb][2] + s[nb][3];
             }
@@ -361,7 +362,7 @@ swin64_fused_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, in
         // ---- G/H. LayerNorm 2 -> Linear(64,128) -> exact GELU -> Linear(128,64) + residual
         {
             uint32_t xn2[4][4];
-            layernorm_frag(xn2, x1, sm.pf + F_LN2G, sm.pf + F_LN2B, t);
+            layernorm_frag(xn2, x1);
             uint32_t hf[8][4];
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -371,7 +372,7 @@ swin64_fused_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, in
 #pragma unroll
                 for (int nb = 0; nb < 8; ++nb)
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) acc[nb][e] = 0.5f * acc[nb][e] * (1.0f + ysod_erf_fast(acc[nb][e] * 0.70710678118654752440f));
+                    for (int e = 0; e < 4; ++e) acc[nb][e] = ysod_gelu_tanh(acc[nb][e]);
                 acc_to_frag<4>(&hf[half * 4], acc);
             }
             float acc[8][4];
@@ -421,6 +422,9 @@ swin64_fused_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, in
 }  // namespace
 
 // x / out: NHWC bf16 views (pixel strides xcs / ocs, multiples of 8, 16 B aligned) with 64 channels.
+// The caller pre-folds what is linear (engine.py does): norm1's gamma / beta into in_proj (W diag(gamma), b + W beta), norm2's into
+// mlp.0, and log2(e) / sqrt(head_dim) into the Q rows of in_proj (weight and bias) -- the kernel normalises without an affine part
+// and exponentiates with ex2. The norm slots of pf32 are ignored.
 // wbf16: dw[3][3][64] | in_proj_weight[192][64] | out_proj.weight[64][64] | mlp.0.weight[128][64] | mlp.2.weight[64][128] |
 //        pw.weight (BN folded)[64][64]                                                                   (37440 bf16)
 // pf32:  norm1.weight | norm1.bias | in_proj_bias[192] | out_proj.bias | norm2.weight | norm2.bias | mlp.0.bias[128] |

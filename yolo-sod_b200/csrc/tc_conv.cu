@@ -229,7 +229,7 @@ __device__ __forceinline__ void act16(float* f) {
             const float h = 0.5f * f[j];
             f[j] = fmaf(h, tanh_approx(h), h);
         }
-        else if (ACT == YSOD_ACT_GELU) f[j] = 0.5f * f[j] * (1.0f + ysod_erf_fast(f[j] * 0.70710678118654752440f));
+        else if (ACT == YSOD_ACT_GELU) f[j] = ysod_gelu_tanh(f[j]);
         else if (ACT == YSOD_ACT_RELU) f[j] = fmaxf(f[j], 0.0f);
     }
 }

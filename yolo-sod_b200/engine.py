@@ -335,12 +335,25 @@ class Program:
             g, b = sd[f"{P}.bn.weight"].float(), sd[f"{P}.bn.bias"].float()
             sc = g / torch.sqrt(sd[f"{P}.bn.running_var"].float() + BN_EPS)
             pw = sd[f"{P}.pw.weight"].float().view(64, 64) * sc.view(-1, 1)
-            wb = torch.cat([dww.view(64, 3, 3).permute(1, 2, 0).reshape(-1), sd[f"{A}.attn.in_proj_weight"].float().reshape(-1),
-                            sd[f"{A}.attn.out_proj.weight"].float().reshape(-1), sd[f"{A}.mlp.0.weight"].float().reshape(-1),
+            # what is linear is folded on the host (swin_fused.cu): LayerNorm affine parts into the linear layers that follow them,
+            # log2(e) / sqrt(head_dim) into the Q rows (the kernel's softmax exponentiates with ex2)
+            g1, be1 = sd[f"{A}.norm1.weight"].float(), sd[f"{A}.norm1.bias"].float()
+            g2, be2 = sd[f"{A}.norm2.weight"].float(), sd[f"{A}.norm2.bias"].float()
+            Wi, bi = sd[f"{A}.attn.in_proj_weight"].float(), sd[f"{A}.attn.in_proj_bias"].float()
+            W1, bm1 = sd[f"{A}.mlp.0.weight"].float(), sd[f"{A}.mlp.0.bias"].float()
+            bi = bi + Wi @ be1
+            Wi = Wi * g1.view(1, -1)
+            qs = math.log2(math.e) / math.sqrt(32.0)
+            Wi = torch.cat([Wi[:64] * qs, Wi[64:]])
+            bi = torch.cat([bi[:64] * qs, bi[64:]])
+            bm1 = bm1 + W1 @ be2
+            W1 = W1 * g2.view(1, -1)
+            wb = torch.cat([dww.view(64, 3, 3).permute(1, 2, 0).reshape(-1), Wi.reshape(-1),
+                            sd[f"{A}.attn.out_proj.weight"].float().reshape(-1), W1.reshape(-1),
                             sd[f"{A}.mlp.2.weight"].float().reshape(-1), pw.reshape(-1)])
-            pf = torch.cat([sd[f"{A}.norm1.weight"].float(), sd[f"{A}.norm1.bias"].float(), sd[f"{A}.attn.in_proj_bias"].float(),
-                            sd[f"{A}.attn.out_proj.bias"].float(), sd[f"{A}.norm2.weight"].float(), sd[f"{A}.norm2.bias"].float(),
-                            sd[f"{A}.mlp.0.bias"].float(), sd[f"{A}.mlp.2.bias"].float(),
+            pf = torch.cat([torch.ones(64), torch.zeros(64), bi,
+                            sd[f"{A}.attn.out_proj.bias"].float(), torch.ones(64), torch.zeros(64),
+                            bm1, sd[f"{A}.mlp.2.bias"].float(),
                             b - sd[f"{P}.bn.running_mean"].float() * sc])
             assert wb.numel() == 37440 and pf.numel() == 768
             wbd, pfd = self.dev_t(wb, self.dt), self.dev_t(pf)
