@@ -12,6 +12,7 @@
 // All are HBM-bound: NHWC, 8 channels (16 B of bf16) per thread access, fp32 math, warp-shuffle / shared-memory
 // reductions, deterministic two-stage global reductions (no float atomics).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -410,6 +411,78 @@ cbam_stats_img_kernel(const T* __restrict__ x, int HW, int C, int xcs, const flo
             }
             if (pix < p1 && gl == 0) sb[pix] = make_float2(su * inv_c, mx);
         }
+    }
+}
+
+// Per-thread asynchronous prefetch ring (cp.async / LDGSTS): a thread requests its next DEPTH 16-byte pieces straight into its own
+// shared-memory slots ([slot][thread]: conflict-free) without holding registers for them, and consumes the oldest. Nobody else reads a
+// thread's slots, so the ring needs no barrier -- only cp.async.wait_group. This multiplies the bytes a streaming kernel keeps in
+// flight (DEPTH x 16 B x threads) at constant register count.
+__device__ __forceinline__ void ysod_cp_async16(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;   // src-size 0: the 16 bytes are zero-filled, nothing is read
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void ysod_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void ysod_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// cbam_stats_img_kernel with the prefetch ring: identical arithmetic (same per-lane sums, same shuffle tree), DEPTH pixels in flight
+// per lane group instead of 4 register-held ones.
+template <typename T, int DEPTH>
+__global__ void __launch_bounds__(256)
+cbam_stats_ring_kernel(const T* __restrict__ x, int HW, int C, int xcs, const float* __restrict__ gate, float2* __restrict__ stats,
+                       int chunk, int iters) {
+    ysod_pdl_sync();
+    extern __shared__ __align__(16) uint8_t ring_raw[];       // [DEPTH][256] x 16 B (bf16) -- T = float uses two pieces per slot
+    constexpr int PIECES = sizeof(T) == 2 ? 1 : 2;
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(ring_raw);
+    const int G = C >> 3;
+    const int lg = __ffs(G) - 1;
+    const int n = blockIdx.y;
+    const int tid = threadIdx.x;
+    const int gl = tid & (G - 1), grp = tid >> lg, ngr = blockDim.x >> lg;
+    const int p0 = blockIdx.x * chunk, p1 = min(HW, p0 + chunk);
+    float gg[8];
+    {
+        const float4 g0 = *reinterpret_cast<const float4*>(gate + (size_t)n * C + gl * 8);
+        const float4 g1 = *reinterpret_cast<const float4*>(gate + (size_t)n * C + gl * 8 + 4);
+        gg[0] = g0.x; gg[1] = g0.y; gg[2] = g0.z; gg[3] = g0.w; gg[4] = g1.x; gg[5] = g1.y; gg[6] = g1.z; gg[7] = g1.w;
+    }
+    const T* xb = x + (size_t)n * HW * xcs + gl * 8;
+    float2* sb = stats + (size_t)n * HW;
+    const float inv_c = 1.0f / (float)C;
+    const int total = iters * 4;                 // pixel slots of this lane group: pixel j = p0 + grp + j * ngr (uniform trip count)
+    auto request = [&](int j) {
+        const int pix = p0 + grp + j * ngr;
+        const bool ok = j < total && pix < p1;
+        const uint32_t dst = ring + (uint32_t)(((j % DEPTH) * 256 + tid) * 16 * PIECES);
+        const T* src = xb + (size_t)(ok ? pix : p0) * xcs;
+#pragma unroll
+        for (int q = 0; q < PIECES; ++q) ysod_cp_async16(dst + 16 * q, reinterpret_cast<const char*>(src) + 16 * q, ok);
+        ysod_cp_async_commit();
+    };
+#pragma unroll
+    for (int j = 0; j < DEPTH - 1; ++j) request(j);
+    for (int j = 0; j < total; ++j) {
+        request(j + DEPTH - 1);
+        ysod_cp_async_wait<DEPTH - 1>();         // the group of slot j has landed
+        const int pix = p0 + grp + j * ngr;
+        float v[8];
+        ysod_vec8<T>::load(reinterpret_cast<const T*>(ring_raw + (size_t)(((j % DEPTH) * 256 + tid) * 16 * PIECES)), v);
+        float su = 0.f, mx = -INFINITY;
+        if (pix < p1) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float tv = v[e] * gg[e];
+                su += tv;
+                mx = fmaxf(mx, tv);
+            }
+        }
+        for (int o = G >> 1; o > 0; o >>= 1) {
+            su += __shfl_xor_sync(0xffffffffu, su, o);
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        }
+        if (pix < p1 && gl == 0) sb[pix] = make_float2(su * inv_c, mx);
     }
 }
 
@@ -1321,6 +1394,19 @@ int ysod_cbam_stats(const void* x, int dtype, int N, int HW, int C, int xcs, con
         S = ysod_cdiv(HW, chunk);
         const int iters = ysod_cdiv(chunk, 4 * ngr);
         dim3 grid(S, N);
+        // cp.async prefetch ring, 8 pixels in flight per lane group (profiles/r02_ab_blocks.json: 49.2 -> 41.0 us at 64 x 160^2, bit-identical;
+        // depth 16 loses occupancy to its 64 KB of shared memory); YSOD_RING_DEPTH=0 selects the register-held 4-deep kernel (A/B)
+        static const int ring_depth = getenv("YSOD_RING_DEPTH") ? atoi(getenv("YSOD_RING_DEPTH")) : 8;
+        if (ring_depth == 8 || ring_depth == 16) {
+            const size_t es = dtype == YSOD_BF16 ? 1 : 2;
+            if (ring_depth == 8) { YSOD_DISPATCH(dtype, (ysod_launch(cbam_stats_ring_kernel<T, 8>, grid, 256, 8 * 256 * 16 * es, st, (const T*)x, HW, C, xcs, gate, (float2*)stats, chunk, iters))); }
+            else {
+                YSOD_DISPATCH(dtype, (cudaFuncSetAttribute(cbam_stats_ring_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(16 * 256 * 16 * es))));
+                YSOD_DISPATCH(dtype, (ysod_launch(cbam_stats_ring_kernel<T, 16>, grid, 256, 16 * 256 * 16 * es, st, (const T*)x, HW, C, xcs, gate, (float2*)stats, chunk, iters)));
+            }
+            YSOD_LAUNCH_CHECK();
+            return YSOD_OK;
+        }
         YSOD_DISPATCH(dtype, (ysod_launch(cbam_stats_img_kernel<T>, grid, 256, 0, st, (const T*)x, HW, C, xcs, gate, (float2*)stats, chunk, iters)));
         YSOD_LAUNCH_CHECK();
         return YSOD_OK;
