@@ -293,6 +293,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per forward (default: the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-library-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="A/B: run every batch's NMS on the forward's stream (no cross-batch overlap)")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel event timing table to this JSON file")
     ap.add_argument("--quick", action="store_true", help="main timed loop only (for ncu launch lists): no e2e / per-kernel / latency legs")
     args = ap.parse_args()
@@ -335,9 +336,11 @@ def main():
     gather = ydist.DetectionGather(world, B, MAX_DET, dev, stream=side) if world > 1 else None
     n_in = 4
     if is_model:
-        yolo = YOLO(c["model"], dtype=torch.bfloat16, device=dev, seed=0)
+        # overlap_nms: batch i's NMS runs on a side stream under batch i+1's forward (two program slots; model.py)
+        yolo = YOLO(c["model"], dtype=torch.bfloat16, device=dev, seed=0, overlap_nms=not args.no_overlap)
         model = yolo.model
-        prog = model.program(B, IMGSZ, IMGSZ, False, False)
+        prog = model.program(B, IMGSZ, IMGSZ, False, False, 0)
+        nms_stream = yolo.nms_stream
         # rotating device-resident fp32 NCHW input batches (the forward reads them in place; a step touches GBs of activations >> 126 MB L2)
         xs = [synth.synth_images(B, IMGSZ, seed=100 * rank + i).to(dev) for i in range(n_in)]
 
@@ -347,6 +350,7 @@ def main():
     else:
         preds = [nms_stress_prediction(B, c["A"], c["nc"], c["dist"], seed0=1000 * rank + 100 * i).to(dev) for i in range(n_in)]
         prog = None
+        nms_stream = None
 
         def forward_nms(i):
             return ops.nms_padded(preds[i % n_in], CONF, IOU, max_det=MAX_DET)[:2]
@@ -358,10 +362,16 @@ def main():
             if mb < n_micro:
                 det, count = forward_nms(i * n_micro_max + mb)
             if world > 1:                 # the only data-path exchange: fixed-size detections over NVLink
-                gather(det, count)
+                if nms_stream is not None:
+                    with torch.cuda.stream(nms_stream):   # det / count are produced on the NMS stream: the gather follows them there
+                        gather(det, count)
+                else:
+                    gather(det, count)
         return det, count
 
     def barrier():
+        if is_model:
+            yolo.join()
         if gather is not None:
             gather.wait()
         torch.cuda.synchronize()
@@ -377,8 +387,10 @@ def main():
     e0.record()
     for i in range(args.steps):
         det, count = step(i)
+    if is_model:
+        yolo.join()                      # the last step's NMS (side stream) is inside the timed region
     if gather is not None:
-        gather.wait()                    # the last step's gather is inside the timed region
+        gather.wait()                    # ... and so is the last step's gather
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -417,6 +429,7 @@ def main():
     pending = []
     ev_in = [torch.cuda.Event() for _ in range(2)]
     ev_free = [torch.cuda.Event() for _ in range(2)]
+    ev_d2h = [torch.cuda.Event() for _ in range(2)]
 
     def h2d(i):
         s = i % 2
@@ -443,14 +456,18 @@ def main():
             det_b, cnt_b = rows.det, rows.count
             n = sum(int(r.shape[0]) for r in rows)
         ev_free[s].record(main_stream)
+        out_stream = nms_stream if (is_model and nms_stream is not None) else main_stream   # the stream det / count are produced on
+        with torch.cuda.stream(out_stream):
+            if world > 1:
+                gather(det_b, cnt_b)
+            # ONE D2H of this step's detections (padded rows; the counts travel separately). Consumed one step later.
+            hdet[s].copy_(det_b, non_blocking=True)
+            ev_d2h[s].record(out_stream)
         if world > 1:
-            gather(det_b, cnt_b)
             gather.wait()
-        # ONE D2H of this step's detections (padded rows; the counts are already on the host). It is consumed one step later:
-        # predict(i+1)'s own host sync orders it, so the transfer never costs a second round trip.
-        hdet[s].copy_(det_b, non_blocking=True)
         if i > 0:
-            consumed[0] += float(hdet[1 - s][0, 0, 4])   # the host touches step i-1's detections (complete: predict(i) synced after it)
+            ev_d2h[1 - s].synchronize()
+            consumed[0] += float(hdet[1 - s][0, 0, 4])   # the host touches step i-1's detections
         return n
 
     for s_ in range(2):
@@ -553,6 +570,7 @@ def main():
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             yolo.predict_padded(x1, CONF, IOU, MAX_DET)
+            yolo.join()                      # the batch's NMS (side stream in overlap mode) belongs to its latency
             b.record()
             b.synchronize()
             lat.append(a.elapsed_time(b))

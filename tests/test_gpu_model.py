@@ -286,6 +286,31 @@ def test_predict_end_to_end_matches_oracle_nms():
     assert len(list(g2)) == 2
 
 
+def test_overlap_nms_mode_gives_identical_results():
+    """YOLO(overlap_nms=True): batch i's NMS on a side stream under batch i+1's forward, two program slots. Same detections as the
+    serial mode for a sequence of different batches, through predict(), predict(stream=True) and predict_padded() + join()."""
+    from yolo_sod_b200.model import YOLO
+    spec = ycfg.get_spec(SOD)
+    sd = synth.synth_state_dict(spec, SOD, 0)
+    serial = YOLO(SOD, weights=sd, dtype=torch.bfloat16)
+    piped = YOLO(SOD, weights=sd, dtype=torch.bfloat16, overlap_nms=True)
+    batches = [synth.synth_images(2, 320, seed=30 + i).cuda() for i in range(5)]
+    want = [[r.boxes.data.clone() for r in serial.predict(b)] for b in batches]
+    gens = [piped.predict(b, stream=True) for b in batches[:4]]          # four batches in flight before the first is consumed
+    for w, g in zip(want, gens):
+        for a, r in zip(w, list(g)):
+            assert torch.equal(a, r.boxes.data)
+    for w, b in zip(want, batches):
+        for a, r in zip(w, piped.predict(b)):
+            assert torch.equal(a, r.boxes.data)
+    outs = [piped.predict_padded(b) for b in batches]
+    piped.join()
+    torch.cuda.synchronize()
+    for w, (det, cnt, _) in zip(want, outs):
+        for b_, a in enumerate(w):
+            assert int(cnt[b_]) == a.shape[0] and torch.equal(det[b_, :a.shape[0]], a)
+
+
 def test_fused_swin_block_matches_oracle_and_unfused_path():
     """Layer 28 (P2 SwinBlock, 64 ch): the single fused kernel vs the oracle layer output and vs the eleven-launch path.
     161 is not a multiple of 7 at 640^2 -> 160x160 maps exercise the zero-padded windows; 96^2 input -> 24x24 map (4x4 windows, ragged)."""

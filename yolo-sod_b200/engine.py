@@ -1083,8 +1083,10 @@ class B200DetectionModel:
         self.max_programs = max(1, int(max_programs))
         self.programs: "OrderedDict[tuple, Program]" = OrderedDict()
 
-    def program(self, B, H, W, src_u8=False, want_raw=True) -> Program:
-        key = (B, H, W, bool(src_u8), bool(want_raw))
+    def program(self, B, H, W, src_u8=False, want_raw=True, slot=0) -> Program:
+        """slot: independent copies of a program (own activation buffers, `y` and CUDA graph) for callers that keep two forwards in
+        flight, e.g. YOLO's overlap of step i's NMS with step i+1's forward."""
+        key = (B, H, W, bool(src_u8), bool(want_raw), int(slot))
         if key in self.programs:
             self.programs.move_to_end(key)
         else:
@@ -1101,7 +1103,7 @@ class B200DetectionModel:
         return self.programs[key]
 
     @torch.no_grad()
-    def forward(self, x, *args, static=None, want_raw=True, **kwargs):
+    def forward(self, x, *args, static=None, want_raw=True, slot=0, **kwargs):
         """x: (B,3,H,W) float tensor in [0,1] (NCHW, as the reference's forward takes it), or (B,H,W,3) uint8 BGR frames (what
         BasePredictor.preprocess receives, predictor.py:116-134; BGR->RGB, HWC->CHW and /255 are fused into the stem kernel).
         Returns (y, [raw maps]) as fresh tensors, like the reference's forward. `static=True` (or `static_outputs=True` at
@@ -1113,9 +1115,9 @@ class B200DetectionModel:
             raise ValueError(f"expected (B,3,H,W) float or (B,H,W,3) uint8, got {tuple(x.shape)} {x.dtype}")
         # host tensors are copied straight into the program's input buffer (pinned memory makes this asynchronous)
         if u8:
-            prog = self.program(int(x.shape[0]), int(x.shape[1]), int(x.shape[2]), True, want_raw)
+            prog = self.program(int(x.shape[0]), int(x.shape[1]), int(x.shape[2]), True, want_raw, slot)
         else:
-            prog = self.program(int(x.shape[0]), int(x.shape[2]), int(x.shape[3]), False, want_raw)
+            prog = self.program(int(x.shape[0]), int(x.shape[2]), int(x.shape[3]), False, want_raw, slot)
         with torch.cuda.device(self.device):
             return prog.run(x, self.static_outputs if static is None else bool(static))
 
