@@ -70,6 +70,10 @@ int ysod_conv_tc_create(ysod_conv_tc** handle, const void* x, int N, int H, int 
  * ysod_conv_tc_set_decode -- the predict path consumes `y` alone (detect/predict.py:25-32 takes preds[0]), so the fp32 raw maps
  * Detect.forward also returns (head.py:74) need not be materialised. `out` must still be a valid 16 B aligned device address. */
 #define YSOD_CONV_NO_STORE 0x20
+/* | 0x10000 (YSOD_CONV_NO_DUO): A/B switch -- 3x3 / stride-1 convs with 32 input and 32 output channels (C2f Bottlenecks at P2,
+ * block.py:343-356) normally run the halo kernel's pixel-duo plan (one MMA row = two adjacent output pixels, N = 64, 128 B operand
+ * rows: tc_conv.cu TcParams::duo); this bit keeps the 32-channel plan (N = 32, 64 B rows), which ysod_conv_tc_set_b2b_cat needs. */
+#define YSOD_CONV_NO_DUO 0x10000
 int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, int W, int Cin, int xcs, const void* wgt,
                            const float* bias, int Cout, int Cout_pad, int ksize, int stride, void* out, int out_dtype, int ocs,
                            const void* res, int rcs, int act, int mode);

@@ -160,7 +160,7 @@ def test_conv_tc_b2b_over_cat(case):
     od = torch.full((N, H, W, 64), 7.0, dtype=torch.bfloat16, device="cuda")
     h = C.c_void_p()
     lib.call("ysod_conv_tc_create_ex", C.byref(h), lib.ptr(xd), N, H, W, 32, 32, lib.ptr(w1d), lib.ptr(b1d), 32, 32, 3, 1, lib.ptr(catd, 64), lib.BF16,
-             96, lib.ptr(catd, 32) if res else None, 96 if res else 0, lib.ACT["silu"], 2)
+             96, lib.ptr(catd, 32) if res else None, 96 if res else 0, lib.ACT["silu"], 2 | lib.CONV_NO_DUO)
     lib.call("ysod_conv_tc_set_b2b_cat", h, lib.ptr(catd), 96, lib.ptr(w2d), lib.ptr(b2d), lib.ACT["silu"], lib.ptr(od), 64)
     lib.call("ysod_conv_tc_run", h, lib.stream_ptr())
     torch.cuda.synchronize()
@@ -245,6 +245,35 @@ HALO_CASES = [
 def test_conv_tc_halo(case):
     *dims, kw = case
     _run_tc(*dims, mode=2, **kw)
+
+
+DUO_CASES = [
+    # 3x3 / stride-1, 32 -> 32 channels: the halo kernel's pixel-duo plan (one MMA row = two adjacent output pixels, tc_conv.cu TcParams::duo)
+    (1, 16, 16, {}),                                                # exactly one 16 x 16 tile
+    (2, 32, 48, dict(res=True)),                                    # 2 x 3 tiles per image + residual
+    (1, 30, 44, dict(res=True)),                                    # ragged in both directions (TMA clips the store, OOB fill pads the halo)
+    (3, 160, 160, dict(res=True, ocs_extra=64)),                    # the C2f Bottleneck at P2: dense hidden map in, slice of the 96-channel cat buffer out
+    (8, 160, 160, {}),                                              # ~5 tiles per CTA: both issuers / epilogue groups / sub-rings wrap
+    (2, 48, 32, dict(act="none")),
+]
+
+
+@pytest.mark.parametrize("case", DUO_CASES, ids=lambda c: "x".join(str(v) for v in c[:3]))
+def test_conv_tc_pixel_duo(case):
+    from yolo_sod_b200 import lib
+    N, H, W, kw = case
+    got, info = _run_tc(N, H, W, 32, 32, 3, 1, mode=0, **kw)
+    assert info[6] >= 20000 and info[2] == 64, f"the duo plan was not chosen: {info}"
+    # same operands on the 32-channel plan (N = 32 MMAs, 64 B rows): equal up to the accumulation order (one bf16 ulp)
+    plain, info2 = _run_tc(N, H, W, 32, 32, 3, 1, mode=lib.CONV_NO_DUO, **kw)
+    assert info2[6] < 20000 and info2[2] == 32
+    d = (got.float() - plain.float()).abs()
+    assert float(d.max()) <= 1.0 / 64 * float(plain.float().abs().max()), float(d.max())
+    assert float((d > 0).float().mean()) < 0.05, "more than rounding-order differences between the two plans"
+    if N == 1 and H == 16:
+        # a strided input view (pixels not contiguous in pairs) must fall back to the 32-channel plan
+        _, info3 = _run_tc(N, H, W, 32, 32, 3, 1, mode=0, xcs_extra=32)
+        assert info3[6] < 20000 and info3[2] == 32
 
 
 def _run_direct(dtype, N, H, W, Cin, Cout, k, s, g, act="silu", res=False, pad=None):

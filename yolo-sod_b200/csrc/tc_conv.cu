@@ -76,6 +76,13 @@ struct TcParams {
     const float* b2_bias;        // [b2_n]
     float* b2_raw;               // NHWC fp32 raw map (pixel stride b2_raw_cs), channels [b2_raw_off, ...), or nullptr
     float* b2_y;                 // y (B, 4+nc, A): geometry in dec_A / dec_off / dec_nc / dec_stride (dec_y stays null: no main-tile decode)
+    int duo;    // pixel-duo plan of the halo kernel for 3x3 / stride-1 convs with 32 input and 32 output channels: one MMA row = TWO horizontally
+                // adjacent output pixels (N = 64 = 2 x 32 channels), one K block = one 128 B shared-memory row = two adjacent input pixels.
+                // Output pair j of a row reads input pixels 2j-1 .. 2j+2 = the two pairs at halo offsets j and j+1, so the 3 x 3 filter becomes
+                // 3 rows x 2 pair-taps of K = 64 with a [64][6 * 64] weight matrix that holds each filter row twice, shifted by one pixel
+                // (25 % structural zeros). Against the 32-channel plan (N = 32, 64 B rows): half the MMA instructions per pixel at the
+                // N = 64 rate, and 128 B swizzled operand rows instead of 64 B ones (whose 8-row groups hit every bank twice: 83 cycles per
+                // N = 32 MMA measured, against 48 in isolation).
     int up2;    // nn.Upsample(scale 2, nearest) fused into the store: every output pixel is written to its 2 x 2 block of the 2Ho x 2Wo destination
     int debug;  // profiling only (mode >> 8): 1 = epilogue drains without work, 2 = producer skips TMA, 4 = MMA issuer skips tcgen05.mma,
                 // 8 = epilogue skips the TMA store, 16 = epilogue skips the activation
@@ -350,7 +357,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp < EPI_WARPS) {
         // SiLU layers keep 0.5 * bias: the epilogue needs h = (acc + bias) / 2 = fma(acc, 0.5, 0.5 * bias), one instruction
         const float bscale = (p.act == YSOD_ACT_SILU && !(p.debug & 16)) ? 0.5f : 1.0f;
-        for (int i = threadIdx.x; i < p.cout_pad; i += EPI_THREADS) bias_s[i] = bscale * __ldg(p.bias + i);
+        for (int i = threadIdx.x; i < p.cout_pad; i += EPI_THREADS) bias_s[i] = bscale * __ldg(p.bias + (p.duo ? (i & 31) : i));   // duo: both pixels of a row
         if (p.b2b) {
             // W2 rows (64 bf16 = 128 B) in the K-major SWIZZLE_128B layout: 16 B piece c of row r at r * 128 + ((c ^ (r & 7)) << 4)
             const int w2ld = 64 + (p.b2b == 4 ? 32 : 0);   // b2b 4: W2 rows are [64 extra-operand channels | 32 staged channels]
@@ -463,16 +470,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 int sa_c = 0, sa_o = 0, sb_c = 0, sb_o = 0, abase_c = 0, abase_o = two ? ah : 0, bbase_c = 0, bbase_o = (b_res || !two) ? 0 : bh;
                 uint32_t pa_c = 0, pa_o = 0, pb_c = 0, pb_o = 0;
                 bool first = true;
+                // filter columns per row of taps / K elements per tap in the weight matrix (duo: 2 pair-taps of 64)
+                const int kw = p.duo ? 2 : 3, ntaps = 3 * kw, kcin = p.duo ? 64 : p.Cin;
                 TileIter ti;
                 ti.init(blockIdx.x, p);
                 if (b_res && ti.valid(p) && p.n_tiles == 1) {
                     // resident weights are static: fetch them while the previous kernel is still draining
                     for (int cc = 0; cc < cchunks; ++cc)
-                        for (int s = 0; s < 3; ++s)
+                        for (int s = 0; s < kw; ++s)
                             for (int r = 0; r < 3; ++r) {
-                                const int slot = cc * 9 + s * 3 + r;
+                                const int slot = cc * ntaps + s * 3 + r;
                                 mbar_expect_tx(fullB + 8u * slot, p.b_bytes);
-                                tma_load_2d(b_base + (uint32_t)slot * p.b_bytes, &tmB, fullB + 8u * slot, (r * 3 + s) * p.Cin + cc * p.BK, 0);
+                                tma_load_2d(b_base + (uint32_t)slot * p.b_bytes, &tmB, fullB + 8u * slot, (r * kw + s) * kcin + cc * p.BK, 0);
                             }
                     first = false;
                 }
@@ -511,7 +520,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 } else
                 for (int tcount = 0; ti.valid(p); ti.step(p), ++tcount) {
                     const int img = ti.img;
-                    const int oh0 = ti.th * 16, ow0 = ti.tw * 8;
+                    const int oh0 = ti.th * 16, ow0 = ti.tw * 8;   // (duo: the A map's W axis counts pixel pairs, a tile is 16 rows x 8 pairs)
                     const int n0 = ti.nt * p.BN;
                     if (p.b2b == 4) {
                         // the tile's 16 x 8 pixels of the second layer's other input (64 channels, 128 B rows): slot = tile parity =
@@ -533,12 +542,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                         if (++sa_c == ah) { sa_c = 0; pa_c ^= 1u; }
                         if (b_res && !first) continue;  // weights already in shared memory
-                        for (int s = 0; s < 3; ++s) {
+                        for (int s = 0; s < kw; ++s) {
                             for (int r = 0; r < 3; ++r) {
-                                const int slot = b_res ? (cc * 9 + s * 3 + r) : (bbase_c + sb_c);
+                                const int slot = b_res ? (cc * ntaps + s * 3 + r) : (bbase_c + sb_c);
                                 if (!b_res) mbar_wait(emptyB + 8u * slot, pb_c ^ 1u);
                                 mbar_expect_tx(fullB + 8u * slot, p.b_bytes);
-                                tma_load_2d(b_base + (uint32_t)slot * p.b_bytes, &tmB, fullB + 8u * slot, (r * 3 + s) * p.Cin + cc * p.BK, n0);
+                                tma_load_2d(b_base + (uint32_t)slot * p.b_bytes, &tmB, fullB + 8u * slot, (r * kw + s) * kcin + cc * p.BK, n0);
                                 if (!b_res && ++sb_c == bh) { sb_c = 0; pb_c ^= 1u; }
                             }
                         }
@@ -614,8 +623,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 } else {
                     const int a_stages = p.a_stages, b_stages = p.b_stages, cchunks = p.cchunks;
-                    const uint32_t row_b = 2u * (uint32_t)p.BK;
-                    const uint32_t halo_desc_hi = ((10u * row_b) >> 4) | (1u << 14) | ((p.BK == 64 ? 2u : 4u) << 29);   // SBO = 10 pixels
+                    const uint32_t row_b = 128u;   // one pixel = one 128 B row (32-channel pixels are padded, see the single-tile path)
+                    const uint32_t halo_desc_hi = ((10u * row_b) >> 4) | (1u << 14) | (2u << 29);   // SBO = 10 pixels, SWIZZLE_128B
                     int sa = 0, sb = 0;
                     uint32_t pa = 0, pb = 0;
                     for (int tcount = 0; t0.valid(p); t0.step2(p), ++tcount) {
@@ -717,9 +726,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {
                 const int a_stages = p.a_stages, b_stages = p.b_stages, cchunks = p.cchunks, SG = p.sgroup;
                 const bool b_res = p.b_resident != 0;
-                const uint32_t row_b = 2u * (uint32_t)p.BK;                       // bytes of one pixel row of the halo copy (128 or 64)
-                const uint32_t halo_desc_hi = ((10u * row_b) >> 4) | (1u << 14) | ((p.BK == 64 ? 2u : 4u) << 29);   // SBO = 10 pixels
+                // one pixel (duo: pixel pair) of the halo copy is ONE 128 B shared-memory row under the 128 B swizzle. A 32-channel pixel
+                // fills half of its row: TMA pads an inner box dimension shorter than the swizzle span (probe: tools/ubench/
+                // tma_swizzle_probe.cu), and the padded copy is the canonical conflict-free K-major layout, whereas packed 64 B rows
+                // (SWIZZLE_64B) make every 8-row operand fetch hit each bank twice (83 cycles per N = 32 MMA measured, against 48).
+                const uint32_t row_b = 128u;
+                const uint32_t halo_desc_hi = ((10u * row_b) >> 4) | (1u << 14) | (2u << 29);   // SBO = 10 rows, SWIZZLE_128B
                 const int ksteps = p.BK >> 4;
+                const int kw = p.duo ? 2 : 3, ntaps = 3 * kw;   // filter columns (duo: pair-taps)
+                // duo: the halo copy starts one pair (two pixels) left of the tile, the four pixels a row reads start at its second pixel
+                const uint32_t a_skew = p.duo ? 64u : 0u;
                 bool first = true;
                 int sa = 0, sb = 0;          // positions inside this issuer's (sub-)rings
                 uint32_t pa = 0, pb = 0;
@@ -733,11 +749,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const int aslot = abase + sa;
                         mbar_wait(fullA + 8u * aslot, pa);
                         if (b_res && first) {  // resident weights land once, during the CTA's first tile
-                            for (int j = 0; j < 9; ++j) mbar_wait(fullB + 8u * (cc * 9 + j), 0u);
+                            for (int j = 0; j < ntaps; ++j) mbar_wait(fullB + 8u * (cc * ntaps + j), 0u);
                         }
                         const uint32_t a_slot_addr = a_base + (uint32_t)aslot * a_bytes;
                         // resident weights: one burst of 36 MMAs per chunk; streamed weights: one burst of 12 per filter column
-                        for (int s0 = 0; s0 < 3; s0 += SG) {
+                        for (int s0 = 0; s0 < kw; s0 += SG) {
                             if (!b_res) {
 #pragma unroll
                                 for (int r = 0; r < 3; ++r) mbar_wait(fullB + 8u * (bbase + sb + r), pb);
@@ -746,12 +762,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             trace(tr, trole, 2, tcount, cc * 3 + s0, tcnt);   // operands landed
                             if (!no_mma) {
                                 for (int s = s0; s < s0 + SG; ++s) {
-                                    const uint32_t slot0 = b_res ? (uint32_t)(cc * 9 + s * 3) : (uint32_t)(bbase + sb);
+                                    const uint32_t slot0 = b_res ? (uint32_t)(cc * ntaps + s * 3) : (uint32_t)(bbase + sb);
 #pragma unroll
                                     for (int r = 0; r < 3; ++r) {
                                         // tap (r, s): the MMA's pixel rows start (r*10 + s) pixels into the 18 x 10 halo copy; the
                                         // 8-pixel row groups are 10 pixels (SBO = 1280 B) apart.
-                                        const uint32_t a_lo = umma_lo(a_slot_addr + (uint32_t)(r * 10 + s) * row_b);
+                                        const uint32_t a_lo = umma_lo(a_slot_addr + (uint32_t)(r * 10 + s) * row_b + a_skew);
                                         const uint32_t b_lo = umma_lo(b_base + (slot0 + r) * b_bytes);
 #pragma unroll 4
                                         for (int k = 0; k < ksteps; ++k)
@@ -766,7 +782,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                 sb += 3;
                                 if (sb == b_stages) { sb = 0; pb ^= 1u; }
                             }
-                            if (s0 + SG == 3) {
+                            if (s0 + SG == kw) {
                                 tc_commit(emptyA + 8u * aslot);
                                 if (cc == cchunks - 1) tc_commit(tfull_bar + 8u * aidx);
                             }
@@ -815,18 +831,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ti.init(p.pair ? 2 * blockIdx.x + grp : blockIdx.x, p);   // pairs: group g owns tile g of every pair of this CTA
         if (!p.pair && grp) ti.step(p);
         if (res != nullptr) pdl_wait();   // the residual may be the previous kernel's output
+        const int duo = p.duo;   // duo plan: row m = the pixel pair (th, 2 tw), (th, 2 tw + 1); columns [0,32) / [32,64) = their 32 channels
         for (int tcount = grp; ti.valid(p); ti.step2(p), tcount += 2) {
             const int img = ti.img;
-            const int oh0 = ti.th * TH, ow0 = ti.tw * TW;
+            const int oh0 = ti.th * TH, ow0 = (ti.tw * TW) << duo;
             const int n0 = ti.nt * BN;
             // residual rows do not depend on the accumulator: fetch the first chunk's before waiting for the MMAs
             bool add_res = false;
             const __nv_bfloat16* rp = nullptr;
             uint4 ra = make_uint4(0, 0, 0, 0), rb = ra;
             if (res != nullptr) {
-                const int oh = oh0 + th, ow = ow0 + tw;
+                const int oh = oh0 + th, ow = ow0 + (tw << duo);
                 add_res = (m < TH * TW) && (oh < p.Ho) && (ow < p.Wo);
                 rp = res + (((size_t)img * p.Ho + oh) * p.Wo + ow) * p.rcs + n0;
+                // (duo: chunks 0, 1 are the first pixel's channels; chunk ch of the pair sits at (ch >> 1) * rcs + (ch & 1) * 16)
                 if (add_res && cg < nchunks) { ra = *reinterpret_cast<const uint4*>(rp + cg * 16); rb = *reinterpret_cast<const uint4*>(rp + cg * 16 + 8); }
             }
             const int aidx = 2 * asel + grp;
@@ -892,7 +910,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         f[2 * j] += r2.x;
                         f[2 * j + 1] += r2.y;
                     }
-                    if (ch + 2 < nchunks) { ra = *reinterpret_cast<const uint4*>(rp + c0 + 32); rb = *reinterpret_cast<const uint4*>(rp + c0 + 40); }
+                    if (ch + 2 < nchunks) {
+                        const __nv_bfloat16* rn = duo ? rp + p.rcs + (ch & 1) * 16 : rp + c0 + 32;   // duo: chunk ch + 2 = the same channels of the second pixel
+                        ra = *reinterpret_cast<const uint4*>(rn); rb = *reinterpret_cast<const uint4*>(rn + 8);
+                    }
                 }
                 if (dec) {
                     if (ch < 4) {
@@ -1091,6 +1112,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                             for (int d = 0; d < 4; ++d)
                                 tma_store_4d(&tmO, sb + (uint32_t)u * unit_bytes, n0 + u * unit_cols, 2 * ow0 + (d & 1), 2 * oh0 + (d >> 1), img);
+                    } else if (duo) {
+                        for (int u = 0; u < 2; ++u) tma_store_4d(&tmO, sb + (uint32_t)u * unit_bytes, 0, ow0 + u, oh0, img);   // unit = pixel parity
                     } else {
                         for (int u = 0; u < n_units; ++u) tma_store_4d(&tmO, sb + (uint32_t)u * unit_bytes, n0 + u * unit_cols, ow0, oh0, img);
                     }
@@ -1111,6 +1134,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)p.tmem_cols) : "memory");
     }
+}
+
+// Weight matrix of the pixel-duo plan (TcParams::duo): w [32][3][3][32] (16-bit elements, K ordered (r, s, cin)) ->
+// wd [64][3][2][2][32]: row n = output pixel (n >> 5) of the pair, channel n & 31; K = (filter row r, pair-tap t, pixel e of that pair, cin).
+// Halo pixel h = 2t + e of the four a row reads feeds output pixel j through filter column s = h - j (zero when s is outside 0..2).
+__global__ void duo_weights_kernel(const uint16_t* __restrict__ w, uint16_t* __restrict__ wd) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 64 * 384) return;
+    const int n = i / 384, k = i - n * 384;
+    const int r = k >> 7, t = (k >> 6) & 1, e = (k >> 5) & 1, ci = k & 31;
+    const int s = 2 * t + e - (n >> 5);
+    wd[i] = (s >= 0 && s < 3) ? w[(n & 31) * 288 + (r * 3 + s) * 32 + ci] : (uint16_t)0;
 }
 
 __global__ void scale_weights_kernel(const float* __restrict__ w, int rows, int K, int Cin, const float* __restrict__ gate,
@@ -1142,6 +1177,7 @@ EncodeTiledFn get_encode() {
 
 struct ConvTc {
     bool halo;
+    void* owned_w;   // duo plan: the repacked weight matrix (device memory owned by the plan)
     CUtensorMap tmA, tmB, tmO, tmA2, tmO2;
     TcParams p;
     dim3 grid;
@@ -1161,6 +1197,8 @@ extern "C" {
 //   out    : NHWC view, pixel stride ocs elements; out_dtype YSOD_BF16 or YSOD_F32
 //   res    : optional NHWC bf16 residual added AFTER the activation (Bottleneck / transformer skip), stride rcs
 // ksize in {1,3}, stride in {1,2} (pad = ksize/2, conv.py:28 autopad), groups == 1, Cin % 32 == 0.
+// 3x3 / stride-1 convs with 32 input and 32 output channels (bf16, even width) run the halo kernel's pixel-duo plan (TcParams::duo)
+// unless mode carries 0x10000 (YSOD_CONV_NO_DUO).
 // mode: 0 = auto, 1 = generic per-tap kernel, 2 = force the 3x3 halo-reuse kernel (error if the shape does not qualify);
 //       | 0x40 = fuse nn.Upsample(scale_factor=2, mode='nearest') into the store: `out` is the N x 2Ho x 2Wo destination view.
 //       | 0x80 = per-image weights: `wgt` is [N][Cout_pad][K] (ysod_scale_weights: an SE channel gate folded into this conv).
@@ -1202,7 +1240,8 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
     }
     // 3x3 / stride-1 halo-reuse specialisation: fixed 16 x 8 output tile; worth it when that tiling wastes < 25 % of M
     bool halo = false;
-    const int dbg = mode >> 8;
+    const int dbg = (mode >> 8) & 0xff;
+    const bool no_duo = (mode & 0x10000) != 0;
     const bool up2 = (mode & 0x40) != 0;
     const bool img_w = (mode & 0x80) != 0;
     const int split_exp = mode & 0x10;
@@ -1219,15 +1258,24 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
         halo = (mode == 2) || (mode == 0 && hutil >= 0.75);
     }
     YSOD_CHECK_ARG(mode != 2 || halo, "ysod_conv_tc_create_ex: shape does not qualify for the halo kernel");
+    // pixel-duo plan (TcParams::duo): 32 -> 32 channels, bf16 out, even width, 16 x 16 pixel tiles that waste < 25 % of the MMA rows
+    bool duo = false;
+    // (xcs == 32: the two pixels of a pair must be contiguous -- TMA cannot pack two strided 64 B pixels into one 128 B row)
+    if (halo && !no_duo && Cin == 32 && xcs == 32 && Cout == 32 && Cout_pad == 32 && out_dtype == YSOD_BF16 && !up2 && !no_store && W % 2 == 0) {
+        const double dutil = (double)Ho * Wo / ((double)ysod_cdiv(Ho, 16) * ysod_cdiv(Wo, 16) * 256.0);
+        duo = dutil >= 0.75;
+    }
+    if (duo) Cout_pad = 64;   // the GEMM's N: two pixels x 32 channels (bias duplicated by the kernel prologue)
+    p.duo = duo ? 1 : 0;
     p.debug = dbg;
     p.up2 = up2 ? 1 : 0;
     p.no_store = no_store ? 1 : 0;
     p.w_img_rows = img_w ? Cout_pad : 0;
     if (halo) { bestTH = 16; bestTW = 8; }
     p.N = N; p.Ho = Ho; p.Wo = Wo; p.TH = bestTH; p.TW = bestTW;
-    p.tiles_h = ysod_cdiv(Ho, bestTH); p.tiles_w = ysod_cdiv(Wo, bestTW);
+    p.tiles_h = ysod_cdiv(Ho, bestTH); p.tiles_w = ysod_cdiv(Wo, bestTW << (duo ? 1 : 0));   // duo: TW counts pixel pairs
     p.Cin = Cin; p.ksize = ksize; p.stride = stride; p.pad = pad;
-    p.BK = (Cin % 64 == 0) ? 64 : 32;
+    p.BK = (Cin % 64 == 0 || duo) ? 64 : 32;
     int BN = Cout_pad;
     if (BN > 128) {
         // <= 128 output channels per tile: the two epilogue groups each stage a whole tile (<= 32 KB), wide layers get more
@@ -1238,7 +1286,7 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
     p.BN = BN;
     p.tmem_cols = 4 * BN <= 32 ? 32 : 4 * BN <= 64 ? 64 : 4 * BN <= 128 ? 128 : 4 * BN <= 256 ? 256 : 512;  // 2 issuers x double-buffered accumulator
     p.n_tiles = Cout_pad / BN;
-    p.num_k = ksize * ksize * (Cin / p.BK);
+    p.num_k = duo ? 6 : ksize * ksize * (Cin / p.BK);
     p.Cout = Cout;
     p.out = out; p.out_f32 = (out_dtype == YSOD_F32); p.ocs = ocs;
     p.bias = bias; p.res = (const __nv_bfloat16*)res; p.rcs = rcs; p.act = act;
@@ -1251,7 +1299,7 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
     const uint32_t sbo = (p.BK == 64 ? 1024u : 512u) >> 4;
     const uint32_t layout = (p.BK == 64) ? 2u : 4u;  // SWIZZLE_128B : SWIZZLE_64B
     p.desc_hi = sbo | (1u << 14) | (layout << 29);
-    p.cchunks = Cin / p.BK;
+    p.cchunks = duo ? 1 : Cin / p.BK;
     {
         const uint32_t es = p.out_f32 ? 4u : 2u;
         uint32_t rb = 32;
@@ -1261,17 +1309,22 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
         p.n_units = (int)(((uint32_t)BN * es + rb - 1) / rb);
         p.swz_mask = rb == 128 ? 7 : rb == 64 ? 3 : 1;
         p.cout_pad = Cout_pad;
+        if (duo) {
+            // the output view may be strided (a slice of a concat buffer), so a staged row cannot leave as one pixel pair: two store
+            // units of 64 B rows, unit e = pixel e of every pair, each stored through a W axis walked with element stride 2
+            p.row_bytes = 64; p.unit_cols = 32; p.n_units = 2; p.swz_mask = 3;
+        }
     }
     // epilogue staging holds the whole BN-wide output tile (n_units sub-buffers of 128 rows); double-buffered up to 32 KB
     uint32_t tile_stage_bytes = (uint32_t)p.n_units * 128u * p.row_bytes;
     p.stage_bufs = 2;   // one per epilogue group
     p.stage_split = 0;
-    if (halo && p.n_units > 1) {
+    if (halo && p.n_units > 1 && !duo) {
         // 3x3 halo plan whose weight taps only fit resident if the staging buffer shrinks to one store unit (64 -> 128 at P2:
         // 144 KB of taps): streamed taps are bound by the latency x depth of the small tap ring (measured 45 % tensor-pipe
         // activity), so trade a second barrier per tile for resident weights. Exact shared-memory accounting, not the 224 KB rule.
-        const uint32_t a_halo = ((18u * 10u * 2u * (uint32_t)p.BK) + 1023u) & ~1023u;
-        const uint32_t b_all = 9u * (uint32_t)p.cchunks * p.b_bytes;
+        const uint32_t a_halo = ((18u * 10u * 128u) + 1023u) & ~1023u;
+        const uint32_t b_all = 9u * (uint32_t)p.cchunks * p.b_bytes;   // (never the duo plan: its N = 64 tile is one store unit)
         const uint32_t nbar_res = 2u * 2u + 2u * 9u * (uint32_t)p.cchunks;
         const uint32_t full_need = b_all + 2u * a_halo + 2u * tile_stage_bytes + 4u * (uint32_t)Cout_pad + 3u * 1024u;
         const uint32_t split_need = b_all + 2u * a_halo + 1024u + (8u * nbar_res + 128u) + 4u * (uint32_t)Cout_pad + 1024u + 2u * 128u * p.row_bytes;
@@ -1354,9 +1407,10 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
             nbar = 4 * p.a_slots;
         }
     } else {
-        p.a_tx = 18u * 10u * 2u * (uint32_t)p.BK;     // one halo copy: 18 rows x 10 px x BK ch bf16 (22.5 KB / 11.25 KB)
-        p.a_bytes = (p.a_tx + 1023u) & ~1023u;        // slot stride (1 KB aligned)
-        const uint32_t b_all = 9u * (uint32_t)p.cchunks * p.b_bytes;
+        p.a_tx = 18u * 10u * 2u * (uint32_t)p.BK;     // bytes landed per halo copy: 18 rows x 10 px x BK ch bf16 (22.5 KB / 11.25 KB)
+        p.a_bytes = (18u * 10u * 128u + 1023u) & ~1023u;   // slot stride: one 128 B row per pixel (32-channel pixels fill half a row)
+        const uint32_t ntaps = duo ? 6u : 9u;         // duo: 3 rows x 2 pair-taps; its halo copy is 18 rows x 10 pixel pairs of 128 B
+        const uint32_t b_all = ntaps * (uint32_t)p.cchunks * p.b_bytes;
         // resident split plan: sized exactly above; streamed split plan: exact accounting against the 227 KB limit (<= 13 barrier
         // pairs, bias, two 1 KB alignment pads, staging) instead of the conservative 224 KB rule -- the ninth tap slot needs it
         const uint32_t avail = p.stage_split == 1 ? b_all + 2u * p.a_bytes
@@ -1366,14 +1420,15 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
         if (b_all + 2u * p.a_bytes <= avail) {   // all weight taps stay resident in shared memory for the CTA lifetime
             p.b_resident = 1;
             p.issuers = 2;            // one 36-MMA burst per tile and chunk: ping-pong two issuers over the tiles
-            p.b_stages = 9 * p.cchunks;
+            p.b_stages = (int)ntaps * p.cchunks;
             p.b_slots = p.b_stages;
             a_total = (int)((avail - b_all) / p.a_bytes);
             if (a_total > 8) a_total = 8;
             a_total &= ~1;
             p.a_stages = a_total / 2;
-            p.sgroup = 3;
+            p.sgroup = duo ? 2 : 3;
         } else {
+            YSOD_CHECK_ARG(!duo, "ysod_conv_tc_create: the duo plan keeps its weights resident");
             p.b_resident = 0;
             p.issuers = 1;            // many bursts per tile: one issuer, one deep ring
             p.b_stages = (9u * p.b_bytes + 2u * p.a_bytes <= avail) ? 9 : 6;   // three (else two) filter columns of three taps in flight
@@ -1429,19 +1484,36 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
         cuuint64_t strides[3] = {(cuuint64_t)xcs * 2, (cuuint64_t)W * xcs * 2, (cuuint64_t)H * W * xcs * 2};
+        if (duo) { dims[0] = 64; dims[1] = (cuuint64_t)(W / 2); strides[0] = 128; }   // W axis in pixel pairs (contiguous: xcs == 32)
         cuuint32_t box[4] = {(cuuint32_t)p.BK, (cuuint32_t)(bestTW * stride), (cuuint32_t)(bestTH * stride), 1};
         if (halo) { box[1] = 10; box[2] = 18; }   // the halo copy: rows oh0-1 .. oh0+16, columns ow0-1 .. ow0+8
         cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+        // the halo copy is always 128 B-swizzled rows of 128 B: a 32-channel pixel is padded to a row by TMA, a duo row is a pixel pair
         CUresult r = enc(&c.tmA, YSOD_TMAP_16, 4, const_cast<void*>(x), dims, strides, box, es,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, halo ? CU_TENSOR_MAP_SWIZZLE_128B : swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             ysod_set_error("ysod_conv_tc_create: cuTensorMapEncodeTiled(A) failed with %d (Cin %d W %d H %d N %d xcs %d box %d,%d,%d)",
                            (int)r, Cin, W, H, N, xcs, p.BK, bestTW * stride, bestTH * stride);
             return YSOD_ERR_CUDA;
         }
     }
+    struct OwnedGuard {   // frees the plan-owned weight copy on every error return below
+        void*& ptr; bool keep;
+        ~OwnedGuard() { if (!keep && ptr) { cudaFree(ptr); ptr = nullptr; } }
+    } owned_guard{c.owned_w, false};
+    if (duo) {
+        YSOD_CUDA(cudaMalloc(&c.owned_w, 64 * 384 * 2));
+        duo_weights_kernel<<<(64 * 384 + 255) / 256, 256>>>((const uint16_t*)wgt, (uint16_t*)c.owned_w);
+        cudaError_t e = cudaDeviceSynchronize();   // plan creation is not on the hot path; `wgt` need not outlive it
+        if (e != cudaSuccess) {
+            ysod_set_error("ysod_conv_tc_create: duo weight repack failed: %s", cudaGetErrorString(e));
+            return YSOD_ERR_CUDA;
+        }
+        wgt = c.owned_w;
+    }
     {
-        const cuuint64_t K = (cuuint64_t)ksize * ksize * Cin;
+        const cuuint64_t K = duo ? 384 : (cuuint64_t)ksize * ksize * Cin;
         cuuint64_t dims[2] = {K, (cuuint64_t)Cout_pad * (cuuint64_t)(img_w ? N : 1)};
         cuuint64_t strides[1] = {K * 2};
         cuuint32_t box[2] = {(cuuint32_t)p.BK, (cuuint32_t)BN};
@@ -1461,6 +1533,7 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
         cuuint64_t strides[3] = {(cuuint64_t)ocs * es, us * Wo * ocs * es, us * Ho * us * Wo * ocs * es};
         cuuint32_t box[4] = {(cuuint32_t)p.unit_cols, (cuuint32_t)(us * bestTW), (cuuint32_t)(us * bestTH), 1};
         cuuint32_t es1[4] = {1, (cuuint32_t)us, (cuuint32_t)us, 1};
+        if (duo) { box[1] = 16; es1[1] = 2; }   // store unit e = pixel e of the tile's 8 pairs per row: 16 pixels walked with stride 2
         const CUtensorMapSwizzle oswz = p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                       : p.row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
         CUresult r = enc(&c.tmO, p.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : YSOD_TMAP_16, 4, out, dims, strides,
@@ -1478,6 +1551,7 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
     ysod_conv_tc* h = new (std::nothrow) ysod_conv_tc;
     YSOD_CHECK_ARG(h, "ysod_conv_tc_create: out of memory");
     h->c = c;
+    owned_guard.keep = true;
     *handle = h;
     return YSOD_OK;
 }
@@ -1514,7 +1588,7 @@ int ysod_conv_tc_run(ysod_conv_tc* h, cudaStream_t stream) {
 int ysod_conv_tc_set_decode(ysod_conv_tc* h, float* y, int A_total, int a_off, int nc, float stride) {
     YSOD_CHECK_ARG(h && y, "ysod_conv_tc_set_decode: null");
     TcParams& p = h->c.p;
-    YSOD_CHECK_ARG(p.out_f32 && p.act == YSOD_ACT_NONE && p.res == nullptr && p.n_tiles == 1 && !p.up2,
+    YSOD_CHECK_ARG(p.out_f32 && p.act == YSOD_ACT_NONE && p.res == nullptr && p.n_tiles == 1 && !p.up2 && !p.duo,
                    "ysod_conv_tc_set_decode: plan must be an fp32-output, activation-free, single-N-tile conv");
     YSOD_CHECK_ARG(nc > 0 && p.Cout == 64 + nc && p.BN >= 64 + nc, "ysod_conv_tc_set_decode: Cout %d != 64 + nc (%d)", p.Cout, nc);
     YSOD_CHECK_ARG(a_off >= 0 && a_off + p.Ho * p.Wo <= A_total, "ysod_conv_tc_set_decode: anchor range out of bounds");
@@ -1533,7 +1607,7 @@ int ysod_conv_tc_set_b2b(ysod_conv_tc* h, const void* w2, const float* bias2, in
     YSOD_CHECK_ARG(h && w2 && bias2 && y, "ysod_conv_tc_set_b2b: null");
     ConvTc& c = h->c;
     TcParams& p = c.p;
-    YSOD_CHECK_ARG(p.BN == 64 && p.n_tiles == 1 && !p.out_f32 && p.n_units == 1 && !p.stage_split && !p.up2 && p.row_bytes == 128 && p.dec_y == nullptr,
+    YSOD_CHECK_ARG(p.BN == 64 && !p.duo && p.n_tiles == 1 && !p.out_f32 && p.n_units == 1 && !p.stage_split && !p.up2 && p.row_bytes == 128 && p.dec_y == nullptr,
                    "ysod_conv_tc_set_b2b: plan must be a 64-channel bf16 conv with a single 128 B staging unit (BN %d, units %d, split %d)", p.BN,
                    p.n_units, p.stage_split);
     YSOD_CHECK_ARG(kind == 1 || kind == 2, "ysod_conv_tc_set_b2b: kind %d", kind);
@@ -1559,7 +1633,7 @@ int ysod_conv_tc_set_b2b_conv(ysod_conv_tc* h, const void* w2, const float* bias
     YSOD_CHECK_ARG(h && w2 && bias2, "ysod_conv_tc_set_b2b_conv: null");
     ConvTc& c = h->c;
     TcParams& p = c.p;
-    YSOD_CHECK_ARG(p.BN == 64 && p.Cout == 64 && p.n_tiles == 1 && !p.out_f32 && p.n_units == 1 && !p.stage_split && !p.up2 && p.row_bytes == 128 &&
+    YSOD_CHECK_ARG(p.BN == 64 && !p.duo && p.Cout == 64 && p.n_tiles == 1 && !p.out_f32 && p.n_units == 1 && !p.stage_split && !p.up2 && p.row_bytes == 128 &&
                    p.dec_y == nullptr && !p.b2b && !p.no_store,
                    "ysod_conv_tc_set_b2b_conv: plan must be a 64-channel bf16 conv with a single 128 B staging unit (BN %d, units %d, split %d)", p.BN,
                    p.n_units, p.stage_split);
@@ -1609,6 +1683,13 @@ int ysod_conv_tc_set_b2b_cat(ysod_conv_tc* h, const void* x2, int x2cs, const vo
     }
     // W2 (64 x 128 B + 64 x 64 B) + bias + 6 barriers + alignment + 2 extra-operand tiles + 2 output staging tiles
     const size_t extra = 128u * 64u + 64u * 64u + 4u * 64u + 48u + 1024u + 4u * 16384u;
+    // make room: the halo ring gives up slots (two at a time: one per issuer sub-ring; each slot = a_bytes + its barrier pair)
+    while (c.smem + extra > 227 * 1024 && p.a_slots >= 2 * p.issuers) {
+        p.a_slots -= p.issuers;
+        p.a_stages = p.a_slots / p.issuers;
+        p.stages = p.a_stages;
+        c.smem -= (size_t)p.issuers * (p.a_bytes + 16u);
+    }
     YSOD_CHECK_ARG(c.smem + extra <= 227 * 1024, "ysod_conv_tc_set_b2b_cat: shared memory plan too large (%zu)", c.smem + extra);
     c.smem += extra;
     p.tmem_cols = 256;   // 4 x 32 accumulator columns + 2 x 64 for the second layer
@@ -1633,12 +1714,15 @@ int ysod_conv_tc_info(ysod_conv_tc* h, int* out8) {
     YSOD_CHECK_ARG(h && out8, "ysod_conv_tc_info: null");
     out8[0] = h->c.p.TH; out8[1] = h->c.p.TW; out8[2] = h->c.p.BN; out8[3] = h->c.p.BK; out8[4] = h->c.p.stages;
     out8[5] = (int)h->c.grid.x; out8[6] = h->c.halo ? (1000 + 100 * h->c.p.issuers + 10 * h->c.p.b_resident + h->c.p.n_tiles) : (100 * h->c.p.issuers + 10 * h->c.p.kgroup + h->c.p.n_tiles);
-    out8[6] += 10000 * h->c.p.pair;
+    out8[6] += 10000 * h->c.p.pair + 20000 * h->c.p.duo;
     out8[7] = (int)h->c.smem;
     return YSOD_OK;
 }
 
-void ysod_conv_tc_destroy(ysod_conv_tc* h) { delete h; }
+void ysod_conv_tc_destroy(ysod_conv_tc* h) {
+    if (h && h->c.owned_w) cudaFree(h->c.owned_w);
+    delete h;
+}
 
 // Profiling aid: copies the pipeline trace of the last launch with debug bit 32 (mode = 32 << 8) to the host and resets it.
 // out: 2 * cap uint64 (tag, clock64); returns the number of records. Synchronises the device.

@@ -146,7 +146,7 @@ class Program:
         return w * s.view(-1, 1, 1, 1), b - mu * s
 
     def conv(self, x: View, w: torch.Tensor, bias: torch.Tensor, k, s, g, act, out: View, res: View = None,
-             out_f32=False, pad=None, up2=False, gate=None, alg_flops=None, no_store=False):
+             out_f32=False, pad=None, up2=False, gate=None, alg_flops=None, no_store=False, no_duo=False):
         """w: (Cout, Cin/g, k, k) fp32 with BN folded; bias fp32 (Cout). up2: `out` is the 2x nearest-upsampled destination
         (tensor-core path only; the caller checks `tc_eligible`). gate: (N, Cin) fp32 device tensor of an SE block folded into this conv
         (per-image weights W * gate[n], rebuilt every forward by ysod_scale_weights; tensor-core path only)."""
@@ -191,6 +191,8 @@ class Program:
             mode = _lib.CONV_UP2 if up2 else 0
             if not self.m.conv_pair:
                 mode |= _lib.CONV_NO_PAIR
+            if no_duo or not self.m.conv_duo:
+                mode |= _lib.CONV_NO_DUO
             if os.environ.get("YSOD_CONV_DEBUG"):
                 mode |= int(os.environ["YSOD_CONV_DEBUG"]) << 8   # A/B switches of the conv kernel (debug bits, tc_conv.cu)
             if os.environ.get("YSOD_TRACE_OP", "") == str(len(self.ops)):
@@ -237,13 +239,13 @@ class Program:
                   out.ptr(), odt, out.cs, res.ptr() if res is not None else None, res.cs if res is not None else 0, actc,
                   flops=2.0 * x.N * Ho * Wo * Cout * k * k * Cin / g, desc=f"direct {Cin}->{Cout} k{k}s{s}g{g} @{Ho}x{Wo}")
 
-    def conv_bn(self, x, pfx, k=1, s=1, g=1, act=True, out=None, res=None, pad=None, up2=False, gate=None):
+    def conv_bn(self, x, pfx, k=1, s=1, g=1, act=True, out=None, res=None, pad=None, up2=False, gate=None, no_duo=False):
         """Reference `Conv` wrapper (conv.py:37-55) with BN folded."""
         w, b = self.folded(pfx)
         if out is None:
             p = k // 2 if pad is None else pad
             out = self.new(x.N, (x.H + 2 * p - k) // s + 1, (x.W + 2 * p - k) // s + 1, w.shape[0])
-        self.conv(x, w, b, k, s, g, "silu" if act else "none", out, res, pad=pad, up2=up2, gate=gate)
+        self.conv(x, w, b, k, s, g, "silu" if act else "none", out, res, pad=pad, up2=up2, gate=gate, no_duo=no_duo)
         return out
 
     def tc_eligible(self, L, cin, h, w):
@@ -278,7 +280,7 @@ class Program:
         else:
             cat = self.new(x.N, x.H, x.W, (2 + n) * c)
             self.conv_bn(x, f"{P}.cv1", out=cat.slice(0, 2 * c))
-        fuse_cv2 = (self.m.fuse_b2b and not c3k2 and n == 1 and c == 32 and out.C == 64 and p["g"] == 1 and self.m.use_tc
+        fuse_cv2 = (self.m.fuse_b2b and self.m.c2f_cat and not c3k2 and n == 1 and c == 32 and out.C == 64 and p["g"] == 1 and self.m.use_tc
                     and self.code == _lib.BF16 and cat.H >= 16 and cat.W >= 8
                     and cat.H * cat.W / (-(-cat.H // 16) * -(-cat.W // 8) * 128.0) >= 0.75)   # the halo (16 x 8 tile) plan will be chosen
         if fuse_cv2:
@@ -287,7 +289,7 @@ class Program:
             src = cat.slice(c, 2 * c)
             mid = self.conv_bn(src, f"{P}.m.0.cv1", 3)
             dummy = View(cat.buf, cat.off + 2 * c, cat.N, cat.H, cat.W, c, cat.cs)     # never written: the tensor map needs an address
-            self.conv_bn(mid, f"{P}.m.0.cv2", 3, out=dummy, res=src if p["shortcut"] else None)
+            self.conv_bn(mid, f"{P}.m.0.cv2", 3, out=dummy, res=src if p["shortcut"] else None, no_duo=True)   # the cat fusion stages 64 B rows
             w2, b2 = self.folded(f"{P}.cv2")
             w2d, b2d = self.dev_t(w2.view(64, 3 * c), self.dt), self.dev_t(b2)
             self.call("ysod_conv_tc_set_b2b_cat", self.tc_handles[-1], cat.ptr(), cat.cs, _lib.ptr(w2d), _lib.ptr(b2d), _lib.ACT["silu"],
@@ -1062,6 +1064,8 @@ class B200DetectionModel:
         if "YSOD_MULTI_STREAM" in os.environ:
             multi_stream = os.environ["YSOD_MULTI_STREAM"] == "1"
         self.conv_pair = os.environ.get("YSOD_NO_PAIR", "0") != "1"   # A/B switch of the conv kernel's tile-pair plan (ysod.h YSOD_CONV_NO_PAIR)
+        self.conv_duo = os.environ.get("YSOD_NO_DUO", "0") != "1"     # A/B switch of the pixel-duo plan for 32 -> 32 3x3 convs (YSOD_CONV_NO_DUO)
+        self.c2f_cat = os.environ.get("YSOD_C2F_CAT", "1") == "1"     # A/B switch: C2f.cv2 inside the last Bottleneck conv's launch (ysod_conv_tc_set_b2b_cat)
         self.attn_impl = attn_impl   # ysod_mha_core_ex impl: 0 = tcgen05 / TMEM attention core where covered, 1 = mma.sync kernels (A/B)
         self.fuse_upsample = fuse_upsample
         self.fuse_decode = fuse_decode
