@@ -203,6 +203,11 @@ int ysod_mha_window_nhwc(const void* q, const void* k, const void* v, int ld, in
  * norm slots of pf32 are ignored (swin_fused.cu). */
 int ysod_swin64_fused(const void* x, int N, int H, int W, int xcs, const void* wbf16, const float* pf32, void* out, int ocs, int window,
                       int heads, void* stream);
+/* The same block (same blobs, same rounding points) with every contraction on tcgen05 / TMEM (swin_tc.cu): two windows per M = 128
+ * tile, thread = token row = TMEM lane, in_proj / QK^T / PV / out_proj / MLP / pw as tcgen05.mma groups from shared-memory operands,
+ * LayerNorm / softmax / GELU on tcgen05.ld registers. ysod_swin64_fused (mma.sync) stays as the A/B baseline. */
+int ysod_swin64_tc(const void* x, int N, int H, int W, int xcs, const void* wbf16, const float* pf32, void* out, int ocs, int window,
+                   int heads, void* stream);
 
 /* ---- softmax attention core: nn.MultiheadAttention internals (blocks_transformer.py:116, a2_attn.py:53) and the manual
  *      path of AAttn (block.py:1348-1357). q/k/v addressed as ptr + batch*bs + token*ld + head*D (elements). ----------- */

@@ -18,20 +18,23 @@ mode = int(sys.argv[9]) if len(sys.argv) > 9 else 0
 act = sys.argv[10] if len(sys.argv) > 10 else "silu"
 pad = k // 2
 Ho, Wo = (H + 2 * pad - k) // s + 1, (W + 2 * pad - k) // s + 1
-x = torch.randn(N, H, W, Cin, device="cuda").bfloat16()
+xcs, ocs = int(os.environ.get("PROF_XCS", Cin)), int(os.environ.get("PROF_OCS", Cout))   # pixel strides: channel slices of wider buffers
+x = torch.randn(N, H, W, xcs, device="cuda").bfloat16()
 cpad = (Cout + 15) // 16 * 16
 w = (torch.randn(cpad, k * k * Cin, device="cuda") / (k * k * Cin) ** 0.5).bfloat16()
 b = torch.zeros(cpad, device="cuda")
-o = torch.empty(N, Ho, Wo, Cout, device="cuda", dtype=torch.bfloat16)
+o = torch.empty(N, Ho, Wo, ocs, device="cuda", dtype=torch.bfloat16)
+r = torch.randn(N, Ho, Wo, Cout, device="cuda").bfloat16() if os.environ.get("PROF_RES") else None
 h = C.c_void_p()
-lib.call("ysod_conv_tc_create_ex", C.byref(h), lib.ptr(x), N, H, W, Cin, Cin, lib.ptr(w), lib.ptr(b), Cout, cpad, k, s, lib.ptr(o), lib.BF16,
-         Cout, None, 0, lib.ACT[act], mode)
+lib.call("ysod_conv_tc_create_ex", C.byref(h), lib.ptr(x), N, H, W, Cin, xcs, lib.ptr(w), lib.ptr(b), Cout, cpad, k, s, lib.ptr(o), lib.BF16,
+         ocs, lib.ptr(r) if r is not None else None, Cout if r is not None else 0, lib.ACT[act], mode)
 info = (C.c_int * 8)()
 lib.call("ysod_conv_tc_info", h, info)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 ts = []
 for i in range(iters):
-    flush.zero_()  # evict L2 between timed launches
+    if not os.environ.get("PROF_WARM"):
+        flush.zero_()  # evict L2 between timed launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     lib.call("ysod_conv_tc_run", h, lib.stream_ptr())

@@ -1399,7 +1399,11 @@ int ysod_cbam_stats(const void* x, int dtype, int N, int HW, int C, int xcs, con
         static const int ring_depth = getenv("YSOD_RING_DEPTH") ? atoi(getenv("YSOD_RING_DEPTH")) : 8;
         if (ring_depth == 8 || ring_depth == 16) {
             const size_t es = dtype == YSOD_BF16 ? 1 : 2;
-            if (ring_depth == 8) { YSOD_DISPATCH(dtype, (ysod_launch(cbam_stats_ring_kernel<T, 8>, grid, 256, 8 * 256 * 16 * es, st, (const T*)x, HW, C, xcs, gate, (float2*)stats, chunk, iters))); }
+            if (ring_depth == 8) {
+                // (fp32 parity mode: 64 KB of ring, above the 48 KB a kernel may use without opting in)
+                if (8 * 256 * 16 * es > 48 * 1024) YSOD_DISPATCH(dtype, (cudaFuncSetAttribute(cbam_stats_ring_kernel<T, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(8 * 256 * 16 * es))));
+                YSOD_DISPATCH(dtype, (ysod_launch(cbam_stats_ring_kernel<T, 8>, grid, 256, 8 * 256 * 16 * es, st, (const T*)x, HW, C, xcs, gate, (float2*)stats, chunk, iters)));
+            }
             else {
                 YSOD_DISPATCH(dtype, (cudaFuncSetAttribute(cbam_stats_ring_kernel<T, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(16 * 256 * 16 * es))));
                 YSOD_DISPATCH(dtype, (ysod_launch(cbam_stats_ring_kernel<T, 16>, grid, 256, 16 * 256 * 16 * es, st, (const T*)x, HW, C, xcs, gate, (float2*)stats, chunk, iters)));

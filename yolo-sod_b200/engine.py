@@ -269,26 +269,31 @@ class Program:
         add = shortcut and x.C == out.C
         self.conv_bn(mid, f"{pfx}.cv2", k[1], 1, g, out=out, res=x if add else None)
 
+    def c2f_fuses_cv2(self, p, c2, H, W, c3k2=False):
+        """True when C2f.cv2 runs inside the launch of the block's last Bottleneck conv (ysod_conv_tc_set_b2b_cat)."""
+        return (self.m.fuse_b2b and self.m.c2f_cat and not c3k2 and p["n"] == 1 and int(c2 * p["e"]) == 32 and c2 == 64 and p["g"] == 1
+                and self.m.use_tc and self.code == _lib.BF16 and H >= 16 and W >= 8
+                and H * W / (-(-H // 16) * -(-W // 8) * 128.0) >= 0.75)   # the halo (16 x 8 tile) plan will be chosen
+
     def c2f(self, x, P, p, c2, out, c3k2=False):
         """block.py:233-248 (C2f) / :733-741 (C3k2): cv1 -> chunk(2) -> n blocks -> cat -> cv2, with the cat buffer
         written slice by slice."""
         n = p["n"]
         c = int(c2 * p["e"])
         li = int(P.split(".")[1])
+        fuse_cv2 = self.c2f_fuses_cv2(p, c2, out.H, out.W, c3k2)   # (x is None when cv1 ran inside its producer)
         if li in getattr(self, "_c2f_pre", {}):
             cat = self._c2f_pre[li]          # cv1 already ran inside the producer conv's launch
         else:
-            cat = self.new(x.N, x.H, x.W, (2 + n) * c)
+            # (fused cv2: the Bottleneck output never reaches HBM, so the buffer holds the cv1 output alone -- full 128 B lines per pixel)
+            cat = self.new(out.N, out.H, out.W, (2 if fuse_cv2 else 2 + n) * c)
             self.conv_bn(x, f"{P}.cv1", out=cat.slice(0, 2 * c))
-        fuse_cv2 = (self.m.fuse_b2b and self.m.c2f_cat and not c3k2 and n == 1 and c == 32 and out.C == 64 and p["g"] == 1 and self.m.use_tc
-                    and self.code == _lib.BF16 and cat.H >= 16 and cat.W >= 8
-                    and cat.H * cat.W / (-(-cat.H // 16) * -(-cat.W // 8) * 128.0) >= 0.75)   # the halo (16 x 8 tile) plan will be chosen
         if fuse_cv2:
             # cv2 (1x1, 96 -> 64) runs inside the launch of the Bottleneck's second 3x3 conv (ysod_conv_tc_set_b2b_cat): its input
             # cat(cv1 output, bottleneck output) = the 64-channel cv1 slice (TMA tile) + the staged 32-channel tile
             src = cat.slice(c, 2 * c)
             mid = self.conv_bn(src, f"{P}.m.0.cv1", 3)
-            dummy = View(cat.buf, cat.off + 2 * c, cat.N, cat.H, cat.W, c, cat.cs)     # never written: the tensor map needs an address
+            dummy = cat.slice(c, 2 * c)     # never written: the plan's output tensor map needs a valid address
             self.conv_bn(mid, f"{P}.m.0.cv2", 3, out=dummy, res=src if p["shortcut"] else None, no_duo=True)   # the cat fusion stages 64 B rows
             w2, b2 = self.folded(f"{P}.cv2")
             w2d, b2d = self.dev_t(w2.view(64, 3 * c), self.dt), self.dev_t(b2)
@@ -370,8 +375,11 @@ class Program:
             assert wb.numel() == 37440 and pf.numel() == 768
             wbd, pfd = self.dev_t(wb, self.dt), self.dev_t(pf)
             T = x.N * (-(-x.H // ws)) * (-(-x.W // ws)) * ws * ws
-            self.emit("ysod_swin64_fused", x.ptr(), x.N, x.H, x.W, x.cs, _lib.ptr(wbd), _lib.ptr(pfd), out.ptr(), out.cs, ws, 2,
-                      flops=2.0 * T * (64 * 192 + 64 * 64 + 2 * 64 * 128 + 64 * 64 + 2 * 49 * 64), desc=f"swin64 fused @{x.H}x{x.W}")
+            # swin_impl 0: tcgen05 / TMEM kernel (swin_tc.cu); 1: the mma.sync kernel (swin_fused.cu), the A/B baseline
+            kern = "ysod_swin64_fused" if self.m.swin_impl == 1 else "ysod_swin64_tc"
+            self.emit(kern, x.ptr(), x.N, x.H, x.W, x.cs, _lib.ptr(wbd), _lib.ptr(pfd), out.ptr(), out.cs, ws, 2,
+                      flops=2.0 * T * (64 * 192 + 64 * 64 + 2 * 64 * 128 + 64 * 64 + 2 * 49 * 64),
+                      desc=f"swin64 fused ({'mma.sync' if self.m.swin_impl == 1 else 'tcgen05'}) @{x.H}x{x.W}")
             return
         heads = p["num_heads"]
         D = Cc // heads
@@ -870,7 +878,7 @@ class Program:
                 elif L.i in fold_cv1:
                     J = layers[fold_cv1[L.i]]
                     cj = int(J.c2 * J.p["e"])
-                    cat = self.new(self.B, h, w, (2 + J.p["n"]) * cj)
+                    cat = self.new(self.B, h, w, (2 if self.c2f_fuses_cv2(J.p, J.c2, h, w) else 2 + J.p["n"]) * cj)
                     self._c2f_pre[J.i] = cat
                     self.conv_bn(x, P, p["k"], p["s"], p["g"], p["act"], out=cat.slice(0, 2 * cj), pad=p["p"], gate=gate)
                     w2, b2 = self.folded(f"model.{J.i}.cv1")
@@ -1034,7 +1042,7 @@ class B200DetectionModel:
     """
 
     def __init__(self, cfg, state_dict, dtype=torch.bfloat16, device="cuda:0", use_tc=True, use_graph=True, nc=None,
-                 static_outputs=False, max_programs=8, attn_impl=0, fuse_cbam=False, ca_single_pass=False, fuse_b2b=True, swin_nhwc=True, fuse_swin=True, multi_stream=True, fuse_upsample=True, fuse_decode=True, fuse_se=True, fuse_gate=False):
+                 static_outputs=False, max_programs=8, attn_impl=0, fuse_cbam=False, ca_single_pass=False, fuse_b2b=True, swin_nhwc=True, fuse_swin=True, multi_stream=True, fuse_upsample=True, fuse_decode=True, fuse_se=True, fuse_gate=False, conv_duo=True, swin_impl=0):
         _lib.require_cuda()
         _lib.load()
         self.spec = cfg if isinstance(cfg, _cfg.ModelSpec) else _cfg.get_spec(cfg, nc=nc)
@@ -1049,6 +1057,9 @@ class B200DetectionModel:
         self.use_tc = use_tc
         self.use_graph = use_graph
         self.fuse_swin = fuse_swin
+        self.swin_impl = int(os.environ.get("YSOD_SWIN_IMPL", swin_impl))   # fused P2 SwinBlock: 0 = tcgen05 kernel, 1 = mma.sync kernel (A/B)
+        if "YSOD_FUSE_SWIN" in os.environ:
+            self.fuse_swin = os.environ["YSOD_FUSE_SWIN"] == "1"
         # Single-pass variants of the CBAM spatial stage (ysod_cbam_spatial) and of the CoordAtt pooling (ysod_ca_pool with a workspace):
         # bit-identical / fp32-rounding-identical to the multi-pass kernels but measured SLOWER on B200 (profiles/r02_ab_blocks.json:
         # 128 vs 107 us at 64 x 160^2, 92 vs 42 us at 256 x 40^2; 120 vs 37 us for the pooling) -- one CTA per tile serialises statistics ->
@@ -1064,7 +1075,8 @@ class B200DetectionModel:
         if "YSOD_MULTI_STREAM" in os.environ:
             multi_stream = os.environ["YSOD_MULTI_STREAM"] == "1"
         self.conv_pair = os.environ.get("YSOD_NO_PAIR", "0") != "1"   # A/B switch of the conv kernel's tile-pair plan (ysod.h YSOD_CONV_NO_PAIR)
-        self.conv_duo = os.environ.get("YSOD_NO_DUO", "0") != "1"     # A/B switch of the pixel-duo plan for 32 -> 32 3x3 convs (YSOD_CONV_NO_DUO)
+        # pixel-duo plan for dense 32 -> 32 3x3 convs (ysod.h YSOD_CONV_NO_DUO): same products, different accumulation order than the 32-channel plan
+        self.conv_duo = conv_duo and os.environ.get("YSOD_NO_DUO", "0") != "1"
         self.c2f_cat = os.environ.get("YSOD_C2F_CAT", "1") == "1"     # A/B switch: C2f.cv2 inside the last Bottleneck conv's launch (ysod_conv_tc_set_b2b_cat)
         self.attn_impl = attn_impl   # ysod_mha_core_ex impl: 0 = tcgen05 / TMEM attention core where covered, 1 = mma.sync kernels (A/B)
         self.fuse_upsample = fuse_upsample
