@@ -48,11 +48,6 @@ __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
     return v;
 }
-__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
-    return v;
-}
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -62,13 +57,29 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float silu_tanh(float x) {   // x * sigmoid(x) = h + h * tanh(h), h = x / 2
-    const float h = 0.5f * x;
+__device__ __forceinline__ float tanh_approx(float x) {
     float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
-    return fmaf(h, t, h);
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
+    return t;
 }
 __device__ __forceinline__ void group_barrier(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
+
+// ---- packed fp32 pairs (sm_100 add / mul / fma .f32x2: FADD2 / FMUL2 / FFMA2, two lanes per issue slot). Every row-wise stage of this
+// kernel is a long stream of independent fp32 operations issued by 2 warps per scheduler, so the instruction count is what bounds it.
+typedef unsigned long long p2;
+__device__ __forceinline__ p2 pk2(float lo, float hi) { p2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ p2 pk2u(uint32_t lo, uint32_t hi) { p2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ float2 up2(p2 v) { float2 f; asm("mov.b64 {%0, %1}, %2;" : "=f"(f.x), "=f"(f.y) : "l"(v)); return f; }
+__device__ __forceinline__ p2 add2(p2 a, p2 b) { p2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ p2 mul2(p2 a, p2 b) { p2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ p2 fma2(p2 a, p2 b, p2 c) { p2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ p2 unpack_p2(uint32_t v) { const float2 f = ysod_unpack2(v); return pk2(f.x, f.y); }   // two 16-bit activations
+__device__ __forceinline__ uint32_t pack_p2(p2 v) { const float2 f = up2(v); return pack2(f.x, f.y); }
+// 4 consecutive fp32 pairs (32 B) from shared memory
+__device__ __forceinline__ void lds_p2x4(uint32_t addr, p2* v) {
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v[0]), "=l"(v[1]) : "r"(addr) : "memory");
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v[2]), "=l"(v[3]) : "r"(addr + 16u) : "memory");
+}
 
 // 16 B chunk c of row r of a K-major tile with 128 B rows (SWIZZLE_128B) / 64 B rows (SWIZZLE_64B); tiles are 1 KB aligned
 __device__ __forceinline__ uint32_t row128(uint32_t tile, int r, int c) { return tile + (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
@@ -83,40 +94,79 @@ __device__ __forceinline__ void stage_weights(uint32_t dst, const __nv_bfloat16*
     }
 }
 
-// this thread's 64 fp32 values -> bf16 -> row r of a 128 B-row tile
-__device__ __forceinline__ void store_row64(uint32_t tile, int r, const float* v) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-        st_shared_v4(row128(tile, r, c), pack2(v[8 * c], v[8 * c + 1]), pack2(v[8 * c + 2], v[8 * c + 3]), pack2(v[8 * c + 4], v[8 * c + 5]),
-                     pack2(v[8 * c + 6], v[8 * c + 7]));
+// 32 accumulator columns of this thread's TMEM lane (asynchronous: tmem_wait32 before the registers are read)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+        "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+          "=r"(v[31])
+        : "r"(taddr));
 }
-// LayerNorm over the thread's 64 values without the affine part (folded into the next linear layer by the caller) -> bf16 row
-__device__ __forceinline__ void layernorm_store(uint32_t tile, int r, const float* v) {
-    float s = 0.f;
+// waits for every outstanding tcgen05.ld of the thread; the "+r" operands tie the loaded registers to the wait
+__device__ __forceinline__ void tmem_wait32(uint32_t* v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]),
+                   "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]),
+                   "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]),
+                   "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+}
+// Streams n32 chunks of 32 accumulator columns starting at taddr through `body(i, v)`: chunk i + 1 is in flight while chunk i is processed.
+template <int N32, typename F>
+__device__ __forceinline__ void for_acc32(uint32_t taddr, F&& body) {
+    uint32_t va[32], vb[32];
+    tmem_ld32(taddr, va);
 #pragma unroll
-    for (int k = 0; k < 64; ++k) s += v[k];
-    const float mean = s * (1.0f / 64.0f);
-    float q = 0.f;
-#pragma unroll
-    for (int k = 0; k < 64; ++k) { const float d = v[k] - mean; q = fmaf(d, d, q); }
-    const float rstd = rsqrtf(q * (1.0f / 64.0f) + 1e-5f), c0 = -mean * rstd;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        float y[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) y[k] = fmaf(v[8 * c + k], rstd, c0);
-        st_shared_v4(row128(tile, r, c), pack2(y[0], y[1]), pack2(y[2], y[3]), pack2(y[4], y[5]), pack2(y[6], y[7]));
+    for (int i = 0; i < N32; ++i) {
+        uint32_t* cur = (i & 1) ? vb : va;
+        uint32_t* nxt = (i & 1) ? va : vb;
+        tmem_wait32(cur);
+        if (i + 1 < N32) tmem_ld32(taddr + (uint32_t)((i + 1) * 32), nxt);
+        body(i, cur);
     }
 }
-// 16 accumulator columns of this thread's TMEM lane + 16 fp32 biases from shared memory
-__device__ __forceinline__ void load_acc16(uint32_t taddr, uint32_t bias, float* f) {
-    uint32_t v[16];
-    tmem_ld16(taddr, v);
-    const float4 b0 = lds_f4(bias), b1 = lds_f4(bias + 16u), b2 = lds_f4(bias + 32u), b3 = lds_f4(bias + 48u);
-    tmem_ld_wait(v);
-    const float bb[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
+// v[2j], v[2j+1] (accumulator columns) + bias pair j from shared memory, 16 pairs
+__device__ __forceinline__ void acc_bias32(const uint32_t* v, uint32_t bias, p2* f) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + bb[j];
+    for (int q = 0; q < 4; ++q) {
+        p2 b[4];
+        lds_p2x4(bias + (uint32_t)(q * 32), b);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) f[4 * q + j] = add2(pk2u(v[8 * q + 2 * j], v[8 * q + 2 * j + 1]), b[j]);
+    }
+}
+// the thread's 32 pairs -> bf16 -> row r of a 128 B-row tile
+__device__ __forceinline__ void store_row64(uint32_t tile, int r, const p2* v) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        st_shared_v4(row128(tile, r, c), pack_p2(v[4 * c]), pack_p2(v[4 * c + 1]), pack_p2(v[4 * c + 2]), pack_p2(v[4 * c + 3]));
+}
+// LayerNorm over the thread's 64 values without the affine part (folded into the next linear layer by the caller) -> bf16 row
+__device__ __forceinline__ void layernorm_store(uint32_t tile, int r, const p2* v) {
+    p2 sa = v[0], sb = v[1];
+#pragma unroll
+    for (int k = 2; k < 32; k += 2) { sa = add2(sa, v[k]); sb = add2(sb, v[k + 1]); }
+    const float2 s = up2(add2(sa, sb));
+    const float mean = (s.x + s.y) * (1.0f / 64.0f);
+    const p2 nm = pk2(-mean, -mean);
+    p2 qa = pk2(0.f, 0.f), qb = qa;
+#pragma unroll
+    for (int k = 0; k < 32; k += 2) {
+        const p2 d0 = add2(v[k], nm), d1 = add2(v[k + 1], nm);
+        qa = fma2(d0, d0, qa);
+        qb = fma2(d1, d1, qb);
+    }
+    const float2 q = up2(add2(qa, qb));
+    const float rstd = rsqrtf((q.x + q.y) * (1.0f / 64.0f) + 1e-5f), c0 = -mean * rstd;
+    const p2 rs = pk2(rstd, rstd), cc = pk2(c0, c0);
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        st_shared_v4(row128(tile, r, c), pack_p2(fma2(v[4 * c], rs, cc)), pack_p2(fma2(v[4 * c + 1], rs, cc)), pack_p2(fma2(v[4 * c + 2], rs, cc)),
+                     pack_p2(fma2(v[4 * c + 3], rs, cc)));
 }
 
 __global__ void __launch_bounds__(256, 1)
@@ -167,16 +217,16 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
                        ID_PV = idesc_f16(128, 32, 0, 1);
     const int wsel = r >> 6, t = r & 63;                 // this row's window of the pair, token inside the window
     const int ti = t / WS, tj = t - ti * WS;
-    const long long nwin = (long long)N * nWh * nWw, npairs = (nwin + 1) / 2;
+    const uint32_t nwin = (uint32_t)N * (uint32_t)nWh * (uint32_t)nWw, npairs = (nwin + 1u) / 2u, per_img = (uint32_t)nWh * (uint32_t)nWw;   // host: < 2^31
     uint32_t phase = 0;
 
-    for (long long pr = (long long)blockIdx.x * 2 + grp; pr < npairs; pr += (long long)gridDim.x * 2) {
+    for (uint32_t pr = blockIdx.x * 2u + (uint32_t)grp; pr < npairs; pr += gridDim.x * 2u) {
         // the pair's two windows (the second may not exist): image, origin
-        const long long wa = 2 * pr, wb2 = 2 * pr + 1;
+        const uint32_t wa = 2u * pr, wb2 = 2u * pr + 1u;
         const bool ok_a = true, ok_b = wb2 < nwin;
-        const long long wcb = ok_b ? wb2 : wa;
-        const int w0_a = (int)(wa % nWw) * WS, h0_a = (int)((wa / nWw) % nWh) * WS, n_a = (int)(wa / ((long long)nWw * nWh));
-        const int w0_b = (int)(wcb % nWw) * WS, h0_b = (int)((wcb / nWw) % nWh) * WS, n_b = (int)(wcb / ((long long)nWw * nWh));
+        const uint32_t wcb = ok_b ? wb2 : wa;
+        const int n_a = (int)(wa / per_img), ra = (int)(wa - (uint32_t)n_a * per_img), h0_a = (ra / nWw) * WS, w0_a = (ra % nWw) * WS;
+        const int n_b = (int)(wcb / per_img), rb = (int)(wcb - (uint32_t)n_b * per_img), h0_b = (rb / nWw) * WS, w0_b = (rb % nWw) * WS;
         // ---- A. the two 9 x 9 input patches (64 ch, zero outside the image) -> the QK region; all loads before the first store
         {
             constexpr int NCH = 2 * 81 * 8, NIT = (NCH + 127) / 128;
@@ -204,38 +254,62 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
         }
         group_barrier(grp);
 
-        // ---- B. depthwise 3x3 (taps accumulated in (r, s) order, fp32) -> bf16 token; tokens beyond the image are window_partition's
-        //         zero padding; MMA padding rows 49..63 are zero. Then LayerNorm 1 -> A1.
+        // ---- B. depthwise 3x3 as a sliding window: thread = (window, token column tj, 8-channel chunk) walks the 9 patch rows once, every
+        //         loaded pixel feeds the (up to) three output rows it belongs to; the nine filter taps of the chunk stay in registers. Each
+        //         output accumulates its taps in (r, s) order in fp32, like the reference's conv. Tokens beyond the image are
+        //         window_partition's zero padding. The bf16 tokens go to A1 (row = token), then thread = token row applies LayerNorm 1.
         const int oh = (wsel ? h0_b : h0_a) + ti, ow = (wsel ? w0_b : w0_a) + tj, on = wsel ? n_b : n_a;
         const bool in_img = t < T && (wsel ? ok_b : ok_a) && oh < H && ow < W;
-        float x1[64];   // running token value: dw output, + attention, + MLP
-#pragma unroll
-        for (int k = 0; k < 64; ++k) x1[k] = 0.f;
-        if (in_img) {
+        if (t < 56) {
+            const int dwc = t & 7, dwj = t >> 3;
             const uint32_t pbase = qk + (uint32_t)wsel * PATCH_BYTES;
-#pragma unroll 1
-            for (int tap = 0; tap < 9; ++tap) {
-                const int dr = tap / 3, ds = tap - dr * 3;
-                const int pp = (ti + dr) * 9 + tj + ds;
-                const uint32_t wt = prm_s + 4u * (uint32_t)(P_DW + tap * 64);
+            p2 wv[9][4], acc[7][4];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint4 v = lds_v4(row128(pbase, pp, c));
-                    const float4 w0 = lds_f4(wt + (uint32_t)(c * 32)), w1 = lds_f4(wt + (uint32_t)(c * 32 + 16));
-                    const float2 p0 = ysod_unpack2(v.x), p1 = ysod_unpack2(v.y), p2 = ysod_unpack2(v.z), p3 = ysod_unpack2(v.w);
-                    x1[8 * c + 0] = fmaf(p0.x, w0.x, x1[8 * c + 0]); x1[8 * c + 1] = fmaf(p0.y, w0.y, x1[8 * c + 1]);
-                    x1[8 * c + 2] = fmaf(p1.x, w0.z, x1[8 * c + 2]); x1[8 * c + 3] = fmaf(p1.y, w0.w, x1[8 * c + 3]);
-                    x1[8 * c + 4] = fmaf(p2.x, w1.x, x1[8 * c + 4]); x1[8 * c + 5] = fmaf(p2.y, w1.y, x1[8 * c + 5]);
-                    x1[8 * c + 6] = fmaf(p3.x, w1.z, x1[8 * c + 6]); x1[8 * c + 7] = fmaf(p3.y, w1.w, x1[8 * c + 7]);
+            for (int tap = 0; tap < 9; ++tap) lds_p2x4(prm_s + 4u * (uint32_t)(P_DW + tap * 64 + dwc * 8), wv[tap]);
+#pragma unroll
+            for (int i = 0; i < 7; ++i)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) acc[i][k] = pk2(0.f, 0.f);
+#pragma unroll
+            for (int prw = 0; prw < 9; ++prw) {
+#pragma unroll
+                for (int ds = 0; ds < 3; ++ds) {
+                    const uint4 v = lds_v4(row128(pbase, prw * 9 + dwj + ds, dwc));
+                    const p2 px[4] = {unpack_p2(v.x), unpack_p2(v.y), unpack_p2(v.z), unpack_p2(v.w)};
+#pragma unroll
+                    for (int dr = 0; dr < 3; ++dr) {
+                        const int orow = prw - dr;
+                        if (orow >= 0 && orow < 7) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) acc[orow][k] = fma2(px[k], wv[dr * 3 + ds][k], acc[orow][k]);
+                        }
+                    }
                 }
             }
+            const bool col_ok = (wsel ? ok_b : ok_a) && (wsel ? w0_b : w0_a) + dwj < W;
+            const int hrow0 = wsel ? h0_b : h0_a;
 #pragma unroll
-            for (int k = 0; k < 64; ++k) x1[k] = __bfloat162float(__float2bfloat16_rn(x1[k]));   // the token as the reference's 16-bit dw output
+            for (int i = 0; i < 7; ++i) {
+                const bool live = col_ok && hrow0 + i < H;
+                st_shared_v4(row128(a1, wsel * 64 + i * 7 + dwj, dwc), live ? pack_p2(acc[i][0]) : 0u, live ? pack_p2(acc[i][1]) : 0u,
+                             live ? pack_p2(acc[i][2]) : 0u, live ? pack_p2(acc[i][3]) : 0u);
+            }
         }
-        layernorm_store(a1, r, x1);
+        group_barrier(grp);     // tokens complete; every thread is done with the patches (QK region)
+        p2 x1[32];   // running token value: dw output (as the reference's 16-bit conv output), + attention, + MLP
+#pragma unroll
+        for (int k = 0; k < 32; ++k) x1[k] = pk2(0.f, 0.f);
+        if (t < T) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint4 v = lds_v4(row128(a1, r, c));
+                x1[4 * c] = unpack_p2(v.x); x1[4 * c + 1] = unpack_p2(v.y); x1[4 * c + 2] = unpack_p2(v.z); x1[4 * c + 3] = unpack_p2(v.w);
+            }
+        }
+        layernorm_store(a1, r, x1);   // in place: a thread reads and writes its own row only (MMA padding rows 49..63 become zero rows)
         tc_fence_before();
         fence_async_smem();
-        group_barrier(grp);     // also: every thread is done with the patches (QK region)
+        group_barrier(grp);
         if (issuer_warp && elect_one()) {
             tc_fence_after();
 #pragma unroll
@@ -246,16 +320,17 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
         mbar_wait(bar, phase); phase ^= 1u;
         tc_fence_after();
 
-        // ---- C. in_proj epilogue: + bias -> bf16 -> per-head Q / K / V tiles (64 B rows). (Q rows carry log2(e) / sqrt(d): caller.)
-#pragma unroll
-        for (int ch = 0; ch < 12; ++ch) {
-            float f[16];
-            load_acc16(trow + (uint32_t)(ch * 16), prm_s + 4u * (uint32_t)(P_BQKV + ch * 16), f);
-            const int sel = ch >> 2, hh = (ch >> 1) & 1, cp = (ch & 1) * 2;
+        // ---- C. in_proj epilogue: + bias -> bf16 -> per-head Q / K / V tiles (64 B rows = one head's 32 dims). (Q rows carry
+        //         log2(e) / sqrt(d): caller.)
+        for_acc32<6>(trow, [&](int i, const uint32_t* v) {
+            p2 f[16];
+            acc_bias32(v, prm_s + 4u * (uint32_t)(P_BQKV + i * 32), f);
+            const int sel = i >> 1, hh = i & 1;
             const uint32_t tile = (sel == 0 ? qk : sel == 1 ? qk + 16384u : vv) + (uint32_t)hh * 8192u;
-            st_shared_v4(row64(tile, r, cp), pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
-            st_shared_v4(row64(tile, r, cp + 1), pack2(f[8], f[9]), pack2(f[10], f[11]), pack2(f[12], f[13]), pack2(f[14], f[15]));
-        }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                st_shared_v4(row64(tile, r, c), pack_p2(f[4 * c]), pack_p2(f[4 * c + 1]), pack_p2(f[4 * c + 2]), pack_p2(f[4 * c + 3]));
+        });
         tc_fence_before();
         fence_async_smem();
         group_barrier(grp);
@@ -275,30 +350,32 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
         // ---- D. softmax over the 49 keys of the row's own window (S is in log2 units), P (bf16, unnormalised) -> the QK region as two
         //         K-major chunks of 64 keys; the other window's chunk of this row is zero. O_h = P V_h.
         float inv[2];
-        uint32_t pk[32];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            float s[64];
+            uint32_t sv[64];
+            tmem_ld32(trow + (uint32_t)(h * 128 + wsel * 64), sv);
+            tmem_ld32(trow + (uint32_t)(h * 128 + wsel * 64 + 32), sv + 32);
+            tmem_wait32(sv);
+            tmem_wait32(sv + 32);
+            float mx = __uint_as_float(sv[0]);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[16];
-                tmem_ld16(trow + (uint32_t)(h * 128 + wsel * 64 + c * 16), v);
-                tmem_ld_wait(v);
+            for (int k = 1; k < T; ++k) mx = fmaxf(mx, __uint_as_float(sv[k]));
+            const p2 nmx = pk2(-mx, -mx);
+            uint32_t pk[32];
+            p2 la = pk2(0.f, 0.f), lb = la;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) s[c * 16 + j] = __uint_as_float(v[j]);
+            for (int k = 0; k < 24; ++k) {
+                const float2 d = up2(add2(pk2u(sv[2 * k], sv[2 * k + 1]), nmx));
+                const float e0 = ex2_approx(d.x), e1 = ex2_approx(d.y);
+                if (k & 1) lb = add2(lb, pk2(e0, e1)); else la = add2(la, pk2(e0, e1));
+                pk[k] = pack2(e0, e1);
             }
-            float mx = s[0];
+            const float e48 = ex2_approx(__uint_as_float(sv[48]) - mx);
+            pk[24] = pack2(e48, 0.f);
 #pragma unroll
-            for (int k = 1; k < T; ++k) mx = fmaxf(mx, s[k]);
-            float l = 0.f;
-#pragma unroll
-            for (int k = 0; k < 64; ++k) {
-                s[k] = k < T ? ex2_approx(s[k] - mx) : 0.f;
-                l += s[k];
-            }
-            inv[h] = 1.0f / l;
-#pragma unroll
-            for (int k = 0; k < 32; ++k) pk[k] = pack2(s[2 * k], s[2 * k + 1]);
+            for (int k = 25; k < 32; ++k) pk[k] = 0u;
+            const float2 l2 = up2(add2(la, lb));
+            inv[h] = 1.0f / (l2.x + l2.y + e48);
             if (h == 1) {   // P_0 must have been consumed (O_0 complete) before P_1 overwrites it
                 mbar_wait(bar, phase); phase ^= 1u;
                 tc_fence_after();
@@ -324,18 +401,13 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
         tc_fence_after();
 
         // ---- E. attention output (normalised) -> A1 -> out_proj
-        {
-            float o[64];
+        for_acc32<2>(trow, [&](int i, const uint32_t* v) {
+            const p2 sc = pk2(inv[i], inv[i]);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[16];
-                tmem_ld16(trow + (uint32_t)(c * 16), v);
-                tmem_ld_wait(v);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) o[c * 16 + j] = __uint_as_float(v[j]) * inv[c >> 1];
-            }
-            store_row64(a1, r, o);
-        }
+            for (int c = 0; c < 4; ++c)
+                st_shared_v4(row128(a1, r, 4 * i + c), pack_p2(mul2(pk2u(v[8 * c], v[8 * c + 1]), sc)), pack_p2(mul2(pk2u(v[8 * c + 2], v[8 * c + 3]), sc)),
+                             pack_p2(mul2(pk2u(v[8 * c + 4], v[8 * c + 5]), sc)), pack_p2(mul2(pk2u(v[8 * c + 6], v[8 * c + 7]), sc)));
+        });
         tc_fence_before();
         fence_async_smem();
         group_barrier(grp);
@@ -350,13 +422,12 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
         tc_fence_after();
 
         // ---- F. + bias + residual -> LayerNorm 2 -> A1 -> MLP linear 1
+        for_acc32<2>(trow + 64u, [&](int i, const uint32_t* v) {
+            p2 f[16];
+            acc_bias32(v, prm_s + 4u * (uint32_t)(P_BO + i * 32), f);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            float f[16];
-            load_acc16(trow + 64u + (uint32_t)(c * 16), prm_s + 4u * (uint32_t)(P_BO + c * 16), f);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) x1[c * 16 + j] += f[j];
-        }
+            for (int j = 0; j < 16; ++j) x1[16 * i + j] = add2(x1[16 * i + j], f[j]);
+        });
         layernorm_store(a1, r, x1);
         tc_fence_before();
         fence_async_smem();
@@ -371,17 +442,27 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
         mbar_wait(bar, phase); phase ^= 1u;
         tc_fence_after();
 
-        // ---- G. + bias -> GELU -> bf16 hidden tile (two K chunks of 64 in the QK region) -> MLP linear 2
+        // ---- G. + bias -> GELU (tanh form, common.cuh ysod_gelu_tanh, on pairs) -> bf16 hidden tile (two K chunks of 64 in the QK region)
+        //         -> MLP linear 2
+        {
+            const p2 g3 = pk2(-3.2060743e-4f, -3.2060743e-4f), g2 = pk2(3.6819429e-2f, 3.6819429e-2f), g1 = pk2(7.9770428e-1f, 7.9770428e-1f),
+                     half2 = pk2(0.5f, 0.5f);
+            for_acc32<4>(trow + 128u, [&](int i, const uint32_t* v) {
+                p2 f[16];
+                acc_bias32(v, prm_s + 4u * (uint32_t)(P_B1 + i * 32), f);
+                uint32_t o[16];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float f[16];
-            load_acc16(trow + 128u + (uint32_t)(c * 16), prm_s + 4u * (uint32_t)(P_B1 + c * 16), f);
+                for (int j = 0; j < 16; ++j) {
+                    const p2 xx = mul2(f[j], f[j]);
+                    const p2 q = fma2(fma2(g3, xx, g2), xx, g1);
+                    const float2 a = up2(mul2(f[j], q));
+                    const p2 hx = mul2(f[j], half2);
+                    o[j] = pack_p2(fma2(hx, pk2(tanh_approx(a.x), tanh_approx(a.y)), hx));
+                }
+                const uint32_t tile = qk + (uint32_t)(i >> 1) * 16384u;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = ysod_gelu_tanh(f[j]);
-            const uint32_t tile = qk + (uint32_t)(c >> 2) * 16384u;
-            const int c2 = (c & 3) * 2;
-            st_shared_v4(row128(tile, r, c2), pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
-            st_shared_v4(row128(tile, r, c2 + 1), pack2(f[8], f[9]), pack2(f[10], f[11]), pack2(f[12], f[13]), pack2(f[14], f[15]));
+                for (int c = 0; c < 4; ++c) st_shared_v4(row128(tile, r, (i & 1) * 4 + c), o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+            });
         }
         tc_fence_before();
         fence_async_smem();
@@ -407,13 +488,12 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
         tc_fence_after();
 
         // ---- H. + bias + residual -> bf16 -> A1 -> pw 1x1 (BN folded)
+        for_acc32<2>(trow, [&](int i, const uint32_t* v) {
+            p2 f[16];
+            acc_bias32(v, prm_s + 4u * (uint32_t)(P_B2 + i * 32), f);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            float f[16];
-            load_acc16(trow + (uint32_t)(c * 16), prm_s + 4u * (uint32_t)(P_B2 + c * 16), f);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) x1[c * 16 + j] += f[j];
-        }
+            for (int j = 0; j < 16; ++j) x1[16 * i + j] = add2(x1[16 * i + j], f[j]);
+        });
         store_row64(a1, r, x1);
         tc_fence_before();
         fence_async_smem();
@@ -428,25 +508,29 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
         mbar_wait(bar, phase); phase ^= 1u;
         tc_fence_after();
 
-        // ---- I. + bias -> SiLU -> + identity -> the pixel's 128 B row in global memory
+        // ---- I. + bias -> SiLU (x * sigmoid(x) = h + h * tanh(h), h = x / 2) -> + identity -> the pixel's 128 B row in global memory
         {
             __nv_bfloat16* op = out + (((size_t)on * H + oh) * W + ow) * ocs;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float f[16];
-                load_acc16(trow + 64u + (uint32_t)(c * 16), prm_s + 4u * (uint32_t)(P_BPW + c * 16), f);
+            const p2 half2 = pk2(0.5f, 0.5f);
+            for_acc32<2>(trow + 64u, [&](int i, const uint32_t* v) {
+                p2 f[16];
+                acc_bias32(v, prm_s + 4u * (uint32_t)(P_BPW + i * 32), f);
                 if (in_img) {
-                    const uint32_t iw[8] = {idv[2 * c].x, idv[2 * c].y, idv[2 * c].z, idv[2 * c].w, idv[2 * c + 1].x, idv[2 * c + 1].y, idv[2 * c + 1].z, idv[2 * c + 1].w};
-                    uint32_t ov[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float2 id = ysod_unpack2(iw[j]);
-                        ov[j] = pack2(silu_tanh(f[2 * j]) + id.x, silu_tanh(f[2 * j + 1]) + id.y);
+                    for (int c = 0; c < 4; ++c) {
+                        const uint4 idw = idv[4 * i + c];
+                        const uint32_t iw[4] = {idw.x, idw.y, idw.z, idw.w};
+                        uint32_t ov[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const p2 hx = mul2(f[4 * c + j], half2);
+                            const float2 hf = up2(hx);
+                            ov[j] = pack_p2(add2(fma2(hx, pk2(tanh_approx(hf.x), tanh_approx(hf.y)), hx), unpack_p2(iw[j])));
+                        }
+                        *reinterpret_cast<uint4*>(op + i * 32 + c * 8) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
                     }
-                    *reinterpret_cast<uint4*>(op + c * 16) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
-                    *reinterpret_cast<uint4*>(op + c * 16 + 8) = make_uint4(ov[4], ov[5], ov[6], ov[7]);
                 }
-            }
+            });
         }
         tc_fence_before();   // this tile's TMEM reads are ordered before the barriers of the next tile's first MMA group
     }
@@ -473,6 +557,7 @@ extern "C" int ysod_swin64_tc(const void* x, int N, int H, int W, int xcs, const
     int dev = 0, sms = 148;
     YSOD_CUDA(cudaGetDevice(&dev));
     YSOD_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    YSOD_CHECK_ARG((long long)N * nWh * nWw < (1ll << 31), "ysod_swin64_tc: too many windows");
     const long long npairs = ((long long)N * nWh * nWw + 1) / 2;
     long long grid = (npairs + 1) / 2;
     if (grid > sms) grid = sms;
