@@ -208,6 +208,9 @@ int ysod_swin64_fused(const void* x, int N, int H, int W, int xcs, const void* w
  * LayerNorm / softmax / GELU on tcgen05.ld registers. ysod_swin64_fused (mma.sync) stays as the A/B baseline. */
 int ysod_swin64_tc(const void* x, int N, int H, int W, int xcs, const void* wbf16, const float* pf32, void* out, int ocs, int window,
                    int heads, void* stream);
+/* profiling only: enable / disable the stage trace of the tcgen05 SwinBlock kernel and (host_out != NULL) read back the previous launch's
+ * 8 x 24 clock64 stamps of CTA 0 (tools/prof_swin.py). Replaces nothing in the reference. */
+int ysod_swin64_tc_trace(int enable, long long* host_out);
 
 /* ---- softmax attention core: nn.MultiheadAttention internals (blocks_transformer.py:116, a2_attn.py:53) and the manual
  *      path of AAttn (block.py:1348-1357). q/k/v addressed as ptr + batch*bs + token*ld + head*D (elements). ----------- */

@@ -29,3 +29,18 @@ for name in ("ysod_swin64_fused", "ysod_swin64_tc"):
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     print(f"{name}: N{N} {H}x{W} median {sorted(ts)[len(ts) // 2] * 1e3:.1f} us")
+
+# stage trace of the tcgen05 kernel (CTA 0, group 0, thread 0; SM cycles)
+import ctypes
+LABELS = ["A patches->smem", "B dw 3x3", "B LN1", "QKV mma wait", "C qkv epilogue", "S mma wait", "D softmax+PV (both heads)", "E O->A1", "out_proj wait",
+          "F +res LN2", "MLP1 wait", "G GELU", "MLP2 wait (+identity load)", "H +res", "pw wait", "I SiLU+store"]
+buf = (ctypes.c_longlong * (8 * 24))()
+lib.call("ysod_swin64_tc_trace", 1, None)
+lib.call("ysod_swin64_tc", lib.ptr(x), N, H, W, 64, lib.ptr(wb), lib.ptr(pf), lib.ptr(o), 64, 7, 2, lib.stream_ptr())
+torch.cuda.synchronize()
+lib.call("ysod_swin64_tc_trace", 0, ctypes.cast(buf, ctypes.c_void_p))
+v = list(buf)
+for tile in range(2, 6):
+    st = v[tile * 24: tile * 24 + 17]
+    print(f"tile {tile}: total {st[16] - st[0]} cycles; next tile starts +{v[(tile + 1) * 24] - st[16]}")
+    print("   " + " | ".join(f"{LABELS[i]} {st[i + 1] - st[i]}" for i in range(16)))

@@ -18,6 +18,7 @@
 // math overlap the other's MMAs. The accumulators never round-trip through registers between the GEMM and its consumer more than
 // the algorithm requires (every GEMM here is followed by a row-wise non-linearity).
 #include "umma.cuh"
+#include <cuda.h>
 
 namespace {
 using namespace umma;
@@ -36,11 +37,11 @@ constexpr uint32_t G_A1 = 0, G_QK = 16384, G_V = 49152;
 //   QK: Q_h0 | Q_h1 | K_h0 | K_h1 (8 KB each, 64 B rows) -- before that the two 9x9 input patches, after S the P tile (2 x 16 KB),
 //       after PV the MLP hidden tile (2 x 16 KB)
 //   V : V_h0 | V_h1 (8 KB each, 64 B rows, row = key: an MN-major B operand)
-constexpr uint32_t PATCH_BYTES = 81 * 128;
+constexpr uint32_t PATCH_BYTES = 81 * 128, PATCH_STRIDE = 11 * 1024;   // the second patch starts on a swizzle-atom boundary
 constexpr uint32_t S_PF = S_GRP + 2 * GRP_BYTES;
 // fp32 parameters in shared memory: dw[9][64] | bqkv[192] | bo[64] | b1[128] | b2[64] | bpw[64]
 constexpr int P_DW = 0, P_BQKV = 576, P_BO = 768, P_B1 = 832, P_B2 = 960, P_BPW = 1024, P_TOTAL = 1088;
-constexpr uint32_t S_BAR = S_PF + P_TOTAL * 4;              // two mbarriers, TMEM slot
+constexpr uint32_t S_BAR = S_PF + P_TOTAL * 4;              // MMA mbarrier per group (2 x 8 B) | TMEM slot (@16) | patch mbarrier per group (@24, @32)
 constexpr uint32_t SMEM_BYTES = S_BAR + 64 + 1024;
 
 __device__ __forceinline__ uint4 lds_v4(uint32_t addr) {
@@ -63,6 +64,12 @@ __device__ __forceinline__ float tanh_approx(float x) {
     return t;
 }
 __device__ __forceinline__ void group_barrier(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 
 // ---- packed fp32 pairs (sm_100 add / mul / fma .f32x2: FADD2 / FMUL2 / FFMA2, two lanes per issue slot). Every row-wise stage of this
 // kernel is a long stream of independent fp32 operations issued by 2 warps per scheduler, so the instruction count is what bounds it.
@@ -169,8 +176,13 @@ __device__ __forceinline__ void layernorm_store(uint32_t tile, int r, const p2* 
                      pack_p2(fma2(v[4 * c + 3], rs, cc)));
 }
 
+// profiling only (ysod_swin64_tc_trace): clock64 at the stage boundaries of the first tiles of CTA 0 / group 0 / thread 0
+__device__ long long g_trace[8 * 24];
+__device__ int g_trace_on = 0;
+#define TR(k) do { if (tr_on && tile_i < 8) g_trace[tile_i * 24 + (k)] = clock64(); } while (0)
+
 __global__ void __launch_bounds__(256, 1)
-swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int xcs, const __nv_bfloat16* __restrict__ wb,
+swin64_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat16* __restrict__ x, int N, int H, int W, int xcs, const __nv_bfloat16* __restrict__ wb,
                  const float* __restrict__ pf, __nv_bfloat16* __restrict__ out, int ocs, int nWh, int nWw) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = smem_u32(smem_raw);
@@ -196,6 +208,8 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
     if (tid == 0) {
         mbar_init(base + S_BAR, 1);
         mbar_init(base + S_BAR + 8u, 1);
+        mbar_init(base + S_BAR + 24u, 1);
+        mbar_init(base + S_BAR + 32u, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -219,40 +233,39 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
     const int ti = t / WS, tj = t - ti * WS;
     const uint32_t nwin = (uint32_t)N * (uint32_t)nWh * (uint32_t)nWw, npairs = (nwin + 1u) / 2u, per_img = (uint32_t)nWh * (uint32_t)nWw;   // host: < 2^31
     uint32_t phase = 0;
+    // The two 9 x 9 x 64 input patches of a window pair arrive by TMA (one box each, zero fill outside the image = the conv padding) in the
+    // QK region, which is idle from the end of MLP linear 2 of the previous tile until this tile's in_proj epilogue.
+    const uint32_t pbar = base + S_BAR + 24u + 8u * (uint32_t)grp;
+    uint32_t pphase = 0;
+    auto request_patches = [&](uint32_t prn) {
+        if (prn < npairs) {
+            const uint32_t qa = 2u * prn, qb = 2u * prn + 1u;
+            const bool okb = qb < nwin;
+            const int na = (int)(qa / per_img), rra = (int)(qa - (uint32_t)na * per_img), ha = (rra / nWw) * WS, wa0 = (rra % nWw) * WS;
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pbar), "r"(okb ? 2u * PATCH_BYTES : PATCH_BYTES) : "memory");
+            tma_load_4d(qk, &tmX, pbar, 0, wa0 - 1, ha - 1, na);
+            if (okb) {
+                const int nb = (int)(qb / per_img), rrb = (int)(qb - (uint32_t)nb * per_img), hb = (rrb / nWw) * WS, wb0 = (rrb % nWw) * WS;
+                tma_load_4d(qk + PATCH_STRIDE, &tmX, pbar, 0, wb0 - 1, hb - 1, nb);
+            }
+        }
+    };
+    if (issuer_warp && elect_one()) request_patches(blockIdx.x * 2u + (uint32_t)grp);
+    const bool tr_on = g_trace_on && blockIdx.x == 0 && tid == 0;
+    int tile_i = -1;
 
     for (uint32_t pr = blockIdx.x * 2u + (uint32_t)grp; pr < npairs; pr += gridDim.x * 2u) {
+        ++tile_i;
+        TR(0);
         // the pair's two windows (the second may not exist): image, origin
         const uint32_t wa = 2u * pr, wb2 = 2u * pr + 1u;
         const bool ok_a = true, ok_b = wb2 < nwin;
         const uint32_t wcb = ok_b ? wb2 : wa;
         const int n_a = (int)(wa / per_img), ra = (int)(wa - (uint32_t)n_a * per_img), h0_a = (ra / nWw) * WS, w0_a = (ra % nWw) * WS;
         const int n_b = (int)(wcb / per_img), rb = (int)(wcb - (uint32_t)n_b * per_img), h0_b = (rb / nWw) * WS, w0_b = (rb % nWw) * WS;
-        // ---- A. the two 9 x 9 input patches (64 ch, zero outside the image) -> the QK region; all loads before the first store
-        {
-            constexpr int NCH = 2 * 81 * 8, NIT = (NCH + 127) / 128;
-            uint4 pv[NIT];
-#pragma unroll
-            for (int it = 0; it < NIT; ++it) {
-                const int i = r + it * 128;
-                const int s = i >= 648 ? 1 : 0, rem = i - s * 648;
-                const int pp = rem >> 3, pc = rem & 7;
-                const int prow = pp / 9, pcol = pp - prow * 9;
-                const int ih = (s ? h0_b : h0_a) - 1 + prow, iw = (s ? w0_b : w0_a) - 1 + pcol;
-                pv[it] = make_uint4(0, 0, 0, 0);
-                if (i < NCH && (s ? ok_b : ok_a) && ih >= 0 && ih < H && iw >= 0 && iw < W)
-                    pv[it] = __ldg(reinterpret_cast<const uint4*>(x + (((size_t)(s ? n_b : n_a) * H + ih) * W + iw) * xcs + pc * 8));
-            }
-#pragma unroll
-            for (int it = 0; it < NIT; ++it) {
-                const int i = r + it * 128;
-                if (i < NCH) {
-                    const int s = i >= 648 ? 1 : 0, rem = i - s * 648;
-                    const int pp = rem >> 3, pc = rem & 7;
-                    st_shared_v4(row128(qk + (uint32_t)s * PATCH_BYTES, pp, pc), pv[it].x, pv[it].y, pv[it].z, pv[it].w);
-                }
-            }
-        }
-        group_barrier(grp);
+        // ---- A. the two 9 x 9 input patches were requested during the previous tile
+        mbar_wait(pbar, pphase); pphase ^= 1u;
+        TR(1);
 
         // ---- B. depthwise 3x3 as a sliding window: thread = (window, token column tj, 8-channel chunk) walks the 9 patch rows once, every
         //         loaded pixel feeds the (up to) three output rows it belongs to; the nine filter taps of the chunk stay in registers. Each
@@ -262,7 +275,7 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
         const bool in_img = t < T && (wsel ? ok_b : ok_a) && oh < H && ow < W;
         if (t < 56) {
             const int dwc = t & 7, dwj = t >> 3;
-            const uint32_t pbase = qk + (uint32_t)wsel * PATCH_BYTES;
+            const uint32_t pbase = qk + (uint32_t)wsel * PATCH_STRIDE;
             p2 wv[9][4], acc[7][4];
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) lds_p2x4(prm_s + 4u * (uint32_t)(P_DW + tap * 64 + dwc * 8), wv[tap]);
@@ -296,6 +309,7 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
             }
         }
         group_barrier(grp);     // tokens complete; every thread is done with the patches (QK region)
+        TR(2);
         p2 x1[32];   // running token value: dw output (as the reference's 16-bit conv output), + attention, + MLP
 #pragma unroll
         for (int k = 0; k < 32; ++k) x1[k] = pk2(0.f, 0.f);
@@ -307,6 +321,7 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
             }
         }
         layernorm_store(a1, r, x1);   // in place: a thread reads and writes its own row only (MMA padding rows 49..63 become zero rows)
+        TR(3);
         tc_fence_before();
         fence_async_smem();
         group_barrier(grp);
@@ -319,6 +334,7 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
         }
         mbar_wait(bar, phase); phase ^= 1u;
         tc_fence_after();
+        TR(4);
 
         // ---- C. in_proj epilogue: + bias -> bf16 -> per-head Q / K / V tiles (64 B rows = one head's 32 dims). (Q rows carry
         //         log2(e) / sqrt(d): caller.)
@@ -331,6 +347,7 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
             for (int c = 0; c < 4; ++c)
                 st_shared_v4(row64(tile, r, c), pack_p2(f[4 * c]), pack_p2(f[4 * c + 1]), pack_p2(f[4 * c + 2]), pack_p2(f[4 * c + 3]));
         });
+        TR(5);
         tc_fence_before();
         fence_async_smem();
         group_barrier(grp);
@@ -346,6 +363,7 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
         }
         mbar_wait(bar, phase); phase ^= 1u;
         tc_fence_after();
+        TR(6);
 
         // ---- D. softmax over the 49 keys of the row's own window (S is in log2 units), P (bf16, unnormalised) -> the QK region as two
         //         K-major chunks of 64 keys; the other window's chunk of this row is zero. O_h = P V_h.
@@ -399,6 +417,7 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
         }
         mbar_wait(bar, phase); phase ^= 1u;
         tc_fence_after();
+        TR(7);
 
         // ---- E. attention output (normalised) -> A1 -> out_proj
         for_acc32<2>(trow, [&](int i, const uint32_t* v) {
@@ -408,6 +427,7 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
                 st_shared_v4(row128(a1, r, 4 * i + c), pack_p2(mul2(pk2u(v[8 * c], v[8 * c + 1]), sc)), pack_p2(mul2(pk2u(v[8 * c + 2], v[8 * c + 3]), sc)),
                              pack_p2(mul2(pk2u(v[8 * c + 4], v[8 * c + 5]), sc)), pack_p2(mul2(pk2u(v[8 * c + 6], v[8 * c + 7]), sc)));
         });
+        TR(8);
         tc_fence_before();
         fence_async_smem();
         group_barrier(grp);
@@ -420,6 +440,7 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
         }
         mbar_wait(bar, phase); phase ^= 1u;
         tc_fence_after();
+        TR(9);
 
         // ---- F. + bias + residual -> LayerNorm 2 -> A1 -> MLP linear 1
         for_acc32<2>(trow + 64u, [&](int i, const uint32_t* v) {
@@ -429,6 +450,7 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
             for (int j = 0; j < 16; ++j) x1[16 * i + j] = add2(x1[16 * i + j], f[j]);
         });
         layernorm_store(a1, r, x1);
+        TR(10);
         tc_fence_before();
         fence_async_smem();
         group_barrier(grp);
@@ -441,6 +463,7 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
         }
         mbar_wait(bar, phase); phase ^= 1u;
         tc_fence_after();
+        TR(11);
 
         // ---- G. + bias -> GELU (tanh form, common.cuh ysod_gelu_tanh, on pairs) -> bf16 hidden tile (two K chunks of 64 in the QK region)
         //         -> MLP linear 2
@@ -464,6 +487,7 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
                 for (int c = 0; c < 4; ++c) st_shared_v4(row128(tile, r, (i & 1) * 4 + c), o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
             });
         }
+        TR(12);
         tc_fence_before();
         fence_async_smem();
         group_barrier(grp);
@@ -486,6 +510,8 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
         }
         mbar_wait(bar, phase); phase ^= 1u;
         tc_fence_after();
+        if (issuer_warp && elect_one()) request_patches(pr + gridDim.x * 2u);   // the hidden tile is consumed: the QK region takes the next tile's patches
+        TR(13);
 
         // ---- H. + bias + residual -> bf16 -> A1 -> pw 1x1 (BN folded)
         for_acc32<2>(trow, [&](int i, const uint32_t* v) {
@@ -495,6 +521,7 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
             for (int j = 0; j < 16; ++j) x1[16 * i + j] = add2(x1[16 * i + j], f[j]);
         });
         store_row64(a1, r, x1);
+        TR(14);
         tc_fence_before();
         fence_async_smem();
         group_barrier(grp);
@@ -507,6 +534,7 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
         }
         mbar_wait(bar, phase); phase ^= 1u;
         tc_fence_after();
+        TR(15);
 
         // ---- I. + bias -> SiLU (x * sigmoid(x) = h + h * tanh(h), h = x / 2) -> + identity -> the pixel's 128 B row in global memory
         {
@@ -532,6 +560,7 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
                 }
             });
         }
+        TR(16);
         tc_fence_before();   // this tile's TMEM reads are ordered before the barriers of the next tile's first MMA group
     }
 
@@ -542,7 +571,17 @@ swin64_tc_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int x
     }
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
 }  // namespace
+
+// profiling only: enable / read the stage trace of swin64_tc_kernel (8 tiles x 24 clock64 stamps of CTA 0, thread 0)
+extern "C" int ysod_swin64_tc_trace(int enable, long long* host_out) {
+    if (host_out) YSOD_CUDA(cudaMemcpyFromSymbol(host_out, g_trace, sizeof(long long) * 8 * 24));
+    YSOD_CUDA(cudaMemcpyToSymbol(g_trace_on, &enable, sizeof(int)));
+    return YSOD_OK;
+}
 
 // Same contract as ysod_swin64_fused (swin_fused.cu): x / out NHWC 16-bit views with 64 channels, the caller pre-folds the LayerNorm
 // affine parts into in_proj / mlp.0 and log2(e) / sqrt(head_dim) into the Q rows; wbf16 / pf32 are the same blobs.
@@ -561,8 +600,28 @@ extern "C" int ysod_swin64_tc(const void* x, int N, int H, int W, int xcs, const
     const long long npairs = ((long long)N * nWh * nWw + 1) / 2;
     long long grid = (npairs + 1) / 2;
     if (grid > sms) grid = sms;
+    // the input map as a 4-D tensor (C = 64 of xcs, W, H, N); one TMA box = a window's 9 x 9 patch in 128 B swizzled pixel rows
+    static EncodeTiledFn enc = nullptr;
+    if (!enc) {
+        void* fp = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) enc = (EncodeTiledFn)fp;
+    }
+    YSOD_CHECK_ARG(enc != nullptr, "ysod_swin64_tc: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+    CUtensorMap tmX;
+    {
+        cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)xcs * 2, (cuuint64_t)W * xcs * 2, (cuuint64_t)H * W * xcs * 2};
+        cuuint32_t box[4] = {64, 9, 9, 1}, es[4] = {1, 1, 1, 1};
+        const CUresult cr = enc(&tmX, YSOD_TMAP_16, 4, const_cast<void*>(x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) {
+            ysod_set_error("ysod_swin64_tc: cuTensorMapEncodeTiled failed with %d (W %d H %d N %d xcs %d)", (int)cr, W, H, N, xcs);
+            return YSOD_ERR_CUDA;
+        }
+    }
     YSOD_CUDA(cudaFuncSetAttribute(swin64_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    ysod_launch(swin64_tc_kernel, (unsigned)grid, 256, SMEM_BYTES, stream, (const __nv_bfloat16*)x, N, H, W, xcs, (const __nv_bfloat16*)wbf16, pf32,
+    ysod_launch(swin64_tc_kernel, (unsigned)grid, 256, SMEM_BYTES, stream, tmX, (const __nv_bfloat16*)x, N, H, W, xcs, (const __nv_bfloat16*)wbf16, pf32,
                 (__nv_bfloat16*)out, ocs, nWh, nWw);
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;

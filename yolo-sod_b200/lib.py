@@ -74,6 +74,7 @@ PROTOTYPES = {
     "ysod_mha_window_nhwc": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp, f32, vp, i32, vp]),
     "ysod_swin64_fused": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, i32, i32, i32, vp]),
     "ysod_swin64_tc": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, i32, i32, i32, vp]),
+    "ysod_swin64_tc_trace": (i32, [i32, vp]),
     "ysod_mha_core": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i64, i64, i64, f32, vp, i32, i64, vp]),
     "ysod_mha_core_ex": (i32, [vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i64, i64, i64, f32, vp, i32, i64, i32, vp]),
 }
