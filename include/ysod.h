@@ -119,6 +119,12 @@ int ysod_stem_conv(const float* img, int N, int H, int W, const float* w, const 
 #define YSOD_STEM_INDIRECT 0x10 /* src_fmt | 0x10: `img` is a device slot (void**) holding the image pointer, see ysod_set_ptr */
 int ysod_stem_mma(const void* img, int src_fmt, int N, int H, int W, const void* wk, const float* bias, int Cout, void* out, int ocs,
                   int act, void* stream);
+/* The same stem conv that also leaves the global-average-pool partial sums of its output for the SE_Block that follows it in the SOD
+ * YAMLs (smallobj_modules.py SE_Block.forward: avg_pool -> fc1 -> ReLU -> fc2 -> sigmoid): psum[N][S][Cout] fp32, S = ceil(W/2 / 64) *
+ * ceil(H/2 / 4) tiles per image, each the sum of the tile's stored 16-bit outputs; ysod_se_gate(psum, N, S, ...) consumes it, so the SE
+ * block does not read the stem's map again for its pooling. */
+int ysod_stem_mma_gap(const void* img, int src_fmt, int N, int H, int W, const void* wk, const float* bias, int Cout, void* out,
+                      int ocs, int act, float* psum, void* stream);
 
 /* Binds the input of a captured forward without a staging copy (the reference's forward reads the caller's tensor in place,
  * nn/tasks.py:129-163): stores `value` in the device pointer slot that ysod_stem_mma(..., src_fmt | YSOD_STEM_INDIRECT) reads. */

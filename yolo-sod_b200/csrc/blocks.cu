@@ -90,10 +90,38 @@ __device__ __forceinline__ void se_gate_body(int n, const float* psum, int S, in
                                              int hid, float* __restrict__ gate, float* sm) {
     float* mean = sm;
     float* h = sm + C;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float a = 0.f;
-        for (int s = 0; s < S; ++s) a += __ldcg(psum + ((size_t)n * S + s) * C + c);
-        mean[c] = a / (float)HW;
+    // many partials (the per-tile sums a producing kernel wrote): blockDim / C threads per channel, each a strided share with four loads in flight
+    {
+        // parts = threads per channel (fixed by blockDim and C, so the summation order is fixed)
+        const int parts = (S > 32 && C <= 128 && blockDim.x >= 256) ? 256 / C : 1;
+        if (parts == 1) {
+            for (int c = threadIdx.x; c < C; c += blockDim.x) {
+                float a = 0.f;
+                for (int s = 0; s < S; ++s) a += __ldcg(psum + ((size_t)n * S + s) * C + c);
+                mean[c] = a / (float)HW;
+            }
+        } else {
+            __shared__ float red[256];
+            const int c = threadIdx.x % C, part = threadIdx.x / C;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            if (part < parts) {
+                int s = part;
+                for (; s + 3 * parts < S; s += 4 * parts) {
+                    a0 += __ldcg(psum + ((size_t)n * S + s) * C + c);
+                    a1 += __ldcg(psum + ((size_t)n * S + s + parts) * C + c);
+                    a2 += __ldcg(psum + ((size_t)n * S + s + 2 * parts) * C + c);
+                    a3 += __ldcg(psum + ((size_t)n * S + s + 3 * parts) * C + c);
+                }
+                for (; s < S; s += parts) a0 += __ldcg(psum + ((size_t)n * S + s) * C + c);
+            }
+            if ((int)threadIdx.x < parts * C) red[threadIdx.x] = (a0 + a1) + (a2 + a3);
+            __syncthreads();
+            if ((int)threadIdx.x < C) {
+                float a = 0.f;
+                for (int q = 0; q < parts; ++q) a += red[q * C + threadIdx.x];
+                mean[threadIdx.x] = a / (float)HW;
+            }
+        }
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;

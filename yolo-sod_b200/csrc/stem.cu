@@ -45,7 +45,7 @@ __device__ __forceinline__ int koff(int k) {
 template <int COUT, int SRC, bool VEC>
 __global__ void __launch_bounds__(256, COUT <= 32 ? 4 : 2)
 stem_mma_kernel(const void* img_, const __nv_bfloat16* __restrict__ wk, const float* __restrict__ bias,
-                __nv_bfloat16* __restrict__ out, int H, int W, int Ho, int Wo, int ocs, int act, int indirect) {
+                __nv_bfloat16* __restrict__ out, int H, int W, int Ho, int Wo, int ocs, int act, int indirect, float* __restrict__ psum) {
     ysod_pdl_sync();
     // indirect: img_ is a device slot holding the image pointer (ysod_set_ptr), so a captured graph can read whichever tensor
     // the caller passed to this forward instead of a private staging copy
@@ -201,6 +201,30 @@ stem_mma_kernel(const void* img_, const __nv_bfloat16* __restrict__ wk, const fl
         }
     }
     __syncthreads();
+    // ---- optional: this tile's per-channel sums of the stored (16-bit) values = partial sums of the global average pool that the
+    //      SE block after the stem starts with (smallobj_modules.py SE_Block: avg_pool), so the map is not read again for them.
+    //      psum[n][tile][COUT], tile = blockIdx.y * gridDim.x + blockIdx.x; fixed summation order.
+    if (psum != nullptr) {
+        constexpr int PG = 256 / COUT;          // pixel groups
+        constexpr int PPG = TH * TW / PG;       // pixels per group
+        float* part = reinterpret_cast<float*>(patch);   // the patch is dead (all m-tiles done): [PG][COUT] floats
+        const int c = tid % COUT, pg = tid / COUT;
+        float a = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < PPG; ++i) {
+            const int pix = pg * PPG + i;
+            const int r = pix / TW, q = pix - r * TW;
+            if (oh0 + r < Ho && ow0 + q < Wo) a += __bfloat162float(stage[(size_t)pix * (COUT + 8) + c]);
+        }
+        part[pg * COUT + c] = a;
+        __syncthreads();
+        if (tid < COUT) {
+            float t2 = 0.f;
+#pragma unroll
+            for (int g2 = 0; g2 < PG; ++g2) t2 += part[g2 * COUT + tid];
+            psum[((size_t)n * (gridDim.x * gridDim.y) + blockIdx.y * gridDim.x + blockIdx.x) * COUT + tid] = t2;
+        }
+    }
     // ---- coalesced write-out: 16-byte pieces, consecutive threads -> consecutive channels then pixels
     constexpr int PIECES = COUT / 8;
     for (int i = tid; i < TH * TW * PIECES; i += 256) {
@@ -231,8 +255,10 @@ extern "C" int ysod_set_ptr(void* slot, const void* value, cudaStream_t stream) 
 //      src_fmt 1 = (N,H,W,3) uint8 BGR frames (what BasePredictor.preprocess receives, predictor.py:116-134).
 // wk: [Cout][32] bf16, column k = (r*3 + s)*3 + c (RGB channel c), columns 27..31 zero; bias fp32 [Cout] (BN folded).
 // out: NHWC bf16 view with pixel stride ocs. 3x3 / stride 2 / pad 1 only; H, W even.
-extern "C" int ysod_stem_mma(const void* img, int src_fmt, int N, int H, int W, const void* wk, const float* bias, int Cout, void* out,
-                             int ocs, int act, cudaStream_t stream) {
+// psum != NULL: the kernel also writes per-tile channel sums of its output, psum[N][S][Cout] fp32 with S = ceil(W/2 / 64) * ceil(H/2 / 4)
+// (the layout ysod_se_gate / ysod_gap_partial use), so a following SE block skips its pooling pass.
+static int stem_mma_impl(const void* img, int src_fmt, int N, int H, int W, const void* wk, const float* bias, int Cout, void* out,
+                         int ocs, int act, float* psum, cudaStream_t stream) {
     YSOD_CHECK_ARG(img && wk && bias && out, "ysod_stem_mma: null pointer");
     YSOD_CHECK_ARG(Cout == 16 || Cout == 32 || Cout == 64, "ysod_stem_mma: Cout %d unsupported (16, 32, 64)", Cout);
     const int indirect = (src_fmt & YSOD_STEM_INDIRECT) ? 1 : 0;
@@ -248,8 +274,8 @@ extern "C" int ysod_stem_mma(const void* img, int src_fmt, int N, int H, int W, 
     const bool vec = (W % 4 == 0) && (indirect || (uintptr_t)img % 16 == 0);
 #define LAUNCH(CO, SRC)                                                                                          \
     do {                                                                                                         \
-        if (vec) ysod_launch(stem_mma_kernel<CO, SRC, true>, grid, 256, 0, stream, img, w, bias, o, H, W, Ho, Wo, ocs, act, indirect);   \
-        else ysod_launch(stem_mma_kernel<CO, SRC, false>, grid, 256, 0, stream, img, w, bias, o, H, W, Ho, Wo, ocs, act, indirect);      \
+        if (vec) ysod_launch(stem_mma_kernel<CO, SRC, true>, grid, 256, 0, stream, img, w, bias, o, H, W, Ho, Wo, ocs, act, indirect, psum);   \
+        else ysod_launch(stem_mma_kernel<CO, SRC, false>, grid, 256, 0, stream, img, w, bias, o, H, W, Ho, Wo, ocs, act, indirect, psum);      \
     } while (0)
     if (Cout == 16) { if (src_fmt) LAUNCH(16, 1); else LAUNCH(16, 0); }
     else if (Cout == 32) { if (src_fmt) LAUNCH(32, 1); else LAUNCH(32, 0); }
@@ -257,4 +283,16 @@ extern "C" int ysod_stem_mma(const void* img, int src_fmt, int N, int H, int W, 
 #undef LAUNCH
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
+}
+
+extern "C" int ysod_stem_mma(const void* img, int src_fmt, int N, int H, int W, const void* wk, const float* bias, int Cout, void* out,
+                             int ocs, int act, cudaStream_t stream) {
+    return stem_mma_impl(img, src_fmt, N, H, W, wk, bias, Cout, out, ocs, act, nullptr, stream);
+}
+
+// ysod_stem_mma + the global-average-pool partial sums of its output (see stem_mma_impl): stem Conv -> SE_Block without a pooling pass.
+extern "C" int ysod_stem_mma_gap(const void* img, int src_fmt, int N, int H, int W, const void* wk, const float* bias, int Cout, void* out,
+                                 int ocs, int act, float* psum, cudaStream_t stream) {
+    YSOD_CHECK_ARG(psum != nullptr, "ysod_stem_mma_gap: null psum");
+    return stem_mma_impl(img, src_fmt, N, H, W, wk, bias, Cout, out, ocs, act, psum, stream);
 }

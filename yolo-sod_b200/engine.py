@@ -551,10 +551,14 @@ class Program:
         Cc, HW = x.C, x.H * x.W
         hid = sd[f"{P}.fc1.weight"].shape[0]
         S = self._splits(x.N, HW)
-        psum, gate = self.f32(x.N, S, Cc), self.f32(x.N, Cc)
+        pre = getattr(self, "_stem_psum", None)
+        pre = pre if (pre is not None and pre[0].buf is x.buf and pre[0].off == x.off and pre[0].C == x.C) else None
+        psum, gate = (pre[1] if pre else self.f32(x.N, S, Cc)), self.f32(x.N, Cc)
         w1, b1 = self.dev_t(sd[f"{P}.fc1.weight"].reshape(hid, Cc)), self.dev_t(sd[f"{P}.fc1.bias"])
         w2, b2 = self.dev_t(sd[f"{P}.fc2.weight"].reshape(Cc, hid)), self.dev_t(sd[f"{P}.fc2.bias"])
-        if self.m.fuse_gate:
+        if pre:     # the producing stem kernel already wrote the pooling partials (ysod_stem_mma_gap)
+            self.emit("ysod_se_gate", _lib.ptr(psum), x.N, pre[2], HW, Cc, _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), hid, _lib.ptr(gate))
+        elif self.m.fuse_gate:
             cnt = torch.zeros(x.N, device=self.dev, dtype=torch.int32)
             self.keep.append(cnt)
             self.emit("ysod_gap_gate", x.ptr(), self.code, x.N, HW, Cc, x.cs, S, _lib.ptr(psum), None, _lib.ptr(cnt), 0, _lib.ptr(w1),
@@ -866,8 +870,18 @@ class Program:
                         wk[:, :27] = wf.permute(0, 2, 3, 1).reshape(co, 27)
                         wd, bd = self.dev_t(wk, self.dt), self.dev_t(bf)
                         self.img_indirect = True
-                        self.emit("ysod_stem_mma", _lib.ptr(self.img_slot), (1 if self.src_u8 else 0) | _lib.STEM_INDIRECT, self.B, self.H, self.W, _lib.ptr(wd),
-                                  _lib.ptr(bd), co, o.ptr(), o.cs, _lib.ACT["silu" if p["act"] else "none"], desc=f"stem 3->{co}")
+                        nxt = layers[1] if len(layers) > 1 else None
+                        if self.m.fuse_stem_gap and nxt is not None and nxt.type == "SE_Block" and nxt.f == -1:
+                            # the SE block after the stem pools the stem's output: the stem kernel leaves the per-tile channel sums (SE_Block avg_pool)
+                            S0 = -(-(self.W // 2) // 64) * -(-(self.H // 2) // 4)
+                            ps0 = self.f32(self.B, S0, co)
+                            self._stem_psum = (o, ps0, S0)
+                            self.emit("ysod_stem_mma_gap", _lib.ptr(self.img_slot), (1 if self.src_u8 else 0) | _lib.STEM_INDIRECT, self.B, self.H, self.W,
+                                      _lib.ptr(wd), _lib.ptr(bd), co, o.ptr(), o.cs, _lib.ACT["silu" if p["act"] else "none"], _lib.ptr(ps0),
+                                      desc=f"stem 3->{co} + GAP partial sums")
+                        else:
+                            self.emit("ysod_stem_mma", _lib.ptr(self.img_slot), (1 if self.src_u8 else 0) | _lib.STEM_INDIRECT, self.B, self.H, self.W, _lib.ptr(wd),
+                                      _lib.ptr(bd), co, o.ptr(), o.cs, _lib.ACT["silu" if p["act"] else "none"], desc=f"stem 3->{co}")
                     else:
                         if self.src_u8:
                             raise NotImplementedError("uint8 frame input needs the bf16 tensor-core stem (3x3/s2, Cout 16/32/64)")
@@ -1042,7 +1056,7 @@ class B200DetectionModel:
     """
 
     def __init__(self, cfg, state_dict, dtype=torch.bfloat16, device="cuda:0", use_tc=True, use_graph=True, nc=None,
-                 static_outputs=False, max_programs=8, attn_impl=0, fuse_cbam=False, ca_single_pass=False, fuse_b2b=True, swin_nhwc=True, fuse_swin=True, multi_stream=True, fuse_upsample=True, fuse_decode=True, fuse_se=True, fuse_gate=False, conv_duo=True, swin_impl=0):
+                 static_outputs=False, max_programs=8, attn_impl=0, fuse_cbam=False, ca_single_pass=False, fuse_b2b=True, swin_nhwc=True, fuse_swin=True, multi_stream=True, fuse_upsample=True, fuse_decode=True, fuse_se=True, fuse_gate=False, conv_duo=True, swin_impl=0, fuse_stem_gap=True):
         _lib.require_cuda()
         _lib.load()
         self.spec = cfg if isinstance(cfg, _cfg.ModelSpec) else _cfg.get_spec(cfg, nc=nc)
@@ -1076,6 +1090,7 @@ class B200DetectionModel:
             multi_stream = os.environ["YSOD_MULTI_STREAM"] == "1"
         self.conv_pair = os.environ.get("YSOD_NO_PAIR", "0") != "1"   # A/B switch of the conv kernel's tile-pair plan (ysod.h YSOD_CONV_NO_PAIR)
         # pixel-duo plan for dense 32 -> 32 3x3 convs (ysod.h YSOD_CONV_NO_DUO): same products, different accumulation order than the 32-channel plan
+        self.fuse_stem_gap = fuse_stem_gap and os.environ.get("YSOD_STEM_GAP", "1") != "0"   # stem kernel leaves the SE pooling partials (A/B switch)
         self.conv_duo = conv_duo and os.environ.get("YSOD_NO_DUO", "0") != "1"
         self.c2f_cat = os.environ.get("YSOD_C2F_CAT", "1") == "1"     # A/B switch: C2f.cv2 inside the last Bottleneck conv's launch (ysod_conv_tc_set_b2b_cat)
         self.attn_impl = attn_impl   # ysod_mha_core_ex impl: 0 = tcgen05 / TMEM attention core where covered, 1 = mma.sync kernels (A/B)

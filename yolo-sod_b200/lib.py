@@ -45,6 +45,7 @@ PROTOTYPES = {
     "ysod_dwconv": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp, i32, i32, i32, vp, i32, vp, i32, i32, vp]),
     "ysod_stem_conv": (i32, [vp, i32, i32, i32, vp, vp, i32, i32, i32, i32, vp, i32, i32, i32, vp]),
     "ysod_stem_mma": (i32, [vp, i32, i32, i32, i32, vp, vp, i32, vp, i32, i32, vp]),
+    "ysod_stem_mma_gap": (i32, [vp, i32, i32, i32, i32, vp, vp, i32, vp, i32, i32, vp, vp]),
     "ysod_set_ptr": (i32, [vp, vp, vp]),
     "ysod_letterbox_u8": (i32, [vp, i32, i32, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp]),
     "ysod_scale_boxes": (i32, [vp, i32, i32, i32, vp, i32, vp]),
