@@ -14,6 +14,7 @@ CONV_NO_SPLIT_STAGING = 0x10   # ysod.h YSOD_CONV_NO_SPLIT_STAGING
 CONV_NO_PAIR = 0x04       # ysod.h YSOD_CONV_NO_PAIR
 CONV_NO_STORE = 0x20      # ysod.h YSOD_CONV_NO_STORE
 CONV_NO_DUO = 0x10000     # ysod.h YSOD_CONV_NO_DUO
+CONV_NO_GRES = 0x20000    # ysod.h YSOD_CONV_NO_GRES
 STEM_INDIRECT = 0x10      # ysod.h YSOD_STEM_INDIRECT
 ACT = {"none": 0, "silu": 1, "gelu": 2, "relu": 3, "sigmoid": 4, "hsigmoid": 5}
 
