@@ -74,11 +74,6 @@ int ysod_conv_tc_create(ysod_conv_tc** handle, const void* x, int N, int H, int 
  * block.py:343-356) normally run the halo kernel's pixel-duo plan (one MMA row = two adjacent output pixels, N = 64, 128 B operand
  * rows: tc_conv.cu TcParams::duo); this bit keeps the 32-channel plan (N = 32, 64 B rows), which ysod_conv_tc_set_b2b_cat needs. */
 #define YSOD_CONV_NO_DUO 0x10000
-/* | 0x20000 (YSOD_CONV_NO_GRES): A/B switch -- deep-K layers without a halo plan (1x1 convs / linears with K >= 192, stride-2 3x3 convs with few
- * input channels) whose whole [BN x K] weight tile fits beside the activation ring keep it RESIDENT in shared memory: every CTA is dealt
- * the tiles of one N tile only, loads the weights once and streams activations alone (tc_conv.cu TcParams::gres). This bit restores the
- * plan that streams {activation, weight} block pairs. Same products and accumulation order either way (bit-identical outputs). */
-#define YSOD_CONV_NO_GRES 0x20000
 int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, int W, int Cin, int xcs, const void* wgt,
                            const float* bias, int Cout, int Cout_pad, int ksize, int stride, void* out, int out_dtype, int ocs,
                            const void* res, int rcs, int act, int mode);

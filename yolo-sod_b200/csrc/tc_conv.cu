@@ -83,13 +83,9 @@ struct TcParams {
                 // (25 % structural zeros). Against the 32-channel plan (N = 32, 64 B rows): half the MMA instructions per pixel at the
                 // N = 64 rate, and 128 B swizzled operand rows instead of 64 B ones (whose 8-row groups hit every bank twice: 83 cycles per
                 // N = 32 MMA measured, against 48 in isolation).
-    int gres;   // generic kernel with RESIDENT weights (1x1 / deep-K layers whose whole [BN x K] weight tile fits beside the A ring): tiles are
-                // dealt so that a CTA keeps ONE N tile for its whole life (tile index = spatial * n_tiles + nt, grid a multiple of n_tiles),
-                // the producer lands the num_k weight blocks once (before the dependency wait: weights are static) and the ring carries
-                // activations only. These layers are bound by bytes in flight x L2 latency: half the bytes per tile, twice the useful depth.
     int up2;    // nn.Upsample(scale 2, nearest) fused into the store: every output pixel is written to its 2 x 2 block of the 2Ho x 2Wo destination
     int debug;  // profiling only (mode >> 8): 1 = epilogue drains without work, 2 = producer skips TMA, 4 = MMA issuer skips tcgen05.mma,
-                // 8 = epilogue skips the TMA store, 16 = epilogue skips the activation, 128 = epilogue requests TMEM chunks without look-ahead
+                // 8 = epilogue skips the TMA store, 16 = epilogue skips the activation
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------
@@ -251,13 +247,6 @@ __device__ __forceinline__ void act16(float* f) {
 struct TileIter {
     int tw, th, img, nt;
     __device__ __forceinline__ void init(int t, const TcParams& p) {
-        if (p.gres) {   // N tile fastest: a CTA (grid % n_tiles == 0) never changes its weight tile
-            nt = t % p.n_tiles; t /= p.n_tiles;
-            tw = t % p.tiles_w; t /= p.tiles_w;
-            th = t % p.tiles_h;
-            img = t / p.tiles_h;
-            return;
-        }
         tw = t % p.tiles_w; t /= p.tiles_w;
         th = t % p.tiles_h; t /= p.tiles_h;
         img = t % p.N;
@@ -266,25 +255,19 @@ struct TileIter {
     __device__ __forceinline__ void step(const TcParams& p) {
         tw += p.step_tw; if (tw >= p.tiles_w) { tw -= p.tiles_w; ++th; }
         th += p.step_th; if (th >= p.tiles_h) { th -= p.tiles_h; ++img; }
-        img += p.step_img;
-        if (!p.gres) {
-            if (img >= p.N) { img -= p.N; ++nt; }
-            nt += p.step_nt;
-        }
+        img += p.step_img; if (img >= p.N) { img -= p.N; ++nt; }
+        nt += p.step_nt;
     }
     __device__ __forceinline__ void step2(const TcParams& p) {   // 2 * gridDim.x tiles ahead
         tw += p.step2_tw; if (tw >= p.tiles_w) { tw -= p.tiles_w; ++th; }
         th += p.step2_th; if (th >= p.tiles_h) { th -= p.tiles_h; ++img; }
-        img += p.step2_img;
-        if (!p.gres) {
-            if (img >= p.N) { img -= p.N; ++nt; }
-            nt += p.step2_nt;
-        }
+        img += p.step2_img; if (img >= p.N) { img -= p.N; ++nt; }
+        nt += p.step2_nt;
     }
     __device__ __forceinline__ void step1(const TcParams& p) {   // the next tile in raster order
         if (++tw >= p.tiles_w) { tw = 0; if (++th >= p.tiles_h) { th = 0; if (++img >= p.N) { img = 0; ++nt; } } }
     }
-    __device__ __forceinline__ bool valid(const TcParams& p) const { return p.gres ? img < p.N : nt < p.n_tiles; }
+    __device__ __forceinline__ bool valid(const TcParams& p) const { return nt < p.n_tiles; }
 };
 
 // Persistent, warp-specialised: each CTA loops over output tiles (tile = blockIdx.x + i*gridDim.x). The smem ring keeps
@@ -449,19 +432,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint32_t ph_c = 0, ph_o = 0;
                 TileIter ti;
                 ti.init(blockIdx.x, p);
-                const bool gres = p.gres != 0;
-                if (gres && ti.valid(p)) {
-                    // resident weights: all K blocks of this CTA's N tile, once, behind fullB[0] (static data: no dependency wait needed)
-                    if (p.debug & 2) mbar_arrive(fullB);
-                    else {
-                        mbar_expect_tx(fullB, (uint32_t)p.num_k * p.b_bytes);
-                        int tap = 0, cc = 0;
-                        for (int kb = 0; kb < p.num_k; ++kb) {
-                            tma_load_2d(b_base + (uint32_t)kb * p.b_bytes, &tmB, fullB, tap * Cin + cc * BK, ti.nt * p.BN);
-                            if (++cc == cchunks) { cc = 0; ++tap; }
-                        }
-                    }
-                }
                 pdl_wait();   // the input activations are written by the previous kernel
                 for (int tcount = 0; ti.valid(p); ti.step(p), ++tcount) {
                     const int img = ti.img;
@@ -474,12 +444,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         trace(tr, 0, 1, tcount, grp, tcnt);
                         const uint32_t full = fullA + 8u * stage;
                         if (p.debug & 2) mbar_arrive(full);
-                        else mbar_expect_tx(full, (gres ? p.a_tx : tx) * (uint32_t)G);
+                        else mbar_expect_tx(full, tx * (uint32_t)G);
                         for (int g = 0; g < G; ++g) {
                             const uint32_t slot = (uint32_t)(stage * G + g);
                             if (!(p.debug & 2)) {
                                 tma_load_4d(a_base + slot * p.a_bytes, &tmA, full, cc * BK, ow0 * cstride + s - pad, oh0 * cstride + r - pad, img);
-                                if (!gres) tma_load_2d(b_base + slot * p.b_bytes, &tmB, full, tap * Cin + cc * BK, n0 + img * p.w_img_rows);
+                                tma_load_2d(b_base + slot * p.b_bytes, &tmB, full, tap * Cin + cc * BK, n0 + img * p.w_img_rows);
                             }
                             if (++cc == cchunks) {
                                 cc = 0; ++tap;
@@ -718,8 +688,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint32_t phase = 0;
                 const int sbase = me * nstages;   // this issuer's sub-ring (0 when there is a single issuer)
                 const uint32_t a_step = a_bytes >> 4, b_step = b_bytes >> 4;
-                const bool gres = p.gres != 0;
-                if (gres && ti.valid(p)) mbar_wait(fullB, 0u);   // the CTA's resident weight tile has landed
                 for (int tcount = me; ti.valid(p); tcount += astep) {
                     const uint32_t d_tmem = tmem_acc + (uint32_t)(aidx * BN);
                     mbar_wait(tempty_bar + 8u * aidx, acc_phase ^ 1u);  // epilogue has drained this accumulator
@@ -732,7 +700,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tc_fence_after();
                         // one burst = G K-blocks; descriptor start address advances by 32 B (>>4 = 2) per UMMA_K = 16
                         uint32_t a_lo = umma_lo(a_base + (uint32_t)(stage * G) * a_bytes);
-                        uint32_t b_lo = umma_lo(b_base + (uint32_t)((gres ? grp : stage) * G) * b_bytes);
+                        uint32_t b_lo = umma_lo(b_base + (uint32_t)(stage * G) * b_bytes);
                         if (!no_mma) {
                             for (int g = 0; g < G; ++g) {
                                 tc_mma_bf16(d_tmem, umma_desc(desc_hi, a_lo), umma_desc(desc_hi, b_lo), idesc, (uint32_t)((grp | g) != 0));
@@ -907,11 +875,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const bool d_ok = dec && (m < TH * TW) && d_oh < p.Ho && d_ow < p.Wo;
             float* const d_y = dec ? p.dec_y + (size_t)img * (4 + p.dec_nc) * p.dec_A + p.dec_off + d_oh * p.Wo + d_ow : nullptr;
             const int chunks_per_pass = split ? chunks_per_unit : nchunks;
-            // The accumulator columns of a chunk are requested one chunk ahead (tcgen05.ld is asynchronous until tcgen05.wait::ld): the next
-            // chunk's TMEM read travels under this chunk's activation math, residual add and staging stores.
-            uint32_t v[16];
-            const bool no_pf = (p.debug & 128) != 0;   // A/B: request each chunk right before it is needed
-            if (!no_pf && cg < chunks_per_pass && cg < nchunks) tmem_ld16(trow + (uint32_t)(cg * 16), v);
             for (int ps = 0; ps < passes; ++ps) {
             if (ps > 0) {   // split staging: the previous unit's store must have read the buffer before it is overwritten
                 if (leader_warp) bulk_wait_read<0>();
@@ -919,34 +882,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             for (int ch = ps * chunks_per_pass + cg; ch < (ps + 1) * chunks_per_pass && ch < nchunks; ch += 2) {   // last unit may be partial (BN = 80)
                 const int c0 = ch * 16;
+                uint32_t v[16];
+                tmem_ld16(trow + (uint32_t)c0, v);
                 const float4* bs = reinterpret_cast<const float4*>(bias_s + n0 + c0);
                 const float4 b0 = bs[0], b1 = bs[1], b2 = bs[2], b3 = bs[3];
-                if (no_pf) tmem_ld16(trow + (uint32_t)c0, v);
                 tmem_ld_wait(v);
                 float f[16];
                 const float bb[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
-                // SiLU layers: f = h = (acc + bias) / 2 (the bias is stored halved); others: f = acc + bias
-                if (act == YSOD_ACT_SILU) {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) f[j] = fmaf(__uint_as_float(v[j]), 0.5f, bb[j]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + bb[j];
-                }
-                {   // v is consumed: request this thread's next chunk (same pass, else the first chunk of the next pass)
-                    int nx = ch + 2;
-                    bool more = nx < (ps + 1) * chunks_per_pass && nx < nchunks;
-                    if (!more && ps + 1 < passes) {
-                        nx = (ps + 1) * chunks_per_pass + cg;
-                        more = nx < (ps + 2) * chunks_per_pass && nx < nchunks;
-                    }
-                    if (more && !no_pf) tmem_ld16(trow + (uint32_t)(nx * 16), v);
-                }
                 if (act == YSOD_ACT_SILU) {
                     // x * sigmoid(x) = h + h * tanh(h) with h = x / 2: FFMA + MUFU + FFMA per element
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) f[j] = fmaf(f[j], tanh_approx(f[j]), f[j]);
+                    for (int j = 0; j < 16; ++j) {
+                        const float h = fmaf(__uint_as_float(v[j]), 0.5f, bb[j]);
+                        f[j] = fmaf(h, tanh_approx(h), h);
+                    }
                 } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + bb[j];
                     if (act == YSOD_ACT_GELU) act16<YSOD_ACT_GELU>(f);
                     else if (act == YSOD_ACT_RELU) act16<YSOD_ACT_RELU>(f);
                 }
@@ -1290,7 +1242,6 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
     bool halo = false;
     const int dbg = (mode >> 8) & 0xff;
     const bool no_duo = (mode & 0x10000) != 0;
-    const bool no_gres = (mode & 0x20000) != 0;
     const bool up2 = (mode & 0x40) != 0;
     const bool img_w = (mode & 0x80) != 0;
     const int split_exp = mode & 0x10;
@@ -1454,29 +1405,6 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
             p.a_slots = p.b_slots = rings * stages * G;
             ring_bytes = (size_t)p.a_slots * slot_bytes;
             nbar = 4 * p.a_slots;
-            // Resident weights (TcParams::gres): single-issuer deep-K layers whose [BN x K] weight tile fits beside >= 4 activation slots,
-            // shared (not per-image) weights, enough tiles that every CTA of an N-tile-aligned grid has work.
-            const uint32_t b_all = (uint32_t)p.num_k * p.b_bytes;
-            int sms_g = 148;
-            {
-                int dev_g = 0;
-                if (cudaGetDevice(&dev_g) == cudaSuccess) cudaDeviceGetAttribute(&sms_g, cudaDevAttrMultiProcessorCount, dev_g);
-            }
-            const long long total_g = (long long)N * p.tiles_h * p.tiles_w * p.n_tiles;
-            long long g_g = total_g < sms_g ? total_g : sms_g;
-            g_g -= g_g % p.n_tiles;
-            if (!no_gres && !img_w && p.issuers == 1 && p.num_k >= 3 && b_all + 4u * p.a_bytes <= budget && g_g >= p.n_tiles &&
-                g_g * 8 >= 7 * (total_g < sms_g ? total_g : sms_g)) {
-                int a_total = (int)((budget - b_all) / p.a_bytes);
-                if (a_total > 8) a_total = 8;
-                p.gres = 1;
-                p.kgroup = 1;
-                p.stages = p.a_stages = a_total;
-                p.a_slots = a_total;
-                p.b_stages = p.b_slots = p.num_k;
-                ring_bytes = (size_t)a_total * p.a_bytes + b_all;
-                nbar = 2 * p.a_slots + 2 * p.b_slots;
-            }
         }
     } else {
         p.a_tx = 18u * 10u * 2u * (uint32_t)p.BK;     // bytes landed per halo copy: 18 rows x 10 px x BK ch bf16 (22.5 KB / 11.25 KB)
@@ -1539,18 +1467,17 @@ int ysod_conv_tc_create_ex(ysod_conv_tc** handle, const void* x, int N, int H, i
         long long g = (long long)sms;   // one persistent CTA per SM
         const long long units = p.pair ? total / 2 : total;   // work items: tiles, or tile pairs
         if (g > units) g = units;
-        if (p.gres) g -= g % p.n_tiles;   // every CTA keeps one N tile: tile index = spatial * n_tiles + nt, stride a multiple of n_tiles
         c.grid = dim3((unsigned)g, 1, 1);
-        long long r = p.gres ? g / p.n_tiles : g;
+        long long r = g;
         p.step_tw = (int)(r % p.tiles_w); r /= p.tiles_w;
         p.step_th = (int)(r % p.tiles_h); r /= p.tiles_h;
-        p.step_img = p.gres ? (int)r : (int)(r % N);
-        p.step_nt = p.gres ? 0 : (int)(r / N);
-        r = p.gres ? 2 * g / p.n_tiles : 2 * g;
+        p.step_img = (int)(r % N);
+        p.step_nt = (int)(r / N);
+        r = 2 * g;
         p.step2_tw = (int)(r % p.tiles_w); r /= p.tiles_w;
         p.step2_th = (int)(r % p.tiles_h); r /= p.tiles_h;
-        p.step2_img = p.gres ? (int)r : (int)(r % N);
-        p.step2_nt = p.gres ? 0 : (int)(r / N);
+        p.step2_img = (int)(r % N);
+        p.step2_nt = (int)(r / N);
     }
 
     const CUtensorMapSwizzle swz = p.BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
@@ -1787,7 +1714,7 @@ int ysod_conv_tc_info(ysod_conv_tc* h, int* out8) {
     YSOD_CHECK_ARG(h && out8, "ysod_conv_tc_info: null");
     out8[0] = h->c.p.TH; out8[1] = h->c.p.TW; out8[2] = h->c.p.BN; out8[3] = h->c.p.BK; out8[4] = h->c.p.stages;
     out8[5] = (int)h->c.grid.x; out8[6] = h->c.halo ? (1000 + 100 * h->c.p.issuers + 10 * h->c.p.b_resident + h->c.p.n_tiles) : (100 * h->c.p.issuers + 10 * h->c.p.kgroup + h->c.p.n_tiles);
-    out8[6] += 10000 * h->c.p.pair + 20000 * h->c.p.duo + 40000 * h->c.p.gres;
+    out8[6] += 10000 * h->c.p.pair + 20000 * h->c.p.duo;
     out8[7] = (int)h->c.smem;
     return YSOD_OK;
 }

@@ -193,8 +193,6 @@ class Program:
                 mode |= _lib.CONV_NO_PAIR
             if no_duo or not self.m.conv_duo:
                 mode |= _lib.CONV_NO_DUO
-            if not self.m.conv_gres:
-                mode |= _lib.CONV_NO_GRES
             if os.environ.get("YSOD_CONV_DEBUG"):
                 mode |= int(os.environ["YSOD_CONV_DEBUG"]) << 8   # A/B switches of the conv kernel (debug bits, tc_conv.cu)
             if os.environ.get("YSOD_TRACE_OP", "") == str(len(self.ops)):
@@ -1093,7 +1091,6 @@ class B200DetectionModel:
         self.conv_pair = os.environ.get("YSOD_NO_PAIR", "0") != "1"   # A/B switch of the conv kernel's tile-pair plan (ysod.h YSOD_CONV_NO_PAIR)
         # pixel-duo plan for dense 32 -> 32 3x3 convs (ysod.h YSOD_CONV_NO_DUO): same products, different accumulation order than the 32-channel plan
         self.fuse_stem_gap = fuse_stem_gap and os.environ.get("YSOD_STEM_GAP", "1") != "0"   # stem kernel leaves the SE pooling partials (A/B switch)
-        self.conv_gres = os.environ.get("YSOD_NO_GRES", "0") != "1"   # resident-weight plan of the generic conv kernel (ysod.h YSOD_CONV_NO_GRES): A/B switch
         self.conv_duo = conv_duo and os.environ.get("YSOD_NO_DUO", "0") != "1"
         self.c2f_cat = os.environ.get("YSOD_C2F_CAT", "1") == "1"     # A/B switch: C2f.cv2 inside the last Bottleneck conv's launch (ysod_conv_tc_set_b2b_cat)
         self.attn_impl = attn_impl   # ysod_mha_core_ex impl: 0 = tcgen05 / TMEM attention core where covered, 1 = mma.sync kernels (A/B)

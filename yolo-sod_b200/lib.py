@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libysod.so")
+LIB_PATH = os.environ.get("YSOD_LIB_PATH") or os.path.join(_HERE, "libysod.so")   # (override: A/B builds of the same sources, tools/gpu_abso.sh)
 LIB_PATH_F16 = os.path.join(_HERE, "libysod_f16.so")   # the same sources built with -DYSOD_HALF=1 (IEEE fp16 storage, `half=True`)
 
 F32, BF16 = 0, 1
@@ -14,7 +14,6 @@ CONV_NO_SPLIT_STAGING = 0x10   # ysod.h YSOD_CONV_NO_SPLIT_STAGING
 CONV_NO_PAIR = 0x04       # ysod.h YSOD_CONV_NO_PAIR
 CONV_NO_STORE = 0x20      # ysod.h YSOD_CONV_NO_STORE
 CONV_NO_DUO = 0x10000     # ysod.h YSOD_CONV_NO_DUO
-CONV_NO_GRES = 0x20000    # ysod.h YSOD_CONV_NO_GRES
 STEM_INDIRECT = 0x10      # ysod.h YSOD_STEM_INDIRECT
 ACT = {"none": 0, "silu": 1, "gelu": 2, "relu": 3, "sigmoid": 4, "hsigmoid": 5}
 
