@@ -71,6 +71,11 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"((uint64_t)map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"((uint64_t)map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
 // ---- packed fp32 pairs (sm_100 add / mul / fma .f32x2: FADD2 / FMUL2 / FFMA2, two lanes per issue slot). Every row-wise stage of this
 // kernel is a long stream of independent fp32 operations issued by 2 warps per scheduler, so the instruction count is what bounds it.
 typedef unsigned long long p2;
@@ -182,7 +187,8 @@ __device__ int g_trace_on = 0;
 #define TR(k) do { if (tr_on && tile_i < 8) g_trace[tile_i * 24 + (k)] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(256, 1)
-swin64_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat16* __restrict__ x, int N, int H, int W, int xcs, const __nv_bfloat16* __restrict__ wb,
+swin64_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmX7, const __grid_constant__ CUtensorMap tmO7,
+                 const __nv_bfloat16* __restrict__ x, int N, int H, int W, int xcs, const __nv_bfloat16* __restrict__ wb,
                  const float* __restrict__ pf, __nv_bfloat16* __restrict__ out, int ocs, int nWh, int nWw) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = smem_u32(smem_raw);
@@ -210,6 +216,8 @@ swin64_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat16* _
         mbar_init(base + S_BAR + 8u, 1);
         mbar_init(base + S_BAR + 24u, 1);
         mbar_init(base + S_BAR + 32u, 1);
+        mbar_init(base + S_BAR + 40u, 1);
+        mbar_init(base + S_BAR + 48u, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -237,6 +245,11 @@ swin64_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat16* _
     // QK region, which is idle from the end of MLP linear 2 of the previous tile until this tile's in_proj epilogue.
     const uint32_t pbar = base + S_BAR + 24u + 8u * (uint32_t)grp;
     uint32_t pphase = 0;
+    // The identity rows (the block's input at the window's own 7 x 7 pixels) arrive by TMA in the V region once PV is done; the output tile is
+    // written over them row by row and leaves by TMA store (out-of-image tokens are clipped by the store, like window_reverse's crop).
+    const uint32_t ibar = base + S_BAR + 40u + 8u * (uint32_t)grp;
+    uint32_t iphase = 0;
+    constexpr uint32_t ID_BYTES = 49u * 128u, ID_STRIDE = 8192u;
     auto request_patches = [&](uint32_t prn) {
         if (prn < npairs) {
             const uint32_t qa = 2u * prn, qb = 2u * prn + 1u;
@@ -321,6 +334,7 @@ swin64_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat16* _
             }
         }
         layernorm_store(a1, r, x1);   // in place: a thread reads and writes its own row only (MMA padding rows 49..63 become zero rows)
+        if (r == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous tile's output store has read the V region (in_proj's epilogue rewrites it)
         TR(3);
         tc_fence_before();
         fence_async_smem();
@@ -419,7 +433,12 @@ swin64_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat16* _
         tc_fence_after();
         TR(7);
 
-        // ---- E. attention output (normalised) -> A1 -> out_proj
+        // ---- E. attention output (normalised) -> A1 -> out_proj. V is consumed: the identity rows of both windows take its place.
+        if (r == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ibar), "r"(ok_b ? 2u * ID_BYTES : ID_BYTES) : "memory");
+            tma_load_4d(vv, &tmX7, ibar, 0, w0_a, h0_a, n_a);
+            if (ok_b) tma_load_4d(vv + ID_STRIDE, &tmX7, ibar, 0, w0_b, h0_b, n_b);
+        }
         for_acc32<2>(trow, [&](int i, const uint32_t* v) {
             const p2 sc = pk2(inv[i], inv[i]);
 #pragma unroll
@@ -499,15 +518,6 @@ swin64_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat16* _
                        smem_desc(base + S_W2 + (uint32_t)(ks >> 2) * 8192u + (uint32_t)(ks & 3) * 32u, 16u, 1024u, 2u), ID_N64, (uint32_t)(ks > 0));
             tc_commit(bar);
         }
-        // the identity row travels while the last two GEMMs run
-        uint4 idv[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) idv[c] = make_uint4(0, 0, 0, 0);
-        if (in_img) {
-            const __nv_bfloat16* ip = x + (((size_t)on * H + oh) * W + ow) * xcs;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) idv[c] = __ldg(reinterpret_cast<const uint4*>(ip + c * 8));
-        }
         mbar_wait(bar, phase); phase ^= 1u;
         tc_fence_after();
         if (issuer_warp && elect_one()) request_patches(pr + gridDim.x * 2u);   // the hidden tile is consumed: the QK region takes the next tile's patches
@@ -536,17 +546,20 @@ swin64_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat16* _
         tc_fence_after();
         TR(15);
 
-        // ---- I. + bias -> SiLU (x * sigmoid(x) = h + h * tanh(h), h = x / 2) -> + identity -> the pixel's 128 B row in global memory
+        // ---- I. + bias -> SiLU (x * sigmoid(x) = h + h * tanh(h), h = x / 2) -> + identity (read from the thread's own row of the V region) -> bf16
+        //         into the same row -> one TMA store per window (7 x 7 x 64 box, clipped at the image border)
+        mbar_wait(ibar, iphase); iphase ^= 1u;
         {
-            __nv_bfloat16* op = out + (((size_t)on * H + oh) * W + ow) * ocs;
+            const uint32_t orow = vv + (uint32_t)wsel * ID_STRIDE;
             const p2 half2 = pk2(0.5f, 0.5f);
             for_acc32<2>(trow + 64u, [&](int i, const uint32_t* v) {
                 p2 f[16];
                 acc_bias32(v, prm_s + 4u * (uint32_t)(P_BPW + i * 32), f);
-                if (in_img) {
+                if (t < T) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
-                        const uint4 idw = idv[4 * i + c];
+                        const uint32_t addr = row128(orow, t, 4 * i + c);
+                        const uint4 idw = lds_v4(addr);
                         const uint32_t iw[4] = {idw.x, idw.y, idw.z, idw.w};
                         uint32_t ov[4];
 #pragma unroll
@@ -555,15 +568,24 @@ swin64_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __nv_bfloat16* _
                             const float2 hf = up2(hx);
                             ov[j] = pack_p2(add2(fma2(hx, pk2(tanh_approx(hf.x), tanh_approx(hf.y)), hx), unpack_p2(iw[j])));
                         }
-                        *reinterpret_cast<uint4*>(op + i * 32 + c * 8) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+                        st_shared_v4(addr, ov[0], ov[1], ov[2], ov[3]);
                     }
                 }
             });
+        }
+        tc_fence_before();   // this tile's TMEM reads are ordered before the barriers of the next tile's first MMA group
+        fence_async_smem();
+        group_barrier(grp);
+        if (r == 0) {
+            tma_store_4d(&tmO7, vv, 0, w0_a, h0_a, n_a);
+            if (ok_b) tma_store_4d(&tmO7, vv + ID_STRIDE, 0, w0_b, h0_b, n_b);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         TR(16);
         tc_fence_before();   // this tile's TMEM reads are ordered before the barriers of the next tile's first MMA group
     }
 
+    if (r == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the last output stores are complete before shared memory goes away
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
@@ -608,20 +630,24 @@ extern "C" int ysod_swin64_tc(const void* x, int N, int H, int W, int xcs, const
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) enc = (EncodeTiledFn)fp;
     }
     YSOD_CHECK_ARG(enc != nullptr, "ysod_swin64_tc: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
-    CUtensorMap tmX;
+    CUtensorMap tmX, tmX7, tmO7;
     {
-        cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-        cuuint64_t strides[3] = {(cuuint64_t)xcs * 2, (cuuint64_t)W * xcs * 2, (cuuint64_t)H * W * xcs * 2};
-        cuuint32_t box[4] = {64, 9, 9, 1}, es[4] = {1, 1, 1, 1};
-        const CUresult cr = enc(&tmX, YSOD_TMAP_16, 4, const_cast<void*>(x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (cr != CUDA_SUCCESS) {
-            ysod_set_error("ysod_swin64_tc: cuTensorMapEncodeTiled failed with %d (W %d H %d N %d xcs %d)", (int)cr, W, H, N, xcs);
-            return YSOD_ERR_CUDA;
+        const cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+        const cuuint32_t es[4] = {1, 1, 1, 1};
+        struct { CUtensorMap* m; const void* ptr; int cs; cuuint32_t side; } maps[3] = {{&tmX, x, xcs, 9}, {&tmX7, x, xcs, 7}, {&tmO7, out, ocs, 7}};
+        for (auto& mp : maps) {   // 9 x 9 input patches (conv halo), 7 x 7 identity windows, 7 x 7 output windows
+            const cuuint64_t strides[3] = {(cuuint64_t)mp.cs * 2, (cuuint64_t)W * mp.cs * 2, (cuuint64_t)H * W * mp.cs * 2};
+            const cuuint32_t box[4] = {64, mp.side, mp.side, 1};
+            const CUresult cr = enc(mp.m, YSOD_TMAP_16, 4, const_cast<void*>(mp.ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (cr != CUDA_SUCCESS) {
+                ysod_set_error("ysod_swin64_tc: cuTensorMapEncodeTiled failed with %d (W %d H %d N %d pixel stride %d)", (int)cr, W, H, N, mp.cs);
+                return YSOD_ERR_CUDA;
+            }
         }
     }
     YSOD_CUDA(cudaFuncSetAttribute(swin64_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    ysod_launch(swin64_tc_kernel, (unsigned)grid, 256, SMEM_BYTES, stream, tmX, (const __nv_bfloat16*)x, N, H, W, xcs, (const __nv_bfloat16*)wbf16, pf32,
+    ysod_launch(swin64_tc_kernel, (unsigned)grid, 256, SMEM_BYTES, stream, tmX, tmX7, tmO7, (const __nv_bfloat16*)x, N, H, W, xcs, (const __nv_bfloat16*)wbf16, pf32,
                 (__nv_bfloat16*)out, ocs, nWh, nWw);
     YSOD_LAUNCH_CHECK();
     return YSOD_OK;
