@@ -16,6 +16,12 @@ __device__ __forceinline__ uint32_t lop(uint32_t a, uint32_t b) { uint32_t d; as
 __device__ __forceinline__ uint32_t shl(uint32_t a) { uint32_t d; asm volatile("shl.b32 %0, %1, 16;" : "=r"(d) : "r"(a)); return d; }
 __device__ __forceinline__ uint32_t cvtpk(float a, float b) { uint32_t d; asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(a), "f"(b)); return d; }
 
+__device__ __forceinline__ uint32_t tanh_h2(uint32_t x) { uint32_t y; asm volatile("tanh.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x)); return y; }
+__device__ __forceinline__ uint32_t tanh_b2(uint32_t x) { uint32_t y; asm volatile("tanh.approx.bf16x2 %0, %1;" : "=r"(y) : "r"(x)); return y; }
+__device__ __forceinline__ uint32_t ex2_b2(uint32_t x) { uint32_t y; asm volatile("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(x)); return y; }
+__device__ __forceinline__ uint32_t ex2_h2(uint32_t x) { uint32_t y; asm volatile("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x)); return y; }
+__device__ __forceinline__ uint32_t cvth2(float a, float b) { uint32_t d; asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(a), "f"(b)); return d; }
+
 constexpr int ITERS = 512, CH = 8;
 
 template <int OP>
@@ -41,6 +47,11 @@ __global__ void k(long long* out, float* sink, float seed) {
             if (OP == 6) u[c] = lop(u[c], 0xffff0fffu + c);
             if (OP == 7) u[c] = shl(u[c]);
             if (OP == 8) u[c] = cvtpk(__uint_as_float(u[c]), f[c]);
+            if (OP == 9) u[c] = tanh_h2(u[c]);
+            if (OP == 10) u[c] = tanh_b2(u[c]);
+            if (OP == 11) u[c] = ex2_b2(u[c]);
+            if (OP == 12) u[c] = ex2_h2(u[c]);
+            if (OP == 13) u[c] = cvth2(__uint_as_float(u[c]), f[c]);
         }
     }
     const long long t1 = clock64();
@@ -81,6 +92,11 @@ int main() {
     run<6>("and.b32 (LOP3)", d_out, sink);
     run<7>("shl.b32 (SHF)", d_out, sink);
     run<8>("cvt.rn.bf16x2.f32 (F2FP)", d_out, sink);
+    run<9>("tanh.approx.f16x2", d_out, sink);
+    run<10>("tanh.approx.bf16x2", d_out, sink);
+    run<11>("ex2.approx.ftz.bf16x2", d_out, sink);
+    run<12>("ex2.approx.f16x2", d_out, sink);
+    run<13>("cvt.rn.f16x2.f32", d_out, sink);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
     return 0;

@@ -144,6 +144,14 @@ __device__ __forceinline__ float tanh_approx(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// fp32 pairs (sm_100 add / mul / fma .f32x2): two lanes per issue slot, each lane rounded like the scalar instruction (bit-identical results)
+typedef unsigned long long p2;
+__device__ __forceinline__ p2 pk2(float lo, float hi) { p2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ p2 pk2u(uint32_t lo, uint32_t hi) { p2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ float2 up2(p2 v) { float2 f; asm("mov.b64 {%0, %1}, %2;" : "=f"(f.x), "=f"(f.y) : "l"(v)); return f; }
+__device__ __forceinline__ p2 add2(p2 a, p2 b) { p2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ p2 mul2(p2 a, p2 b) { p2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ p2 fma2(p2 a, p2 b, p2 c) { p2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -230,6 +238,19 @@ __device__ __forceinline__ uint32_t umma_lo(uint32_t addr) { return ((addr >> 4)
 
 template <int ACT>
 __device__ __forceinline__ void act16(float* f) {
+    if (ACT == YSOD_ACT_GELU) {   // ysod_gelu_tanh (common.cuh) on fp32 pairs: same operations, same rounding
+        const p2 g3 = pk2(-3.2060743e-4f, -3.2060743e-4f), g2 = pk2(3.6819429e-2f, 3.6819429e-2f), g1 = pk2(7.9770428e-1f, 7.9770428e-1f), half2 = pk2(0.5f, 0.5f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const p2 x = pk2(f[2 * j], f[2 * j + 1]);
+            const p2 xx = mul2(x, x);
+            const float2 a = up2(mul2(x, fma2(fma2(g3, xx, g2), xx, g1)));
+            const p2 hx = mul2(half2, x);
+            const float2 o = up2(fma2(hx, pk2(tanh_approx(a.x), tanh_approx(a.y)), hx));
+            f[2 * j] = o.x; f[2 * j + 1] = o.y;
+        }
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
         if (ACT == YSOD_ACT_SILU) {  // x*sigmoid(x) = h + h*tanh(h), h = x/2: one MUFU op per element
@@ -891,10 +912,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const float bb[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
                 if (act == YSOD_ACT_SILU) {
                     // x * sigmoid(x) = h + h * tanh(h) with h = x / 2: FFMA + MUFU + FFMA per element
+                    const p2 half2 = pk2(0.5f, 0.5f);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float h = fmaf(__uint_as_float(v[j]), 0.5f, bb[j]);
-                        f[j] = fmaf(h, tanh_approx(h), h);
+                    for (int j = 0; j < 8; ++j) {   // on fp32 pairs: half the FMA issue slots of the epilogue
+                        const p2 h2 = fma2(pk2u(v[2 * j], v[2 * j + 1]), half2, pk2(bb[2 * j], bb[2 * j + 1]));
+                        const float2 h = up2(h2);
+                        const float2 o = up2(fma2(h2, pk2(tanh_approx(h.x), tanh_approx(h.y)), h2));
+                        f[2 * j] = o.x; f[2 * j + 1] = o.y;
                     }
                 } else {
 #pragma unroll
@@ -907,8 +931,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float2 r2 = ysod_unpack2(rw[j]);
-                        f[2 * j] += r2.x;
-                        f[2 * j + 1] += r2.y;
+                        const float2 o = up2(add2(pk2(f[2 * j], f[2 * j + 1]), pk2(r2.x, r2.y)));
+                        f[2 * j] = o.x; f[2 * j + 1] = o.y;
                     }
                     if (ch + 2 < nchunks) {
                         const __nv_bfloat16* rn = duo ? rp + p.rcs + (ch & 1) * 16 : rp + c0 + 32;   // duo: chunk ch + 2 = the same channels of the second pixel
@@ -1016,10 +1040,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         tmem_ld_wait(v2);
                         float g[16];
                         if (p.b2_act == YSOD_ACT_SILU) {
+                            const p2 half2 = pk2(0.5f, 0.5f);
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const float hh = 0.5f * (__uint_as_float(v2[j]) + b2_bias_s[ch2 * 16 + j]);
-                                g[j] = fmaf(hh, tanh_approx(hh), hh);
+                            for (int j = 0; j < 8; ++j) {
+                                const p2 h2 = mul2(half2, add2(pk2u(v2[2 * j], v2[2 * j + 1]), pk2(b2_bias_s[ch2 * 16 + 2 * j], b2_bias_s[ch2 * 16 + 2 * j + 1])));
+                                const float2 hh = up2(h2);
+                                const float2 o = up2(fma2(h2, pk2(tanh_approx(hh.x), tanh_approx(hh.y)), h2));
+                                g[2 * j] = o.x; g[2 * j + 1] = o.y;
                             }
                         } else {
 #pragma unroll
