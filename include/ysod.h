@@ -209,9 +209,11 @@ int ysod_mha_window_nhwc(const void* q, const void* k, const void* v, int ld, in
  * norm slots of pf32 are ignored (swin_fused.cu). */
 int ysod_swin64_fused(const void* x, int N, int H, int W, int xcs, const void* wbf16, const float* pf32, void* out, int ocs, int window,
                       int heads, void* stream);
-/* The same block (same blobs, same rounding points) with every contraction on tcgen05 / TMEM (swin_tc.cu): two windows per M = 128
- * tile, thread = token row = TMEM lane, in_proj / QK^T / PV / out_proj / MLP / pw as tcgen05.mma groups from shared-memory operands,
- * LayerNorm / softmax / GELU on tcgen05.ld registers. ysod_swin64_fused (mma.sync) stays as the A/B baseline. */
+/* The same block (same blobs, same rounding points) with every contraction on tcgen05 / TMEM (swin_tc.cu), the default: two windows per
+ * M = 128 tile, thread = token row = TMEM lane, in_proj / QK^T / PV / out_proj / MLP / pw as tcgen05.mma groups from shared-memory operands,
+ * LayerNorm / softmax / GELU / SiLU on tcgen05.ld registers as packed fp32 pairs (fma.rn.f32x2), the 9 x 9 input patches, the identity rows
+ * and the output tile moved by TMA (out-of-bounds fill = conv padding, store clipping = window_reverse's crop). x / out are 16 B aligned
+ * NHWC views (any pixel stride that is a multiple of 8). ysod_swin64_fused (mma.sync) stays as the A/B baseline. */
 int ysod_swin64_tc(const void* x, int N, int H, int W, int xcs, const void* wbf16, const float* pf32, void* out, int ocs, int window,
                    int heads, void* stream);
 /* profiling only: enable / disable the stage trace of the tcgen05 SwinBlock kernel and (host_out != NULL) read back the previous launch's
