@@ -367,6 +367,17 @@ def test_stem_mma(cout, src, W):
     err = (got - ref).abs()
     tol = 1.0 / 128
     assert bool((err <= tol * ref.abs() + tol * ref.abs().max() + 1e-5).all()), err.max().item()
+    # ysod_stem_mma_gap: the same output bit for bit, plus per-tile channel sums of the stored values (the SE block's pooling partials)
+    S = -(-(W // 2) // 64) * -(-(H // 2) // 4)
+    od2 = torch.full_like(od, 7.0)
+    ps = torch.full((N, S, cout), float("nan"), device="cuda")
+    lib.call("ysod_stem_mma_gap", lib.ptr(dev_img), fmt, N, H, W, lib.ptr(wd), lib.ptr(bd), cout, lib.ptr(od2), cout + 8, lib.ACT["silu"],
+             lib.ptr(ps), lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(od2, od), "the pooling variant changed the stem's output"
+    want = od[..., :cout].double().sum(dim=(1, 2)).cpu()
+    gsum = ps.double().sum(dim=1).cpu()
+    assert bool(torch.isfinite(ps).all()) and bool(((gsum - want).abs() <= 1e-4 * want.abs() + 1e-2).all()), (gsum - want).abs().max().item()
 
 
 MHA_CASES = [(5, 49, 2, 32), (3, 49, 4, 64), (2, 64, 2, 64), (2, 33, 1, 32), (2, 160, 8, 64), (1, 400, 2, 32), (6, 49, 4, 16), (2, 100, 4, 16),

@@ -43,7 +43,7 @@ __device__ __forceinline__ int koff(int k) {
 
 // SRC = 0: img is (N,3,H,W) fp32 in [0,1];  SRC = 1: img is (N,H,W,3) uint8 BGR in 0..255 (-> RGB, /255)
 template <int COUT, int SRC, bool VEC>
-__global__ void __launch_bounds__(256, COUT <= 32 ? 4 : 2)
+__global__ void __launch_bounds__(256, 2)
 stem_mma_kernel(const void* img_, const __nv_bfloat16* __restrict__ wk, const float* __restrict__ bias,
                 __nv_bfloat16* __restrict__ out, int H, int W, int Ho, int Wo, int ocs, int act, int indirect, float* __restrict__ psum) {
     ysod_pdl_sync();
@@ -53,92 +53,14 @@ stem_mma_kernel(const void* img_, const __nv_bfloat16* __restrict__ wk, const fl
     constexpr int NB = COUT / 8;
     __shared__ __align__(16) __nv_bfloat16 patch[3 * PLANE];
     __shared__ __align__(16) __nv_bfloat16 stage[TH * TW * (COUT + 8)];   // +8: keeps the 4-byte fragment stores conflict-free
+    // uint8 source: the 256 possible values of bf16(x / 255.0f) (the reference's `im / 255` then the 16-bit cast), built once per CTA
+    __shared__ __nv_bfloat16 lut[SRC == 1 ? 256 : 1];
+    if (SRC == 1) lut[threadIdx.x] = __float2bfloat16_rn((float)threadIdx.x / 255.0f);   // 256 threads; visible after the first barrier below
     const int n = blockIdx.z;
-    const int oh0 = blockIdx.y * TH, ow0 = blockIdx.x * TW;
-    const int ih0 = 2 * oh0 - 1, iw0 = 2 * ow0 - 1;
+    const int oh0 = blockIdx.y * TH;
+    const int ih0 = 2 * oh0 - 1;
     const int tid = threadIdx.x;
-
-    // ---- stage the input patch, converting to bf16 exactly like the reference's cast of the image tensor. Patch column j holds
-    //      image column 2*ow0 - 4 + j (so rows start 16-byte aligned); all loads of a thread are issued before any is used.
-    if (SRC == 0) {
-        const float* img = static_cast<const float*>(img_);
-        if (VEC) {
-            constexpr int NV = 3 * PH * 33;   // float4 pieces
-            float4 v[(NV + 255) / 256];
-#pragma unroll
-            for (int it = 0; it < (NV + 255) / 256; ++it) {
-                const int i = tid + it * 256;
-                v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i < NV) {
-                    const int cr = i / 33, j = i - cr * 33;
-                    const int c = cr / PH, r = cr - c * PH;
-                    const int ih = ih0 + r, iw = 2 * ow0 - 4 + 4 * j;
-                    if (ih >= 0 && ih < H && iw >= 0 && iw < W) v[it] = __ldg(reinterpret_cast<const float4*>(img + (((size_t)n * 3 + c) * H + ih) * W + iw));
-                }
-            }
-#pragma unroll
-            for (int it = 0; it < (NV + 255) / 256; ++it) {
-                const int i = tid + it * 256;
-                if (i < NV) {
-                    const int cr = i / 33, j = i - cr * 33;
-                    __nv_bfloat162* d = reinterpret_cast<__nv_bfloat162*>(&patch[cr * PWP + 4 * j]);
-                    d[0] = __floats2bfloat162_rn(v[it].x, v[it].y);
-                    d[1] = __floats2bfloat162_rn(v[it].z, v[it].w);
-                }
-            }
-        } else {
-            for (int i = tid; i < 3 * PH * PW; i += 256) {
-                const int c = i / (PH * PW);
-                const int rem = i - c * (PH * PW);
-                const int r = rem / PW, q = rem - r * PW;
-                const int ih = ih0 + r, iw = iw0 + q;
-                float v = 0.f;
-                if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(img + (((size_t)n * 3 + c) * H + ih) * W + iw);
-                patch[c * PLANE + r * PWP + q + 3] = __float2bfloat16_rn(v);
-            }
-        }
-    } else {
-        const uint8_t* img = static_cast<const uint8_t*>(img_);
-        if (VEC) {
-            constexpr int NV = PH * 99;   // 4-byte words: 132 pixels x 3 bytes per patch row
-            uint32_t v[(NV + 255) / 256];
-#pragma unroll
-            for (int it = 0; it < (NV + 255) / 256; ++it) {
-                const int i = tid + it * 256;
-                v[it] = 0u;
-                if (i < NV) {
-                    const int r = i / 99, j = i - r * 99;
-                    const int ih = ih0 + r;
-                    const int b0 = (2 * ow0 - 4) * 3 + 4 * j;          // byte offset inside the image row
-                    if (ih >= 0 && ih < H && b0 >= 0 && b0 + 3 < W * 3) v[it] = __ldg(reinterpret_cast<const uint32_t*>(img + ((size_t)n * H + ih) * W * 3 + b0));
-                }
-            }
-#pragma unroll
-            for (int it = 0; it < (NV + 255) / 256; ++it) {
-                const int i = tid + it * 256;
-                if (i < NV) {
-                    const int r = i / 99, j = i - r * 99;
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int bi = 4 * j + e;
-                        const int q = bi / 3, cs = bi - q * 3;           // cs = channel in the BGR source
-                        const float f = (float)((v[it] >> (8 * e)) & 0xffu) / 255.0f;
-                        patch[(2 - cs) * PLANE + r * PWP + q] = __float2bfloat16_rn(f);
-                    }
-                }
-            }
-        } else {
-            for (int i = tid; i < PH * PW * 3; i += 256) {
-                const int r = i / (PW * 3);
-                const int rem = i - r * (PW * 3);
-                const int q = rem / 3, cs = rem - q * 3;
-                const int ih = ih0 + r, iw = iw0 + q;
-                float v = 0.f;
-                if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = (float)__ldg(img + (((size_t)n * H + ih) * W + iw) * 3 + cs) / 255.0f;
-                patch[(2 - cs) * PLANE + r * PWP + q + 3] = __float2bfloat16_rn(v);
-            }
-        }
-    }
+    const int ntx = (Wo + TW - 1) / TW;   // the CTA walks the ntx tiles of its 4-row strip; the next tile's input is in flight while this one is computed
 
     // ---- weights: B fragments of the [COUT][32] bf16 matrix, held in registers for the whole CTA
     const int lane = tid & 31, warp = tid >> 5;
@@ -165,76 +87,192 @@ stem_mma_kernel(const void* img_, const __nv_bfloat16* __restrict__ wk, const fl
     float bv[NB][2];
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) { bv[nb][0] = __ldg(bias + nb * 8 + 2 * t); bv[nb][1] = __ldg(bias + nb * 8 + 2 * t + 1); }
-    __syncthreads();
 
-    const unsigned short* ps = reinterpret_cast<const unsigned short*>(patch);
-    // 16 m-tiles (16 consecutive output columns of one output row each); warp w takes m-tiles 2w, 2w+1
+    // ---- input patch of a tile: the VEC paths hold it in registers between the request (issued one tile ahead) and the conversion to
+    //      bf16 in shared memory, exactly like the reference's cast of the image tensor. Patch column j holds image column 2*ow0 - 4 + j
+    //      (so rows start 16-byte aligned).
+    constexpr int NV0 = 3 * PH * 33, NV1 = PH * 99;             // float4 pieces (fp32 planes) / 4-byte words (uint8 BGR rows: 132 pixels x 3 bytes)
+    constexpr int NIT = ((SRC == 0 ? NV0 : NV1) + 255) / 256;
+    float4 vf[SRC == 0 ? NIT : 1];
+    uint32_t vu[SRC == 1 ? NIT : 1];
+    auto request = [&](int ow0) {
+        if (SRC == 0) {
+            const float* img = static_cast<const float*>(img_);
 #pragma unroll
-    for (int mi = 0; mi < 2; ++mi) {
-        const int mt = warp * 2 + mi;
-        const int row = mt >> 2, col0 = (mt & 3) * 16;
-        const int base0 = (2 * row) * PWP + 2 * (col0 + g) + 3;    // pixel g of the m-tile (patch column 3 = image column 2*ow0-1)
-        const int base1 = base0 + 16;                               // pixel g + 8
-        float acc[NB][4];
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb) { acc[nb][0] = bv[nb][0]; acc[nb][1] = bv[nb][1]; acc[nb][2] = bv[nb][0]; acc[nb][3] = bv[nb][1]; }
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-            uint32_t a[4];
-            a[0] = (uint32_t)ps[base0 + ko[ks][0]] | ((uint32_t)ps[base0 + ko[ks][1]] << 16);
-            a[1] = (uint32_t)ps[base1 + ko[ks][0]] | ((uint32_t)ps[base1 + ko[ks][1]] << 16);
-            a[2] = (uint32_t)ps[base0 + ko[ks][2]] | ((uint32_t)ps[base0 + ko[ks][3]] << 16);
-            a[3] = (uint32_t)ps[base1 + ko[ks][2]] | ((uint32_t)ps[base1 + ko[ks][3]] << 16);
-#pragma unroll
-            for (int nb = 0; nb < NB; ++nb) mma_bf16_16816(acc[nb], a, bf[nb][ks][0], bf[nb][ks][1]);
-        }
-        // activation -> bf16 -> staging tile [pixel][COUT + 8]
-        const int p0 = row * TW + col0 + g;
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb) {
-            float v0 = acc[nb][0], v1 = acc[nb][1], v2 = acc[nb][2], v3 = acc[nb][3];
-            if (act == YSOD_ACT_SILU) {   // x * sigmoid(x) = h + h * tanh(h), h = x / 2 (same form as the tcgen05 conv epilogue)
-                v0 = silu_tanh(v0); v1 = silu_tanh(v1); v2 = silu_tanh(v2); v3 = silu_tanh(v3);
+            for (int it = 0; it < NIT; ++it) {
+                const int i = tid + it * 256;
+                vf[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (i < NV0) {
+                    const int cr = i / 33, j = i - cr * 33;
+                    const int c = cr / PH, r = cr - c * PH;
+                    const int ih = ih0 + r, iw = 2 * ow0 - 4 + 4 * j;
+                    if (ih >= 0 && ih < H && iw >= 0 && iw < W) vf[it] = __ldg(reinterpret_cast<const float4*>(img + (((size_t)n * 3 + c) * H + ih) * W + iw));
+                }
             }
-            *reinterpret_cast<__nv_bfloat162*>(&stage[(size_t)p0 * (COUT + 8) + nb * 8 + 2 * t]) = __floats2bfloat162_rn(v0, v1);
-            *reinterpret_cast<__nv_bfloat162*>(&stage[(size_t)(p0 + 8) * (COUT + 8) + nb * 8 + 2 * t]) = __floats2bfloat162_rn(v2, v3);
-        }
-    }
-    __syncthreads();
-    // ---- optional: this tile's per-channel sums of the stored (16-bit) values = partial sums of the global average pool that the
-    //      SE block after the stem starts with (smallobj_modules.py SE_Block: avg_pool), so the map is not read again for them.
-    //      psum[n][tile][COUT], tile = blockIdx.y * gridDim.x + blockIdx.x; fixed summation order.
-    if (psum != nullptr) {
-        constexpr int PG = 256 / COUT;          // pixel groups
-        constexpr int PPG = TH * TW / PG;       // pixels per group
-        float* part = reinterpret_cast<float*>(patch);   // the patch is dead (all m-tiles done): [PG][COUT] floats
-        const int c = tid % COUT, pg = tid / COUT;
-        float a = 0.f;
-#pragma unroll 8
-        for (int i = 0; i < PPG; ++i) {
-            const int pix = pg * PPG + i;
-            const int r = pix / TW, q = pix - r * TW;
-            if (oh0 + r < Ho && ow0 + q < Wo) a += __bfloat162float(stage[(size_t)pix * (COUT + 8) + c]);
-        }
-        part[pg * COUT + c] = a;
-        __syncthreads();
-        if (tid < COUT) {
-            float t2 = 0.f;
+        } else {
+            const uint8_t* img = static_cast<const uint8_t*>(img_);
 #pragma unroll
-            for (int g2 = 0; g2 < PG; ++g2) t2 += part[g2 * COUT + tid];
-            psum[((size_t)n * (gridDim.x * gridDim.y) + blockIdx.y * gridDim.x + blockIdx.x) * COUT + tid] = t2;
+            for (int it = 0; it < NIT; ++it) {
+                const int i = tid + it * 256;
+                vu[it] = 0u;
+                if (i < NV1) {
+                    const int r = i / 99, j = i - r * 99;
+                    const int ih = ih0 + r;
+                    const int b0 = (2 * ow0 - 4) * 3 + 4 * j;          // byte offset inside the image row
+                    if (ih >= 0 && ih < H && b0 >= 0 && b0 + 3 < W * 3) vu[it] = __ldg(reinterpret_cast<const uint32_t*>(img + ((size_t)n * H + ih) * W * 3 + b0));
+                }
+            }
         }
-    }
-    // ---- coalesced write-out: 16-byte pieces, consecutive threads -> consecutive channels then pixels
-    constexpr int PIECES = COUT / 8;
-    for (int i = tid; i < TH * TW * PIECES; i += 256) {
-        const int pix = i / PIECES, pc = i - pix * PIECES;
-        const int r = pix / TW, q = pix - r * TW;
-        const int oh = oh0 + r, ow = ow0 + q;
-        if (oh < Ho && ow < Wo) {
-            const uint4 v = *reinterpret_cast<const uint4*>(&stage[(size_t)pix * (COUT + 8) + pc * 8]);
-            *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + oh) * Wo + ow) * ocs + pc * 8) = v;
+    };
+    auto commit = [&]() {
+        if (SRC == 0) {
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int i = tid + it * 256;
+                if (i < NV0) {
+                    const int cr = i / 33, j = i - cr * 33;
+                    __nv_bfloat162* d = reinterpret_cast<__nv_bfloat162*>(&patch[cr * PWP + 4 * j]);
+                    d[0] = __floats2bfloat162_rn(vf[it].x, vf[it].y);
+                    d[1] = __floats2bfloat162_rn(vf[it].z, vf[it].w);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int it = 0; it < NIT; ++it) {
+                const int i = tid + it * 256;
+                if (i < NV1) {
+                    const int r = i / 99, j = i - r * 99;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int bi = 4 * j + e;
+                        const int q = bi / 3, cs = bi - q * 3;           // cs = channel in the BGR source
+                        patch[(2 - cs) * PLANE + r * PWP + q] = lut[(vu[it] >> (8 * e)) & 0xffu];
+                    }
+                }
+            }
         }
+    };
+    if (VEC) request(0);
+    if (SRC == 1) __syncthreads();   // the table is complete before the first conversion
+
+    for (int tx = 0; tx < ntx; ++tx) {
+        const int ow0 = tx * TW, iw0 = 2 * ow0 - 1;
+        if (VEC) {
+            commit();
+        } else if (SRC == 0) {
+            const float* img = static_cast<const float*>(img_);
+            for (int i = tid; i < 3 * PH * PW; i += 256) {
+                const int c = i / (PH * PW);
+                const int rem = i - c * (PH * PW);
+                const int r = rem / PW, q = rem - r * PW;
+                const int ih = ih0 + r, iw = iw0 + q;
+                float v = 0.f;
+                if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(img + (((size_t)n * 3 + c) * H + ih) * W + iw);
+                patch[c * PLANE + r * PWP + q + 3] = __float2bfloat16_rn(v);
+            }
+        } else {
+            const uint8_t* img = static_cast<const uint8_t*>(img_);
+            for (int i = tid; i < PH * PW * 3; i += 256) {
+                const int r = i / (PW * 3);
+                const int rem = i - r * (PW * 3);
+                const int q = rem / 3, cs = rem - q * 3;
+                const int ih = ih0 + r, iw = iw0 + q;
+                unsigned int v = 0u;
+                if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(img + (((size_t)n * H + ih) * W + iw) * 3 + cs);
+                patch[(2 - cs) * PLANE + r * PWP + q + 3] = lut[v];
+            }
+        }
+        __syncthreads();
+        if (VEC && tx + 1 < ntx) request(ow0 + TW);   // travels under this tile's MMAs and stores
+        float gs[NB][2];
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) gs[nb][0] = gs[nb][1] = 0.f;
+
+        const unsigned short* ps = reinterpret_cast<const unsigned short*>(patch);
+        // 16 m-tiles (16 consecutive output columns of one output row each); warp w takes m-tiles 2w, 2w+1
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi) {
+            const int mt = warp * 2 + mi;
+            const int row = mt >> 2, col0 = (mt & 3) * 16;
+            const int base0 = (2 * row) * PWP + 2 * (col0 + g) + 3;    // pixel g of the m-tile (patch column 3 = image column 2*ow0-1)
+            const int base1 = base0 + 16;                               // pixel g + 8
+            float acc[NB][4];
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) { acc[nb][0] = bv[nb][0]; acc[nb][1] = bv[nb][1]; acc[nb][2] = bv[nb][0]; acc[nb][3] = bv[nb][1]; }
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                uint32_t a[4];
+                a[0] = (uint32_t)ps[base0 + ko[ks][0]] | ((uint32_t)ps[base0 + ko[ks][1]] << 16);
+                a[1] = (uint32_t)ps[base1 + ko[ks][0]] | ((uint32_t)ps[base1 + ko[ks][1]] << 16);
+                a[2] = (uint32_t)ps[base0 + ko[ks][2]] | ((uint32_t)ps[base0 + ko[ks][3]] << 16);
+                a[3] = (uint32_t)ps[base1 + ko[ks][2]] | ((uint32_t)ps[base1 + ko[ks][3]] << 16);
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) mma_bf16_16816(acc[nb], a, bf[nb][ks][0], bf[nb][ks][1]);
+            }
+            // activation -> bf16 -> staging tile [pixel][COUT + 8]
+            const int p0 = row * TW + col0 + g;
+            const bool ok0 = oh0 + row < Ho && ow0 + col0 + g < Wo, ok1 = oh0 + row < Ho && ow0 + col0 + g + 8 < Wo;
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) {
+                float v0 = acc[nb][0], v1 = acc[nb][1], v2 = acc[nb][2], v3 = acc[nb][3];
+                if (act == YSOD_ACT_SILU) {   // x * sigmoid(x) = h + h * tanh(h), h = x / 2 (same form as the tcgen05 conv epilogue)
+                    v0 = silu_tanh(v0); v1 = silu_tanh(v1); v2 = silu_tanh(v2); v3 = silu_tanh(v3);
+                }
+                const __nv_bfloat162 q0 = __floats2bfloat162_rn(v0, v1), q1 = __floats2bfloat162_rn(v2, v3);
+                *reinterpret_cast<__nv_bfloat162*>(&stage[(size_t)p0 * (COUT + 8) + nb * 8 + 2 * t]) = q0;
+                *reinterpret_cast<__nv_bfloat162*>(&stage[(size_t)(p0 + 8) * (COUT + 8) + nb * 8 + 2 * t]) = q1;
+                if (psum != nullptr) {   // pooling partials of the STORED values (this thread: channels nb*8 + 2t, +1 of two pixels)
+                    const float2 f0 = __bfloat1622float2(q0), f1 = __bfloat1622float2(q1);
+                    gs[nb][0] += (ok0 ? f0.x : 0.f) + (ok1 ? f1.x : 0.f);
+                    gs[nb][1] += (ok0 ? f0.y : 0.f) + (ok1 ? f1.y : 0.f);
+                }
+            }
+        }
+        if (psum != nullptr) {
+            // sum over the 8 pixel lanes (g) of the warp, then lanes 0..3 (t) hold the warp's sums of channels nb*8 + 2t, +1
+            float* part = reinterpret_cast<float*>(patch) ;   // [8 warps][COUT], written after the barrier below (the patch is dead then)
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    float a = gs[nb][e];
+                    a += __shfl_xor_sync(0xffffffffu, a, 4);
+                    a += __shfl_xor_sync(0xffffffffu, a, 8);
+                    a += __shfl_xor_sync(0xffffffffu, a, 16);
+                    gs[nb][e] = a;
+                }
+            __syncthreads();   // every warp is done reading the patch
+            if (g == 0) {
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) { part[warp * COUT + nb * 8 + 2 * t] = gs[nb][0]; part[warp * COUT + nb * 8 + 2 * t + 1] = gs[nb][1]; }
+            }
+        }
+        __syncthreads();
+        // ---- optional: this tile's per-channel sums of the stored (16-bit) values = partial sums of the global average pool that the
+        //      SE block after the stem starts with (smallobj_modules.py SE_Block: avg_pool), so the map is not read again for them.
+        //      psum[n][tile][COUT], tile = blockIdx.y * ntx + tx; fixed summation order (lanes, then warps 0..7).
+        if (psum != nullptr) {
+            const float* part = reinterpret_cast<const float*>(patch);
+            if (tid < COUT) {
+                float t2 = 0.f;
+#pragma unroll
+                for (int w2 = 0; w2 < 8; ++w2) t2 += part[w2 * COUT + tid];
+                psum[((size_t)n * (ntx * gridDim.y) + blockIdx.y * ntx + tx) * COUT + tid] = t2;
+            }
+            __syncthreads();   // `part` aliases the patch the next tile's conversion overwrites
+        }
+        // ---- coalesced write-out: 16-byte pieces, consecutive threads -> consecutive channels then pixels
+        constexpr int PIECES = COUT / 8;
+        for (int i = tid; i < TH * TW * PIECES; i += 256) {
+            const int pix = i / PIECES, pc = i - pix * PIECES;
+            const int r = pix / TW, q = pix - r * TW;
+            const int oh = oh0 + r, ow = ow0 + q;
+            if (oh < Ho && ow < Wo) {
+                const uint4 v = *reinterpret_cast<const uint4*>(&stage[(size_t)pix * (COUT + 8) + pc * 8]);
+                *reinterpret_cast<uint4*>(out + (((size_t)n * Ho + oh) * Wo + ow) * ocs + pc * 8) = v;
+            }
+        }
+        // (the next tile's staging writes come after its own __syncthreads, which every thread reaches only after these reads)
     }
 }
 
@@ -267,7 +305,7 @@ static int stem_mma_impl(const void* img, int src_fmt, int N, int H, int W, cons
     YSOD_CHECK_ARG(H % 2 == 0 && W % 2 == 0 && ocs % 8 == 0 && ((uintptr_t)out % 16) == 0, "ysod_stem_mma: bad geometry / alignment");
     YSOD_CHECK_ARG(act == YSOD_ACT_SILU || act == YSOD_ACT_NONE, "ysod_stem_mma: activation %d unsupported", act);
     const int Ho = H / 2, Wo = W / 2;
-    dim3 grid(ysod_cdiv(Wo, TW), ysod_cdiv(Ho, TH), N);
+    dim3 grid(1, ysod_cdiv(Ho, TH), N);   // a CTA walks the tiles of its 4-row strip
     const __nv_bfloat16* w = (const __nv_bfloat16*)wk;
     __nv_bfloat16* o = (__nv_bfloat16*)out;
     // aligned 16 B / 4 B row loads (an indirect image pointer must be 16 B aligned: the binder checks it)
