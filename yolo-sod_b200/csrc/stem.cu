@@ -91,10 +91,10 @@ stem_mma_kernel(const void* img_, const __nv_bfloat16* __restrict__ wk, const fl
     // ---- input patch of a tile: the VEC paths hold it in registers between the request (issued one tile ahead) and the conversion to
     //      bf16 in shared memory, exactly like the reference's cast of the image tensor. Patch column j holds image column 2*ow0 - 4 + j
     //      (so rows start 16-byte aligned).
-    constexpr int NV0 = 3 * PH * 33, NV1 = PH * 99;             // float4 pieces (fp32 planes) / 4-byte words (uint8 BGR rows: 132 pixels x 3 bytes)
+    constexpr int NV0 = 3 * PH * 33, NV1 = PH * 33;             // float4 pieces (fp32 planes) / 12-byte items = 4 BGR pixels (uint8 rows: 132 pixels)
     constexpr int NIT = ((SRC == 0 ? NV0 : NV1) + 255) / 256;
     float4 vf[SRC == 0 ? NIT : 1];
-    uint32_t vu[SRC == 1 ? NIT : 1];
+    uint32_t vu[SRC == 1 ? NIT : 1][3];
     auto request = [&](int ow0) {
         if (SRC == 0) {
             const float* img = static_cast<const float*>(img_);
@@ -114,12 +114,17 @@ stem_mma_kernel(const void* img_, const __nv_bfloat16* __restrict__ wk, const fl
 #pragma unroll
             for (int it = 0; it < NIT; ++it) {
                 const int i = tid + it * 256;
-                vu[it] = 0u;
+                vu[it][0] = vu[it][1] = vu[it][2] = 0u;
                 if (i < NV1) {
-                    const int r = i / 99, j = i - r * 99;
+                    const int r = i / 33, j = i - r * 33;
                     const int ih = ih0 + r;
-                    const int b0 = (2 * ow0 - 4) * 3 + 4 * j;          // byte offset inside the image row
-                    if (ih >= 0 && ih < H && b0 >= 0 && b0 + 3 < W * 3) vu[it] = __ldg(reinterpret_cast<const uint32_t*>(img + ((size_t)n * H + ih) * W * 3 + b0));
+                    const int b0 = (2 * ow0 - 4) * 3 + 12 * j;         // byte offset inside the image row (a multiple of 4: W % 4 == 0)
+                    if (ih >= 0 && ih < H) {
+                        const uint32_t* rowp = reinterpret_cast<const uint32_t*>(img + ((size_t)n * H + ih) * W * 3);
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+                            if (b0 + 4 * k >= 0 && b0 + 4 * k + 3 < W * 3) vu[it][k] = __ldg(rowp + (b0 >> 2) + k);
+                    }
                 }
             }
         }
@@ -141,12 +146,18 @@ stem_mma_kernel(const void* img_, const __nv_bfloat16* __restrict__ wk, const fl
             for (int it = 0; it < NIT; ++it) {
                 const int i = tid + it * 256;
                 if (i < NV1) {
-                    const int r = i / 99, j = i - r * 99;
+                    const int r = i / 33, j = i - r * 33;
+                    // 12 bytes = B0 G0 R0 B1 G1 R1 B2 G2 R2 B3 G3 R3 -> four consecutive patch columns of each RGB plane (8 B stores)
+                    const unsigned short* lt = reinterpret_cast<const unsigned short*>(lut);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int bi = 4 * j + e;
-                        const int q = bi / 3, cs = bi - q * 3;           // cs = channel in the BGR source
-                        patch[(2 - cs) * PLANE + r * PWP + q] = lut[(vu[it] >> (8 * e)) & 0xffu];
+                    for (int cs = 0; cs < 3; ++cs) {
+                        uint32_t e[4];
+#pragma unroll
+                        for (int px = 0; px < 4; ++px) {
+                            const int bi = 3 * px + cs;
+                            e[px] = lt[(vu[it][bi >> 2] >> (8 * (bi & 3))) & 0xffu];
+                        }
+                        *reinterpret_cast<uint2*>(&patch[(2 - cs) * PLANE + r * PWP + 4 * j]) = make_uint2(e[0] | (e[1] << 16), e[2] | (e[3] << 16));
                     }
                 }
             }
