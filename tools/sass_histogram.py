@@ -1,7 +1,7 @@
 """SASS opcode evidence for the built libraries (no GPU needed): per kernel, how many tensor-core / TMA / TMEM instructions it contains.
     python tools/sass_histogram.py [lib ...] > profiles/r02_sass_opcodes.txt
 UTCHMMA = tcgen05.mma, UTMALDG / UTMASTG = TMA tensor load / store, LDTM = tcgen05.ld (TMEM -> registers), UTCBAR = tcgen05.commit,
-HMMA = legacy mma.sync, LDSM = ldmatrix, SYNCS = mbarrier ops, UBLKPF / CCTL.. = prefetches."""
+HMMA = legacy mma.sync, FFMA2 / FADD2 / FMUL2 = packed fp32 pairs (fma / add / mul .f32x2), LDSM = ldmatrix, SYNCS = mbarrier ops, UBLKPF / CCTL.. = prefetches."""
 import collections
 import os
 import re
@@ -10,7 +10,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 libs = sys.argv[1:] or [os.path.join(ROOT, "yolo-sod_b200", n) for n in ("libysod.so", "libysod_f16.so")]
-KEYS = ["UTCHMMA", "UTMALDG", "UTMASTG", "UTMAPF", "LDTM", "UTCBAR", "UTCATOMSWS", "HMMA", "LDSM", "SYNCS", "MUFU", "LDG", "STG", "LDS", "STS", "SHFL", "ELECT", "ACQBULK", "UTMACMDFLUSH"]
+KEYS = ["UTCHMMA", "UTMALDG", "UTMASTG", "UTMAPF", "LDTM", "UTCBAR", "UTCATOMSWS", "HMMA", "LDSM", "SYNCS", "MUFU", "LDG", "STG", "LDS", "STS", "SHFL", "ELECT", "ACQBULK", "UTMACMDFLUSH", "FFMA2", "FADD2", "FMUL2"]
 for lib in libs:
     out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
     per = collections.OrderedDict()
