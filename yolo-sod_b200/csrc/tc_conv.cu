@@ -13,13 +13,15 @@
 //     shifted patch directly in the canonical K-major 128B/64B-swizzled UMMA layout (row = pixel, 128/64 B of
 //     channels); the conv zero padding is TMA out-of-bounds fill; stride-2 convs use TMA element strides {1,2,2,1}.
 //     No im2col buffer ever exists in HBM.
-//   * warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + tcgen05.mma issuer (one lane),
-//     warps 2..5 = epilogue: tcgen05.ld -> +bias -> act -> (+residual) -> bf16/fp32 -> 16 B stores into a channel
-//     slice of the consumer's NHWC buffer (this is what removes Concat/chunk copies).
-//   * smem ring of `stages` {A,B} tiles with full/empty mbarriers; accumulator (128 lanes x BN fp32 columns) in TMEM.
+//   * ONE persistent CTA of 608 threads per SM: warps 0..15 = epilogue (two groups of 8 warps, one per tile parity: tcgen05.ld ->
+//     +bias -> act (fp32 pairs, fma.rn.f32x2) -> (+residual) -> bf16/fp32 -> swizzled staging tile -> TMA tensor store into a channel
+//     slice of the consumer's NHWC buffer: this is what removes Concat/chunk copies), warp 16 = TMA producer (one elected lane),
+//     warps 17 / 18 = tcgen05.mma issuers (one elected lane each; the second one only for single-burst tiles), warp 17 also owns TMEM.
+//   * smem rings of {A,B} tiles (generic mode) or separate halo-copy / weight-tap rings (3x3 stride-1 mode) with full/empty mbarriers;
+//     four accumulators (128 lanes x BN fp32 columns each) in TMEM, so the epilogue of tile i overlaps the main loop of tile i+1.
 //
-// BN/BK/stage count are runtime values (instruction + smem descriptors are built from them), so one kernel
-// serves every layer shape; two CTAs per SM co-reside for the common configs to hide prologue/epilogue.
+// BN/BK/stage counts are runtime values (instruction + smem descriptors are built from them), so one kernel serves every layer shape;
+// the plan (ysod_conv_tc_create) sizes the rings against the 227 KB of one SM.
 #include "common.cuh"
 #include <cuda.h>
 #include <new>
