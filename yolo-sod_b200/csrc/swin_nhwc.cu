@@ -60,35 +60,55 @@ dwconv3_ln_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int 
 #pragma unroll
         for (int v = 0; v < V; ++v) {
             const int c0 = (v * 32 + lane) * 8;
+            // all 18 input pieces (3 rows x 6 pixels x 8 channels, 16 B each) are requested before the first one is used; the taps are then
+            // accumulated in (r, s) order on fp32 pairs (fma.rn.f32x2: same rounding per lane, half the issue slots)
+            uint4 xr[3][SW + 2];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int ih = ph + r - 1;
+#pragma unroll
+                for (int q = 0; q < SW + 2; ++q) {
+                    const int iw = w0 + q - 1;
+                    xr[r][q] = make_uint4(0u, 0u, 0u, 0u);
+                    if (ih >= 0 && ih < H && iw >= 0 && iw < W) xr[r][q] = *reinterpret_cast<const uint4*>(x + ((n * H + ih) * W + iw) * xcs + c0);
+                }
+            }
+            unsigned long long acc2[SW][4];
+#pragma unroll
+            for (int j = 0; j < SW; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc2[j][e] = 0ull;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                if (ph + r - 1 < 0 || ph + r - 1 >= H) continue;   // (zero rows add nothing; skipping keeps the products identical)
+                unsigned long long xin2[SW + 2][4];
+#pragma unroll
+                for (int q = 0; q < SW + 2; ++q) {
+                    const uint32_t wv[4] = {xr[r][q].x, xr[r][q].y, xr[r][q].z, xr[r][q].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 f = ysod_unpack2(wv[e]);
+                        asm("mov.b64 %0, {%1, %2};" : "=l"(xin2[q][e]) : "f"(f.x), "f"(f.y));
+                    }
+                }
+#pragma unroll
+                for (int s = 0; s < 3; ++s) {
+                    unsigned long long wt2[4];
+                    const float* wp = sw + (r * 3 + s) * C + c0;
+                    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(wt2[0]), "=l"(wt2[1]) : "r"((uint32_t)__cvta_generic_to_shared(wp)) : "memory");
+                    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(wt2[2]), "=l"(wt2[3]) : "r"((uint32_t)__cvta_generic_to_shared(wp + 4)) : "memory");
+#pragma unroll
+                    for (int j = 0; j < SW; ++j)
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[j][e]) : "l"(xin2[j + s][e]), "l"(wt2[e]));
+                }
+            }
             float acc[SW][8];
 #pragma unroll
             for (int j = 0; j < SW; ++j)
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc[j][e] = 0.f;
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const int ih = ph + r - 1;
-                if (ih < 0 || ih >= H) continue;
-                float xin[SW + 2][8];
-#pragma unroll
-                for (int q = 0; q < SW + 2; ++q) {
-                    const int iw = w0 + q - 1;
-                    if (iw >= 0 && iw < W) ysod_vec8<__nv_bfloat16>::load(x + ((n * H + ih) * W + iw) * xcs + c0, xin[q]);
-                    else
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) xin[q][e] = 0.f;
-                }
-#pragma unroll
-                for (int s = 0; s < 3; ++s) {
-                    const float4 wa = *reinterpret_cast<const float4*>(sw + (r * 3 + s) * C + c0);
-                    const float4 wb = *reinterpret_cast<const float4*>(sw + (r * 3 + s) * C + c0 + 4);
-                    const float wt[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-#pragma unroll
-                    for (int j = 0; j < SW; ++j)
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) acc[j][e] = fmaf(xin[j + s][e], wt[e], acc[j][e]);
-                }
-            }
+                for (int e = 0; e < 4; ++e) asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[j][2 * e]), "=f"(acc[j][2 * e + 1]) : "l"(acc2[j][e]));
             // V == 1: the lane holds the pixel's whole share; V == 2 keeps the first half in registers until the second is done
             if (V == 1) {
                 float su[SW], sq[SW], mean[SW], rstd[SW];
