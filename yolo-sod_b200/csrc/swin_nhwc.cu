@@ -212,22 +212,34 @@ mha_window_nhwc_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16*
         rowpix[tid] = rp;
     }
     __syncthreads();
-    for (int i = tid; i < 64 * (D / 8); i += 128) {
-        const int r = i / (D / 8), pc = i - r * (D / 8);
-        const int rp = rowpix[r];
-        uint4 qv = make_uint4(0, 0, 0, 0), kv = qv, vv = qv;
-        if (rp >= 0) {
-            const size_t off = (size_t)rp * ld + h * D + pc * 8;
-            qv = *reinterpret_cast<const uint4*>(q + off);
-            kv = *reinterpret_cast<const uint4*>(k + off);
-            vv = *reinterpret_cast<const uint4*>(v + off);
-        } else if (rp == -1) {   // a zero-padded window token: LayerNorm(0) = beta -> constant key / value rows
-            kv = *reinterpret_cast<const uint4*>(kpad + h * D + pc * 8);
-            vv = *reinterpret_cast<const uint4*>(vpad + h * D + pc * 8);
+    {
+        // every piece of the window's q / k / v rows is requested before the first shared-memory store (one latency, not NIT of them)
+        constexpr int NIT = 64 * (D / 8) / 128;
+        uint4 qv[NIT], kv[NIT], vv[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int i = tid + it * 128;
+            const int r = i / (D / 8), pc = i - r * (D / 8);
+            const int rp = rowpix[r];
+            qv[it] = make_uint4(0, 0, 0, 0); kv[it] = qv[it]; vv[it] = qv[it];
+            if (rp >= 0) {
+                const size_t off = (size_t)rp * ld + h * D + pc * 8;
+                qv[it] = *reinterpret_cast<const uint4*>(q + off);
+                kv[it] = *reinterpret_cast<const uint4*>(k + off);
+                vv[it] = *reinterpret_cast<const uint4*>(v + off);
+            } else if (rp == -1) {   // a zero-padded window token: LayerNorm(0) = beta -> constant key / value rows
+                kv[it] = *reinterpret_cast<const uint4*>(kpad + h * D + pc * 8);
+                vv[it] = *reinterpret_cast<const uint4*>(vpad + h * D + pc * 8);
+            }
         }
-        *reinterpret_cast<uint4*>(&Qs[r * LDQ + pc * 8]) = qv;
-        *reinterpret_cast<uint4*>(&Ks[r * LDQ + pc * 8]) = kv;
-        *reinterpret_cast<uint4*>(&Vs[r * LDQ + pc * 8]) = vv;
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int i = tid + it * 128;
+            const int r = i / (D / 8), pc = i - r * (D / 8);
+            *reinterpret_cast<uint4*>(&Qs[r * LDQ + pc * 8]) = qv[it];
+            *reinterpret_cast<uint4*>(&Ks[r * LDQ + pc * 8]) = kv[it];
+            *reinterpret_cast<uint4*>(&Vs[r * LDQ + pc * 8]) = vv[it];
+        }
     }
     __syncthreads();
     const int row0 = warp * 16 + g;
