@@ -247,12 +247,38 @@ mha_flash_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __res
     const __nv_bfloat16* qb = q + (size_t)b * bsq + h * D;
     const __nv_bfloat16* kb = k + (size_t)b * bsk + h * D;
     const __nv_bfloat16* vb = v + (size_t)b * bsv + h * D;
-    for (int i = tid; i < 64 * (D / 8); i += 128) {
-        const int r = i / (D / 8), pc = i - r * (D / 8);
-        uint4 qv = make_uint4(0, 0, 0, 0);
-        if (q0 + r < L) qv = *reinterpret_cast<const uint4*>(qb + (size_t)(q0 + r) * ldq + pc * 8);
-        *reinterpret_cast<uint4*>(&Qs[r * LDQ + pc * 8]) = qv;
+    constexpr int NIT = 64 * (D / 8) / 128;   // 16 B pieces of a 64-row tile per thread
+    {
+        uint4 qv[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int i = tid + it * 128;
+            const int r = i / (D / 8), pc = i - r * (D / 8);
+            qv[it] = make_uint4(0, 0, 0, 0);
+            if (q0 + r < L) qv[it] = *reinterpret_cast<const uint4*>(qb + (size_t)(q0 + r) * ldq + pc * 8);
+        }
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int i = tid + it * 128;
+            const int r = i / (D / 8), pc = i - r * (D / 8);
+            *reinterpret_cast<uint4*>(&Qs[r * LDQ + pc * 8]) = qv[it];
+        }
     }
+    // the K / V rows of a 64-key block are requested one block ahead: they travel under the previous block's MMAs and softmax
+    uint4 kvr[NIT], vvr[NIT];
+    auto request_kv = [&](int k0) {
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int i = tid + it * 128;
+            const int r = i / (D / 8), pc = i - r * (D / 8);
+            kvr[it] = make_uint4(0, 0, 0, 0); vvr[it] = kvr[it];
+            if (k0 + r < L) {
+                kvr[it] = *reinterpret_cast<const uint4*>(kb + (size_t)(k0 + r) * ldk + pc * 8);
+                vvr[it] = *reinterpret_cast<const uint4*>(vb + (size_t)(k0 + r) * ldv + pc * 8);
+            }
+        }
+    };
+    request_kv(0);
     __syncthreads();
     const int row0 = warp * 16 + g;
     uint32_t qf[D / 16][4];
@@ -269,19 +295,17 @@ mha_flash_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __res
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
     for (int k0 = 0; k0 < L; k0 += 64) {
         __syncthreads();   // previous block's K / V^T fully consumed
-        for (int i = tid; i < 64 * (D / 8); i += 128) {
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int i = tid + it * 128;
             const int r = i / (D / 8), pc = i - r * (D / 8);
-            uint4 kv = make_uint4(0, 0, 0, 0), vv = kv;
-            if (k0 + r < L) {
-                kv = *reinterpret_cast<const uint4*>(kb + (size_t)(k0 + r) * ldk + pc * 8);
-                vv = *reinterpret_cast<const uint4*>(vb + (size_t)(k0 + r) * ldv + pc * 8);
-            }
-            *reinterpret_cast<uint4*>(&Ks[r * LDQ + pc * 8]) = kv;
-            const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vv);
+            *reinterpret_cast<uint4*>(&Ks[r * LDQ + pc * 8]) = kvr[it];
+            const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vvr[it]);
 #pragma unroll
             for (int e = 0; e < 8; ++e) Vt[(pc * 8 + e) * LDV + r] = ve[e];
         }
         __syncthreads();
+        if (k0 + 64 < L) request_kv(k0 + 64);
         float s[8][4];
 #pragma unroll
         for (int nb = 0; nb < 8; ++nb) {
