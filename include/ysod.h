@@ -213,7 +213,8 @@ int ysod_swin64_fused(const void* x, int N, int H, int W, int xcs, const void* w
  * M = 128 tile, thread = token row = TMEM lane, in_proj / QK^T / PV / out_proj / MLP / pw as tcgen05.mma groups from shared-memory operands,
  * LayerNorm / softmax / GELU / SiLU on tcgen05.ld registers as packed fp32 pairs (fma.rn.f32x2), the 9 x 9 input patches, the identity rows
  * and the output tile moved by TMA (out-of-bounds fill = conv padding, store clipping = window_reverse's crop). x / out are 16 B aligned
- * NHWC views (any pixel stride that is a multiple of 8). ysod_swin64_fused (mma.sync) stays as the A/B baseline. */
+ * NHWC views (any pixel stride that is a multiple of 8). The K and V thirds of the in_proj bias (pf32[192..320)) must be zero: the caller
+ * drops the key bias (softmax-invariant) and folds the value bias into out_proj's (bo += Wo bv). ysod_swin64_fused (mma.sync) stays as the A/B baseline. */
 int ysod_swin64_tc(const void* x, int N, int H, int W, int xcs, const void* wbf16, const float* pf32, void* out, int ocs, int window,
                    int heads, void* stream);
 /* profiling only: enable / disable the stage trace of the tcgen05 SwinBlock kernel and (host_out != NULL) read back the previous launch's

@@ -22,7 +22,9 @@ def test_swin64_tc_equals_mma_sync(shape, xcs_extra):
     # dw[9][64] | wqkv[192][64] | wo[64][64] | w1[128][64] | w2[64][128] | wpw[64][64]
     wb = torch.cat([torch.randn(576, generator=g) / 3, torch.randn(192 * 64, generator=g) / 8, torch.randn(64 * 64, generator=g) / 8,
                     torch.randn(128 * 64, generator=g) / 8, torch.randn(64 * 128, generator=g) / 11, torch.randn(64 * 64, generator=g) / 8]).bfloat16().cuda()
-    pf = (torch.randn(768, generator=g) * 0.1).cuda()
+    pf = torch.randn(768, generator=g) * 0.1
+    pf[192:320] = 0.0   # K / V thirds of the in_proj bias: folded away by the caller (ysod.h ysod_swin64_tc), not read by the tcgen05 kernel
+    pf = pf.cuda()
     outs = []
     for name in ("ysod_swin64_fused", "ysod_swin64_tc"):
         ob = torch.full((N, H, W, cs), 7.0, dtype=torch.bfloat16, device="cuda")

@@ -15,7 +15,9 @@ g = torch.Generator().manual_seed(7)
 x = torch.randn(N, H, W, 64, generator=g).bfloat16().cuda()
 wb = torch.cat([torch.randn(576, generator=g) / 3, torch.randn(192 * 64, generator=g) / 8, torch.randn(64 * 64, generator=g) / 8,
                 torch.randn(128 * 64, generator=g) / 8, torch.randn(64 * 128, generator=g) / 11, torch.randn(64 * 64, generator=g) / 8]).bfloat16().cuda()
-pf = (torch.randn(768, generator=g) * 0.1).cuda()
+pf = torch.randn(768, generator=g) * 0.1
+pf[192:320] = 0.0
+pf = pf.cuda()
 o = torch.empty_like(x)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for name in ("ysod_swin64_fused", "ysod_swin64_tc"):

@@ -354,7 +354,12 @@ swin64_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         //         log2(e) / sqrt(d): caller.)
         for_acc32<6>(trow, [&](int i, const uint32_t* v) {
             p2 f[16];
-            acc_bias32(v, prm_s + 4u * (uint32_t)(P_BQKV + i * 32), f);
+            if (i < 2) {
+                acc_bias32(v, prm_s + 4u * (uint32_t)(P_BQKV + i * 32), f);
+            } else {   // K / V carry no bias here: a key bias is softmax-invariant, the value bias is folded into out_proj's by the caller
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = pk2u(v[2 * j], v[2 * j + 1]);
+            }
             const int sel = i >> 1, hh = i & 1;
             const uint32_t tile = (sel == 0 ? qk : sel == 1 ? qk + 16384u : vv) + (uint32_t)hh * 8192u;
 #pragma unroll
@@ -606,7 +611,10 @@ extern "C" int ysod_swin64_tc_trace(int enable, long long* host_out) {
 }
 
 // Same contract as ysod_swin64_fused (swin_fused.cu): x / out NHWC 16-bit views with 64 channels, the caller pre-folds the LayerNorm
-// affine parts into in_proj / mlp.0 and log2(e) / sqrt(head_dim) into the Q rows; wbf16 / pf32 are the same blobs.
+// affine parts into in_proj / mlp.0 and log2(e) / sqrt(head_dim) into the Q rows; wbf16 / pf32 are the same blobs. In addition this kernel
+// does not read the K and V thirds of the in_proj bias (pf32[192..320)): the caller zeroes them -- a bias added to every key shifts all scores
+// of a query by the same amount (softmax-invariant), a bias added to every value passes through the attention average and belongs to
+// out_proj's bias (bo += Wo bv).
 extern "C" int ysod_swin64_tc(const void* x, int N, int H, int W, int xcs, const void* wbf16, const float* pf32, void* out, int ocs,
                               int window, int heads, cudaStream_t stream) {
     YSOD_CHECK_ARG(x && wbf16 && pf32 && out, "ysod_swin64_tc: null pointer");

@@ -365,11 +365,16 @@ class Program:
             bi = torch.cat([bi[:64] * qs, bi[64:]])
             bm1 = bm1 + W1 @ be2
             W1 = W1 * g2.view(1, -1)
+            # the key bias shifts every score of a query equally (softmax-invariant); the value bias passes through the attention average
+            # (rows of softmax sum to 1) and lands in out_proj's bias: neither is added per token (ysod.h ysod_swin64_tc)
+            Wo, bo = sd[f"{A}.attn.out_proj.weight"].float(), sd[f"{A}.attn.out_proj.bias"].float()
+            bo = bo + Wo @ bi[128:]
+            bi = torch.cat([bi[:64], torch.zeros(128)])
             wb = torch.cat([dww.view(64, 3, 3).permute(1, 2, 0).reshape(-1), Wi.reshape(-1),
                             sd[f"{A}.attn.out_proj.weight"].float().reshape(-1), W1.reshape(-1),
                             sd[f"{A}.mlp.2.weight"].float().reshape(-1), pw.reshape(-1)])
             pf = torch.cat([torch.ones(64), torch.zeros(64), bi,
-                            sd[f"{A}.attn.out_proj.bias"].float(), torch.ones(64), torch.zeros(64),
+                            bo, torch.ones(64), torch.zeros(64),
                             bm1, sd[f"{A}.mlp.2.bias"].float(),
                             b - sd[f"{P}.bn.running_mean"].float() * sc])
             assert wb.numel() == 37440 and pf.numel() == 768
