@@ -13,7 +13,7 @@
 // (bf16 in, fp32 accumulate) with the accumulator -> A-fragment register re-packing trick, LayerNorm / softmax row
 // reductions are quad shuffles.
 // This is the mma.sync version (round 1), kept as the A/B baseline of swin_tc.cu: the tcgen05 / TMEM / TMA kernel there (two windows per
-// M = 128 tile, row-wise stages on fp32 pairs) runs the same block in 333 us against 467 us for this one at B = 32; round 1's
+// M = 128 tile, row-wise stages on fp32 pairs) runs the same block in 322 us against 467 us for this one at B = 32; round 1's
 // guess that K = 32..128 per GEMM and M = 49 tokens per window make tcgen05 the wrong shape did not survive the measurement.
 // Zero-padded tokens (pixels beyond H/W) take part in attention unmasked, exactly as in the reference; only the MMA padding
 // rows 49..63 are masked as keys.
