@@ -33,6 +33,21 @@ def test_library_exports_every_declared_symbol():
     assert lib.load().ysod_storage_dtype() == 1 and lib.load(half=True).ysod_storage_dtype() == 2
 
 
+def test_binding_prototypes_have_the_header_arity():
+    """Every ctypes prototype in lib.py passes as many arguments as include/ysod.h declares (catches a drifted binding before a GPU run)."""
+    header = re.sub(r"/\*.*?\*/", " ", open(os.path.join(ROOT, "include", "ysod.h")).read(), flags=re.S)
+    decls = dict(re.findall(r"\b(ysod_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S))
+    decls.pop("ysod_conv_tc", None)
+    checked = 0
+    for name, (res, args) in lib.PROTOTYPES.items():
+        assert name in decls, name
+        params = decls[name].strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(args), f"{name}: header declares {n} parameters, lib.py passes {len(args)}"
+        checked += 1
+    assert checked >= 30
+
+
 def test_error_reporting_without_compute():
     _built()
     so = lib.load()
